@@ -1,0 +1,218 @@
+/*
+ * laud_b200.h - C ABI of the B200-native LAUDNet dynamic-operator hot path.
+ *
+ * One shared library (liblaud_b200.so, sm_100a) exports everything below.
+ * All pointers are DEVICE pointers unless marked `host`; activations are
+ * fp16 NHWC ("channels last"); masks are uint8 0/1; index lists int32; all
+ * reductions that feed a gating decision accumulate in fp32 in a fixed order.
+ * Every entry point enqueues work on `stream` (a cudaStream_t passed as
+ * void*), performs no host synchronisation and no allocation (workspaces are
+ * caller-provided), returns 0 on success or a negative LAUD_E_* code, and
+ * leaves a thread-local message for laud_last_error().
+ *
+ * The reference (LeapLabTHU/LAUDNet) is pure Python and has no FFI; each entry
+ * point names the reference interface it replaces (paths relative to the
+ * reference checkout, imagenet_classification/models/...).  The Python
+ * binding a maintainer would add is shown in INTEGRATION.md.
+ */
+#ifndef LAUD_B200_H_
+#define LAUD_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LAUD_ABI_VERSION 1
+
+enum {
+  LAUD_OK = 0,
+  LAUD_E_BADARG = -1,      /* shape / alignment / unsupported combination */
+  LAUD_E_CUDA = -2,        /* a CUDA runtime call failed (message has the cudaError string) */
+  LAUD_E_UNSUPPORTED = -3  /* valid in the reference, not implemented here (raises, never falls back) */
+};
+
+/* which implementation of the gather-GEMM convolution to run */
+enum {
+  LAUD_CONV_AUTO = 0,   /* product path: tcgen05/TMEM kernel */
+  LAUD_CONV_UMMA = 1,   /* tcgen05.mma + TMEM accumulators, swizzled smem staging */
+  LAUD_CONV_HMMA = 2,   /* legacy warp-level tensor-core kernel (cross-check / bring-up) */
+  LAUD_CONV_NAIVE = 3   /* one thread per output, fp32 (self-test only) */
+};
+
+/* relu_mode of laud_conv_desc */
+enum {
+  LAUD_RELU_NONE = 0,
+  LAUD_RELU_ALL = 1,
+  LAUD_RELU_WHERE_GATE0 = 2 /* relu only where out_mask == 0 (downsample branch of a spatially skipped block) */
+};
+
+#define LAUD_GAP_SPLITS 8        /* row splits of the deterministic two-phase global average pool */
+#define LAUD_PREBIAS_CLASSES 16  /* border classes of a 3x3/pad-1 conv: 4 row patterns x 4 col patterns */
+
+int laud_abi_version(void);
+const char* laud_last_error(void);
+/* number of kernels this library has launched in this process (all streams) */
+unsigned long long laud_launch_count(void);
+
+/* ---------------------------------------------------------------------------
+ * (a1) channel masker.  Replaces Masker_channel_MLP.forward, eval branch
+ * (models/utils.py:113-131): GAP -> [Linear -> ReLU ->] Linear -> keep>=drop.
+ *   x        fp16 [B, HW, C] (C % 8 == 0)
+ *   layers   2: w1[hidden,C] b1[hidden] w2[2G,hidden] b2[2G]   (fp32)
+ *            1: w1[2G,C]     b1[2G]     (w2,b2 NULL, hidden ignored)
+ *   partial_ws  fp32 [B, LAUD_GAP_SPLITS, C] scratch
+ *   pooled_out  fp32 [B, C]      (nullable)  the GAP values
+ *   logits_out  fp32 [B, 2G]     (nullable)  first G = keep, last G = drop
+ *   mask_out    u8   [B, G]
+ *   idx_out     i32  [B, G]: ascending ACTIVE group ids in [0,cnt), then the
+ *                             ascending INACTIVE ids in [cnt,G)
+ *   cnt_out     i32  [B]
+ *   total_out   i32  [1]   += sum_b cnt[b]  (caller zeroes it; feeds rho_c)
+ * ------------------------------------------------------------------------- */
+int laud_masker_channel_mlp(const void* x, int B, int HW, int C, int layers,
+                            const float* w1, const float* b1, int hidden,
+                            const float* w2, const float* b2, int G,
+                            float* partial_ws, float* pooled_out, float* logits_out,
+                            uint8_t* mask_out, int32_t* idx_out, int32_t* cnt_out,
+                            int32_t* total_out, void* stream);
+
+/* Decision + compaction only, from caller-provided pooled features [B,C]
+ * (used by Masker_channel_conv_linear, models/utils.py:150-169, whose pooled
+ * input is the GAP of a conv-BN-ReLU branch). Same outputs as above. */
+int laud_masker_channel_from_pooled(const float* pooled, int B, int C, int layers,
+                                    const float* w1, const float* b1, int hidden,
+                                    const float* w2, const float* b2, int G,
+                                    float* logits_out, uint8_t* mask_out, int32_t* idx_out,
+                                    int32_t* cnt_out, int32_t* total_out, void* stream);
+
+/* Deterministic global average pool of fp16 [B,HW,ldx] (first C channels) -> fp32 [B,C]. */
+int laud_global_avg_pool(const void* x, int B, int HW, int C, int ldx,
+                         float* partial_ws, float* pooled_out, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * (a2) spatial / layer masker.  Replaces Masker_spatial.forward, eval branch
+ * (models/utils.py:47-65): adaptive_avg_pool2d(x, S) [skipped if S >= H]
+ * -> 1x1 conv C->2g (+bias) -> keep>=drop.   S == 1 is the layer gate.
+ *   x fp16 [B,H,W,C];  w fp32 [2g,C];  bias fp32 [2g]
+ *   logits_out fp32 [B,2g,S,S] (nullable);  mask_out u8 [B,g,S,S]
+ *   total_out  i32 [1] += number of ones
+ * ------------------------------------------------------------------------- */
+int laud_masker_spatial(const void* x, int B, int H, int W, int C,
+                        const float* w, const float* bias, int g, int S,
+                        float* logits_out, uint8_t* mask_out, int32_t* total_out, void* stream);
+
+/* (a4) ExpandMask.forward (models/utils.py:74-89): zero-insert upsample by
+ * `stride`, then OR over a (2*padding+1)^2 window and over all g groups.
+ *   mask u8 [B,g,H,W] -> out u8 [B,g,H*stride,W*stride]; total_out += ones. */
+int laud_expand_mask(const uint8_t* mask, int B, int g, int H, int W, int stride, int padding,
+                     uint8_t* out, int32_t* total_out, void* stream);
+
+/* F.interpolate(mode='nearest') of a mask (laud_resnet.py:106): src = floor(dst*S/H). */
+int laud_resize_mask_nearest(const uint8_t* mask, int B, int g, int S, int H_out,
+                             uint8_t* out, void* stream);
+
+/* Ordered compaction of a gate: rows_out[0..n) = ascending flat indices i with
+ * gate[i] != 0 (any group), n -> count_out[0].  gate u8 [N] (g==1) or [B,g,HW]
+ * (a row is active if any of its g groups is).  Deterministic (single pass,
+ * decoupled look-back free: one CTA per 2048 items + ordered prefix). */
+int laud_compact_rows(const uint8_t* gate, int B, int g, int HW,
+                      int32_t* rows_out, int32_t* count_out, int32_t* block_ws, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * (a5-a7) the mask-conditioned convolution: implicit-GEMM conv (1x1 or 3x3)
+ * + folded BatchNorm + mask + residual + ReLU, with per-sample channel
+ * gathers and row (pixel / sample) gathers.  Replaces the
+ * conv -> apply_channel_mask -> bn -> relu / conv -> bn -> apply_spatial_mask
+ * -> += identity -> relu chains of Bottleneck.forward (laud_resnet.py:115-144).
+ *
+ * GEMM view: D[m, n] = sum_k A[m, k] * Wt[n, k]
+ *   m = output pixel (b, oy, ox), n = output channel, k = (tap, in-channel).
+ * Channel gathers (per sample b, granularity `gran` consecutive channels):
+ *   k side: x holds only the ACTIVE input channels of sample b, compacted to
+ *           the front (x[b,p,j], j < k_cnt[b]*k_gran); compact channel j is
+ *           weight in-channel k_idx[b, j/gran]*gran + j%gran.
+ *   n side: y receives only the ACTIVE output channels, compacted the same way.
+ * Row gathers: sample_idx/sample_cnt restrict the batch to a device-side list
+ *   of samples (layer skip); row_idx/row_cnt restrict to a device-side list of
+ *   output pixels, flat index b*H_out*W_out + oy*W_out + ox (spatial skip).
+ *   Rows not listed are NOT written (in-place residual semantics).
+ * Epilogue, for real output channel o (compact j):
+ *   v = acc + pre_bias[b, cls(oy,ox), j]          (H1 constants; optional)
+ *   v = v * scale[o] + shift[o]                   (folded BN; optional)
+ *   v = v * out_mask[b, o / (C_out/mask_groups), oy, ox]   (optional, u8)
+ *   v = v + residual[b, oy, ox, o]                (optional, fp16)
+ *   v = relu(v) per relu_mode;  y = fp16(v)
+ *   compact channels [n_count, round_up(n_count, n_pad_align)) := 0  (n_pad_align > 0)
+ * ------------------------------------------------------------------------- */
+typedef struct laud_conv_desc {
+  const void* x;  int32_t ldx;          /* fp16 [B,H_in,W_in,ldx] */
+  const void* w;                        /* fp16 [C_out, ksize*ksize, C_in] */
+  void* y;        int32_t ldy;          /* fp16 [B,H_out,W_out,ldy] */
+  int32_t B, H_in, W_in, C_in, H_out, W_out, C_out;
+  int32_t ksize, stride, pad;
+  const float* scale; const float* shift;      /* [C_out] */
+  int32_t relu_mode;
+  const void* residual; int32_t ldr;           /* fp16 [B,H_out,W_out,ldr] */
+  const int32_t* k_idx; const int32_t* k_cnt; int32_t k_ld; int32_t k_gran;
+  const int32_t* n_idx; const int32_t* n_cnt; int32_t n_ld; int32_t n_gran;
+  const float* pre_bias; int32_t pre_bias_classes; int32_t pre_bias_ld; /* fp32 [B,classes,pre_bias_ld] */
+  const uint8_t* out_mask; int32_t mask_groups;  /* u8 [B,mask_groups,H_out,W_out] */
+  const int32_t* sample_idx; const int32_t* sample_cnt;
+  const int32_t* row_idx; const int32_t* row_cnt;
+  int32_t n_pad_align;      /* 0 | 8 | 16: zero-pad each sample's compact output channels to this multiple */
+  float* gap_partial;       /* optional fused GAP of the OUTPUT: fp32 [B, gap_tiles, C_out] partial sums */
+  int32_t gap_tiles;
+} laud_conv_desc;
+
+int laud_conv_forward(const laud_conv_desc* desc /* host */, int impl, void* stream);
+
+/* H1 constants of channel-skipping with mask-before-BN (laud_resnet.py:115-118,
+ * 123-126): a masked channel k of conv1's (conv2's) output is the constant
+ * c_k = relu(shift_k) after BN+ReLU.  For every sample this computes
+ *   pre_bias2[b, cls, j] = sum_{taps valid in border class cls} sum_{k masked}
+ *                          relu(shift1[k]) * w2[o_j, tap, k]    (active o_j, compact j)
+ *   pre_bias3[b, 0, o]   = sum_{k masked} relu(shift2[k]) * w3[o, k]   (all o)
+ * idx/cnt are the masker outputs (active ids first, then inactive ids). */
+int laud_channel_consts(const void* w2, const void* w3, int width, int C_out,
+                        const float* shift1, const float* shift2,
+                        const int32_t* idx, const int32_t* cnt, int B, int G, int gran,
+                        int H_in, int W_in, int H_out, int W_out, int stride,
+                        float* pre_bias2 /* [B,16,width] */, float* pre_bias3 /* [B,1,C_out] */,
+                        void* stream);
+
+/* ---------------------------------------------------------------------------
+ * (a8) network ends.  Stem: conv7x7/2 + BN + ReLU + maxpool3x3/2 fused
+ * (laud_resnet.py:317-324).  x fp16 NCHW [B,3,H,W] -> y fp16 NHWC [B,H/4,W/4,C0].
+ *   w fp16 [C0,3,7,7] (reference layout), scale/shift fp32 [C0].
+ * Head: global avgpool + fc (laud_resnet.py:349-356).
+ *   x fp16 [B,HW,C] -> logits fp32 [B,n_cls]; w fp16 [n_cls,C], bias fp32.
+ * ------------------------------------------------------------------------- */
+int laud_stem_forward(const void* x_nchw, int B, int H, int W, const void* w, int C0,
+                      const float* scale, const float* shift, void* y_nhwc, void* stream);
+int laud_head_forward(const void* x, int B, int HW, int C, const void* w, const float* bias,
+                      int n_cls, float* pooled_ws /* [B,C] */, float* logits, void* stream);
+
+/* Layout helpers (operator-level API / tests): fp32|fp16 NCHW <-> fp16 NHWC. */
+int laud_nchw_to_nhwc_f16(const void* src, int src_is_f32, int B, int C, int H, int W,
+                          void* dst, int ldd, void* stream);
+int laud_nhwc_f16_to_nchw_f32(const void* src, int lds, int B, int C, int H, int W,
+                              float* dst, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Forward statistics.  Reproduces, in one launch and in the reference's fp32
+ * evaluation order, the per-block densities / flops_perc / flops that
+ * Bottleneck.forward and ResNet.forward thread through the network
+ * (laud_resnet.py:112-162, 321-356).
+ *   counts i32 [n_blocks,4]: ones in (channel mask, mask_conv3 small, mask_conv2, mask_conv1)
+ *   consts i64 [n_blocks,12]: see laud_stats_consts_t in laudnet_b200/_stats.py
+ *   out    f32 [n_blocks,5 + 1]: rho3,rho2,rho1,rho_c,flops_perc per block, then total flops
+ * ------------------------------------------------------------------------- */
+int laud_forward_stats(const int32_t* counts, const int64_t* consts, int n_blocks,
+                       int64_t stem_flops, int64_t pool_flops, int64_t fc_flops, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LAUD_B200_H_ */

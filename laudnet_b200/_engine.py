@@ -1,0 +1,388 @@
+"""Host-side executor of the LAUD-ResNet forward on top of the C ABI.
+
+Holds the *prepared* model (fp16 K-major conv weights, folded BatchNorm
+scale/shift, fp32 masker parameters) and the activation / mask workspaces, and
+sequences the kernels of one forward pass on torch's current CUDA stream.
+torch is used for device memory and streams only; every arithmetic kernel
+launched from here lives in liblaud_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import ConvDesc, LaudError, check, lib, ptr, stream_ptr
+
+
+def fold_bn(bn: nn.BatchNorm2d):
+    """Eval-mode BatchNorm as y = x*scale + shift (fp32)."""
+    with torch.no_grad():
+        scale = (bn.weight.float() / torch.sqrt(bn.running_var.float() + bn.eps)).contiguous()
+        shift = (bn.bias.float() - bn.running_mean.float() * scale).contiguous()
+    return scale, shift
+
+
+def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
+    """[C_out, C_in, kh, kw] fp32 -> fp16 [C_out, kh*kw, C_in] (K-major: in-channel fastest)."""
+    with torch.no_grad():
+        co, ci, kh, kw = w.shape
+        return w.detach().permute(0, 2, 3, 1).reshape(co, kh * kw, ci).to(torch.float16).contiguous()
+
+
+def round_up(v: int, a: int) -> int:
+    return (v + a - 1) // a * a
+
+
+def run_conv(x, w, y, B, H_in, W_in, C_in, H_out, W_out, C_out, ksize, stride, pad, *,
+             ldx=None, ldy=None, scale=None, shift=None, relu=_lib.RELU_NONE, residual=None, ldr=0,
+             k_idx=None, k_cnt=None, k_gran=1, n_idx=None, n_cnt=None, n_gran=1,
+             pre_bias=None, pre_bias_classes=0, pre_bias_ld=0, out_mask=None, mask_groups=1,
+             sample_idx=None, sample_cnt=None, row_idx=None, row_cnt=None, n_pad_align=0,
+             impl=_lib.CONV_AUTO) -> None:
+    """Fill a laud_conv_desc and enqueue laud_conv_forward on the current stream."""
+    d = ConvDesc()
+    d.x, d.ldx = ptr(x), ldx if ldx is not None else x.shape[-1]
+    d.w = ptr(w)
+    d.y, d.ldy = ptr(y), ldy if ldy is not None else y.shape[-1]
+    d.B, d.H_in, d.W_in, d.C_in = B, H_in, W_in, C_in
+    d.H_out, d.W_out, d.C_out = H_out, W_out, C_out
+    d.ksize, d.stride, d.pad = ksize, stride, pad
+    d.scale, d.shift = ptr(scale), ptr(shift)
+    d.relu_mode = relu
+    d.residual, d.ldr = ptr(residual), ldr
+    d.k_idx, d.k_cnt = ptr(k_idx), ptr(k_cnt)
+    d.k_ld, d.k_gran = (k_idx.shape[-1] if k_idx is not None else 0), k_gran
+    d.n_idx, d.n_cnt = ptr(n_idx), ptr(n_cnt)
+    d.n_ld, d.n_gran = (n_idx.shape[-1] if n_idx is not None else 0), n_gran
+    d.pre_bias, d.pre_bias_classes, d.pre_bias_ld = ptr(pre_bias), pre_bias_classes, pre_bias_ld
+    d.out_mask, d.mask_groups = ptr(out_mask), mask_groups
+    d.sample_idx, d.sample_cnt = ptr(sample_idx), ptr(sample_cnt)
+    d.row_idx, d.row_cnt = ptr(row_idx), ptr(row_cnt)
+    d.n_pad_align = n_pad_align
+    d.gap_partial, d.gap_tiles = None, 0
+    check(lib().laud_conv_forward(C.byref(d), impl, stream_ptr()), "laud_conv_forward")
+
+
+@dataclass
+class BlockPlan:
+    """Static description + prepared parameters of one bottleneck."""
+    index: int
+    stage: int
+    inplanes: int
+    width: int
+    outplanes: int
+    stride: int
+    H_in: int
+    H_out: int
+    mode: str
+    gran: int
+    G: int
+    g_spatial: int
+    mask_size: int
+    w1: torch.Tensor = None
+    w2: torch.Tensor = None
+    w3: torch.Tensor = None
+    wd: Optional[torch.Tensor] = None
+    s1: torch.Tensor = None
+    t1: torch.Tensor = None
+    s2: torch.Tensor = None
+    t2: torch.Tensor = None
+    s3: torch.Tensor = None
+    t3: torch.Tensor = None
+    sd: Optional[torch.Tensor] = None
+    td: Optional[torch.Tensor] = None
+    module: nn.Module = None
+
+    @property
+    def use_c(self) -> bool:
+        return self.mode in ("channel", "both")
+
+    @property
+    def use_s(self) -> bool:
+        return self.mode in ("spatial", "layer", "both")
+
+
+class BlockOutputs:
+    """Optional per-block device tensors kept for parity tests."""
+    __slots__ = ("channel_mask", "channel_idx", "channel_cnt", "channel_logits", "spatial_mask_small",
+                 "spatial_logits", "mask_conv3", "mask_conv2", "mask_conv1", "a1", "a2", "out")
+
+    def __init__(self):
+        for s in self.__slots__:
+            setattr(self, s, None)
+
+
+class ResNetEngine:
+    """Runs ResNet.forward (reference laud_resnet.py:316-363) as a kernel sequence."""
+
+    def __init__(self, model: "nn.Module"):
+        self.model = model
+        self.plans: List[BlockPlan] = []
+        self.prepared_for: Optional[torch.device] = None
+        self.impl = _lib.CONV_AUTO
+        self._ws: Dict[tuple, dict] = {}
+
+    # ------------------------------------------------------------------ prepare
+    def prepare(self) -> None:
+        m = self.model
+        dev = m.conv1.weight.device
+        if dev.type != "cuda":
+            raise LaudError("prepare(): move the model to a CUDA device first - there is no CPU path")
+        self.stem_w = m.conv1.weight.detach().to(torch.float16).contiguous()
+        self.stem_s, self.stem_t = fold_bn(m.bn1)
+        self.fc_w = m.fc.weight.detach().to(torch.float16).contiguous()
+        self.fc_b = m.fc.bias.detach().float().contiguous()
+        self.plans = []
+        idx = 0
+        for s, layer in enumerate((m.layer1, m.layer2, m.layer3, m.layer4)):
+            for blk in layer:
+                p = BlockPlan(index=idx, stage=s, inplanes=blk.conv1.weight.shape[1], width=blk.conv1.weight.shape[0],
+                              outplanes=blk.conv3.weight.shape[0], stride=blk.stride,
+                              H_in=blk.output_size * blk.stride, H_out=blk.output_size, mode=blk.dyn_mode,
+                              gran=blk.channel_dyn_granularity, G=blk.channel_dyn_group,
+                              g_spatial=blk.spatial_mask_channel_group, mask_size=blk.mask_size, module=blk)
+                if blk.conv2.groups != 1:
+                    raise LaudError("grouped conv2 (group_width>1) is not supported by the CUDA path")
+                p.w1, p.w2, p.w3 = (pack_conv_weight(c.weight) for c in (blk.conv1, blk.conv2, blk.conv3))
+                p.s1, p.t1 = fold_bn(blk.bn1)
+                p.s2, p.t2 = fold_bn(blk.bn2)
+                p.s3, p.t3 = fold_bn(blk.bn3)
+                if blk.downsample is not None:
+                    p.wd = pack_conv_weight(blk.downsample[0].weight)
+                    p.sd, p.td = fold_bn(blk.downsample[1])
+                for cdim in (p.inplanes, p.width, p.outplanes):
+                    if cdim % 8:
+                        raise LaudError(f"channel counts must be multiples of 8 for the fp16 kernels (got {cdim})")
+                self.plans.append(p)
+                idx += 1
+        self.stats_consts = self._stats_consts(dev)
+        self.prepared_for = dev
+        self._ws.clear()
+
+    def _stats_consts(self, dev) -> torch.Tensor:
+        rows = []
+        for p in self.plans:
+            blk = p.module
+            m_chan = m_spat = 0
+            if p.use_c:
+                mk = blk.masker_channel
+                if hasattr(mk, "conv_flops"):
+                    m_chan = p.inplanes * p.H_in * p.H_in + mk.conv_flops
+                else:
+                    cr = mk.conv[0].weight.shape[0]
+                    m_chan = cr * p.H_in * p.H_in + mk.masker_flops
+            S = min(p.mask_size, p.H_in)
+            if p.use_s:
+                m_spat = p.inplanes * S * S + blk.masker_spatial.conv_flops_pp * S * S
+            rows.append([m_chan, m_spat,
+                         blk.conv1_flops_per_pixel * p.H_in * p.H_in,
+                         blk.conv2_flops_per_pixel * p.H_out * p.H_out,
+                         blk.conv3_flops_per_pixel * p.H_out * p.H_out,
+                         (blk.downsample_flops * p.H_out * p.H_out) if blk.downsample is not None else 0,
+                         0, 0, 0, 0,      # denominators depend on the batch: filled per forward
+                         (1 if p.use_c else 0) | (2 if p.use_s else 0), 0])
+        return torch.tensor(rows, dtype=torch.int64)     # host; a device copy per batch size lives in the workspace
+
+    # --------------------------------------------------------------- workspaces
+    def _workspace(self, B: int, H: int, W: int, dev) -> dict:
+        key = (B, H, W, dev)
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        m = self.model
+        f16 = dict(dtype=torch.float16, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+        C0 = m.conv1.weight.shape[0]
+        act = max([B * (H // 4) * (W // 4) * C0] + [B * p.H_out * p.H_out * p.outplanes for p in self.plans])
+        a1 = max(B * p.H_in * p.H_in * (p.width + 16) for p in self.plans)
+        a2 = max(B * p.H_out * p.H_out * (p.width + 16) for p in self.plans)
+        nb = len(self.plans)
+        Gmax = max([p.G for p in self.plans if p.use_c] or [1])
+        Cmax = max([p.inplanes for p in self.plans] + [m.fc.weight.shape[1]])
+        wmax = max(p.width for p in self.plans)
+        comax = max(p.outplanes for p in self.plans)
+        hw_max = max(p.H_in * p.H_in for p in self.plans)
+        g_max = max(p.g_spatial for p in self.plans)
+        ws = dict(
+            act=[torch.empty(act, **f16), torch.empty(act, **f16), torch.empty(act, **f16)],
+            a1=torch.empty(a1, **f16), a2=torch.empty(a2, **f16),
+            partial=torch.empty(B * (_lib.GAP_SPLITS + 1) * Cmax, dtype=torch.float32, device=dev),
+            cmask=torch.empty((B, Gmax), dtype=torch.uint8, device=dev),
+            cidx=torch.empty((B, Gmax), **i32), ccnt=torch.empty((B,), **i32),
+            pb2=torch.empty(B * 16 * wmax, dtype=torch.float32, device=dev),
+            pb3=torch.empty(B * comax, dtype=torch.float32, device=dev),
+            smask=torch.empty(B * g_max * hw_max, dtype=torch.uint8, device=dev),
+            m3=torch.empty(B * g_max * hw_max, dtype=torch.uint8, device=dev),
+            m2=torch.empty(B * g_max * hw_max, dtype=torch.uint8, device=dev),
+            m1=torch.empty(B * g_max * hw_max, dtype=torch.uint8, device=dev),
+            counts=torch.zeros((nb, 4), **i32),
+            stats=torch.empty(nb * 5 + 1, dtype=torch.float32, device=dev),
+            logits=None,
+        )
+        consts = self.stats_consts.clone()
+        for i, p in enumerate(self.plans):
+            S = min(p.mask_size, p.H_in)
+            consts[i, 6] = B * p.G
+            consts[i, 7] = B * p.g_spatial * S * S
+            consts[i, 8] = B * p.g_spatial * p.H_out * p.H_out
+            consts[i, 9] = B * p.g_spatial * p.H_in * p.H_in
+        ws["consts"] = consts.to(dev)
+        self._ws[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------ blocks
+    def run_block(self, p: BlockPlan, x: torch.Tensor, out: torch.Tensor, idbuf: torch.Tensor, B: int, ws: dict,
+                  keep: Optional[BlockOutputs] = None, forced_channel_mask: Optional[torch.Tensor] = None,
+                  forced_spatial_mask: Optional[torch.Tensor] = None) -> None:
+        """x: fp16 [B,H_in,H_in,inplanes] -> out: fp16 [B,H_out,H_out,outplanes]."""
+        blk = p.module
+        L = lib()
+        st = stream_ptr()
+        Hi, Ho = p.H_in, p.H_out
+        counts = ws["counts"][p.index]
+        gate = None
+        m3 = None
+        wp = p.width + 16                       # channel pitch of the compact intermediates
+        if p.use_c:
+            from .utils import _ChannelGate
+            G = p.G
+            gate = _ChannelGate(ws["cmask"].view(-1)[:B * G].view(B, G), ws["cidx"].view(-1)[:B * G].view(B, G),
+                                ws["ccnt"], None, None)
+            if keep is not None:
+                gate.logits = torch.empty((B, 2 * G), dtype=torch.float32, device=x.device)
+                gate.pooled = torch.empty((B, x.shape[-1]), dtype=torch.float32, device=x.device)
+            if forced_channel_mask is not None:
+                self._force_channel_gate(gate, forced_channel_mask, counts[0:1])
+            else:
+                blk.masker_channel.gate_nhwc(x[:B * Hi * Hi * p.inplanes].view(B, Hi, Hi, p.inplanes), counts[0:1],
+                                             out=gate, partial_ws=ws["partial"])
+            check(L.laud_channel_consts(ptr(p.w2), ptr(p.w3), p.width, p.outplanes, ptr(p.t1), ptr(p.t2),
+                                        ptr(gate.idx), ptr(gate.cnt), B, G, p.gran, Hi, Hi, Ho, Ho, p.stride,
+                                        ptr(ws["pb2"]), ptr(ws["pb3"]), st), "laud_channel_consts")
+        if p.use_s:
+            g = p.g_spatial
+            S = min(p.mask_size, Hi)
+            small = ws["smask"][:B * g * S * S].view(B, g, S, S)
+            if forced_spatial_mask is not None:
+                small.copy_(forced_spatial_mask.to(torch.uint8))
+                counts[1:2].copy_(small.sum().to(torch.int32).view(1))
+                slog = None
+            else:
+                slog = torch.empty((B, 2 * g, S, S), dtype=torch.float32, device=x.device) if keep is not None else None
+                wt = blk.masker_spatial.conv.weight.detach().reshape(2 * g, p.inplanes)
+                check(L.laud_masker_spatial(ptr(x), B, Hi, Hi, p.inplanes, ptr(wt),
+                                            ptr(blk.masker_spatial.conv.bias.detach()), g, S, ptr(slog), ptr(small),
+                                            ptr(counts[1:2]), st), "laud_masker_spatial")
+            m3 = ws["m3"][:B * g * Ho * Ho].view(B, g, Ho, Ho)
+            m2 = ws["m2"][:B * g * Ho * Ho].view(B, g, Ho, Ho)
+            m1 = ws["m1"][:B * g * Hi * Hi].view(B, g, Hi, Hi)
+            check(L.laud_resize_mask_nearest(ptr(small), B, g, S, Ho, ptr(m3), st), "laud_resize_mask_nearest")
+            check(L.laud_expand_mask(ptr(m3), B, g, Ho, Ho, 1, 0, ptr(m2), ptr(counts[2:3]), st), "laud_expand_mask")
+            check(L.laud_expand_mask(ptr(m2), B, g, Ho, Ho, p.stride, 1, ptr(m1), ptr(counts[3:4]), st),
+                  "laud_expand_mask")
+            if keep is not None:
+                keep.spatial_mask_small, keep.spatial_logits = small.clone(), slog
+                keep.mask_conv3, keep.mask_conv2, keep.mask_conv1 = m3.clone(), m2.clone(), m1.clone()
+
+        a1, a2 = ws["a1"], ws["a2"]
+        ck = dict(k_idx=gate.idx, k_cnt=gate.cnt, k_gran=p.gran) if gate else {}
+        cn = dict(n_idx=gate.idx, n_cnt=gate.cnt, n_gran=p.gran, n_pad_align=16) if gate else {}
+        ld12 = wp if gate else p.width
+        # conv1 1x1 (+ mask) + bn1 + relu      laud_resnet.py:115-118
+        run_conv(x, p.w1, a1, B, Hi, Hi, p.inplanes, Hi, Hi, p.width, 1, 1, 0, ldx=p.inplanes, ldy=ld12,
+                 scale=p.s1, shift=p.t1, relu=_lib.RELU_ALL, impl=self.impl, **cn)
+        # conv2 3x3/stride (+ mask) + bn2 + relu     laud_resnet.py:123-126
+        run_conv(a1, p.w2, a2, B, Hi, Hi, p.width, Ho, Ho, p.width, 3, p.stride, 1, ldx=ld12, ldy=ld12,
+                 scale=p.s2, shift=p.t2, relu=_lib.RELU_ALL, impl=self.impl,
+                 pre_bias=ws["pb2"] if gate else None, pre_bias_classes=16 if gate else 0,
+                 pre_bias_ld=p.width if gate else 0, **ck, **cn)
+        # identity branch      laud_resnet.py:138-141
+        if p.wd is not None:
+            run_conv(x, p.wd, idbuf, B, Hi, Hi, p.inplanes, Ho, Ho, p.outplanes, 1, p.stride, 0, ldx=p.inplanes,
+                     ldy=p.outplanes, scale=p.sd, shift=p.td, relu=_lib.RELU_NONE, impl=self.impl)
+            res = idbuf
+        else:
+            res = x
+        # conv3 1x1 + bn3 (+ spatial mask) + identity + relu     laud_resnet.py:131-144
+        run_conv(a2, p.w3, out, B, Ho, Ho, p.width, Ho, Ho, p.outplanes, 1, 1, 0, ldx=ld12, ldy=p.outplanes,
+                 scale=p.s3, shift=p.t3, relu=_lib.RELU_ALL, residual=res, ldr=p.outplanes, impl=self.impl,
+                 pre_bias=ws["pb3"] if gate else None, pre_bias_classes=1 if gate else 0,
+                 pre_bias_ld=p.outplanes if gate else 0, out_mask=m3, mask_groups=p.g_spatial if m3 is not None else 1,
+                 **ck)
+        if keep is not None:
+            if gate is not None:
+                keep.channel_mask, keep.channel_idx, keep.channel_cnt = gate.mask.clone(), gate.idx.clone(), gate.cnt.clone()
+                keep.channel_logits = gate.logits
+            keep.a1 = a1[:B * Hi * Hi * ld12].view(B, Hi, Hi, ld12).clone()
+            keep.a2 = a2[:B * Ho * Ho * ld12].view(B, Ho, Ho, ld12).clone()
+            keep.out = out[:B * Ho * Ho * p.outplanes].view(B, Ho, Ho, p.outplanes).clone()
+
+    @staticmethod
+    def _force_channel_gate(gate, mask: torch.Tensor, total: torch.Tensor) -> None:
+        """Teacher forcing (tests): install a given 0/1 mask [B,G] as the gate."""
+        m = mask.to(torch.uint8)
+        gate.mask.copy_(m)
+        B, G = m.shape
+        order = torch.argsort(1 - m.to(torch.int32), dim=1, stable=True).to(torch.int32)   # actives first, ascending
+        gate.idx.copy_(order)
+        gate.cnt.copy_(m.sum(dim=1).to(torch.int32))
+        total.copy_(m.sum().to(torch.int32).view(1))
+
+    # ----------------------------------------------------------------- forward
+    def forward(self, x: torch.Tensor, keep: Optional[List[BlockOutputs]] = None):
+        m = self.model
+        if x.device.type != "cuda":
+            raise LaudError("ResNet.forward: expected a CUDA tensor - there is no CPU path")
+        if self.prepared_for != x.device:
+            self.prepare()
+        if x.dtype not in (torch.float16, torch.float32):
+            raise LaudError(f"ResNet.forward: unsupported input dtype {x.dtype}")
+        B, cin, H, W = x.shape
+        if cin != 3 or H != m.input_size or W != m.input_size:
+            raise LaudError(f"ResNet.forward: expected [B,3,{m.input_size},{m.input_size}], got {tuple(x.shape)}")
+        xh = x.contiguous() if x.dtype == torch.float16 else x.contiguous().to(torch.float16)
+        ws = self._workspace(B, H, W, x.device)
+        L = lib()
+        st = stream_ptr()
+        ws["counts"].zero_()
+        C0 = m.conv1.weight.shape[0]
+        bufs = ws["act"]
+        cur = 0
+        check(L.laud_stem_forward(ptr(xh), B, H, W, ptr(self.stem_w), C0, ptr(self.stem_s), ptr(self.stem_t),
+                                  ptr(bufs[cur]), st), "laud_stem_forward")
+        for p in self.plans:
+            nxt = (cur + 1) % 3
+            idb = (cur + 2) % 3
+            ko = None
+            if keep is not None:
+                ko = BlockOutputs()
+                keep.append(ko)
+            self.run_block(p, bufs[cur], bufs[nxt], bufs[idb], B, ws, ko)
+            cur = nxt
+        last = self.plans[-1]
+        feat = last.outplanes
+        ncls = m.fc.weight.shape[0]
+        logits = torch.empty((B, ncls), dtype=torch.float32, device=x.device)
+        check(L.laud_head_forward(ptr(bufs[cur]), B, last.H_out * last.H_out, feat, ptr(self.fc_w), ptr(self.fc_b),
+                                  ncls, ptr(ws["partial"]), ptr(logits), st), "laud_head_forward")
+        stem_flops = 3 * C0 * (H // 2) * (W // 2) * 49 + C0 * (H // 4) * (W // 4) * 9
+        stats = torch.empty_like(ws["stats"])
+        check(L.laud_forward_stats(ptr(ws["counts"]), ptr(ws["consts"]), len(self.plans), stem_flops, feat,
+                                   feat * ncls, ptr(stats), st), "laud_forward_stats")
+        return logits, stats
+
+    def split_stats(self, stats: torch.Tensor):
+        """stats [n_blocks*5+1] -> the reference's (rho3[4], rho2[4], rho1[4], rho_c[4], flops_perc, flops)."""
+        nb = len(self.plans)
+        tab = stats[:nb * 5].view(nb, 5)
+        bounds, s0 = [], 0
+        for layer in (self.model.layer1, self.model.layer2, self.model.layer3, self.model.layer4):
+            bounds.append((s0, s0 + len(layer)))
+            s0 += len(layer)
+        col = lambda c: [tab[a:b, c] for a, b in bounds]
+        return col(0), col(1), col(2), col(3), tab[:, 4], stats[nb * 5]

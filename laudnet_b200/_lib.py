@@ -1,0 +1,116 @@
+"""ctypes binding of liblaud_b200.so (the C ABI declared in include/laud_b200.h).
+
+There is no fallback: if the CUDA library has not been built, importing the
+operators raises.  Build it with `python -m laudnet_b200.build` (or
+`__graft_entry__.build()`); the .so is kept in-tree under laudnet_b200/lib/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "liblaud_b200.so")
+
+CONV_AUTO, CONV_UMMA, CONV_HMMA, CONV_NAIVE = 0, 1, 2, 3
+RELU_NONE, RELU_ALL, RELU_WHERE_GATE0 = 0, 1, 2
+GAP_SPLITS = 8
+PREBIAS_CLASSES = 16
+
+_vp, _i, _fp, _u8p, _i32p, _i64 = C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64
+
+
+class ConvDesc(C.Structure):
+    """Mirror of `struct laud_conv_desc`."""
+    _fields_ = [
+        ("x", _vp), ("ldx", C.c_int32),
+        ("w", _vp),
+        ("y", _vp), ("ldy", C.c_int32),
+        ("B", C.c_int32), ("H_in", C.c_int32), ("W_in", C.c_int32), ("C_in", C.c_int32),
+        ("H_out", C.c_int32), ("W_out", C.c_int32), ("C_out", C.c_int32),
+        ("ksize", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
+        ("scale", _vp), ("shift", _vp),
+        ("relu_mode", C.c_int32),
+        ("residual", _vp), ("ldr", C.c_int32),
+        ("k_idx", _vp), ("k_cnt", _vp), ("k_ld", C.c_int32), ("k_gran", C.c_int32),
+        ("n_idx", _vp), ("n_cnt", _vp), ("n_ld", C.c_int32), ("n_gran", C.c_int32),
+        ("pre_bias", _vp), ("pre_bias_classes", C.c_int32), ("pre_bias_ld", C.c_int32),
+        ("out_mask", _vp), ("mask_groups", C.c_int32),
+        ("sample_idx", _vp), ("sample_cnt", _vp),
+        ("row_idx", _vp), ("row_cnt", _vp),
+        ("n_pad_align", C.c_int32),
+        ("gap_partial", _vp), ("gap_tiles", C.c_int32),
+    ]
+
+
+# name -> argtypes; every symbol include/laud_b200.h declares must be listed here
+SIGNATURES = {
+    "laud_abi_version": ([], C.c_int),
+    "laud_last_error": ([], C.c_char_p),
+    "laud_launch_count": ([], C.c_ulonglong),
+    "laud_masker_channel_mlp": ([_vp, _i, _i, _i, _i, _fp, _fp, _i, _fp, _fp, _i, _fp, _fp, _fp, _u8p, _i32p, _i32p, _i32p, _vp], _i),
+    "laud_masker_channel_from_pooled": ([_fp, _i, _i, _i, _fp, _fp, _i, _fp, _fp, _i, _fp, _u8p, _i32p, _i32p, _i32p, _vp], _i),
+    "laud_global_avg_pool": ([_vp, _i, _i, _i, _i, _fp, _fp, _vp], _i),
+    "laud_masker_spatial": ([_vp, _i, _i, _i, _i, _fp, _fp, _i, _i, _fp, _u8p, _i32p, _vp], _i),
+    "laud_expand_mask": ([_u8p, _i, _i, _i, _i, _i, _i, _u8p, _i32p, _vp], _i),
+    "laud_resize_mask_nearest": ([_u8p, _i, _i, _i, _i, _u8p, _vp], _i),
+    "laud_compact_rows": ([_u8p, _i, _i, _i, _i32p, _i32p, _i32p, _vp], _i),
+    "laud_conv_forward": ([C.POINTER(ConvDesc), _i, _vp], _i),
+    "laud_channel_consts": ([_vp, _vp, _i, _i, _fp, _fp, _i32p, _i32p, _i, _i, _i, _i, _i, _i, _i, _i, _fp, _fp, _vp], _i),
+    "laud_stem_forward": ([_vp, _i, _i, _i, _vp, _i, _fp, _fp, _vp, _vp], _i),
+    "laud_head_forward": ([_vp, _i, _i, _i, _vp, _fp, _i, _fp, _fp, _vp], _i),
+    "laud_nchw_to_nhwc_f16": ([_vp, _i, _i, _i, _i, _i, _vp, _i, _vp], _i),
+    "laud_nhwc_f16_to_nchw_f32": ([_vp, _i, _i, _i, _i, _i, _fp, _vp], _i),
+    "laud_forward_stats": ([_i32p, _vp, _i, _i64, _i64, _i64, _fp, _vp], _i),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+class LaudError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """Load the shared library (once).  Fails loudly when it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LaudError(
+                f"{LIB_PATH} is missing: the CUDA extension has not been built. "
+                "Run `python -m laudnet_b200.build` - there is no CPU/PyTorch fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (argtypes, restype) in SIGNATURES.items():
+            fn = getattr(handle, name)      # AttributeError if the symbol is not exported
+            fn.argtypes = argtypes
+            fn.restype = restype
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().laud_last_error().decode(errors="replace")
+        raise LaudError(f"{what or 'laud call'} failed (code {rc}): {msg}")
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr() -> int:
+    """cudaStream_t of torch's current stream, so our launches order with torch's."""
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise LaudError(f"{what}: expected a CUDA tensor - the LAUD operators have no CPU path")
+
+
+def launch_count() -> int:
+    return int(lib().laud_launch_count())

@@ -1,0 +1,101 @@
+// C-ABI glue: error strings, launch accounting, descriptor validation and
+// dispatch of the mask-conditioned convolution.
+#include <stdarg.h>
+#include <string.h>
+#include "laud_common.cuh"
+
+namespace laud {
+
+static thread_local char g_err[512] = "";
+std::atomic<unsigned long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+}  // namespace laud
+
+using namespace laud;
+
+extern "C" int laud_abi_version(void) { return LAUD_ABI_VERSION; }
+extern "C" const char* laud_last_error(void) { return g_err; }
+extern "C" unsigned long long laud_launch_count(void) { return g_launches.load(); }
+
+extern "C" int laud_conv_forward(const laud_conv_desc* d, int impl, void* stream) {
+  LAUD_REQUIRE(d != nullptr, "laud_conv_forward: null descriptor");
+  LAUD_REQUIRE(d->x && d->w && d->y, "laud_conv_forward: null x/w/y");
+  LAUD_REQUIRE(d->B > 0 && d->H_in > 0 && d->W_in > 0 && d->H_out > 0 && d->W_out > 0 && d->C_in > 0 && d->C_out > 0,
+               "laud_conv_forward: non-positive dimension");
+  LAUD_REQUIRE(d->ksize == 1 || d->ksize == 3, "laud_conv_forward: ksize must be 1 or 3 (got %d)", d->ksize);
+  LAUD_REQUIRE(d->stride >= 1 && d->pad >= 0 && d->pad <= 1, "laud_conv_forward: bad stride/pad");
+  LAUD_REQUIRE((d->H_in + 2 * d->pad - d->ksize) / d->stride + 1 == d->H_out &&
+                   (d->W_in + 2 * d->pad - d->ksize) / d->stride + 1 == d->W_out,
+               "laud_conv_forward: output size %dx%d inconsistent with input %dx%d k=%d s=%d p=%d", d->H_out,
+               d->W_out, d->H_in, d->W_in, d->ksize, d->stride, d->pad);
+  LAUD_REQUIRE(d->C_in % 8 == 0 && d->ldx % 8 == 0 && d->ldy % 2 == 0,
+               "laud_conv_forward: need C_in %% 8 == 0, ldx %% 8 == 0, ldy even (C_in=%d ldx=%d ldy=%d)", d->C_in,
+               d->ldx, d->ldy);
+  LAUD_REQUIRE(d->n_pad_align == 0 || d->n_pad_align == 8 || d->n_pad_align == 16, "laud_conv_forward: n_pad_align");
+  LAUD_REQUIRE(d->ldy >= round_up(d->C_out, d->n_pad_align) || d->n_idx, "laud_conv_forward: ldy too small");
+  LAUD_REQUIRE((d->scale == nullptr) == (d->shift == nullptr), "laud_conv_forward: scale and shift go together");
+  if (d->k_idx) {
+    LAUD_REQUIRE(d->k_cnt && d->k_gran >= 1 && d->k_ld * d->k_gran == d->C_in,
+                 "laud_conv_forward: k gather needs k_cnt and k_ld*k_gran == C_in");
+    LAUD_REQUIRE(d->ldx >= round_up(d->C_in, 8), "laud_conv_forward: ldx too small for compact input");
+  } else {
+    LAUD_REQUIRE(d->ldx >= d->C_in, "laud_conv_forward: ldx < C_in");
+  }
+  if (d->n_idx)
+    LAUD_REQUIRE(d->n_cnt && d->n_gran >= 1 && d->n_ld * d->n_gran == d->C_out && d->ldy >= round_up(d->C_out, d->n_pad_align),
+                 "laud_conv_forward: n gather needs n_cnt, n_ld*n_gran == C_out, ldy >= padded C_out");
+  if (d->row_idx) {
+    LAUD_REQUIRE(d->row_cnt, "laud_conv_forward: row_idx needs row_cnt");
+    LAUD_REQUIRE(!d->k_idx && !d->n_idx && !d->sample_idx && !d->pre_bias,
+                 "laud_conv_forward: row gather cannot be combined with per-sample channel/sample lists");
+  }
+  if (d->sample_idx) LAUD_REQUIRE(d->sample_cnt, "laud_conv_forward: sample_idx needs sample_cnt");
+  if (d->pre_bias)
+    LAUD_REQUIRE((d->pre_bias_classes == 1 || d->pre_bias_classes == LAUD_PREBIAS_CLASSES) && d->pre_bias_ld > 0,
+                 "laud_conv_forward: pre_bias_classes must be 1 or 16");
+  if (d->out_mask)
+    LAUD_REQUIRE(d->mask_groups >= 1 && d->C_out % d->mask_groups == 0, "laud_conv_forward: bad mask_groups");
+  LAUD_REQUIRE(d->relu_mode >= 0 && d->relu_mode <= 2, "laud_conv_forward: bad relu_mode");
+  LAUD_REQUIRE(d->relu_mode != LAUD_RELU_WHERE_GATE0 || d->out_mask, "laud_conv_forward: RELU_WHERE_GATE0 needs out_mask");
+  if (d->residual) LAUD_REQUIRE(d->ldr >= d->C_out && !d->n_idx, "laud_conv_forward: residual needs dense output channels");
+  LAUD_REQUIRE(d->gap_partial == nullptr, "laud_conv_forward: fused GAP epilogue not available in this build");
+
+  ConvArgs a;
+  a.x = (const __half*)d->x; a.ldx = d->ldx;
+  a.w = (const __half*)d->w;
+  a.y = (__half*)d->y; a.ldy = d->ldy;
+  a.B = d->B; a.H_in = d->H_in; a.W_in = d->W_in; a.C_in = d->C_in;
+  a.H_out = d->H_out; a.W_out = d->W_out; a.C_out = d->C_out;
+  a.ksize = d->ksize; a.stride = d->stride; a.pad = d->pad;
+  a.scale = d->scale; a.shift = d->shift; a.relu_mode = d->relu_mode;
+  a.residual = (const __half*)d->residual; a.ldr = d->ldr;
+  a.k_idx = d->k_idx; a.k_cnt = d->k_cnt; a.k_ld = d->k_ld; a.k_gran = d->k_gran;
+  a.n_idx = d->n_idx; a.n_cnt = d->n_cnt; a.n_ld = d->n_ld; a.n_gran = d->n_gran;
+  a.pre_bias = d->pre_bias; a.pre_bias_classes = d->pre_bias_classes; a.pre_bias_ld = d->pre_bias_ld;
+  a.out_mask = d->out_mask; a.mask_groups = d->mask_groups;
+  a.sample_idx = d->sample_idx; a.sample_cnt = d->sample_cnt;
+  a.row_idx = d->row_idx; a.row_cnt = d->row_cnt;
+  a.n_pad_align = d->n_pad_align;
+  a.gap_partial = d->gap_partial; a.gap_tiles = d->gap_tiles;
+
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (impl) {
+    case LAUD_CONV_AUTO:
+    case LAUD_CONV_UMMA:
+      return conv_forward_umma(a, s);
+    case LAUD_CONV_HMMA:
+      return conv_forward_hmma(a, s);
+    case LAUD_CONV_NAIVE:
+      return conv_forward_naive(a, s);
+    default:
+      set_error("laud_conv_forward: unknown impl %d", impl);
+      return LAUD_E_BADARG;
+  }
+}

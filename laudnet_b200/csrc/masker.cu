@@ -1,0 +1,447 @@
+// Gating maskers: channel (GAP -> MLP -> 2-way decision -> compact index list)
+// and spatial/layer (adaptive pool -> 1x1 conv -> decision), plus the mask
+// geometry helpers (nearest resize, ExpandMask dilation, row compaction).
+//
+// Reference behaviour restated (not ported): imagenet_classification/models/
+// utils.py:47-65 (Masker_spatial), :74-89 (ExpandMask), :113-131
+// (Masker_channel_MLP).  All sums that feed a decision are fp32, fixed order.
+#include "laud_common.cuh"
+
+namespace laud {
+
+// ---------------------------------------------------------------------------
+// Phase 1 of the deterministic GAP: grid (SPLITS, B), 256 threads.
+// x [B,HW,ldx] fp16, C % 8 == 0.  partial[b][s][c] = sum over the rows of split s.
+// Threads are laid out as (row lane, 16-byte channel vector) so a warp reads
+// contiguous 16B vectors of one pixel row: fully coalesced.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gap_partial_kernel(const __half* __restrict__ x, int HW, int C,
+                                                          int ldx, float* __restrict__ partial) {
+  __shared__ float red[2048 + 64];
+  const int s = blockIdx.x, b = blockIdx.y, nsplit = gridDim.x;
+  const int nvec = C >> 3;
+  const int vt = nvec < 256 ? nvec : 256;       // vector lanes in use
+  const int rl = 256 / vt;                      // row lanes
+  const int tid = threadIdx.x;
+  const int v0 = tid % vt, r0 = tid / vt;
+  const int rows_per = (HW + nsplit - 1) / nsplit;
+  const int rbeg = s * rows_per;
+  const int rend = min(HW, rbeg + rows_per);
+  const __half* xb = x + (size_t)b * HW * ldx;
+  float* out = partial + ((size_t)b * nsplit + s) * C;
+
+  for (int vbase = 0; vbase < nvec; vbase += vt) {
+    const int v = vbase + v0;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    if (r0 < rl && v < nvec) {
+      for (int r = rbeg + r0; r < rend; r += rl) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(xb + (size_t)r * ldx + v * 8));
+        const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __half22float2(h[i]);
+          acc[2 * i] += f.x;
+          acc[2 * i + 1] += f.y;
+        }
+      }
+    }
+    __syncthreads();
+    if (r0 < rl && v < nvec) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) red[r0 * (vt * 8) + v0 * 8 + i] = acc[i];
+    }
+    __syncthreads();
+    // fixed-order reduction over the row lanes
+    for (int c = tid; c < vt * 8; c += 256) {
+      if (vbase * 8 + c < C) {
+        float t = 0.f;
+        for (int r = 0; r < rl; ++r) t += red[r * (vt * 8) + c];
+        out[vbase * 8 + c] = t;
+      }
+    }
+  }
+}
+
+// Phase 2 alone (used by laud_global_avg_pool): pooled[b][c] = sum_s partial / HW.
+__global__ void gap_final_kernel(const float* __restrict__ partial, int C, int nsplit, int HW,
+                                 float* __restrict__ pooled) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float t = 0.f;
+  for (int s = 0; s < nsplit; ++s) t += partial[((size_t)b * nsplit + s) * C + c];
+  pooled[(size_t)b * C + c] = t / (float)HW;
+}
+
+// ---------------------------------------------------------------------------
+// Phase 2 + MLP + decision + ordered compaction.  One CTA (256 thr) per sample.
+// dynamic smem: p[C] | h[hidden] | l[2G] | flag[G] (as int) | wsum[64]
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) masker_decide_kernel(
+    const float* __restrict__ partial, const float* __restrict__ pooled_in, int C, int nsplit, int HW,
+    int layers, const float* __restrict__ w1, const float* __restrict__ b1, int hidden,
+    const float* __restrict__ w2, const float* __restrict__ b2, int G,
+    float* __restrict__ pooled_out, float* __restrict__ logits_out, uint8_t* __restrict__ mask_out,
+    int* __restrict__ idx_out, int* __restrict__ cnt_out, int* __restrict__ total_out) {
+  extern __shared__ float sm[];
+  float* p = sm;
+  float* h = p + C;
+  float* l = h + (hidden > 0 ? hidden : 1);
+  int* flag = reinterpret_cast<int*>(l + 2 * G);
+  int* wsum = flag + G;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  for (int c = tid; c < C; c += 256) {
+    float t;
+    if (pooled_in) {
+      t = pooled_in[(size_t)b * C + c];
+    } else {
+      t = 0.f;
+      for (int s = 0; s < nsplit; ++s) t += partial[((size_t)b * nsplit + s) * C + c];
+      t = t / (float)HW;
+    }
+    p[c] = t;
+    if (pooled_out) pooled_out[(size_t)b * C + c] = t;
+  }
+  __syncthreads();
+
+  // first linear layer: one warp per output row, lanes stride the channels
+  const int rows1 = layers == 2 ? hidden : 2 * G;
+  float* dst1 = layers == 2 ? h : l;
+  for (int j = warp; j < rows1; j += 8) {
+    const float* wr = w1 + (size_t)j * C;
+    float t = 0.f;
+    for (int c = lane; c < C; c += 32) t = fmaf(wr[c], p[c], t);
+    t = warp_sum(t);
+    if (lane == 0) {
+      t += b1[j];
+      dst1[j] = layers == 2 ? fmaxf(t, 0.f) : t;
+    }
+  }
+  __syncthreads();
+  if (layers == 2) {
+    for (int o = tid; o < 2 * G; o += 256) {
+      const float* wr = w2 + (size_t)o * hidden;
+      float t = 0.f;
+      for (int j = 0; j < hidden; ++j) t = fmaf(wr[j], h[j], t);
+      l[o] = t + b2[o];
+    }
+    __syncthreads();
+  }
+  for (int o = tid; o < 2 * G; o += 256)
+    if (logits_out) logits_out[(size_t)b * 2 * G + o] = l[o];
+  for (int g = tid; g < G; g += 256) {
+    const int f = l[g] >= l[G + g] ? 1 : 0;          // ties keep (utils.py:127)
+    flag[g] = f;
+    mask_out[(size_t)b * G + g] = (uint8_t)f;
+  }
+  __syncthreads();
+
+  // ordered compaction: chunks of 256 groups; ballot + warp prefix
+  int base_on = 0;
+  // pass 1: active ids
+  for (int g0 = 0; g0 < G; g0 += 256) {
+    const int g = g0 + tid;
+    const int f = g < G ? flag[g] : 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) wsum[warp] = __popc(bal);
+    __syncthreads();
+    int off = base_on;
+    for (int w = 0; w < warp; ++w) off += wsum[w];
+    if (f) idx_out[(size_t)b * G + off + __popc(bal & ((1u << lane) - 1))] = g;
+    int tot = 0;
+    for (int w = 0; w < 8; ++w) tot += wsum[w];
+    base_on += tot;
+    __syncthreads();
+  }
+  // pass 2: inactive ids behind them
+  int base_off = base_on;
+  for (int g0 = 0; g0 < G; g0 += 256) {
+    const int g = g0 + tid;
+    const int f = g < G ? (flag[g] ? 0 : 1) : 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) wsum[warp] = __popc(bal);
+    __syncthreads();
+    int off = base_off;
+    for (int w = 0; w < warp; ++w) off += wsum[w];
+    if (f) idx_out[(size_t)b * G + off + __popc(bal & ((1u << lane) - 1))] = g;
+    int tot = 0;
+    for (int w = 0; w < 8; ++w) tot += wsum[w];
+    base_off += tot;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    cnt_out[b] = base_on;
+    if (total_out) atomicAdd(total_out, base_on);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Spatial masker: one warp per (b, cell).  Pool the cell (adaptive_avg_pool2d
+// region: [floor(i*H/S), ceil((i+1)*H/S)) ), then the 2g-row 1x1 conv.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) masker_spatial_kernel(
+    const __half* __restrict__ x, int B, int H, int W, int C, const float* __restrict__ w,
+    const float* __restrict__ bias, int g, int S, float* __restrict__ logits_out,
+    uint8_t* __restrict__ mask_out, int* __restrict__ total_out) {
+  const int lane = threadIdx.x & 31;
+  const long long cell = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (cell >= (long long)B * S * S) return;
+  const int b = (int)(cell / (S * S));
+  const int ci = (int)(cell % (S * S)) / S, cj = (int)(cell % S);
+  int y0, y1, x0, x1;
+  if (S >= H) { y0 = ci; y1 = ci + 1; x0 = cj; x1 = cj + 1; }
+  else {
+    y0 = (ci * H) / S; y1 = ((ci + 1) * H + S - 1) / S;
+    x0 = (cj * W) / S; x1 = ((cj + 1) * W + S - 1) / S;
+  }
+  const float area = (float)((y1 - y0) * (x1 - x0));
+  float keep[4], drop[4];  // g <= 4 handled in registers; larger g loops below
+  // accumulate logits lane-partial: sum_c w[o][c] * pooled[c]
+  float part[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) part[i] = 0.f;
+  const int G2 = 2 * g;
+  for (int c0 = lane * 8; c0 < C; c0 += 256) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int yy = y0; yy < y1; ++yy)
+      for (int xx = x0; xx < x1; ++xx) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)b * H + yy) * W + xx) * C + c0));
+        const __half2* hh = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __half22float2(hh[i]);
+          acc[2 * i] += f.x;
+          acc[2 * i + 1] += f.y;
+        }
+      }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = (S >= H) ? acc[i] : acc[i] / area;
+    for (int o = 0; o < G2 && o < 8; ++o) {
+      const float* wr = w + (size_t)o * C + c0;
+      float t = part[o];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t = fmaf(wr[i], acc[i], t);
+      part[o] = t;
+    }
+  }
+  (void)keep; (void)drop;
+  int ones = 0;
+  for (int o = 0; o < G2 && o < 8; ++o) part[o] = warp_sum(part[o]) + bias[o];
+  if (lane == 0) {
+    for (int o = 0; o < G2; ++o)
+      if (logits_out) logits_out[(((size_t)b * G2 + o) * S + ci) * S + cj] = part[o];
+    for (int q = 0; q < g; ++q) {
+      const int f = part[q] >= part[g + q] ? 1 : 0;
+      mask_out[(((size_t)b * g + q) * S + ci) * S + cj] = (uint8_t)f;
+      ones += f;
+    }
+    if (total_out && ones) atomicAdd(total_out, ones);
+  }
+}
+
+__global__ void resize_mask_kernel(const uint8_t* __restrict__ m, int B, int g, int S, int Ho,
+                                   uint8_t* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n = (long long)B * g * Ho * Ho;
+  if (i >= n) return;
+  const int ox = (int)(i % Ho), oy = (int)((i / Ho) % Ho);
+  const long long bg = i / ((long long)Ho * Ho);
+  const int sy = (oy * S) / Ho, sx = (ox * S) / Ho;       // floor(dst * in / out)
+  out[i] = m[(bg * S + sy) * S + sx];
+}
+
+// ExpandMask: out[b,*,y,x] = OR over groups and window of zero-inserted mask.
+__global__ void expand_mask_kernel(const uint8_t* __restrict__ m, int B, int g, int H, int W,
+                                   int stride, int pad, uint8_t* __restrict__ out,
+                                   int* __restrict__ total_out) {
+  const int Ho = H * stride, Wo = W * stride;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n = (long long)B * Ho * Wo;
+  int f = 0;
+  if (i < n) {
+    const int ox = (int)(i % Wo), oy = (int)((i / Wo) % Ho);
+    const int b = (int)(i / ((long long)Ho * Wo));
+    for (int dy = -pad; dy <= pad && !f; ++dy)
+      for (int dx = -pad; dx <= pad && !f; ++dx) {
+        const int uy = oy + dy, ux = ox + dx;
+        if (uy < 0 || ux < 0 || uy >= Ho || ux >= Wo) continue;
+        if (uy % stride || ux % stride) continue;      // zero-inserted positions
+        for (int q = 0; q < g; ++q)
+          if (m[(((size_t)b * g + q) * H + uy / stride) * W + ux / stride]) { f = 1; break; }
+      }
+    for (int q = 0; q < g; ++q) out[(((size_t)b * g + q) * Ho + oy) * Wo + ox] = (uint8_t)f;
+  }
+  // count ones (x g groups, as the reference's mean runs over [B,g,H,W])
+  const unsigned bal = __ballot_sync(0xffffffffu, f);
+  if ((threadIdx.x & 31) == 0 && bal && total_out) atomicAdd(total_out, __popc(bal) * g);
+}
+
+// Ordered compaction of active rows.  Pass A: per-CTA counts (2048 items each);
+// pass B: one CTA scans the counts; pass C: ordered scatter.
+constexpr int kCompactItems = 2048;
+__device__ __forceinline__ int row_active(const uint8_t* gate, int g, int HW, long long i) {
+  if (g == 1) return gate[i] != 0;
+  const long long b = i / HW, p = i % HW;
+  for (int q = 0; q < g; ++q)
+    if (gate[(b * g + q) * HW + p]) return 1;
+  return 0;
+}
+__global__ void __launch_bounds__(256) compact_count_kernel(const uint8_t* gate, int g, int HW, long long n,
+                                                            int* block_ws) {
+  __shared__ int ws[8];
+  int c = 0;
+  const long long base = (long long)blockIdx.x * kCompactItems;
+  for (int k = 0; k < kCompactItems / 256; ++k) {
+    const long long i = base + k * 256 + threadIdx.x;
+    c += (i < n) ? row_active(gate, g, HW, i) : 0;
+  }
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < 8; ++w) t += ws[w];
+    block_ws[blockIdx.x] = t;
+  }
+}
+__global__ void compact_scan_kernel(int* block_ws, int nblk, int* count_out) {
+  // single thread: nblk is small (<= B*HW/2048)
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int run = 0;
+    for (int i = 0; i < nblk; ++i) { const int t = block_ws[i]; block_ws[i] = run; run += t; }
+    count_out[0] = run;
+  }
+}
+__global__ void __launch_bounds__(256) compact_write_kernel(const uint8_t* gate, int g, int HW, long long n,
+                                                            const int* block_ws, int* rows_out) {
+  __shared__ int ws[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int run = block_ws[blockIdx.x];
+  const long long base = (long long)blockIdx.x * kCompactItems;
+  for (int k = 0; k < kCompactItems / 256; ++k) {
+    const long long i = base + k * 256 + threadIdx.x;
+    const int f = (i < n) ? row_active(gate, g, HW, i) : 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) ws[warp] = __popc(bal);
+    __syncthreads();
+    int off = run;
+    for (int w = 0; w < warp; ++w) off += ws[w];
+    if (f) rows_out[off + __popc(bal & ((1u << lane) - 1))] = (int)i;
+    for (int w = 0; w < 8; ++w) run += ws[w];
+    __syncthreads();
+  }
+}
+
+}  // namespace laud
+
+using namespace laud;
+
+static size_t decide_smem(int C, int hidden, int G) {
+  return sizeof(float) * ((size_t)C + (hidden > 0 ? hidden : 1) + 2 * (size_t)G) + sizeof(int) * ((size_t)G + 64);
+}
+
+extern "C" int laud_global_avg_pool(const void* x, int B, int HW, int C, int ldx, float* partial_ws,
+                                    float* pooled_out, void* stream) {
+  LAUD_REQUIRE(x && partial_ws && pooled_out, "laud_global_avg_pool: null pointer");
+  LAUD_REQUIRE(B > 0 && HW > 0 && C > 0 && C % 8 == 0 && ldx % 8 == 0 && ldx >= C,
+               "laud_global_avg_pool: need C %% 8 == 0 and ldx %% 8 == 0 (C=%d ldx=%d)", C, ldx);
+  cudaStream_t s = (cudaStream_t)stream;
+  gap_partial_kernel<<<dim3(LAUD_GAP_SPLITS, B), 256, 0, s>>>((const __half*)x, HW, C, ldx, partial_ws);
+  if (int e = check_launch("gap_partial_kernel")) return e;
+  gap_final_kernel<<<dim3((C + 255) / 256, B), 256, 0, s>>>(partial_ws, C, LAUD_GAP_SPLITS, HW, pooled_out);
+  return check_launch("gap_final_kernel");
+}
+
+static int launch_decide(const float* partial, const float* pooled_in, int B, int HW, int C, int layers,
+                         const float* w1, const float* b1, int hidden, const float* w2, const float* b2,
+                         int G, float* pooled_out, float* logits_out, uint8_t* mask_out, int32_t* idx_out,
+                         int32_t* cnt_out, int32_t* total_out, cudaStream_t s) {
+  LAUD_REQUIRE(layers == 1 || layers == 2, "channel masker: layers must be 1 or 2 (got %d)", layers);
+  LAUD_REQUIRE(w1 && b1 && mask_out && idx_out && cnt_out, "channel masker: null pointer");
+  LAUD_REQUIRE(layers == 1 || (w2 && b2 && hidden > 0), "channel masker: 2-layer MLP needs w2,b2,hidden");
+  LAUD_REQUIRE(G > 0, "channel masker: G must be positive");
+  const size_t smem = decide_smem(C, layers == 2 ? hidden : 0, G);
+  LAUD_REQUIRE(smem <= 200 * 1024, "channel masker: C/G too large for shared memory");
+  if (smem > 48 * 1024)
+    LAUD_CUDA(cudaFuncSetAttribute(masker_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  masker_decide_kernel<<<B, 256, smem, s>>>(partial, pooled_in, C, LAUD_GAP_SPLITS, HW, layers, w1, b1,
+                                            layers == 2 ? hidden : 0, w2, b2, G, pooled_out, logits_out,
+                                            mask_out, idx_out, cnt_out, total_out);
+  return check_launch("masker_decide_kernel");
+}
+
+extern "C" int laud_masker_channel_mlp(const void* x, int B, int HW, int C, int layers, const float* w1,
+                                       const float* b1, int hidden, const float* w2, const float* b2, int G,
+                                       float* partial_ws, float* pooled_out, float* logits_out,
+                                       uint8_t* mask_out, int32_t* idx_out, int32_t* cnt_out,
+                                       int32_t* total_out, void* stream) {
+  LAUD_REQUIRE(x && partial_ws, "laud_masker_channel_mlp: null pointer");
+  LAUD_REQUIRE(B > 0 && HW > 0 && C > 0 && C % 8 == 0, "laud_masker_channel_mlp: need C %% 8 == 0 (C=%d)", C);
+  cudaStream_t s = (cudaStream_t)stream;
+  gap_partial_kernel<<<dim3(LAUD_GAP_SPLITS, B), 256, 0, s>>>((const __half*)x, HW, C, C, partial_ws);
+  if (int e = check_launch("gap_partial_kernel")) return e;
+  return launch_decide(partial_ws, nullptr, B, HW, C, layers, w1, b1, hidden, w2, b2, G, pooled_out,
+                       logits_out, mask_out, idx_out, cnt_out, total_out, s);
+}
+
+extern "C" int laud_masker_channel_from_pooled(const float* pooled, int B, int C, int layers, const float* w1,
+                                               const float* b1, int hidden, const float* w2, const float* b2,
+                                               int G, float* logits_out, uint8_t* mask_out, int32_t* idx_out,
+                                               int32_t* cnt_out, int32_t* total_out, void* stream) {
+  LAUD_REQUIRE(pooled && B > 0 && C > 0, "laud_masker_channel_from_pooled: bad arguments");
+  return launch_decide(nullptr, pooled, B, 1, C, layers, w1, b1, hidden, w2, b2, G, nullptr, logits_out,
+                       mask_out, idx_out, cnt_out, total_out, (cudaStream_t)stream);
+}
+
+extern "C" int laud_masker_spatial(const void* x, int B, int H, int W, int C, const float* w, const float* bias,
+                                   int g, int S, float* logits_out, uint8_t* mask_out, int32_t* total_out,
+                                   void* stream) {
+  LAUD_REQUIRE(x && w && bias && mask_out, "laud_masker_spatial: null pointer");
+  LAUD_REQUIRE(B > 0 && H > 0 && W > 0 && C % 8 == 0 && S > 0, "laud_masker_spatial: bad shape (C=%d S=%d)", C, S);
+  LAUD_REQUIRE(g >= 1 && g <= 4, "laud_masker_spatial: mask_channel_group must be in [1,4] (got %d)", g);
+  LAUD_REQUIRE(S <= H, "laud_masker_spatial: mask_size %d exceeds feature size %d", S, H);
+  const long long cells = (long long)B * S * S;
+  const int grid = (int)((cells + 7) / 8);
+  masker_spatial_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)x, B, H, W, C, w, bias, g, S,
+                                                                logits_out, mask_out, total_out);
+  return check_launch("masker_spatial_kernel");
+}
+
+extern "C" int laud_resize_mask_nearest(const uint8_t* mask, int B, int g, int S, int H_out, uint8_t* out,
+                                        void* stream) {
+  LAUD_REQUIRE(mask && out && B > 0 && g > 0 && S > 0 && H_out > 0, "laud_resize_mask_nearest: bad arguments");
+  const long long n = (long long)B * g * H_out * H_out;
+  resize_mask_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(mask, B, g, S, H_out, out);
+  return check_launch("resize_mask_kernel");
+}
+
+extern "C" int laud_expand_mask(const uint8_t* mask, int B, int g, int H, int W, int stride, int padding,
+                                uint8_t* out, int32_t* total_out, void* stream) {
+  LAUD_REQUIRE(mask && out && B > 0 && g > 0 && H > 0 && W > 0, "laud_expand_mask: bad arguments");
+  LAUD_REQUIRE(stride >= 1 && padding >= 0 && padding <= 3, "laud_expand_mask: bad stride/padding");
+  const long long n = (long long)B * H * stride * W * stride;
+  expand_mask_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(mask, B, g, H, W, stride, padding,
+                                                                              out, total_out);
+  return check_launch("expand_mask_kernel");
+}
+
+extern "C" int laud_compact_rows(const uint8_t* gate, int B, int g, int HW, int32_t* rows_out,
+                                 int32_t* count_out, int32_t* block_ws, void* stream) {
+  LAUD_REQUIRE(gate && rows_out && count_out && block_ws && B > 0 && g > 0 && HW > 0,
+               "laud_compact_rows: bad arguments");
+  const long long n = (long long)B * HW;
+  LAUD_REQUIRE(n < (1ll << 31), "laud_compact_rows: too many rows");
+  const int nblk = (int)((n + kCompactItems - 1) / kCompactItems);
+  cudaStream_t s = (cudaStream_t)stream;
+  compact_count_kernel<<<nblk, 256, 0, s>>>(gate, g, HW, n, block_ws);
+  if (int e = check_launch("compact_count_kernel")) return e;
+  compact_scan_kernel<<<1, 32, 0, s>>>(block_ws, nblk, count_out);
+  if (int e = check_launch("compact_scan_kernel")) return e;
+  compact_write_kernel<<<nblk, 256, 0, s>>>(gate, g, HW, n, block_ws, rows_out);
+  return check_launch("compact_write_kernel");
+}

@@ -1,0 +1,354 @@
+// Network ends and bookkeeping kernels: fused stem (conv7x7/2+BN+ReLU+maxpool),
+// head (avgpool+fc), H1 constant tables for channel skipping, layout helpers and
+// the forward-statistics kernel.
+#include "laud_common.cuh"
+
+namespace laud {
+
+// ---------------------------------------------------------------------------
+// Stem.  One CTA = one sample x a 4x8 tile of POOLED outputs.  It needs the
+// 9x17 conv outputs around it, which need a 23x39 input patch (x3 channels).
+// Restates laud_resnet.py:317-324 (conv1 -> bn1 -> relu -> maxpool).
+// ---------------------------------------------------------------------------
+constexpr int ST_PH = 4, ST_PW = 8;                 // pooled tile
+constexpr int ST_CH = 2 * ST_PH + 1, ST_CW = 2 * ST_PW + 1;   // conv tile 9x17
+constexpr int ST_IH = 2 * ST_CH + 5, ST_IW = 2 * ST_CW + 5;   // input tile 23x39
+constexpr int ST_IWP = ST_IW + 1;
+
+__global__ void __launch_bounds__(256) stem_kernel(const __half* __restrict__ x, int H, int W,
+                                                   const __half* __restrict__ w, int C0,
+                                                   const float* __restrict__ scale,
+                                                   const float* __restrict__ shift,
+                                                   __half* __restrict__ y) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* s_in = reinterpret_cast<float*>(smem_raw);                         // [3][ST_IH][ST_IWP]
+  __half* s_w = reinterpret_cast<__half*>(s_in + 3 * ST_IH * ST_IWP);       // [147][C0]
+  __half* s_c = s_w + 147 * C0;                                             // [ST_CH*ST_CW][C0]
+  const int Hc = H / 2, Wc = W / 2, Hp = Hc / 2, Wp = Wc / 2;
+  const int b = blockIdx.z;
+  const int py0 = blockIdx.y * ST_PH, px0 = blockIdx.x * ST_PW;
+  const int cy0 = 2 * py0 - 1, cx0 = 2 * px0 - 1;       // conv-tile origin (may be -1)
+  const int iy0 = 2 * cy0 - 3, ix0 = 2 * cx0 - 3;       // input-tile origin
+  const int tid = threadIdx.x;
+
+  for (int i = tid; i < 3 * ST_IH * ST_IW; i += 256) {
+    const int c = i / (ST_IH * ST_IW), r = (i / ST_IW) % ST_IH, q = i % ST_IW;
+    const int iy = iy0 + r, ix = ix0 + q;
+    float v = 0.f;
+    if (iy >= 0 && ix >= 0 && iy < H && ix < W) v = __half2float(x[(((size_t)b * 3 + c) * H + iy) * W + ix]);
+    s_in[(c * ST_IH + r) * ST_IWP + q] = v;
+  }
+  for (int i = tid; i < 147 * C0; i += 256) {
+    const int o = i / 147, t = i % 147;               // global layout [C0][3][7][7]
+    s_w[t * C0 + o] = w[i];
+  }
+  __syncthreads();
+
+  const int ncg = C0 / 8;
+  const int items = ST_CH * ST_CW * ncg;
+  for (int it = tid; it < items; it += 256) {
+    const int cg = it / (ST_CH * ST_CW), pxl = it % (ST_CH * ST_CW);
+    const int r = pxl / ST_CW, q = pxl % ST_CW;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int c = 0; c < 3; ++c)
+      for (int ky = 0; ky < 7; ++ky) {
+        const float* irow = s_in + (c * ST_IH + 2 * r + ky) * ST_IWP + 2 * q;
+        const __half* wrow = s_w + ((c * 7 + ky) * 7) * C0 + cg * 8;
+#pragma unroll
+        for (int kx = 0; kx < 7; ++kx) {
+          const float v = irow[kx];
+          const uint4 wq = *reinterpret_cast<const uint4*>(wrow + kx * C0);
+          const __half2* wh = reinterpret_cast<const __half2*>(&wq);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(wh[e]);
+            acc[2 * e] = fmaf(v, f.x, acc[2 * e]);
+            acc[2 * e + 1] = fmaf(v, f.y, acc[2 * e + 1]);
+          }
+        }
+      }
+    const int cy = cy0 + r, cx = cx0 + q;
+    const bool inside = cy >= 0 && cx >= 0 && cy < Hc && cx < Wc;
+    __align__(16) __half o8[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int ch = cg * 8 + e;
+      // outside the conv output: 0 is neutral for the max of post-ReLU values
+      const float v = inside ? fmaxf(acc[e] * scale[ch] + shift[ch], 0.f) : 0.f;
+      o8[e] = __float2half(v);
+    }
+    *reinterpret_cast<uint4*>(s_c + (size_t)pxl * C0 + cg * 8) = *reinterpret_cast<uint4*>(o8);
+  }
+  __syncthreads();
+
+  for (int it = tid; it < ST_PH * ST_PW * ncg; it += 256) {
+    const int cg = it % ncg, pp = it / ncg;
+    const int pr = pp / ST_PW, pq = pp % ST_PW;
+    const int py = py0 + pr, px = px0 + pq;
+    if (py >= Hp || px >= Wp) continue;
+    __half2 m[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) m[e] = __float2half2_rn(0.f);
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const uint4 q4 = *reinterpret_cast<const uint4*>(s_c + (size_t)((2 * pr + dy) * ST_CW + 2 * pq + dx) * C0 + cg * 8);
+        const __half2* h = reinterpret_cast<const __half2*>(&q4);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) m[e] = __hmax2(m[e], h[e]);
+      }
+    *reinterpret_cast<uint4*>(y + (((size_t)b * Hp + py) * Wp + px) * C0 + cg * 8) = *reinterpret_cast<uint4*>(m);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Head fc: CTA = 4 samples x 64 classes; pooled features of the 4 samples in smem.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) head_fc_kernel(const float* __restrict__ pooled, int B, int C,
+                                                      const __half* __restrict__ w,
+                                                      const float* __restrict__ bias, int n_cls,
+                                                      float* __restrict__ logits) {
+  extern __shared__ float sp[];   // [4][C]
+  const int b0 = blockIdx.y * 4;
+  for (int i = threadIdx.x; i < 4 * C; i += 256) {
+    const int bb = b0 + i / C;
+    sp[i] = bb < B ? pooled[(size_t)bb * C + i % C] : 0.f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = 0; k < 8; ++k) {
+    const int o = blockIdx.x * 64 + warp * 8 + k;
+    if (o >= n_cls) break;
+    const __half* wr = w + (size_t)o * C;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = lane * 8; c < C; c += 256) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(wr + c));
+      const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(h[e]);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          acc[s] = fmaf(f.x, sp[s * C + c + 2 * e], acc[s]);
+          acc[s] = fmaf(f.y, sp[s * C + c + 2 * e + 1], acc[s]);
+        }
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < 4; ++s) acc[s] = warp_sum(acc[s]);
+    if (lane == 0)
+      for (int s = 0; s < 4; ++s)
+        if (b0 + s < B) logits[(size_t)(b0 + s) * n_cls + o] = acc[s] + bias[o];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// H1 constants (see laud_b200.h).  One warp per output unit.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) consts_conv2_kernel(const __half* __restrict__ w2, int width,
+                                                           const float* __restrict__ shift1,
+                                                           const int* __restrict__ idx,
+                                                           const int* __restrict__ cnt, int G, int gran,
+                                                           float* __restrict__ pre_bias2) {
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);     // compact output channel
+  const int na = cnt[b];
+  if (j >= na * gran) return;
+  const int* il = idx + (size_t)b * G;
+  const int o = il[j / gran] * gran + j % gran;
+  const int nm = (G - na) * gran;                         // masked channels
+  float T[9];
+  for (int tap = 0; tap < 9; ++tap) {
+    const __half* wr = w2 + ((size_t)o * 9 + tap) * width;
+    float t = 0.f;
+    for (int mi = lane; mi < nm; mi += 32) {
+      const int k = il[na + mi / gran] * gran + mi % gran;
+      t = fmaf(fmaxf(shift1[k], 0.f), __half2float(wr[k]), t);
+    }
+    T[tap] = warp_sum(t);
+  }
+  if (lane < 16) {
+    const int rc = lane >> 2, cc = lane & 3;
+    float s = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      if ((dy == 0 && (rc & 1)) || (dy == 2 && (rc & 2))) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        if ((dx == 0 && (cc & 1)) || (dx == 2 && (cc & 2))) continue;
+        s += T[dy * 3 + dx];
+      }
+    }
+    pre_bias2[((size_t)b * 16 + lane) * width + j] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256) consts_conv3_kernel(const __half* __restrict__ w3, int width, int C_out,
+                                                           const float* __restrict__ shift2,
+                                                           const int* __restrict__ idx,
+                                                           const int* __restrict__ cnt, int G, int gran,
+                                                           float* __restrict__ pre_bias3) {
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int o = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (o >= C_out) return;
+  const int na = cnt[b];
+  const int* il = idx + (size_t)b * G;
+  const int nm = (G - na) * gran;
+  const __half* wr = w3 + (size_t)o * width;
+  float t = 0.f;
+  for (int mi = lane; mi < nm; mi += 32) {
+    const int k = il[na + mi / gran] * gran + mi % gran;
+    t = fmaf(fmaxf(shift2[k], 0.f), __half2float(wr[k]), t);
+  }
+  t = warp_sum(t);
+  if (lane == 0) pre_bias3[(size_t)b * C_out + o] = t;
+}
+
+// ---------------------------------------------------------------------------
+// layout helpers
+// ---------------------------------------------------------------------------
+__global__ void nchw_to_nhwc_kernel(const void* src, int is_f32, int B, int C, int H, int W, __half* dst, int ldd) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n = (long long)B * C * H * W;
+  if (i >= n) return;
+  const int c = (int)(i % C);
+  const long long p = i / C;             // b*H*W + y*W + x
+  const long long hw = (long long)H * W;
+  const long long b = p / hw, q = p % hw;
+  const long long s = (b * C + c) * hw + q;
+  const float v = is_f32 ? reinterpret_cast<const float*>(src)[s] : __half2float(reinterpret_cast<const __half*>(src)[s]);
+  dst[p * ldd + c] = __float2half(v);
+}
+__global__ void nhwc_to_nchw_kernel(const __half* src, int lds, int B, int C, int H, int W, float* dst) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n = (long long)B * C * H * W;
+  if (i >= n) return;
+  const long long hw = (long long)H * W;
+  const long long q = i % hw, bc = i / hw;
+  const long long b = bc / C, c = bc % C;
+  dst[i] = __half2float(src[(b * hw + q) * lds + c]);
+}
+
+// ---------------------------------------------------------------------------
+// Forward statistics in the reference's evaluation order (single thread).
+// consts[i] = {m_chan, m_spat, c1hw, c2hw, c3hw, ds, n_c, n_3, n_2, n_1, flags, extra}
+// ---------------------------------------------------------------------------
+__global__ void forward_stats_kernel(const int* __restrict__ counts, const long long* __restrict__ consts,
+                                     int n_blocks, long long stem_flops, long long pool_flops,
+                                     long long fc_flops, float* __restrict__ out) {
+  if (threadIdx.x || blockIdx.x) return;
+  float flops = 0.f;
+  bool flops_is_tensor = false;
+  long long flops_int = stem_flops;
+  for (int i = 0; i < n_blocks; ++i) {
+    const long long* k = consts + (size_t)i * 12;
+    const int* c = counts + (size_t)i * 4;
+    const bool use_c = k[10] & 1, use_s = k[10] & 2;
+    const float rc = use_c ? __fdiv_rn((float)c[0], (float)k[6]) : 1.0f;
+    const float r3 = use_s ? __fdiv_rn((float)c[1], (float)k[7]) : 1.0f;
+    const float r2 = use_s ? __fdiv_rn((float)c[2], (float)k[8]) : 1.0f;
+    const float r1 = use_s ? __fdiv_rn((float)c[3], (float)k[9]) : 1.0f;
+    const long long m = k[0] + k[1];
+    float sparse = __fadd_rn((float)m, __fmul_rn(__fmul_rn((float)k[2], rc), r1));
+    sparse = __fadd_rn(sparse, __fmul_rn(__fmul_rn((float)k[3], __fmul_rn(rc, rc)), r2));
+    sparse = __fadd_rn(sparse, __fmul_rn(__fmul_rn((float)k[4], rc), r3));
+    long long dense = m + k[2] + k[3] + k[4];
+    if (k[5]) {
+      sparse = __fadd_rn(sparse, (float)k[5]);
+      dense += k[5];
+    }
+    if (!flops_is_tensor) {
+      flops = __fadd_rn((float)flops_int, sparse);
+      flops_is_tensor = true;
+    } else {
+      flops = __fadd_rn(flops, sparse);
+    }
+    float* o = out + (size_t)i * 5;
+    o[0] = r3; o[1] = r2; o[2] = r1; o[3] = rc;
+    o[4] = __fdiv_rn(sparse, (float)dense);
+  }
+  // avgpool + fc flops are added one at a time as python ints (laud_resnet.py:350,356)
+  flops = __fadd_rn(flops, (float)pool_flops);
+  flops = __fadd_rn(flops, (float)fc_flops);
+  out[(size_t)n_blocks * 5] = flops;
+}
+
+}  // namespace laud
+
+using namespace laud;
+
+extern "C" int laud_stem_forward(const void* x, int B, int H, int W, const void* w, int C0, const float* scale,
+                                 const float* shift, void* y, void* stream) {
+  LAUD_REQUIRE(x && w && scale && shift && y, "laud_stem_forward: null pointer");
+  LAUD_REQUIRE(B > 0 && H % 4 == 0 && W % 4 == 0 && C0 % 8 == 0, "laud_stem_forward: need H,W %% 4 == 0, C0 %% 8 == 0");
+  const int Hp = H / 4, Wp = W / 4;
+  const size_t smem = sizeof(float) * 3 * ST_IH * ST_IWP + sizeof(__half) * (147 + ST_CH * ST_CW) * (size_t)C0;
+  LAUD_REQUIRE(smem <= 200 * 1024, "laud_stem_forward: stem width %d too large", C0);
+  LAUD_CUDA(cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((Wp + ST_PW - 1) / ST_PW, (Hp + ST_PH - 1) / ST_PH, B);
+  stem_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const __half*)x, H, W, (const __half*)w, C0, scale, shift,
+                                                         (__half*)y);
+  return check_launch("stem_kernel");
+}
+
+extern "C" int laud_head_forward(const void* x, int B, int HW, int C, const void* w, const float* bias, int n_cls,
+                                 float* pooled_ws, float* logits, void* stream) {
+  LAUD_REQUIRE(x && w && bias && pooled_ws && logits, "laud_head_forward: null pointer");
+  LAUD_REQUIRE(C % 8 == 0 && C <= 8192, "laud_head_forward: need C %% 8 == 0 and C <= 8192 (C=%d)", C);
+  // pooled_ws: [B, LAUD_GAP_SPLITS + 1, C]: partial sums followed by the pooled features
+  float* pooled = pooled_ws + (size_t)B * LAUD_GAP_SPLITS * C;
+  if (int e = laud_global_avg_pool(x, B, HW, C, C, pooled_ws, pooled, stream)) return e;
+  const size_t smem = sizeof(float) * 4 * (size_t)C;
+  if (smem > 48 * 1024)
+    LAUD_CUDA(cudaFuncSetAttribute(head_fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((n_cls + 63) / 64, (B + 3) / 4);
+  head_fc_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(pooled, B, C, (const __half*)w, bias, n_cls, logits);
+  return check_launch("head_fc_kernel");
+}
+
+extern "C" int laud_channel_consts(const void* w2, const void* w3, int width, int C_out, const float* shift1,
+                                   const float* shift2, const int32_t* idx, const int32_t* cnt, int B, int G,
+                                   int gran, int H_in, int W_in, int H_out, int W_out, int stride,
+                                   float* pre_bias2, float* pre_bias3, void* stream) {
+  (void)H_in; (void)W_in; (void)H_out; (void)W_out; (void)stride;
+  LAUD_REQUIRE(w2 && w3 && shift1 && shift2 && idx && cnt && pre_bias2 && pre_bias3, "laud_channel_consts: null pointer");
+  LAUD_REQUIRE(G * gran == width, "laud_channel_consts: G*gran (%d*%d) != width %d", G, gran, width);
+  cudaStream_t s = (cudaStream_t)stream;
+  consts_conv2_kernel<<<dim3((width + 7) / 8, B), 256, 0, s>>>((const __half*)w2, width, shift1, idx, cnt, G, gran,
+                                                             pre_bias2);
+  if (int e = check_launch("consts_conv2_kernel")) return e;
+  consts_conv3_kernel<<<dim3((C_out + 7) / 8, B), 256, 0, s>>>((const __half*)w3, width, C_out, shift2, idx, cnt, G,
+                                                              gran, pre_bias3);
+  return check_launch("consts_conv3_kernel");
+}
+
+extern "C" int laud_nchw_to_nhwc_f16(const void* src, int src_is_f32, int B, int C, int H, int W, void* dst, int ldd,
+                                     void* stream) {
+  LAUD_REQUIRE(src && dst && ldd >= C, "laud_nchw_to_nhwc_f16: bad arguments");
+  const long long n = (long long)B * C * H * W;
+  nchw_to_nhwc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, src_is_f32, B, C, H, W,
+                                                                                    (__half*)dst, ldd);
+  return check_launch("nchw_to_nhwc_kernel");
+}
+
+extern "C" int laud_nhwc_f16_to_nchw_f32(const void* src, int lds, int B, int C, int H, int W, float* dst,
+                                         void* stream) {
+  LAUD_REQUIRE(src && dst && lds >= C, "laud_nhwc_f16_to_nchw_f32: bad arguments");
+  const long long n = (long long)B * C * H * W;
+  nhwc_to_nchw_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __half*)src, lds, B, C, H,
+                                                                                    W, dst);
+  return check_launch("nhwc_to_nchw_kernel");
+}
+
+extern "C" int laud_forward_stats(const int32_t* counts, const int64_t* consts, int n_blocks, int64_t stem_flops,
+                                  int64_t pool_flops, int64_t fc_flops, float* out, void* stream) {
+  LAUD_REQUIRE(counts && consts && out && n_blocks > 0, "laud_forward_stats: bad arguments");
+  forward_stats_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(counts, (const long long*)consts, n_blocks, stem_flops,
+                                                           pool_flops, fc_flops, out);
+  return check_launch("forward_stats_kernel");
+}

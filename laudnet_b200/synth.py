@@ -1,0 +1,229 @@
+"""Deterministic synthetic weights / inputs for the LAUD hot path.
+
+There is no network access for the model-zoo checkpoints (reference
+README.md:61-64), so parity tests and the benchmark run on seeded synthetic
+parameters.  Everything here is numpy `RandomState`-based so that the build
+container (where the golden fixtures are generated from the reference) and the
+GPU box produce bit-identical parameters from the same seed, independent of
+torch's RNG implementation.
+
+Recipe:
+  * backbone convs: Kaiming-normal fan_out, as the reference initialises them
+    (imagenet_classification/models/laud_resnet.py:255-260);
+  * BatchNorm: gamma~N(1,.2), beta~N(0,.5), running_mean~N(0,.5),
+    running_var~U(.5,2) so the mask-before-BN constants relu(bn(0)) are
+    non-trivial;
+  * masker layers: torch's default Linear/Conv init (U(+-1/sqrt(fan_in)));
+    the final 2-way bias is then *calibrated* (see `calibrate_two_way_bias`) so
+    the eval-mode activation rate hits the requested target - random init
+    alone gives density ~1.0 because of the +2/-2 (+5/0) keep bias
+    (imagenet_classification/models/utils.py:42-43,107-108).
+"""
+from __future__ import annotations
+
+import zlib
+from typing import Dict, Mapping, Tuple
+
+import numpy as np
+import torch
+
+
+def _rng(seed: int, name: str) -> np.random.RandomState:
+    return np.random.RandomState((seed * 1000003 + zlib.crc32(name.encode())) % (2 ** 32))
+
+
+def synth_tensor(name: str, shape: Tuple[int, ...], seed: int) -> torch.Tensor:
+    """One parameter/buffer, chosen by its state_dict key."""
+    r = _rng(seed, name)
+    leaf = name.rsplit(".", 1)[-1]
+    is_masker = "masker" in name
+    if leaf == "num_batches_tracked":
+        return torch.zeros((), dtype=torch.long)
+    if leaf == "running_mean":
+        a = r.standard_normal(shape) * 0.5
+    elif leaf == "running_var":
+        a = r.uniform(0.5, 2.0, size=shape)
+    elif leaf == "weight" and len(shape) == 1:          # BN gamma
+        a = 1.0 + 0.2 * r.standard_normal(shape)
+    elif leaf == "bias" and not is_masker and name != "fc.bias" and ".se." not in name:   # BN beta
+        a = 0.5 * r.standard_normal(shape)
+    elif leaf == "weight" and len(shape) == 4 and not is_masker:
+        fan_out = shape[0] * shape[2] * shape[3]
+        a = r.standard_normal(shape) * np.sqrt(2.0 / fan_out)
+    elif leaf == "weight":                              # Linear / masker conv
+        fan_in = int(np.prod(shape[1:]))
+        a = r.uniform(-1.0, 1.0, size=shape) / np.sqrt(fan_in)
+    else:                                               # Linear / masker / SE bias
+        a = r.uniform(-1.0, 1.0, size=shape) * 0.1
+    return torch.from_numpy(np.asarray(a, dtype=np.float32).reshape(shape))
+
+
+def synth_state_dict(shapes: Mapping[str, Tuple[int, ...]], seed: int,
+                     fp16_weights: bool = True) -> Dict[str, torch.Tensor]:
+    """Fill every key of `shapes` (name -> shape).  With `fp16_weights` the
+    convolution / fc weights are rounded to fp16-representable values (kept in
+    fp32), which is the model-preparation step of the CUDA path: the oracle is
+    then fed exactly the weights the tensor cores see."""
+    sd = {}
+    for name, shape in shapes.items():
+        t = synth_tensor(name, tuple(shape), seed)
+        if fp16_weights and t.dtype == torch.float32 and t.dim() in (2, 4) and "masker" not in name:
+            t = t.half().float()
+        sd[name] = t
+    return sd
+
+
+def synth_images(batch: int, size: int, seed: int, start: int = 0) -> torch.Tensor:
+    """fp16-representable images with per-sample gain/offset so that pooled
+    features (and therefore gating decisions) differ between samples.
+    Sample i depends only on (seed, start+i): shards of a batch agree with the
+    unsharded batch."""
+    out = np.empty((batch, 3, size, size), dtype=np.float32)
+    for i in range(batch):
+        r = np.random.RandomState((seed * 7919 + 104729 * (start + i) + 1) % (2 ** 32))
+        gain = r.uniform(0.5, 1.5)
+        offs = r.standard_normal((3, 1, 1)) * 0.5
+        yy, xx = np.meshgrid(np.linspace(-1, 1, size), np.linspace(-1, 1, size), indexing="ij")
+        tilt = r.standard_normal((3, 1, 1)) * yy[None] + r.standard_normal((3, 1, 1)) * xx[None]
+        out[i] = gain * r.standard_normal((3, size, size)) + offs + 0.5 * tilt
+    return torch.from_numpy(out).half().float()
+
+
+def calibrate_two_way_bias(margin: torch.Tensor, rate: float, per_group: bool) -> torch.Tensor:
+    """Bias shift that makes a 2-way gate fire at `rate`.
+
+    `margin` is keep-logit minus drop-logit, shape [N, G] (N = samples or
+    samples*positions).  Returns delta[G] to SUBTRACT from the keep bias so
+    that a fraction `rate` of the margins stay >= 0.  The threshold sits midway
+    between two order statistics, so no calibration sample lands on a tie.
+    """
+    m = margin.detach().double().cpu()
+    if not per_group:
+        m = m.reshape(-1, 1)
+    n = m.shape[0]
+    k = int(round((1.0 - rate) * n))            # number of samples to switch off
+    srt, _ = torch.sort(m, dim=0)
+    if k <= 0:
+        thr = srt[0] - 1.0
+    elif k >= n:
+        thr = srt[-1] + 1.0
+    else:
+        thr = 0.5 * (srt[k - 1] + srt[k])
+    thr = thr.float()
+    return thr if per_group else thr.expand(margin.shape[1]).clone()
+
+
+# --------------------------------------------------------------------------
+# Data-driven calibration: the stand-in for training.
+# --------------------------------------------------------------------------
+def _set_bn_from_data(sd, prefix: str, z: torch.Tensor, seed: int) -> None:
+    """Point a BatchNorm's running statistics at the statistics of the tensor it
+    will actually normalise (jittered), the way a trained network's would be.
+    Without this a randomly initialised 33-block residual chain is
+    linear-homogeneous in its input and overflows fp16."""
+    mean = z.mean(dim=(0, 2, 3))
+    var = z.var(dim=(0, 2, 3), unbiased=False).clamp_min(1e-6)
+    r = _rng(seed, prefix + "jitter")
+    c = mean.numel()
+    jm = torch.from_numpy(r.standard_normal(c).astype(np.float32)).to(z.device)
+    jv = torch.from_numpy(r.uniform(0.5, 2.0, size=c).astype(np.float32)).to(z.device)
+    sd[prefix + "running_mean"] = (mean + 0.5 * var.sqrt() * jm).float().cpu()
+    sd[prefix + "running_var"] = (var * jv).float().cpu()
+
+
+def _bn_eval(z, sd, prefix, eps=1e-5):
+    dev = z.device
+    g, b = sd[prefix + "weight"].to(dev), sd[prefix + "bias"].to(dev)
+    m, v = sd[prefix + "running_mean"].to(dev), sd[prefix + "running_var"].to(dev)
+    scale = g / torch.sqrt(v + eps)
+    return z * scale.view(1, -1, 1, 1) + (b - m * scale).view(1, -1, 1, 1)
+
+
+def calibrate_resnet(sd: Dict[str, torch.Tensor], geoms, images: torch.Tensor, seed: int,
+                     channel_rate: float = 0.6, spatial_rate: float = 0.4,
+                     layer_rate: float = 0.47) -> Dict[str, torch.Tensor]:
+    """One sequential pass over a calibration batch that (i) sets every
+    BatchNorm's running stats from data and (ii) shifts every masker's keep
+    bias so that its gate fires at the requested rate (per channel group for
+    the channel masker; per mask group for the spatial/layer masker).
+
+    `geoms` is a list of objects with the attributes of a bottleneck
+    (prefix, inplanes, width, stride, output_size, mask_size, dyn_mode,
+    groups_channel, masker_kind, masker_layers, has_downsample).
+    Uses stock torch ops on `images.device`: this is weight *synthesis* (it
+    replaces training), it is not part of the inference hot path.
+    """
+    import torch.nn.functional as F
+    dev = images.device
+    W = lambda k: sd[k].to(dev)
+    with torch.no_grad():
+        z = F.conv2d(images.float(), W("conv1.weight"), stride=2, padding=3)
+        _set_bn_from_data(sd, "bn1.", z, seed)
+        x = F.max_pool2d(torch.relu(_bn_eval(z, sd, "bn1.")), 3, 2, 1)
+        for g in geoms:
+            p = g.prefix
+            b = x.shape[0]
+            cmask = None
+            m3 = None
+            if g.dyn_mode in ("channel", "both"):
+                mp = p + "masker_channel."
+                G = g.groups_channel
+                if g.masker_kind == "MLP":
+                    pooled = x.mean(dim=(2, 3))
+                    if g.masker_layers == 2:
+                        h = torch.relu(F.linear(pooled, W(mp + "conv.0.weight"), W(mp + "conv.0.bias")))
+                        bias_key = mp + "conv.2.bias"
+                        logits = F.linear(h, W(mp + "conv.2.weight"), W(bias_key))
+                    else:
+                        bias_key = mp + "conv.bias"
+                        logits = F.linear(pooled, W(mp + "conv.weight"), W(bias_key))
+                else:
+                    zc = F.conv2d(x, W(mp + "conv.0.weight"))
+                    _set_bn_from_data(sd, mp + "conv.1.", zc, seed)
+                    pooled = torch.relu(_bn_eval(zc, sd, mp + "conv.1.")).mean(dim=(2, 3))
+                    bias_key = mp + "linear.bias"
+                    logits = F.linear(pooled, W(mp + "linear.weight"), W(bias_key))
+                margin = logits[:, :G] - logits[:, G:]
+                delta = calibrate_two_way_bias(margin, channel_rate, per_group=True).to(dev)
+                nb = sd[bias_key].clone()
+                nb[:G] -= delta.cpu()
+                sd[bias_key] = nb
+                cmask = ((margin - delta) >= 0).float()
+                cmask = cmask.repeat_interleave(g.width // G, dim=1).view(b, g.width, 1, 1)
+            if g.dyn_mode in ("spatial", "layer", "both"):
+                wk, bk = p + "masker_spatial.conv.weight", p + "masker_spatial.conv.bias"
+                q = F.adaptive_avg_pool2d(x, g.mask_size) if g.mask_size < x.shape[2] else x
+                logits = F.conv2d(q, W(wk), W(bk))
+                gs = logits.shape[1] // 2
+                margin = logits[:, :gs] - logits[:, gs:]
+                rate = layer_rate if g.dyn_mode == "layer" else spatial_rate
+                flat = margin.permute(0, 2, 3, 1).reshape(-1, gs)
+                delta = calibrate_two_way_bias(flat, rate, per_group=True).to(dev)
+                nb = sd[bk].clone()
+                nb[:gs] -= delta.cpu()
+                sd[bk] = nb
+                small = ((margin - delta.view(1, gs, 1, 1)) >= 0).float()
+                S = small.shape[-1]
+                idx = torch.div(torch.arange(g.output_size, device=dev) * S, g.output_size, rounding_mode="floor")
+                m3 = small[:, :, idx][:, :, :, idx]
+                cout = g.outplanes
+                if gs > 1 and gs != cout:
+                    m3 = m3.repeat_interleave(cout // gs, dim=1)
+            z1 = F.conv2d(x, W(p + "conv1.weight"))
+            _set_bn_from_data(sd, p + "bn1.", z1, seed)
+            a1 = torch.relu(_bn_eval(z1 * cmask if cmask is not None else z1, sd, p + "bn1."))
+            z2 = F.conv2d(a1, W(p + "conv2.weight"), stride=g.stride, padding=1)
+            _set_bn_from_data(sd, p + "bn2.", z2, seed)
+            a2 = torch.relu(_bn_eval(z2 * cmask if cmask is not None else z2, sd, p + "bn2."))
+            z3 = F.conv2d(a2, W(p + "conv3.weight"))
+            _set_bn_from_data(sd, p + "bn3.", z3, seed)
+            y = _bn_eval(z3, sd, p + "bn3.")
+            if m3 is not None:
+                y = y * m3
+            ident = x
+            if g.has_downsample:
+                zd = F.conv2d(x, W(p + "downsample.0.weight"), stride=g.stride)
+                _set_bn_from_data(sd, p + "downsample.1.", zd, seed)
+                ident = _bn_eval(zd, sd, p + "downsample.1.")
+            x = torch.relu(y + ident)
+    return sd

@@ -1,0 +1,63 @@
+"""Shared definition of the golden cases (used by tests/golden/make_golden.py,
+which needs the reference, and by the tests, which do not)."""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from laudnet_b200 import synth              # noqa: E402
+from oracle import laud_oracle as O         # noqa: E402
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+CASES = {
+    # name: (cfg, batch, seed)
+    "tiny_channel": (O.ResNetCfg(layers=(2, 2, 2, 1), width_mult=0.25, input_size=64, num_classes=40,
+                                 dyn_mode=("channel",) * 4, channel_dyn_granularity=(2, 2, 2, 2),
+                                 channel_masker=("MLP",) * 4, channel_masker_layers=(2, 2, 2, 2)), 4, 11),
+    "tiny_spatial": (O.ResNetCfg(layers=(2, 2, 2, 1), width_mult=0.25, input_size=64, num_classes=40,
+                                 dyn_mode=("spatial",) * 4, mask_spatial_granularity=(4, 4, 2, 1)), 4, 12),
+    "tiny_layer": (O.ResNetCfg(layers=(2, 2, 3, 2), width_mult=0.25, input_size=64, num_classes=40,
+                               dyn_mode=("layer",) * 4, mask_spatial_granularity=(16, 8, 4, 2)), 6, 13),
+    "tiny_both": (O.ResNetCfg(layers=(1, 2, 2, 1), width_mult=0.25, input_size=64, num_classes=40,
+                              dyn_mode=("both", "both", "channel", "spatial"),
+                              channel_dyn_granularity=(4, 2, 1, 2), spatial_mask_channel_group=(2, 1, 1, 2),
+                              mask_spatial_granularity=(2, 2, 2, 1),
+                              channel_masker=("MLP", "conv_linear", "MLP", "MLP"),
+                              channel_masker_layers=(1, 2, 1, 2), reduction_ratio=(16, 2, 16, 16)), 3, 14),
+}
+
+
+def state_dict_digest(sd) -> bytes:
+    h = hashlib.sha256()
+    for k in sorted(sd):
+        h.update(k.encode())
+        h.update(np.ascontiguousarray(sd[k].numpy()).tobytes())
+    return h.digest()
+
+
+def model_shapes(cfg):
+    """state_dict key -> shape of the network, taken from the drop-in module tree
+    (identical to the reference's; tests/test_host_logic.py checks the key list)."""
+    from laudnet_b200.laud_resnet import Bottleneck, ResNet
+    m = ResNet(Bottleneck, list(cfg.layers), **cfg.kwargs())
+    return {k: tuple(v.shape) for k, v in m.state_dict().items()}
+
+
+def load_case(name):
+    """-> (cfg, state_dict, x[fp32, fp16-representable], golden npz dict)."""
+    cfg, batch, seed = CASES[name]
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    sd = synth.synth_state_dict(model_shapes(cfg), int(z["seed"]))
+    for k in z.files:
+        if k.startswith("sd."):
+            sd[k[3:]] = torch.from_numpy(z[k])
+    assert state_dict_digest(sd) == z["sd_sha256"].tobytes(), f"{name}: regenerated state_dict differs from the fixture's"
+    x = torch.from_numpy(z["x"].astype(np.float32))
+    return cfg, sd, x, z
