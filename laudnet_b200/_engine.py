@@ -38,12 +38,38 @@ def round_up(v: int, a: int) -> int:
     return (v + a - 1) // a * a
 
 
+class conv_profile:
+    """Context manager: bracket every laud_conv_forward launch with CUDA events
+    on the launching stream (bench.py's per-kernel timing).  `.total_ms()` after
+    a synchronize gives the summed device time of the conv launches."""
+    active = None
+
+    def __enter__(self):
+        self.records = []
+        conv_profile.active = self
+        return self
+
+    def __exit__(self, *exc):
+        conv_profile.active = None
+        return False
+
+    def total_ms(self) -> float:
+        return sum(a.elapsed_time(b) for _, a, b in self.records)
+
+    def by_tag(self):
+        out = {}
+        for tag, a, b in self.records:
+            n, t = out.get(tag, (0, 0.0))
+            out[tag] = (n + 1, t + a.elapsed_time(b))
+        return out
+
+
 def run_conv(x, w, y, B, H_in, W_in, C_in, H_out, W_out, C_out, ksize, stride, pad, *,
              ldx=None, ldy=None, scale=None, shift=None, relu=_lib.RELU_NONE, residual=None, ldr=0,
              k_idx=None, k_cnt=None, k_gran=1, n_idx=None, n_cnt=None, n_gran=1,
              pre_bias=None, pre_bias_classes=0, pre_bias_ld=0, out_mask=None, mask_groups=1,
              sample_idx=None, sample_cnt=None, row_idx=None, row_cnt=None, n_pad_align=0,
-             impl=_lib.CONV_AUTO) -> None:
+             impl=_lib.CONV_AUTO, tag="conv") -> None:
     """Fill a laud_conv_desc and enqueue laud_conv_forward on the current stream."""
     d = ConvDesc()
     d.x, d.ldx = ptr(x), ldx if ldx is not None else x.shape[-1]
@@ -65,7 +91,14 @@ def run_conv(x, w, y, B, H_in, W_in, C_in, H_out, W_out, C_out, ksize, stride, p
     d.row_idx, d.row_cnt = ptr(row_idx), ptr(row_cnt)
     d.n_pad_align = n_pad_align
     d.gap_partial, d.gap_tiles = None, 0
+    prof = conv_profile.active
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(lib().laud_conv_forward(C.byref(d), impl, stream_ptr()), "laud_conv_forward")
+    if prof is not None:
+        e1.record()
+        prof.records.append((tag, e0, e1))
 
 
 @dataclass
@@ -295,23 +328,24 @@ class ResNetEngine:
         ld12 = wp if gate else p.width
         # conv1 1x1 (+ mask) + bn1 + relu      laud_resnet.py:115-118
         run_conv(x, p.w1, a1, B, Hi, Hi, p.inplanes, Hi, Hi, p.width, 1, 1, 0, ldx=p.inplanes, ldy=ld12,
-                 scale=p.s1, shift=p.t1, relu=_lib.RELU_ALL, impl=self.impl, **cn)
+                 scale=p.s1, shift=p.t1, relu=_lib.RELU_ALL, impl=self.impl, tag=f"s{p.stage + 1}.conv1", **cn)
         # conv2 3x3/stride (+ mask) + bn2 + relu     laud_resnet.py:123-126
         run_conv(a1, p.w2, a2, B, Hi, Hi, p.width, Ho, Ho, p.width, 3, p.stride, 1, ldx=ld12, ldy=ld12,
-                 scale=p.s2, shift=p.t2, relu=_lib.RELU_ALL, impl=self.impl,
+                 scale=p.s2, shift=p.t2, relu=_lib.RELU_ALL, impl=self.impl, tag=f"s{p.stage + 1}.conv2",
                  pre_bias=ws["pb2"] if gate else None, pre_bias_classes=16 if gate else 0,
                  pre_bias_ld=p.width if gate else 0, **ck, **cn)
         # identity branch      laud_resnet.py:138-141
         if p.wd is not None:
             run_conv(x, p.wd, idbuf, B, Hi, Hi, p.inplanes, Ho, Ho, p.outplanes, 1, p.stride, 0, ldx=p.inplanes,
-                     ldy=p.outplanes, scale=p.sd, shift=p.td, relu=_lib.RELU_NONE, impl=self.impl)
+                     ldy=p.outplanes, scale=p.sd, shift=p.td, relu=_lib.RELU_NONE, impl=self.impl,
+                     tag=f"s{p.stage + 1}.down")
             res = idbuf
         else:
             res = x
         # conv3 1x1 + bn3 (+ spatial mask) + identity + relu     laud_resnet.py:131-144
         run_conv(a2, p.w3, out, B, Ho, Ho, p.width, Ho, Ho, p.outplanes, 1, 1, 0, ldx=ld12, ldy=p.outplanes,
                  scale=p.s3, shift=p.t3, relu=_lib.RELU_ALL, residual=res, ldr=p.outplanes, impl=self.impl,
-                 pre_bias=ws["pb3"] if gate else None, pre_bias_classes=1 if gate else 0,
+                 tag=f"s{p.stage + 1}.conv3", pre_bias=ws["pb3"] if gate else None, pre_bias_classes=1 if gate else 0,
                  pre_bias_ld=p.outplanes if gate else 0, out_mask=m3, mask_groups=p.g_spatial if m3 is not None else 1,
                  **ck)
         if keep is not None:
@@ -376,6 +410,13 @@ class ResNetEngine:
                                    feat * ncls, ptr(stats), st), "laud_forward_stats")
         return logits, stats
 
+    # ------------------------------------------------------------- CUDA graph
+    def capture(self, x_example: torch.Tensor) -> "GraphedForward":
+        """Capture one forward (all kernels of liblaud_b200.so for this batch
+        shape) into a CUDA graph: the launch-bound host loop (~10 launches per
+        block) becomes a single cudaGraphLaunch."""
+        return GraphedForward(self, x_example)
+
     def split_stats(self, stats: torch.Tensor):
         """stats [n_blocks*5+1] -> the reference's (rho3[4], rho2[4], rho1[4], rho_c[4], flops_perc, flops)."""
         nb = len(self.plans)
@@ -386,3 +427,36 @@ class ResNetEngine:
             s0 += len(layer)
         col = lambda c: [tab[a:b, c] for a, b in bounds]
         return col(0), col(1), col(2), col(3), tab[:, 4], stats[nb * 5]
+
+
+class GraphedForward:
+    """A captured forward.  `run(x)` copies x into the static input (device to
+    device, or host to device when x is pinned host memory), replays the graph
+    and returns the static logits / stats tensors (overwritten by the next run)."""
+
+    def __init__(self, engine: ResNetEngine, x_example: torch.Tensor):
+        if x_example.device.type != "cuda":
+            raise LaudError("capture(): expected a CUDA example input")
+        self.engine = engine
+        self.static_x = x_example.detach().to(torch.float16).contiguous().clone()
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):              # warm-up: workspaces, func attributes, lazy prepare
+            for _ in range(2):
+                engine.forward(self.static_x)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        n0 = _lib.launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.logits, self.stats = engine.forward(self.static_x)
+        self.launches = _lib.launch_count() - n0     # kernels of ours inside one replay
+
+    def replay(self):
+        self.graph.replay()
+        return self.logits, self.stats
+
+    def run(self, x: torch.Tensor):
+        self.static_x.copy_(x, non_blocking=True)
+        return self.replay()

@@ -367,8 +367,11 @@ static int launch_decide(const float* partial, const float* pooled_in, int B, in
   LAUD_REQUIRE(G > 0, "channel masker: G must be positive");
   const size_t smem = decide_smem(C, layers == 2 ? hidden : 0, G);
   LAUD_REQUIRE(smem <= 200 * 1024, "channel masker: C/G too large for shared memory");
-  if (smem > 48 * 1024)
+  static size_t decide_smem_set = 48 * 1024;
+  if (smem > decide_smem_set) {
     LAUD_CUDA(cudaFuncSetAttribute(masker_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    decide_smem_set = smem;
+  }
   masker_decide_kernel<<<B, 256, smem, s>>>(partial, pooled_in, C, LAUD_GAP_SPLITS, HW, layers, w1, b1,
                                             layers == 2 ? hidden : 0, w2, b2, G, pooled_out, logits_out,
                                             mask_out, idx_out, cnt_out, total_out);

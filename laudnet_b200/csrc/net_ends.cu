@@ -289,7 +289,11 @@ extern "C" int laud_stem_forward(const void* x, int B, int H, int W, const void*
   const int Hp = H / 4, Wp = W / 4;
   const size_t smem = sizeof(float) * 3 * ST_IH * ST_IWP + sizeof(__half) * (147 + ST_CH * ST_CW) * (size_t)C0;
   LAUD_REQUIRE(smem <= 200 * 1024, "laud_stem_forward: stem width %d too large", C0);
-  LAUD_CUDA(cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static size_t stem_smem_set = 0;      // set once per size: keeps the launch path free of attribute calls (graph capture)
+  if (smem > stem_smem_set) {
+    LAUD_CUDA(cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    stem_smem_set = smem;
+  }
   dim3 grid((Wp + ST_PW - 1) / ST_PW, (Hp + ST_PH - 1) / ST_PH, B);
   stem_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const __half*)x, H, W, (const __half*)w, C0, scale, shift,
                                                          (__half*)y);
@@ -304,8 +308,11 @@ extern "C" int laud_head_forward(const void* x, int B, int HW, int C, const void
   float* pooled = pooled_ws + (size_t)B * LAUD_GAP_SPLITS * C;
   if (int e = laud_global_avg_pool(x, B, HW, C, C, pooled_ws, pooled, stream)) return e;
   const size_t smem = sizeof(float) * 4 * (size_t)C;
-  if (smem > 48 * 1024)
+  static size_t head_smem_set = 48 * 1024;
+  if (smem > head_smem_set) {
     LAUD_CUDA(cudaFuncSetAttribute(head_fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    head_smem_set = smem;
+  }
   dim3 grid((n_cls + 63) / 64, (B + 3) / 4);
   head_fc_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(pooled, B, C, (const __half*)w, bias, n_cls, logits);
   return check_launch("head_fc_kernel");

@@ -269,6 +269,12 @@ class ResNet(nn.Module):
             raise LaudError("ResNet: call .eval() first")
         return self._engine.forward(x)[0]
 
+    def capture(self, x_example):
+        """CUDA-graph the eval forward for this input shape (see _engine.GraphedForward)."""
+        if self.training:
+            raise LaudError("ResNet: call .eval() first")
+        return self._engine.capture(x_example)
+
     def get_optim_policies(self):
         """Same two parameter groups as the reference (laud_resnet.py:365-401)."""
         groups = {"backbone_params": [], "masker_params": []}

@@ -227,3 +227,48 @@ def calibrate_resnet(sd: Dict[str, torch.Tensor], geoms, images: torch.Tensor, s
                 ident = _bn_eval(zd, sd, p + "downsample.1.")
             x = torch.relu(y + ident)
     return sd
+
+
+# --------------------------------------------------------------------------
+# Workload construction shared by bench.py, the tests and smoke().
+# --------------------------------------------------------------------------
+class _Geom:
+    """Bottleneck geometry read off a drop-in module (same attribute names as
+    the oracle's BlockGeom, so `calibrate_resnet` accepts either)."""
+
+    def __init__(self, prefix, blk):
+        self.prefix = prefix
+        self.inplanes = blk.conv1.weight.shape[1]
+        self.width = blk.conv1.weight.shape[0]
+        self.outplanes = blk.conv3.weight.shape[0]
+        self.stride = blk.stride
+        self.output_size = blk.output_size
+        self.mask_size = blk.mask_size
+        self.dyn_mode = blk.dyn_mode
+        self.groups_channel = blk.channel_dyn_group
+        self.groups_spatial = blk.spatial_mask_channel_group
+        mk = blk.masker_channel
+        self.masker_kind = "MLP" if (mk is None or hasattr(mk, "layers")) else "conv_linear"
+        self.masker_layers = getattr(mk, "layers", 2)
+        self.has_downsample = blk.downsample is not None
+
+
+def geometry_of(model):
+    return [_Geom(f"layer{s + 1}.{i}.", blk)
+            for s in range(4) for i, blk in enumerate(getattr(model, f"layer{s + 1}"))]
+
+
+HEADLINE_KWARGS = dict(          # LAUD-ResNet101 channel-2222 (SURVEY appendix B.3)
+    input_size=224, dyn_mode=["channel"] * 4, channel_dyn_granularity=[2, 2, 2, 2],
+    channel_masker=["MLP"] * 4, channel_masker_layers=[2] * 4, reduction_ratio=[16] * 4,
+    spatial_mask_channel_group=[1] * 4, mask_spatial_granularity=[4, 4, 2, 1], lr_mult=1.0)
+
+
+def synth_calibrated_state_dict(model, seed: int, calib_images: torch.Tensor, channel_rate: float = 0.6,
+                                spatial_rate: float = 0.4, layer_rate: float = 0.47):
+    """Seeded weights for `model`'s architecture, BN statistics and gate biases
+    calibrated on `calib_images` (on that tensor's device, stock torch ops)."""
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    sd = synth_state_dict(shapes, seed)
+    return calibrate_resnet(sd, geometry_of(model), calib_images, seed, channel_rate=channel_rate,
+                            spatial_rate=spatial_rate, layer_rate=layer_rate)
