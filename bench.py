@@ -328,7 +328,7 @@ def run_graft(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": graphed.launches * args.steps, "launches_per_step": graphed.launches,
-            "eager_launches_per_step": launches_per_step,
+            "eager_launches_per_step": launches_per_step, "conv_paths": _lib.conv_path_counts(),
             "clocks": clocks, "roofline": roof, "net": net, "cpu_baseline": cpu,
         }))
     if world > 1:

@@ -55,6 +55,9 @@ int laud_abi_version(void);
 const char* laud_last_error(void);
 /* number of kernels this library has launched in this process (all streams) */
 unsigned long long laud_launch_count(void);
+/* launches of the mask-conditioned convolution by implementation:
+ * out[0] tcgen05/TMEM kernel, out[1] legacy HMMA kernel, out[2] naive self-test kernel */
+void laud_conv_path_counts(unsigned long long out[3]);
 
 /* ---------------------------------------------------------------------------
  * (a1) channel masker.  Replaces Masker_channel_MLP.forward, eval branch

@@ -51,6 +51,7 @@ SIGNATURES = {
     "laud_abi_version": ([], C.c_int),
     "laud_last_error": ([], C.c_char_p),
     "laud_launch_count": ([], C.c_ulonglong),
+    "laud_conv_path_counts": ([C.POINTER(C.c_ulonglong * 3)], None),
     "laud_masker_channel_mlp": ([_vp, _i, _i, _i, _i, _fp, _fp, _i, _fp, _fp, _i, _fp, _fp, _fp, _u8p, _i32p, _i32p, _i32p, _vp], _i),
     "laud_masker_channel_from_pooled": ([_fp, _i, _i, _i, _fp, _fp, _i, _fp, _fp, _i, _fp, _u8p, _i32p, _i32p, _i32p, _vp], _i),
     "laud_global_avg_pool": ([_vp, _i, _i, _i, _i, _fp, _fp, _vp], _i),
@@ -114,3 +115,11 @@ def require_cuda(t: torch.Tensor, what: str) -> None:
 
 def launch_count() -> int:
     return int(lib().laud_launch_count())
+
+
+def conv_path_counts() -> dict:
+    """Launches of the mask-conditioned conv by implementation (evidence that the
+    tcgen05 kernel is the one that runs)."""
+    out = (C.c_ulonglong * 3)()
+    lib().laud_conv_path_counts(C.byref(out))
+    return {"umma_tcgen05": int(out[0]), "hmma_legacy": int(out[1]), "naive_selftest": int(out[2])}

@@ -8,6 +8,7 @@ namespace laud {
 
 static thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
+std::atomic<unsigned long long> g_conv_paths[3];
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -23,6 +24,9 @@ using namespace laud;
 extern "C" int laud_abi_version(void) { return LAUD_ABI_VERSION; }
 extern "C" const char* laud_last_error(void) { return g_err; }
 extern "C" unsigned long long laud_launch_count(void) { return g_launches.load(); }
+extern "C" void laud_conv_path_counts(unsigned long long out[3]) {
+  for (int i = 0; i < 3; ++i) out[i] = g_conv_paths[i].load();
+}
 
 extern "C" int laud_conv_forward(const laud_conv_desc* d, int impl, void* stream) {
   LAUD_REQUIRE(d != nullptr, "laud_conv_forward: null descriptor");

@@ -88,6 +88,7 @@ int conv_forward_naive(const ConvArgs& a, cudaStream_t s) {
   const long long rows = a.row_idx ? (long long)a.B * HWo : HWo;
   const long long threads = rows * Nmax;
   dim3 grid((unsigned)((threads + 255) / 256), a.row_idx ? 1 : a.B);
+  g_conv_paths[2].fetch_add(1, std::memory_order_relaxed);
   conv_naive_kernel<<<grid, 256, 0, s>>>(a);
   return check_launch("conv_naive_kernel");
 }
@@ -248,6 +249,7 @@ int conv_forward_hmma(const ConvArgs& a, cudaStream_t s) {
   const long long rows = a.row_idx ? (long long)a.B * HWo : HWo;
   const int Nmax = round_up(a.C_out, a.n_pad_align);
   dim3 grid((unsigned)((rows + BM - 1) / BM), a.row_idx ? 1 : a.B, (Nmax + BN - 1) / BN);
+  g_conv_paths[1].fetch_add(1, std::memory_order_relaxed);
   conv_hmma_kernel<<<grid, 128, 0, s>>>(a);
   return check_launch("conv_hmma_kernel");
 }

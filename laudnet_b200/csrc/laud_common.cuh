@@ -11,6 +11,7 @@ namespace laud {
 
 void set_error(const char* fmt, ...);
 extern std::atomic<unsigned long long> g_launches;
+extern std::atomic<unsigned long long> g_conv_paths[3];
 
 inline int check_launch(const char* what) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
