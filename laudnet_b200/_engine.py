@@ -9,6 +9,7 @@ launched from here lives in liblaud_b200.so.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional
 
@@ -389,6 +390,7 @@ class ResNetEngine:
         cur = 0
         check(L.laud_stem_forward(ptr(xh), B, H, W, ptr(self.stem_w), C0, ptr(self.stem_s), ptr(self.stem_t),
                                   ptr(bufs[cur]), st), "laud_stem_forward")
+        nvtx = bool(os.environ.get("LAUD_NVTX"))
         for p in self.plans:
             nxt = (cur + 1) % 3
             idb = (cur + 2) % 3
@@ -396,7 +398,11 @@ class ResNetEngine:
             if keep is not None:
                 ko = BlockOutputs()
                 keep.append(ko)
+            if nvtx:
+                torch.cuda.nvtx.range_push(f"blk{p.index}")
             self.run_block(p, bufs[cur], bufs[nxt], bufs[idb], B, ws, ko)
+            if nvtx:
+                torch.cuda.nvtx.range_pop()
             cur = nxt
         last = self.plans[-1]
         feat = last.outplanes
