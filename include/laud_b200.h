@@ -167,6 +167,10 @@ typedef struct laud_conv_desc {
   int32_t n_pad_align;      /* 0 | 8 | 16: zero-pad each sample's compact output channels to this multiple */
   float* gap_partial;       /* optional fused GAP of the OUTPUT: fp32 [B, gap_tiles, C_out] partial sums */
   int32_t gap_tiles;
+  const void* w_t;          /* optional transposed copy of w: fp16 [ksize*ksize, C_in, C_out].  With k_idx it
+                               selects the K-row-gather path (16-byte gathers of the active input channels;
+                               all output channels are computed and, with n_idx, compacted in the epilogue).
+                               In that path pre_bias is indexed by REAL output channel, not compact column. */
 } laud_conv_desc;
 
 int laud_conv_forward(const laud_conv_desc* desc /* host */, int impl, void* stream);

@@ -35,6 +35,14 @@ def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
         return w.detach().permute(0, 2, 3, 1).reshape(co, kh * kw, ci).to(torch.float16).contiguous()
 
 
+def pack_conv_weight_t(w: torch.Tensor) -> torch.Tensor:
+    """[C_out, C_in, kh, kw] fp32 -> fp16 [kh*kw, C_in, C_out] (out-channel fastest): the
+    transposed copy the K-row-gather path reads (16-byte gathers of active INPUT channels)."""
+    with torch.no_grad():
+        co, ci, kh, kw = w.shape
+        return w.detach().permute(2, 3, 1, 0).reshape(kh * kw, ci, co).to(torch.float16).contiguous()
+
+
 def round_up(v: int, a: int) -> int:
     return (v + a - 1) // a * a
 
@@ -70,7 +78,7 @@ def run_conv(x, w, y, B, H_in, W_in, C_in, H_out, W_out, C_out, ksize, stride, p
              k_idx=None, k_cnt=None, k_gran=1, n_idx=None, n_cnt=None, n_gran=1,
              pre_bias=None, pre_bias_classes=0, pre_bias_ld=0, out_mask=None, mask_groups=1,
              sample_idx=None, sample_cnt=None, row_idx=None, row_cnt=None, n_pad_align=0,
-             impl=_lib.CONV_AUTO, tag="conv") -> None:
+             impl=_lib.CONV_AUTO, tag="conv", w_t=None) -> None:
     """Fill a laud_conv_desc and enqueue laud_conv_forward on the current stream."""
     d = ConvDesc()
     d.x, d.ldx = ptr(x), ldx if ldx is not None else x.shape[-1]
@@ -92,6 +100,7 @@ def run_conv(x, w, y, B, H_in, W_in, C_in, H_out, W_out, C_out, ksize, stride, p
     d.row_idx, d.row_cnt = ptr(row_idx), ptr(row_cnt)
     d.n_pad_align = n_pad_align
     d.gap_partial, d.gap_tiles = None, 0
+    d.w_t = ptr(w_t)
     prof = conv_profile.active
     if prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

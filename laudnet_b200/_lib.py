@@ -43,6 +43,7 @@ class ConvDesc(C.Structure):
         ("row_idx", _vp), ("row_cnt", _vp),
         ("n_pad_align", C.c_int32),
         ("gap_partial", _vp), ("gap_tiles", C.c_int32),
+        ("w_t", _vp),
     ]
 
 

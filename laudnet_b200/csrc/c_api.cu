@@ -88,6 +88,7 @@ extern "C" int laud_conv_forward(const laud_conv_desc* d, int impl, void* stream
   a.row_idx = d->row_idx; a.row_cnt = d->row_cnt;
   a.n_pad_align = d->n_pad_align;
   a.gap_partial = d->gap_partial; a.gap_tiles = d->gap_tiles;
+  a.wt = (const __half*)d->w_t;
 
   cudaStream_t s = (cudaStream_t)stream;
   switch (impl) {

@@ -3,28 +3,31 @@
 //
 //   D[m, n] = sum_{tap, k} A[m, (tap,k)] * W[n, (tap,k)]
 //     m : up to 128 output pixels of ONE sample (or of a device-side row list)
-//     n : that sample's ACTIVE output channels (compact), <= 256 per tile
+//     n : output channels of one tile (<= 256)
 //     k : that sample's ACTIVE input channels (compact), per filter tap
 //
-// Roles (288 threads, one CTA per SM, grid = #SMs, static round-robin over
-// work items (sample, m-tile, n-tile)):
-//   warps 0-3  epilogue : tcgen05.ld the fp32 accumulator out of TMEM, apply the
-//                         H1 pre-bias / folded BN / spatial gate / residual /
-//                         ReLU, store fp16 (compact channels, zero pad);
-//   warp  4    MMA      : one elected lane issues tcgen05.mma (M=128, N = the
-//                         tile's runtime width, K=16) on 128B-swizzled K-major
-//                         shared-memory operands; accumulators double-buffered
-//                         in TMEM (2 x 256 columns) so the epilogue of tile i
-//                         overlaps the main loop of tile i+1;
-//   warps 5-8  producers: stage ONLY the active patches/channels: the im2col
-//                         gather of the activation rows (zero-fill for padding
-//                         and ragged tiles) and the per-sample row (n) and
-//                         in-row (k) gather of the weights, with cp.async
-//                         (16 B, or 4/8 B units for channel granularity 2/4)
-//                         written straight into the UMMA swizzle layout;
-//                         completion is signalled on mbarriers
-//                         (cp.async.mbarrier.arrive), stages are released by
-//                         tcgen05.commit.
+// 416 threads, one CTA per SM, grid = #SMs, static round-robin over work items
+// (sample, m-tile, n-tile):
+//   warps 0-3   epilogue : residual rows are prefetched into a shared staging tile
+//                          with cp.async.bulk; the fp32 accumulator comes out of
+//                          TMEM with tcgen05.ld; H1 pre-bias / folded BN / spatial
+//                          gate / residual / ReLU in registers; the fp16 row is
+//                          written back to the staging tile and leaves with one
+//                          cp.async.bulk store per pixel row (compact channels);
+//   warp  4     MMA      : one elected lane issues tcgen05.mma (M=128, runtime N,
+//                          K=16) on 128B-swizzled shared-memory operands;
+//                          accumulators double-buffered in TMEM (2 x 256 columns);
+//   warps 5-12  producers: stage ONLY the active patches / channels with cp.async
+//                          straight into the UMMA swizzle layout, signalling
+//                          mbarriers (cp.async.mbarrier.arrive); stages are
+//                          released by tcgen05.commit.  Three weight modes:
+//        ROWS  : K-major B, row gather of the active OUTPUT channels (16-byte units);
+//        KROWS : MN-major B from the transposed weights [tap][k][o]: row gather of the
+//                active INPUT channels (16-byte units), all output channels of the
+//                tile are computed and the epilogue compacts the active ones;
+//        KUNITS: K-major B with an in-row gather of the active input channels
+//                (4/8/16-byte units) - general fallback when no transposed copy
+//                of the weights is supplied.
 // Restates (does not port) the conv -> mask -> bn -> relu chains of
 // imagenet_classification/models/laud_resnet.py:115-144 of the reference.
 #include "laud_common.cuh"
@@ -33,32 +36,38 @@ namespace laud {
 namespace {
 
 constexpr int BM = 128;                  // UMMA M: output pixels per tile
-constexpr int BN_MAX = 256;              // UMMA N upper bound: compact output channels per tile
-constexpr int STAGES = 4;
-constexpr int A_STAGE_BYTES = BM * 128;        // 128 rows x 64 fp16
-constexpr int B_STAGE_BYTES = BN_MAX * 128;    // 256 rows x 64 fp16
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int EPI_WARPS = 4, PROD_WARPS = 4;
+constexpr int BN_MAX = 256;              // UMMA N upper bound
+constexpr int A_STAGE_BYTES = BM * 128;  // 128 rows x 64 fp16
+constexpr int EPI_WARPS = 4, PROD_WARPS = 8;
 constexpr int MMA_WARP = EPI_WARPS;
 constexpr int PROD_WARP0 = EPI_WARPS + 1;
-constexpr int NUM_THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;
+constexpr int NUM_THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;   // 416
 constexpr int PROD_THREADS = PROD_WARPS * 32;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int KIDX_MAX = 1024;
+constexpr int MAX_STAGES = 8;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr long long SPIN_CYCLES = 4000000000ll;  // watchdog (~2 s): trap instead of hanging the GPU
+constexpr int SMEM_LIMIT = 232448;               // 227 KB opt-in maximum per CTA
+
+enum { MODE_ROWS = 1, MODE_KROWS = 2, MODE_KUNITS = 3 };
 
 struct Tables {
-  int brow[BN_MAX];        // element offset of the weight row of compact column j (or -1: zero row)
-  int kidx[KIDX_MAX];      // this sample's active input-channel groups
+  int brow[BN_MAX];        // KUNITS: element offset of the weight row of compact column j (or -1)
+  int kch[KIDX_MAX];       // real input channel of this sample's compact input channel e
   float scale[BN_MAX];
   float shift[BN_MAX];
-  int ochan[BN_MAX];       // real output channel of compact column j (or -1: zero pad)
-  unsigned long long full[STAGES], empty[STAGES], tfull[2], tempty[2];
+  int ochan[BN_MAX];       // real output channel of tile column c (or -1: zero pad / inactive)
+  int cpos[BN_MAX];        // position of tile column c in the stored row (staging / compact output)
+  unsigned long long full[MAX_STAGES], empty[MAX_STAGES], tfull[2], tempty[2], rfull;
   uint32_t tmem_base;
 };
 
-constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + sizeof(Tables);
+struct Plan {              // host-computed launch geometry
+  int n_mtiles, NT, total_items;
+  int stages, stage_bytes, stg_pitch, mode;
+  int staged;              // 1: rows leave through the shared staging tile + bulk copies
+};
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -68,6 +77,9 @@ __device__ __forceinline__ void mbar_init(unsigned long long* b, uint32_t count)
 }
 __device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity) {
   const uint32_t addr = smem_u32(b);
@@ -99,6 +111,20 @@ __device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src, uint32
 __device__ __forceinline__ void cp_async_arrive(unsigned long long* b) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(b)) : "memory");
 }
+// bulk (TMA engine) row copies
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -135,36 +161,39 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+// Shared-memory matrix descriptors (SWIZZLE_128B).
+//  K-major : rows (m or n) of 128 B = 64 k; 8-row groups `sbo` bytes apart.
+//  MN-major: rows (k) of 128 B = 64 n; 8-k groups `sbo` bytes apart, 64-n blocks `lbo` bytes apart.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;              // leading byte offset (unused for swizzled K-major) = 1
-  d |= (uint64_t)(1024 >> 4) << 32;    // stride byte offset: next 8-row group
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;              // descriptor version (Blackwell)
   d |= (uint64_t)2 << 61;              // SWIZZLE_128B
   return d;
 }
-__device__ __forceinline__ uint32_t umma_idesc_f16(int n) {
+__device__ __forceinline__ uint32_t umma_idesc_f16(int n, int b_mn_major) {
   return (1u << 4)                      // D = fp32
          | (0u << 7) | (0u << 10)       // A, B = fp16
-         | (0u << 15) | (0u << 16)      // A, B K-major
+         | (0u << 15)                   // A K-major
+         | ((uint32_t)b_mn_major << 16) // B K-major (0) / MN-major (1)
          | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
-// byte offset of (row r, 16-byte chunk c) inside a swizzled tile
+// byte offset of (row r, 16-byte chunk c) inside a swizzled K-major tile
 __device__ __forceinline__ uint32_t sw128_off(int r, int c) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
 }
 
 // ------------------------------------------------------------------ work items
 struct Item {
-  int b, mt, n0, n_valid, umma_n, Nc, Kc, nk16, cpt, nchunks;
+  int b, mt, nt, ntiles, n0, n_valid, umma_n, Nc, Nfill, Kc, nk16, cpt, nchunks;
 };
 
-__device__ __forceinline__ bool decode_item(const ConvArgs& a, int t, int n_mtiles, int NT, Item& it) {
-  const int nt = t % NT;
-  const int r = t / NT;
-  it.mt = r % n_mtiles;
-  const int slot = r / n_mtiles;
+__device__ __forceinline__ bool decode_item(const ConvArgs& a, const Plan& pl, int t, Item& it) {
+  it.nt = t % pl.NT;
+  const int r = t / pl.NT;
+  it.mt = r % pl.n_mtiles;
+  const int slot = r / pl.n_mtiles;
   int b = 0;
   if (a.row_idx) {
     if ((long long)it.mt * BM >= (long long)__ldg(a.row_cnt)) return false;
@@ -175,13 +204,15 @@ __device__ __forceinline__ bool decode_item(const ConvArgs& a, int t, int n_mtil
   }
   it.b = b;
   it.Nc = a.n_idx ? __ldg(a.n_cnt + b) * a.n_gran : a.C_out;
-  const int Nfill = round_up(it.Nc, a.n_pad_align);
-  const int ntiles = (Nfill + BN_MAX - 1) / BN_MAX;
-  if (nt >= ntiles) return false;
-  const int per = round_up((Nfill + ntiles - 1) / ntiles, 16);
-  it.n0 = nt * per;
-  if (it.n0 >= Nfill) return false;
-  it.n_valid = min(per, Nfill - it.n0);
+  it.Nfill = round_up(it.Nc, a.n_pad_align);
+  // KROWS tiles span REAL output channels (the epilogue compacts); the others span the compact row
+  const int span = (pl.mode == MODE_KROWS) ? a.C_out : it.Nfill;
+  it.ntiles = (span + BN_MAX - 1) / BN_MAX;
+  if (it.nt >= it.ntiles) return false;
+  const int per = round_up((span + it.ntiles - 1) / it.ntiles, 16);
+  it.n0 = it.nt * per;
+  if (it.n0 >= span) return false;
+  it.n_valid = min(per, span - it.n0);
   it.umma_n = round_up(it.n_valid, 16);
   it.Kc = a.k_idx ? __ldg(a.k_cnt + b) * a.k_gran : a.C_in;
   it.nk16 = (it.Kc + 15) >> 4;
@@ -213,19 +244,25 @@ __device__ __forceinline__ RowPos row_pos(const ConvArgs& a, const Item& it, int
   return p;
 }
 
+__device__ __forceinline__ int real_out_channel(const ConvArgs& a, int b, int jj) {
+  return a.n_idx ? __ldg(a.n_idx + (size_t)b * a.n_ld + jj / a.n_gran) * a.n_gran + jj % a.n_gran : jj;
+}
+
 // ------------------------------------------------------------------ the kernel
-__global__ void __launch_bounds__(NUM_THREADS, 1) conv_umma_kernel(const __grid_constant__ ConvArgs a, int n_mtiles,
-                                                                   int NT, int total_items) {
+__global__ void __launch_bounds__(NUM_THREADS, 1) conv_umma_kernel(const __grid_constant__ ConvArgs a,
+                                                                   const __grid_constant__ Plan pl) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  Tables& T = *reinterpret_cast<Tables*>(smem + (size_t)STAGES * STAGE_BYTES);
+  unsigned char* stg = smem + (size_t)pl.stages * pl.stage_bytes;                       // staging tile [128][stg_pitch]
+  Tables& T = *reinterpret_cast<Tables*>(stg + (size_t)(pl.staged ? BM * pl.stg_pitch : 0));
   const uint32_t smem_base = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int HWo = a.H_out * a.W_out;
   const int taps = a.ksize * a.ksize;
+  const int mode = pl.mode;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < pl.stages; ++s) {
       mbar_init(&T.full[s], PROD_THREADS);
       mbar_init(&T.empty[s], 1);
     }
@@ -233,6 +270,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_umma_kernel(const __grid_
       mbar_init(&T.tfull[i], 1);
       mbar_init(&T.tempty[i], EPI_THREADS);
     }
+    mbar_init(&T.rfull, EPI_THREADS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == MMA_WARP) {
@@ -248,36 +286,47 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_umma_kernel(const __grid_
 
   if (warp >= PROD_WARP0) {
     // =========================================================== producers
-    const int pt = threadIdx.x - PROD_WARP0 * 32;      // 0..127
-    const int ac = pt & 7, ar0 = pt >> 3;              // A (and dense-K B): 16-byte chunk, first row
-    // K-gather unit geometry (bytes per unit, units per 128-byte row)
-    const int ub = a.k_idx ? min(16, a.k_gran * 2) : 16;
+    const int pt = threadIdx.x - PROD_WARP0 * 32;      // 0..255
+    const int ac = pt & 7, ar0 = pt >> 3;              // 16-byte chunk, first row (rows ar0 + 32 i)
+    const uint32_t off0 = sw128_off(ar0, ac);          // + 4096 i for row ar0 + 32 i
+    // KUNITS geometry: bytes per unit, units per 128-byte row
+    const int ub = (mode == MODE_KUNITS) ? min(16, a.k_gran * 2) : 16;
     const int upc = 128 / ub;
-    const int ku = pt % upc, kr0 = pt / upc, krstep = PROD_THREADS / upc;
+    const int ku = pt % upc, kr0 = pt / upc, krstep = PROD_THREADS / upc;      // krstep is a multiple of 8
+    const uint32_t koff0 = sw128_off(kr0, (ku * ub) >> 4) + ((ku * ub) & 15);  // + 128 * krstep per step
+    // KROWS geometry: warp pw stages k-rows pw + 8 i, lane = 16-byte chunk of the row
+    const int pw = pt >> 5;
+    const uint32_t roff0 = (uint32_t)((lane >> 3) * 8192 + pw * 128 + (((lane & 7) ^ pw) << 4));   // + 1024 i
     int stage = 0;
     uint32_t phase = 0;
-    for (int t = blockIdx.x; t < total_items; t += gridDim.x) {
+    for (int t = blockIdx.x; t < pl.total_items; t += gridDim.x) {
       Item it;
-      if (!decode_item(a, t, n_mtiles, NT, it)) continue;
+      if (!decode_item(a, pl, t, it)) continue;
       named_bar_sync(1, PROD_THREADS);                 // previous item's table reads are done
-      for (int j = pt; j < it.umma_n; j += PROD_THREADS) {
-        const int jj = it.n0 + j;
-        int off = -1;
-        if (jj < it.Nc) {
-          const int o = a.n_idx ? __ldg(a.n_idx + (size_t)it.b * a.n_ld + jj / a.n_gran) * a.n_gran + jj % a.n_gran : jj;
-          off = o * taps * a.C_in;
+      int browr[8];                                    // ROWS: weight-row offsets of the 8 rows this thread stages
+      if (mode == MODE_ROWS) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int jj = it.n0 + ar0 + 32 * i;
+          browr[i] = (ar0 + 32 * i < it.umma_n && jj < it.Nc) ? real_out_channel(a, it.b, jj) * taps * a.C_in : -1;
         }
-        T.brow[j] = off;
+      } else if (mode == MODE_KUNITS) {
+        for (int j = pt; j < it.umma_n; j += PROD_THREADS) {
+          const int jj = it.n0 + j;
+          T.brow[j] = jj < it.Nc ? real_out_channel(a, it.b, jj) * taps * a.C_in : -1;
+        }
       }
       if (a.k_idx) {
-        const int ng = it.Kc / a.k_gran;
-        for (int q = pt; q < ng; q += PROD_THREADS) T.kidx[q] = __ldg(a.k_idx + (size_t)it.b * a.k_ld + q);
+        for (int e = pt; e < it.Kc; e += PROD_THREADS) {
+          const int q = e / a.k_gran;
+          T.kch[e] = __ldg(a.k_idx + (size_t)it.b * a.k_ld + q) * a.k_gran + (e - q * a.k_gran);
+        }
       }
-      // the 8 activation rows this thread stages: pixel base and top-left input coordinate
-      int pbase[8], iy0[8], ix0[8];
+      // the 4 activation rows this thread stages: pixel base and top-left input coordinate
+      int pbase[4], iy0[4], ix0[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const RowPos p = row_pos(a, it, ar0 + 16 * i, HWo);
+      for (int i = 0; i < 4; ++i) {
+        const RowPos p = row_pos(a, it, ar0 + 32 * i, HWo);
         pbase[i] = p.b * a.H_in * a.W_in;
         iy0[i] = p.valid ? p.oy * a.stride - a.pad : -(1 << 20);
         ix0[i] = p.ox * a.stride - a.pad;
@@ -285,57 +334,82 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_umma_kernel(const __grid_
       named_bar_sync(1, PROD_THREADS);
       const int ka_lim = a.k_idx ? it.nk16 * 16 : a.C_in;    // compact inputs are zero-padded to 16 by their producer
 
-      for (int ch = 0; ch < it.nchunks; ++ch) {
-        const int tap = ch / it.cpt, kq = ch - tap * it.cpt;
+      for (int tap = 0; tap < taps; ++tap) {
         const int ty = tap / a.ksize, tx = tap - ty * a.ksize;
-        const int k0 = kq * 64;
-        const int n16 = min(4, it.nk16 - kq * 4);
-        const int nch = 2 * n16;                              // 16-byte chunks the MMAs of this stage will read
-        mbar_wait(&T.empty[stage], phase ^ 1);
-        const uint32_t As = smem_base + stage * STAGE_BYTES;
-        const uint32_t Bs = As + A_STAGE_BYTES;
-        // ---- A: im2col gather of 128 pixel rows x 64 channels of this tap
-        if (ac < nch) {
-          const int k = k0 + ac * 8;
-          const bool kok = k < ka_lim;
+        const __half* aptr[4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int iy = iy0[i] + ty, ix = ix0[i] + tx;
-            const bool ok = kok && iy >= 0 && iy < a.H_in && ix >= 0 && ix < a.W_in;
-            const __half* src = ok ? a.x + ((size_t)(pbase[i] + iy * a.W_in + ix)) * a.ldx + k : a.x;
-            cp_async_16(As + sw128_off(ar0 + 16 * i, ac), src, ok ? 16u : 0u);
-          }
+        for (int i = 0; i < 4; ++i) {
+          const int iy = iy0[i] + ty, ix = ix0[i] + tx;
+          const bool ok = iy >= 0 && iy < a.H_in && ix >= 0 && ix < a.W_in;
+          aptr[i] = ok ? a.x + (size_t)(pbase[i] + iy * a.W_in + ix) * a.ldx + ac * 8 : nullptr;
         }
-        // ---- B: weight rows of the active output channels, active input channels only
-        const __half* wt = a.w + (size_t)tap * a.C_in;
-        if (!a.k_idx) {
+        const int tapk = tap * a.C_in;
+        for (int kq = 0; kq < it.cpt; ++kq) {
+          const int k0 = kq * 64;
+          const int n16 = min(4, it.nk16 - kq * 4);
+          const int nch = 2 * n16;                            // 16-byte chunks the MMAs of this stage will read
+          mbar_wait(&T.empty[stage], phase ^ 1);
+          const uint32_t As = smem_base + stage * pl.stage_bytes;
+          const uint32_t Bs = As + A_STAGE_BYTES;
+          // ---- A: im2col gather of 128 pixel rows x 64 channels of this tap
           if (ac < nch) {
-            const int k = k0 + ac * 8;
-            const bool kok = k < a.C_in;
-            for (int j = ar0; j < it.umma_n; j += 16) {
-              const int off = T.brow[j];
-              const bool ok = kok && off >= 0;
-              cp_async_16(Bs + sw128_off(j, ac), ok ? wt + off + k : a.w, ok ? 16u : 0u);
+            const bool kok = k0 + ac * 8 < ka_lim;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const bool ok = kok && aptr[i] != nullptr;
+              cp_async_16(As + off0 + 4096 * i, ok ? aptr[i] + k0 : a.x, ok ? 16u : 0u);
             }
           }
-        } else if (ku * ub < nch * 16) {
-          const int e = k0 + ku * (ub >> 1);                   // compact input channel of this unit
-          const bool kok = e < it.Kc;
-          int col = 0;
-          if (kok) col = T.kidx[e / a.k_gran] * a.k_gran + e % a.k_gran;
-          const int c16 = (ku * ub) >> 4, w16 = (ku * ub) & 15;
-          for (int j = kr0; j < it.umma_n; j += krstep) {
-            const int off = T.brow[j];
-            const bool ok = kok && off >= 0;
-            const uint32_t dst = Bs + sw128_off(j, c16) + w16;
-            const __half* src = ok ? wt + off + col : a.w;
-            if (ub == 4) cp_async_4(dst, src, ok ? 4u : 0u);
-            else if (ub == 8) cp_async_8(dst, src, ok ? 8u : 0u);
-            else cp_async_16(dst, src, ok ? 16u : 0u);
+          // ---- B
+          if (mode == MODE_ROWS) {
+            if (ac < nch) {
+              const int k = k0 + ac * 8;
+              const bool kok = k < a.C_in;
+              const __half* wk = a.w + tapk + k;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (ar0 + 32 * i < it.umma_n) {
+                  const bool ok = kok && browr[i] >= 0;
+                  cp_async_16(Bs + off0 + 4096 * i, ok ? wk + browr[i] : a.w, ok ? 16u : 0u);
+                }
+              }
+            }
+          } else if (mode == MODE_KROWS) {
+            if (lane * 8 < it.umma_n) {
+              const bool nok = it.n0 + lane * 8 < a.C_out;
+              const __half* wn = a.wt + it.n0 + lane * 8;
+              const int nrows = 16 * n16;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int kk = pw + 8 * i;
+                if (kk < nrows) {
+                  const int e = k0 + kk;
+                  const bool ok = nok && e < it.Kc;
+                  int rk = 0;
+                  if (ok) rk = T.kch[e];
+                  cp_async_16(Bs + roff0 + 1024 * i, ok ? wn + (size_t)(tapk + rk) * a.C_out : a.w, ok ? 16u : 0u);
+                }
+              }
+            }
+          } else if (ku * ub < nch * 16) {
+            const int e = k0 + ku * (ub >> 1);                 // compact input channel of this unit
+            const bool kok = e < it.Kc;
+            int col = 0;
+            if (kok) col = T.kch[e];
+            const __half* wc = a.w + tapk + col;
+            uint32_t dst = Bs + koff0;
+            for (int j = kr0; j < it.umma_n; j += krstep, dst += 128 * krstep) {
+              const int off = T.brow[j];
+              const bool ok = kok && off >= 0;
+              const __half* src = ok ? wc + off : a.w;
+              if (ub == 4) cp_async_4(dst, src, ok ? 4u : 0u);
+              else if (ub == 8) cp_async_8(dst, src, ok ? 8u : 0u);
+              else cp_async_16(dst, src, ok ? 16u : 0u);
+            }
           }
+          cp_async_arrive(&T.full[stage]);
+          if (++stage == pl.stages) { stage = 0; phase ^= 1; }
         }
-        cp_async_arrive(&T.full[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
@@ -344,25 +418,33 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_umma_kernel(const __grid_
     if (lane == 0) {
       int stage = 0, acc = 0;
       uint32_t phase = 0, aphase = 0;
-      for (int t = blockIdx.x; t < total_items; t += gridDim.x) {
+      for (int t = blockIdx.x; t < pl.total_items; t += gridDim.x) {
         Item it;
-        if (!decode_item(a, t, n_mtiles, NT, it)) continue;
+        if (!decode_item(a, pl, t, it)) continue;
         mbar_wait(&T.tempty[acc], aphase ^ 1);              // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN_MAX;
-        const uint32_t idesc = umma_idesc_f16(it.umma_n);
+        const uint32_t idesc = umma_idesc_f16(it.umma_n, mode == MODE_KROWS);
         for (int ch = 0; ch < it.nchunks; ++ch) {
           const int kq = ch % it.cpt;
           const int n16 = min(4, it.nk16 - kq * 4);
           mbar_wait(&T.full[stage], phase);
           fence_proxy_async();
           tc_fence_after();
-          const uint32_t As = smem_base + stage * STAGE_BYTES;
-          const uint64_t ad = umma_desc_sw128(As), bd = umma_desc_sw128(As + A_STAGE_BYTES);
-          for (int k = 0; k < n16; ++k)                        // +32 B per K=16 step inside the swizzle atom
-            umma_f16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (ch | k) ? 1u : 0u);
+          const uint32_t As = smem_base + stage * pl.stage_bytes;
+          const uint32_t Bs = As + A_STAGE_BYTES;
+          const uint64_t ad = umma_desc(As, 16, 1024);
+          if (mode == MODE_KROWS) {
+            // B rows are k: one MMA consumes two 8-k groups (2 x 1024 B); 64-n blocks are 8192 B apart
+            const uint64_t bd = umma_desc(Bs, 8192, 1024);
+            for (int k = 0; k < n16; ++k) umma_f16(d_tmem, ad + 2 * k, bd + 128 * k, idesc, (ch | k) ? 1u : 0u);
+          } else {
+            const uint64_t bd = umma_desc(Bs, 16, 1024);
+            for (int k = 0; k < n16; ++k)                      // +32 B per K=16 step inside the swizzle atom
+              umma_f16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (ch | k) ? 1u : 0u);
+          }
           umma_commit(&T.empty[stage]);                         // frees the stage when these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == pl.stages) { stage = 0; phase ^= 1; }
         }
         if (it.nchunks > 0) umma_commit(&T.tfull[acc]);
         else mbar_arrive(&T.tfull[acc]);                        // no active input channel: accumulator is all zero
@@ -373,21 +455,36 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_umma_kernel(const __grid_
   } else {
     // =========================================================== epilogue
     const int et = threadIdx.x;                                 // 0..127 == accumulator row (TMEM lane)
+    unsigned char* srow = stg + (size_t)et * pl.stg_pitch;      // this thread's row of the staging tile
+    const uint32_t srow_u32 = smem_u32(srow);
+    const bool compact = (mode == MODE_KROWS) && a.n_idx;       // tile columns are real channels; store the active ones
     int acc = 0;
-    uint32_t aphase = 0;
-    for (int t = blockIdx.x; t < total_items; t += gridDim.x) {
+    uint32_t aphase = 0, rphase = 0;
+    for (int t = blockIdx.x; t < pl.total_items; t += gridDim.x) {
       Item it;
-      if (!decode_item(a, t, n_mtiles, NT, it)) continue;
+      if (!decode_item(a, pl, t, it)) continue;
       named_bar_sync(2, EPI_THREADS);                           // previous item's table reads are done
-      for (int j = et; j < it.umma_n; j += EPI_THREADS) {
-        const int jj = it.n0 + j;
-        int o = -1;
-        float sc = 1.f, sh = 0.f;
-        if (jj < it.Nc) {
-          o = a.n_idx ? __ldg(a.n_idx + (size_t)it.b * a.n_ld + jj / a.n_gran) * a.n_gran + jj % a.n_gran : jj;
-          if (a.scale) { sc = __ldg(a.scale + o); sh = __ldg(a.shift + o); }
+      for (int c = et; c < it.umma_n; c += EPI_THREADS) {
+        const int jj = it.n0 + c;
+        int o = -1, pos = c;
+        if (compact) {
+          // real channel jj: active iff its group is in the sample's ascending list; its rank is the compact position
+          if (c < it.n_valid) {
+            const int grp = jj / a.n_gran, na = it.Nc / a.n_gran;
+            const int* lst = a.n_idx + (size_t)it.b * a.n_ld;
+            int lo = 0, hi = na;
+            while (lo < hi) {
+              const int mid = (lo + hi) >> 1;
+              if (__ldg(lst + mid) < grp) lo = mid + 1; else hi = mid;
+            }
+            if (lo < na && __ldg(lst + lo) == grp) { o = jj; pos = lo * a.n_gran + jj % a.n_gran; }
+          }
+        } else if (jj < it.Nc) {
+          o = real_out_channel(a, it.b, jj);
         }
-        T.ochan[j] = o; T.scale[j] = sc; T.shift[j] = sh;
+        float sc = 1.f, sh = 0.f;
+        if (o >= 0 && a.scale) { sc = __ldg(a.scale + o); sh = __ldg(a.shift + o); }
+        T.ochan[c] = o; T.cpos[c] = pos; T.scale[c] = sc; T.shift[c] = sh;
       }
       const RowPos p = row_pos(a, it, et, HWo);
       const size_t pix = (size_t)p.b * HWo + (size_t)p.oy * a.W_out + p.ox;
@@ -396,9 +493,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_umma_kernel(const __grid_
         cls = border_class(p.oy, a.stride, a.pad, a.H_in) * 4 + border_class(p.ox, a.stride, a.pad, a.W_in);
       const float* pb = a.pre_bias ? a.pre_bias + ((size_t)p.b * a.pre_bias_classes + cls) * a.pre_bias_ld + it.n0 : nullptr;
       const int cpg = a.out_mask ? a.C_out / a.mask_groups : 1;
+      // stored row of this tile: [row_c0, row_c0 + row_n) of y's channel axis
+      const int row_c0 = compact ? 0 : it.n0;
+      const int row_n = compact ? it.Nfill : it.n_valid;
+      const bool staged = pl.staged && !(compact && it.ntiles > 1);
+      if (pl.staged) bulk_wait_read();                          // the previous store of this row has left shared memory
+      if (staged && a.residual) {
+        if (p.valid) {
+          mbar_arrive_expect_tx(&T.rfull, (uint32_t)row_n * 2);
+          bulk_load(srow_u32, a.residual + pix * a.ldr + row_c0, (uint32_t)row_n * 2, &T.rfull);
+        } else {
+          mbar_arrive(&T.rfull);
+        }
+      }
       named_bar_sync(2, EPI_THREADS);
       mbar_wait(&T.tfull[acc], aphase);
       tc_fence_after();
+      if (staged && a.residual) { mbar_wait(&T.rfull, rphase); rphase ^= 1; }
       const uint32_t taddr = tmem_base + acc * BN_MAX + ((uint32_t)(warp * 32) << 16);
       for (int c0 = 0; c0 < it.n_valid; c0 += 16) {
         float v[16];
@@ -418,9 +529,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_umma_kernel(const __grid_
           }
           __align__(16) __half rs[16];
           if (a.residual) {
-            const uint4* rp = reinterpret_cast<const uint4*>(a.residual + pix * a.ldr + it.n0 + c0);
-            *reinterpret_cast<uint4*>(rs) = __ldg(rp);
-            if (c0 + 8 < it.n_valid) *reinterpret_cast<uint4*>(rs + 8) = __ldg(rp + 1);
+            if (staged) {
+              *reinterpret_cast<uint4*>(rs) = *reinterpret_cast<const uint4*>(srow + c0 * 2);
+              *reinterpret_cast<uint4*>(rs + 8) = *reinterpret_cast<const uint4*>(srow + c0 * 2 + 16);
+            } else {
+              const uint4* rp = reinterpret_cast<const uint4*>(a.residual + pix * a.ldr + it.n0 + c0);
+              *reinterpret_cast<uint4*>(rs) = __ldg(rp);
+              if (c0 + 8 < it.n_valid) *reinterpret_cast<uint4*>(rs + 8) = __ldg(rp + 1);
+            }
           }
           __align__(16) __half out[16];
 #pragma unroll
@@ -432,19 +548,50 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_umma_kernel(const __grid_
               gate = a.out_mask[((size_t)p.b * a.mask_groups + o / cpg) * HWo + (size_t)p.oy * a.W_out + p.ox];
               if (a.relu_mode != LAUD_RELU_WHERE_GATE0) val = gate ? val : 0.f;
             }
-            if (a.residual && c0 + e < it.n_valid) val += __half2float(rs[e]);
+            if (a.residual) val += __half2float(rs[e]);
             if (a.relu_mode == LAUD_RELU_ALL || (a.relu_mode == LAUD_RELU_WHERE_GATE0 && !gate)) val = fmaxf(val, 0.f);
             out[e] = __float2half(o >= 0 ? val : 0.f);
           }
-          __half* yp = a.y + pix * a.ldy + it.n0 + c0;
-          *reinterpret_cast<uint4*>(yp) = *reinterpret_cast<const uint4*>(out);
-          if (c0 + 8 < it.n_valid) *reinterpret_cast<uint4*>(yp + 8) = *reinterpret_cast<const uint4*>(out + 8);
+          if (compact) {
+            // scatter the active columns to their compact positions (2-byte stores)
+            if (staged) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e)
+                if (T.ochan[c0 + e] >= 0) *reinterpret_cast<__half*>(srow + T.cpos[c0 + e] * 2) = out[e];
+            } else {
+              __half* yp = a.y + pix * a.ldy;
+#pragma unroll
+              for (int e = 0; e < 16; ++e)
+                if (T.ochan[c0 + e] >= 0) yp[T.cpos[c0 + e]] = out[e];
+            }
+          } else if (staged) {
+            *reinterpret_cast<uint4*>(srow + c0 * 2) = *reinterpret_cast<const uint4*>(out);
+            *reinterpret_cast<uint4*>(srow + c0 * 2 + 16) = *reinterpret_cast<const uint4*>(out + 8);
+          } else {
+            __half* yp = a.y + pix * a.ldy + it.n0 + c0;
+            *reinterpret_cast<uint4*>(yp) = *reinterpret_cast<const uint4*>(out);
+            if (c0 + 8 < it.n_valid) *reinterpret_cast<uint4*>(yp + 8) = *reinterpret_cast<const uint4*>(out + 8);
+          }
         }
       }
       tc_fence_before();
-      mbar_arrive(&T.tempty[acc]);
+      mbar_arrive(&T.tempty[acc]);                              // accumulator drained: the MMA warp may reuse it
       if (++acc == 2) { acc = 0; aphase ^= 1; }
+      if (p.valid && compact) {
+        // zero pad [Nc, Nfill) of the compact row (once per row: by the last n-tile)
+        if (staged) {
+          for (int j = it.Nc; j < it.Nfill; ++j) *reinterpret_cast<__half*>(srow + j * 2) = __float2half(0.f);
+        } else if (it.nt == it.ntiles - 1) {
+          for (int j = it.Nc; j < it.Nfill; ++j) a.y[pix * a.ldy + j] = __float2half(0.f);
+        }
+      }
+      if (staged) {
+        fence_proxy_async();                                    // generic-proxy row writes -> visible to the bulk copy
+        if (p.valid && row_n > 0) bulk_store(a.y + pix * a.ldy + row_c0, srow_u32, (uint32_t)row_n * 2);
+        bulk_commit();
+      }
     }
+    bulk_wait_all();
   }
 
   tc_fence_before();
@@ -468,7 +615,7 @@ bool conv_umma_supported(const ConvArgs& a) {
   if (a.pre_bias && (a.pre_bias_ld % 4 || !aligned16(a.pre_bias))) return false;
   if (a.k_idx) {
     if (a.k_gran != 2 && a.k_gran != 4 && a.k_gran % 8) return false;   // 4-, 8- or 16-byte gather units
-    if (a.k_ld > KIDX_MAX) return false;
+    if (a.C_in > KIDX_MAX) return false;
     if (a.ldx < round_up(a.C_in, 16)) return false;
   }
   if (a.n_idx && a.n_pad_align < 8) return false;
@@ -483,20 +630,40 @@ int conv_forward_umma(const ConvArgs& a, cudaStream_t s) {
     int dev = 0;
     LAUD_CUDA(cudaGetDevice(&dev));
     LAUD_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    LAUD_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    LAUD_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
   }
+  Plan pl;
+  pl.mode = (a.k_idx && a.wt && aligned16(a.wt)) ? MODE_KROWS : (a.k_idx ? MODE_KUNITS : MODE_ROWS);
   const long long HWo = (long long)a.H_out * a.W_out;
   const long long rows = a.row_idx ? (long long)a.B * HWo : HWo;
-  const int n_mtiles = (int)((rows + BM - 1) / BM);
-  const int NT = (round_up(a.C_out, a.n_pad_align) + BN_MAX - 1) / BN_MAX;
-  const long long total = (long long)(a.row_idx ? 1 : a.B) * n_mtiles * NT;
+  pl.n_mtiles = (int)((rows + BM - 1) / BM);
+  const int nfill_max = round_up(a.C_out, a.n_pad_align);
+  const int span = pl.mode == MODE_KROWS ? a.C_out : nfill_max;
+  pl.NT = (span + BN_MAX - 1) / BN_MAX;
+  const long long total = (long long)(a.row_idx ? 1 : a.B) * pl.n_mtiles * pl.NT;
   if (total >= (1ll << 31)) {
     set_error("conv_forward_umma: too many tiles");
     return LAUD_E_BADARG;
   }
+  pl.total_items = (int)total;
+  // widest tile of this launch -> B stage size, staging row pitch, pipeline depth
+  const int bn_cap = min(BN_MAX, round_up(span, 16));
+  const int b_bytes = pl.mode == MODE_KROWS ? ((bn_cap + 63) / 64) * 8192 : bn_cap * 128;
+  pl.stage_bytes = A_STAGE_BYTES + round_up(b_bytes, 1024);
+  const int row_max = (pl.mode == MODE_KROWS && a.n_idx) ? max(round_up(nfill_max, 16), bn_cap) : bn_cap;   // stored-row width
+  pl.stg_pitch = row_max * 2 + 16;
+  pl.staged = 1;
+  int avail = SMEM_LIMIT - 1024 - (int)sizeof(Tables) - BM * pl.stg_pitch;
+  if (avail < 2 * pl.stage_bytes) {        // staging tile does not fit beside a 2-stage pipeline: direct stores
+    pl.staged = 0;
+    avail = SMEM_LIMIT - 1024 - (int)sizeof(Tables);
+  }
+  pl.stages = avail / pl.stage_bytes;
+  if (pl.stages > MAX_STAGES) pl.stages = MAX_STAGES;
+  const size_t smem = 1024 + (size_t)pl.stages * pl.stage_bytes + (pl.staged ? (size_t)BM * pl.stg_pitch : 0) + sizeof(Tables);
   const int grid = (int)(total < num_sms ? total : num_sms);
   g_conv_paths[0].fetch_add(1, std::memory_order_relaxed);
-  conv_umma_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(a, n_mtiles, NT, (int)total);
+  conv_umma_kernel<<<grid, NUM_THREADS, smem, s>>>(a, pl);
   return check_launch("conv_umma_kernel");
 }
 

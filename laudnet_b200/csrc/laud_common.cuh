@@ -75,6 +75,7 @@ struct ConvArgs {
   const int* row_idx; const int* row_cnt;
   int n_pad_align;
   float* gap_partial; int gap_tiles;
+  const __half* wt;
 };
 
 int conv_forward_naive(const ConvArgs& a, cudaStream_t s);

@@ -11,14 +11,18 @@ sys.path.insert(0, ROOT)
 from laudnet_b200 import _lib            # noqa: E402
 from tests import test_gpu_parity as T   # noqa: E402
 
-impls = {"umma": _lib.CONV_UMMA, "hmma": _lib.CONV_HMMA}
+impls = {"umma": _lib.CONV_UMMA, "umma_wt": "wt"}
+if os.environ.get("DIAG_HMMA"):
+    impls["hmma"] = _lib.CONV_HMMA
 only = sys.argv[1:] or list(T.CONV_CASES)
 bad = 0
 for name in only:
     d = T._conv_case(sum(map(ord, name)), **T.CONV_CASES[name])
     for iname, impl in impls.items():
+        if impl == "wt" and name not in T.WT_CASES:
+            continue
         try:
-            err = T._run_conv_case(d, impl)
+            err = T._run_conv_case(d, _lib.CONV_UMMA, use_wt=True) if impl == "wt" else T._run_conv_case(d, impl)
             flag = "OK " if err <= T.ACT_TOL else "BAD"
             print(f"{flag} {name:24s} {iname}: normalised max err {err:.3e}", flush=True)
             bad += err > T.ACT_TOL

@@ -221,7 +221,7 @@ def _lists(mask_u8):
     return order.contiguous().to(DEV), m.sum(1).to(torch.int32).contiguous().to(DEV)
 
 
-def _run_conv_case(d, impl):
+def _run_conv_case(d, impl, use_wt=False):
     B, H, Cin, Cout, k, Ho = d["B"], d["H"], d["Cin"], d["Cout"], d["k"], d["Ho"]
     kg = d.get("kmask")
     ng = d.get("nmask")
@@ -240,6 +240,8 @@ def _run_conv_case(d, impl):
         kw.update(k_idx=kidx, k_cnt=kcnt, k_gran=gran)
     xd = x_nhwc.half().to(DEV)
     wd = _engine.pack_conv_weight(d["w"]).to(DEV)
+    if use_wt:          # transposed copy [taps, C_in, C_out]: selects the K-row-gather (MN-major B) path
+        kw["w_t"] = _engine.pack_conv_weight_t(d["w"]).to(DEV)
     ldy = Cout
     if ng is not None:
         ngran = Cout // ng.shape[1]
@@ -249,7 +251,7 @@ def _run_conv_case(d, impl):
     y = torch.full((B, Ho, Ho, ldy), 7.0, dtype=torch.float16, device=DEV)
     if "prebias_full" in d:
         pb = d["prebias_full"]
-        if ng is not None:      # pre-bias is indexed by COMPACT output channel
+        if ng is not None and not (use_wt and kg is not None):      # pre-bias is indexed by COMPACT output channel
             pbc = torch.zeros_like(pb)
             for b in range(B):
                 ch = (nidx[b, :ncnt[b]].cpu().long().view(-1, 1) * ngran + torch.arange(ngran).view(1, -1)).view(-1)
@@ -317,7 +319,11 @@ CONV_CASES = {
     "1x1_samples": dict(B=6, H=7, Cin=64, Cout=32, k=1, stride=1, samples=True),
     "3x3_wide_N": dict(B=2, H=7, Cin=128, Cout=512, k=3, stride=1, kgather=2, ngather=2, prebias=True),
     "1x1_tail_rows": dict(B=1, H=13, Cin=40, Cout=72, k=1, stride=1),
+    "3x3_kn_gather_big": dict(B=3, H=14, Cin=256, Cout=256, k=3, stride=1, kgather=2, ngather=2, prebias=True),
+    "1x1_kgather_wide": dict(B=3, H=14, Cin=256, Cout=1024, k=1, stride=1, kgather=2, prebias=True, residual=True),
 }
+# cases with a K gather also run through the K-row-gather path (transposed weights supplied)
+WT_CASES = [n for n, c in CONV_CASES.items() if c.get("kgather")]
 
 
 @pytest.mark.parametrize("impl", [_lib.CONV_UMMA, _lib.CONV_HMMA, _lib.CONV_NAIVE], ids=["umma", "hmma", "naive"])
@@ -325,6 +331,13 @@ CONV_CASES = {
 def test_conv_forward_vs_oracle(cuda_lib, name, impl):
     d = _conv_case(abs(hash(name)) % 1000 if False else sum(map(ord, name)), **CONV_CASES[name])
     err = _run_conv_case(d, impl)
+    assert err <= ACT_TOL, f"{name}: normalised max error {err:.2e} > {ACT_TOL}"
+
+
+@pytest.mark.parametrize("name", WT_CASES)
+def test_conv_forward_krows_vs_oracle(cuda_lib, name):
+    d = _conv_case(sum(map(ord, name)), **CONV_CASES[name])
+    err = _run_conv_case(d, _lib.CONV_UMMA, use_wt=True)
     assert err <= ACT_TOL, f"{name}: normalised max error {err:.2e} > {ACT_TOL}"
 
 
