@@ -171,23 +171,37 @@ typedef struct laud_conv_desc {
                                selects the K-row-gather path (16-byte gathers of the active input channels;
                                all output channels are computed and, with n_idx, compacted in the epilogue).
                                In that path pre_bias is indexed by REAL output channel, not compact column. */
+  const void* bias_t;       /* optional, w_t path only: H1 constants fp16 [B, ksize*ksize, C_out] (sample pitch
+                               bias_ld elements).  Enters the GEMM as one extra K=16 step:
+                               acc[p,o] += sum_{taps of p that fall inside the input} bias_t[b,tap,o].
+                               Replaces pre_bias (mutually exclusive). */
+  int32_t bias_ld;
 } laud_conv_desc;
 
 int laud_conv_forward(const laud_conv_desc* desc /* host */, int impl, void* stream);
 
 /* H1 constants of channel-skipping with mask-before-BN (laud_resnet.py:115-118,
  * 123-126): a masked channel k of conv1's (conv2's) output is the constant
- * c_k = relu(shift_k) after BN+ReLU.  For every sample this computes
- *   pre_bias2[b, cls, j] = sum_{taps valid in border class cls} sum_{k masked}
- *                          relu(shift1[k]) * w2[o_j, tap, k]    (active o_j, compact j)
- *   pre_bias3[b, 0, o]   = sum_{k masked} relu(shift2[k]) * w3[o, k]   (all o)
- * idx/cnt are the masker outputs (active ids first, then inactive ids). */
-int laud_channel_consts(const void* w2, const void* w3, int width, int C_out,
-                        const float* shift1, const float* shift2,
-                        const int32_t* idx, const int32_t* cnt, int B, int G, int gran,
-                        int H_in, int W_in, int H_out, int W_out, int stride,
-                        float* pre_bias2 /* [B,16,width] */, float* pre_bias3 /* [B,1,C_out] */,
-                        void* stream);
+ * c_k = relu(shift_k) after BN+ReLU, so the exact sparse conv2 / conv3 add
+ *   T2[b,tap,o] = sum_{k masked} relu(shift1[k]) * w2[o,tap,k]   (per valid tap)
+ *   T3[b,o]     = sum_{k masked} relu(shift2[k]) * w3[o,k]
+ * Both are ONE dense GEMM  inact[B,width] x cw[9*width + C_out, width]^T  run with
+ * laud_conv_forward (1x1, B=1, H_out*W_out = batch), where cw are the weights
+ * pre-scaled by relu(shift) (packed once per model) and inact is the 0/1
+ * indicator of the masked channels:
+ *   laud_gate_inactive: mask u8 [B,G] -> inact fp16 [B, G*gran] (1.0 where masked)
+ * On the w_t path T feeds the convolutions directly (laud_conv_desc.bias_t: one extra K=16
+ * MMA step, no pre_bias).  For the other layouts:
+ *   laud_channel_consts_fold: T fp16 [B, 9*width + C_out] (the GEMM output, T2 rows tap-major) ->
+ *     pre_bias2 fp32 [B,16,width]: the 9 taps folded into the 16 border classes,
+ *       indexed by compact active output channel (compact_index=1, needs idx/cnt)
+ *       or by real output channel (compact_index=0, the w_t path);
+ *     pre_bias3 fp32 [B,C_out]. */
+int laud_gate_inactive(const uint8_t* mask, int B, int G, int gran, void* inact_f16, void* stream);
+int laud_channel_consts_fold(const void* T, int B, int width, int C_out, const int32_t* idx,
+                             const int32_t* cnt, int G, int gran, int compact_index,
+                             float* pre_bias2 /* [B,16,width] */, float* pre_bias3 /* [B,C_out] */,
+                             void* stream);
 
 /* ---------------------------------------------------------------------------
  * (a8) network ends.  Stem: conv7x7/2 + BN + ReLU + maxpool3x3/2 fused

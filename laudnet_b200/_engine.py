@@ -78,7 +78,7 @@ def run_conv(x, w, y, B, H_in, W_in, C_in, H_out, W_out, C_out, ksize, stride, p
              k_idx=None, k_cnt=None, k_gran=1, n_idx=None, n_cnt=None, n_gran=1,
              pre_bias=None, pre_bias_classes=0, pre_bias_ld=0, out_mask=None, mask_groups=1,
              sample_idx=None, sample_cnt=None, row_idx=None, row_cnt=None, n_pad_align=0,
-             impl=_lib.CONV_AUTO, tag="conv", w_t=None) -> None:
+             impl=_lib.CONV_AUTO, tag="conv", w_t=None, bias_t=None, bias_ld=0) -> None:
     """Fill a laud_conv_desc and enqueue laud_conv_forward on the current stream."""
     d = ConvDesc()
     d.x, d.ldx = ptr(x), ldx if ldx is not None else x.shape[-1]
@@ -101,6 +101,7 @@ def run_conv(x, w, y, B, H_in, W_in, C_in, H_out, W_out, C_out, ksize, stride, p
     d.n_pad_align = n_pad_align
     d.gap_partial, d.gap_tiles = None, 0
     d.w_t = ptr(w_t)
+    d.bias_t, d.bias_ld = ptr(bias_t), bias_ld
     prof = conv_profile.active
     if prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -139,11 +140,31 @@ class BlockPlan:
     t3: torch.Tensor = None
     sd: Optional[torch.Tensor] = None
     td: Optional[torch.Tensor] = None
+    w2t: Optional[torch.Tensor] = None      # transposed copies for the K-row-gather path
+    w3t: Optional[torch.Tensor] = None
+    cw: Optional[torch.Tensor] = None       # H1 constants: [9*width + outplanes, width] weights pre-scaled by relu(shift)
     module: nn.Module = None
 
     @property
     def use_c(self) -> bool:
         return self.mode in ("channel", "both")
+
+    @property
+    def krows_ok(self) -> bool:
+        """Channel granularities the 16-byte K-row-gather path takes (laud_conv_desc.w_t)."""
+        return self.use_c and (self.gran in (2, 4) or self.gran % 8 == 0) and self.width <= 1024
+
+    def pack_channel_mode(self, blk) -> None:
+        """Per-model packing for channel skipping: transposed conv2/conv3 weights and the
+        relu(shift)-scaled weights of the H1-constant GEMM (include/laud_b200.h)."""
+        with torch.no_grad():
+            self.w2t = pack_conv_weight_t(blk.conv2.weight)
+            self.w3t = pack_conv_weight_t(blk.conv3.weight)
+            c1, c2 = torch.relu(self.t1), torch.relu(self.t2)
+            # rows ordered (tap, o): T2[b] comes out as [tap][o], the layout laud_conv_desc.bias_t wants
+            w2s = (blk.conv2.weight.detach().float() * c1.view(1, -1, 1, 1)).permute(2, 3, 0, 1).reshape(9 * self.width, self.width)
+            w3s = blk.conv3.weight.detach().float().view(self.outplanes, self.width) * c2.view(1, -1)
+            self.cw = torch.cat([w2s, w3s]).to(torch.float16).contiguous()
 
     @property
     def use_s(self) -> bool:
@@ -198,6 +219,8 @@ class ResNetEngine:
                 if blk.downsample is not None:
                     p.wd = pack_conv_weight(blk.downsample[0].weight)
                     p.sd, p.td = fold_bn(blk.downsample[1])
+                if p.use_c:
+                    p.pack_channel_mode(blk)
                 for cdim in (p.inplanes, p.width, p.outplanes):
                     if cdim % 8:
                         raise LaudError(f"channel counts must be multiples of 8 for the fp16 kernels (got {cdim})")
@@ -259,6 +282,7 @@ class ResNetEngine:
             cidx=torch.empty((B, Gmax), **i32), ccnt=torch.empty((B,), **i32),
             pb2=torch.empty(B * 16 * wmax, dtype=torch.float32, device=dev),
             pb3=torch.empty(B * comax, dtype=torch.float32, device=dev),
+            inact=torch.empty(B * wmax, **f16), T=torch.empty(B * (9 * wmax + comax), **f16),
             smask=torch.empty(B * g_max * hw_max, dtype=torch.uint8, device=dev),
             m3=torch.empty(B * g_max * hw_max, dtype=torch.uint8, device=dev),
             m2=torch.empty(B * g_max * hw_max, dtype=torch.uint8, device=dev),
@@ -291,6 +315,8 @@ class ResNetEngine:
         gate = None
         m3 = None
         wp = p.width + 16                       # channel pitch of the compact intermediates
+        use_wt = False
+        T, Tn = None, 0
         if p.use_c:
             from .utils import _ChannelGate
             G = p.G
@@ -304,9 +330,18 @@ class ResNetEngine:
             else:
                 blk.masker_channel.gate_nhwc(x[:B * Hi * Hi * p.inplanes].view(B, Hi, Hi, p.inplanes), counts[0:1],
                                              out=gate, partial_ws=ws["partial"])
-            check(L.laud_channel_consts(ptr(p.w2), ptr(p.w3), p.width, p.outplanes, ptr(p.t1), ptr(p.t2),
-                                        ptr(gate.idx), ptr(gate.cnt), B, G, p.gran, Hi, Hi, Ho, Ho, p.stride,
-                                        ptr(ws["pb2"]), ptr(ws["pb3"]), st), "laud_channel_consts")
+            # H1 constants: 0/1 indicator of the masked channels -> one dense GEMM -> fold taps into border classes
+            use_wt = p.krows_ok and self.impl in (_lib.CONV_AUTO, _lib.CONV_UMMA)
+            inact = ws["inact"][:B * p.width].view(B, p.width)
+            Tn = 9 * p.width + p.outplanes
+            T = ws["T"][:B * Tn].view(B, Tn)
+            check(L.laud_gate_inactive(ptr(gate.mask), B, G, p.gran, ptr(inact), st), "laud_gate_inactive")
+            run_conv(inact, p.cw, T, 1, B, 1, p.width, B, 1, Tn, 1, 1, 0, ldx=p.width, ldy=Tn, impl=self.impl,
+                     tag=f"s{p.stage + 1}.h1gemm")
+            if not use_wt:      # fallback layouts: fold the taps into per-border-class pre-bias tables
+                check(L.laud_channel_consts_fold(ptr(T), B, p.width, p.outplanes, ptr(gate.idx), ptr(gate.cnt), G,
+                                                 p.gran, 1, ptr(ws["pb2"]), ptr(ws["pb3"]), st),
+                      "laud_channel_consts_fold")
         if p.use_s:
             g = p.g_spatial
             S = min(p.mask_size, Hi)
@@ -342,8 +377,9 @@ class ResNetEngine:
         # conv2 3x3/stride (+ mask) + bn2 + relu     laud_resnet.py:123-126
         run_conv(a1, p.w2, a2, B, Hi, Hi, p.width, Ho, Ho, p.width, 3, p.stride, 1, ldx=ld12, ldy=ld12,
                  scale=p.s2, shift=p.t2, relu=_lib.RELU_ALL, impl=self.impl, tag=f"s{p.stage + 1}.conv2",
-                 pre_bias=ws["pb2"] if gate else None, pre_bias_classes=16 if gate else 0,
-                 pre_bias_ld=p.width if gate else 0, **ck, **cn)
+                 pre_bias=ws["pb2"] if (gate and not use_wt) else None, pre_bias_classes=16 if (gate and not use_wt) else 0,
+                 pre_bias_ld=p.width if gate else 0, w_t=p.w2t if use_wt else None,
+                 bias_t=T if use_wt else None, bias_ld=Tn if use_wt else 0, **ck, **cn)
         # identity branch      laud_resnet.py:138-141
         if p.wd is not None:
             run_conv(x, p.wd, idbuf, B, Hi, Hi, p.inplanes, Ho, Ho, p.outplanes, 1, p.stride, 0, ldx=p.inplanes,
@@ -355,9 +391,11 @@ class ResNetEngine:
         # conv3 1x1 + bn3 (+ spatial mask) + identity + relu     laud_resnet.py:131-144
         run_conv(a2, p.w3, out, B, Ho, Ho, p.width, Ho, Ho, p.outplanes, 1, 1, 0, ldx=ld12, ldy=p.outplanes,
                  scale=p.s3, shift=p.t3, relu=_lib.RELU_ALL, residual=res, ldr=p.outplanes, impl=self.impl,
-                 tag=f"s{p.stage + 1}.conv3", pre_bias=ws["pb3"] if gate else None, pre_bias_classes=1 if gate else 0,
+                 tag=f"s{p.stage + 1}.conv3", pre_bias=ws["pb3"] if (gate and not use_wt) else None,
+                 pre_bias_classes=1 if (gate and not use_wt) else 0,
+                 bias_t=T.view(-1)[9 * p.width:] if use_wt else None, bias_ld=Tn if use_wt else 0,
                  pre_bias_ld=p.outplanes if gate else 0, out_mask=m3, mask_groups=p.g_spatial if m3 is not None else 1,
-                 **ck)
+                 w_t=p.w3t if (gate and use_wt) else None, **ck)
         if keep is not None:
             if gate is not None:
                 keep.channel_mask, keep.channel_idx, keep.channel_cnt = gate.mask.clone(), gate.idx.clone(), gate.cnt.clone()

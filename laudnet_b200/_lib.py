@@ -44,6 +44,7 @@ class ConvDesc(C.Structure):
         ("n_pad_align", C.c_int32),
         ("gap_partial", _vp), ("gap_tiles", C.c_int32),
         ("w_t", _vp),
+        ("bias_t", _vp), ("bias_ld", C.c_int32),
     ]
 
 
@@ -61,7 +62,8 @@ SIGNATURES = {
     "laud_resize_mask_nearest": ([_u8p, _i, _i, _i, _i, _u8p, _vp], _i),
     "laud_compact_rows": ([_u8p, _i, _i, _i, _i32p, _i32p, _i32p, _vp], _i),
     "laud_conv_forward": ([C.POINTER(ConvDesc), _i, _vp], _i),
-    "laud_channel_consts": ([_vp, _vp, _i, _i, _fp, _fp, _i32p, _i32p, _i, _i, _i, _i, _i, _i, _i, _i, _fp, _fp, _vp], _i),
+    "laud_gate_inactive": ([_u8p, _i, _i, _i, _vp, _vp], _i),
+    "laud_channel_consts_fold": ([_vp, _i, _i, _i, _i32p, _i32p, _i, _i, _i, _fp, _fp, _vp], _i),
     "laud_stem_forward": ([_vp, _i, _i, _i, _vp, _i, _fp, _fp, _vp, _vp], _i),
     "laud_head_forward": ([_vp, _i, _i, _i, _vp, _fp, _i, _fp, _fp, _vp], _i),
     "laud_nchw_to_nhwc_f16": ([_vp, _i, _i, _i, _i, _i, _vp, _i, _vp], _i),

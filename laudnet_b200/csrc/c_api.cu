@@ -70,6 +70,13 @@ extern "C" int laud_conv_forward(const laud_conv_desc* d, int impl, void* stream
   LAUD_REQUIRE(d->relu_mode != LAUD_RELU_WHERE_GATE0 || d->out_mask, "laud_conv_forward: RELU_WHERE_GATE0 needs out_mask");
   if (d->residual) LAUD_REQUIRE(d->ldr >= d->C_out && !d->n_idx, "laud_conv_forward: residual needs dense output channels");
   LAUD_REQUIRE(d->gap_partial == nullptr, "laud_conv_forward: fused GAP epilogue not available in this build");
+  if (d->bias_t)
+    LAUD_REQUIRE(d->w_t && d->k_idx && !d->pre_bias && d->bias_ld % 8 == 0 && d->ksize * d->ksize <= 9 &&
+                     (reinterpret_cast<uintptr_t>(d->bias_t) & 15) == 0,
+                 "laud_conv_forward: bias_t needs the w_t path (k_idx + w_t), no pre_bias, bias_ld %% 8 == 0");
+  if (d->w_t && d->k_idx)
+    LAUD_REQUIRE(impl == LAUD_CONV_AUTO || impl == LAUD_CONV_UMMA,
+                 "laud_conv_forward: w_t (K-row-gather path, real-channel pre_bias) is a tcgen05-path argument");
 
   ConvArgs a;
   a.x = (const __half*)d->x; a.ldx = d->ldx;
@@ -89,11 +96,17 @@ extern "C" int laud_conv_forward(const laud_conv_desc* d, int impl, void* stream
   a.n_pad_align = d->n_pad_align;
   a.gap_partial = d->gap_partial; a.gap_tiles = d->gap_tiles;
   a.wt = (const __half*)d->w_t;
+  a.bias_t = (const __half*)d->bias_t; a.bias_ld = d->bias_ld;
 
   cudaStream_t s = (cudaStream_t)stream;
   switch (impl) {
     case LAUD_CONV_AUTO:
     case LAUD_CONV_UMMA:
+      if (a.wt && a.k_idx && !conv_umma_supported(a)) {
+        set_error("laud_conv_forward: layout not supported by the tcgen05 kernel but w_t was given "
+                  "(channel granularity must be 2, 4 or a multiple of 8; pitches multiples of 8; 16-byte aligned)");
+        return LAUD_E_UNSUPPORTED;
+      }
       return conv_forward_umma(a, s);
     case LAUD_CONV_HMMA:
       return conv_forward_hmma(a, s);

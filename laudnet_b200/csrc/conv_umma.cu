@@ -52,6 +52,14 @@ constexpr int SMEM_LIMIT = 232448;               // 227 KB opt-in maximum per CT
 
 enum { MODE_ROWS = 1, MODE_KROWS = 2, MODE_KUNITS = 3 };
 
+// Tap-validity rows for the H1-constant K-step: row `mask` (9-bit set of filter taps that fall
+// inside the input) holds 1.0 at the valid taps, 0 elsewhere (16 fp16).  Filled once per process.
+__device__ __half g_vtab[512 * 16];
+__global__ void vtab_init_kernel() {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 512 * 16) g_vtab[i] = __float2half(((i & 15) < 9 && ((i >> 4) >> (i & 15) & 1)) ? 1.f : 0.f);
+}
+
 struct Tables {
   int brow[BN_MAX];        // KUNITS: element offset of the weight row of compact column j (or -1)
   int kch[KIDX_MAX];       // real input channel of this sample's compact input channel e
@@ -186,7 +194,7 @@ __device__ __forceinline__ uint32_t sw128_off(int r, int c) {
 
 // ------------------------------------------------------------------ work items
 struct Item {
-  int b, mt, nt, ntiles, n0, n_valid, umma_n, Nc, Nfill, Kc, nk16, cpt, nchunks;
+  int b, mt, nt, ntiles, n0, n_valid, umma_n, Nc, Nfill, Kc, nk16, cpt, nchunks, has_bias;
 };
 
 __device__ __forceinline__ bool decode_item(const ConvArgs& a, const Plan& pl, int t, Item& it) {
@@ -217,7 +225,8 @@ __device__ __forceinline__ bool decode_item(const ConvArgs& a, const Plan& pl, i
   it.Kc = a.k_idx ? __ldg(a.k_cnt + b) * a.k_gran : a.C_in;
   it.nk16 = (it.Kc + 15) >> 4;
   it.cpt = (it.nk16 + 3) >> 2;
-  it.nchunks = it.cpt * a.ksize * a.ksize;
+  it.has_bias = (pl.mode == MODE_KROWS && a.bias_t != nullptr) ? 1 : 0;   // H1 constants as one extra K=16 step
+  it.nchunks = it.cpt * a.ksize * a.ksize + it.has_bias;
   return true;
 }
 
@@ -411,6 +420,37 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_umma_kernel(const __grid_
           if (++stage == pl.stages) { stage = 0; phase ^= 1; }
         }
       }
+      if (it.has_bias) {
+        // one more K=16 step: A' = tap-validity indicator of each pixel, B' = this sample's H1 constants
+        // T[b, tap, o] (zero rows for tap >= taps): adds sum_{valid taps} T[b,tap,o] to the accumulator
+        mbar_wait(&T.empty[stage], phase ^ 1);
+        const uint32_t As = smem_base + stage * pl.stage_bytes;
+        const uint32_t Bs = As + A_STAGE_BYTES;
+        if (ac < 2) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            int vm = 0;
+            for (int tap = 0; tap < taps; ++tap) {
+              const int iy = iy0[i] + tap / a.ksize, ix = ix0[i] + tap % a.ksize;
+              if (iy >= 0 && iy < a.H_in && ix >= 0 && ix < a.W_in) vm |= 1 << tap;
+            }
+            cp_async_16(As + off0 + 4096 * i, g_vtab + vm * 16 + ac * 8, 16u);
+          }
+        }
+        if (lane * 8 < it.umma_n) {
+          const bool nok = it.n0 + lane * 8 < a.C_out;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int kk = pw + 8 * i;
+            const bool ok = nok && kk < taps;
+            cp_async_16(Bs + roff0 + 1024 * i,
+                        ok ? a.bias_t + (size_t)it.b * a.bias_ld + (size_t)kk * a.C_out + it.n0 + lane * 8 : a.w,
+                        ok ? 16u : 0u);
+          }
+        }
+        cp_async_arrive(&T.full[stage]);
+        if (++stage == pl.stages) { stage = 0; phase ^= 1; }
+      }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
   } else if (warp == MMA_WARP) {
@@ -426,8 +466,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_umma_kernel(const __grid_
         const uint32_t d_tmem = tmem_base + acc * BN_MAX;
         const uint32_t idesc = umma_idesc_f16(it.umma_n, mode == MODE_KROWS);
         for (int ch = 0; ch < it.nchunks; ++ch) {
-          const int kq = ch % it.cpt;
-          const int n16 = min(4, it.nk16 - kq * 4);
+          const bool bias_step = it.has_bias && ch == it.nchunks - 1;
+          const int n16 = bias_step ? 1 : min(4, it.nk16 - (ch % it.cpt) * 4);
           mbar_wait(&T.full[stage], phase);
           fence_proxy_async();
           tc_fence_after();
@@ -482,9 +522,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_umma_kernel(const __grid_
         } else if (jj < it.Nc) {
           o = real_out_channel(a, it.b, jj);
         }
-        float sc = 1.f, sh = 0.f;
+        float sc = o >= 0 ? 1.f : 0.f, sh = 0.f;      // inactive / pad columns come out as exact zeros
         if (o >= 0 && a.scale) { sc = __ldg(a.scale + o); sh = __ldg(a.shift + o); }
-        T.ochan[c] = o; T.cpos[c] = pos; T.scale[c] = sc; T.shift[c] = sh;
+        T.ochan[c] = o; T.cpos[c] = o >= 0 ? pos : -1; T.scale[c] = sc; T.shift[c] = sh;
       }
       const RowPos p = row_pos(a, it, et, HWo);
       const size_t pix = (size_t)p.b * HWo + (size_t)p.oy * a.W_out + p.ox;
@@ -511,6 +551,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_umma_kernel(const __grid_
       tc_fence_after();
       if (staged && a.residual) { mbar_wait(&T.rfull, rphase); rphase ^= 1; }
       const uint32_t taddr = tmem_base + acc * BN_MAX + ((uint32_t)(warp * 32) << 16);
+      // generic path: per-class pre-bias table, per-group spatial gates, RELU_WHERE_GATE0 (fallback layouts)
+      const bool generic = pb != nullptr || (a.out_mask && a.mask_groups != 1) || a.relu_mode == LAUD_RELU_WHERE_GATE0;
+      const bool relu_all = a.relu_mode == LAUD_RELU_ALL;
+      bool row_on = true;                                        // spatial gate of this pixel (one mask group)
+      if (!generic && a.out_mask && p.valid) row_on = a.out_mask[(size_t)p.b * HWo + (size_t)p.oy * a.W_out + p.ox] != 0;
       for (int c0 = 0; c0 < it.n_valid; c0 += 16) {
         float v[16];
         if (it.nchunks > 0) {
@@ -519,7 +564,50 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_umma_kernel(const __grid_
 #pragma unroll
           for (int e = 0; e < 16; ++e) v[e] = 0.f;
         }
-        if (p.valid) {
+        if (!p.valid) continue;
+        __align__(16) __half2 out2[8];
+        __half* out = reinterpret_cast<__half*>(out2);
+        __align__(16) __half2 rs2[8];
+        if (a.residual) {
+          if (staged) {
+            *reinterpret_cast<uint4*>(rs2) = *reinterpret_cast<const uint4*>(srow + c0 * 2);
+            *reinterpret_cast<uint4*>(rs2 + 4) = *reinterpret_cast<const uint4*>(srow + c0 * 2 + 16);
+          } else {
+            const uint4* rp = reinterpret_cast<const uint4*>(a.residual + pix * a.ldr + it.n0 + c0);
+            *reinterpret_cast<uint4*>(rs2) = __ldg(rp);
+            if (c0 + 8 < it.n_valid) *reinterpret_cast<uint4*>(rs2 + 4) = __ldg(rp + 1);
+          }
+        }
+        if (!generic) {
+          const float4* scp = reinterpret_cast<const float4*>(T.scale + c0);
+          const float4* shp = reinterpret_cast<const float4*>(T.shift + c0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 s4 = scp[q], h4 = shp[q];
+            v[4 * q] = fmaf(v[4 * q], s4.x, h4.x);
+            v[4 * q + 1] = fmaf(v[4 * q + 1], s4.y, h4.y);
+            v[4 * q + 2] = fmaf(v[4 * q + 2], s4.z, h4.z);
+            v[4 * q + 3] = fmaf(v[4 * q + 3], s4.w, h4.w);
+          }
+          if (!row_on) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = 0.f;
+          }
+          if (a.residual) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float2 r = __half22float2(rs2[q]);
+              v[2 * q] += r.x;
+              v[2 * q + 1] += r.y;
+            }
+          }
+          if (relu_all) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) out2[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
+        } else {
           if (pb) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -527,18 +615,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_umma_kernel(const __grid_
               v[4 * q] += f.x; v[4 * q + 1] += f.y; v[4 * q + 2] += f.z; v[4 * q + 3] += f.w;
             }
           }
-          __align__(16) __half rs[16];
-          if (a.residual) {
-            if (staged) {
-              *reinterpret_cast<uint4*>(rs) = *reinterpret_cast<const uint4*>(srow + c0 * 2);
-              *reinterpret_cast<uint4*>(rs + 8) = *reinterpret_cast<const uint4*>(srow + c0 * 2 + 16);
-            } else {
-              const uint4* rp = reinterpret_cast<const uint4*>(a.residual + pix * a.ldr + it.n0 + c0);
-              *reinterpret_cast<uint4*>(rs) = __ldg(rp);
-              if (c0 + 8 < it.n_valid) *reinterpret_cast<uint4*>(rs + 8) = __ldg(rp + 1);
-            }
-          }
-          __align__(16) __half out[16];
+          const __half* rs = reinterpret_cast<const __half*>(rs2);
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
             const int o = T.ochan[c0 + e];
@@ -552,26 +629,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_umma_kernel(const __grid_
             if (a.relu_mode == LAUD_RELU_ALL || (a.relu_mode == LAUD_RELU_WHERE_GATE0 && !gate)) val = fmaxf(val, 0.f);
             out[e] = __float2half(o >= 0 ? val : 0.f);
           }
-          if (compact) {
-            // scatter the active columns to their compact positions (2-byte stores)
-            if (staged) {
+        }
+        if (compact) {
+          // scatter the active columns to their compact positions (2-byte stores)
+          const int4* cpp = reinterpret_cast<const int4*>(T.cpos + c0);
+          __half* dst = staged ? reinterpret_cast<__half*>(srow) : a.y + pix * a.ldy;
 #pragma unroll
-              for (int e = 0; e < 16; ++e)
-                if (T.ochan[c0 + e] >= 0) *reinterpret_cast<__half*>(srow + T.cpos[c0 + e] * 2) = out[e];
-            } else {
-              __half* yp = a.y + pix * a.ldy;
-#pragma unroll
-              for (int e = 0; e < 16; ++e)
-                if (T.ochan[c0 + e] >= 0) yp[T.cpos[c0 + e]] = out[e];
-            }
-          } else if (staged) {
-            *reinterpret_cast<uint4*>(srow + c0 * 2) = *reinterpret_cast<const uint4*>(out);
-            *reinterpret_cast<uint4*>(srow + c0 * 2 + 16) = *reinterpret_cast<const uint4*>(out + 8);
-          } else {
-            __half* yp = a.y + pix * a.ldy + it.n0 + c0;
-            *reinterpret_cast<uint4*>(yp) = *reinterpret_cast<const uint4*>(out);
-            if (c0 + 8 < it.n_valid) *reinterpret_cast<uint4*>(yp + 8) = *reinterpret_cast<const uint4*>(out + 8);
+          for (int q = 0; q < 4; ++q) {
+            const int4 cp = cpp[q];
+            if (cp.x >= 0) dst[cp.x] = out[4 * q];
+            if (cp.y >= 0) dst[cp.y] = out[4 * q + 1];
+            if (cp.z >= 0) dst[cp.z] = out[4 * q + 2];
+            if (cp.w >= 0) dst[cp.w] = out[4 * q + 3];
           }
+        } else if (staged) {
+          *reinterpret_cast<uint4*>(srow + c0 * 2) = *reinterpret_cast<const uint4*>(out2);
+          *reinterpret_cast<uint4*>(srow + c0 * 2 + 16) = *reinterpret_cast<const uint4*>(out2 + 4);
+        } else {
+          __half* yp = a.y + pix * a.ldy + it.n0 + c0;
+          *reinterpret_cast<uint4*>(yp) = *reinterpret_cast<const uint4*>(out2);
+          if (c0 + 8 < it.n_valid) *reinterpret_cast<uint4*>(yp + 8) = *reinterpret_cast<const uint4*>(out2 + 4);
         }
       }
       tc_fence_before();
@@ -631,6 +708,8 @@ int conv_forward_umma(const ConvArgs& a, cudaStream_t s) {
     LAUD_CUDA(cudaGetDevice(&dev));
     LAUD_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     LAUD_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    vtab_init_kernel<<<32, 256, 0, s>>>();      // tap-validity table of the H1-constant K-step (once per process)
+    if (int e = check_launch("vtab_init_kernel")) return e;
   }
   Plan pl;
   pl.mode = (a.k_idx && a.wt && aligned16(a.wt)) ? MODE_KROWS : (a.k_idx ? MODE_KUNITS : MODE_ROWS);

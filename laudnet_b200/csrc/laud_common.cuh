@@ -76,11 +76,13 @@ struct ConvArgs {
   int n_pad_align;
   float* gap_partial; int gap_tiles;
   const __half* wt;
+  const __half* bias_t; int bias_ld;
 };
 
 int conv_forward_naive(const ConvArgs& a, cudaStream_t s);
 int conv_forward_hmma(const ConvArgs& a, cudaStream_t s);
 int conv_forward_umma(const ConvArgs& a, cudaStream_t s);
+bool conv_umma_supported(const ConvArgs& a);
 
 // Shared epilogue: value for output (b, oy, ox), compact channel j / real channel o.
 __device__ __forceinline__ float conv_epilogue(const ConvArgs& a, float acc, int b, int oy, int ox,

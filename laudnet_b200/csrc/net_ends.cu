@@ -146,67 +146,54 @@ __global__ void __launch_bounds__(256) head_fc_kernel(const float* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------
-// H1 constants (see laud_b200.h).  One warp per output unit.
+// H1 constants (see laud_b200.h).  The per-sample sums over MASKED channels
+//   T2[b,tap,o] = sum_k inact[b,k] * relu(shift1[k]) * w2[o,tap,k]
+//   T3[b,o]     = sum_k inact[b,k] * relu(shift2[k]) * w3[o,k]
+// are ONE dense GEMM [B x width] x [width x 13*width] on the tcgen05 conv kernel
+// (inact = 0/1 indicator of the masked channels, the scaled weights are packed
+// at model-preparation time).  What is left here: the 0/1 indicator, and the
+// fold of the 9 taps into the 16 border classes of a 3x3/pad-1 convolution.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) consts_conv2_kernel(const __half* __restrict__ w2, int width,
-                                                           const float* __restrict__ shift1,
-                                                           const int* __restrict__ idx,
-                                                           const int* __restrict__ cnt, int G, int gran,
-                                                           float* __restrict__ pre_bias2) {
-  const int b = blockIdx.y;
-  const int lane = threadIdx.x & 31;
-  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);     // compact output channel
-  const int na = cnt[b];
-  if (j >= na * gran) return;
-  const int* il = idx + (size_t)b * G;
-  const int o = il[j / gran] * gran + j % gran;
-  const int nm = (G - na) * gran;                         // masked channels
-  float T[9];
-  for (int tap = 0; tap < 9; ++tap) {
-    const __half* wr = w2 + ((size_t)o * 9 + tap) * width;
-    float t = 0.f;
-    for (int mi = lane; mi < nm; mi += 32) {
-      const int k = il[na + mi / gran] * gran + mi % gran;
-      t = fmaf(fmaxf(shift1[k], 0.f), __half2float(wr[k]), t);
-    }
-    T[tap] = warp_sum(t);
-  }
-  if (lane < 16) {
-    const int rc = lane >> 2, cc = lane & 3;
-    float s = 0.f;
-#pragma unroll
-    for (int dy = 0; dy < 3; ++dy) {
-      if ((dy == 0 && (rc & 1)) || (dy == 2 && (rc & 2))) continue;
-#pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-        if ((dx == 0 && (cc & 1)) || (dx == 2 && (cc & 2))) continue;
-        s += T[dy * 3 + dx];
-      }
-    }
-    pre_bias2[((size_t)b * 16 + lane) * width + j] = s;
-  }
+__global__ void gate_inactive_kernel(const uint8_t* __restrict__ mask, int B, int G, int gran,
+                                     __half* __restrict__ inact) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n = (long long)B * G * gran;
+  if (i >= n) return;
+  const int c = (int)(i % (G * gran));
+  const long long b = i / (G * gran);
+  inact[i] = __float2half(mask[b * G + c / gran] ? 0.f : 1.f);
 }
 
-__global__ void __launch_bounds__(256) consts_conv3_kernel(const __half* __restrict__ w3, int width, int C_out,
-                                                           const float* __restrict__ shift2,
-                                                           const int* __restrict__ idx,
-                                                           const int* __restrict__ cnt, int G, int gran,
-                                                           float* __restrict__ pre_bias3) {
-  const int b = blockIdx.y;
-  const int lane = threadIdx.x & 31;
-  const int o = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (o >= C_out) return;
-  const int na = cnt[b];
-  const int* il = idx + (size_t)b * G;
-  const int nm = (G - na) * gran;
-  const __half* wr = w3 + (size_t)o * width;
-  float t = 0.f;
-  for (int mi = lane; mi < nm; mi += 32) {
-    const int k = il[na + mi / gran] * gran + mi % gran;
-    t = fmaf(fmaxf(shift2[k], 0.f), __half2float(wr[k]), t);
+// grid (B), 256 threads.  T: fp16 [B, 9*width + C_out] (row b: T2[tap*width+o], then T3[o]).
+__global__ void __launch_bounds__(256) consts_fold_kernel(const __half* __restrict__ T, int width, int C_out,
+                                                          const int* __restrict__ idx, const int* __restrict__ cnt,
+                                                          int G, int gran, int compact_index,
+                                                          float* __restrict__ pre_bias2, float* __restrict__ pre_bias3) {
+  const int b = blockIdx.x;
+  const __half* Tb = T + (size_t)b * (9 * width + C_out);
+  const int n_out = compact_index ? cnt[b] * gran : width;
+  for (int j = threadIdx.x; j < n_out; j += 256) {
+    const int o = compact_index ? idx[(size_t)b * G + j / gran] * gran + j % gran : j;
+    float t[9];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) t[tap] = __half2float(Tb[tap * width + o]);
+#pragma unroll
+    for (int cls = 0; cls < 16; ++cls) {
+      const int rc = cls >> 2, cc = cls & 3;
+      float s = 0.f;
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+        if ((dy == 0 && (rc & 1)) || (dy == 2 && (rc & 2))) continue;     // tap row falls outside the input
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          if ((dx == 0 && (cc & 1)) || (dx == 2 && (cc & 2))) continue;
+          s += t[dy * 3 + dx];
+        }
+      }
+      pre_bias2[((size_t)b * 16 + cls) * width + j] = s;
+    }
   }
-  t = warp_sum(t);
-  if (lane == 0) pre_bias3[(size_t)b * C_out + o] = t;
+  for (int o = threadIdx.x; o < C_out; o += 256) pre_bias3[(size_t)b * C_out + o] = __half2float(Tb[9 * width + o]);
 }
 
 // ---------------------------------------------------------------------------
@@ -318,20 +305,21 @@ extern "C" int laud_head_forward(const void* x, int B, int HW, int C, const void
   return check_launch("head_fc_kernel");
 }
 
-extern "C" int laud_channel_consts(const void* w2, const void* w3, int width, int C_out, const float* shift1,
-                                   const float* shift2, const int32_t* idx, const int32_t* cnt, int B, int G,
-                                   int gran, int H_in, int W_in, int H_out, int W_out, int stride,
-                                   float* pre_bias2, float* pre_bias3, void* stream) {
-  (void)H_in; (void)W_in; (void)H_out; (void)W_out; (void)stride;
-  LAUD_REQUIRE(w2 && w3 && shift1 && shift2 && idx && cnt && pre_bias2 && pre_bias3, "laud_channel_consts: null pointer");
-  LAUD_REQUIRE(G * gran == width, "laud_channel_consts: G*gran (%d*%d) != width %d", G, gran, width);
-  cudaStream_t s = (cudaStream_t)stream;
-  consts_conv2_kernel<<<dim3((width + 7) / 8, B), 256, 0, s>>>((const __half*)w2, width, shift1, idx, cnt, G, gran,
-                                                             pre_bias2);
-  if (int e = check_launch("consts_conv2_kernel")) return e;
-  consts_conv3_kernel<<<dim3((C_out + 7) / 8, B), 256, 0, s>>>((const __half*)w3, width, C_out, shift2, idx, cnt, G,
-                                                              gran, pre_bias3);
-  return check_launch("consts_conv3_kernel");
+extern "C" int laud_gate_inactive(const uint8_t* mask, int B, int G, int gran, void* inact_f16, void* stream) {
+  LAUD_REQUIRE(mask && inact_f16 && B > 0 && G > 0 && gran > 0, "laud_gate_inactive: bad arguments");
+  const long long n = (long long)B * G * gran;
+  gate_inactive_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(mask, B, G, gran, (__half*)inact_f16);
+  return check_launch("gate_inactive_kernel");
+}
+
+extern "C" int laud_channel_consts_fold(const void* T, int B, int width, int C_out, const int32_t* idx,
+                                        const int32_t* cnt, int G, int gran, int compact_index, float* pre_bias2,
+                                        float* pre_bias3, void* stream) {
+  LAUD_REQUIRE(T && idx && cnt && pre_bias2 && pre_bias3, "laud_channel_consts_fold: null pointer");
+  LAUD_REQUIRE(G * gran == width, "laud_channel_consts_fold: G*gran (%d*%d) != width %d", G, gran, width);
+  consts_fold_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((const __half*)T, width, C_out, idx, cnt, G, gran,
+                                                         compact_index, pre_bias2, pre_bias3);
+  return check_launch("consts_fold_kernel");
 }
 
 extern "C" int laud_nchw_to_nhwc_f16(const void* src, int src_is_f32, int B, int C, int H, int W, void* dst, int ldd,

@@ -138,6 +138,8 @@ class _SoloEngine(ResNetEngine):
         if blk.downsample is not None:
             p.wd = pack_conv_weight(blk.downsample[0].weight)
             p.sd, p.td = fold_bn(blk.downsample[1])
+        if p.use_c:
+            p.pack_channel_mode(blk)
         self.plans = [p]
         self.stats_consts = self._stats_consts(dev)
         self.prepared_for = dev
@@ -156,6 +158,7 @@ class _SoloEngine(ResNetEngine):
                 ccnt=torch.empty((B,), **i32),
                 pb2=torch.empty(B * 16 * p.width, dtype=torch.float32, device=dev),
                 pb3=torch.empty(B * p.outplanes, dtype=torch.float32, device=dev),
+                inact=torch.empty(B * p.width, **f16), T=torch.empty(B * (9 * p.width + p.outplanes), **f16),
                 smask=torch.empty(B * p.g_spatial * hw, dtype=torch.uint8, device=dev),
                 m3=torch.empty(B * p.g_spatial * hw, dtype=torch.uint8, device=dev),
                 m2=torch.empty(B * p.g_spatial * hw, dtype=torch.uint8, device=dev),

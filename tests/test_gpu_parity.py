@@ -157,7 +157,7 @@ class TestOperators:
 
 # --------------------------------------------------------------------------- the mask-conditioned convolution
 def _conv_case(seed, B, H, Cin, Cout, k, stride, *, kgather=0, ngather=0, rho=0.6, residual=False, mask_groups=0,
-               prebias=False, rows=False, samples=False, relu=_lib.RELU_ALL):
+               prebias=False, rows=False, samples=False, relu=_lib.RELU_ALL, tapbias=False):
     """Build one laud_conv_forward case + its fp32 oracle result (F.conv2d on CPU)."""
     r = np.random.RandomState(seed)
     pad = 1 if k == 3 else 0
@@ -192,6 +192,16 @@ def _conv_case(seed, B, H, Cin, Cout, k, stride, *, kgather=0, ngather=0, rho=0.
             cls1 = ((oy * stride - pad < 0).long() + 2 * (oy * stride + 2 - pad >= H).long())
             cls = cls1.view(Ho, 1) * 4 + cls1.view(1, Ho)
             y = y + pb[:, cls].permute(0, 3, 1, 2)
+    if tapbias:
+        # H1-constant form: acc[p,o] += sum over the taps of p that fall inside the input of bt[b,tap,o]
+        bt = torch.from_numpy((r.standard_normal((B, k * k, Cout)) * 0.2).astype(np.float32)).half().float()
+        d["bias_t"] = bt
+        ones = torch.ones(1, 1, H, H)
+        for tap in range(k * k):
+            kern = torch.zeros(1, 1, k, k)
+            kern[0, 0, tap // k, tap % k] = 1.0
+            valid = F.conv2d(ones, kern, stride=stride, padding=pad)          # [1,1,Ho,Ho] in {0,1}
+            y = y + valid * bt[:, tap].view(B, Cout, 1, 1)
     y = y * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
     if mask_groups:
         om = torch.from_numpy((r.uniform(size=(B, mask_groups, Ho, Ho)) < 0.5).astype(np.uint8))
@@ -258,6 +268,9 @@ def _run_conv_case(d, impl, use_wt=False):
                 pbc[b, :, :len(ch)] = pb[b][:, ch]
             pb = pbc
         kw.update(pre_bias=pb.contiguous().to(DEV), pre_bias_classes=pb.shape[1], pre_bias_ld=Cout)
+    if "bias_t" in d:
+        assert use_wt, "bias_t is a w_t-path argument"
+        kw.update(bias_t=d["bias_t"].half().contiguous().to(DEV), bias_ld=d["bias_t"].shape[1] * Cout)
     if "out_mask" in d:
         kw.update(out_mask=d["out_mask"].to(DEV), mask_groups=d["out_mask"].shape[1])
     if "res" in d:
@@ -322,8 +335,17 @@ CONV_CASES = {
     "3x3_kn_gather_big": dict(B=3, H=14, Cin=256, Cout=256, k=3, stride=1, kgather=2, ngather=2, prebias=True),
     "1x1_kgather_wide": dict(B=3, H=14, Cin=256, Cout=1024, k=1, stride=1, kgather=2, prebias=True, residual=True),
 }
+# H1 constants entering as an extra K=16 MMA step (w_t path only)
+TAPBIAS_CASES = {
+    "3x3_kn_gather_tapbias": dict(B=4, H=14, Cin=64, Cout=64, k=3, stride=1, kgather=2, ngather=2, tapbias=True),
+    "3x3_s2_tapbias": dict(B=3, H=28, Cin=32, Cout=32, k=3, stride=2, kgather=2, ngather=2, tapbias=True),
+    "1x1_kgather_tapbias_res": dict(B=4, H=7, Cin=128, Cout=512, k=1, stride=1, kgather=2, tapbias=True, residual=True),
+    "3x3_wide_tapbias": dict(B=2, H=7, Cin=128, Cout=512, k=3, stride=1, kgather=2, ngather=2, tapbias=True),
+    "3x3_tiny_H2_tapbias": dict(B=3, H=2, Cin=16, Cout=16, k=3, stride=1, kgather=2, ngather=2, tapbias=True),
+}
 # cases with a K gather also run through the K-row-gather path (transposed weights supplied)
 WT_CASES = [n for n, c in CONV_CASES.items() if c.get("kgather")]
+CONV_CASES_ALL = dict(CONV_CASES, **TAPBIAS_CASES)
 
 
 @pytest.mark.parametrize("impl", [_lib.CONV_UMMA, _lib.CONV_HMMA, _lib.CONV_NAIVE], ids=["umma", "hmma", "naive"])
@@ -334,9 +356,9 @@ def test_conv_forward_vs_oracle(cuda_lib, name, impl):
     assert err <= ACT_TOL, f"{name}: normalised max error {err:.2e} > {ACT_TOL}"
 
 
-@pytest.mark.parametrize("name", WT_CASES)
+@pytest.mark.parametrize("name", WT_CASES + list(TAPBIAS_CASES))
 def test_conv_forward_krows_vs_oracle(cuda_lib, name):
-    d = _conv_case(sum(map(ord, name)), **CONV_CASES[name])
+    d = _conv_case(sum(map(ord, name)), **CONV_CASES_ALL[name])
     err = _run_conv_case(d, _lib.CONV_UMMA, use_wt=True)
     assert err <= ACT_TOL, f"{name}: normalised max error {err:.2e} > {ACT_TOL}"
 
