@@ -105,6 +105,182 @@ __global__ void __launch_bounds__(256) stem_kernel(const __half* __restrict__ x,
 }
 
 // ---------------------------------------------------------------------------
+// Stem, tensor-core version (the product path for C0 in {16, 32, 64}).
+// Persistent CTAs; one work item = one sample x an 8x14 tile of POOLED outputs,
+// i.e. a 17x29 tile of conv outputs computed as an implicit GEMM with
+// mma.sync.m16n8k16 (fp16 in, fp32 accumulate) straight from the fp16 input
+// patch in shared memory:  M = conv pixel, N = output channel,
+// K = (c, ky) x 8 with kx fastest (the 8th kx and the 22nd (c,ky) row carry
+// zero weights), so an A fragment is a pair of adjacent input pixels - no
+// im2col buffer.  BN + ReLU, then the 3x3/2 max-pool from the fp16 conv tile.
+// (K = 147 with 3 input channels does not map onto UMMA shared-memory
+// descriptors without materialising im2col; at 1.5 % of the network's MACs the
+// legacy warp-level MMA is the right tool here.)
+// ---------------------------------------------------------------------------
+constexpr int S2_PH = 8, S2_PW = 14;
+constexpr int S2_CH = 2 * S2_PH + 1, S2_CW = 2 * S2_PW + 1;    // 17 x 29 conv outputs
+constexpr int S2_NPIX = S2_CH * S2_CW;                         // 493
+constexpr int S2_MT = (S2_NPIX + 15) / 16;                     // 31 m16 tiles
+constexpr int S2_IH = 2 * S2_CH + 5, S2_IW = 2 * S2_CW + 5;    // 39 x 63 input patch
+constexpr int S2_IWP = 64;                                     // even pitch: fragment loads are 32-bit aligned
+constexpr int S2_KS = 11, S2_KP = 184;                         // k16 steps (176 >= 21*8), padded weight-row pitch
+
+__device__ __forceinline__ void mma_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int NT>   // C0 = 8 * NT output channels
+__global__ void __launch_bounds__(256, 2) stem_mma_kernel(const __half* __restrict__ x, int B, int H, int W,
+                                                          const __half* __restrict__ w,
+                                                          const float* __restrict__ scale,
+                                                          const float* __restrict__ shift,
+                                                          __half* __restrict__ y) {
+  constexpr int C0 = 8 * NT, CP = C0 + 8;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __half* s_w = reinterpret_cast<__half*>(smem_raw);            // [C0][S2_KP]
+  __half* s_in = s_w + C0 * S2_KP;                              // [3][S2_IH][S2_IWP]
+  __half* s_c = s_in + 3 * S2_IH * S2_IWP;                      // [S2_NPIX][CP]
+  const int Hc = H / 2, Wc = W / 2, Hp = Hc / 2, Wp = Wc / 2;
+  const int tiles_x = (Wp + S2_PW - 1) / S2_PW, tiles_y = (Hp + S2_PH - 1) / S2_PH;
+  const int total = B * tiles_x * tiles_y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+
+  // weights [C0][3][7][7] -> [C0][(c,ky) x 8 + kx], zero padded
+  for (int i = tid; i < C0 * S2_KP; i += 256) {
+    const int o = i / S2_KP, k = i - o * S2_KP;
+    const int row = k >> 3, kx = k & 7;
+    s_w[i] = (row < 21 && kx < 7) ? w[o * 147 + row * 7 + kx] : __float2half(0.f);
+  }
+
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    const int b = item / (tiles_x * tiles_y);
+    const int tr = item - b * tiles_x * tiles_y;
+    const int py0 = (tr / tiles_x) * S2_PH, px0 = (tr % tiles_x) * S2_PW;
+    const int cy0 = 2 * py0 - 1, cx0 = 2 * px0 - 1;       // conv-tile origin (may be -1)
+    const int iy0 = 2 * cy0 - 3, ix0 = 2 * cx0 - 3;       // input-patch origin
+    __syncthreads();                                      // previous item's pooling has finished with s_c / s_in
+    for (int i = tid; i < 3 * S2_IH * S2_IWP; i += 256) {
+      const int c = i / (S2_IH * S2_IWP), rr = (i / S2_IWP) % S2_IH, q = i % S2_IWP;
+      const int iy = iy0 + rr, ix = ix0 + q;
+      __half v = __float2half(0.f);
+      if (iy >= 0 && ix >= 0 && iy < H && ix < W) v = x[(((size_t)b * 3 + c) * H + iy) * W + ix];
+      s_in[i] = v;
+    }
+    __syncthreads();
+
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      int poff[2][2];                                     // patch offsets of this thread's 2 pixels in 2 m-tiles
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int p = min((warp + 8 * (2 * pass + m)) * 16 + g + 8 * h, S2_NPIX - 1);
+          const int r = p / S2_CW, q = p - r * S2_CW;
+          poff[m][h] = 2 * r * S2_IWP + 2 * q + 2 * t;
+        }
+      float acc[2][NT][4];
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[m][j][e] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < S2_KS; ++ks) {
+        const int ra = 2 * ks, rb = 2 * ks + 1;
+        const int offa = ((ra / 7) * S2_IH + ra % 7) * S2_IWP;
+        const int offb = rb < 21 ? ((rb / 7) * S2_IH + rb % 7) * S2_IWP : 0;     // pad row: zero weights, any finite data
+        uint32_t a[2][4];
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          a[m][0] = *reinterpret_cast<const uint32_t*>(s_in + poff[m][0] + offa);
+          a[m][1] = *reinterpret_cast<const uint32_t*>(s_in + poff[m][1] + offa);
+          a[m][2] = *reinterpret_cast<const uint32_t*>(s_in + poff[m][0] + offb);
+          a[m][3] = *reinterpret_cast<const uint32_t*>(s_in + poff[m][1] + offb);
+        }
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          const __half* wp = s_w + (j * 8 + g) * S2_KP + ks * 16 + 2 * t;
+          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wp);
+          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(wp + 8);
+          mma_16816(acc[0][j], a[0], b0, b1);
+          mma_16816(acc[1][j], a[1], b0, b1);
+        }
+      }
+      // BN + ReLU -> fp16 conv tile (0 outside the conv output: neutral for the max of post-ReLU values)
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int p = (warp + 8 * (2 * pass + m)) * 16 + g + 8 * h;
+          if (p < S2_NPIX) {
+            const int r = p / S2_CW, q = p - r * S2_CW;
+            const int cy = cy0 + r, cx = cx0 + q;
+            const bool inside = cy >= 0 && cx >= 0 && cy < Hc && cx < Wc;
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+              const int n = j * 8 + 2 * t;
+              float v0 = 0.f, v1 = 0.f;
+              if (inside) {
+                v0 = fmaxf(fmaf(acc[m][j][2 * h], __ldg(scale + n), __ldg(shift + n)), 0.f);
+                v1 = fmaxf(fmaf(acc[m][j][2 * h + 1], __ldg(scale + n + 1), __ldg(shift + n + 1)), 0.f);
+              }
+              *reinterpret_cast<__half2*>(s_c + p * CP + n) = __floats2half2_rn(v0, v1);
+            }
+          }
+        }
+    }
+    __syncthreads();
+
+    constexpr int ncg = C0 / 8;
+    for (int it = tid; it < S2_PH * S2_PW * ncg; it += 256) {
+      const int cg = it % ncg, pp = it / ncg;
+      const int pr = pp / S2_PW, pq = pp - pr * S2_PW;
+      const int py = py0 + pr, px = px0 + pq;
+      if (py >= Hp || px >= Wp) continue;
+      __half2 mx[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) mx[e] = __float2half2_rn(0.f);
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const uint4 q4 = *reinterpret_cast<const uint4*>(s_c + ((2 * pr + dy) * S2_CW + 2 * pq + dx) * CP + cg * 8);
+          const __half2* hh = reinterpret_cast<const __half2*>(&q4);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) mx[e] = __hmax2(mx[e], hh[e]);
+        }
+      *reinterpret_cast<uint4*>(y + (((size_t)b * Hp + py) * Wp + px) * C0 + cg * 8) = *reinterpret_cast<uint4*>(mx);
+    }
+  }
+}
+
+template <int NT>
+int launch_stem_mma(const __half* x, int B, int H, int W, const __half* w, const float* scale, const float* shift,
+                    __half* y, cudaStream_t s) {
+  constexpr int C0 = 8 * NT;
+  const size_t smem = sizeof(__half) * ((size_t)C0 * S2_KP + 3 * S2_IH * S2_IWP + (size_t)S2_NPIX * (C0 + 8));
+  static bool attr_set = false;
+  static int num_sms = 0;
+  if (!attr_set) {
+    int dev = 0;
+    LAUD_CUDA(cudaGetDevice(&dev));
+    LAUD_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    LAUD_CUDA(cudaFuncSetAttribute(stem_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int Hp = H / 4, Wp = W / 4;
+  const long long total = (long long)B * ((Wp + S2_PW - 1) / S2_PW) * ((Hp + S2_PH - 1) / S2_PH);
+  const int grid = (int)(total < 2ll * num_sms ? total : 2ll * num_sms);
+  stem_mma_kernel<NT><<<grid, 256, smem, s>>>(x, B, H, W, w, scale, shift, y);
+  return check_launch("stem_mma_kernel");
+}
+
+// ---------------------------------------------------------------------------
 // Head fc: CTA = 4 samples x 64 classes; pooled features of the 4 samples in smem.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) head_fc_kernel(const float* __restrict__ pooled, int B, int C,
@@ -273,6 +449,14 @@ extern "C" int laud_stem_forward(const void* x, int B, int H, int W, const void*
                                  const float* shift, void* y, void* stream) {
   LAUD_REQUIRE(x && w && scale && shift && y, "laud_stem_forward: null pointer");
   LAUD_REQUIRE(B > 0 && H % 4 == 0 && W % 4 == 0 && C0 % 8 == 0, "laud_stem_forward: need H,W %% 4 == 0, C0 %% 8 == 0");
+  {
+    const __half *xh = (const __half*)x, *wh = (const __half*)w;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C0 == 64) return launch_stem_mma<8>(xh, B, H, W, wh, scale, shift, (__half*)y, st);
+    if (C0 == 32) return launch_stem_mma<4>(xh, B, H, W, wh, scale, shift, (__half*)y, st);
+    if (C0 == 16) return launch_stem_mma<2>(xh, B, H, W, wh, scale, shift, (__half*)y, st);
+  }
+  // other stem widths: scalar kernel
   const int Hp = H / 4, Wp = W / 4;
   const size_t smem = sizeof(float) * 3 * ST_IH * ST_IWP + sizeof(__half) * (147 + ST_CH * ST_CW) * (size_t)C0;
   LAUD_REQUIRE(smem <= 200 * 1024, "laud_stem_forward: stem width %d too large", C0);

@@ -375,6 +375,31 @@ def test_conv_rejects_bad_arguments(cuda_lib):
         _engine.run_conv(x, w, y, 1, 4, 4, 16, 3, 3, 8, 1, 1, 0)
 
 
+# --------------------------------------------------------------------------- network ends
+@pytest.mark.parametrize("B,size,C0", [(2, 224, 64), (3, 64, 16), (1, 96, 32), (2, 72, 64), (1, 64, 24)])
+def test_stem_vs_oracle(cuda_lib, B, size, C0):
+    """conv7x7/2 + BN + ReLU + maxpool3x3/2 (laud_resnet.py:317-324): tensor-core stem (C0 16/32/64) and the
+    scalar kernel (other widths) against the oracle, on fp16-representable inputs and weights; ragged pooled
+    tiles (sizes that are not multiples of the 8x14 tile) included."""
+    gen = torch.Generator().manual_seed(B * 1000 + size + C0)
+    x = torch.randn(B, 3, size, size, generator=gen).half()
+    w = (torch.randn(C0, 3, 7, 7, generator=gen) * 0.1).half()
+    sd = {"conv1.weight": w.float(), "bn1.weight": torch.randn(C0, generator=gen) * 0.2 + 1.0,
+          "bn1.bias": torch.randn(C0, generator=gen) * 0.5, "bn1.running_mean": torch.randn(C0, generator=gen) * 0.5,
+          "bn1.running_var": torch.rand(C0, generator=gen) * 1.5 + 0.5}
+    ref, _ = O.stem_forward(x.float(), sd)
+    scale = sd["bn1.weight"] / torch.sqrt(sd["bn1.running_var"] + 1e-5)
+    shift = sd["bn1.bias"] - sd["bn1.running_mean"] * scale
+    y = torch.full((B, size // 4, size // 4, C0), float("nan"), dtype=torch.float16, device=DEV)
+    xd, wd, sc, sh = x.to(DEV), w.to(DEV), scale.to(DEV).contiguous(), shift.to(DEV).contiguous()
+    _lib.check(cuda_lib.laud_stem_forward(xd.data_ptr(), B, size, size, wd.data_ptr(), C0, sc.data_ptr(), sh.data_ptr(),
+                                          y.data_ptr(), _lib.stream_ptr()), "laud_stem_forward")
+    torch.cuda.synchronize()
+    ours = y.float().permute(0, 3, 1, 2).cpu()
+    assert torch.isfinite(ours).all()
+    assert _rel_err(ours, ref) <= ACT_TOL
+
+
 # --------------------------------------------------------------------------- blocks, teacher-forced
 @pytest.mark.parametrize("name", list(CASES))
 def test_blocks_teacher_forced(cuda_lib, name):
