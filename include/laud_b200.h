@@ -58,6 +58,8 @@ unsigned long long laud_launch_count(void);
 /* launches of the mask-conditioned convolution by implementation:
  * out[0] tcgen05/TMEM kernel, out[1] legacy HMMA kernel, out[2] naive self-test kernel */
 void laud_conv_path_counts(unsigned long long out[3]);
+/* launches of the TMA-staged tcgen05 kernel (conv_tma.cu), a subset of out[0] above */
+unsigned long long laud_conv_tma_launch_count(void);
 
 /* ---------------------------------------------------------------------------
  * (a1) channel masker.  Replaces Masker_channel_MLP.forward, eval branch
@@ -147,7 +149,9 @@ int laud_compact_rows(const uint8_t* gate, int B, int g, int HW,
  *   v = v * out_mask[b, o / (C_out/mask_groups), oy, ox]   (optional, u8)
  *   v = v + residual[b, oy, ox, o]                (optional, fp16)
  *   v = relu(v) per relu_mode;  y = fp16(v)
- *   compact channels [n_count, round_up(n_count, n_pad_align)) := 0  (n_pad_align > 0)
+ *   compact channels [n_count, round_up(n_count, n_pad_align)) := 0  (n_pad_align > 0);
+ *   with n_idx the rest of the row, [round_up(n_count, n_pad_align), ldy), is SCRATCH: the
+ *   TMA-staged kernel stores whole 64-channel slabs, consumers read only the padded width.
  * ------------------------------------------------------------------------- */
 typedef struct laud_conv_desc {
   const void* x;  int32_t ldx;          /* fp16 [B,H_in,W_in,ldx] */

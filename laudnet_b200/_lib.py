@@ -13,7 +13,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "liblaud_b200.so")
+LIB_PATH = os.environ.get("LAUD_LIB") or os.path.join(_HERE, "lib", "liblaud_b200.so")   # LAUD_LIB: diagnostic builds
 
 CONV_AUTO, CONV_UMMA, CONV_HMMA, CONV_NAIVE = 0, 1, 2, 3
 RELU_NONE, RELU_ALL, RELU_WHERE_GATE0 = 0, 1, 2
@@ -54,6 +54,7 @@ SIGNATURES = {
     "laud_last_error": ([], C.c_char_p),
     "laud_launch_count": ([], C.c_ulonglong),
     "laud_conv_path_counts": ([C.POINTER(C.c_ulonglong * 3)], None),
+    "laud_conv_tma_launch_count": ([], C.c_ulonglong),
     "laud_masker_channel_mlp": ([_vp, _i, _i, _i, _i, _fp, _fp, _i, _fp, _fp, _i, _fp, _fp, _fp, _u8p, _i32p, _i32p, _i32p, _vp], _i),
     "laud_masker_channel_from_pooled": ([_fp, _i, _i, _i, _fp, _fp, _i, _fp, _fp, _i, _fp, _u8p, _i32p, _i32p, _i32p, _vp], _i),
     "laud_global_avg_pool": ([_vp, _i, _i, _i, _i, _fp, _fp, _vp], _i),
@@ -125,4 +126,5 @@ def conv_path_counts() -> dict:
     tcgen05 kernel is the one that runs)."""
     out = (C.c_ulonglong * 3)()
     lib().laud_conv_path_counts(C.byref(out))
-    return {"umma_tcgen05": int(out[0]), "hmma_legacy": int(out[1]), "naive_selftest": int(out[2])}
+    return {"umma_tcgen05": int(out[0]), "umma_tcgen05_tma": int(lib().laud_conv_tma_launch_count()),
+            "hmma_legacy": int(out[1]), "naive_selftest": int(out[2])}

@@ -43,6 +43,18 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_prof() -> str:
+    """Diagnostic build with in-kernel lap timers (-DLAUD_KPROF) -> lib/liblaud_b200_prof.so;
+    load it with LAUD_LIB=<path> (scripts/kprof.py)."""
+    out = os.path.join(LIBDIR, "liblaud_b200_prof.so")
+    cmd = [_nvcc(), *[f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")], "-DLAUD_KPROF", "-I",
+           os.path.join(ROOT, "include"), *sources(), "-o", out]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + (proc.stdout + proc.stderr)[-4000:])
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
@@ -61,4 +73,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--prof" in sys.argv:
+        print(build_prof())
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,6 +1,7 @@
 // C-ABI glue: error strings, launch accounting, descriptor validation and
 // dispatch of the mask-conditioned convolution.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include "laud_common.cuh"
 
@@ -9,6 +10,7 @@ namespace laud {
 static thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
 std::atomic<unsigned long long> g_conv_paths[3];
+std::atomic<unsigned long long> g_conv_tma_launches{0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -24,6 +26,7 @@ using namespace laud;
 extern "C" int laud_abi_version(void) { return LAUD_ABI_VERSION; }
 extern "C" const char* laud_last_error(void) { return g_err; }
 extern "C" unsigned long long laud_launch_count(void) { return g_launches.load(); }
+extern "C" unsigned long long laud_conv_tma_launch_count(void) { return g_conv_tma_launches.load(); }
 extern "C" void laud_conv_path_counts(unsigned long long out[3]) {
   for (int i = 0; i < 3; ++i) out[i] = g_conv_paths[i].load();
 }
@@ -106,6 +109,10 @@ extern "C" int laud_conv_forward(const laud_conv_desc* d, int impl, void* stream
         set_error("laud_conv_forward: layout not supported by the tcgen05 kernel but w_t was given "
                   "(channel granularity must be 2, 4 or a multiple of 8; pitches multiples of 8; 16-byte aligned)");
         return LAUD_E_UNSUPPORTED;
+      }
+      {
+        static const bool force_v3 = getenv("LAUD_CONV_V3") != nullptr;     // A/B switch for profiling
+        if (!force_v3 && conv_tma_supported(a)) return conv_forward_tma(a, s);
       }
       return conv_forward_umma(a, s);
     case LAUD_CONV_HMMA:

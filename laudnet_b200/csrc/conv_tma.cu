@@ -1,0 +1,811 @@
+// The product kernel of the mask-conditioned convolution (v4): a persistent,
+// warp-specialised gather-GEMM on tcgen05 tensor cores whose dense operands
+// move with TMA tensor-tile copies.
+//
+//   D[m, n] = sum_{tap, k} A[m, (tap,k)] * W[n, (tap,k)]
+//     m : output pixels of ONE sample: MT (1|2) tiles of up to 128 pixels share every weight stage
+//     n : output channels of one tile (BN = 64 | 128 | 256)
+//     k : that sample's ACTIVE input channels (compact), per filter tap
+//
+// 512 threads, one CTA per SM, static round-robin over (sample, m-group, n-group):
+//   warps 0-7   epilogue : tcgen05.ld the fp32 accumulators out of TMEM; folded BN / gate /
+//                          residual / ReLU in registers.
+//                          SLAB mode: each half (4 warps) owns a ring of [128 px][64 ch]
+//                          swizzled slabs; residual slabs ARRIVE by TMA (prefetched two tasks
+//                          ahead), the fp16 result overwrites them in place and LEAVES by TMA
+//                          (one cp.async.bulk.tensor per slab instead of one copy per pixel row).
+//                          ROWS mode (K-row-gather with compaction of the active output
+//                          channels): word-swizzled row staging, coalesced cooperative flush.
+//   warp  8     TMA      : one lane issues the A tiles (im2col by 4-d tile boxes whose
+//                          out-of-bounds taps are zero-filled by the TMA unit) and, when the
+//                          weights are not gathered, the B tile.
+//   warp  9     MMA      : one lane issues tcgen05.mma (M=128, N<=256, K=16); accumulators in
+//                          TMEM, multi-buffered so the epilogue of one item overlaps the MMAs
+//                          of the next.
+//   warps 10-15 gather   : per-sample weight gathers with cp.async into the UMMA swizzle layout
+//                          (ROWS: active OUTPUT channels of K-major weights; KROWS: active INPUT
+//                          channels of the transposed weights) + the H1-constant K=16 step.
+// Layouts it does not take (stride 2, row lists, per-class pre-bias, KUNITS) run on the v3
+// kernel (conv_umma.cu).  Restates (does not port) laud_resnet.py:115-144 of the reference.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+#include "laud_common.cuh"
+#include "umma_ptx.cuh"
+
+namespace laud {
+namespace {
+
+constexpr int BM = 128;
+constexpr int A_TILE_BYTES = BM * 128;           // 128 rows x 64 fp16
+constexpr int EPI_WARPS = 8, TMA_WARP = 8, MMA_WARP = 9, GATHER_WARP0 = 10, GATHER_WARPS = 6;
+constexpr int NUM_THREADS = (GATHER_WARP0 + GATHER_WARPS) * 32;   // 512
+constexpr int EPI_THREADS = EPI_WARPS * 32, HALF_THREADS = EPI_THREADS / 2;
+constexpr int GATHER_THREADS = GATHER_WARPS * 32;
+constexpr int KIDX_MAX = 1024;
+constexpr int MAX_STAGES = 6;
+constexpr int SLAB_BYTES = BM * 128;             // [128 px][64 ch] fp16
+constexpr int MAX_RING = 3;
+constexpr int BN_MAX = 256;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr int SMEM_LIMIT = 232448;
+
+enum { BMODE_TMA = 0, BMODE_ROWS = 1, BMODE_KROWS = 2 };
+enum { OUT_SLAB = 0, OUT_ROWS = 1 };
+
+// Optional in-kernel lap timers (-DLAUD_KPROF, scripts/kprof.py): cycles each warp role spends per phase.
+#ifdef LAUD_KPROF
+constexpr int KP_ROLES = 5, KP_SITES = 8;
+__device__ long long g_kprof[160 * KP_ROLES * KP_SITES];
+#define KP_DECL long long kp_t = clock64(), kp_acc[KP_SITES] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define KP_LAP(i) do { const long long kp_n = clock64(); kp_acc[i] += kp_n - kp_t; kp_t = kp_n; } while (0)
+#define KP_FLUSH(role) do { if (blockIdx.x < 160) for (int kp_i = 0; kp_i < KP_SITES; ++kp_i) \
+    g_kprof[(blockIdx.x * KP_ROLES + (role)) * KP_SITES + kp_i] = kp_acc[kp_i]; } while (0)
+#else
+#define KP_DECL
+#define KP_LAP(i)
+#define KP_FLUSH(role)
+#endif
+
+__device__ __half g_vtab4[512 * 16];             // tap-validity rows of the H1-constant K-step (see conv_umma.cu)
+__global__ void vtab4_init_kernel() {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 512 * 16) g_vtab4[i] = __float2half(((i & 15) < 9 && ((i >> 4) >> (i & 15) & 1)) ? 1.f : 0.f);
+}
+
+struct Tables {
+  int kch[KIDX_MAX];       // real input channel of this sample's compact input channel e
+  float scale[BN_MAX];
+  float shift[BN_MAX];
+  int cpos[BN_MAX];        // OUT_ROWS: compact position of tile column c, or -1
+  unsigned long long full[MAX_STAGES], empty[MAX_STAGES], tfull[4], tempty[4], rfull[2][MAX_RING];
+  uint32_t tmem_base;
+};
+
+struct Plan {              // host-computed launch geometry
+  int n_mtiles, n_mgroups, MT, NT, NTI, BN, total_items;
+  int stages, stage_bytes, b_off;
+  int bmode, omode;
+  int R;                   // 3x3: output rows per m-tile (0 for 1x1)
+  int rows_per_tile;       // pixels of a full m-tile: 128 (1x1) or R*W_out
+  int nbuf, acc_cols;      // accumulator buffers; TMEM columns of one accumulator
+  int ring;                // slabs per half (OUT_SLAB)
+  int stg_pitch;           // OUT_ROWS: bytes per staging row (multiple of 128)
+  int full_count;          // arrivals that complete a stage
+  int a_tx, b_tx, r_tx;    // bytes one A-tile / B-tile / residual-slab TMA copy delivers
+};
+
+struct Sub {               // one (sample, m-group, n-tile) unit of work
+  int b, nt, n0, n_valid, umma_n, Nc, Nfill, Kc, nk16, cpt, nchunks, has_bias, mt0, mt_cnt;
+};
+
+__device__ __forceinline__ bool decode_sub(const ConvArgs& a, const Plan& pl, int t, int nti, Sub& s) {
+  const int NG = pl.NT / pl.NTI;
+  const int ng = t % NG;
+  const int r = t / NG;
+  const int mg = r % pl.n_mgroups;
+  const int slot = r / pl.n_mgroups;
+  const int ns = a.sample_cnt ? __ldg(a.sample_cnt) : a.B;
+  if (slot >= ns) return false;
+  s.b = a.sample_idx ? __ldg(a.sample_idx + slot) : slot;
+  s.nt = ng * pl.NTI + nti;
+  s.Nc = a.n_idx ? __ldg(a.n_cnt + s.b) * a.n_gran : a.C_out;
+  s.Nfill = round_up(s.Nc, a.n_pad_align);
+  // KROWS tiles span REAL output channels (the epilogue compacts); the others span the stored row
+  const int span = (pl.bmode == BMODE_KROWS) ? a.C_out : s.Nfill;
+  s.n0 = s.nt * pl.BN;
+  if (s.n0 >= span) return false;
+  s.n_valid = min(pl.BN, span - s.n0);
+  s.umma_n = round_up(s.n_valid, 16);
+  s.Kc = a.k_idx ? __ldg(a.k_cnt + s.b) * a.k_gran : a.C_in;
+  s.nk16 = (s.Kc + 15) >> 4;
+  s.cpt = (s.nk16 + 3) >> 2;
+  s.has_bias = a.bias_t != nullptr ? 1 : 0;
+  s.nchunks = s.cpt * a.ksize * a.ksize + s.has_bias;
+  s.mt0 = mg * pl.MT;
+  s.mt_cnt = min(pl.MT, pl.n_mtiles - s.mt0);
+  return true;
+}
+
+// first output pixel (within the sample) and number of valid pixels of m-tile mt
+__device__ __forceinline__ void tile_rows(const ConvArgs& a, const Plan& pl, int mt, int& m0, int& rows) {
+  if (pl.R) {
+    const int oy0 = mt * pl.R;
+    m0 = oy0 * a.W_out;
+    rows = min(pl.R, a.H_out - oy0) * a.W_out;
+  } else {
+    m0 = mt * BM;
+    rows = min(BM, a.H_out * a.W_out - m0);
+  }
+}
+
+// slab tasks of one epilogue half, in execution order (used by the residual prefetcher)
+struct Cursor {
+  int t, nti, mt, sl, have;
+  Sub s;
+};
+__device__ __forceinline__ bool cursor_next(const ConvArgs& a, const Plan& pl, Cursor& c, int h) {
+  if (c.have) {
+    c.sl += 2;
+    if (c.sl * 64 < c.s.n_valid) return true;
+    c.sl = h;
+    if (++c.mt < c.s.mt_cnt) return true;
+    c.have = 0;
+  }
+  while (true) {                                   // advance to the next sub-item in which this half has a slab
+    if (c.t < 0) { c.t = (int)blockIdx.x; c.nti = 0; }
+    else if (++c.nti >= pl.NTI) { c.t += (int)gridDim.x; c.nti = 0; }
+    if (c.t >= pl.total_items) return false;
+    if (decode_sub(a, pl, c.t, c.nti, c.s) && h * 64 < c.s.n_valid) {
+      c.have = 1;
+      c.mt = 0;
+      c.sl = h;
+      return true;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan pl,
+                const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_r) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* stg = smem + (size_t)pl.stages * pl.stage_bytes;       // slab rings / row staging (1024-aligned)
+  const int stg_bytes = pl.omode == OUT_SLAB ? 2 * pl.ring * SLAB_BYTES : BM * pl.stg_pitch;
+  Tables& T = *reinterpret_cast<Tables*>(stg + stg_bytes);
+  const uint32_t smem_base = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int HWo = a.H_out * a.W_out;
+  const int taps = a.ksize * a.ksize;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < pl.stages; ++s) {
+      mbar_init(&T.full[s], pl.full_count);
+      mbar_init(&T.empty[s], 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&T.tfull[i], 1);
+      mbar_init(&T.tempty[i], EPI_THREADS);
+    }
+    for (int h = 0; h < 2; ++h)
+      for (int i = 0; i < MAX_RING; ++i) mbar_init(&T.rfull[h][i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == TMA_WARP && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    if (pl.bmode == BMODE_TMA) tma_prefetch_desc(&map_b);
+  }
+  if (warp == 0 && lane == 0 && pl.omode == OUT_SLAB) {
+    tma_prefetch_desc(&map_y);
+    if (a.residual) tma_prefetch_desc(&map_r);
+  }
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&T.tmem_base)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = T.tmem_base;
+
+  if (warp == TMA_WARP) {
+    // =========================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      KP_DECL;
+      for (int t = blockIdx.x; t < pl.total_items; t += gridDim.x) {
+        for (int nti = 0; nti < pl.NTI; ++nti) {
+          Sub s;
+          if (!decode_sub(a, pl, t, nti, s)) continue;
+          KP_LAP(0);                                 // decode
+          const uint32_t tx = (uint32_t)(s.mt_cnt * pl.a_tx + (pl.bmode == BMODE_TMA ? pl.b_tx : 0));
+          for (int tap = 0; tap < taps; ++tap) {
+            const int ty = tap / a.ksize, tx_ = tap - ty * a.ksize;
+            for (int kq = 0; kq < s.cpt; ++kq) {
+              const int k0 = kq * 64;
+              mbar_wait(&T.empty[stage], phase ^ 1);
+              KP_LAP(1);                             // wait for a free stage
+              const uint32_t As = smem_base + stage * pl.stage_bytes;
+              mbar_arrive_expect_tx(&T.full[stage], tx);
+              for (int m = 0; m < s.mt_cnt; ++m) {
+                const int mt = s.mt0 + m;
+                if (pl.R) tma_load_4d(As + m * A_TILE_BYTES, &map_a, &T.full[stage], k0, tx_ - a.pad, mt * pl.R + ty - a.pad, s.b);
+                else tma_load_3d(As + m * A_TILE_BYTES, &map_a, &T.full[stage], k0, mt * BM, s.b);
+              }
+              if (pl.bmode == BMODE_TMA)
+                tma_load_2d(As + pl.b_off, &map_b, &T.full[stage], tap * a.C_in + k0, s.n0);
+              if (++stage == pl.stages) { stage = 0; phase ^= 1; }
+              KP_LAP(2);                             // issue
+            }
+          }
+          if (s.has_bias) {                       // the H1-constant step is staged by the gather warps only
+            mbar_wait(&T.empty[stage], phase ^ 1);
+            mbar_arrive(&T.full[stage]);
+            if (++stage == pl.stages) { stage = 0; phase ^= 1; }
+            KP_LAP(1);
+          }
+        }
+      }
+      KP_FLUSH(0);
+    }
+    __syncwarp();
+  } else if (warp == MMA_WARP) {
+    // =========================================================== MMA issuer
+    if (lane == 0) {
+      int stage = 0, buf = 0;
+      uint32_t phase = 0, bphase = 0;
+      KP_DECL;
+      for (int t = blockIdx.x; t < pl.total_items; t += gridDim.x) {
+        for (int nti = 0; nti < pl.NTI; ++nti) {
+          Sub s;
+          if (!decode_sub(a, pl, t, nti, s)) continue;
+          KP_LAP(0);                                             // decode
+          mbar_wait(&T.tempty[buf], bphase ^ 1);                 // epilogue has drained this buffer
+          KP_LAP(1);                                             // wait for a free accumulator
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * (pl.MT * pl.acc_cols);
+          const uint32_t idesc = umma_idesc_f16(s.umma_n, pl.bmode == BMODE_KROWS);
+          for (int ch = 0; ch < s.nchunks; ++ch) {
+            const bool bias_step = s.has_bias && ch == s.nchunks - 1;
+            const int n16 = bias_step ? 1 : min(4, s.nk16 - (ch % s.cpt) * 4);
+            mbar_wait(&T.full[stage], phase);
+            KP_LAP(2);                                           // wait for operands
+            fence_proxy_async();
+            tc_fence_after();
+            const uint32_t As = smem_base + stage * pl.stage_bytes;
+            const uint32_t Bs = As + pl.b_off;
+            const uint64_t bd = pl.bmode == BMODE_KROWS ? umma_desc(Bs, 8192, 1024) : umma_desc(Bs, 16, 1024);
+            const uint64_t bstep = pl.bmode == BMODE_KROWS ? 128 : 2;
+            for (int m = 0; m < s.mt_cnt; ++m) {
+              const uint64_t ad = umma_desc(As + m * A_TILE_BYTES, 16, 1024);
+              for (int k = 0; k < n16; ++k)
+                umma_f16(d_tmem + m * pl.acc_cols, ad + 2 * k, bd + bstep * k, idesc, (ch | k) ? 1u : 0u);
+            }
+            umma_commit(&T.empty[stage]);                        // frees the stage when these MMAs retire
+            if (++stage == pl.stages) { stage = 0; phase ^= 1; }
+            KP_LAP(3);                                           // issue
+          }
+          if (s.nchunks > 0) umma_commit(&T.tfull[buf]);
+          else mbar_arrive(&T.tfull[buf]);                       // no active input channel: accumulator unused
+          if (++buf == pl.nbuf) { buf = 0; bphase ^= 1; }
+        }
+      }
+      KP_FLUSH(1);
+    }
+    __syncwarp();
+  } else if (warp >= GATHER_WARP0) {
+    // =========================================================== weight gather (cp.async)
+    if (pl.bmode != BMODE_TMA) {
+      const int pt = threadIdx.x - GATHER_WARP0 * 32;            // 0..191
+      const int pw = pt >> 5;
+      const int ac = pt & 7, ar0 = pt >> 3;                      // ROWS: 16-byte chunk, first row (rows ar0 + 24 i)
+      int stage = 0;
+      uint32_t phase = 0;
+      KP_DECL;
+      for (int t = blockIdx.x; t < pl.total_items; t += gridDim.x) {
+        for (int nti = 0; nti < pl.NTI; ++nti) {
+          Sub s;
+          if (!decode_sub(a, pl, t, nti, s)) continue;
+          KP_LAP(0);                                             // decode
+          const int cpr = s.umma_n >> 3;                         // 16-byte chunks per k-row (KROWS)
+          int cpr2 = 2;
+          while (cpr2 < cpr) cpr2 <<= 1;                         // lanes per k-row (power of two <= 32)
+          const int rows_per_pass = 32 / cpr2 * GATHER_WARPS;
+          const int kr0 = pw * (32 / cpr2) + lane / cpr2, kc = lane % cpr2;
+          const bool kc_ok = kc < cpr && s.n0 + kc * 8 < a.C_out;
+          const uint32_t kdst0 = (uint32_t)((kc >> 3) * 8192 + ((kc & 7) << 4));   // n-block + chunk (pre-swizzle)
+          int browr[11];
+          named_bar_sync(1, GATHER_THREADS);                     // previous sub-item's table reads are done
+          if (pl.bmode == BMODE_ROWS) {
+#pragma unroll
+            for (int i = 0; i < 11; ++i) {
+              const int row = ar0 + 24 * i, jj = s.n0 + row;
+              browr[i] = (row < s.umma_n && jj < s.Nc)
+                             ? (a.n_idx ? __ldg(a.n_idx + (size_t)s.b * a.n_ld + jj / a.n_gran) * a.n_gran + jj % a.n_gran : jj) * taps * a.C_in
+                             : -1;
+            }
+          } else {
+            for (int e = pt; e < s.Kc; e += GATHER_THREADS) {
+              const int q = e / a.k_gran;
+              T.kch[e] = __ldg(a.k_idx + (size_t)s.b * a.k_ld + q) * a.k_gran + (e - q * a.k_gran);
+            }
+          }
+          named_bar_sync(1, GATHER_THREADS);
+          KP_LAP(1);                                             // index tables + barriers
+          for (int tap = 0; tap < taps; ++tap) {
+            const int tapk = tap * a.C_in;
+            for (int kq = 0; kq < s.cpt; ++kq) {
+              const int k0 = kq * 64;
+              const int n16 = min(4, s.nk16 - kq * 4);
+              mbar_wait(&T.empty[stage], phase ^ 1);
+              KP_LAP(2);                                         // wait for a free stage
+              const uint32_t Bs = smem_base + stage * pl.stage_bytes + pl.b_off;
+              if (pl.bmode == BMODE_ROWS) {
+                if (ac < 2 * n16) {
+                  const int k = k0 + ac * 8;
+                  const bool kok = k < a.C_in;
+                  const __half* wk = a.w + tapk + k;
+#pragma unroll
+                  for (int i = 0; i < 11; ++i) {
+                    const int row = ar0 + 24 * i;
+                    if (row < s.umma_n) {
+                      const bool ok = kok && browr[i] >= 0;
+                      cp_async_16(Bs + sw128_off(row, ac), ok ? wk + browr[i] : a.w, ok ? 16u : 0u);
+                    }
+                  }
+                }
+              } else if (kc < cpr) {
+                const int nrows = 16 * n16;
+                const __half* wn = a.wt + s.n0 + kc * 8;
+                for (int kk = kr0; kk < nrows; kk += rows_per_pass) {
+                  const int e = k0 + kk;
+                  const bool ok = kc_ok && e < s.Kc;
+                  int rk = 0;
+                  if (ok) rk = T.kch[e];
+                  const uint32_t dst = Bs + (kdst0 ^ (uint32_t)((kk & 7) << 4)) + (kk >> 3) * 1024 + (kk & 7) * 128;
+                  cp_async_16(dst, ok ? wn + (size_t)(tapk + rk) * a.C_out : a.w, ok ? 16u : 0u);
+                }
+              }
+              cp_async_arrive(&T.full[stage]);
+              if (++stage == pl.stages) { stage = 0; phase ^= 1; }
+              KP_LAP(3);                                         // issue
+            }
+          }
+          if (s.has_bias) {
+            // one more K=16 step: A' = tap-validity indicator of each pixel, B' = this sample's H1 constants
+            // T[b, tap, o] (zero rows for tap >= taps): adds sum_{valid taps} T[b,tap,o] to the accumulator
+            mbar_wait(&T.empty[stage], phase ^ 1);
+            KP_LAP(2);
+            const uint32_t As = smem_base + stage * pl.stage_bytes;
+            const uint32_t Bs = As + pl.b_off;
+            for (int i = pt; i < s.mt_cnt * BM * 2; i += GATHER_THREADS) {
+              const int m = i / (BM * 2), rr = (i >> 1) & (BM - 1), c = i & 1;
+              int m0, rows;
+              tile_rows(a, pl, s.mt0 + m, m0, rows);
+              int vm = 0;
+              if (rr < rows) {
+                const int p = m0 + rr;
+                const int oy = p / a.W_out, ox = p - oy * a.W_out;
+                for (int tp = 0; tp < taps; ++tp) {
+                  const int iy = oy - a.pad + tp / a.ksize, ix = ox - a.pad + tp % a.ksize;
+                  if (iy >= 0 && iy < a.H_in && ix >= 0 && ix < a.W_in) vm |= 1 << tp;
+                }
+              }
+              cp_async_16(As + m * A_TILE_BYTES + sw128_off(rr, c), g_vtab4 + vm * 16 + c * 8, 16u);
+            }
+            if (kc < cpr) {
+              for (int kk = kr0; kk < 16; kk += rows_per_pass) {
+                const bool ok = kc_ok && kk < taps;
+                const uint32_t dst = Bs + (kdst0 ^ (uint32_t)((kk & 7) << 4)) + (kk >> 3) * 1024 + (kk & 7) * 128;
+                cp_async_16(dst, ok ? a.bias_t + (size_t)s.b * a.bias_ld + (size_t)kk * a.C_out + s.n0 + kc * 8 : a.w,
+                            ok ? 16u : 0u);
+              }
+            }
+            cp_async_arrive(&T.full[stage]);
+            if (++stage == pl.stages) { stage = 0; phase ^= 1; }
+            KP_LAP(4);                                           // H1-constant step
+          }
+        }
+      }
+      if (pt == 0) KP_FLUSH(2);
+      asm volatile("cp.async.wait_all;" ::: "memory");
+    }
+  } else {
+    // =========================================================== epilogue
+    const int et = threadIdx.x;                                  // 0..255
+    const int q = warp & 3, h = warp >> 2;                       // TMEM lane quadrant, column half
+    const int row = q * 32 + lane;                               // accumulator row (TMEM lane) of this thread
+    const bool elected = (warp == 4 * h) && lane == 0;           // issues this half's TMA copies
+    unsigned char* ring = stg + (size_t)h * pl.ring * SLAB_BYTES;
+    const bool relu_all = a.relu_mode == LAUD_RELU_ALL;
+    int buf = 0;
+    uint32_t bphase = 0;
+    int task = 0;                                                // slab tasks done by this half
+    Cursor cur;                                                  // residual prefetcher (elected thread)
+    cur.t = -1; cur.nti = 0; cur.mt = 0; cur.sl = 0; cur.have = 0;
+    int pf = 0;                                                  // slab tasks whose residual load has been issued
+    if (pl.omode == OUT_SLAB && a.residual && elected) {
+      for (; pf < pl.ring - 1; ++pf) {
+        if (!cursor_next(a, pl, cur, h)) break;
+        int m0, rows;
+        tile_rows(a, pl, cur.s.mt0 + cur.mt, m0, rows);
+        mbar_arrive_expect_tx(&T.rfull[h][pf % pl.ring], (uint32_t)pl.r_tx);
+        tma_load_3d(smem_u32(ring + (pf % pl.ring) * SLAB_BYTES), &map_r, &T.rfull[h][pf % pl.ring],
+                    cur.s.n0 + cur.sl * 64, m0, cur.s.b);
+      }
+    }
+    KP_DECL;
+    for (int t = blockIdx.x; t < pl.total_items; t += gridDim.x) {
+      for (int nti = 0; nti < pl.NTI; ++nti) {
+        Sub s;
+        if (!decode_sub(a, pl, t, nti, s)) continue;
+        KP_LAP(0);                                               // decode
+        named_bar_sync(2, EPI_THREADS);                          // previous sub-item's table reads are done
+        for (int c = et; c < min(round_up(s.umma_n, 64), BN_MAX); c += EPI_THREADS) {
+          const int jj = s.n0 + c;
+          int o = -1, pos = -1;
+          if (pl.omode == OUT_ROWS) {
+            // real channel jj: active iff its group is in the sample's ascending list; its rank is the compact position
+            if (c < s.n_valid) {
+              if (a.n_idx) {
+                const int grp = jj / a.n_gran, na = s.Nc / a.n_gran;
+                const int* lst = a.n_idx + (size_t)s.b * a.n_ld;
+                int lo = 0, hi = na;
+                while (lo < hi) {
+                  const int mid = (lo + hi) >> 1;
+                  if (__ldg(lst + mid) < grp) lo = mid + 1; else hi = mid;
+                }
+                if (lo < na && __ldg(lst + lo) == grp) { o = jj; pos = lo * a.n_gran + jj % a.n_gran; }
+              } else {
+                o = jj; pos = jj;
+              }
+            }
+          } else if (c < s.n_valid && jj < s.Nc) {
+            o = a.n_idx ? __ldg(a.n_idx + (size_t)s.b * a.n_ld + jj / a.n_gran) * a.n_gran + jj % a.n_gran : jj;
+          }
+          float sc = o >= 0 ? 1.f : 0.f, sh = 0.f;               // inactive / pad columns come out as exact zeros
+          if (o >= 0 && a.scale) { sc = __ldg(a.scale + o); sh = __ldg(a.shift + o); }
+          T.scale[c] = sc; T.shift[c] = sh; T.cpos[c] = pos;
+        }
+        named_bar_sync(2, EPI_THREADS);
+        KP_LAP(1);                                               // column tables + barriers
+        mbar_wait(&T.tfull[buf], bphase);
+        KP_LAP(2);                                               // wait for the accumulator
+        tc_fence_after();
+        const uint32_t tbase = tmem_base + buf * (pl.MT * pl.acc_cols) + ((uint32_t)(q * 32) << 16);
+        const bool have_acc = s.nchunks > 0;
+
+        for (int m = 0; m < s.mt_cnt; ++m) {
+          int m0, rows;
+          tile_rows(a, pl, s.mt0 + m, m0, rows);
+          if (pl.omode == OUT_SLAB) {
+            bool row_on = true;                                  // spatial / layer gate of this pixel (one mask group)
+            if (a.out_mask) row_on = row < rows && a.out_mask[(size_t)s.b * HWo + m0 + row] != 0;
+            for (int sl = h; sl * 64 < s.n_valid; sl += 2, ++task) {
+              const int slot = task % pl.ring;
+              unsigned char* slab = ring + slot * SLAB_BYTES;
+              unsigned char* srow = slab + row * 128;
+              if (a.residual) mbar_wait(&T.rfull[h][slot], (uint32_t)(task / pl.ring) & 1u);
+              KP_LAP(3);                                         // wait for the residual slab
+#pragma unroll
+              for (int p = 0; p < 2; ++p) {
+                const int c0 = sl * 64 + p * 32;
+                if (c0 >= s.umma_n) break;
+                float v[32];
+                if (have_acc) {
+                  tmem_ld32(tbase + m * pl.acc_cols + c0, v);
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 32; ++e) v[e] = 0.f;
+                }
+#pragma unroll
+                for (int g4 = 0; g4 < 4; ++g4) {                 // 8 channels = one 16-byte chunk
+                  const float4 s0 = *reinterpret_cast<const float4*>(T.scale + c0 + g4 * 8);
+                  const float4 s1 = *reinterpret_cast<const float4*>(T.scale + c0 + g4 * 8 + 4);
+                  const float4 h0 = *reinterpret_cast<const float4*>(T.shift + c0 + g4 * 8);
+                  const float4 h1 = *reinterpret_cast<const float4*>(T.shift + c0 + g4 * 8 + 4);
+                  float* w = v + g4 * 8;
+                  w[0] = fmaf(w[0], s0.x, h0.x); w[1] = fmaf(w[1], s0.y, h0.y);
+                  w[2] = fmaf(w[2], s0.z, h0.z); w[3] = fmaf(w[3], s0.w, h0.w);
+                  w[4] = fmaf(w[4], s1.x, h1.x); w[5] = fmaf(w[5], s1.y, h1.y);
+                  w[6] = fmaf(w[6], s1.z, h1.z); w[7] = fmaf(w[7], s1.w, h1.w);
+                  if (!row_on) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) w[e] = 0.f;
+                  }
+                  uint4* cell = reinterpret_cast<uint4*>(srow + (((p * 4 + g4) ^ (row & 7)) << 4));
+                  if (a.residual) {
+                    const uint4 r4 = *cell;
+                    const __half2* rh = reinterpret_cast<const __half2*>(&r4);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      const float2 f = __half22float2(rh[e]);
+                      w[2 * e] += f.x;
+                      w[2 * e + 1] += f.y;
+                    }
+                  }
+                  if (relu_all) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) w[e] = fmaxf(w[e], 0.f);
+                  }
+                  uint4 o4;
+                  __half2* oh = reinterpret_cast<__half2*>(&o4);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(w[2 * e], w[2 * e + 1]);
+                  *cell = o4;
+                }
+              }
+              KP_LAP(4);                                         // TMEM -> registers -> slab
+              fence_proxy_async();                               // generic-proxy slab writes -> visible to the TMA store
+              if (elected && !a.residual) {                      // the NEXT task's slab must have left shared memory
+                if (pl.ring == 3) bulk_wait_read_n<1>(); else bulk_wait_read_n<0>();
+              }
+              named_bar_sync(3 + h, HALF_THREADS);
+              if (elected) {
+                tma_store_3d(&map_y, smem_u32(slab), s.n0 + sl * 64, m0, s.b);
+                bulk_commit();
+                if (a.residual) {
+                  // slab of task-1 is free once its store has been read out; refill it for task + ring - 1
+                  bulk_wait_read_n<1>();
+                  if (pf == task + pl.ring - 1 && cursor_next(a, pl, cur, h)) {
+                    int pm0, prow;
+                    tile_rows(a, pl, cur.s.mt0 + cur.mt, pm0, prow);
+                    const int ps = pf % pl.ring;
+                    mbar_arrive_expect_tx(&T.rfull[h][ps], (uint32_t)pl.r_tx);
+                    tma_load_3d(smem_u32(ring + ps * SLAB_BYTES), &map_r, &T.rfull[h][ps], cur.s.n0 + cur.sl * 64, pm0,
+                                cur.s.b);
+                    ++pf;
+                  }
+                }
+              }
+              KP_LAP(5);                                         // barrier + store + prefetch
+            }
+          } else {
+            // ---- OUT_ROWS: compact the active real channels of this pixel row into the staging row
+            unsigned char* srow = stg + (size_t)row * pl.stg_pitch;
+            for (int c0 = h * 32; c0 < s.n_valid; c0 += 64) {
+              float v[32];
+              if (have_acc) {
+                tmem_ld32(tbase + m * pl.acc_cols + c0, v);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 32; ++e) v[e] = 0.f;
+              }
+#pragma unroll
+              for (int e = 0; e < 32; e += 2) {
+                const int pos = T.cpos[c0 + e];                  // channel pairs share a gate (even granularity)
+                if (pos >= 0) {
+                  float x0 = fmaf(v[e], T.scale[c0 + e], T.shift[c0 + e]);
+                  float x1 = fmaf(v[e + 1], T.scale[c0 + e + 1], T.shift[c0 + e + 1]);
+                  if (relu_all) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+                  const int wd = pos >> 1;
+                  *reinterpret_cast<__half2*>(srow + (((wd & ~31) | ((wd ^ row) & 31)) << 2)) = __floats2half2_rn(x0, x1);
+                }
+              }
+            }
+            KP_LAP(4);
+            if (nti == pl.NTI - 1) {
+              // last n-tile of the row: zero pad [Nc, Nfill), then flush the tile's rows to y (coalesced words)
+              if (h == 0)
+                for (int j = s.Nc; j < s.Nfill; j += 2) {
+                  const int wd = j >> 1;
+                  *reinterpret_cast<__half2*>(srow + (((wd & ~31) | ((wd ^ row) & 31)) << 2)) = __floats2half2_rn(0.f, 0.f);
+                }
+              named_bar_sync(5, EPI_THREADS);
+              const int nw = s.Nfill >> 1;
+              for (int r = warp; r < rows; r += EPI_WARPS) {
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(stg + (size_t)r * pl.stg_pitch);
+                uint32_t* dst = reinterpret_cast<uint32_t*>(a.y + ((size_t)s.b * HWo + m0 + r) * a.ldy);
+                for (int w = lane; w < nw; w += 32) dst[w] = src[(w & ~31) | ((w ^ r) & 31)];
+              }
+              named_bar_sync(5, EPI_THREADS);                    // staging may be overwritten by the next tile
+              KP_LAP(5);                                         // flush
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&T.tempty[buf]);                             // accumulators drained: the MMA warp may reuse them
+        if (++buf == pl.nbuf) { buf = 0; bphase ^= 1; }
+      }
+    }
+    if (pl.omode == OUT_SLAB) bulk_wait_all();
+    KP_LAP(6);
+    if (et == 0) KP_FLUSH(3);
+    if (et == HALF_THREADS) KP_FLUSH(4);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// fp16 tensor map, 128-byte swizzle, innermost dimension first; strides in ELEMENTS for dims 1..rank-1
+bool make_map(CUtensorMap* m, const void* base, int rank, const long long* dims, const long long* strides_elems,
+              const int* box) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t gdim[4], gstr[3];
+  cuuint32_t bx[4], es[4];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = (cuuint64_t)dims[i];
+    bx[i] = (cuuint32_t)box[i];
+    es[i] = 1;
+    if (i > 0) gstr[i - 1] = (cuuint64_t)strides_elems[i - 1] * 2;
+  }
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+// Layouts the TMA kernel takes; everything else runs on the v3 kernel.
+bool conv_tma_supported(const ConvArgs& a) {
+  if (!conv_umma_supported(a)) return false;
+  if (a.stride != 1) return false;
+  if (!((a.ksize == 1 && a.pad == 0) || (a.ksize == 3 && a.pad == 1))) return false;
+  if (a.row_idx || a.pre_bias || a.relu_mode == LAUD_RELU_WHERE_GATE0) return false;
+  if (a.out_mask && a.mask_groups != 1) return false;
+  if (a.k_idx && !(a.wt && aligned16(a.wt))) return false;        // KUNITS layout
+  if (a.k_idx && a.n_idx && (a.residual || a.out_mask || (a.n_gran & 1))) return false;
+  if (a.n_idx && !a.k_idx && a.wt) return false;
+  if (a.ksize == 3 && (a.W_out > BM || a.H_in != a.H_out || a.W_in != a.W_out)) return false;
+  if (a.k_idx && a.n_idx && round_up(a.C_out, 16) * 2 > 1024) return false;   // staging row
+  if ((long long)a.B * a.H_out * a.W_out >= (1ll << 31)) return false;
+  if (a.bias_t && !a.k_idx) return false;
+  return encode_fn() != nullptr;
+}
+
+int conv_forward_tma(const ConvArgs& a, cudaStream_t s) {
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    LAUD_CUDA(cudaGetDevice(&dev));
+    LAUD_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    LAUD_CUDA(cudaFuncSetAttribute(conv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    vtab4_init_kernel<<<32, 256, 0, s>>>();
+    if (int e = check_launch("vtab4_init_kernel")) return e;
+  }
+  Plan pl{};
+  const int HWo = a.H_out * a.W_out;
+  const int taps = a.ksize * a.ksize;
+  pl.bmode = a.k_idx ? BMODE_KROWS : (a.n_idx ? BMODE_ROWS : BMODE_TMA);
+  pl.omode = (a.k_idx && a.n_idx) ? OUT_ROWS : OUT_SLAB;
+  if (a.ksize == 3) {
+    pl.R = BM / a.W_out;
+    if (pl.R > a.H_out) pl.R = a.H_out;
+    // prefer an even split of the rows over one full and one nearly empty tile
+    const int nt0 = (a.H_out + pl.R - 1) / pl.R;
+    pl.R = (a.H_out + nt0 - 1) / nt0;
+    pl.rows_per_tile = pl.R * a.W_out;
+    pl.n_mtiles = (a.H_out + pl.R - 1) / pl.R;
+  } else {
+    pl.R = 0;
+    pl.rows_per_tile = BM;
+    pl.n_mtiles = (HWo + BM - 1) / BM;
+  }
+  pl.MT = pl.n_mtiles >= 2 ? 2 : 1;
+  const int nfill_max = round_up(a.C_out, a.n_pad_align);
+  const int span = pl.bmode == BMODE_KROWS ? a.C_out : nfill_max;
+  if (pl.omode == OUT_ROWS) {
+    pl.BN = span <= BN_MAX ? round_up(span, 16) : BN_MAX;
+    pl.NT = (span + pl.BN - 1) / pl.BN;
+    pl.NTI = pl.NT;
+    if (pl.NTI > 1) pl.MT = 1;                 // one staging tile: all n-tiles of ONE m-tile before the flush
+  } else {
+    pl.BN = span <= 64 ? 64 : 128;
+    pl.NT = (span + pl.BN - 1) / pl.BN;
+    pl.NTI = 1;
+  }
+  pl.n_mgroups = (pl.n_mtiles + pl.MT - 1) / pl.MT;
+  const long long total = (long long)a.B * pl.n_mgroups * (pl.NT / pl.NTI);
+  if (total >= (1ll << 31)) {
+    set_error("conv_forward_tma: too many tiles");
+    return LAUD_E_BADARG;
+  }
+  pl.total_items = (int)total;
+  pl.acc_cols = pl.BN <= 64 ? 64 : (pl.BN <= 128 ? 128 : 256);
+  pl.nbuf = (int)TMEM_COLS / (pl.MT * pl.acc_cols);
+  if (pl.nbuf > 4) pl.nbuf = 4;
+  const int b_bytes = pl.bmode == BMODE_KROWS ? ((pl.BN + 63) / 64) * 8192 : pl.BN * 128;
+  pl.b_off = pl.MT * A_TILE_BYTES;
+  pl.stage_bytes = pl.b_off + round_up(b_bytes, 1024);
+  pl.ring = a.residual ? 3 : 2;
+  pl.stg_pitch = round_up(round_up(nfill_max, 16) * 2, 128);
+  const int stg_bytes = pl.omode == OUT_SLAB ? 2 * pl.ring * SLAB_BYTES : BM * pl.stg_pitch;
+  const int avail = SMEM_LIMIT - 1024 - (int)sizeof(Tables) - stg_bytes;
+  pl.stages = avail / pl.stage_bytes;
+  if (pl.stages > MAX_STAGES) pl.stages = MAX_STAGES;
+  if (pl.stages < 2) return conv_forward_umma(a, s);
+  pl.full_count = 1 + (pl.bmode == BMODE_TMA ? 0 : GATHER_THREADS);
+  const int rows_box = pl.rows_per_tile < HWo ? pl.rows_per_tile : HWo;     // boxes never exceed the tensor extent
+  const int bn_box = pl.BN < a.C_out ? pl.BN : a.C_out;
+  pl.a_tx = 128 * rows_box;
+  pl.b_tx = 128 * bn_box;
+  pl.r_tx = 128 * rows_box;
+
+  CUtensorMap map_a, map_b, map_y, map_r;
+  memset(&map_b, 0, sizeof(map_b));
+  memset(&map_y, 0, sizeof(map_y));
+  memset(&map_r, 0, sizeof(map_r));
+  bool ok = true;
+  const long long cext_a = a.k_idx ? a.ldx : a.C_in;     // compact inputs may be read up to their pitch (zero padded by the producer)
+  if (a.ksize == 3) {
+    const long long dims[4] = {cext_a, a.W_in, a.H_in, a.B};
+    const long long str[3] = {a.ldx, (long long)a.W_in * a.ldx, (long long)a.H_in * a.W_in * a.ldx};
+    const int box[4] = {64, a.W_out, pl.R, 1};
+    ok = ok && make_map(&map_a, a.x, 4, dims, str, box);
+  } else {
+    const long long dims[3] = {cext_a, HWo, a.B};
+    const long long str[2] = {a.ldx, (long long)HWo * a.ldx};
+    const int box[3] = {64, rows_box, 1};
+    ok = ok && make_map(&map_a, a.x, 3, dims, str, box);
+  }
+  if (pl.bmode == BMODE_TMA) {
+    const long long dims[2] = {(long long)taps * a.C_in, a.C_out};
+    const long long str[1] = {(long long)taps * a.C_in};
+    const int box[2] = {64, bn_box};
+    ok = ok && make_map(&map_b, a.w, 2, dims, str, box);
+  }
+  if (pl.omode == OUT_SLAB) {
+    const long long dims[3] = {a.ldy, HWo, a.B};
+    const long long str[2] = {a.ldy, (long long)HWo * a.ldy};
+    const int box[3] = {64, rows_box, 1};
+    ok = ok && make_map(&map_y, a.y, 3, dims, str, box);
+    if (a.residual) {
+      const long long rdims[3] = {a.C_out, HWo, a.B};
+      const long long rstr[2] = {a.ldr, (long long)HWo * a.ldr};
+      ok = ok && make_map(&map_r, a.residual, 3, rdims, rstr, box);
+    }
+  }
+  if (!ok) return conv_forward_umma(a, s);       // the driver refused a descriptor: v3 takes every layout v4 does
+
+  const size_t smem = 1024 + (size_t)pl.stages * pl.stage_bytes + stg_bytes + sizeof(Tables);
+  const int grid = (int)(total < num_sms ? total : num_sms);
+  g_conv_paths[0].fetch_add(1, std::memory_order_relaxed);
+  g_conv_tma_launches.fetch_add(1, std::memory_order_relaxed);
+  conv_tma_kernel<<<grid, NUM_THREADS, smem, s>>>(a, pl, map_a, map_b, map_y, map_r);
+  return check_launch("conv_tma_kernel");
+}
+
+#ifdef LAUD_KPROF
+// debug build only: copy (or reset) the lap timers of the last launches
+extern "C" int laud_debug_kprof(long long* host_out /* [160][5][8] */, int reset) {
+  void* p = nullptr;
+  if (cudaGetSymbolAddress(&p, g_kprof) != cudaSuccess) return -1;
+  const size_t n = sizeof(long long) * 160 * KP_ROLES * KP_SITES;
+  if (reset) return cudaMemset(p, 0, n) == cudaSuccess ? 0 : -1;
+  return cudaMemcpy(host_out, p, n, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
+}
+#endif
+
+}  // namespace laud

@@ -12,6 +12,7 @@ namespace laud {
 void set_error(const char* fmt, ...);
 extern std::atomic<unsigned long long> g_launches;
 extern std::atomic<unsigned long long> g_conv_paths[3];
+extern std::atomic<unsigned long long> g_conv_tma_launches;   // launches of the TMA-staged tcgen05 kernel (subset of g_conv_paths[0])
 
 inline int check_launch(const char* what) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -83,6 +84,8 @@ int conv_forward_naive(const ConvArgs& a, cudaStream_t s);
 int conv_forward_hmma(const ConvArgs& a, cudaStream_t s);
 int conv_forward_umma(const ConvArgs& a, cudaStream_t s);
 bool conv_umma_supported(const ConvArgs& a);
+int conv_forward_tma(const ConvArgs& a, cudaStream_t s);
+bool conv_tma_supported(const ConvArgs& a);
 
 // Shared epilogue: value for output (b, oy, ox), compact channel j / real channel o.
 __device__ __forceinline__ float conv_epilogue(const ConvArgs& a, float acc, int b, int oy, int ox,
