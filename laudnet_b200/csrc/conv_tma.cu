@@ -73,11 +73,15 @@ __global__ void vtab4_init_kernel() {
   if (i < 512 * 16) g_vtab4[i] = __float2half(((i & 15) < 9 && ((i >> 4) >> (i & 15) & 1)) ? 1.f : 0.f);
 }
 
+constexpr int CNT_CACHE = 512;                   // per-sample active counts cached in shared memory when B fits
+
 struct Tables {
   int kch[KIDX_MAX];       // real input channel of this sample's compact input channel e
-  float scale[BN_MAX];
-  float shift[BN_MAX];
-  int cpos[BN_MAX];        // OUT_ROWS: compact position of tile column c, or -1
+  float scale[2][BN_MAX];  // epilogue column tables, double-buffered across sub-items
+  float shift[2][BN_MAX];
+  int cpos[2][BN_MAX];     // OUT_ROWS: compact position of tile column c, or -1
+  int kcnt[CNT_CACHE], ncnt[CNT_CACHE];
+  unsigned short vmask[2][BM];   // tap-validity bit sets of the pixels of the current m-group (H1-constant step)
   unsigned long long full[MAX_STAGES], empty[MAX_STAGES], tfull[4], tempty[4], rfull[2][MAX_RING];
   uint32_t tmem_base;
 };
@@ -90,26 +94,41 @@ struct Plan {              // host-computed launch geometry
   int rows_per_tile;       // pixels of a full m-tile: 128 (1x1) or R*W_out
   int nbuf, acc_cols;      // accumulator buffers; TMEM columns of one accumulator
   int ring;                // slabs per half (OUT_SLAB)
-  int stg_pitch;           // OUT_ROWS: bytes per staging row (multiple of 128)
+  int stg_pitch, stg_rows; // OUT_ROWS: bytes per staging row (multiple of 128), rows
   int full_count;          // arrivals that complete a stage
   int a_tx, b_tx, r_tx;    // bytes one A-tile / B-tile / residual-slab TMA copy delivers
+  int cnt_cached;          // 1: Tables::kcnt / ncnt hold k_cnt / n_cnt of every sample
 };
 
 struct Sub {               // one (sample, m-group, n-tile) unit of work
-  int b, nt, n0, n_valid, umma_n, Nc, Nfill, Kc, nk16, cpt, nchunks, has_bias, mt0, mt_cnt;
+  int b, mg, nt, n0, n_valid, umma_n, Nc, Nfill, Kc, nk16, cpt, nchunks, has_bias, mt0, mt_cnt;
 };
 
-__device__ __forceinline__ bool decode_sub(const ConvArgs& a, const Plan& pl, int t, int nti, Sub& s) {
+// Every role walks the same CONTIGUOUS range of items (sample slot, m-group, n-group) of its CTA, and the
+// n-tiles inside an item, in the same order; consecutive sub-items mostly share the sample.
+struct Walker {
+  int t, t_end, slot, mg, ng, nti, started;
+};
+__device__ __forceinline__ void walker_init(const Plan& pl, Walker& w) {
+  const int base = pl.total_items / (int)gridDim.x, rem = pl.total_items % (int)gridDim.x;
+  const int c = (int)blockIdx.x;
+  w.t = c * base + min(c, rem);
+  w.t_end = w.t + base + (c < rem ? 1 : 0);
   const int NG = pl.NT / pl.NTI;
-  const int ng = t % NG;
-  const int r = t / NG;
-  const int mg = r % pl.n_mgroups;
-  const int slot = r / pl.n_mgroups;
+  w.ng = w.t % NG;
+  const int r = w.t / NG;
+  w.mg = r % pl.n_mgroups;
+  w.slot = r / pl.n_mgroups;
+  w.nti = 0;
+  w.started = 0;
+}
+__device__ __forceinline__ bool decode_sub(const ConvArgs& a, const Plan& pl, const Tables& T, const Walker& w, Sub& s) {
   const int ns = a.sample_cnt ? __ldg(a.sample_cnt) : a.B;
-  if (slot >= ns) return false;
-  s.b = a.sample_idx ? __ldg(a.sample_idx + slot) : slot;
-  s.nt = ng * pl.NTI + nti;
-  s.Nc = a.n_idx ? __ldg(a.n_cnt + s.b) * a.n_gran : a.C_out;
+  if (w.slot >= ns) return false;
+  s.b = a.sample_idx ? __ldg(a.sample_idx + w.slot) : w.slot;
+  s.mg = w.mg;
+  s.nt = w.ng * pl.NTI + w.nti;
+  s.Nc = a.n_idx ? (pl.cnt_cached ? T.ncnt[s.b] : __ldg(a.n_cnt + s.b)) * a.n_gran : a.C_out;
   s.Nfill = round_up(s.Nc, a.n_pad_align);
   // KROWS tiles span REAL output channels (the epilogue compacts); the others span the stored row
   const int span = (pl.bmode == BMODE_KROWS) ? a.C_out : s.Nfill;
@@ -117,14 +136,31 @@ __device__ __forceinline__ bool decode_sub(const ConvArgs& a, const Plan& pl, in
   if (s.n0 >= span) return false;
   s.n_valid = min(pl.BN, span - s.n0);
   s.umma_n = round_up(s.n_valid, 16);
-  s.Kc = a.k_idx ? __ldg(a.k_cnt + s.b) * a.k_gran : a.C_in;
+  s.Kc = a.k_idx ? (pl.cnt_cached ? T.kcnt[s.b] : __ldg(a.k_cnt + s.b)) * a.k_gran : a.C_in;
   s.nk16 = (s.Kc + 15) >> 4;
   s.cpt = (s.nk16 + 3) >> 2;
   s.has_bias = a.bias_t != nullptr ? 1 : 0;
   s.nchunks = s.cpt * a.ksize * a.ksize + s.has_bias;
-  s.mt0 = mg * pl.MT;
+  s.mt0 = w.mg * pl.MT;
   s.mt_cnt = min(pl.MT, pl.n_mtiles - s.mt0);
   return true;
+}
+// advance to the next valid sub-item of this CTA; false when the range is exhausted
+__device__ __forceinline__ bool walker_next(const ConvArgs& a, const Plan& pl, const Tables& T, Walker& w, Sub& s) {
+  while (true) {
+    if (!w.started) {
+      w.started = 1;
+    } else if (++w.nti >= pl.NTI) {
+      w.nti = 0;
+      ++w.t;
+      if (++w.ng >= pl.NT / pl.NTI) {
+        w.ng = 0;
+        if (++w.mg >= pl.n_mgroups) { w.mg = 0; ++w.slot; }
+      }
+    }
+    if (w.t >= w.t_end) return false;
+    if (decode_sub(a, pl, T, w, s)) return true;
+  }
 }
 
 // first output pixel (within the sample) and number of valid pixels of m-tile mt
@@ -141,10 +177,11 @@ __device__ __forceinline__ void tile_rows(const ConvArgs& a, const Plan& pl, int
 
 // slab tasks of one epilogue half, in execution order (used by the residual prefetcher)
 struct Cursor {
-  int t, nti, mt, sl, have;
+  Walker w;
   Sub s;
+  int mt, sl, have;
 };
-__device__ __forceinline__ bool cursor_next(const ConvArgs& a, const Plan& pl, Cursor& c, int h) {
+__device__ __forceinline__ bool cursor_next(const ConvArgs& a, const Plan& pl, const Tables& T, Cursor& c, int h) {
   if (c.have) {
     c.sl += 2;
     if (c.sl * 64 < c.s.n_valid) return true;
@@ -152,17 +189,45 @@ __device__ __forceinline__ bool cursor_next(const ConvArgs& a, const Plan& pl, C
     if (++c.mt < c.s.mt_cnt) return true;
     c.have = 0;
   }
-  while (true) {                                   // advance to the next sub-item in which this half has a slab
-    if (c.t < 0) { c.t = (int)blockIdx.x; c.nti = 0; }
-    else if (++c.nti >= pl.NTI) { c.t += (int)gridDim.x; c.nti = 0; }
-    if (c.t >= pl.total_items) return false;
-    if (decode_sub(a, pl, c.t, c.nti, c.s) && h * 64 < c.s.n_valid) {
+  while (walker_next(a, pl, T, c.w, c.s)) {          // next sub-item in which this half has a slab
+    if (h * 64 < c.s.n_valid) {
       c.have = 1;
       c.mt = 0;
       c.sl = h;
       return true;
     }
   }
+  return false;
+}
+
+// epilogue column tables of one sub-item: folded-BN scale / shift of tile column c and (OUT_ROWS) its compact position
+__device__ __forceinline__ void column_entry(const ConvArgs& a, const Plan& pl, const Sub& s, int c, float& sc, float& sh,
+                                             int& pos) {
+  const int jj = s.n0 + c;
+  int o = -1;
+  pos = -1;
+  if (c < s.n_valid) {
+    if (pl.omode == OUT_ROWS) {
+      // real channel jj: active iff its group is in the sample's ascending list; its rank is the compact position
+      if (a.n_idx) {
+        const int grp = jj / a.n_gran, na = s.Nc / a.n_gran;
+        const int* lst = a.n_idx + (size_t)s.b * a.n_ld;
+        int lo = 0, hi = na;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (__ldg(lst + mid) < grp) lo = mid + 1; else hi = mid;
+        }
+        if (lo < na && __ldg(lst + lo) == grp) { o = jj; pos = lo * a.n_gran + jj % a.n_gran; }
+      } else {
+        o = jj; pos = jj;
+      }
+    } else if (jj < s.Nc) {
+      o = a.n_idx ? __ldg(a.n_idx + (size_t)s.b * a.n_ld + jj / a.n_gran) * a.n_gran + jj % a.n_gran : jj;
+    }
+  }
+  sc = o >= 0 ? 1.f : 0.f;                                       // inactive / pad columns come out as exact zeros
+  sh = 0.f;
+  if (o >= 0 && a.scale) { sc = __ldg(a.scale + o); sh = __ldg(a.shift + o); }
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -173,7 +238,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* stg = smem + (size_t)pl.stages * pl.stage_bytes;       // slab rings / row staging (1024-aligned)
-  const int stg_bytes = pl.omode == OUT_SLAB ? 2 * pl.ring * SLAB_BYTES : BM * pl.stg_pitch;
+  const int stg_bytes = pl.omode == OUT_SLAB ? 2 * pl.ring * SLAB_BYTES : pl.stg_rows * pl.stg_pitch;
   Tables& T = *reinterpret_cast<Tables*>(stg + stg_bytes);
   const uint32_t smem_base = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -193,6 +258,11 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
       for (int i = 0; i < MAX_RING; ++i) mbar_init(&T.rfull[h][i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (pl.cnt_cached)                                              // one round trip for every per-sample count
+    for (int i = threadIdx.x; i < a.B; i += NUM_THREADS) {
+      T.kcnt[i] = a.k_idx ? __ldg(a.k_cnt + i) : 0;
+      T.ncnt[i] = a.n_idx ? __ldg(a.n_cnt + i) : 0;
+    }
   if (warp == TMA_WARP && lane == 0) {
     tma_prefetch_desc(&map_a);
     if (pl.bmode == BMODE_TMA) tma_prefetch_desc(&map_b);
@@ -211,6 +281,9 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = T.tmem_base;
+  Walker wk;
+  walker_init(pl, wk);
+  Sub s;
 
   if (warp == TMA_WARP) {
     // =========================================================== TMA producer
@@ -218,37 +291,33 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
       int stage = 0;
       uint32_t phase = 0;
       KP_DECL;
-      for (int t = blockIdx.x; t < pl.total_items; t += gridDim.x) {
-        for (int nti = 0; nti < pl.NTI; ++nti) {
-          Sub s;
-          if (!decode_sub(a, pl, t, nti, s)) continue;
-          KP_LAP(0);                                 // decode
-          const uint32_t tx = (uint32_t)(s.mt_cnt * pl.a_tx + (pl.bmode == BMODE_TMA ? pl.b_tx : 0));
-          for (int tap = 0; tap < taps; ++tap) {
-            const int ty = tap / a.ksize, tx_ = tap - ty * a.ksize;
-            for (int kq = 0; kq < s.cpt; ++kq) {
-              const int k0 = kq * 64;
-              mbar_wait(&T.empty[stage], phase ^ 1);
-              KP_LAP(1);                             // wait for a free stage
-              const uint32_t As = smem_base + stage * pl.stage_bytes;
-              mbar_arrive_expect_tx(&T.full[stage], tx);
-              for (int m = 0; m < s.mt_cnt; ++m) {
-                const int mt = s.mt0 + m;
-                if (pl.R) tma_load_4d(As + m * A_TILE_BYTES, &map_a, &T.full[stage], k0, tx_ - a.pad, mt * pl.R + ty - a.pad, s.b);
-                else tma_load_3d(As + m * A_TILE_BYTES, &map_a, &T.full[stage], k0, mt * BM, s.b);
-              }
-              if (pl.bmode == BMODE_TMA)
-                tma_load_2d(As + pl.b_off, &map_b, &T.full[stage], tap * a.C_in + k0, s.n0);
-              if (++stage == pl.stages) { stage = 0; phase ^= 1; }
-              KP_LAP(2);                             // issue
-            }
-          }
-          if (s.has_bias) {                       // the H1-constant step is staged by the gather warps only
+      while (walker_next(a, pl, T, wk, s)) {
+        KP_LAP(0);                                   // decode
+        const uint32_t tx = (uint32_t)(s.mt_cnt * pl.a_tx + (pl.bmode == BMODE_TMA ? pl.b_tx : 0));
+        for (int tap = 0; tap < taps; ++tap) {
+          const int ty = tap / a.ksize, tx_ = tap - ty * a.ksize;
+          for (int kq = 0; kq < s.cpt; ++kq) {
+            const int k0 = kq * 64;
             mbar_wait(&T.empty[stage], phase ^ 1);
-            mbar_arrive(&T.full[stage]);
+            KP_LAP(1);                               // wait for a free stage
+            const uint32_t As = smem_base + stage * pl.stage_bytes;
+            mbar_arrive_expect_tx(&T.full[stage], tx);
+            for (int m = 0; m < s.mt_cnt; ++m) {
+              const int mt = s.mt0 + m;
+              if (pl.R) tma_load_4d(As + m * A_TILE_BYTES, &map_a, &T.full[stage], k0, tx_ - a.pad, mt * pl.R + ty - a.pad, s.b);
+              else tma_load_3d(As + m * A_TILE_BYTES, &map_a, &T.full[stage], k0, mt * BM, s.b);
+            }
+            if (pl.bmode == BMODE_TMA)
+              tma_load_2d(As + pl.b_off, &map_b, &T.full[stage], tap * a.C_in + k0, s.n0);
             if (++stage == pl.stages) { stage = 0; phase ^= 1; }
-            KP_LAP(1);
+            KP_LAP(2);                               // issue
           }
+        }
+        if (s.has_bias) {                            // the H1-constant step is staged by the gather warps only
+          mbar_wait(&T.empty[stage], phase ^ 1);
+          mbar_arrive(&T.full[stage]);
+          if (++stage == pl.stages) { stage = 0; phase ^= 1; }
+          KP_LAP(1);
         }
       }
       KP_FLUSH(0);
@@ -260,40 +329,38 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
       int stage = 0, buf = 0;
       uint32_t phase = 0, bphase = 0;
       KP_DECL;
-      for (int t = blockIdx.x; t < pl.total_items; t += gridDim.x) {
-        for (int nti = 0; nti < pl.NTI; ++nti) {
-          Sub s;
-          if (!decode_sub(a, pl, t, nti, s)) continue;
-          KP_LAP(0);                                             // decode
-          mbar_wait(&T.tempty[buf], bphase ^ 1);                 // epilogue has drained this buffer
-          KP_LAP(1);                                             // wait for a free accumulator
+      while (walker_next(a, pl, T, wk, s)) {
+        KP_LAP(0);                                               // decode
+        mbar_wait(&T.tempty[buf], bphase ^ 1);                   // epilogue has drained this buffer
+        KP_LAP(1);                                               // wait for a free accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * (pl.MT * pl.acc_cols);
+        const uint32_t idesc = umma_idesc_f16(s.umma_n, pl.bmode == BMODE_KROWS);
+        for (int ch = 0; ch < s.nchunks; ++ch) {
+          const bool bias_step = s.has_bias && ch == s.nchunks - 1;
+          const int n16 = bias_step ? 1 : min(4, s.nk16 - (ch % s.cpt) * 4);
+          mbar_wait(&T.full[stage], phase);
+          KP_LAP(2);                                             // wait for operands
+          if (pl.bmode != BMODE_TMA) fence_proxy_async();        // cp.async (generic proxy) writes -> async proxy
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + buf * (pl.MT * pl.acc_cols);
-          const uint32_t idesc = umma_idesc_f16(s.umma_n, pl.bmode == BMODE_KROWS);
-          for (int ch = 0; ch < s.nchunks; ++ch) {
-            const bool bias_step = s.has_bias && ch == s.nchunks - 1;
-            const int n16 = bias_step ? 1 : min(4, s.nk16 - (ch % s.cpt) * 4);
-            mbar_wait(&T.full[stage], phase);
-            KP_LAP(2);                                           // wait for operands
-            fence_proxy_async();
-            tc_fence_after();
-            const uint32_t As = smem_base + stage * pl.stage_bytes;
-            const uint32_t Bs = As + pl.b_off;
-            const uint64_t bd = pl.bmode == BMODE_KROWS ? umma_desc(Bs, 8192, 1024) : umma_desc(Bs, 16, 1024);
-            const uint64_t bstep = pl.bmode == BMODE_KROWS ? 128 : 2;
-            for (int m = 0; m < s.mt_cnt; ++m) {
-              const uint64_t ad = umma_desc(As + m * A_TILE_BYTES, 16, 1024);
-              for (int k = 0; k < n16; ++k)
-                umma_f16(d_tmem + m * pl.acc_cols, ad + 2 * k, bd + bstep * k, idesc, (ch | k) ? 1u : 0u);
-            }
-            umma_commit(&T.empty[stage]);                        // frees the stage when these MMAs retire
-            if (++stage == pl.stages) { stage = 0; phase ^= 1; }
-            KP_LAP(3);                                           // issue
+          KP_LAP(4);                                             // fences
+          const uint32_t As = smem_base + stage * pl.stage_bytes;
+          const uint32_t Bs = As + pl.b_off;
+          const uint64_t bd = pl.bmode == BMODE_KROWS ? umma_desc(Bs, 8192, 1024) : umma_desc(Bs, 16, 1024);
+          const uint64_t bstep = pl.bmode == BMODE_KROWS ? 128 : 2;
+          for (int m = 0; m < s.mt_cnt; ++m) {
+            const uint64_t ad = umma_desc(As + m * A_TILE_BYTES, 16, 1024);
+            for (int k = 0; k < n16; ++k)
+              umma_f16(d_tmem + m * pl.acc_cols, ad + 2 * k, bd + bstep * k, idesc, (ch | k) ? 1u : 0u);
           }
-          if (s.nchunks > 0) umma_commit(&T.tfull[buf]);
-          else mbar_arrive(&T.tfull[buf]);                       // no active input channel: accumulator unused
-          if (++buf == pl.nbuf) { buf = 0; bphase ^= 1; }
+          KP_LAP(3);                                             // issue
+          umma_commit(&T.empty[stage]);                          // frees the stage when these MMAs retire
+          if (++stage == pl.stages) { stage = 0; phase ^= 1; }
+          KP_LAP(5);                                             // commit
         }
+        if (s.nchunks > 0) umma_commit(&T.tfull[buf]);
+        else mbar_arrive(&T.tfull[buf]);                         // no active input channel: accumulator unused
+        if (++buf == pl.nbuf) { buf = 0; bphase ^= 1; }
       }
       KP_FLUSH(1);
     }
@@ -306,85 +373,38 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
       const int ac = pt & 7, ar0 = pt >> 3;                      // ROWS: 16-byte chunk, first row (rows ar0 + 24 i)
       int stage = 0;
       uint32_t phase = 0;
+      int last_b = -1, last_mg = -1;
       KP_DECL;
-      for (int t = blockIdx.x; t < pl.total_items; t += gridDim.x) {
-        for (int nti = 0; nti < pl.NTI; ++nti) {
-          Sub s;
-          if (!decode_sub(a, pl, t, nti, s)) continue;
-          KP_LAP(0);                                             // decode
-          const int cpr = s.umma_n >> 3;                         // 16-byte chunks per k-row (KROWS)
-          int cpr2 = 2;
-          while (cpr2 < cpr) cpr2 <<= 1;                         // lanes per k-row (power of two <= 32)
-          const int rows_per_pass = 32 / cpr2 * GATHER_WARPS;
-          const int kr0 = pw * (32 / cpr2) + lane / cpr2, kc = lane % cpr2;
-          const bool kc_ok = kc < cpr && s.n0 + kc * 8 < a.C_out;
-          const uint32_t kdst0 = (uint32_t)((kc >> 3) * 8192 + ((kc & 7) << 4));   // n-block + chunk (pre-swizzle)
-          int browr[11];
-          named_bar_sync(1, GATHER_THREADS);                     // previous sub-item's table reads are done
-          if (pl.bmode == BMODE_ROWS) {
+      while (walker_next(a, pl, T, wk, s)) {
+        KP_LAP(0);                                               // decode
+        const int cpr = s.umma_n >> 3;                           // 16-byte chunks per k-row (KROWS)
+        int cpr2 = 2;
+        while (cpr2 < cpr) cpr2 <<= 1;                           // lanes per k-row (power of two <= 32)
+        const int rows_per_pass = 32 / cpr2 * GATHER_WARPS;
+        const int kr0 = pw * (32 / cpr2) + lane / cpr2, kc = lane % cpr2;
+        const bool kc_ok = kc < cpr && s.n0 + kc * 8 < a.C_out;
+        const uint32_t kdst0 = (uint32_t)((kc >> 3) * 8192 + ((kc & 7) << 4));   // n-block + chunk (pre-swizzle)
+        int browr[11];
+        if (pl.bmode == BMODE_ROWS) {
 #pragma unroll
-            for (int i = 0; i < 11; ++i) {
-              const int row = ar0 + 24 * i, jj = s.n0 + row;
-              browr[i] = (row < s.umma_n && jj < s.Nc)
-                             ? (a.n_idx ? __ldg(a.n_idx + (size_t)s.b * a.n_ld + jj / a.n_gran) * a.n_gran + jj % a.n_gran : jj) * taps * a.C_in
-                             : -1;
-            }
-          } else {
+          for (int i = 0; i < 11; ++i) {
+            const int row = ar0 + 24 * i, jj = s.n0 + row;
+            browr[i] = (row < s.umma_n && jj < s.Nc)
+                           ? (__ldg(a.n_idx + (size_t)s.b * a.n_ld + jj / a.n_gran) * a.n_gran + jj % a.n_gran) * taps * a.C_in
+                           : -1;
+          }
+        } else if (s.b != last_b || (s.has_bias && s.mg != last_mg)) {
+          // per-sample channel table / per-m-group tap-validity sets: rebuilt only when they change.  Every cp.async
+          // that read the old tables was issued before these barriers (program order within each gather thread).
+          named_bar_sync(1, GATHER_THREADS);
+          if (s.b != last_b)
             for (int e = pt; e < s.Kc; e += GATHER_THREADS) {
               const int q = e / a.k_gran;
               T.kch[e] = __ldg(a.k_idx + (size_t)s.b * a.k_ld + q) * a.k_gran + (e - q * a.k_gran);
             }
-          }
-          named_bar_sync(1, GATHER_THREADS);
-          KP_LAP(1);                                             // index tables + barriers
-          for (int tap = 0; tap < taps; ++tap) {
-            const int tapk = tap * a.C_in;
-            for (int kq = 0; kq < s.cpt; ++kq) {
-              const int k0 = kq * 64;
-              const int n16 = min(4, s.nk16 - kq * 4);
-              mbar_wait(&T.empty[stage], phase ^ 1);
-              KP_LAP(2);                                         // wait for a free stage
-              const uint32_t Bs = smem_base + stage * pl.stage_bytes + pl.b_off;
-              if (pl.bmode == BMODE_ROWS) {
-                if (ac < 2 * n16) {
-                  const int k = k0 + ac * 8;
-                  const bool kok = k < a.C_in;
-                  const __half* wk = a.w + tapk + k;
-#pragma unroll
-                  for (int i = 0; i < 11; ++i) {
-                    const int row = ar0 + 24 * i;
-                    if (row < s.umma_n) {
-                      const bool ok = kok && browr[i] >= 0;
-                      cp_async_16(Bs + sw128_off(row, ac), ok ? wk + browr[i] : a.w, ok ? 16u : 0u);
-                    }
-                  }
-                }
-              } else if (kc < cpr) {
-                const int nrows = 16 * n16;
-                const __half* wn = a.wt + s.n0 + kc * 8;
-                for (int kk = kr0; kk < nrows; kk += rows_per_pass) {
-                  const int e = k0 + kk;
-                  const bool ok = kc_ok && e < s.Kc;
-                  int rk = 0;
-                  if (ok) rk = T.kch[e];
-                  const uint32_t dst = Bs + (kdst0 ^ (uint32_t)((kk & 7) << 4)) + (kk >> 3) * 1024 + (kk & 7) * 128;
-                  cp_async_16(dst, ok ? wn + (size_t)(tapk + rk) * a.C_out : a.w, ok ? 16u : 0u);
-                }
-              }
-              cp_async_arrive(&T.full[stage]);
-              if (++stage == pl.stages) { stage = 0; phase ^= 1; }
-              KP_LAP(3);                                         // issue
-            }
-          }
-          if (s.has_bias) {
-            // one more K=16 step: A' = tap-validity indicator of each pixel, B' = this sample's H1 constants
-            // T[b, tap, o] (zero rows for tap >= taps): adds sum_{valid taps} T[b,tap,o] to the accumulator
-            mbar_wait(&T.empty[stage], phase ^ 1);
-            KP_LAP(2);
-            const uint32_t As = smem_base + stage * pl.stage_bytes;
-            const uint32_t Bs = As + pl.b_off;
-            for (int i = pt; i < s.mt_cnt * BM * 2; i += GATHER_THREADS) {
-              const int m = i / (BM * 2), rr = (i >> 1) & (BM - 1), c = i & 1;
+          if (s.has_bias && s.mg != last_mg)
+            for (int i = pt; i < s.mt_cnt * BM; i += GATHER_THREADS) {
+              const int m = i / BM, rr = i & (BM - 1);
               int m0, rows;
               tile_rows(a, pl, s.mt0 + m, m0, rows);
               int vm = 0;
@@ -396,20 +416,74 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
                   if (iy >= 0 && iy < a.H_in && ix >= 0 && ix < a.W_in) vm |= 1 << tp;
                 }
               }
-              cp_async_16(As + m * A_TILE_BYTES + sw128_off(rr, c), g_vtab4 + vm * 16 + c * 8, 16u);
+              T.vmask[m][rr] = (unsigned short)vm;
             }
-            if (kc < cpr) {
-              for (int kk = kr0; kk < 16; kk += rows_per_pass) {
-                const bool ok = kc_ok && kk < taps;
+          named_bar_sync(1, GATHER_THREADS);
+          last_b = s.b;
+          last_mg = s.mg;
+        }
+        KP_LAP(1);                                               // index tables + barriers
+        for (int tap = 0; tap < taps; ++tap) {
+          const int tapk = tap * a.C_in;
+          for (int kq = 0; kq < s.cpt; ++kq) {
+            const int k0 = kq * 64;
+            const int n16 = min(4, s.nk16 - kq * 4);
+            mbar_wait(&T.empty[stage], phase ^ 1);
+            KP_LAP(2);                                           // wait for a free stage
+            const uint32_t Bs = smem_base + stage * pl.stage_bytes + pl.b_off;
+            if (pl.bmode == BMODE_ROWS) {
+              if (ac < 2 * n16) {
+                const int k = k0 + ac * 8;
+                const bool kok = k < a.C_in;
+                const __half* wk_ = a.w + tapk + k;
+#pragma unroll
+                for (int i = 0; i < 11; ++i) {
+                  const int row = ar0 + 24 * i;
+                  if (row < s.umma_n) {
+                    const bool ok = kok && browr[i] >= 0;
+                    cp_async_16(Bs + sw128_off(row, ac), ok ? wk_ + browr[i] : a.w, ok ? 16u : 0u);
+                  }
+                }
+              }
+            } else if (kc < cpr) {
+              const int nrows = 16 * n16;
+              const __half* wn = a.wt + s.n0 + kc * 8;
+              for (int kk = kr0; kk < nrows; kk += rows_per_pass) {
+                const int e = k0 + kk;
+                const bool ok = kc_ok && e < s.Kc;
+                int rk = 0;
+                if (ok) rk = T.kch[e];
                 const uint32_t dst = Bs + (kdst0 ^ (uint32_t)((kk & 7) << 4)) + (kk >> 3) * 1024 + (kk & 7) * 128;
-                cp_async_16(dst, ok ? a.bias_t + (size_t)s.b * a.bias_ld + (size_t)kk * a.C_out + s.n0 + kc * 8 : a.w,
-                            ok ? 16u : 0u);
+                cp_async_16(dst, ok ? wn + (size_t)(tapk + rk) * a.C_out : a.w, ok ? 16u : 0u);
               }
             }
             cp_async_arrive(&T.full[stage]);
             if (++stage == pl.stages) { stage = 0; phase ^= 1; }
-            KP_LAP(4);                                           // H1-constant step
+            KP_LAP(3);                                           // issue
           }
+        }
+        if (s.has_bias) {
+          // one more K=16 step: A' = tap-validity indicator of each pixel, B' = this sample's H1 constants
+          // T[b, tap, o] (zero rows for tap >= taps): adds sum_{valid taps} T[b,tap,o] to the accumulator
+          mbar_wait(&T.empty[stage], phase ^ 1);
+          KP_LAP(2);
+          const uint32_t As = smem_base + stage * pl.stage_bytes;
+          const uint32_t Bs = As + pl.b_off;
+          for (int i = pt; i < s.mt_cnt * BM * 2; i += GATHER_THREADS) {
+            const int m = i / (BM * 2), rr = (i >> 1) & (BM - 1), c = i & 1;
+            cp_async_16(As + m * A_TILE_BYTES + sw128_off(rr, c), g_vtab4 + (int)T.vmask[m][rr] * 16 + c * 8, 16u);
+          }
+          if (kc < cpr) {
+            for (int kk = kr0; kk < 16; kk += rows_per_pass) {
+              const bool ok = kc_ok && kk < taps;
+              const uint32_t dst = Bs + (kdst0 ^ (uint32_t)((kk & 7) << 4)) + (kk >> 3) * 1024 + (kk & 7) * 128;
+              cp_async_16(dst, ok ? a.bias_t + (size_t)s.b * a.bias_ld + (size_t)kk * a.C_out + s.n0 + kc * 8 : a.w,
+                          ok ? 16u : 0u);
+            }
+          }
+          cp_async_arrive(&T.full[stage]);
+          if (++stage == pl.stages) { stage = 0; phase ^= 1; }
+          KP_LAP(4);                                             // H1-constant step
         }
       }
       if (pt == 0) KP_FLUSH(2);
@@ -417,7 +491,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
     }
   } else {
     // =========================================================== epilogue
-    const int et = threadIdx.x;                                  // 0..255
+    const int et = threadIdx.x;                                  // 0..255 == tile column whose table entry this thread fills
     const int q = warp & 3, h = warp >> 2;                       // TMEM lane quadrant, column half
     const int row = q * 32 + lane;                               // accumulator row (TMEM lane) of this thread
     const bool elected = (warp == 4 * h) && lane == 0;           // issues this half's TMA copies
@@ -427,11 +501,12 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
     uint32_t bphase = 0;
     int task = 0;                                                // slab tasks done by this half
     Cursor cur;                                                  // residual prefetcher (elected thread)
-    cur.t = -1; cur.nti = 0; cur.mt = 0; cur.sl = 0; cur.have = 0;
+    walker_init(pl, cur.w);
+    cur.mt = 0; cur.sl = 0; cur.have = 0;
     int pf = 0;                                                  // slab tasks whose residual load has been issued
     if (pl.omode == OUT_SLAB && a.residual && elected) {
       for (; pf < pl.ring - 1; ++pf) {
-        if (!cursor_next(a, pl, cur, h)) break;
+        if (!cursor_next(a, pl, T, cur, h)) break;
         int m0, rows;
         tile_rows(a, pl, cur.s.mt0 + cur.mt, m0, rows);
         mbar_arrive_expect_tx(&T.rfull[h][pf % pl.ring], (uint32_t)pl.r_tx);
@@ -440,135 +515,49 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
       }
     }
     KP_DECL;
-    for (int t = blockIdx.x; t < pl.total_items; t += gridDim.x) {
-      for (int nti = 0; nti < pl.NTI; ++nti) {
-        Sub s;
-        if (!decode_sub(a, pl, t, nti, s)) continue;
-        KP_LAP(0);                                               // decode
-        named_bar_sync(2, EPI_THREADS);                          // previous sub-item's table reads are done
-        for (int c = et; c < min(round_up(s.umma_n, 64), BN_MAX); c += EPI_THREADS) {
-          const int jj = s.n0 + c;
-          int o = -1, pos = -1;
-          if (pl.omode == OUT_ROWS) {
-            // real channel jj: active iff its group is in the sample's ascending list; its rank is the compact position
-            if (c < s.n_valid) {
-              if (a.n_idx) {
-                const int grp = jj / a.n_gran, na = s.Nc / a.n_gran;
-                const int* lst = a.n_idx + (size_t)s.b * a.n_ld;
-                int lo = 0, hi = na;
-                while (lo < hi) {
-                  const int mid = (lo + hi) >> 1;
-                  if (__ldg(lst + mid) < grp) lo = mid + 1; else hi = mid;
-                }
-                if (lo < na && __ldg(lst + lo) == grp) { o = jj; pos = lo * a.n_gran + jj % a.n_gran; }
-              } else {
-                o = jj; pos = jj;
-              }
-            }
-          } else if (c < s.n_valid && jj < s.Nc) {
-            o = a.n_idx ? __ldg(a.n_idx + (size_t)s.b * a.n_ld + jj / a.n_gran) * a.n_gran + jj % a.n_gran : jj;
-          }
-          float sc = o >= 0 ? 1.f : 0.f, sh = 0.f;               // inactive / pad columns come out as exact zeros
-          if (o >= 0 && a.scale) { sc = __ldg(a.scale + o); sh = __ldg(a.shift + o); }
-          T.scale[c] = sc; T.shift[c] = sh; T.cpos[c] = pos;
-        }
-        named_bar_sync(2, EPI_THREADS);
-        KP_LAP(1);                                               // column tables + barriers
-        mbar_wait(&T.tfull[buf], bphase);
-        KP_LAP(2);                                               // wait for the accumulator
-        tc_fence_after();
-        const uint32_t tbase = tmem_base + buf * (pl.MT * pl.acc_cols) + ((uint32_t)(q * 32) << 16);
-        const bool have_acc = s.nchunks > 0;
+    // column tables: entry `et` of the NEXT sub-item is fetched into registers while the current one is processed
+    Sub nx;
+    bool more = walker_next(a, pl, T, wk, nx);
+    int par = 0;
+    if (more) {
+      float sc, sh;
+      int pos;
+      column_entry(a, pl, nx, et, sc, sh, pos);
+      T.scale[0][et] = sc; T.shift[0][et] = sh; T.cpos[0][et] = pos;
+    }
+    while (more) {
+      s = nx;
+      named_bar_sync(2, EPI_THREADS);        // tables[par] are complete; nobody still reads tables[par ^ 1]
+      more = walker_next(a, pl, T, wk, nx);
+      float nsc = 0.f, nsh = 0.f;
+      int npos = -1;
+      if (more) column_entry(a, pl, nx, et, nsc, nsh, npos);
+      KP_LAP(1);                                                 // decode + next table entry (loads in flight)
+      const float* t_scale = T.scale[par];
+      const float* t_shift = T.shift[par];
+      const int* t_cpos = T.cpos[par];
+      mbar_wait(&T.tfull[buf], bphase);
+      KP_LAP(2);                                                 // wait for the accumulator
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + buf * (pl.MT * pl.acc_cols) + ((uint32_t)(q * 32) << 16);
+      const bool have_acc = s.nchunks > 0;
 
-        for (int m = 0; m < s.mt_cnt; ++m) {
-          int m0, rows;
-          tile_rows(a, pl, s.mt0 + m, m0, rows);
-          if (pl.omode == OUT_SLAB) {
-            bool row_on = true;                                  // spatial / layer gate of this pixel (one mask group)
-            if (a.out_mask) row_on = row < rows && a.out_mask[(size_t)s.b * HWo + m0 + row] != 0;
-            for (int sl = h; sl * 64 < s.n_valid; sl += 2, ++task) {
-              const int slot = task % pl.ring;
-              unsigned char* slab = ring + slot * SLAB_BYTES;
-              unsigned char* srow = slab + row * 128;
-              if (a.residual) mbar_wait(&T.rfull[h][slot], (uint32_t)(task / pl.ring) & 1u);
-              KP_LAP(3);                                         // wait for the residual slab
+      for (int m = 0; m < s.mt_cnt; ++m) {
+        int m0, rows;
+        tile_rows(a, pl, s.mt0 + m, m0, rows);
+        if (pl.omode == OUT_SLAB) {
+          bool row_on = true;                                    // spatial / layer gate of this pixel (one mask group)
+          if (a.out_mask) row_on = row < rows && a.out_mask[(size_t)s.b * HWo + m0 + row] != 0;
+          for (int sl = h; sl * 64 < s.n_valid; sl += 2, ++task) {
+            const int slot = task % pl.ring;
+            unsigned char* slab = ring + slot * SLAB_BYTES;
+            unsigned char* srow = slab + row * 128;
+            if (a.residual) mbar_wait(&T.rfull[h][slot], (uint32_t)(task / pl.ring) & 1u);
+            KP_LAP(3);                                           // wait for the residual slab
 #pragma unroll
-              for (int p = 0; p < 2; ++p) {
-                const int c0 = sl * 64 + p * 32;
-                if (c0 >= s.umma_n) break;
-                float v[32];
-                if (have_acc) {
-                  tmem_ld32(tbase + m * pl.acc_cols + c0, v);
-                } else {
-#pragma unroll
-                  for (int e = 0; e < 32; ++e) v[e] = 0.f;
-                }
-#pragma unroll
-                for (int g4 = 0; g4 < 4; ++g4) {                 // 8 channels = one 16-byte chunk
-                  const float4 s0 = *reinterpret_cast<const float4*>(T.scale + c0 + g4 * 8);
-                  const float4 s1 = *reinterpret_cast<const float4*>(T.scale + c0 + g4 * 8 + 4);
-                  const float4 h0 = *reinterpret_cast<const float4*>(T.shift + c0 + g4 * 8);
-                  const float4 h1 = *reinterpret_cast<const float4*>(T.shift + c0 + g4 * 8 + 4);
-                  float* w = v + g4 * 8;
-                  w[0] = fmaf(w[0], s0.x, h0.x); w[1] = fmaf(w[1], s0.y, h0.y);
-                  w[2] = fmaf(w[2], s0.z, h0.z); w[3] = fmaf(w[3], s0.w, h0.w);
-                  w[4] = fmaf(w[4], s1.x, h1.x); w[5] = fmaf(w[5], s1.y, h1.y);
-                  w[6] = fmaf(w[6], s1.z, h1.z); w[7] = fmaf(w[7], s1.w, h1.w);
-                  if (!row_on) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) w[e] = 0.f;
-                  }
-                  uint4* cell = reinterpret_cast<uint4*>(srow + (((p * 4 + g4) ^ (row & 7)) << 4));
-                  if (a.residual) {
-                    const uint4 r4 = *cell;
-                    const __half2* rh = reinterpret_cast<const __half2*>(&r4);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                      const float2 f = __half22float2(rh[e]);
-                      w[2 * e] += f.x;
-                      w[2 * e + 1] += f.y;
-                    }
-                  }
-                  if (relu_all) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) w[e] = fmaxf(w[e], 0.f);
-                  }
-                  uint4 o4;
-                  __half2* oh = reinterpret_cast<__half2*>(&o4);
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(w[2 * e], w[2 * e + 1]);
-                  *cell = o4;
-                }
-              }
-              KP_LAP(4);                                         // TMEM -> registers -> slab
-              fence_proxy_async();                               // generic-proxy slab writes -> visible to the TMA store
-              if (elected && !a.residual) {                      // the NEXT task's slab must have left shared memory
-                if (pl.ring == 3) bulk_wait_read_n<1>(); else bulk_wait_read_n<0>();
-              }
-              named_bar_sync(3 + h, HALF_THREADS);
-              if (elected) {
-                tma_store_3d(&map_y, smem_u32(slab), s.n0 + sl * 64, m0, s.b);
-                bulk_commit();
-                if (a.residual) {
-                  // slab of task-1 is free once its store has been read out; refill it for task + ring - 1
-                  bulk_wait_read_n<1>();
-                  if (pf == task + pl.ring - 1 && cursor_next(a, pl, cur, h)) {
-                    int pm0, prow;
-                    tile_rows(a, pl, cur.s.mt0 + cur.mt, pm0, prow);
-                    const int ps = pf % pl.ring;
-                    mbar_arrive_expect_tx(&T.rfull[h][ps], (uint32_t)pl.r_tx);
-                    tma_load_3d(smem_u32(ring + ps * SLAB_BYTES), &map_r, &T.rfull[h][ps], cur.s.n0 + cur.sl * 64, pm0,
-                                cur.s.b);
-                    ++pf;
-                  }
-                }
-              }
-              KP_LAP(5);                                         // barrier + store + prefetch
-            }
-          } else {
-            // ---- OUT_ROWS: compact the active real channels of this pixel row into the staging row
-            unsigned char* srow = stg + (size_t)row * pl.stg_pitch;
-            for (int c0 = h * 32; c0 < s.n_valid; c0 += 64) {
+            for (int p = 0; p < 2; ++p) {
+              const int c0 = sl * 64 + p * 32;
+              if (c0 >= s.umma_n) break;
               float v[32];
               if (have_acc) {
                 tmem_ld32(tbase + m * pl.acc_cols + c0, v);
@@ -577,41 +566,119 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
                 for (int e = 0; e < 32; ++e) v[e] = 0.f;
               }
 #pragma unroll
+              for (int g4 = 0; g4 < 4; ++g4) {                   // 8 channels = one 16-byte chunk
+                const float4 s0 = *reinterpret_cast<const float4*>(t_scale + c0 + g4 * 8);
+                const float4 s1 = *reinterpret_cast<const float4*>(t_scale + c0 + g4 * 8 + 4);
+                const float4 h0 = *reinterpret_cast<const float4*>(t_shift + c0 + g4 * 8);
+                const float4 h1 = *reinterpret_cast<const float4*>(t_shift + c0 + g4 * 8 + 4);
+                float* w = v + g4 * 8;
+                w[0] = fmaf(w[0], s0.x, h0.x); w[1] = fmaf(w[1], s0.y, h0.y);
+                w[2] = fmaf(w[2], s0.z, h0.z); w[3] = fmaf(w[3], s0.w, h0.w);
+                w[4] = fmaf(w[4], s1.x, h1.x); w[5] = fmaf(w[5], s1.y, h1.y);
+                w[6] = fmaf(w[6], s1.z, h1.z); w[7] = fmaf(w[7], s1.w, h1.w);
+                if (!row_on) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) w[e] = 0.f;
+                }
+                uint4* cell = reinterpret_cast<uint4*>(srow + (((p * 4 + g4) ^ (row & 7)) << 4));
+                if (a.residual) {
+                  const uint4 r4 = *cell;
+                  const __half2* rh = reinterpret_cast<const __half2*>(&r4);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f = __half22float2(rh[e]);
+                    w[2 * e] += f.x;
+                    w[2 * e + 1] += f.y;
+                  }
+                }
+                uint4 o4;
+                __half2* oh = reinterpret_cast<__half2*>(&o4);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(w[2 * e], w[2 * e + 1]);
+                if (relu_all) {                                  // max(.,0) commutes with the rounding to fp16
+                  const __half2 z = __float2half2_rn(0.f);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) oh[e] = __hmax2(oh[e], z);
+                }
+                *cell = o4;
+              }
+            }
+            KP_LAP(4);                                           // TMEM -> registers -> slab
+            fence_proxy_async();                                 // generic-proxy slab writes -> visible to the TMA store
+            if (elected && !a.residual) {                        // the NEXT task's slab must have left shared memory
+              if (pl.ring == 3) bulk_wait_read_n<1>(); else bulk_wait_read_n<0>();
+            }
+            named_bar_sync(3 + h, HALF_THREADS);
+            if (elected) {
+              tma_store_3d(&map_y, smem_u32(slab), s.n0 + sl * 64, m0, s.b);
+              bulk_commit();
+              if (a.residual) {
+                // slab of task-1 is free once its store has been read out; refill it for task + ring - 1
+                bulk_wait_read_n<1>();
+                if (pf == task + pl.ring - 1 && cursor_next(a, pl, T, cur, h)) {
+                  int pm0, prow;
+                  tile_rows(a, pl, cur.s.mt0 + cur.mt, pm0, prow);
+                  const int ps = pf % pl.ring;
+                  mbar_arrive_expect_tx(&T.rfull[h][ps], (uint32_t)pl.r_tx);
+                  tma_load_3d(smem_u32(ring + ps * SLAB_BYTES), &map_r, &T.rfull[h][ps], cur.s.n0 + cur.sl * 64, pm0,
+                              cur.s.b);
+                  ++pf;
+                }
+              }
+            }
+            KP_LAP(5);                                           // barrier + store + prefetch
+          }
+        } else {
+          // ---- OUT_ROWS: compact the active real channels of this pixel row into the staging row
+          unsigned char* srow = stg + (size_t)row * pl.stg_pitch;
+          const bool row_ok = row < pl.stg_rows;
+          for (int c0 = h * 32; c0 < s.n_valid; c0 += 64) {
+            float v[32];
+            if (have_acc) {
+              tmem_ld32(tbase + m * pl.acc_cols + c0, v);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) v[e] = 0.f;
+            }
+            if (row_ok) {
+#pragma unroll
               for (int e = 0; e < 32; e += 2) {
-                const int pos = T.cpos[c0 + e];                  // channel pairs share a gate (even granularity)
+                const int pos = t_cpos[c0 + e];                  // channel pairs share a gate (even granularity)
                 if (pos >= 0) {
-                  float x0 = fmaf(v[e], T.scale[c0 + e], T.shift[c0 + e]);
-                  float x1 = fmaf(v[e + 1], T.scale[c0 + e + 1], T.shift[c0 + e + 1]);
+                  float x0 = fmaf(v[e], t_scale[c0 + e], t_shift[c0 + e]);
+                  float x1 = fmaf(v[e + 1], t_scale[c0 + e + 1], t_shift[c0 + e + 1]);
                   if (relu_all) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
                   const int wd = pos >> 1;
                   *reinterpret_cast<__half2*>(srow + (((wd & ~31) | ((wd ^ row) & 31)) << 2)) = __floats2half2_rn(x0, x1);
                 }
               }
             }
-            KP_LAP(4);
-            if (nti == pl.NTI - 1) {
-              // last n-tile of the row: zero pad [Nc, Nfill), then flush the tile's rows to y (coalesced words)
-              if (h == 0)
-                for (int j = s.Nc; j < s.Nfill; j += 2) {
-                  const int wd = j >> 1;
-                  *reinterpret_cast<__half2*>(srow + (((wd & ~31) | ((wd ^ row) & 31)) << 2)) = __floats2half2_rn(0.f, 0.f);
-                }
-              named_bar_sync(5, EPI_THREADS);
-              const int nw = s.Nfill >> 1;
-              for (int r = warp; r < rows; r += EPI_WARPS) {
-                const uint32_t* src = reinterpret_cast<const uint32_t*>(stg + (size_t)r * pl.stg_pitch);
-                uint32_t* dst = reinterpret_cast<uint32_t*>(a.y + ((size_t)s.b * HWo + m0 + r) * a.ldy);
-                for (int w = lane; w < nw; w += 32) dst[w] = src[(w & ~31) | ((w ^ r) & 31)];
+          }
+          KP_LAP(4);
+          if (s.nt == pl.NT - 1) {
+            // last n-tile of the row: zero pad [Nc, Nfill), then flush the tile's rows to y (coalesced words)
+            if (h == 0 && row_ok)
+              for (int j = s.Nc; j < s.Nfill; j += 2) {
+                const int wd = j >> 1;
+                *reinterpret_cast<__half2*>(srow + (((wd & ~31) | ((wd ^ row) & 31)) << 2)) = __floats2half2_rn(0.f, 0.f);
               }
-              named_bar_sync(5, EPI_THREADS);                    // staging may be overwritten by the next tile
-              KP_LAP(5);                                         // flush
+            named_bar_sync(5, EPI_THREADS);
+            const int nw = s.Nfill >> 1;
+            for (int r = warp; r < rows; r += EPI_WARPS) {
+              const uint32_t* src = reinterpret_cast<const uint32_t*>(stg + (size_t)r * pl.stg_pitch);
+              uint32_t* dst = reinterpret_cast<uint32_t*>(a.y + ((size_t)s.b * HWo + m0 + r) * a.ldy);
+              for (int w = lane; w < nw; w += 32) dst[w] = src[(w & ~31) | ((w ^ r) & 31)];
             }
+            named_bar_sync(5, EPI_THREADS);                      // staging may be overwritten by the next tile
+            KP_LAP(5);                                           // flush
           }
         }
-        tc_fence_before();
-        mbar_arrive(&T.tempty[buf]);                             // accumulators drained: the MMA warp may reuse them
-        if (++buf == pl.nbuf) { buf = 0; bphase ^= 1; }
       }
+      tc_fence_before();
+      mbar_arrive(&T.tempty[buf]);                               // accumulators drained: the MMA warp may reuse them
+      if (++buf == pl.nbuf) { buf = 0; bphase ^= 1; }
+      par ^= 1;
+      if (more) { T.scale[par][et] = nsc; T.shift[par][et] = nsh; T.cpos[par][et] = npos; }
     }
     if (pl.omode == OUT_SLAB) bulk_wait_all();
     KP_LAP(6);
@@ -741,7 +808,10 @@ int conv_forward_tma(const ConvArgs& a, cudaStream_t s) {
   pl.stage_bytes = pl.b_off + round_up(b_bytes, 1024);
   pl.ring = a.residual ? 3 : 2;
   pl.stg_pitch = round_up(round_up(nfill_max, 16) * 2, 128);
-  const int stg_bytes = pl.omode == OUT_SLAB ? 2 * pl.ring * SLAB_BYTES : BM * pl.stg_pitch;
+  pl.stg_rows = pl.rows_per_tile <= 64 ? 64 : BM;            // small images (7x7): half-height staging
+  if (HWo < pl.stg_rows) pl.stg_rows = round_up(HWo, 32);
+  pl.cnt_cached = a.B <= CNT_CACHE ? 1 : 0;
+  const int stg_bytes = pl.omode == OUT_SLAB ? 2 * pl.ring * SLAB_BYTES : pl.stg_rows * pl.stg_pitch;
   const int avail = SMEM_LIMIT - 1024 - (int)sizeof(Tables) - stg_bytes;
   pl.stages = avail / pl.stage_bytes;
   if (pl.stages > MAX_STAGES) pl.stages = MAX_STAGES;

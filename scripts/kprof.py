@@ -19,7 +19,7 @@ from laudnet_b200 import _engine, _lib, synth   # noqa: E402
 
 SITES = {
     "tma": ["decode", "wait_empty", "issue"],
-    "mma": ["decode", "wait_tempty", "wait_full", "issue"],
+    "mma": ["decode", "wait_tempty", "wait_full", "issue", "fences", "commit"],
     "gather": ["decode", "tables", "wait_empty", "issue", "h1step"],
     "epi0": ["decode", "tables", "wait_tfull", "wait_rfull", "compute", "store", "drain"],
     "epi1": ["decode", "tables", "wait_tfull", "wait_rfull", "compute", "store", "drain"],
