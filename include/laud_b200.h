@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define LAUD_ABI_VERSION 1
+#define LAUD_ABI_VERSION 2
 
 enum {
   LAUD_OK = 0,
@@ -180,6 +180,12 @@ typedef struct laud_conv_desc {
                                acc[p,o] += sum_{taps of p that fall inside the input} bias_t[b,tap,o].
                                Replaces pre_bias (mutually exclusive). */
   int32_t bias_ld;
+  const uint8_t* n_mask;    /* optional MASKED-DENSE execution of the channel gate (reference laud_resnet.py:116,124:
+                               conv -> x mask -> bn): u8 [B, C_out / n_mask_gran].  Every output channel is computed
+                               with weights shared by all samples (no gather); a channel whose gate is 0 is emitted as
+                               if its accumulator were 0, i.e. the BN constant shift[o] (then ReLU) - the same values
+                               the gathered path reproduces through the H1 constants.  Exclusive with n_idx / k_idx. */
+  int32_t n_mask_gran;
 } laud_conv_desc;
 
 int laud_conv_forward(const laud_conv_desc* desc /* host */, int impl, void* stream);

@@ -78,7 +78,7 @@ def run_conv(x, w, y, B, H_in, W_in, C_in, H_out, W_out, C_out, ksize, stride, p
              k_idx=None, k_cnt=None, k_gran=1, n_idx=None, n_cnt=None, n_gran=1,
              pre_bias=None, pre_bias_classes=0, pre_bias_ld=0, out_mask=None, mask_groups=1,
              sample_idx=None, sample_cnt=None, row_idx=None, row_cnt=None, n_pad_align=0,
-             impl=_lib.CONV_AUTO, tag="conv", w_t=None, bias_t=None, bias_ld=0) -> None:
+             impl=_lib.CONV_AUTO, tag="conv", w_t=None, bias_t=None, bias_ld=0, n_mask=None, n_mask_gran=1) -> None:
     """Fill a laud_conv_desc and enqueue laud_conv_forward on the current stream."""
     d = ConvDesc()
     d.x, d.ldx = ptr(x), ldx if ldx is not None else x.shape[-1]
@@ -102,6 +102,7 @@ def run_conv(x, w, y, B, H_in, W_in, C_in, H_out, W_out, C_out, ksize, stride, p
     d.gap_partial, d.gap_tiles = None, 0
     d.w_t = ptr(w_t)
     d.bias_t, d.bias_ld = ptr(bias_t), bias_ld
+    d.n_mask, d.n_mask_gran = ptr(n_mask), n_mask_gran
     prof = conv_profile.active
     if prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -189,6 +190,10 @@ class ResNetEngine:
         self.plans: List[BlockPlan] = []
         self.prepared_for: Optional[torch.device] = None
         self.impl = _lib.CONV_AUTO
+        # How a channel-gated block executes (both reproduce laud_resnet.py:115-126 exactly):
+        #   "sparse": gathered GEMMs over the active channels only + H1 constants (compact a1 / a2);
+        #   "dense" : masked-dense - weights shared by all samples, gated channels emitted as their BN constant.
+        self.channel_exec = os.environ.get("LAUD_CHANNEL_EXEC", "sparse")
         self._ws: Dict[tuple, dict] = {}
 
     # ------------------------------------------------------------------ prepare
@@ -316,6 +321,7 @@ class ResNetEngine:
         m3 = None
         wp = p.width + 16                       # channel pitch of the compact intermediates
         use_wt = False
+        dense_gate = False
         T, Tn = None, 0
         if p.use_c:
             from .utils import _ChannelGate
@@ -330,18 +336,20 @@ class ResNetEngine:
             else:
                 blk.masker_channel.gate_nhwc(x[:B * Hi * Hi * p.inplanes].view(B, Hi, Hi, p.inplanes), counts[0:1],
                                              out=gate, partial_ws=ws["partial"])
-            # H1 constants: 0/1 indicator of the masked channels -> one dense GEMM -> fold taps into border classes
-            use_wt = p.krows_ok and self.impl in (_lib.CONV_AUTO, _lib.CONV_UMMA)
-            inact = ws["inact"][:B * p.width].view(B, p.width)
-            Tn = 9 * p.width + p.outplanes
-            T = ws["T"][:B * Tn].view(B, Tn)
-            check(L.laud_gate_inactive(ptr(gate.mask), B, G, p.gran, ptr(inact), st), "laud_gate_inactive")
-            run_conv(inact, p.cw, T, 1, B, 1, p.width, B, 1, Tn, 1, 1, 0, ldx=p.width, ldy=Tn, impl=self.impl,
-                     tag=f"s{p.stage + 1}.h1gemm")
-            if not use_wt:      # fallback layouts: fold the taps into per-border-class pre-bias tables
-                check(L.laud_channel_consts_fold(ptr(T), B, p.width, p.outplanes, ptr(gate.idx), ptr(gate.cnt), G,
-                                                 p.gran, 1, ptr(ws["pb2"]), ptr(ws["pb3"]), st),
-                      "laud_channel_consts_fold")
+            dense_gate = self.channel_exec == "dense"
+            if not dense_gate:
+                # H1 constants: 0/1 indicator of the masked channels -> one dense GEMM -> fold taps into border classes
+                use_wt = p.krows_ok and self.impl in (_lib.CONV_AUTO, _lib.CONV_UMMA)
+                inact = ws["inact"][:B * p.width].view(B, p.width)
+                Tn = 9 * p.width + p.outplanes
+                T = ws["T"][:B * Tn].view(B, Tn)
+                check(L.laud_gate_inactive(ptr(gate.mask), B, G, p.gran, ptr(inact), st), "laud_gate_inactive")
+                run_conv(inact, p.cw, T, 1, B, 1, p.width, B, 1, Tn, 1, 1, 0, ldx=p.width, ldy=Tn, impl=self.impl,
+                         tag=f"s{p.stage + 1}.h1gemm")
+                if not use_wt:      # fallback layouts: fold the taps into per-border-class pre-bias tables
+                    check(L.laud_channel_consts_fold(ptr(T), B, p.width, p.outplanes, ptr(gate.idx), ptr(gate.cnt), G,
+                                                     p.gran, 1, ptr(ws["pb2"]), ptr(ws["pb3"]), st),
+                          "laud_channel_consts_fold")
         if p.use_s:
             g = p.g_spatial
             S = min(p.mask_size, Hi)
@@ -368,18 +376,21 @@ class ResNetEngine:
                 keep.mask_conv3, keep.mask_conv2, keep.mask_conv1 = m3.clone(), m2.clone(), m1.clone()
 
         a1, a2 = ws["a1"], ws["a2"]
-        ck = dict(k_idx=gate.idx, k_cnt=gate.cnt, k_gran=p.gran) if gate else {}
-        cn = dict(n_idx=gate.idx, n_cnt=gate.cnt, n_gran=p.gran, n_pad_align=16) if gate else {}
-        ld12 = wp if gate else p.width
+        sparse_gate = gate is not None and not dense_gate
+        ck = dict(k_idx=gate.idx, k_cnt=gate.cnt, k_gran=p.gran) if sparse_gate else {}
+        cn = dict(n_idx=gate.idx, n_cnt=gate.cnt, n_gran=p.gran, n_pad_align=16) if sparse_gate else {}
+        nm = dict(n_mask=gate.mask, n_mask_gran=p.gran) if dense_gate else {}
+        ld12 = wp if sparse_gate else p.width
         # conv1 1x1 (+ mask) + bn1 + relu      laud_resnet.py:115-118
         run_conv(x, p.w1, a1, B, Hi, Hi, p.inplanes, Hi, Hi, p.width, 1, 1, 0, ldx=p.inplanes, ldy=ld12,
-                 scale=p.s1, shift=p.t1, relu=_lib.RELU_ALL, impl=self.impl, tag=f"s{p.stage + 1}.conv1", **cn)
+                 scale=p.s1, shift=p.t1, relu=_lib.RELU_ALL, impl=self.impl, tag=f"s{p.stage + 1}.conv1", **cn, **nm)
         # conv2 3x3/stride (+ mask) + bn2 + relu     laud_resnet.py:123-126
         run_conv(a1, p.w2, a2, B, Hi, Hi, p.width, Ho, Ho, p.width, 3, p.stride, 1, ldx=ld12, ldy=ld12,
                  scale=p.s2, shift=p.t2, relu=_lib.RELU_ALL, impl=self.impl, tag=f"s{p.stage + 1}.conv2",
-                 pre_bias=ws["pb2"] if (gate and not use_wt) else None, pre_bias_classes=16 if (gate and not use_wt) else 0,
-                 pre_bias_ld=p.width if gate else 0, w_t=p.w2t if use_wt else None,
-                 bias_t=T if use_wt else None, bias_ld=Tn if use_wt else 0, **ck, **cn)
+                 pre_bias=ws["pb2"] if (sparse_gate and not use_wt) else None,
+                 pre_bias_classes=16 if (sparse_gate and not use_wt) else 0,
+                 pre_bias_ld=p.width if sparse_gate else 0, w_t=p.w2t if use_wt else None,
+                 bias_t=T if use_wt else None, bias_ld=Tn if use_wt else 0, **ck, **cn, **nm)
         # identity branch      laud_resnet.py:138-141
         if p.wd is not None:
             run_conv(x, p.wd, idbuf, B, Hi, Hi, p.inplanes, Ho, Ho, p.outplanes, 1, p.stride, 0, ldx=p.inplanes,
@@ -391,11 +402,11 @@ class ResNetEngine:
         # conv3 1x1 + bn3 (+ spatial mask) + identity + relu     laud_resnet.py:131-144
         run_conv(a2, p.w3, out, B, Ho, Ho, p.width, Ho, Ho, p.outplanes, 1, 1, 0, ldx=ld12, ldy=p.outplanes,
                  scale=p.s3, shift=p.t3, relu=_lib.RELU_ALL, residual=res, ldr=p.outplanes, impl=self.impl,
-                 tag=f"s{p.stage + 1}.conv3", pre_bias=ws["pb3"] if (gate and not use_wt) else None,
-                 pre_bias_classes=1 if (gate and not use_wt) else 0,
+                 tag=f"s{p.stage + 1}.conv3", pre_bias=ws["pb3"] if (sparse_gate and not use_wt) else None,
+                 pre_bias_classes=1 if (sparse_gate and not use_wt) else 0,
                  bias_t=T.view(-1)[9 * p.width:] if use_wt else None, bias_ld=Tn if use_wt else 0,
-                 pre_bias_ld=p.outplanes if gate else 0, out_mask=m3, mask_groups=p.g_spatial if m3 is not None else 1,
-                 w_t=p.w3t if (gate and use_wt) else None, **ck)
+                 pre_bias_ld=p.outplanes if sparse_gate else 0, out_mask=m3, mask_groups=p.g_spatial if m3 is not None else 1,
+                 w_t=p.w3t if (sparse_gate and use_wt) else None, **ck)
         if keep is not None:
             if gate is not None:
                 keep.channel_mask, keep.channel_idx, keep.channel_cnt = gate.mask.clone(), gate.idx.clone(), gate.cnt.clone()

@@ -45,6 +45,7 @@ class ConvDesc(C.Structure):
         ("gap_partial", _vp), ("gap_tiles", C.c_int32),
         ("w_t", _vp),
         ("bias_t", _vp), ("bias_ld", C.c_int32),
+        ("n_mask", _vp), ("n_mask_gran", C.c_int32),
     ]
 
 

@@ -77,6 +77,9 @@ extern "C" int laud_conv_forward(const laud_conv_desc* d, int impl, void* stream
     LAUD_REQUIRE(d->w_t && d->k_idx && !d->pre_bias && d->bias_ld % 8 == 0 && d->ksize * d->ksize <= 9 &&
                      (reinterpret_cast<uintptr_t>(d->bias_t) & 15) == 0,
                  "laud_conv_forward: bias_t needs the w_t path (k_idx + w_t), no pre_bias, bias_ld %% 8 == 0");
+  if (d->n_mask)
+    LAUD_REQUIRE(!d->n_idx && !d->k_idx && !d->pre_bias && d->n_mask_gran >= 1 && d->C_out % d->n_mask_gran == 0,
+                 "laud_conv_forward: n_mask (masked-dense gate) excludes n_idx / k_idx / pre_bias and needs C_out %% n_mask_gran == 0");
   if (d->w_t && d->k_idx)
     LAUD_REQUIRE(impl == LAUD_CONV_AUTO || impl == LAUD_CONV_UMMA,
                  "laud_conv_forward: w_t (K-row-gather path, real-channel pre_bias) is a tcgen05-path argument");
@@ -100,6 +103,7 @@ extern "C" int laud_conv_forward(const laud_conv_desc* d, int impl, void* stream
   a.gap_partial = d->gap_partial; a.gap_tiles = d->gap_tiles;
   a.wt = (const __half*)d->w_t;
   a.bias_t = (const __half*)d->bias_t; a.bias_ld = d->bias_ld;
+  a.n_mask = d->n_mask; a.n_mask_gran = d->n_mask_gran;
 
   cudaStream_t s = (cudaStream_t)stream;
   switch (impl) {

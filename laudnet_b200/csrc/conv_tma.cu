@@ -51,7 +51,7 @@ constexpr uint32_t TMEM_COLS = 512;
 constexpr int SMEM_LIMIT = 232448;
 
 enum { BMODE_TMA = 0, BMODE_ROWS = 1, BMODE_KROWS = 2 };
-enum { OUT_SLAB = 0, OUT_ROWS = 1 };
+enum { OUT_SLAB = 0, OUT_ROWS = 1, OUT_DIRECT = 2 };
 
 // Optional in-kernel lap timers (-DLAUD_KPROF, scripts/kprof.py): cycles each warp role spends per phase.
 #ifdef LAUD_KPROF
@@ -228,6 +228,7 @@ __device__ __forceinline__ void column_entry(const ConvArgs& a, const Plan& pl, 
   sc = o >= 0 ? 1.f : 0.f;                                       // inactive / pad columns come out as exact zeros
   sh = 0.f;
   if (o >= 0 && a.scale) { sc = __ldg(a.scale + o); sh = __ldg(a.shift + o); }
+  if (o >= 0 && a.n_mask && __ldg(a.n_mask + (size_t)s.b * (a.C_out / a.n_mask_gran) + o / a.n_mask_gran) == 0) sc = 0.f;   // mask before BN
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -238,7 +239,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* stg = smem + (size_t)pl.stages * pl.stage_bytes;       // slab rings / row staging (1024-aligned)
-  const int stg_bytes = pl.omode == OUT_SLAB ? 2 * pl.ring * SLAB_BYTES : pl.stg_rows * pl.stg_pitch;
+  const int stg_bytes = pl.omode == OUT_SLAB ? 2 * pl.ring * SLAB_BYTES : (pl.omode == OUT_ROWS ? pl.stg_rows * pl.stg_pitch : 0);
   Tables& T = *reinterpret_cast<Tables*>(stg + stg_bytes);
   const uint32_t smem_base = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -628,6 +629,53 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
             }
             KP_LAP(5);                                           // barrier + store + prefetch
           }
+        } else if (pl.omode == OUT_DIRECT) {
+          // ---- OUT_DIRECT: long-K layers whose epilogue is a small share of the item: registers -> global,
+          //      16 bytes per store, no staging (all shared memory goes to the operand pipeline)
+          const bool valid = row < rows;
+          bool row_on = true;
+          if (a.out_mask) row_on = valid && a.out_mask[(size_t)s.b * HWo + m0 + row] != 0;
+          __half* yrow = a.y + ((size_t)s.b * HWo + m0 + row) * a.ldy + s.n0;
+          for (int c0 = h * 32; c0 < s.n_valid; c0 += 64) {
+            float v[32];
+            if (have_acc) {
+              tmem_ld32(tbase + m * pl.acc_cols + c0, v);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) v[e] = 0.f;
+            }
+            if (valid) {
+#pragma unroll
+              for (int g4 = 0; g4 < 4; ++g4) {
+                if (c0 + g4 * 8 < s.n_valid) {
+                  const float4 s0 = *reinterpret_cast<const float4*>(t_scale + c0 + g4 * 8);
+                  const float4 s1 = *reinterpret_cast<const float4*>(t_scale + c0 + g4 * 8 + 4);
+                  const float4 h0 = *reinterpret_cast<const float4*>(t_shift + c0 + g4 * 8);
+                  const float4 h1 = *reinterpret_cast<const float4*>(t_shift + c0 + g4 * 8 + 4);
+                  float* w = v + g4 * 8;
+                  w[0] = fmaf(w[0], s0.x, h0.x); w[1] = fmaf(w[1], s0.y, h0.y);
+                  w[2] = fmaf(w[2], s0.z, h0.z); w[3] = fmaf(w[3], s0.w, h0.w);
+                  w[4] = fmaf(w[4], s1.x, h1.x); w[5] = fmaf(w[5], s1.y, h1.y);
+                  w[6] = fmaf(w[6], s1.z, h1.z); w[7] = fmaf(w[7], s1.w, h1.w);
+                  if (!row_on) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) w[e] = 0.f;
+                  }
+                  uint4 o4;
+                  __half2* oh = reinterpret_cast<__half2*>(&o4);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(w[2 * e], w[2 * e + 1]);
+                  if (relu_all) {
+                    const __half2 z = __float2half2_rn(0.f);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) oh[e] = __hmax2(oh[e], z);
+                  }
+                  *reinterpret_cast<uint4*>(yrow + c0 + g4 * 8) = o4;
+                }
+              }
+            }
+          }
+          KP_LAP(4);
         } else {
           // ---- OUT_ROWS: compact the active real channels of this pixel row into the staging row
           unsigned char* srow = stg + (size_t)row * pl.stg_pitch;
@@ -765,8 +813,10 @@ int conv_forward_tma(const ConvArgs& a, cudaStream_t s) {
   Plan pl{};
   const int HWo = a.H_out * a.W_out;
   const int taps = a.ksize * a.ksize;
+  const int taps_h = taps;
   pl.bmode = a.k_idx ? BMODE_KROWS : (a.n_idx ? BMODE_ROWS : BMODE_TMA);
-  pl.omode = (a.k_idx && a.n_idx) ? OUT_ROWS : OUT_SLAB;
+  const long long ktotal = (long long)taps_h * a.C_in;
+  pl.omode = (a.k_idx && a.n_idx) ? OUT_ROWS : ((!a.residual && ktotal >= 512) ? OUT_DIRECT : OUT_SLAB);
   if (a.ksize == 3) {
     pl.R = BM / a.W_out;
     if (pl.R > a.H_out) pl.R = a.H_out;
@@ -789,7 +839,9 @@ int conv_forward_tma(const ConvArgs& a, cudaStream_t s) {
     pl.NTI = pl.NT;
     if (pl.NTI > 1) pl.MT = 1;                 // one staging tile: all n-tiles of ONE m-tile before the flush
   } else {
-    pl.BN = span <= 64 ? 64 : 128;
+    // wide tiles halve the re-reads of the activations when the reduction is long enough to hide a
+    // non-overlapped epilogue (BN = 256 with two m-tiles fills TMEM: one accumulator buffer)
+    pl.BN = span <= 64 ? 64 : ((span > 128 && pl.omode == OUT_DIRECT) ? 256 : 128);
     pl.NT = (span + pl.BN - 1) / pl.BN;
     pl.NTI = 1;
   }
@@ -811,7 +863,7 @@ int conv_forward_tma(const ConvArgs& a, cudaStream_t s) {
   pl.stg_rows = pl.rows_per_tile <= 64 ? 64 : BM;            // small images (7x7): half-height staging
   if (HWo < pl.stg_rows) pl.stg_rows = round_up(HWo, 32);
   pl.cnt_cached = a.B <= CNT_CACHE ? 1 : 0;
-  const int stg_bytes = pl.omode == OUT_SLAB ? 2 * pl.ring * SLAB_BYTES : pl.stg_rows * pl.stg_pitch;
+  const int stg_bytes = pl.omode == OUT_SLAB ? 2 * pl.ring * SLAB_BYTES : (pl.omode == OUT_ROWS ? pl.stg_rows * pl.stg_pitch : 0);
   const int avail = SMEM_LIMIT - 1024 - (int)sizeof(Tables) - stg_bytes;
   pl.stages = avail / pl.stage_bytes;
   if (pl.stages > MAX_STAGES) pl.stages = MAX_STAGES;

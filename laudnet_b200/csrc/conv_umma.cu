@@ -409,6 +409,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_umma_kernel(const __grid_
         }
         float sc = o >= 0 ? 1.f : 0.f, sh = 0.f;      // inactive / pad columns come out as exact zeros
         if (o >= 0 && a.scale) { sc = __ldg(a.scale + o); sh = __ldg(a.shift + o); }
+        if (o >= 0 && a.n_mask && a.n_mask[(size_t)it.b * (a.C_out / a.n_mask_gran) + o / a.n_mask_gran] == 0) sc = 0.f;
         T.ochan[c] = o; T.cpos[c] = o >= 0 ? pos : -1; T.scale[c] = sc; T.shift[c] = sh;
       }
       const RowPos p = row_pos(a, it, et, HWo);

@@ -78,6 +78,7 @@ struct ConvArgs {
   float* gap_partial; int gap_tiles;
   const __half* wt;
   const __half* bias_t; int bias_ld;
+  const uint8_t* n_mask; int n_mask_gran;
 };
 
 int conv_forward_naive(const ConvArgs& a, cudaStream_t s);
@@ -97,6 +98,7 @@ __device__ __forceinline__ float conv_epilogue(const ConvArgs& a, float acc, int
       cls = border_class(oy, a.stride, a.pad, a.H_in) * 4 + border_class(ox, a.stride, a.pad, a.W_in);
     v += a.pre_bias[((size_t)b * a.pre_bias_classes + cls) * a.pre_bias_ld + j];
   }
+  if (a.n_mask && a.n_mask[(size_t)b * (a.C_out / a.n_mask_gran) + o / a.n_mask_gran] == 0) v = 0.0f;   // mask before BN
   if (a.scale) v = v * a.scale[o] + a.shift[o];
   uint8_t gate = 1;
   const size_t pix = (size_t)oy * a.W_out + ox;

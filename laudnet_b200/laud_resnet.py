@@ -124,6 +124,7 @@ class _SoloEngine(ResNetEngine):
     def __init__(self, blk: Bottleneck):
         self.model = None
         self.impl = _lib.CONV_AUTO
+        self.channel_exec = "sparse"
         self._ws = {}
         dev = blk.conv1.weight.device
         p = BlockPlan(index=0, stage=0, inplanes=blk.conv1.weight.shape[1], width=blk.conv1.weight.shape[0],

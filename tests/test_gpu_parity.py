@@ -402,17 +402,22 @@ def test_stem_vs_oracle(cuda_lib, B, size, C0):
 
 
 # --------------------------------------------------------------------------- blocks, teacher-forced
+@pytest.mark.parametrize("channel_exec", ["sparse", "dense"])
 @pytest.mark.parametrize("name", list(CASES))
-def test_blocks_teacher_forced(cuda_lib, name):
+def test_blocks_teacher_forced(cuda_lib, name, channel_exec):
     """Every bottleneck of the golden networks, fed the ORACLE's block input
     (rounded to fp16) and the ORACLE's gating masks: activations within ACT_TOL."""
     cfg, sd, x, z = load_case(name)
+    if channel_exec == "dense" and not any(m in ("channel", "both") for m in cfg.dyn_mode):
+        pytest.skip("no channel gate in this configuration")
     model = _model(cfg, sd)
     geoms = O.resnet_geometry(cfg)
     blocks = [b for s in range(4) for b in getattr(model, f"layer{s + 1}")]
     with torch.no_grad():
         feat, _ = O.stem_forward(x, sd)
         for g, blk in zip(geoms, blocks):
+            blk._plan()
+            blk._solo_engine.channel_exec = channel_exec
             xin = feat.half().float()
             tr = O.BlockTrace()
             out_o = O.bottleneck_forward(xin, sd, g, tr)
@@ -451,10 +456,15 @@ def test_layer_skip_leaves_skipped_samples_bit_exact(cuda_lib):
 
 
 # --------------------------------------------------------------------------- whole networks vs the reference's golden outputs
+@pytest.mark.parametrize("channel_exec", ["sparse", "dense"])
 @pytest.mark.parametrize("name", list(CASES))
-def test_network_free_running_vs_golden(cuda_lib, name):
+def test_network_free_running_vs_golden(cuda_lib, name, channel_exec):
+    """Both executions of the channel gate (gathered GEMMs + H1 constants / masked-dense) against the reference."""
     cfg, sd, x, z = load_case(name)
+    if channel_exec == "dense" and not any(m in ("channel", "both") for m in cfg.dyn_mode):
+        pytest.skip("no channel gate in this configuration")
     model = _model(cfg, sd)
+    model._engine.channel_exec = channel_exec
     keep = []
     with torch.no_grad():
         logits, r3, r2, r1, rc, perc, flops = model(x.to(DEV), 1.0, keep=keep)
