@@ -288,7 +288,7 @@ def run_graft(args):
     conv_flops = work.conv_flops_per_image * B
     ach_gbs = conv_bytes / (conv_ms_step * 1e-3) / 1e9
     roof = {
-        "kernel": "laud::conv_umma_kernel (mask-conditioned gather-GEMM conv; all %d launches of one step)" % n_conv,
+        "kernel": "laud::conv_tma_kernel (mask-conditioned tcgen05 conv, TMA-staged; all %d launches of one step)" % n_conv,
         "bound": "hbm", "achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
         "frac": ach_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
         "launches_per_step": n_conv, "avg_launch_us": 1e3 * conv_ms_step / max(n_conv, 1),
@@ -324,7 +324,7 @@ def run_graft(args):
                        "replicated weights, one NCCL all-gather of logits per step" if world > 1 else "single GPU",
                        "l2": "inputs + activations per step (>2 GB) exceed the 126 MB L2; no explicit flush",
                        "weights": "seeded synthetic, BN stats + gate biases calibrated to channel density 0.6",
-                       "cuda_graph": True},
+                       "cuda_graph": True, "channel_exec": model._engine.channel_exec},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": graphed.launches * args.steps, "launches_per_step": graphed.launches,

@@ -193,7 +193,7 @@ class ResNetEngine:
         # How a channel-gated block executes (both reproduce laud_resnet.py:115-126 exactly):
         #   "sparse": gathered GEMMs over the active channels only + H1 constants (compact a1 / a2);
         #   "dense" : masked-dense - weights shared by all samples, gated channels emitted as their BN constant.
-        self.channel_exec = os.environ.get("LAUD_CHANNEL_EXEC", "sparse")
+        self.channel_exec = os.environ.get("LAUD_CHANNEL_EXEC", "dense")     # measured faster at every ResNet-101 stage (profiles/)
         self._ws: Dict[tuple, dict] = {}
 
     # ------------------------------------------------------------------ prepare

@@ -305,7 +305,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
             mbar_arrive_expect_tx(&T.full[stage], tx);
             for (int m = 0; m < s.mt_cnt; ++m) {
               const int mt = s.mt0 + m;
-              if (pl.R) tma_load_4d(As + m * A_TILE_BYTES, &map_a, &T.full[stage], k0, tx_ - a.pad, mt * pl.R + ty - a.pad, s.b);
+              if (pl.R) tma_load_4d(As + m * A_TILE_BYTES, &map_a, &T.full[stage], k0, tx_ - a.pad, mt * pl.R * a.stride + ty - a.pad, s.b);
               else tma_load_3d(As + m * A_TILE_BYTES, &map_a, &T.full[stage], k0, mt * BM, s.b);
             }
             if (pl.bmode == BMODE_TMA)
@@ -413,7 +413,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
                 const int p = m0 + rr;
                 const int oy = p / a.W_out, ox = p - oy * a.W_out;
                 for (int tp = 0; tp < taps; ++tp) {
-                  const int iy = oy - a.pad + tp / a.ksize, ix = ox - a.pad + tp % a.ksize;
+                  const int iy = oy * a.stride - a.pad + tp / a.ksize, ix = ox * a.stride - a.pad + tp % a.ksize;
                   if (iy >= 0 && iy < a.H_in && ix >= 0 && ix < a.W_in) vm |= 1 << tp;
                 }
               }
@@ -763,7 +763,7 @@ EncodeTiledFn encode_fn() {
 
 // fp16 tensor map, 128-byte swizzle, innermost dimension first; strides in ELEMENTS for dims 1..rank-1
 bool make_map(CUtensorMap* m, const void* base, int rank, const long long* dims, const long long* strides_elems,
-              const int* box) {
+              const int* box, const int* elem_strides = nullptr) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   cuuint64_t gdim[4], gstr[3];
@@ -771,7 +771,7 @@ bool make_map(CUtensorMap* m, const void* base, int rank, const long long* dims,
   for (int i = 0; i < rank; ++i) {
     gdim[i] = (cuuint64_t)dims[i];
     bx[i] = (cuuint32_t)box[i];
-    es[i] = 1;
+    es[i] = elem_strides ? (cuuint32_t)elem_strides[i] : 1;
     if (i > 0) gstr[i - 1] = (cuuint64_t)strides_elems[i - 1] * 2;
   }
   return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
@@ -786,14 +786,16 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 // Layouts the TMA kernel takes; everything else runs on the v3 kernel.
 bool conv_tma_supported(const ConvArgs& a) {
   if (!conv_umma_supported(a)) return false;
-  if (a.stride != 1) return false;
+  if (a.stride != 1 && a.stride != 2) return false;
   if (!((a.ksize == 1 && a.pad == 0) || (a.ksize == 3 && a.pad == 1))) return false;
+  if (a.stride == 2 && (a.H_in != 2 * a.H_out || a.W_in != 2 * a.W_out || 2 * a.W_out > 256)) return false;
   if (a.row_idx || a.pre_bias || a.relu_mode == LAUD_RELU_WHERE_GATE0) return false;
   if (a.out_mask && a.mask_groups != 1) return false;
   if (a.k_idx && !(a.wt && aligned16(a.wt))) return false;        // KUNITS layout
   if (a.k_idx && a.n_idx && (a.residual || a.out_mask || (a.n_gran & 1))) return false;
   if (a.n_idx && !a.k_idx && a.wt) return false;
-  if (a.ksize == 3 && (a.W_out > BM || a.H_in != a.H_out || a.W_in != a.W_out)) return false;
+  if ((a.ksize == 3 || a.stride == 2) && a.W_out > BM) return false;
+  if (a.ksize == 3 && a.stride == 1 && (a.H_in != a.H_out || a.W_in != a.W_out)) return false;
   if (a.k_idx && a.n_idx && round_up(a.C_out, 16) * 2 > 1024) return false;   // staging row
   if ((long long)a.B * a.H_out * a.W_out >= (1ll << 31)) return false;
   if (a.bias_t && !a.k_idx) return false;
@@ -817,7 +819,8 @@ int conv_forward_tma(const ConvArgs& a, cudaStream_t s) {
   pl.bmode = a.k_idx ? BMODE_KROWS : (a.n_idx ? BMODE_ROWS : BMODE_TMA);
   const long long ktotal = (long long)taps_h * a.C_in;
   pl.omode = (a.k_idx && a.n_idx) ? OUT_ROWS : ((!a.residual && ktotal >= 512) ? OUT_DIRECT : OUT_SLAB);
-  if (a.ksize == 3) {
+  const bool row_tiles = a.ksize == 3 || a.stride == 2;   // m-tiles of whole output rows: 4-d boxes (im2col / subsampling by TMA)
+  if (row_tiles) {
     pl.R = BM / a.W_out;
     if (pl.R > a.H_out) pl.R = a.H_out;
     // prefer an even split of the rows over one full and one nearly empty tile
@@ -881,11 +884,13 @@ int conv_forward_tma(const ConvArgs& a, cudaStream_t s) {
   memset(&map_r, 0, sizeof(map_r));
   bool ok = true;
   const long long cext_a = a.k_idx ? a.ldx : a.C_in;     // compact inputs may be read up to their pitch (zero padded by the producer)
-  if (a.ksize == 3) {
+  if (row_tiles) {
+    // traversal stride = conv stride: the box spans stride*W_out x stride*R input pixels and delivers W_out x R of them
     const long long dims[4] = {cext_a, a.W_in, a.H_in, a.B};
     const long long str[3] = {a.ldx, (long long)a.W_in * a.ldx, (long long)a.H_in * a.W_in * a.ldx};
-    const int box[4] = {64, a.W_out, pl.R, 1};
-    ok = ok && make_map(&map_a, a.x, 4, dims, str, box);
+    const int box[4] = {64, a.W_out * a.stride, pl.R * a.stride, 1};
+    const int es[4] = {1, a.stride, a.stride, 1};
+    ok = ok && make_map(&map_a, a.x, 4, dims, str, box, es);
   } else {
     const long long dims[3] = {cext_a, HWo, a.B};
     const long long str[2] = {a.ldx, (long long)HWo * a.ldx};

@@ -179,6 +179,146 @@ __global__ void __launch_bounds__(256) masker_decide_kernel(
 }
 
 // ---------------------------------------------------------------------------
+// Fused channel masker (the product path of laud_masker_channel_mlp): ONE launch, one CTA of 512
+// threads per sample: GAP (16-byte loads, 4 rows in flight per thread, fixed-order fp32 reduction)
+// -> MLP -> keep>=drop -> ordered compaction.  Replaces the gap_partial + masker_decide pair (two
+// launches, a [B,8,C] round trip through HBM and ~60 us of exposed latency per block).
+// dynamic smem: red[512*8] | p[C] | h[hidden] | l[2G] | flag[G] | wsum[64]
+// ---------------------------------------------------------------------------
+constexpr int MF_THREADS = 512;
+__global__ void __launch_bounds__(MF_THREADS) masker_channel_fused_kernel(
+    const __half* __restrict__ x, int HW, int C, int layers, const float* __restrict__ w1,
+    const float* __restrict__ b1, int hidden, const float* __restrict__ w2, const float* __restrict__ b2, int G,
+    float* __restrict__ pooled_out, float* __restrict__ logits_out, uint8_t* __restrict__ mask_out,
+    int* __restrict__ idx_out, int* __restrict__ cnt_out, int* __restrict__ total_out) {
+  extern __shared__ float sm[];
+  float* red = sm;
+  float* p = red + MF_THREADS * 8;
+  float* h = p + C;
+  float* l = h + (hidden > 0 ? hidden : 1);
+  int* flag = reinterpret_cast<int*>(l + 2 * G);
+  int* wsum = flag + G;
+  constexpr int NW = MF_THREADS / 32;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nvec = C >> 3;
+  const int vt = nvec < MF_THREADS ? nvec : MF_THREADS;      // vector lanes in use
+  const int rl = MF_THREADS / vt;                            // row lanes
+  const int v0 = tid % vt, r0 = tid / vt;
+  const __half* xb = x + (size_t)b * HW * C;
+  const float inv = 1.0f / (float)HW;
+
+  for (int vbase = 0; vbase < nvec; vbase += vt) {
+    const int v = vbase + v0;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    if (r0 < rl && v < nvec) {
+      const uint4* src = reinterpret_cast<const uint4*>(xb + v * 8);
+      const size_t pitch = (size_t)C >> 3;                   // row pitch in 16-byte units
+      int r = r0;
+      for (; r + 3 * rl < HW; r += 4 * rl) {                 // four independent loads in flight
+        uint4 q[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) q[u] = __ldg(src + (size_t)(r + u * rl) * pitch);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const __half2* hh = reinterpret_cast<const __half2*>(&q[u]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(hh[i]);
+            acc[2 * i] += f.x;
+            acc[2 * i + 1] += f.y;
+          }
+        }
+      }
+      for (; r < HW; r += rl) {
+        const uint4 q = __ldg(src + (size_t)r * pitch);
+        const __half2* hh = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __half22float2(hh[i]);
+          acc[2 * i] += f.x;
+          acc[2 * i + 1] += f.y;
+        }
+      }
+    }
+    __syncthreads();
+    if (r0 < rl && v < nvec) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) red[r0 * (vt * 8) + v0 * 8 + i] = acc[i];
+    }
+    __syncthreads();
+    for (int c = tid; c < vt * 8; c += MF_THREADS) {         // fixed-order reduction over the row lanes
+      if (vbase * 8 + c < C) {
+        float t = 0.f;
+        for (int r = 0; r < rl; ++r) t += red[r * (vt * 8) + c];
+        t *= inv;
+        p[vbase * 8 + c] = t;
+        if (pooled_out) pooled_out[(size_t)b * C + vbase * 8 + c] = t;
+      }
+    }
+  }
+  __syncthreads();
+
+  // first linear layer: one warp per output row, lanes stride the channels
+  const int rows1 = layers == 2 ? hidden : 2 * G;
+  float* dst1 = layers == 2 ? h : l;
+  for (int j = warp; j < rows1; j += NW) {
+    const float* wr = w1 + (size_t)j * C;
+    float t = 0.f;
+    for (int c = lane; c < C; c += 32) t = fmaf(__ldg(wr + c), p[c], t);
+    t = warp_sum(t);
+    if (lane == 0) {
+      t += b1[j];
+      dst1[j] = layers == 2 ? fmaxf(t, 0.f) : t;
+    }
+  }
+  __syncthreads();
+  if (layers == 2) {
+    for (int o = tid; o < 2 * G; o += MF_THREADS) {
+      const float* wr = w2 + (size_t)o * hidden;
+      float t = 0.f;
+      for (int j = 0; j < hidden; ++j) t = fmaf(__ldg(wr + j), h[j], t);
+      l[o] = t + b2[o];
+    }
+    __syncthreads();
+  }
+  for (int o = tid; o < 2 * G; o += MF_THREADS)
+    if (logits_out) logits_out[(size_t)b * 2 * G + o] = l[o];
+  for (int g = tid; g < G; g += MF_THREADS) {
+    const int f = l[g] >= l[G + g] ? 1 : 0;          // ties keep (utils.py:127)
+    flag[g] = f;
+    mask_out[(size_t)b * G + g] = (uint8_t)f;
+  }
+  __syncthreads();
+
+  // ordered compaction (active ids, then inactive ids): ballot + warp prefix over chunks of 512 groups
+  int base = 0, n_on = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int g0 = 0; g0 < G; g0 += MF_THREADS) {
+      const int g = g0 + tid;
+      const int f = g < G ? (flag[g] ? 1 - pass : pass) : 0;
+      const unsigned bal = __ballot_sync(0xffffffffu, f);
+      if (lane == 0) wsum[warp] = __popc(bal);
+      __syncthreads();
+      int off = base, tot = 0;
+      for (int w = 0; w < NW; ++w) {
+        if (w < warp) off += wsum[w];
+        tot += wsum[w];
+      }
+      if (f) idx_out[(size_t)b * G + off + __popc(bal & ((1u << lane) - 1))] = g;
+      base += tot;
+      __syncthreads();
+    }
+    if (pass == 0) n_on = base;
+  }
+  if (tid == 0) {
+    cnt_out[b] = n_on;
+    if (total_out) atomicAdd(total_out, n_on);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Spatial masker: one warp per (b, cell).  Pool the cell (adaptive_avg_pool2d
 // region: [floor(i*H/S), ceil((i+1)*H/S)) ), then the 2g-row 1x1 conv.
 // ---------------------------------------------------------------------------
@@ -386,10 +526,21 @@ extern "C" int laud_masker_channel_mlp(const void* x, int B, int HW, int C, int 
   LAUD_REQUIRE(x && partial_ws, "laud_masker_channel_mlp: null pointer");
   LAUD_REQUIRE(B > 0 && HW > 0 && C > 0 && C % 8 == 0, "laud_masker_channel_mlp: need C %% 8 == 0 (C=%d)", C);
   cudaStream_t s = (cudaStream_t)stream;
-  gap_partial_kernel<<<dim3(LAUD_GAP_SPLITS, B), 256, 0, s>>>((const __half*)x, HW, C, C, partial_ws);
-  if (int e = check_launch("gap_partial_kernel")) return e;
-  return launch_decide(partial_ws, nullptr, B, HW, C, layers, w1, b1, hidden, w2, b2, G, pooled_out,
-                       logits_out, mask_out, idx_out, cnt_out, total_out, s);
+  LAUD_REQUIRE(layers == 1 || layers == 2, "channel masker: layers must be 1 or 2 (got %d)", layers);
+  LAUD_REQUIRE(w1 && b1 && mask_out && idx_out && cnt_out, "channel masker: null pointer");
+  LAUD_REQUIRE(layers == 1 || (w2 && b2 && hidden > 0), "channel masker: 2-layer MLP needs w2,b2,hidden");
+  LAUD_REQUIRE(G > 0, "channel masker: G must be positive");
+  const size_t smem = sizeof(float) * MF_THREADS * 8 + decide_smem(C, layers == 2 ? hidden : 0, G);
+  LAUD_REQUIRE(smem <= 200 * 1024, "channel masker: C/G too large for shared memory");
+  static size_t fused_smem_set = 48 * 1024;
+  if (smem > fused_smem_set) {
+    LAUD_CUDA(cudaFuncSetAttribute(masker_channel_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fused_smem_set = smem;
+  }
+  masker_channel_fused_kernel<<<B, MF_THREADS, smem, s>>>((const __half*)x, HW, C, layers, w1, b1,
+                                                          layers == 2 ? hidden : 0, w2, b2, G, pooled_out, logits_out,
+                                                          mask_out, idx_out, cnt_out, total_out);
+  return check_launch("masker_channel_fused_kernel");
 }
 
 extern "C" int laud_masker_channel_from_pooled(const float* pooled, int B, int C, int layers, const float* w1,

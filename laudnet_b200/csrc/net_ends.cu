@@ -321,6 +321,54 @@ __global__ void __launch_bounds__(256) head_fc_kernel(const float* __restrict__ 
   }
 }
 
+// Head fc, tiled: CTA = 32 samples x 64 classes, 128 threads with a 4x4 register tile each; both
+// operands staged through shared memory in K-chunks of 32 (fp32 features, fp16 weights widened once).
+// The first kernel above re-read the weights once per 4 samples (64x) and paid one LDS per FMA.
+constexpr int HF_BS = 32, HF_BO = 64, HF_BK = 32;
+__global__ void __launch_bounds__(128) head_fc_tiled_kernel(const float* __restrict__ pooled, int B, int C,
+                                                            const __half* __restrict__ w,
+                                                            const float* __restrict__ bias, int n_cls,
+                                                            float* __restrict__ logits) {
+  __shared__ float sa[HF_BK][HF_BS + 4];      // [k][sample]
+  __shared__ float sb[HF_BK][HF_BO + 4];      // [k][class]
+  const int tid = threadIdx.x;
+  const int s0 = blockIdx.y * HF_BS, o0 = blockIdx.x * HF_BO;
+  const int ts = (tid & 7) * 4, to = (tid >> 3) * 4;          // this thread's 4 samples x 4 classes
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < C; k0 += HF_BK) {
+    for (int i = tid; i < HF_BS * HF_BK; i += 128) {
+      const int sidx = i / HF_BK, k = i % HF_BK;               // consecutive threads -> consecutive k: coalesced
+      sa[k][sidx] = (s0 + sidx < B && k0 + k < C) ? pooled[(size_t)(s0 + sidx) * C + k0 + k] : 0.f;
+    }
+    for (int i = tid; i < HF_BO * HF_BK; i += 128) {
+      const int o = i / HF_BK, k = i % HF_BK;
+      sb[k][o] = (o0 + o < n_cls && k0 + k < C) ? __half2float(w[(size_t)(o0 + o) * C + k0 + k]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < HF_BK; ++k) {
+      const float4 av = *reinterpret_cast<const float4*>(&sa[k][ts]);
+      const float4 bv = *reinterpret_cast<const float4*>(&sb[k][to]);
+      const float a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], b4[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (s0 + ts + i < B && o0 + to + j < n_cls)
+        logits[(size_t)(s0 + ts + i) * n_cls + o0 + to + j] = acc[i][j] + bias[o0 + to + j];
+}
+
 // ---------------------------------------------------------------------------
 // H1 constants (see laud_b200.h).  The per-sample sums over MASKED channels
 //   T2[b,tap,o] = sum_k inact[b,k] * relu(shift1[k]) * w2[o,tap,k]
@@ -478,15 +526,9 @@ extern "C" int laud_head_forward(const void* x, int B, int HW, int C, const void
   // pooled_ws: [B, LAUD_GAP_SPLITS + 1, C]: partial sums followed by the pooled features
   float* pooled = pooled_ws + (size_t)B * LAUD_GAP_SPLITS * C;
   if (int e = laud_global_avg_pool(x, B, HW, C, C, pooled_ws, pooled, stream)) return e;
-  const size_t smem = sizeof(float) * 4 * (size_t)C;
-  static size_t head_smem_set = 48 * 1024;
-  if (smem > head_smem_set) {
-    LAUD_CUDA(cudaFuncSetAttribute(head_fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    head_smem_set = smem;
-  }
-  dim3 grid((n_cls + 63) / 64, (B + 3) / 4);
-  head_fc_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(pooled, B, C, (const __half*)w, bias, n_cls, logits);
-  return check_launch("head_fc_kernel");
+  dim3 grid((n_cls + HF_BO - 1) / HF_BO, (B + HF_BS - 1) / HF_BS);
+  head_fc_tiled_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(pooled, B, C, (const __half*)w, bias, n_cls, logits);
+  return check_launch("head_fc_tiled_kernel");
 }
 
 extern "C" int laud_gate_inactive(const uint8_t* mask, int B, int G, int gran, void* inact_f16, void* stream) {

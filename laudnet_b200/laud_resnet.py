@@ -21,6 +21,8 @@ Training mode and CPU tensors raise `LaudError` - there is no fallback path.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -124,7 +126,7 @@ class _SoloEngine(ResNetEngine):
     def __init__(self, blk: Bottleneck):
         self.model = None
         self.impl = _lib.CONV_AUTO
-        self.channel_exec = "sparse"
+        self.channel_exec = os.environ.get("LAUD_CHANNEL_EXEC", "dense")
         self._ws = {}
         dev = blk.conv1.weight.device
         p = BlockPlan(index=0, stage=0, inplanes=blk.conv1.weight.shape[1], width=blk.conv1.weight.shape[0],
