@@ -83,6 +83,7 @@ struct Tables {
   int kcnt[CNT_CACHE], ncnt[CNT_CACHE];
   unsigned short vmask[2][BM];   // tap-validity bit sets of the pixels of the current m-group (H1-constant step)
   unsigned long long full[MAX_STAGES], empty[MAX_STAGES], tfull[4], tempty[4], rfull[2][MAX_RING];
+  unsigned long long afull[2], aempty[2];   // halo mode: ring of activation tiles (one per 64-channel chunk)
   uint32_t tmem_base;
 };
 
@@ -98,6 +99,10 @@ struct Plan {              // host-computed launch geometry
   int full_count;          // arrivals that complete a stage
   int a_tx, b_tx, r_tx;    // bytes one A-tile / B-tile / residual-slab TMA copy delivers
   int cnt_cached;          // 1: Tables::kcnt / ncnt hold k_cnt / n_cnt of every sample
+  // HALO mode (3x3, stride 1, shared weights): the activations of an m-group are staged ONCE per 64-channel chunk,
+  // with their zero-padded 1-pixel halo, as rows of a (W+2)-wide padded image; the nine taps are the same tile read
+  // at nine row offsets (UMMA descriptors with a base offset), so only the weights stream per tap.
+  int halo, Wp, a_slot_bytes, a_region_bytes, halo_bo;
 };
 
 struct Sub {               // one (sample, m-group, n-tile) unit of work
@@ -237,11 +242,12 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
                 const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_r) {
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  unsigned char* stg = smem + (size_t)pl.stages * pl.stage_bytes;       // slab rings / row staging (1024-aligned)
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
+  unsigned char* stg = smem + pl.a_region_bytes + (size_t)pl.stages * pl.stage_bytes;   // slab rings / row staging (1024-aligned)
   const int stg_bytes = pl.omode == OUT_SLAB ? 2 * pl.ring * SLAB_BYTES : (pl.omode == OUT_ROWS ? pl.stg_rows * pl.stg_pitch : 0);
   Tables& T = *reinterpret_cast<Tables*>(stg + stg_bytes);
-  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t a_base = smem_u32(smem);                           // halo mode: two activation slots in front of the stages
+  const uint32_t smem_base = a_base + pl.a_region_bytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int HWo = a.H_out * a.W_out;
   const int taps = a.ksize * a.ksize;
@@ -257,6 +263,10 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
     }
     for (int h = 0; h < 2; ++h)
       for (int i = 0; i < MAX_RING; ++i) mbar_init(&T.rfull[h][i], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&T.afull[i], 1);
+      mbar_init(&T.aempty[i], 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (pl.cnt_cached)                                              // one round trip for every per-sample count
@@ -292,6 +302,42 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
       int stage = 0;
       uint32_t phase = 0;
       KP_DECL;
+      if (pl.halo) {
+        // two streams issued by this one thread: activation tiles (one per sub-item and 64-channel chunk, kept one
+        // chunk ahead, also across sub-items) and weight tiles (one per chunk and tap)
+        Walker wa;
+        walker_init(pl, wa);
+        Sub sa;
+        bool a_more = walker_next(a, pl, T, wa, sa);
+        while (a_more && sa.cpt == 0) a_more = walker_next(a, pl, T, wa, sa);
+        int a_kq = 0, a_next = 0, g = 0;
+        while (walker_next(a, pl, T, wk, s)) {
+          for (int kq = 0; kq < s.cpt; ++kq, ++g) {
+            while (a_more && a_next <= g + 1) {
+              const int slot = a_next & 1;
+              mbar_wait(&T.aempty[slot], (uint32_t)((a_next >> 1) & 1) ^ 1u);
+              mbar_arrive_expect_tx(&T.afull[slot], (uint32_t)pl.a_tx);
+              tma_load_4d(a_base + slot * pl.a_slot_bytes, &map_a, &T.afull[slot], a_kq * 64, -1,
+                          (sa.mt0) * pl.R - 1, sa.b);
+              ++a_next;
+              if (++a_kq >= sa.cpt) {
+                a_kq = 0;
+                a_more = walker_next(a, pl, T, wa, sa);
+                while (a_more && sa.cpt == 0) a_more = walker_next(a, pl, T, wa, sa);
+              }
+            }
+            KP_LAP(0);
+            for (int tap = 0; tap < taps; ++tap) {
+              mbar_wait(&T.empty[stage], phase ^ 1);
+              KP_LAP(1);
+              mbar_arrive_expect_tx(&T.full[stage], (uint32_t)pl.b_tx);
+              tma_load_2d(smem_base + stage * pl.stage_bytes, &map_b, &T.full[stage], tap * a.C_in + kq * 64, s.n0);
+              if (++stage == pl.stages) { stage = 0; phase ^= 1; }
+              KP_LAP(2);
+            }
+          }
+        }
+      } else
       while (walker_next(a, pl, T, wk, s)) {
         KP_LAP(0);                                   // decode
         const uint32_t tx = (uint32_t)(s.mt_cnt * pl.a_tx + (pl.bmode == BMODE_TMA ? pl.b_tx : 0));
@@ -327,7 +373,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
   } else if (warp == MMA_WARP) {
     // =========================================================== MMA issuer
     if (lane == 0) {
-      int stage = 0, buf = 0;
+      int stage = 0, buf = 0, hg = 0;
       uint32_t phase = 0, bphase = 0;
       KP_DECL;
       while (walker_next(a, pl, T, wk, s)) {
@@ -337,6 +383,35 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * (pl.MT * pl.acc_cols);
         const uint32_t idesc = umma_idesc_f16(s.umma_n, pl.bmode == BMODE_KROWS);
+        if (pl.halo) {
+          for (int kq = 0; kq < s.cpt; ++kq, ++hg) {
+            const int aslot = hg & 1;
+            const int n16 = min(4, s.nk16 - kq * 4);
+            mbar_wait(&T.afull[aslot], (uint32_t)((hg >> 1) & 1));
+            KP_LAP(2);
+            tc_fence_after();
+            const uint32_t Aslot = a_base + aslot * pl.a_slot_bytes;
+            for (int tap = 0; tap < taps; ++tap) {
+              const int ty = tap / 3, tx_ = tap - ty * 3;
+              mbar_wait(&T.full[stage], phase);
+              KP_LAP(2);
+              tc_fence_after();
+              const uint64_t bd = umma_desc(smem_base + stage * pl.stage_bytes, 16, 1024);
+              for (int m = 0; m < s.mt_cnt; ++m) {
+                // tile m, tap (ty,tx): 128 consecutive rows of the padded image starting at row (m R + ty) Wp + tx
+                const uint32_t aaddr = Aslot + (uint32_t)(((m * pl.R + ty) * pl.Wp + tx_) * 128);
+                const uint64_t ad = umma_desc(aaddr, 16, 1024) | (pl.halo_bo ? ((uint64_t)((aaddr >> 7) & 7u) << 49) : 0ull);
+                for (int k = 0; k < n16; ++k)
+                  umma_f16(d_tmem + m * pl.acc_cols, ad + 2 * k, bd + 2 * k, idesc, (kq | tap | k) ? 1u : 0u);
+              }
+              KP_LAP(3);
+              umma_commit(&T.empty[stage]);
+              if (++stage == pl.stages) { stage = 0; phase ^= 1; }
+              KP_LAP(5);
+            }
+            umma_commit(&T.aempty[aslot]);                         // the activation slot is free once these MMAs retire
+          }
+        } else
         for (int ch = 0; ch < s.nchunks; ++ch) {
           const bool bias_step = s.has_bias && ch == s.nchunks - 1;
           const int n16 = bias_step ? 1 : min(4, s.nk16 - (ch % s.cpt) * 4);
@@ -534,9 +609,9 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
       int npos = -1;
       if (more) column_entry(a, pl, nx, et, nsc, nsh, npos);
       KP_LAP(1);                                                 // decode + next table entry (loads in flight)
-      const float* t_scale = T.scale[par];
-      const float* t_shift = T.shift[par];
-      const int* t_cpos = T.cpos[par];
+      const uint32_t t_scale = smem_u32(&T.scale[par][0]);       // shared-space addresses of this sub-item's tables
+      const uint32_t t_shift = smem_u32(&T.shift[par][0]);
+      const uint32_t t_cpos = smem_u32(&T.cpos[par][0]);
       mbar_wait(&T.tfull[buf], bphase);
       KP_LAP(2);                                                 // wait for the accumulator
       tc_fence_after();
@@ -546,14 +621,24 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
       for (int m = 0; m < s.mt_cnt; ++m) {
         int m0, rows;
         tile_rows(a, pl, s.mt0 + m, m0, rows);
+        // pixel of this accumulator row inside the tile (halo mode: rows are positions of the padded image)
+        int prow = row;
+        bool pvalid = row < rows;
+        if (pl.halo) {
+          const int oyl = row / pl.Wp, ox = row - oyl * pl.Wp;
+          prow = oyl * a.W_out + ox;
+          pvalid = ox < a.W_out && prow < rows;
+        }
         if (pl.omode == OUT_SLAB) {
           bool row_on = true;                                    // spatial / layer gate of this pixel (one mask group)
-          if (a.out_mask) row_on = row < rows && a.out_mask[(size_t)s.b * HWo + m0 + row] != 0;
+          if (a.out_mask) row_on = pvalid && a.out_mask[(size_t)s.b * HWo + m0 + prow] != 0;
           for (int sl = h; sl * 64 < s.n_valid; sl += 2, ++task) {
             const int slot = task % pl.ring;
             unsigned char* slab = ring + slot * SLAB_BYTES;
-            unsigned char* srow = slab + row * 128;
-            if (a.residual) mbar_wait(&T.rfull[h][slot], (uint32_t)(task / pl.ring) & 1u);
+            const uint32_t srow = smem_u32(slab) + (uint32_t)prow * 128u;
+            const uint32_t sw = (uint32_t)(prow & 7);
+            const bool has_res = a.residual != nullptr;
+            if (has_res) mbar_wait(&T.rfull[h][slot], (uint32_t)(task / pl.ring) & 1u);
             KP_LAP(3);                                           // wait for the residual slab
 #pragma unroll
             for (int p = 0; p < 2; ++p) {
@@ -566,42 +651,44 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
 #pragma unroll
                 for (int e = 0; e < 32; ++e) v[e] = 0.f;
               }
+              if (!(pl.halo && !pvalid)) {                       // (padding column of the padded image: not a pixel)
 #pragma unroll
-              for (int g4 = 0; g4 < 4; ++g4) {                   // 8 channels = one 16-byte chunk
-                const float4 s0 = *reinterpret_cast<const float4*>(t_scale + c0 + g4 * 8);
-                const float4 s1 = *reinterpret_cast<const float4*>(t_scale + c0 + g4 * 8 + 4);
-                const float4 h0 = *reinterpret_cast<const float4*>(t_shift + c0 + g4 * 8);
-                const float4 h1 = *reinterpret_cast<const float4*>(t_shift + c0 + g4 * 8 + 4);
-                float* w = v + g4 * 8;
-                w[0] = fmaf(w[0], s0.x, h0.x); w[1] = fmaf(w[1], s0.y, h0.y);
-                w[2] = fmaf(w[2], s0.z, h0.z); w[3] = fmaf(w[3], s0.w, h0.w);
-                w[4] = fmaf(w[4], s1.x, h1.x); w[5] = fmaf(w[5], s1.y, h1.y);
-                w[6] = fmaf(w[6], s1.z, h1.z); w[7] = fmaf(w[7], s1.w, h1.w);
-                if (!row_on) {
+                for (int g4 = 0; g4 < 4; ++g4) {                 // 8 channels = one 16-byte chunk
+                  const float4 s0 = lds_f4(t_scale + (uint32_t)(c0 + g4 * 8) * 4u);
+                  const float4 s1 = lds_f4(t_scale + (uint32_t)(c0 + g4 * 8 + 4) * 4u);
+                  const float4 h0 = lds_f4(t_shift + (uint32_t)(c0 + g4 * 8) * 4u);
+                  const float4 h1 = lds_f4(t_shift + (uint32_t)(c0 + g4 * 8 + 4) * 4u);
+                  float* w = v + g4 * 8;
+                  w[0] = fmaf(w[0], s0.x, h0.x); w[1] = fmaf(w[1], s0.y, h0.y);
+                  w[2] = fmaf(w[2], s0.z, h0.z); w[3] = fmaf(w[3], s0.w, h0.w);
+                  w[4] = fmaf(w[4], s1.x, h1.x); w[5] = fmaf(w[5], s1.y, h1.y);
+                  w[6] = fmaf(w[6], s1.z, h1.z); w[7] = fmaf(w[7], s1.w, h1.w);
+                  if (!row_on) {
 #pragma unroll
-                  for (int e = 0; e < 8; ++e) w[e] = 0.f;
-                }
-                uint4* cell = reinterpret_cast<uint4*>(srow + (((p * 4 + g4) ^ (row & 7)) << 4));
-                if (a.residual) {
-                  const uint4 r4 = *cell;
-                  const __half2* rh = reinterpret_cast<const __half2*>(&r4);
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const float2 f = __half22float2(rh[e]);
-                    w[2 * e] += f.x;
-                    w[2 * e + 1] += f.y;
+                    for (int e = 0; e < 8; ++e) w[e] = 0.f;
                   }
-                }
-                uint4 o4;
-                __half2* oh = reinterpret_cast<__half2*>(&o4);
+                  const uint32_t cell = srow + ((((uint32_t)(p * 4 + g4)) ^ sw) << 4);
+                  if (has_res) {
+                    const uint4 r4 = lds128(cell);
+                    const __half2* rh = reinterpret_cast<const __half2*>(&r4);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(w[2 * e], w[2 * e + 1]);
-                if (relu_all) {                                  // max(.,0) commutes with the rounding to fp16
-                  const __half2 z = __float2half2_rn(0.f);
+                    for (int e = 0; e < 4; ++e) {
+                      const float2 f = __half22float2(rh[e]);
+                      w[2 * e] += f.x;
+                      w[2 * e + 1] += f.y;
+                    }
+                  }
+                  uint4 o4;
+                  __half2* oh = reinterpret_cast<__half2*>(&o4);
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) oh[e] = __hmax2(oh[e], z);
+                  for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(w[2 * e], w[2 * e + 1]);
+                  if (relu_all) {                                // max(.,0) commutes with the rounding to fp16
+                    const __half2 z = __float2half2_rn(0.f);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) oh[e] = __hmax2(oh[e], z);
+                  }
+                  sts128(cell, o4);
                 }
-                *cell = o4;
               }
             }
             KP_LAP(4);                                           // TMEM -> registers -> slab
@@ -632,10 +719,10 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
         } else if (pl.omode == OUT_DIRECT) {
           // ---- OUT_DIRECT: long-K layers whose epilogue is a small share of the item: registers -> global,
           //      16 bytes per store, no staging (all shared memory goes to the operand pipeline)
-          const bool valid = row < rows;
+          const bool valid = pvalid;
           bool row_on = true;
-          if (a.out_mask) row_on = valid && a.out_mask[(size_t)s.b * HWo + m0 + row] != 0;
-          __half* yrow = a.y + ((size_t)s.b * HWo + m0 + row) * a.ldy + s.n0;
+          if (a.out_mask) row_on = valid && a.out_mask[(size_t)s.b * HWo + m0 + prow] != 0;
+          __half* yrow = a.y + ((size_t)s.b * HWo + m0 + prow) * a.ldy + s.n0;
           for (int c0 = h * 32; c0 < s.n_valid; c0 += 64) {
             float v[32];
             if (have_acc) {
@@ -648,10 +735,10 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
 #pragma unroll
               for (int g4 = 0; g4 < 4; ++g4) {
                 if (c0 + g4 * 8 < s.n_valid) {
-                  const float4 s0 = *reinterpret_cast<const float4*>(t_scale + c0 + g4 * 8);
-                  const float4 s1 = *reinterpret_cast<const float4*>(t_scale + c0 + g4 * 8 + 4);
-                  const float4 h0 = *reinterpret_cast<const float4*>(t_shift + c0 + g4 * 8);
-                  const float4 h1 = *reinterpret_cast<const float4*>(t_shift + c0 + g4 * 8 + 4);
+                  const float4 s0 = lds_f4(t_scale + (uint32_t)(c0 + g4 * 8) * 4u);
+                  const float4 s1 = lds_f4(t_scale + (uint32_t)(c0 + g4 * 8 + 4) * 4u);
+                  const float4 h0 = lds_f4(t_shift + (uint32_t)(c0 + g4 * 8) * 4u);
+                  const float4 h1 = lds_f4(t_shift + (uint32_t)(c0 + g4 * 8 + 4) * 4u);
                   float* w = v + g4 * 8;
                   w[0] = fmaf(w[0], s0.x, h0.x); w[1] = fmaf(w[1], s0.y, h0.y);
                   w[2] = fmaf(w[2], s0.z, h0.z); w[3] = fmaf(w[3], s0.w, h0.w);
@@ -678,7 +765,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
           KP_LAP(4);
         } else {
           // ---- OUT_ROWS: compact the active real channels of this pixel row into the staging row
-          unsigned char* srow = stg + (size_t)row * pl.stg_pitch;
+          const uint32_t srow = smem_u32(stg) + (uint32_t)row * (uint32_t)pl.stg_pitch;
           const bool row_ok = row < pl.stg_rows;
           for (int c0 = h * 32; c0 < s.n_valid; c0 += 64) {
             float v[32];
@@ -691,13 +778,14 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
             if (row_ok) {
 #pragma unroll
               for (int e = 0; e < 32; e += 2) {
-                const int pos = t_cpos[c0 + e];                  // channel pairs share a gate (even granularity)
+                const int pos = lds_i1(t_cpos + (uint32_t)(c0 + e) * 4u);   // channel pairs share a gate (even granularity)
                 if (pos >= 0) {
-                  float x0 = fmaf(v[e], t_scale[c0 + e], t_shift[c0 + e]);
-                  float x1 = fmaf(v[e + 1], t_scale[c0 + e + 1], t_shift[c0 + e + 1]);
+                  float x0 = fmaf(v[e], lds_f1(t_scale + (uint32_t)(c0 + e) * 4u), lds_f1(t_shift + (uint32_t)(c0 + e) * 4u));
+                  float x1 = fmaf(v[e + 1], lds_f1(t_scale + (uint32_t)(c0 + e + 1) * 4u), lds_f1(t_shift + (uint32_t)(c0 + e + 1) * 4u));
                   if (relu_all) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
                   const int wd = pos >> 1;
-                  *reinterpret_cast<__half2*>(srow + (((wd & ~31) | ((wd ^ row) & 31)) << 2)) = __floats2half2_rn(x0, x1);
+                  const __half2 hv = __floats2half2_rn(x0, x1);
+                  sts32(srow + (uint32_t)(((wd & ~31) | ((wd ^ row) & 31)) << 2), *reinterpret_cast<const uint32_t*>(&hv));
                 }
               }
             }
@@ -708,7 +796,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
             if (h == 0 && row_ok)
               for (int j = s.Nc; j < s.Nfill; j += 2) {
                 const int wd = j >> 1;
-                *reinterpret_cast<__half2*>(srow + (((wd & ~31) | ((wd ^ row) & 31)) << 2)) = __floats2half2_rn(0.f, 0.f);
+                sts32(srow + (uint32_t)(((wd & ~31) | ((wd ^ row) & 31)) << 2), 0u);
               }
             named_bar_sync(5, EPI_THREADS);
             const int nw = s.Nfill >> 1;
@@ -820,8 +908,15 @@ int conv_forward_tma(const ConvArgs& a, cudaStream_t s) {
   const long long ktotal = (long long)taps_h * a.C_in;
   pl.omode = (a.k_idx && a.n_idx) ? OUT_ROWS : ((!a.residual && ktotal >= 512) ? OUT_DIRECT : OUT_SLAB);
   const bool row_tiles = a.ksize == 3 || a.stride == 2;   // m-tiles of whole output rows: 4-d boxes (im2col / subsampling by TMA)
+  static const bool no_halo = getenv("LAUD_NO_HALO") != nullptr;
+  pl.halo = (!no_halo && a.ksize == 3 && a.stride == 1 && pl.bmode == BMODE_TMA && !a.bias_t && a.W_out + 2 <= BM) ? 1 : 0;
+  pl.Wp = a.W_out + 2;
+  {
+    const char* e = getenv("LAUD_HALO_BO");
+    pl.halo_bo = e ? atoi(e) : 0;   // measured: the swizzle is a function of the absolute shared-memory address, a row-shifted start needs no base offset
+  }
   if (row_tiles) {
-    pl.R = BM / a.W_out;
+    pl.R = BM / (pl.halo ? pl.Wp : a.W_out);
     if (pl.R > a.H_out) pl.R = a.H_out;
     // prefer an even split of the rows over one full and one nearly empty tile
     const int nt0 = (a.H_out + pl.R - 1) / pl.R;
@@ -859,22 +954,32 @@ int conv_forward_tma(const ConvArgs& a, cudaStream_t s) {
   pl.nbuf = (int)TMEM_COLS / (pl.MT * pl.acc_cols);
   if (pl.nbuf > 4) pl.nbuf = 4;
   const int b_bytes = pl.bmode == BMODE_KROWS ? ((pl.BN + 63) / 64) * 8192 : pl.BN * 128;
-  pl.b_off = pl.MT * A_TILE_BYTES;
+  pl.b_off = pl.halo ? 0 : pl.MT * A_TILE_BYTES;
   pl.stage_bytes = pl.b_off + round_up(b_bytes, 1024);
+  int halo_box_rows = 0;
+  if (pl.halo) {
+    halo_box_rows = pl.MT * pl.R + 2;
+    const int rows_read = ((pl.MT - 1) * pl.R + 2) * pl.Wp + 2 + BM;      // last row any tap of any tile may read (+1)
+    const int rows_alloc = halo_box_rows * pl.Wp > rows_read ? halo_box_rows * pl.Wp : rows_read;
+    pl.a_slot_bytes = round_up(rows_alloc * 128, 1024);
+    pl.a_region_bytes = 2 * pl.a_slot_bytes;
+    if (halo_box_rows > 256) pl.halo = 0;
+  }
+  if (!pl.halo) { pl.a_slot_bytes = 0; pl.a_region_bytes = 0; pl.b_off = pl.MT * A_TILE_BYTES; pl.stage_bytes = pl.b_off + round_up(b_bytes, 1024); }
   pl.ring = a.residual ? 3 : 2;
   pl.stg_pitch = round_up(round_up(nfill_max, 16) * 2, 128);
   pl.stg_rows = pl.rows_per_tile <= 64 ? 64 : BM;            // small images (7x7): half-height staging
   if (HWo < pl.stg_rows) pl.stg_rows = round_up(HWo, 32);
   pl.cnt_cached = a.B <= CNT_CACHE ? 1 : 0;
   const int stg_bytes = pl.omode == OUT_SLAB ? 2 * pl.ring * SLAB_BYTES : (pl.omode == OUT_ROWS ? pl.stg_rows * pl.stg_pitch : 0);
-  const int avail = SMEM_LIMIT - 1024 - (int)sizeof(Tables) - stg_bytes;
+  const int avail = SMEM_LIMIT - 1024 - (int)sizeof(Tables) - stg_bytes - pl.a_region_bytes;
   pl.stages = avail / pl.stage_bytes;
   if (pl.stages > MAX_STAGES) pl.stages = MAX_STAGES;
   if (pl.stages < 2) return conv_forward_umma(a, s);
   pl.full_count = 1 + (pl.bmode == BMODE_TMA ? 0 : GATHER_THREADS);
   const int rows_box = pl.rows_per_tile < HWo ? pl.rows_per_tile : HWo;     // boxes never exceed the tensor extent
   const int bn_box = pl.BN < a.C_out ? pl.BN : a.C_out;
-  pl.a_tx = 128 * rows_box;
+  pl.a_tx = pl.halo ? 128 * pl.Wp * halo_box_rows : 128 * rows_box;
   pl.b_tx = 128 * bn_box;
   pl.r_tx = 128 * rows_box;
 
@@ -888,7 +993,7 @@ int conv_forward_tma(const ConvArgs& a, cudaStream_t s) {
     // traversal stride = conv stride: the box spans stride*W_out x stride*R input pixels and delivers W_out x R of them
     const long long dims[4] = {cext_a, a.W_in, a.H_in, a.B};
     const long long str[3] = {a.ldx, (long long)a.W_in * a.ldx, (long long)a.H_in * a.W_in * a.ldx};
-    const int box[4] = {64, a.W_out * a.stride, pl.R * a.stride, 1};
+    const int box[4] = {64, pl.halo ? pl.Wp : a.W_out * a.stride, pl.halo ? halo_box_rows : pl.R * a.stride, 1};
     const int es[4] = {1, a.stride, a.stride, 1};
     ok = ok && make_map(&map_a, a.x, 4, dims, str, box, es);
   } else {
@@ -916,7 +1021,7 @@ int conv_forward_tma(const ConvArgs& a, cudaStream_t s) {
   }
   if (!ok) return conv_forward_umma(a, s);       // the driver refused a descriptor: v3 takes every layout v4 does
 
-  const size_t smem = 1024 + (size_t)pl.stages * pl.stage_bytes + stg_bytes + sizeof(Tables);
+  const size_t smem = 1024 + (size_t)pl.a_region_bytes + (size_t)pl.stages * pl.stage_bytes + stg_bytes + sizeof(Tables);
   const int grid = (int)(total < num_sms ? total : num_sms);
   g_conv_paths[0].fetch_add(1, std::memory_order_relaxed);
   g_conv_tma_launches.fetch_add(1, std::memory_order_relaxed);
