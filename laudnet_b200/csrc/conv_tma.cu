@@ -236,6 +236,56 @@ __device__ __forceinline__ void column_entry(const ConvArgs& a, const Plan& pl, 
   if (o >= 0 && a.n_mask && __ldg(a.n_mask + (size_t)s.b * (a.C_out / a.n_mask_gran) + o / a.n_mask_gran) == 0) sc = 0.f;   // mask before BN
 }
 
+// One 32-column pass of the slab epilogue for this thread's pixel row: accumulator (registers) -> folded BN ->
+// gate -> (+ residual from the slab) -> fp16 -> ReLU -> back into the slab.  The flags are template parameters so the
+// eight 16-byte groups are straight-line code: the table / residual loads of all groups issue back to back.
+template <bool RES, bool RELU>
+__device__ __forceinline__ void slab_pass(float* v, uint32_t t_scale, uint32_t t_shift, int c0, uint32_t srow, uint32_t sw,
+                                          int p, float gate) {
+#pragma unroll
+  for (int gp = 0; gp < 4; gp += 2) {             // two 16-byte groups at a time: loads first, then arithmetic
+    float4 s0[2], s1[2], h0[2], h1[2];
+    uint4 r4[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int g4 = gp + j;
+      s0[j] = lds_f4(t_scale + (uint32_t)(c0 + g4 * 8) * 4u);
+      s1[j] = lds_f4(t_scale + (uint32_t)(c0 + g4 * 8 + 4) * 4u);
+      h0[j] = lds_f4(t_shift + (uint32_t)(c0 + g4 * 8) * 4u);
+      h1[j] = lds_f4(t_shift + (uint32_t)(c0 + g4 * 8 + 4) * 4u);
+      if (RES) r4[j] = lds128(srow + ((((uint32_t)(p * 4 + g4)) ^ sw) << 4));
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int g4 = gp + j;
+      float* w = v + g4 * 8;
+      w[0] = fmaf(w[0], s0[j].x, h0[j].x) * gate; w[1] = fmaf(w[1], s0[j].y, h0[j].y) * gate;
+      w[2] = fmaf(w[2], s0[j].z, h0[j].z) * gate; w[3] = fmaf(w[3], s0[j].w, h0[j].w) * gate;
+      w[4] = fmaf(w[4], s1[j].x, h1[j].x) * gate; w[5] = fmaf(w[5], s1[j].y, h1[j].y) * gate;
+      w[6] = fmaf(w[6], s1[j].z, h1[j].z) * gate; w[7] = fmaf(w[7], s1[j].w, h1[j].w) * gate;
+      if (RES) {
+        const __half2* rh = reinterpret_cast<const __half2*>(&r4[j]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(rh[e]);
+          w[2 * e] += f.x;
+          w[2 * e + 1] += f.y;
+        }
+      }
+      uint4 o4;
+      __half2* oh = reinterpret_cast<__half2*>(&o4);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(w[2 * e], w[2 * e + 1]);
+      if (RELU) {                                  // max(.,0) commutes with the rounding to fp16
+        const __half2 z = __float2half2_rn(0.f);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) oh[e] = __hmax2(oh[e], z);
+      }
+      sts128(srow + ((((uint32_t)(p * 4 + g4)) ^ sw) << 4), o4);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ the kernel
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan pl,
@@ -652,42 +702,14 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
                 for (int e = 0; e < 32; ++e) v[e] = 0.f;
               }
               if (!(pl.halo && !pvalid)) {                       // (padding column of the padded image: not a pixel)
-#pragma unroll
-                for (int g4 = 0; g4 < 4; ++g4) {                 // 8 channels = one 16-byte chunk
-                  const float4 s0 = lds_f4(t_scale + (uint32_t)(c0 + g4 * 8) * 4u);
-                  const float4 s1 = lds_f4(t_scale + (uint32_t)(c0 + g4 * 8 + 4) * 4u);
-                  const float4 h0 = lds_f4(t_shift + (uint32_t)(c0 + g4 * 8) * 4u);
-                  const float4 h1 = lds_f4(t_shift + (uint32_t)(c0 + g4 * 8 + 4) * 4u);
-                  float* w = v + g4 * 8;
-                  w[0] = fmaf(w[0], s0.x, h0.x); w[1] = fmaf(w[1], s0.y, h0.y);
-                  w[2] = fmaf(w[2], s0.z, h0.z); w[3] = fmaf(w[3], s0.w, h0.w);
-                  w[4] = fmaf(w[4], s1.x, h1.x); w[5] = fmaf(w[5], s1.y, h1.y);
-                  w[6] = fmaf(w[6], s1.z, h1.z); w[7] = fmaf(w[7], s1.w, h1.w);
-                  if (!row_on) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) w[e] = 0.f;
-                  }
-                  const uint32_t cell = srow + ((((uint32_t)(p * 4 + g4)) ^ sw) << 4);
-                  if (has_res) {
-                    const uint4 r4 = lds128(cell);
-                    const __half2* rh = reinterpret_cast<const __half2*>(&r4);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                      const float2 f = __half22float2(rh[e]);
-                      w[2 * e] += f.x;
-                      w[2 * e + 1] += f.y;
-                    }
-                  }
-                  uint4 o4;
-                  __half2* oh = reinterpret_cast<__half2*>(&o4);
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(w[2 * e], w[2 * e + 1]);
-                  if (relu_all) {                                // max(.,0) commutes with the rounding to fp16
-                    const __half2 z = __float2half2_rn(0.f);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) oh[e] = __hmax2(oh[e], z);
-                  }
-                  sts128(cell, o4);
+                // a gated-off VALID pixel has a finite accumulator, so multiplying by 0 zeroes it exactly
+                const float gate = row_on ? 1.f : 0.f;
+                if (has_res) {
+                  if (relu_all) slab_pass<true, true>(v, t_scale, t_shift, c0, srow, sw, p, gate);
+                  else slab_pass<true, false>(v, t_scale, t_shift, c0, srow, sw, p, gate);
+                } else {
+                  if (relu_all) slab_pass<false, true>(v, t_scale, t_shift, c0, srow, sw, p, gate);
+                  else slab_pass<false, false>(v, t_scale, t_shift, c0, srow, sw, p, gate);
                 }
               }
             }
@@ -939,7 +961,10 @@ int conv_forward_tma(const ConvArgs& a, cudaStream_t s) {
   } else {
     // wide tiles halve the re-reads of the activations when the reduction is long enough to hide a
     // non-overlapped epilogue (BN = 256 with two m-tiles fills TMEM: one accumulator buffer)
-    pl.BN = span <= 64 ? 64 : ((span > 128 && pl.omode == OUT_DIRECT) ? 256 : 128);
+    // (an SS-mode tcgen05.mma costs >= ~128 cycles whatever its N - measured - so N = 256 is the only full-rate shape)
+    static const bool slab256 = getenv("LAUD_SLAB_BN128") == nullptr;
+    pl.BN = span <= 64 ? 64 : ((span > 128 && (pl.omode == OUT_DIRECT || slab256)) ? 256 : 128);
+    if (pl.BN == 256 && pl.omode == OUT_SLAB) pl.MT = 1;   // keep two accumulator buffers: this epilogue must overlap the MMAs
     pl.NT = (span + pl.BN - 1) / pl.BN;
     pl.NTI = 1;
   }
