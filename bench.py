@@ -173,6 +173,9 @@ def run_graft(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # NCCL prints its version banner on stdout: keep stdout clean for the one JSON line
+    out_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
@@ -315,7 +318,8 @@ def run_graft(args):
                "sample": f"{args.cpu_sample} of the 256 images, 2 timed forwards after a warm-up (fp32 torch CPU oracle, "
                          f"{cores} threads; flops ratio {ratio:.3f})"}
     if rank == 0:
-        print(json.dumps({
+        sys.stdout.flush()
+        os.write(out_fd, (json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
@@ -330,7 +334,7 @@ def run_graft(args):
             "gpu_launches": graphed.launches * args.steps, "launches_per_step": graphed.launches,
             "eager_launches_per_step": launches_per_step, "conv_paths": _lib.conv_path_counts(),
             "clocks": clocks, "roofline": roof, "net": net, "cpu_baseline": cpu,
-        }))
+        }) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
