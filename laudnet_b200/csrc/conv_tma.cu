@@ -912,7 +912,17 @@ bool conv_tma_supported(const ConvArgs& a) {
   return encode_fn() != nullptr;
 }
 
-int conv_forward_tma(const ConvArgs& a, cudaStream_t s) {
+int conv_forward_tma(const ConvArgs& a_in, cudaStream_t s) {
+  // A 1x1 stride-1 layer with nothing per sample (no gather, gate or list) is one flat GEMM over all B*H*W pixels:
+  // m-tiles run across sample boundaries, so images smaller than a tile (14x14, 7x7) leave no padded rows.
+  ConvArgs a = a_in;
+  static const bool no_flat = getenv("LAUD_NO_FLAT") != nullptr;
+  if (!no_flat && a.ksize == 1 && a.stride == 1 && !a.k_idx && !a.n_idx && !a.n_mask && !a.sample_idx && !a.out_mask &&
+      !a.bias_t && (long long)a.B * a.H_out * a.W_out < (1ll << 31)) {
+    a.W_in = a.W_out = a.B * a.H_out * a.W_out;
+    a.H_in = a.H_out = 1;
+    a.B = 1;
+  }
   static int num_sms = 0;
   if (num_sms == 0) {
     int dev = 0;
