@@ -19,6 +19,7 @@ to the GPU box; oracle/laud_oracle.py is its restatement, pinned to it by tests/
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import statistics
@@ -275,25 +276,39 @@ def run_graft(args):
         h2d = x_host.numel() * x_host.element_size()
         d2h = logits_host.numel() * logits_host.element_size()
 
-        # ---- per-kernel timing of the conv launches of one step (CUDA events around each launch)
-        conv_ms, by_tag = [], {}
+        # ---- per-kernel timing of the conv launches of one step: the library brackets each kernel (only the
+        #      kernel, not the host-side descriptor encoding) with CUDA events on the launching stream
+        conv_ms, by_tag, n_conv = [], {}, 0
+        L = _lib.lib()
         for _ in range(3):
-            with _engine.conv_profile() as prof:
-                model.forward_logits(x_dev)
-                torch.cuda.synchronize()
-            conv_ms.append(prof.total_ms())
-            by_tag = prof.by_tag()
-        n_conv = sum(n for n, _ in by_tag.values())
+            L.laud_conv_profile(1)
+            model.forward_logits(x_dev)
+            torch.cuda.synchronize()
+            tot = ctypes.c_float(0.0)
+            n_conv = L.laud_conv_profile_read(ctypes.byref(tot))
+            conv_ms.append(tot.value)
+            L.laud_conv_profile(0)
+        with _engine.conv_profile() as prof:            # per-layer split (includes host launch gaps: shares only)
+            model.forward_logits(x_dev)
+            torch.cuda.synchronize()
+        by_tag = prof.by_tag()
         conv_ms_step = statistics.median(conv_ms)
 
     peaks = _peaks()
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01q_conv_traffic.json")
+    if os.path.exists(tpath):                  # dram__bytes_read+write of the conv launches from the committed ncu capture
+        tj = json.load(open(tpath))
+        traffic = tj["dram_bytes_per_launch_avg"]
+        traffic_src = "profiles/r01q_conv_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, average per conv launch)"
     conv_bytes = work.conv_bytes_per_image * B
     conv_flops = work.conv_flops_per_image * B
     ach_gbs = conv_bytes / (conv_ms_step * 1e-3) / 1e9
     roof = {
         "kernel": "laud::conv_tma_kernel (mask-conditioned tcgen05 conv, TMA-staged; all %d launches of one step)" % n_conv,
         "bound": "hbm", "achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-        "frac": ach_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+        "frac": ach_gbs / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
+        "peak_source": peaks["source"],
         "launches_per_step": n_conv, "avg_launch_us": 1e3 * conv_ms_step / max(n_conv, 1),
         "algorithmic_bytes_per_step": conv_bytes, "kernel_ms_per_step": conv_ms_step,
         "share_of_step": conv_ms_step / ms_step,

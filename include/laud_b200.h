@@ -60,6 +60,11 @@ unsigned long long laud_launch_count(void);
 void laud_conv_path_counts(unsigned long long out[3]);
 /* launches of the TMA-staged tcgen05 kernel (conv_tma.cu), a subset of out[0] above */
 unsigned long long laud_conv_tma_launch_count(void);
+/* Measurement aid: while enabled, every tcgen05 conv launch is bracketed - the kernel only, not the host-side
+ * descriptor encoding - by CUDA events on its stream.  laud_conv_profile_read (after a synchronize) returns the
+ * number of recorded launches and their summed device time.  Not for use during CUDA-graph capture. */
+void laud_conv_profile(int enable);
+int laud_conv_profile_read(float* total_ms);
 
 /* ---------------------------------------------------------------------------
  * (a1) channel masker.  Replaces Masker_channel_MLP.forward, eval branch

@@ -56,6 +56,8 @@ SIGNATURES = {
     "laud_launch_count": ([], C.c_ulonglong),
     "laud_conv_path_counts": ([C.POINTER(C.c_ulonglong * 3)], None),
     "laud_conv_tma_launch_count": ([], C.c_ulonglong),
+    "laud_conv_profile": ([_i], None),
+    "laud_conv_profile_read": ([C.POINTER(C.c_float)], _i),
     "laud_masker_channel_mlp": ([_vp, _i, _i, _i, _i, _fp, _fp, _i, _fp, _fp, _i, _fp, _fp, _fp, _u8p, _i32p, _i32p, _i32p, _vp], _i),
     "laud_masker_channel_from_pooled": ([_fp, _i, _i, _i, _fp, _fp, _i, _fp, _fp, _i, _fp, _u8p, _i32p, _i32p, _i32p, _vp], _i),
     "laud_global_avg_pool": ([_vp, _i, _i, _i, _i, _fp, _fp, _vp], _i),

@@ -3,6 +3,8 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
+#include <utility>
+#include <vector>
 #include "laud_common.cuh"
 
 namespace laud {
@@ -19,9 +21,47 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static bool g_prof_on = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+
+ConvProfScope::ConvProfScope(cudaStream_t stream) : s(stream), e0(nullptr), on(g_prof_on) {
+  if (on) {
+    cudaEventCreate(&e0);
+    cudaEventRecord(e0, s);
+  }
+}
+ConvProfScope::~ConvProfScope() {
+  if (on) {
+    cudaEvent_t e1;
+    cudaEventCreate(&e1);
+    cudaEventRecord(e1, s);
+    g_prof_events.emplace_back(e0, e1);
+  }
+}
+
 }  // namespace laud
 
 using namespace laud;
+
+// enable != 0: start collecting (drops earlier records); 0: stop.
+extern "C" void laud_conv_profile(int enable) {
+  for (auto& pr : g_prof_events) {
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
+  g_prof_events.clear();
+  g_prof_on = enable != 0;
+}
+// After a synchronize: number of recorded conv launches and their summed device time in ms.
+extern "C" int laud_conv_profile_read(float* total_ms) {
+  float tot = 0.f;
+  for (auto& pr : g_prof_events) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) tot += ms;
+  }
+  if (total_ms) *total_ms = tot;
+  return (int)g_prof_events.size();
+}
 
 extern "C" int laud_abi_version(void) { return LAUD_ABI_VERSION; }
 extern "C" const char* laud_last_error(void) { return g_err; }

@@ -1060,7 +1060,10 @@ int conv_forward_tma(const ConvArgs& a_in, cudaStream_t s) {
   const int grid = (int)(total < num_sms ? total : num_sms);
   g_conv_paths[0].fetch_add(1, std::memory_order_relaxed);
   g_conv_tma_launches.fetch_add(1, std::memory_order_relaxed);
-  conv_tma_kernel<<<grid, NUM_THREADS, smem, s>>>(a, pl, map_a, map_b, map_y, map_r);
+  {
+    ConvProfScope prof(s);
+    conv_tma_kernel<<<grid, NUM_THREADS, smem, s>>>(a, pl, map_a, map_b, map_y, map_r);
+  }
   return check_launch("conv_tma_kernel");
 }
 

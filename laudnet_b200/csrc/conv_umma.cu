@@ -628,7 +628,10 @@ int conv_forward_umma(const ConvArgs& a, cudaStream_t s) {
   const size_t smem = 1024 + (size_t)pl.stages * pl.stage_bytes + (pl.staged ? (size_t)BM * pl.stg_pitch : 0) + sizeof(Tables);
   const int grid = (int)(total < num_sms ? total : num_sms);
   g_conv_paths[0].fetch_add(1, std::memory_order_relaxed);
-  conv_umma_kernel<<<grid, NUM_THREADS, smem, s>>>(a, pl);
+  {
+    ConvProfScope prof(s);
+    conv_umma_kernel<<<grid, NUM_THREADS, smem, s>>>(a, pl);
+  }
   return check_launch("conv_umma_kernel");
 }
 

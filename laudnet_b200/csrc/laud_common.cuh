@@ -81,6 +81,16 @@ struct ConvArgs {
   const uint8_t* n_mask; int n_mask_gran;
 };
 
+// Per-launch CUDA-event timing of the convolution kernels (bench.py's roofline leg): when enabled through
+// laud_conv_profile(), the launch sites bracket the kernel - and only the kernel - with events on its stream.
+struct ConvProfScope {
+  cudaStream_t s;
+  cudaEvent_t e0;
+  bool on;
+  explicit ConvProfScope(cudaStream_t stream);
+  ~ConvProfScope();
+};
+
 int conv_forward_naive(const ConvArgs& a, cudaStream_t s);
 int conv_forward_hmma(const ConvArgs& a, cudaStream_t s);
 int conv_forward_umma(const ConvArgs& a, cudaStream_t s);
