@@ -75,7 +75,7 @@ __global__ void vtab4_init_kernel() {
 
 constexpr int CNT_CACHE = 512;                   // per-sample active counts cached in shared memory when B fits
 
-struct Tables {
+struct alignas(16) Tables {
   int kch[KIDX_MAX];       // real input channel of this sample's compact input channel e
   float scale[2][BN_MAX];  // epilogue column tables, double-buffered across sub-items
   float shift[2][BN_MAX];
@@ -84,6 +84,7 @@ struct Tables {
   unsigned short vmask[2][BM];   // tap-validity bit sets of the pixels of the current m-group (H1-constant step)
   unsigned long long full[MAX_STAGES], empty[MAX_STAGES], tfull[4], tempty[4], rfull[2][MAX_RING];
   unsigned long long afull[2], aempty[2];   // halo mode: ring of activation tiles (one per 64-channel chunk)
+  unsigned long long sready[2][MAX_RING], sfree[2][MAX_RING];   // slab hand-off between the epilogue halves and their DMA threads
   uint32_t tmem_base;
 };
 
@@ -103,6 +104,10 @@ struct Plan {              // host-computed launch geometry
   // with their zero-padded 1-pixel halo, as rows of a (W+2)-wide padded image; the nine taps are the same tile read
   // at nine row offsets (UMMA descriptors with a base offset), so only the weights stream per tap.
   int halo, Wp, a_slot_bytes, a_region_bytes, halo_bo;
+  // layers whose output columns do not depend on the sample (no gather, no channel gate): folded-BN scale / shift of ALL
+  // output channels are loaded once per CTA (stab_cols floats each, zero padded) - no per-item column tables, no barrier
+  int static_cols, stab_cols;
+  int dma;                 // 1: slab stores / residual prefetches are issued by two otherwise idle threads (shared-weight layers)
 };
 
 struct Sub {               // one (sample, m-group, n-tile) unit of work
@@ -317,12 +322,24 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
       mbar_init(&T.afull[i], 1);
       mbar_init(&T.aempty[i], 1);
     }
+    for (int h = 0; h < 2; ++h)
+      for (int i = 0; i < MAX_RING; ++i) {
+        mbar_init(&T.sready[h][i], HALF_THREADS);
+        mbar_init(&T.sfree[h][i], 1);
+      }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (pl.cnt_cached)                                              // one round trip for every per-sample count
     for (int i = threadIdx.x; i < a.B; i += NUM_THREADS) {
       T.kcnt[i] = a.k_idx ? __ldg(a.k_cnt + i) : 0;
       T.ncnt[i] = a.n_idx ? __ldg(a.n_cnt + i) : 0;
+    }
+  float* stab = reinterpret_cast<float*>(&T + 1);
+  if (pl.static_cols)
+    for (int i = threadIdx.x; i < pl.stab_cols; i += NUM_THREADS) {
+      const bool in = i < a.C_out;
+      stab[i] = in ? (a.scale ? __ldg(a.scale + i) : 1.f) : 0.f;
+      stab[pl.stab_cols + i] = (in && a.scale) ? __ldg(a.shift + i) : 0.f;
     }
   if (warp == TMA_WARP && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -614,6 +631,48 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
       }
       if (pt == 0) KP_FLUSH(2);
       asm volatile("cp.async.wait_all;" ::: "memory");
+    } else if (pl.dma && warp < GATHER_WARP0 + 2 && lane == 0) {
+      // =========================================================== slab DMA thread of epilogue half h
+      // Issues the TMA store of every finished slab and keeps the residual slabs ring - 1 tasks ahead, so the 128
+      // epilogue threads of the half never wait for a copy to be ISSUED, only for data (rfull) or space (sfree).
+      const int h = warp - GATHER_WARP0;
+      unsigned char* ring = stg + (size_t)h * pl.ring * SLAB_BYTES;
+      const bool has_res = a.residual != nullptr;
+      Cursor cs, cl;
+      walker_init(pl, cs.w);
+      cs.mt = 0; cs.sl = 0; cs.have = 0;
+      cl = cs;
+      if (has_res)
+        for (int t = 0; t < pl.ring; ++t) {
+          if (!cursor_next(a, pl, T, cl, h)) break;
+          int m0, rows;
+          tile_rows(a, pl, cl.s.mt0 + cl.mt, m0, rows);
+          mbar_arrive_expect_tx(&T.rfull[h][t], (uint32_t)pl.r_tx);
+          tma_load_3d(smem_u32(ring + t * SLAB_BYTES), &map_r, &T.rfull[h][t], cl.s.n0 + cl.sl * 64, m0, cl.s.b);
+        }
+      for (int j = 0; cursor_next(a, pl, T, cs, h); ++j) {
+        const int slot = j % pl.ring;
+        int m0, rows;
+        tile_rows(a, pl, cs.s.mt0 + cs.mt, m0, rows);
+        mbar_wait(&T.sready[h][slot], (uint32_t)(j / pl.ring) & 1u);
+        tma_store_3d(&map_y, smem_u32(ring + slot * SLAB_BYTES), cs.s.n0 + cs.sl * 64, m0, cs.s.b);
+        bulk_commit();
+        if (j >= 1) {
+          bulk_wait_read_n<1>();                                 // the PREVIOUS store has been read out of its slab
+          const int ps = (j - 1) % pl.ring;
+          if (has_res) {
+            if (cursor_next(a, pl, T, cl, h)) {                  // refill it: residual of task (j - 1) + ring
+              int pm0, prow;
+              tile_rows(a, pl, cl.s.mt0 + cl.mt, pm0, prow);
+              mbar_arrive_expect_tx(&T.rfull[h][ps], (uint32_t)pl.r_tx);
+              tma_load_3d(smem_u32(ring + ps * SLAB_BYTES), &map_r, &T.rfull[h][ps], cl.s.n0 + cl.sl * 64, pm0, cl.s.b);
+            }
+          } else {
+            mbar_arrive(&T.sfree[h][ps]);
+          }
+        }
+      }
+      bulk_wait_all();
     }
   } else {
     // =========================================================== epilogue
@@ -630,7 +689,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
     walker_init(pl, cur.w);
     cur.mt = 0; cur.sl = 0; cur.have = 0;
     int pf = 0;                                                  // slab tasks whose residual load has been issued
-    if (pl.omode == OUT_SLAB && a.residual && elected) {
+    if (pl.omode == OUT_SLAB && a.residual && elected && !pl.dma) {
       for (; pf < pl.ring - 1; ++pf) {
         if (!cursor_next(a, pl, T, cur, h)) break;
         int m0, rows;
@@ -645,7 +704,8 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
     Sub nx;
     bool more = walker_next(a, pl, T, wk, nx);
     int par = 0;
-    if (more) {
+    const bool dyn_cols = !pl.static_cols;
+    if (more && dyn_cols) {
       float sc, sh;
       int pos;
       column_entry(a, pl, nx, et, sc, sh, pos);
@@ -653,14 +713,15 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
     }
     while (more) {
       s = nx;
-      named_bar_sync(2, EPI_THREADS);        // tables[par] are complete; nobody still reads tables[par ^ 1]
+      if (dyn_cols) named_bar_sync(2, EPI_THREADS);   // tables[par] are complete; nobody still reads tables[par ^ 1]
       more = walker_next(a, pl, T, wk, nx);
       float nsc = 0.f, nsh = 0.f;
       int npos = -1;
-      if (more) column_entry(a, pl, nx, et, nsc, nsh, npos);
+      if (more && dyn_cols) column_entry(a, pl, nx, et, nsc, nsh, npos);
       KP_LAP(1);                                                 // decode + next table entry (loads in flight)
-      const uint32_t t_scale = smem_u32(&T.scale[par][0]);       // shared-space addresses of this sub-item's tables
-      const uint32_t t_shift = smem_u32(&T.shift[par][0]);
+      // shared-space addresses of this sub-item's column tables
+      const uint32_t t_scale = dyn_cols ? smem_u32(&T.scale[par][0]) : smem_u32(stab) + (uint32_t)s.n0 * 4u;
+      const uint32_t t_shift = dyn_cols ? smem_u32(&T.shift[par][0]) : t_scale + (uint32_t)pl.stab_cols * 4u;
       const uint32_t t_cpos = smem_u32(&T.cpos[par][0]);
       mbar_wait(&T.tfull[buf], bphase);
       KP_LAP(2);                                                 // wait for the accumulator
@@ -689,6 +750,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
             const uint32_t sw = (uint32_t)(prow & 7);
             const bool has_res = a.residual != nullptr;
             if (has_res) mbar_wait(&T.rfull[h][slot], (uint32_t)(task / pl.ring) & 1u);
+            else if (pl.dma && task >= pl.ring) mbar_wait(&T.sfree[h][slot], (uint32_t)(task / pl.ring - 1) & 1u);
             KP_LAP(3);                                           // wait for the residual slab
 #pragma unroll
             for (int p = 0; p < 2; ++p) {
@@ -715,6 +777,11 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
             }
             KP_LAP(4);                                           // TMEM -> registers -> slab
             fence_proxy_async();                                 // generic-proxy slab writes -> visible to the TMA store
+            if (pl.dma) {
+              mbar_arrive(&T.sready[h][slot]);                   // hand the slab to this half's DMA thread
+              KP_LAP(5);
+              continue;
+            }
             if (elected && !a.residual) {                        // the NEXT task's slab must have left shared memory
               if (pl.ring == 3) bulk_wait_read_n<1>(); else bulk_wait_read_n<0>();
             }
@@ -836,9 +903,9 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
       mbar_arrive(&T.tempty[buf]);                               // accumulators drained: the MMA warp may reuse them
       if (++buf == pl.nbuf) { buf = 0; bphase ^= 1; }
       par ^= 1;
-      if (more) { T.scale[par][et] = nsc; T.shift[par][et] = nsh; T.cpos[par][et] = npos; }
+      if (more && dyn_cols) { T.scale[par][et] = nsc; T.shift[par][et] = nsh; T.cpos[par][et] = npos; }
     }
-    if (pl.omode == OUT_SLAB) bulk_wait_all();
+    if (pl.omode == OUT_SLAB && !pl.dma) bulk_wait_all();
     KP_LAP(6);
     if (et == 0) KP_FLUSH(3);
     if (et == HALF_THREADS) KP_FLUSH(4);
@@ -1007,7 +1074,17 @@ int conv_forward_tma(const ConvArgs& a_in, cudaStream_t s) {
   if (HWo < pl.stg_rows) pl.stg_rows = round_up(HWo, 32);
   pl.cnt_cached = a.B <= CNT_CACHE ? 1 : 0;
   const int stg_bytes = pl.omode == OUT_SLAB ? 2 * pl.ring * SLAB_BYTES : (pl.omode == OUT_ROWS ? pl.stg_rows * pl.stg_pitch : 0);
-  const int avail = SMEM_LIMIT - 1024 - (int)sizeof(Tables) - stg_bytes - pl.a_region_bytes;
+  static const bool no_dma = getenv("LAUD_NO_DMA") != nullptr;
+  pl.dma = (!no_dma && pl.omode == OUT_SLAB && pl.bmode == BMODE_TMA) ? 1 : 0;
+  pl.static_cols = (pl.omode != OUT_ROWS && !a.n_idx && !a.n_mask) ? 1 : 0;
+  pl.stab_cols = round_up(a.C_out, 64) + BN_MAX;              // reads of a partial last tile stay inside the (zero) padding
+  int stab_bytes = pl.static_cols ? 2 * pl.stab_cols * 4 : 0;
+  int avail = SMEM_LIMIT - 1024 - (int)sizeof(Tables) - stg_bytes - pl.a_region_bytes - stab_bytes;
+  if (pl.static_cols && avail / pl.stage_bytes < 2) {         // no room beside a two-stage pipeline: per-item tables
+    pl.static_cols = 0;
+    avail += stab_bytes;
+    stab_bytes = 0;
+  }
   pl.stages = avail / pl.stage_bytes;
   if (pl.stages > MAX_STAGES) pl.stages = MAX_STAGES;
   if (pl.stages < 2) return conv_forward_umma(a, s);
@@ -1056,7 +1133,7 @@ int conv_forward_tma(const ConvArgs& a_in, cudaStream_t s) {
   }
   if (!ok) return conv_forward_umma(a, s);       // the driver refused a descriptor: v3 takes every layout v4 does
 
-  const size_t smem = 1024 + (size_t)pl.a_region_bytes + (size_t)pl.stages * pl.stage_bytes + stg_bytes + sizeof(Tables);
+  const size_t smem = 1024 + (size_t)pl.a_region_bytes + (size_t)pl.stages * pl.stage_bytes + stg_bytes + sizeof(Tables) + stab_bytes;
   const int grid = (int)(total < num_sms ? total : num_sms);
   g_conv_paths[0].fetch_add(1, std::memory_order_relaxed);
   g_conv_tma_launches.fetch_add(1, std::memory_order_relaxed);
