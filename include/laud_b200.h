@@ -130,6 +130,12 @@ int laud_resize_mask_nearest(const uint8_t* mask, int B, int g, int S, int H_out
 int laud_compact_rows(const uint8_t* gate, int B, int g, int HW,
                       int32_t* rows_out, int32_t* count_out, int32_t* block_ws, void* stream);
 
+/* Layer gate (dyn_mode='layer', laud_resnet.py:72,97-110: one gate per sample) in one launch: the ordered list of
+ * the ACTIVE samples (the work list of laud_conv_forward's sample_idx / sample_cnt) and the statistics counts of the
+ * broadcast / dilated masks: counts4[2] += n_active*hw_out, counts4[3] += n_active*hw_in (counts4 nullable). */
+int laud_layer_gate_lists(const uint8_t* gate /* [B] */, int B, int hw_out, int hw_in, int32_t* counts4,
+                          int32_t* rows_out /* [B] */, int32_t* count_out /* [1] */, void* stream);
+
 /* ---------------------------------------------------------------------------
  * (a5-a7) the mask-conditioned convolution: implicit-GEMM conv (1x1 or 3x3)
  * + folded BatchNorm + mask + residual + ReLU, with per-sample channel

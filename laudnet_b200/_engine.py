@@ -194,6 +194,10 @@ class ResNetEngine:
         #   "sparse": gathered GEMMs over the active channels only + H1 constants (compact a1 / a2);
         #   "dense" : masked-dense - weights shared by all samples, gated channels emitted as their BN constant.
         self.channel_exec = os.environ.get("LAUD_CHANNEL_EXEC", "dense")     # measured faster at every ResNet-101 stage (profiles/)
+        # How a layer-gated block executes: "skip" = the convolutions run only on the device-side list of ACTIVE samples
+        # and the block output is written in place over the block input (skipped samples are untouched: relu(identity)
+        # == identity bit-exactly, laud_resnet.py:133-144); "mask" = masked-dense (compute all, zero the gated rows).
+        self.layer_exec = os.environ.get("LAUD_LAYER_EXEC", "skip")
         self._ws: Dict[tuple, dict] = {}
 
     # ------------------------------------------------------------------ prepare
@@ -293,6 +297,8 @@ class ResNetEngine:
             m2=torch.empty(B * g_max * hw_max, dtype=torch.uint8, device=dev),
             m1=torch.empty(B * g_max * hw_max, dtype=torch.uint8, device=dev),
             counts=torch.zeros((nb, 4), **i32),
+            srows=torch.empty((B,), **i32), scnt=torch.zeros((1,), **i32), cws=torch.zeros((64,), **i32),
+            lidx=torch.empty((B * g_max,), **i32), lcnt=torch.empty((B,), **i32),
             stats=torch.empty(nb * 5 + 1, dtype=torch.float32, device=dev),
             logits=None,
         )
@@ -319,6 +325,7 @@ class ResNetEngine:
         counts = ws["counts"][p.index]
         gate = None
         m3 = None
+        fast_layer = False
         wp = p.width + 16                       # channel pitch of the compact intermediates
         use_wt = False
         dense_gate = False
@@ -361,20 +368,45 @@ class ResNetEngine:
             else:
                 slog = torch.empty((B, 2 * g, S, S), dtype=torch.float32, device=x.device) if keep is not None else None
                 wt = blk.masker_spatial.conv.weight.detach().reshape(2 * g, p.inplanes)
-                check(L.laud_masker_spatial(ptr(x), B, Hi, Hi, p.inplanes, ptr(wt),
-                                            ptr(blk.masker_spatial.conv.bias.detach()), g, S, ptr(slog), ptr(small),
-                                            ptr(counts[1:2]), st), "laud_masker_spatial")
+                if S == 1 and "lidx" in ws:
+                    # one gate per sample (layer skip): global pool -> 2g-row linear -> keep>=drop is exactly the
+                    # one-layer channel masker; its fused one-CTA-per-sample kernel pools at HBM speed
+                    check(L.laud_masker_channel_mlp(ptr(x), B, Hi * Hi, p.inplanes, 1, ptr(wt),
+                                                    ptr(blk.masker_spatial.conv.bias.detach()), 0, None, None, g,
+                                                    ptr(ws["partial"]), None, ptr(slog), ptr(small), ptr(ws["lidx"]),
+                                                    ptr(ws["lcnt"]), ptr(counts[1:2]), st), "laud_masker_channel_mlp")
+                else:
+                    check(L.laud_masker_spatial(ptr(x), B, Hi, Hi, p.inplanes, ptr(wt),
+                                                ptr(blk.masker_spatial.conv.bias.detach()), g, S, ptr(slog), ptr(small),
+                                                ptr(counts[1:2]), st), "laud_masker_spatial")
             m3 = ws["m3"][:B * g * Ho * Ho].view(B, g, Ho, Ho)
             m2 = ws["m2"][:B * g * Ho * Ho].view(B, g, Ho, Ho)
             m1 = ws["m1"][:B * g * Hi * Hi].view(B, g, Hi, Hi)
-            check(L.laud_resize_mask_nearest(ptr(small), B, g, S, Ho, ptr(m3), st), "laud_resize_mask_nearest")
-            check(L.laud_expand_mask(ptr(m3), B, g, Ho, Ho, 1, 0, ptr(m2), ptr(counts[2:3]), st), "laud_expand_mask")
-            check(L.laud_expand_mask(ptr(m2), B, g, Ho, Ho, p.stride, 1, ptr(m1), ptr(counts[3:4]), st),
-                  "laud_expand_mask")
+            fast_layer = (p.mode == "layer" and self.layer_exec == "skip" and g == 1 and S == 1 and "srows" in ws
+                          and keep is None)
+            if fast_layer:
+                # one launch: active-sample work list + the counts of the broadcast / dilated masks
+                check(L.laud_layer_gate_lists(ptr(small), B, Ho * Ho, Hi * Hi, ptr(counts), ptr(ws["srows"]),
+                                              ptr(ws["scnt"]), st), "laud_layer_gate_lists")
+                if p.wd is not None:     # the downsample branch gates its ReLU per pixel
+                    check(L.laud_resize_mask_nearest(ptr(small), B, g, S, Ho, ptr(m3), st), "laud_resize_mask_nearest")
+            else:
+                check(L.laud_resize_mask_nearest(ptr(small), B, g, S, Ho, ptr(m3), st), "laud_resize_mask_nearest")
+                check(L.laud_expand_mask(ptr(m3), B, g, Ho, Ho, 1, 0, ptr(m2), ptr(counts[2:3]), st), "laud_expand_mask")
+                check(L.laud_expand_mask(ptr(m2), B, g, Ho, Ho, p.stride, 1, ptr(m1), ptr(counts[3:4]), st),
+                      "laud_expand_mask")
             if keep is not None:
                 keep.spatial_mask_small, keep.spatial_logits = small.clone(), slog
                 keep.mask_conv3, keep.mask_conv2, keep.mask_conv1 = m3.clone(), m2.clone(), m1.clone()
 
+        # layer skip: ordered list of the active samples; convolutions take it as their work list
+        skip = (p.mode == "layer" and self.layer_exec == "skip" and gate is None and "srows" in ws)
+        sl = {}
+        if skip:
+            if not fast_layer:
+                check(L.laud_compact_rows(ptr(small), B, 1, 1, ptr(ws["srows"]), ptr(ws["scnt"]), ptr(ws["cws"]), st),
+                      "laud_compact_rows")
+            sl = dict(sample_idx=ws["srows"], sample_cnt=ws["scnt"])
         a1, a2 = ws["a1"], ws["a2"]
         sparse_gate = gate is not None and not dense_gate
         ck = dict(k_idx=gate.idx, k_cnt=gate.cnt, k_gran=p.gran) if sparse_gate else {}
@@ -383,30 +415,45 @@ class ResNetEngine:
         ld12 = wp if sparse_gate else p.width
         # conv1 1x1 (+ mask) + bn1 + relu      laud_resnet.py:115-118
         run_conv(x, p.w1, a1, B, Hi, Hi, p.inplanes, Hi, Hi, p.width, 1, 1, 0, ldx=p.inplanes, ldy=ld12,
-                 scale=p.s1, shift=p.t1, relu=_lib.RELU_ALL, impl=self.impl, tag=f"s{p.stage + 1}.conv1", **cn, **nm)
+                 scale=p.s1, shift=p.t1, relu=_lib.RELU_ALL, impl=self.impl, tag=f"s{p.stage + 1}.conv1", **cn, **nm, **sl)
         # conv2 3x3/stride (+ mask) + bn2 + relu     laud_resnet.py:123-126
         run_conv(a1, p.w2, a2, B, Hi, Hi, p.width, Ho, Ho, p.width, 3, p.stride, 1, ldx=ld12, ldy=ld12,
                  scale=p.s2, shift=p.t2, relu=_lib.RELU_ALL, impl=self.impl, tag=f"s{p.stage + 1}.conv2",
                  pre_bias=ws["pb2"] if (sparse_gate and not use_wt) else None,
                  pre_bias_classes=16 if (sparse_gate and not use_wt) else 0,
                  pre_bias_ld=p.width if sparse_gate else 0, w_t=p.w2t if use_wt else None,
-                 bias_t=T if use_wt else None, bias_ld=Tn if use_wt else 0, **ck, **cn, **nm)
+                 bias_t=T if use_wt else None, bias_ld=Tn if use_wt else 0, **ck, **cn, **nm, **sl)
         # identity branch      laud_resnet.py:138-141
-        if p.wd is not None:
-            run_conv(x, p.wd, idbuf, B, Hi, Hi, p.inplanes, Ho, Ho, p.outplanes, 1, p.stride, 0, ldx=p.inplanes,
-                     ldy=p.outplanes, scale=p.sd, shift=p.td, relu=_lib.RELU_NONE, impl=self.impl,
-                     tag=f"s{p.stage + 1}.down")
-            res = idbuf
+        if skip:
+            if p.wd is not None:
+                # every sample gets its downsampled identity straight into `out`; a skipped sample's output is
+                # relu(identity) (ReLU applied here, where the gate is 0), an active one is finished by conv3 in place
+                run_conv(x, p.wd, out, B, Hi, Hi, p.inplanes, Ho, Ho, p.outplanes, 1, p.stride, 0, ldx=p.inplanes,
+                         ldy=p.outplanes, scale=p.sd, shift=p.td, relu=_lib.RELU_WHERE_GATE0, out_mask=m3, mask_groups=1,
+                         impl=self.impl, tag=f"s{p.stage + 1}.down")
+                dst = out
+            else:
+                dst = x                            # in place: skipped samples keep relu(x) == x
+            run_conv(a2, p.w3, dst, B, Ho, Ho, p.width, Ho, Ho, p.outplanes, 1, 1, 0, ldx=ld12, ldy=p.outplanes,
+                     scale=p.s3, shift=p.t3, relu=_lib.RELU_ALL, residual=dst, ldr=p.outplanes, impl=self.impl,
+                     tag=f"s{p.stage + 1}.conv3", **sl)
+            out = dst
         else:
-            res = x
-        # conv3 1x1 + bn3 (+ spatial mask) + identity + relu     laud_resnet.py:131-144
-        run_conv(a2, p.w3, out, B, Ho, Ho, p.width, Ho, Ho, p.outplanes, 1, 1, 0, ldx=ld12, ldy=p.outplanes,
-                 scale=p.s3, shift=p.t3, relu=_lib.RELU_ALL, residual=res, ldr=p.outplanes, impl=self.impl,
-                 tag=f"s{p.stage + 1}.conv3", pre_bias=ws["pb3"] if (sparse_gate and not use_wt) else None,
-                 pre_bias_classes=1 if (sparse_gate and not use_wt) else 0,
-                 bias_t=T.view(-1)[9 * p.width:] if use_wt else None, bias_ld=Tn if use_wt else 0,
-                 pre_bias_ld=p.outplanes if sparse_gate else 0, out_mask=m3, mask_groups=p.g_spatial if m3 is not None else 1,
-                 w_t=p.w3t if (sparse_gate and use_wt) else None, **ck)
+            if p.wd is not None:
+                run_conv(x, p.wd, idbuf, B, Hi, Hi, p.inplanes, Ho, Ho, p.outplanes, 1, p.stride, 0, ldx=p.inplanes,
+                         ldy=p.outplanes, scale=p.sd, shift=p.td, relu=_lib.RELU_NONE, impl=self.impl,
+                         tag=f"s{p.stage + 1}.down")
+                res = idbuf
+            else:
+                res = x
+            # conv3 1x1 + bn3 (+ spatial mask) + identity + relu     laud_resnet.py:131-144
+            run_conv(a2, p.w3, out, B, Ho, Ho, p.width, Ho, Ho, p.outplanes, 1, 1, 0, ldx=ld12, ldy=p.outplanes,
+                     scale=p.s3, shift=p.t3, relu=_lib.RELU_ALL, residual=res, ldr=p.outplanes, impl=self.impl,
+                     tag=f"s{p.stage + 1}.conv3", pre_bias=ws["pb3"] if (sparse_gate and not use_wt) else None,
+                     pre_bias_classes=1 if (sparse_gate and not use_wt) else 0,
+                     bias_t=T.view(-1)[9 * p.width:] if use_wt else None, bias_ld=Tn if use_wt else 0,
+                     pre_bias_ld=p.outplanes if sparse_gate else 0, out_mask=m3, mask_groups=p.g_spatial if m3 is not None else 1,
+                     w_t=p.w3t if (sparse_gate and use_wt) else None, **ck)
         if keep is not None:
             if gate is not None:
                 keep.channel_mask, keep.channel_idx, keep.channel_cnt = gate.mask.clone(), gate.idx.clone(), gate.cnt.clone()
@@ -414,6 +461,7 @@ class ResNetEngine:
             keep.a1 = a1[:B * Hi * Hi * ld12].view(B, Hi, Hi, ld12).clone()
             keep.a2 = a2[:B * Ho * Ho * ld12].view(B, Ho, Ho, ld12).clone()
             keep.out = out[:B * Ho * Ho * p.outplanes].view(B, Ho, Ho, p.outplanes).clone()
+        return out          # the buffer that holds the block output (the input buffer for an in-place layer skip)
 
     @staticmethod
     def _force_channel_gate(gate, mask: torch.Tensor, total: torch.Tensor) -> None:
@@ -458,10 +506,11 @@ class ResNetEngine:
                 keep.append(ko)
             if nvtx:
                 torch.cuda.nvtx.range_push(f"blk{p.index}")
-            self.run_block(p, bufs[cur], bufs[nxt], bufs[idb], B, ws, ko)
+            res_buf = self.run_block(p, bufs[cur], bufs[nxt], bufs[idb], B, ws, ko)
             if nvtx:
                 torch.cuda.nvtx.range_pop()
-            cur = nxt
+            if res_buf is not bufs[cur]:
+                cur = nxt
         last = self.plans[-1]
         feat = last.outplanes
         ncls = m.fc.weight.shape[0]

@@ -119,8 +119,10 @@ struct Sub {               // one (sample, m-group, n-tile) unit of work
 struct Walker {
   int t, t_end, slot, mg, ng, nti, started;
 };
-__device__ __forceinline__ void walker_init(const Plan& pl, Walker& w) {
-  const int base = pl.total_items / (int)gridDim.x, rem = pl.total_items % (int)gridDim.x;
+__device__ __forceinline__ void walker_init(const ConvArgs& a, const Plan& pl, Walker& w) {
+  // with a device-side sample list only the ACTIVE samples' items are partitioned, so every CTA gets its share
+  const int total = a.sample_cnt ? min(__ldg(a.sample_cnt), a.B) * (pl.total_items / a.B) : pl.total_items;
+  const int base = total / (int)gridDim.x, rem = total % (int)gridDim.x;
   const int c = (int)blockIdx.x;
   w.t = c * base + min(c, rem);
   w.t_end = w.t + base + (c < rem ? 1 : 0);
@@ -360,7 +362,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
   tc_fence_after();
   const uint32_t tmem_base = T.tmem_base;
   Walker wk;
-  walker_init(pl, wk);
+  walker_init(a, pl, wk);
   Sub s;
 
   if (warp == TMA_WARP) {
@@ -373,7 +375,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
         // two streams issued by this one thread: activation tiles (one per sub-item and 64-channel chunk, kept one
         // chunk ahead, also across sub-items) and weight tiles (one per chunk and tap)
         Walker wa;
-        walker_init(pl, wa);
+        walker_init(a, pl, wa);
         Sub sa;
         bool a_more = walker_next(a, pl, T, wa, sa);
         while (a_more && sa.cpt == 0) a_more = walker_next(a, pl, T, wa, sa);
@@ -639,7 +641,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
       unsigned char* ring = stg + (size_t)h * pl.ring * SLAB_BYTES;
       const bool has_res = a.residual != nullptr;
       Cursor cs, cl;
-      walker_init(pl, cs.w);
+      walker_init(a, pl, cs.w);
       cs.mt = 0; cs.sl = 0; cs.have = 0;
       cl = cs;
       if (has_res)
@@ -686,7 +688,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
     uint32_t bphase = 0;
     int task = 0;                                                // slab tasks done by this half
     Cursor cur;                                                  // residual prefetcher (elected thread)
-    walker_init(pl, cur.w);
+    walker_init(a, pl, cur.w);
     cur.mt = 0; cur.sl = 0; cur.have = 0;
     int pf = 0;                                                  // slab tasks whose residual load has been issued
     if (pl.omode == OUT_SLAB && a.residual && elected && !pl.dma) {
@@ -764,13 +766,16 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
                 for (int e = 0; e < 32; ++e) v[e] = 0.f;
               }
               if (!(pl.halo && !pvalid)) {                       // (padding column of the padded image: not a pixel)
-                // a gated-off VALID pixel has a finite accumulator, so multiplying by 0 zeroes it exactly
-                const float gate = row_on ? 1.f : 0.f;
+                // a gated-off VALID pixel has a finite accumulator, so multiplying by 0 zeroes it exactly;
+                // RELU_WHERE_GATE0 keeps the value and applies the ReLU only where the gate is 0
+                const bool gate0_relu = a.relu_mode == LAUD_RELU_WHERE_GATE0;
+                const float gate = (row_on || gate0_relu) ? 1.f : 0.f;
+                const bool relu_row = relu_all || (gate0_relu && !row_on);
                 if (has_res) {
-                  if (relu_all) slab_pass<true, true>(v, t_scale, t_shift, c0, srow, sw, p, gate);
+                  if (relu_row) slab_pass<true, true>(v, t_scale, t_shift, c0, srow, sw, p, gate);
                   else slab_pass<true, false>(v, t_scale, t_shift, c0, srow, sw, p, gate);
                 } else {
-                  if (relu_all) slab_pass<false, true>(v, t_scale, t_shift, c0, srow, sw, p, gate);
+                  if (relu_row) slab_pass<false, true>(v, t_scale, t_shift, c0, srow, sw, p, gate);
                   else slab_pass<false, false>(v, t_scale, t_shift, c0, srow, sw, p, gate);
                 }
               }
@@ -833,7 +838,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
                   w[2] = fmaf(w[2], s0.z, h0.z); w[3] = fmaf(w[3], s0.w, h0.w);
                   w[4] = fmaf(w[4], s1.x, h1.x); w[5] = fmaf(w[5], s1.y, h1.y);
                   w[6] = fmaf(w[6], s1.z, h1.z); w[7] = fmaf(w[7], s1.w, h1.w);
-                  if (!row_on) {
+                  if (!row_on && a.relu_mode != LAUD_RELU_WHERE_GATE0) {
 #pragma unroll
                     for (int e = 0; e < 8; ++e) w[e] = 0.f;
                   }
@@ -841,7 +846,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
                   __half2* oh = reinterpret_cast<__half2*>(&o4);
 #pragma unroll
                   for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(w[2 * e], w[2 * e + 1]);
-                  if (relu_all) {
+                  if (relu_all || (a.relu_mode == LAUD_RELU_WHERE_GATE0 && !row_on)) {
                     const __half2 z = __float2half2_rn(0.f);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) oh[e] = __hmax2(oh[e], z);
@@ -966,7 +971,7 @@ bool conv_tma_supported(const ConvArgs& a) {
   if (a.stride != 1 && a.stride != 2) return false;
   if (!((a.ksize == 1 && a.pad == 0) || (a.ksize == 3 && a.pad == 1))) return false;
   if (a.stride == 2 && (a.H_in != 2 * a.H_out || a.W_in != 2 * a.W_out || 2 * a.W_out > 256)) return false;
-  if (a.row_idx || a.pre_bias || a.relu_mode == LAUD_RELU_WHERE_GATE0) return false;
+  if (a.row_idx || a.pre_bias) return false;
   if (a.out_mask && a.mask_groups != 1) return false;
   if (a.k_idx && !(a.wt && aligned16(a.wt))) return false;        // KUNITS layout
   if (a.k_idx && a.n_idx && (a.residual || a.out_mask || (a.n_gran & 1))) return false;

@@ -584,6 +584,46 @@ extern "C" int laud_expand_mask(const uint8_t* mask, int B, int g, int H, int W,
   return check_launch("expand_mask_kernel");
 }
 
+// Layer gate bookkeeping in one launch (one CTA): ordered list of the ACTIVE samples of a [B] gate + the counts the
+// statistics need (ones of the gate broadcast to the H_out x W_out and, dilated, to the H_in x W_in maps: a per-sample
+// gate dilates to itself).  Replaces resize + 2 x expand + 3-kernel compaction for dyn_mode='layer'.
+__global__ void __launch_bounds__(1024) layer_gate_lists_kernel(const uint8_t* __restrict__ gate, int B, int hw_out,
+                                                                int hw_in, int* __restrict__ counts4,
+                                                                int* __restrict__ rows_out, int* __restrict__ count_out) {
+  __shared__ int wsum[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int base = 0;
+  for (int b0 = 0; b0 < B; b0 += 1024) {
+    const int b = b0 + tid;
+    const int f = (b < B && gate[b]) ? 1 : 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) wsum[warp] = __popc(bal);
+    __syncthreads();
+    int off = base, tot = 0;
+    for (int w = 0; w < 32; ++w) {
+      if (w < warp) off += wsum[w];
+      tot += wsum[w];
+    }
+    if (f) rows_out[off + __popc(bal & ((1u << lane) - 1))] = b;
+    base += tot;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    *count_out = base;
+    if (counts4) {
+      counts4[2] += base * hw_out;
+      counts4[3] += base * hw_in;
+    }
+  }
+}
+
+extern "C" int laud_layer_gate_lists(const uint8_t* gate, int B, int hw_out, int hw_in, int32_t* counts4,
+                                     int32_t* rows_out, int32_t* count_out, void* stream) {
+  LAUD_REQUIRE(gate && rows_out && count_out && B > 0, "laud_layer_gate_lists: bad arguments");
+  layer_gate_lists_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(gate, B, hw_out, hw_in, counts4, rows_out, count_out);
+  return check_launch("layer_gate_lists_kernel");
+}
+
 extern "C" int laud_compact_rows(const uint8_t* gate, int B, int g, int HW, int32_t* rows_out,
                                  int32_t* count_out, int32_t* block_ws, void* stream) {
   LAUD_REQUIRE(gate && rows_out && count_out && block_ws && B > 0 && g > 0 && HW > 0,

@@ -101,8 +101,9 @@ class Bottleneck(nn.Module):
         xin = to_nhwc_f16(x)
         out = torch.empty((B, plan.H_out, plan.H_out, plan.outplanes), dtype=torch.float16, device=x.device)
         idb = torch.empty_like(out)
-        eng.run_block(plan, xin.view(-1), out.view(-1), idb.view(-1), B, ws, keep, forced_channel_mask,
-                      forced_spatial_mask)
+        res = eng.run_block(plan, xin.view(-1), out.view(-1), idb.view(-1), B, ws, keep, forced_channel_mask,
+                            forced_spatial_mask)
+        out = res[:out.numel()].view(out.shape)      # an in-place layer skip returns the (converted) input buffer
         stats = torch.empty(6, dtype=torch.float32, device=x.device)
         _lib.check(_lib.lib().laud_forward_stats(_lib.ptr(ws["counts"]), _lib.ptr(ws["consts"]), 1, 0, 0, 0,
                                                  _lib.ptr(stats), _lib.stream_ptr()), "laud_forward_stats")
@@ -127,6 +128,7 @@ class _SoloEngine(ResNetEngine):
         self.model = None
         self.impl = _lib.CONV_AUTO
         self.channel_exec = os.environ.get("LAUD_CHANNEL_EXEC", "dense")
+        self.layer_exec = os.environ.get("LAUD_LAYER_EXEC", "skip")
         self._ws = {}
         dev = blk.conv1.weight.device
         p = BlockPlan(index=0, stage=0, inplanes=blk.conv1.weight.shape[1], width=blk.conv1.weight.shape[0],
@@ -166,6 +168,8 @@ class _SoloEngine(ResNetEngine):
                 m3=torch.empty(B * p.g_spatial * hw, dtype=torch.uint8, device=dev),
                 m2=torch.empty(B * p.g_spatial * hw, dtype=torch.uint8, device=dev),
                 m1=torch.empty(B * p.g_spatial * hw, dtype=torch.uint8, device=dev),
+                srows=torch.empty((B,), **i32), scnt=torch.zeros((1,), **i32), cws=torch.zeros((64,), **i32),
+                lidx=torch.empty((B * p.g_spatial,), **i32), lcnt=torch.empty((B,), **i32),
                 counts=torch.zeros((1, 4), **i32))
             consts = self.stats_consts.clone()
             S = min(p.mask_size, p.H_in)

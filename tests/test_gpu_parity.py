@@ -516,6 +516,26 @@ def test_network_free_running_vs_golden(cuda_lib, name, channel_exec):
     assert frac <= 2e-3, f"{name}: {excused}/{total} decisions flipped (fp16 upstream noise budget exceeded)"
 
 
+@pytest.mark.parametrize("layer_exec", ["skip", "mask"])
+def test_layer_network_serving_path_matches_golden(cuda_lib, layer_exec):
+    """dyn_mode='layer' without per-block capture (the serving path: one-launch gate bookkeeping, active-sample work
+    lists, in-place block outputs) and masked-dense: logits and the reference's statistics vs the golden run."""
+    cfg, sd, x, z = load_case("tiny_layer")
+    model = _model(cfg, sd)
+    model._engine.layer_exec = layer_exec
+    with torch.no_grad():
+        logits, r3, r2, r1, rc, perc, flops = model(x.to(DEV), 1.0)
+        again = model.forward_logits(x.to(DEV)).clone()
+    assert torch.equal(logits, again), "the forward must be repeatable (in-place block outputs)"
+    err = _rel_err(logits, torch.from_numpy(z["logits"]))
+    assert err <= 5e-3, f"logits error {err:.2e}"
+    # the seeded fixture has no within-noise gate flips (test_network_free_running_vs_golden): statistics are exact
+    np.testing.assert_array_equal(np.concatenate([t.cpu().numpy() for t in r3]),
+                                  np.concatenate([z[f"rho3.{s}"] for s in range(4)]))
+    np.testing.assert_allclose(perc.cpu().numpy(), z["flops_perc"], rtol=1e-6)
+    np.testing.assert_allclose(flops.item(), float(z["flops"]), rtol=1e-6)
+
+
 def test_sharding_invariance(cuda_lib):
     """Eval-mode samples are independent: logits of a batch == logits of its halves."""
     cfg, sd, x, z = load_case("tiny_channel")
