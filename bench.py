@@ -326,6 +326,16 @@ def run_graft(args):
         "mean_channel_density": sum(rho_c) / len(rho_c),
     }
 
+    dynet = None
+    dpath = os.path.join(ROOT, "profiles", "dynet_prediction_b200.json")
+    if os.path.exists(dpath):        # the reference's own analytic latency model, evaluated in the build container
+        dj = json.load(open(dpath))
+        key = "channel_2222_density_0.587_measured_mean"
+        dynet = {"predicted_images_per_s_per_gpu": dj[key]["images_per_s"],
+                 "predicted_static_dense_images_per_s_per_gpu": dj["static_dense"]["images_per_s"],
+                 "measured_images_per_s_per_gpu": value / world, "hardware_parameters": dj["hardware_parameters"],
+                 "scope": dj["network"], "caveat": dj["caveat"], "source": "profiles/dynet_prediction_b200.json "
+                 "(scripts/make_dynet_prediction.py: DyNetSimulator imported unchanged from the reference)"}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         v, cores, ratio = cpu_oracle_rate(sd, args.cpu_sample, 2)
@@ -348,7 +358,7 @@ def run_graft(args):
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": graphed.launches * args.steps, "launches_per_step": graphed.launches,
             "eager_launches_per_step": launches_per_step, "conv_paths": _lib.conv_path_counts(),
-            "clocks": clocks, "roofline": roof, "net": net, "cpu_baseline": cpu,
+            "clocks": clocks, "roofline": roof, "net": net, "dynet_simulator": dynet, "cpu_baseline": cpu,
         }) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
