@@ -243,12 +243,35 @@ int laud_nhwc_f16_to_nchw_f32(const void* src, int lds, int B, int C, int H, int
                               float* dst, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * (a9) LAUD-RegNet-Y operators (models/laud_regnet.py).  The 1x1 convolutions a / c / proj, the maskers and the head
+ * run on the entry points above.
+ *   laud_regnet_stem_forward     SimpleStemIN conv3x3/2 + BN + ReLU (:59-71): x fp16 NCHW [B,3,H,W] -> y fp16 NHWC
+ *                                [B,H/2,W/2,C0]; w fp16 [C0,3,3,3]
+ *   laud_grouped_conv3x3_forward the transform's conv b (:118-120,188): grouped 3x3 (pad 1, stride 1|2) + BN + ReLU,
+ *                                w fp16 [C][9][group_width] (out channel, tap, in channel of its group); optional channel
+ *                                gate ch_mask u8 [B, C/mask_gran] applied to the input (= conv a's gated output, :183)
+ *                                and to the output (:189)
+ *   laud_se_gate                 SqueezeExcitation gate (:128-132,194) from the pooled features fp32 [B,C]:
+ *                                gate = sigmoid(W2 relu(W1 p + b1) + b2)  (p and gate multiplied by ch_mask if given)
+ *   laud_scale_channels          x[b,p,c] *= gate[b,c]  (fp16 NHWC, in place)
+ * ------------------------------------------------------------------------- */
+int laud_regnet_stem_forward(const void* x_nchw, int B, int H, int W, const void* w, int C0, const float* scale,
+                             const float* shift, void* y_nhwc, void* stream);
+int laud_grouped_conv3x3_forward(const void* x, int B, int H_in, int W_in, int C, int stride, const void* w,
+                                 int group_width, const float* scale, const float* shift, const uint8_t* ch_mask,
+                                 int mask_gran, void* y, void* stream);
+int laud_se_gate(const float* pooled, int B, int C, const float* w1, const float* b1, int S, const float* w2,
+                 const float* b2, const uint8_t* ch_mask, int mask_gran, float* gate, void* stream);
+int laud_scale_channels(void* x, int B, int HW, int C, const float* gate, void* stream);
+
+/* ---------------------------------------------------------------------------
  * Forward statistics.  Reproduces, in one launch and in the reference's fp32
  * evaluation order, the per-block densities / flops_perc / flops that
  * Bottleneck.forward and ResNet.forward thread through the network
  * (laud_resnet.py:112-162, 321-356).
  *   counts i32 [n_blocks,4]: ones in (channel mask, mask_conv3 small, mask_conv2, mask_conv1)
- *   consts i64 [n_blocks,12]: see laud_stats_consts_t in laudnet_b200/_stats.py
+ *   consts i64 [n_blocks,12]: masker MACs (channel, spatial), c1, c2, c3, projection MACs, the four density
+ *          denominators, flags (1 channel gate, 2 spatial gate, 4 RegNet accumulation order), SE flops
  *   out    f32 [n_blocks,5 + 1]: rho3,rho2,rho1,rho_c,flops_perc per block, then total flops
  * ------------------------------------------------------------------------- */
 int laud_forward_stats(const int32_t* counts, const int64_t* consts, int n_blocks,

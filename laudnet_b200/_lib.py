@@ -69,6 +69,10 @@ SIGNATURES = {
     "laud_conv_forward": ([C.POINTER(ConvDesc), _i, _vp], _i),
     "laud_gate_inactive": ([_u8p, _i, _i, _i, _vp, _vp], _i),
     "laud_channel_consts_fold": ([_vp, _i, _i, _i, _i32p, _i32p, _i, _i, _i, _fp, _fp, _vp], _i),
+    "laud_regnet_stem_forward": ([_vp, _i, _i, _i, _vp, _i, _fp, _fp, _vp, _vp], _i),
+    "laud_grouped_conv3x3_forward": ([_vp, _i, _i, _i, _i, _i, _vp, _i, _fp, _fp, _u8p, _i, _vp, _vp], _i),
+    "laud_se_gate": ([_fp, _i, _i, _fp, _fp, _i, _fp, _fp, _u8p, _i, _fp, _vp], _i),
+    "laud_scale_channels": ([_vp, _i, _i, _i, _fp, _vp], _i),
     "laud_stem_forward": ([_vp, _i, _i, _i, _vp, _i, _fp, _fp, _vp, _vp], _i),
     "laud_head_forward": ([_vp, _i, _i, _i, _vp, _fp, _i, _fp, _fp, _vp], _i),
     "laud_nchw_to_nhwc_f16": ([_vp, _i, _i, _i, _i, _i, _vp, _i, _vp], _i),

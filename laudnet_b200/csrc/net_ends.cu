@@ -469,15 +469,33 @@ __global__ void forward_stats_kernel(const int* __restrict__ counts, const long 
     sparse = __fadd_rn(sparse, __fmul_rn(__fmul_rn((float)k[3], __fmul_rn(rc, rc)), r2));
     sparse = __fadd_rn(sparse, __fmul_rn(__fmul_rn((float)k[4], rc), r3));
     long long dense = m + k[2] + k[3] + k[4];
-    if (k[5]) {
-      sparse = __fadd_rn(sparse, (float)k[5]);
-      dense += k[5];
-    }
-    if (!flops_is_tensor) {
-      flops = __fadd_rn((float)flops_int, sparse);
-      flops_is_tensor = true;
+    const bool regnet_order = (k[10] & 4) != 0;
+    if (regnet_order) {
+      // laud_regnet.py: flops += se_flops (:195), flops += sparse of the transform (:203), then the block adds the
+      // projection to sparse, dense AND flops separately (:285-288)
+      if (!flops_is_tensor) flops_int += k[11]; else flops = __fadd_rn(flops, (float)k[11]);
+      if (!flops_is_tensor) {
+        flops = __fadd_rn((float)flops_int, sparse);
+        flops_is_tensor = true;
+      } else {
+        flops = __fadd_rn(flops, sparse);
+      }
+      if (k[5]) {
+        sparse = __fadd_rn(sparse, (float)k[5]);
+        dense += k[5];
+        flops = __fadd_rn(flops, (float)k[5]);
+      }
     } else {
-      flops = __fadd_rn(flops, sparse);
+      if (k[5]) {
+        sparse = __fadd_rn(sparse, (float)k[5]);
+        dense += k[5];
+      }
+      if (!flops_is_tensor) {
+        flops = __fadd_rn((float)flops_int, sparse);
+        flops_is_tensor = true;
+      } else {
+        flops = __fadd_rn(flops, sparse);
+      }
     }
     float* o = out + (size_t)i * 5;
     o[0] = r3; o[1] = r2; o[2] = r1; o[3] = rc;

@@ -229,6 +229,92 @@ def calibrate_resnet(sd: Dict[str, torch.Tensor], geoms, images: torch.Tensor, s
     return sd
 
 
+def calibrate_regnet(sd: Dict[str, torch.Tensor], geoms, images: torch.Tensor, seed: int,
+                     channel_rate: float = 0.6, spatial_rate: float = 0.4) -> Dict[str, torch.Tensor]:
+    """`calibrate_resnet` for the LAUD-RegNet-Y trunk (reference laud_regnet.py): one sequential pass that sets every
+    BatchNorm's running statistics from data and shifts every masker's keep bias to the requested firing rate.
+    `geoms`: objects with the attributes of oracle.RegBlockGeom."""
+    import torch.nn.functional as F
+    dev = images.device
+    W = lambda k: sd[k].to(dev)
+    with torch.no_grad():
+        z = F.conv2d(images.float(), W("stem.0.weight"), stride=2, padding=1)
+        _set_bn_from_data(sd, "stem.1.", z, seed)
+        x = torch.relu(_bn_eval(z, sd, "stem.1."))
+        for g in geoms:
+            p = g.prefix + "f."
+            b = x.shape[0]
+            cmask = None
+            m3 = None
+            if g.dyn_mode in ("channel", "both"):
+                mp = p + "masker_channel."
+                G = g.groups_channel
+                if g.masker_kind == "MLP":
+                    pooled = x.mean(dim=(2, 3))
+                    if g.masker_layers == 2:
+                        h = torch.relu(F.linear(pooled, W(mp + "conv.0.weight"), W(mp + "conv.0.bias")))
+                        bias_key = mp + "conv.2.bias"
+                        logits = F.linear(h, W(mp + "conv.2.weight"), W(bias_key))
+                    else:
+                        bias_key = mp + "conv.bias"
+                        logits = F.linear(pooled, W(mp + "conv.weight"), W(bias_key))
+                else:
+                    zc = F.conv2d(x, W(mp + "conv.0.weight"))
+                    _set_bn_from_data(sd, mp + "conv.1.", zc, seed)
+                    pooled = torch.relu(_bn_eval(zc, sd, mp + "conv.1.")).mean(dim=(2, 3))
+                    bias_key = mp + "linear.bias"
+                    logits = F.linear(pooled, W(mp + "linear.weight"), W(bias_key))
+                margin = logits[:, :G] - logits[:, G:]
+                delta = calibrate_two_way_bias(margin, channel_rate, per_group=True).to(dev)
+                nb = sd[bias_key].clone()
+                nb[:G] -= delta.cpu()
+                sd[bias_key] = nb
+                cmask = ((margin - delta) >= 0).float()
+                cmask = cmask.repeat_interleave(g.w_b // G, dim=1).view(b, g.w_b, 1, 1)
+            if g.dyn_mode in ("spatial", "both"):
+                wk, bk = p + "masker_spatial.conv.weight", p + "masker_spatial.conv.bias"
+                q = F.adaptive_avg_pool2d(x, g.mask_size) if g.mask_size < x.shape[2] else x
+                logits = F.conv2d(q, W(wk), W(bk))
+                gs = logits.shape[1] // 2
+                margin = logits[:, :gs] - logits[:, gs:]
+                flat = margin.permute(0, 2, 3, 1).reshape(-1, gs)
+                delta = calibrate_two_way_bias(flat, spatial_rate, per_group=True).to(dev)
+                nb = sd[bk].clone()
+                nb[:gs] -= delta.cpu()
+                sd[bk] = nb
+                small = ((margin - delta.view(1, gs, 1, 1)) >= 0).float()
+                S = small.shape[-1]
+                idx = torch.div(torch.arange(g.output_size, device=dev) * S, g.output_size, rounding_mode="floor")
+                m3 = small[:, :, idx][:, :, :, idx]
+                if gs > 1 and gs != g.w_out:
+                    m3 = m3.repeat_interleave(g.w_out // gs, dim=1)
+            za = F.conv2d(x, W(p + "a.0.weight"))
+            _set_bn_from_data(sd, p + "a.1.", za, seed)
+            a1 = torch.relu(_bn_eval(za, sd, p + "a.1."))
+            if cmask is not None:
+                a1 = a1 * cmask
+            zb = F.conv2d(a1, W(p + "b.0.weight"), stride=g.stride, padding=1, groups=g.conv_groups)
+            _set_bn_from_data(sd, p + "b.1.", zb, seed)
+            a2 = torch.relu(_bn_eval(zb, sd, p + "b.1."))
+            if cmask is not None:
+                a2 = a2 * cmask
+            sq = a2.mean(dim=(2, 3), keepdim=True)
+            sq = torch.relu(F.conv2d(sq, W(p + "se.fc1.weight"), W(p + "se.fc1.bias")))
+            a2 = a2 * torch.sigmoid(F.conv2d(sq, W(p + "se.fc2.weight"), W(p + "se.fc2.bias")))
+            zc3 = F.conv2d(a2, W(p + "c.0.weight"))
+            _set_bn_from_data(sd, p + "c.1.", zc3, seed)
+            y = _bn_eval(zc3, sd, p + "c.1.")
+            if m3 is not None:
+                y = y * m3
+            ident = x
+            if g.has_proj:
+                zd = F.conv2d(x, W(g.prefix + "proj.0.weight"), stride=g.stride)
+                _set_bn_from_data(sd, g.prefix + "proj.1.", zd, seed)
+                ident = _bn_eval(zd, sd, g.prefix + "proj.1.")
+            x = torch.relu(ident + y)
+    return sd
+
+
 # --------------------------------------------------------------------------
 # Workload construction shared by bench.py, the tests and smoke().
 # --------------------------------------------------------------------------

@@ -367,3 +367,205 @@ def dense_flops(cfg: ResNetCfg) -> int:
             total += g.inplanes * g.outplanes * g.output_size ** 2
     feat = int(512 * cfg.width_mult) * 4
     return total + feat * (s // 32) ** 2 + feat * cfg.num_classes
+
+
+# ==========================================================================
+# LAUD-RegNet-Y (models/laud_regnet.py) - same operators on the RegNet trunk
+# ==========================================================================
+@dataclass
+class RegNetCfg:
+    """Constructor arguments of LAD_RegNet (laud_regnet.py:468-488) with the per-stage block parameters spelled out
+    (the reference derives them with BlockParams.from_init_params, :374-446; `laudnet_b200.laud_regnet.stage_params`
+    restates that derivation and tests compare it with the values stored in the golden fixtures)."""
+    widths: Sequence[int] = (64, 144, 320, 784)            # RegNetY-800MF (SURVEY appendix B.2)
+    depths: Sequence[int] = (1, 3, 8, 2)
+    group_widths: Sequence[int] = (16, 16, 16, 16)
+    strides: Sequence[int] = (2, 2, 2, 2)
+    bottleneck_multiplier: float = 1.0
+    se_ratio: float = 0.25
+    stem_width: int = 32
+    input_size: int = 224
+    num_classes: int = 1000
+    dyn_mode: Sequence[str] = ("spatial",) * 4
+    channel_dyn_granularity: Sequence[int] = (1, 1, 1, 1)
+    spatial_mask_channel_group: Sequence[int] = (1, 1, 1, 1)
+    mask_spatial_granularity: Sequence[int] = (4, 4, 2, 1)
+    channel_masker: Sequence[str] = ("MLP",) * 4
+    channel_masker_layers: Sequence[int] = (2, 2, 2, 2)
+    reduction_ratio: Sequence[int] = (16, 16, 16, 16)
+
+    def kwargs(self) -> dict:
+        return dict(
+            input_size=self.input_size, num_classes=self.num_classes, stem_width=self.stem_width,
+            dyn_mode=list(self.dyn_mode), channel_dyn_granularity=list(self.channel_dyn_granularity),
+            spatial_mask_channel_group=list(self.spatial_mask_channel_group),
+            mask_spatial_granularity=list(self.mask_spatial_granularity),
+            channel_masker=list(self.channel_masker), channel_masker_layers=list(self.channel_masker_layers),
+            reduction_ratio=list(self.reduction_ratio))
+
+
+@dataclass
+class RegBlockGeom:
+    """Static geometry of one ResBottleneckBlock (laud_regnet.py:74-155, 221-279)."""
+    prefix: str                  # "trunk_output.block{s}.block{s}-{i}."
+    w_in: int
+    w_b: int
+    w_out: int
+    conv_groups: int             # groups of the 3x3 conv = w_b // group_width
+    stride: int
+    output_size: int
+    mask_size: int
+    dyn_mode: str
+    groups_channel: int
+    groups_spatial: int
+    masker_kind: str
+    masker_layers: int
+    has_proj: bool
+    se_width: int
+
+
+def regnet_geometry(cfg: RegNetCfg) -> List[RegBlockGeom]:
+    """Blocks in execution order (laud_regnet.py:521-561 builds the stages, :326-346 the blocks of a stage)."""
+    geoms: List[RegBlockGeom] = []
+    w_prev = cfg.stem_width
+    for s in range(len(cfg.widths)):
+        w_out, gw = cfg.widths[s], cfg.group_widths[s]
+        out_size = cfg.input_size // (2 ** (s + 2))
+        for i in range(cfg.depths[s]):
+            w_in = w_prev if i == 0 else w_out
+            stride = cfg.strides[s] if i == 0 else 1
+            w_b = int(round(w_out * cfg.bottleneck_multiplier))
+            geoms.append(RegBlockGeom(
+                prefix=f"trunk_output.block{s + 1}.block{s + 1}-{i}.", w_in=w_in, w_b=w_b, w_out=w_out,
+                conv_groups=w_b // gw, stride=stride, output_size=out_size,
+                mask_size=out_size // cfg.mask_spatial_granularity[s], dyn_mode=cfg.dyn_mode[s],
+                groups_channel=w_b // cfg.channel_dyn_granularity[s],
+                groups_spatial=cfg.spatial_mask_channel_group[s], masker_kind=cfg.channel_masker[s],
+                masker_layers=cfg.channel_masker_layers[s], has_proj=(w_in != w_out) or stride != 1,
+                se_width=int(round(cfg.se_ratio * w_in))))
+        w_prev = w_out
+    return geoms
+
+
+def squeeze_excitation(x: Tensor, sd: Dict[str, Tensor], p: str) -> Tensor:
+    """torchvision.ops.misc.SqueezeExcitation as used at laud_regnet.py:128-132,194:
+    x * sigmoid(fc2(relu(fc1(avgpool(x))))), fc1/fc2 are 1x1 convolutions with bias."""
+    s = x.mean(dim=(2, 3), keepdim=True)
+    s = torch.relu(F.conv2d(s, sd[p + "fc1.weight"], sd[p + "fc1.bias"]))
+    s = torch.sigmoid(F.conv2d(s, sd[p + "fc2.weight"], sd[p + "fc2.bias"]))
+    return x * s
+
+
+def regnet_block_forward(x: Tensor, sd: Dict[str, Tensor], g: RegBlockGeom, trace: Optional[BlockTrace] = None,
+                         forced_channel_mask: Optional[Tensor] = None, forced_spatial_mask: Optional[Tensor] = None):
+    """BottleneckTransform.forward + ResBottleneckBlock.forward (laud_regnet.py:157-217, 281-295), eval mode.
+    Returns (out, rho3, rho2, rho1, rho_c, sparse_flops, dense_flops, se_flops, sparse_flops_of_the_transform,
+    projection_flops) - the last two because the reference adds them to `flops` separately."""
+    p = g.prefix + "f."
+    one = torch.tensor(1.0)
+    use_c = g.dyn_mode in ("channel", "both")
+    use_s = g.dyn_mode in ("spatial", "both")
+    cm = sm3 = None
+    rho_c = rho1 = rho2 = rho3 = one
+    cflops = sflops = 0
+    if use_c:                                                       # :161,:169
+        if g.masker_kind == "MLP":
+            cm, rho_c, cflops, clog = masker_channel_mlp(x, sd, p + "masker_channel.", g.masker_layers)
+        else:
+            cm, rho_c, cflops, clog = masker_channel_conv_linear(x, sd, p + "masker_channel.")
+        if forced_channel_mask is not None:
+            cm = forced_channel_mask.to(torch.float32)
+            rho_c = cm.mean()
+        if trace is not None:
+            trace.channel_mask, trace.channel_logits = cm, clog
+    if use_s:                                                       # :165,:170,:172-177
+        small, rho3, sflops, slog = masker_spatial(
+            x, sd[p + "masker_spatial.conv.weight"], sd[p + "masker_spatial.conv.bias"], g.mask_size)
+        if forced_spatial_mask is not None:
+            small = forced_spatial_mask.to(torch.float32)
+            rho3 = small.mean()
+        sm3 = nearest_resize(small, g.output_size)
+        sm2 = expand_mask(sm3, 1, 0)
+        rho2 = sm2.float().mean()
+        sm1 = expand_mask(sm2, g.stride, 1)
+        rho1 = sm1.float().mean()
+        if trace is not None:
+            trace.spatial_mask_small, trace.spatial_logits = small, slog
+            trace.mask_conv3, trace.mask_conv2, trace.mask_conv1 = sm3, sm2, sm1
+    sparse = cflops + sflops
+    dense = cflops + sflops
+
+    a1 = torch.relu(_bn(F.conv2d(x, sd[p + "a.0.weight"]), sd, p + "a.1."))          # :182
+    if use_c:
+        a1 = apply_channel_mask(a1, cm)                                               # :183 (mask AFTER bn+relu)
+    hw_in = a1.shape[2] * a1.shape[3]
+    c1 = g.w_in * g.w_b
+    dense = dense + c1 * hw_in
+    sparse = sparse + c1 * hw_in * rho_c * rho1                                       # :186
+
+    a2 = torch.relu(_bn(F.conv2d(a1, sd[p + "b.0.weight"], stride=g.stride, padding=1, groups=g.conv_groups),
+                        sd, p + "b.1."))                                              # :188
+    if use_c:
+        a2 = apply_channel_mask(a2, cm)                                               # :189
+    hw = a2.shape[2] * a2.shape[3]
+    c2 = g.w_b * g.w_b * 9 // g.conv_groups
+    dense = dense + c2 * hw
+    sparse = sparse + c2 * hw * rho_c ** 2 * rho2                                     # :192
+
+    a2s = squeeze_excitation(a2, sd, p + "se.")                                       # :194 (pools the DENSE a2)
+    se_flops = g.w_b * g.se_width * 2                                                 # :151,:195
+
+    y = _bn(F.conv2d(a2s, sd[p + "c.0.weight"]), sd, p + "c.1.")                      # :197
+    if use_s:
+        y = apply_spatial_mask(y, sm3)                                                # :198
+    c3 = g.w_b * g.w_out
+    dense = dense + c3 * hw
+    sparse = sparse + c3 * hw * rho_c * rho3                                          # :201
+
+    sparse_t = sparse                                                                 # what the transform returns
+    ds = 0
+    if g.has_proj:                                                                    # :284-288
+        ident = _bn(F.conv2d(x, sd[g.prefix + "proj.0.weight"], stride=g.stride), sd, g.prefix + "proj.1.")
+        ds = g.w_in * g.w_out * hw
+        sparse = sparse + ds
+        dense = dense + ds
+    else:
+        ident = x
+    out = torch.relu(ident + y)                                                       # :295
+    if trace is not None:
+        trace.x, trace.a1, trace.a2, trace.out = x, a1, a2s, out
+    return out, rho3, rho2, rho1, rho_c, sparse, dense, se_flops, sparse_t, ds
+
+
+def regnet_stem_forward(x: Tensor, sd: Dict[str, Tensor]) -> Tuple[Tensor, int]:
+    """SimpleStemIN: conv3x3/2 -> BN -> ReLU (laud_regnet.py:59-71, 574-577)."""
+    z = torch.relu(_bn(F.conv2d(x, sd["stem.0.weight"], stride=2, padding=1), sd, "stem.1."))
+    return z, x.shape[1] * z.shape[1] * z.shape[2] * z.shape[3] * 9
+
+
+def regnet_forward(sd: Dict[str, Tensor], cfg: RegNetCfg, x: Tensor, traces: Optional[List[BlockTrace]] = None):
+    """LAD_RegNet.forward (laud_regnet.py:574-613): the reference's 7-tuple."""
+    feat, flops = regnet_stem_forward(x, sd)
+    per_stage = {k: [[] for _ in range(4)] for k in ("r3", "r2", "r1", "rc")}
+    perc: List[Tensor] = []
+    for g in regnet_geometry(cfg):
+        tr = BlockTrace() if traces is not None else None
+        feat, r3, r2, r1, rc, sparse, dense, se_flops, sparse_t, ds = regnet_block_forward(feat, sd, g, tr)
+        s = int(g.prefix.split(".")[1][5:]) - 1
+        for key, val in (("r3", r3), ("r2", r2), ("r1", r1), ("rc", rc)):
+            per_stage[key][s].append(val.reshape(1))
+        flops = flops + se_flops                                                      # :195 (before the sparse flops)
+        flops = flops + sparse_t                                                      # :203
+        if ds:
+            flops = flops + ds                                                        # :288
+        perc.append((sparse / dense).reshape(1))
+        if traces is not None:
+            traces.append(tr)
+    c = feat.shape[1]
+    pooled = feat.mean(dim=(2, 3))
+    flops = flops + c                                                                 # :596
+    logits = F.linear(pooled, sd["fc.weight"], sd["fc.bias"])
+    flops = flops + c * logits.shape[1]                                               # :602
+    cat = lambda lst: [torch.cat(v) for v in lst]
+    return (logits, cat(per_stage["r3"]), cat(per_stage["r2"]), cat(per_stage["r1"]), cat(per_stage["rc"]),
+            torch.cat(perc), flops)

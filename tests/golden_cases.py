@@ -34,6 +34,51 @@ CASES = {
 }
 
 
+# LAUD-RegNet-Y cases: (design-space parameters of BlockParams.from_init_params, cfg overrides, batch, seed).  The stage
+# widths / depths the reference derives from the parameters are stored in the fixture and compared with
+# laudnet_b200.laud_regnet.stage_params by the tests.
+REGNET_CASES = {
+    "tiny_regnet_spatial": (dict(depth=6, w_0=16, w_a=24.0, w_m=2.0, group_width=8),
+                            dict(input_size=64, num_classes=24, stem_width=16, dyn_mode=("spatial",) * 4,
+                                 mask_spatial_granularity=(4, 2, 2, 1)), 4, 21),
+    "tiny_regnet_both": (dict(depth=6, w_0=16, w_a=24.0, w_m=2.0, group_width=8),
+                         dict(input_size=64, num_classes=24, stem_width=16,
+                              dyn_mode=("both", "channel", "spatial", "both"), channel_dyn_granularity=(2, 4, 1, 8),
+                              spatial_mask_channel_group=(1, 1, 2, 1), mask_spatial_granularity=(2, 2, 2, 1),
+                              channel_masker=("MLP", "conv_linear", "MLP", "MLP"), channel_masker_layers=(2, 2, 1, 1),
+                              reduction_ratio=(16, 2, 16, 16)), 3, 22),
+}
+
+
+def regnet_cfg(name, widths, depths, group_widths):
+    params, over, batch, seed = REGNET_CASES[name]
+    return O.RegNetCfg(widths=tuple(widths), depths=tuple(depths), group_widths=tuple(group_widths),
+                       strides=(2,) * len(widths), se_ratio=0.25, **over)
+
+
+def regnet_model(name, cfg):
+    from laudnet_b200.laud_regnet import BlockParams, LAD_RegNet
+    params = REGNET_CASES[name][0]
+    bp = BlockParams.from_init_params(se_ratio=0.25, **params)
+    return LAD_RegNet(bp, **cfg.kwargs())
+
+
+def load_regnet_case(name):
+    """-> (cfg, state_dict, x, golden npz dict) for a LAUD-RegNet-Y fixture."""
+    params, over, batch, seed = REGNET_CASES[name]
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    cfg = regnet_cfg(name, z["stage_widths"].tolist(), z["stage_depths"].tolist(), z["stage_group_widths"].tolist())
+    m = regnet_model(name, cfg)
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    sd = synth.synth_state_dict(shapes, int(z["seed"]))
+    for k in z.files:
+        if k.startswith("sd."):
+            sd[k[3:]] = torch.from_numpy(z[k])
+    assert state_dict_digest(sd) == z["sd_sha256"].tobytes(), f"{name}: regenerated state_dict differs from the fixture's"
+    x = torch.from_numpy(z["x"].astype(np.float32))
+    return cfg, sd, x, z
+
+
 def state_dict_digest(sd) -> bytes:
     h = hashlib.sha256()
     for k in sorted(sd):

@@ -573,3 +573,154 @@ def test_resnet50_spatial_bs8_full_size(cuda_lib):
         assert torch.all(m1[:, :, ::s, ::s] >= m2)
         out = ko.out.float()                      # [B,H,W,C]
         assert torch.isfinite(out).all() and (out >= 0).all()
+
+
+# =========================================================================== LAUD-RegNet-Y (laud_regnet.py)
+from tests.golden_cases import REGNET_CASES, load_regnet_case, regnet_model     # noqa: E402
+
+
+def _regnet(name):
+    cfg, sd, x, z = load_regnet_case(name)
+    m = regnet_model(name, cfg)
+    m.load_state_dict(sd, strict=True)
+    return cfg, sd, x, z, m.to(DEV).eval()
+
+
+@pytest.mark.parametrize("B,size,C0", [(2, 64, 16), (1, 224, 32), (3, 40, 24)])
+def test_regnet_stem_vs_oracle(cuda_lib, B, size, C0):
+    gen = torch.Generator().manual_seed(7 * B + size + C0)
+    x = torch.randn(B, 3, size, size, generator=gen).half()
+    w = (torch.randn(C0, 3, 3, 3, generator=gen) * 0.2).half()
+    sd = {"stem.0.weight": w.float(), "stem.1.weight": torch.randn(C0, generator=gen) * 0.2 + 1.0,
+          "stem.1.bias": torch.randn(C0, generator=gen) * 0.5, "stem.1.running_mean": torch.randn(C0, generator=gen) * 0.5,
+          "stem.1.running_var": torch.rand(C0, generator=gen) * 1.5 + 0.5}
+    ref, _ = O.regnet_stem_forward(x.float(), sd)
+    scale = sd["stem.1.weight"] / torch.sqrt(sd["stem.1.running_var"] + 1e-5)
+    shift = sd["stem.1.bias"] - sd["stem.1.running_mean"] * scale
+    y = torch.full((B, size // 2, size // 2, C0), float("nan"), dtype=torch.float16, device=DEV)
+    xd, wd, sc, sh = x.to(DEV), w.to(DEV), scale.to(DEV).contiguous(), shift.to(DEV).contiguous()
+    _lib.check(cuda_lib.laud_regnet_stem_forward(xd.data_ptr(), B, size, size, wd.data_ptr(), C0, sc.data_ptr(),
+                                                 sh.data_ptr(), y.data_ptr(), _lib.stream_ptr()), "laud_regnet_stem_forward")
+    torch.cuda.synchronize()
+    assert _rel_err(y.float().permute(0, 3, 1, 2), ref) <= ACT_TOL
+
+
+@pytest.mark.parametrize("B,H,C,gw,stride,gran", [(2, 8, 32, 8, 1, 0), (3, 14, 64, 16, 2, 0), (2, 6, 48, 16, 1, 4),
+                                                  (1, 10, 40, 8, 2, 8)])
+def test_grouped_conv3x3_vs_torch(cuda_lib, B, H, C, gw, stride, gran):
+    """conv b of the RegNet transform (laud_regnet.py:118-120,188-189): grouped 3x3 + BN + ReLU, optional channel gate
+    applied to its input and output, against F.conv2d(groups=...) on fp16-representable data."""
+    gen = torch.Generator().manual_seed(B * 100 + H + C + gw)
+    x = torch.randn(B, C, H, H, generator=gen).half().float()
+    w = (torch.randn(C, gw, 3, 3, generator=gen) * 0.2).half().float()
+    scale = torch.randn(C, generator=gen) * 0.2 + 1.0
+    shift = torch.randn(C, generator=gen) * 0.3
+    mask = None
+    xin = x
+    if gran:
+        mask = (torch.rand(B, C // gran, generator=gen) < 0.6).float()
+        xin = O.apply_channel_mask(x, mask)
+    ref = torch.relu(F.conv2d(xin, w, stride=stride, padding=1, groups=C // gw) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    if gran:
+        ref = O.apply_channel_mask(ref, mask)
+    xd = x.permute(0, 2, 3, 1).contiguous().half().to(DEV)
+    wd = w.permute(0, 2, 3, 1).reshape(C, 9, gw).contiguous().half().to(DEV)
+    md = mask.to(torch.uint8).to(DEV) if gran else None
+    y = torch.full((B, H // stride, H // stride, C), float("nan"), dtype=torch.float16, device=DEV)
+    sc, sh = scale.to(DEV), shift.to(DEV)
+    _lib.check(cuda_lib.laud_grouped_conv3x3_forward(xd.data_ptr(), B, H, H, C, stride, wd.data_ptr(), gw, sc.data_ptr(),
+                                                     sh.data_ptr(), _lib.ptr(md), max(gran, 1), y.data_ptr(),
+                                                     _lib.stream_ptr()), "laud_grouped_conv3x3_forward")
+    torch.cuda.synchronize()
+    assert _rel_err(y.float().permute(0, 3, 1, 2), ref) <= ACT_TOL
+
+
+def test_squeeze_excitation_vs_oracle(cuda_lib):
+    gen = torch.Generator().manual_seed(3)
+    B, C, S, H = 3, 48, 6, 5
+    a2 = torch.relu(torch.randn(B, C, H, H, generator=gen)).half().float()
+    sd = {"se.fc1.weight": torch.randn(S, C, 1, 1, generator=gen) * 0.2, "se.fc1.bias": torch.randn(S, generator=gen) * 0.1,
+          "se.fc2.weight": torch.randn(C, S, 1, 1, generator=gen) * 0.3, "se.fc2.bias": torch.randn(C, generator=gen) * 0.1}
+    ref = O.squeeze_excitation(a2, sd, "se.")
+    xd = a2.permute(0, 2, 3, 1).contiguous().half().to(DEV)
+    partial = torch.empty(B * (_lib.GAP_SPLITS + 1) * C, device=DEV)
+    pooled = torch.empty(B, C, device=DEV)
+    gate = torch.empty(B, C, device=DEV)
+    w1, b1 = sd["se.fc1.weight"].reshape(S, C).contiguous().to(DEV), sd["se.fc1.bias"].to(DEV)
+    w2, b2 = sd["se.fc2.weight"].reshape(C, S).contiguous().to(DEV), sd["se.fc2.bias"].to(DEV)
+    st = _lib.stream_ptr()
+    _lib.check(cuda_lib.laud_global_avg_pool(xd.data_ptr(), B, H * H, C, C, partial.data_ptr(), pooled.data_ptr(), st), "gap")
+    _lib.check(cuda_lib.laud_se_gate(pooled.data_ptr(), B, C, w1.data_ptr(), b1.data_ptr(), S, w2.data_ptr(), b2.data_ptr(),
+                                     None, 1, gate.data_ptr(), st), "laud_se_gate")
+    _lib.check(cuda_lib.laud_scale_channels(xd.data_ptr(), B, H * H, C, gate.data_ptr(), st), "laud_scale_channels")
+    torch.cuda.synchronize()
+    assert _rel_err(xd.float().permute(0, 3, 1, 2), ref) <= ACT_TOL
+
+
+@pytest.mark.parametrize("name", list(REGNET_CASES))
+def test_regnet_blocks_teacher_forced(cuda_lib, name):
+    """Every ResBottleneckBlock of the golden RegNets, fed the ORACLE's block input (rounded to fp16) and the ORACLE's
+    gating masks: block outputs within ACT_TOL."""
+    cfg, sd, x, z, model = _regnet(name)
+    eng = model._engine
+    eng.prepare()
+    geoms = O.regnet_geometry(cfg)
+    B = x.shape[0]
+    ws = eng._workspace(B, cfg.input_size, cfg.input_size, torch.device(DEV))
+    with torch.no_grad():
+        feat, _ = O.regnet_stem_forward(x, sd)
+        for g, p in zip(geoms, eng.plans):
+            xin = feat.half().float()
+            tr = O.BlockTrace()
+            out_o = O.regnet_block_forward(xin, sd, g, tr)
+            xd = L.utils.to_nhwc_f16(xin.to(DEV))
+            out = torch.empty((B, p.H_out, p.H_out, p.w_out), dtype=torch.float16, device=DEV)
+            idb = torch.empty_like(out)
+            ws["counts"].zero_()
+            eng.run_block(p, xd.view(-1), out.view(-1), idb.view(-1), B, ws, None,
+                          None if tr.channel_mask is None else tr.channel_mask.to(DEV),
+                          None if tr.spatial_mask_small is None else tr.spatial_mask_small.to(DEV))
+            torch.cuda.synchronize()
+            err = _rel_err(out.float().permute(0, 3, 1, 2), out_o[0])
+            assert err <= ACT_TOL, f"{name} {g.prefix}: block output error {err:.2e}"
+            feat = out_o[0]
+
+
+@pytest.mark.parametrize("name", list(REGNET_CASES))
+def test_regnet_network_free_running_vs_golden(cuda_lib, name):
+    cfg, sd, x, z, model = _regnet(name)
+    keep = []
+    with torch.no_grad():
+        logits, r3, r2, r1, rc, perc, flops = model(x.to(DEV), 1.0, keep=keep)
+        traces = []
+        O.regnet_forward(sd, cfg, x, traces)
+    geoms = O.regnet_geometry(cfg)
+    excused = total = 0
+    exact = True
+    for g, ko, tr in zip(geoms, keep, traces):
+        tag = "ref." + g.prefix.split(".")[2]
+        for got_t, key, logit_t, G in ((ko.channel_mask, ".channel_mask", tr.channel_logits, g.groups_channel),
+                                       (ko.spatial_mask_small, ".spatial_mask", tr.spatial_logits, g.groups_spatial)):
+            if got_t is None:
+                continue
+            want, got = z[tag + key], got_t.cpu().numpy()
+            margin = (logit_t[:, :G] - logit_t[:, G:]).abs().numpy()
+            clear = margin > MARGIN_TOL * float(logit_t.abs().max())
+            diff = got != want
+            total += diff.size
+            excused += int((diff & ~clear).sum())
+            if (diff & clear).any():
+                exact = False
+    if exact and excused == 0:
+        np.testing.assert_array_equal(np.concatenate([t.cpu().numpy() for t in r3]),
+                                      np.concatenate([z[f"rho3.{s}"] for s in range(4)]))
+        np.testing.assert_array_equal(np.concatenate([t.cpu().numpy() for t in rc]),
+                                      np.concatenate([z[f"rhoc.{s}"] for s in range(4)]))
+        np.testing.assert_allclose(perc.cpu().numpy(), z["flops_perc"], rtol=1e-6)
+        np.testing.assert_allclose(flops.item(), float(z["flops"]), rtol=1e-6)
+        err = _rel_err(logits, torch.from_numpy(z["logits"]))
+        assert err <= 5e-3, f"{name}: logits error {err:.2e}"
+    frac = excused / max(total, 1)
+    print(f"{name}: {total} gating decisions, {excused} within-noise flips, exact_elsewhere={exact}")
+    assert exact, f"{name}: a gating decision with a clear margin differs from the reference's"
+    assert frac <= 2e-3

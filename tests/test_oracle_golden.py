@@ -126,3 +126,54 @@ def test_masked_channel_constant_and_layer_skip_identity():
     skipped = (tr.spatial_mask_small.view(-1) == 0).nonzero().view(-1)
     assert len(skipped) > 0
     assert torch.equal(tr.out[skipped], torch.relu(feat[skipped]))
+
+
+# --------------------------------------------------------------------------- LAUD-RegNet-Y (laud_regnet.py)
+from tests.golden_cases import REGNET_CASES, load_regnet_case, regnet_model     # noqa: E402
+
+
+@pytest.mark.parametrize("name", list(REGNET_CASES))
+def test_regnet_matches_reference(name):
+    cfg, sd, x, z = load_regnet_case(name)
+    traces = []
+    with torch.no_grad():
+        logits, r3, r2, r1, rc, perc, flops = O.regnet_forward(sd, cfg, x, traces)
+    np.testing.assert_allclose(logits.numpy(), z["logits"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(perc.numpy(), z["flops_perc"], rtol=1e-6)
+    np.testing.assert_allclose(flops.item(), z["flops"], rtol=1e-6)
+    for key, lst in (("rho3", r3), ("rho2", r2), ("rho1", r1), ("rhoc", rc)):
+        for s in range(4):
+            np.testing.assert_array_equal(lst[s].numpy(), z[f"{key}.{s}"])
+    geoms = O.regnet_geometry(cfg)
+    assert len(geoms) == len(traces)
+    for g, tr in zip(geoms, traces):
+        tag = "ref." + g.prefix.split(".")[2]
+        if tr.channel_mask is not None:
+            np.testing.assert_array_equal(tr.channel_mask.numpy().astype(np.uint8), z[tag + ".channel_mask"])
+        if tr.spatial_mask_small is not None:
+            np.testing.assert_array_equal(tr.spatial_mask_small.numpy().astype(np.uint8), z[tag + ".spatial_mask"])
+        o = tr.out.double()
+        stats = np.array([o.mean().item(), o.abs().mean().item(), o.abs().max().item()])
+        np.testing.assert_allclose(stats, z[tag + ".out_stats"], rtol=1e-5)
+        if tag + ".out" in z.files:
+            np.testing.assert_allclose(tr.out.numpy(), z[tag + ".out"], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", list(REGNET_CASES))
+def test_regnet_stage_params_and_state_dict_layout(name):
+    """The drop-in's design-space derivation and module tree against what the reference produced."""
+    from laudnet_b200.laud_regnet import stage_params
+    cfg, sd, x, z = load_regnet_case(name)
+    widths, depths, gws = stage_params(**REGNET_CASES[name][0])
+    assert widths == z["stage_widths"].tolist() and depths == z["stage_depths"].tolist()
+    assert gws == z["stage_group_widths"].tolist()
+    m = regnet_model(name, cfg)
+    assert sorted(m.state_dict().keys()) == z["state_dict_keys"].tolist()
+    m.load_state_dict(sd, strict=True)
+
+
+def test_regnet_y_800mf_geometry():
+    """SURVEY appendix B.2 (verified there against the instantiated reference model)."""
+    from laudnet_b200.laud_regnet import stage_params
+    assert stage_params(depth=14, w_0=56, w_a=38.84, w_m=2.4, group_width=16) == ([64, 144, 320, 784], [1, 3, 8, 2], [16] * 4)
+    assert stage_params(depth=16, w_0=48, w_a=27.89, w_m=2.09, group_width=8) == ([48, 104, 208, 440], [1, 3, 6, 6], [8] * 4)
