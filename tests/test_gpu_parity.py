@@ -724,3 +724,34 @@ def test_regnet_network_free_running_vs_golden(cuda_lib, name):
     print(f"{name}: {total} gating decisions, {excused} within-noise flips, exact_elsewhere={exact}")
     assert exact, f"{name}: a gating decision with a clear margin differs from the reference's"
     assert frac <= 2e-3
+
+
+def test_regnet_y_800mf_spatial_full_size_vs_oracle(cuda_lib):
+    """BASELINE config 4 architecture (LAUD-RegNetY-800MF spatial 4-4-2-1, 224x224) at batch 4: the CUDA path against
+    the CPU oracle on calibrated synthetic weights (spatial target ~0.3): gates and logits."""
+    kw = dict(input_size=224, dyn_mode=["spatial"] * 4, mask_spatial_granularity=[4, 4, 2, 1],
+              spatial_mask_channel_group=[1] * 4, channel_dyn_granularity=[1] * 4, channel_masker=["MLP"] * 4,
+              channel_masker_layers=[2] * 4, reduction_ratio=[16] * 4)
+    m = L.lad_regnet_y_800mf(**kw)
+    cfg = O.RegNetCfg(**{k: tuple(v) if isinstance(v, list) else v for k, v in kw.items()})
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    x = synth.synth_images(4, 224, 9)
+    sd = synth.calibrate_regnet(synth.synth_state_dict(shapes, 9), O.regnet_geometry(cfg), x, 9, spatial_rate=0.3)
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    keep = []
+    with torch.no_grad():
+        logits, r3, r2, r1, rc, perc, flops = m(x.to(DEV), 1.0, keep=keep)
+        traces = []
+        ref = O.regnet_forward(sd, cfg, x, traces)
+    assert [len(t) for t in r3] == [1, 3, 8, 2] and perc.shape == (14,)
+    flips = total = 0
+    for ko, tr in zip(keep, traces):
+        got, want = ko.spatial_mask_small.cpu().float(), tr.spatial_mask_small
+        flips += int((got != want).sum())
+        total += want.numel()
+    assert flips <= 2e-3 * total, f"{flips}/{total} spatial gates differ from the oracle's"
+    if flips == 0:
+        assert _rel_err(logits, ref[0]) <= 5e-3
+        np.testing.assert_allclose(flops.item(), ref[6].item(), rtol=1e-6)
+    assert 0.2 < float(torch.cat(r3).mean()) < 0.4
