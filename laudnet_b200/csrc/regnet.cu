@@ -129,6 +129,105 @@ __global__ void __launch_bounds__(128) grouped_conv3x3_kernel(const __half* __re
 }
 
 // ---------------------------------------------------------------------------
+// Grouped 3x3, group width 16, no channel gate: warp-level tensor-core version (the product path of RegNetY-800MF).
+// Per group the convolution is a GEMM  [pixels] x [16 out] x [K = 9 taps x 16 in]: one tap is exactly one k16 step of
+// mma.sync.m16n8k16, whose A fragment is 16 pixels x the group's 16 contiguous input channels (32 bytes per pixel,
+// read straight from global memory / L1 - no im2col buffer) and whose B fragments come from the group's weights in
+// shared memory.  grid (pixel tiles, groups); a warp owns 16 output pixels per iteration.
+// (Group width 16 cannot fill a tcgen05 tile: N = 16 at M = 128 would cost the same ~128 cycles as N = 256.)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void mma_16816_f16(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                              uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+constexpr int GC_WP = 24;      // padded k pitch (halves) of a weight row in shared memory: conflict-free fragment loads
+__global__ void __launch_bounds__(128) grouped_conv3x3_mma16_kernel(const __half* __restrict__ x, int B, int H_in,
+                                                                    int W_in, int C, int stride,
+                                                                    const __half* __restrict__ w,
+                                                                    const float* __restrict__ scale,
+                                                                    const float* __restrict__ shift,
+                                                                    __half* __restrict__ y) {
+  __shared__ __align__(16) __half s_w[9 * 16 * GC_WP];           // [tap][out n][k]
+  const int grp = blockIdx.y, c0 = grp * 16;
+  for (int i = threadIdx.x; i < 16 * 9 * 16; i += 128) {         // global [out][tap][in]
+    const int n = i / 144, r = i % 144, tap = r / 16, k = r % 16;
+    s_w[(tap * 16 + n) * GC_WP + k] = w[(size_t)c0 * 144 + i];
+  }
+  __syncthreads();
+  const int H_out = H_in / stride, W_out = W_in / stride;
+  const long long npix = (long long)B * H_out * W_out;
+  const long long ntiles = (npix + 15) / 16;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  float sc[4], sh[4];                                            // this thread's 4 output channels: nt*8 + 2t, +1
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) {
+    sc[2 * nt] = scale[c0 + nt * 8 + 2 * t];
+    sc[2 * nt + 1] = scale[c0 + nt * 8 + 2 * t + 1];
+    sh[2 * nt] = shift[c0 + nt * 8 + 2 * t];
+    sh[2 * nt + 1] = shift[c0 + nt * 8 + 2 * t + 1];
+  }
+  for (long long tile = (long long)blockIdx.x * 4 + warp; tile < ntiles; tile += (long long)gridDim.x * 4) {
+    int oy[2], ox[2], bb[2];
+    bool pv[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      long long p = tile * 16 + g + 8 * h;
+      pv[h] = p < npix;
+      if (!pv[h]) p = npix - 1;
+      ox[h] = (int)(p % W_out);
+      oy[h] = (int)((p / W_out) % H_out);
+      bb[h] = (int)(p / ((long long)W_out * H_out));
+    }
+    float acc[2][4];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int ky = tap / 3, kx = tap % 3;
+      uint32_t a[4];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int iy = oy[h] * stride - 1 + ky, ix = ox[h] * stride - 1 + kx;
+        const bool ok = iy >= 0 && iy < H_in && ix >= 0 && ix < W_in;
+        uint32_t lo = 0u, hi = 0u;
+        if (ok) {
+          const uint32_t* xp = reinterpret_cast<const uint32_t*>(x + (((size_t)bb[h] * H_in + iy) * W_in + ix) * C + c0);
+          lo = __ldg(xp + t);                                    // channels 2t, 2t+1
+          hi = __ldg(xp + 4 + t);                                // channels 2t+8, 2t+9
+        }
+        a[h] = lo;                                               // a0 (row g) / a1 (row g+8)
+        a[2 + h] = hi;                                           // a2 / a3
+      }
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const __half* wp = s_w + (tap * 16 + nt * 8 + g) * GC_WP + 2 * t;
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wp);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(wp + 8);
+        mma_16816_f16(acc[nt], a[0], a[1], a[2], a[3], b0, b1);
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (!pv[h]) continue;
+      const long long p = tile * 16 + g + 8 * h;
+      __half* yp = y + (size_t)p * C + c0 + 2 * t;
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const float v0 = fmaxf(fmaf(acc[nt][2 * h], sc[2 * nt], sh[2 * nt]), 0.f);
+        const float v1 = fmaxf(fmaf(acc[nt][2 * h + 1], sc[2 * nt + 1], sh[2 * nt + 1]), 0.f);
+        *reinterpret_cast<__half2*>(yp + nt * 8) = __floats2half2_rn(v0, v1);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Squeeze-Excitation gate (torchvision SqueezeExcitation, laud_regnet.py:194): per sample
 //   s = sigmoid(W2 relu(W1 p + b1) + b2),  p = pooled features [C]  (optionally gated: p *= mask, s *= mask - the
 //   channel gate of :189 commutes with the pooling because it is constant over the pixels).
@@ -220,6 +319,14 @@ extern "C" int laud_grouped_conv3x3_forward(const void* x, int B, int H_in, int 
   if (tiles > cap) tiles = cap;
   dim3 grid((unsigned)tiles, (unsigned)groups);
   cudaStream_t s = (cudaStream_t)stream;
+  if (group_width == 16 && !ch_mask) {
+    const long long ntiles = ((long long)B * (H_in / stride) * (W_in / stride) + 15) / 16;
+    long long gx = (ntiles + 3) / 4;
+    if (gx > cap) gx = cap;
+    grouped_conv3x3_mma16_kernel<<<dim3((unsigned)gx, (unsigned)groups), 128, 0, s>>>(
+        (const __half*)x, B, H_in, W_in, C, stride, (const __half*)w, scale, shift, (__half*)y);
+    return check_launch("grouped_conv3x3_mma16_kernel");
+  }
   if (group_width == 16)
     grouped_conv3x3_kernel<16><<<grid, 128, 0, s>>>((const __half*)x, B, H_in, W_in, C, stride, (const __half*)w, scale,
                                                     shift, ch_mask, mask_gran, (__half*)y);
