@@ -309,8 +309,8 @@ extern "C" int laud_grouped_conv3x3_forward(const void* x, int B, int H_in, int 
   LAUD_REQUIRE(x && w && scale && shift && y, "laud_grouped_conv3x3_forward: null pointer");
   LAUD_REQUIRE(B > 0 && (stride == 1 || stride == 2) && H_in % stride == 0 && W_in % stride == 0,
                "laud_grouped_conv3x3_forward: stride must be 1 or 2 and divide H,W");
-  LAUD_REQUIRE((group_width == 8 || group_width == 16) && C % group_width == 0,
-               "laud_grouped_conv3x3_forward: group width must be 8 or 16 and divide C (got %d, C=%d)", group_width, C);
+  LAUD_REQUIRE((group_width == 8 || group_width == 16 || group_width == 24) && C % group_width == 0,
+               "laud_grouped_conv3x3_forward: group width must be 8, 16 or 24 and divide C (got %d, C=%d)", group_width, C);
   LAUD_REQUIRE(!ch_mask || (mask_gran >= 1 && C % mask_gran == 0), "laud_grouped_conv3x3_forward: bad mask granularity");
   const long long total = (long long)B * (H_in / stride) * (W_in / stride) * (group_width / 8);
   const int groups = C / group_width;
@@ -327,7 +327,10 @@ extern "C" int laud_grouped_conv3x3_forward(const void* x, int B, int H_in, int 
         (const __half*)x, B, H_in, W_in, C, stride, (const __half*)w, scale, shift, (__half*)y);
     return check_launch("grouped_conv3x3_mma16_kernel");
   }
-  if (group_width == 16)
+  if (group_width == 24)
+    grouped_conv3x3_kernel<24><<<grid, 128, 0, s>>>((const __half*)x, B, H_in, W_in, C, stride, (const __half*)w, scale,
+                                                    shift, ch_mask, mask_gran, (__half*)y);
+  else if (group_width == 16)
     grouped_conv3x3_kernel<16><<<grid, 128, 0, s>>>((const __half*)x, B, H_in, W_in, C, stride, (const __half*)w, scale,
                                                     shift, ch_mask, mask_gran, (__half*)y);
   else

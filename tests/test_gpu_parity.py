@@ -606,7 +606,7 @@ def test_regnet_stem_vs_oracle(cuda_lib, B, size, C0):
 
 
 @pytest.mark.parametrize("B,H,C,gw,stride,gran", [(2, 8, 32, 8, 1, 0), (3, 14, 64, 16, 2, 0), (2, 6, 48, 16, 1, 4),
-                                                  (1, 10, 40, 8, 2, 8)])
+                                                  (1, 10, 40, 8, 2, 8), (2, 8, 48, 24, 1, 0), (1, 12, 72, 24, 2, 8)])
 def test_grouped_conv3x3_vs_torch(cuda_lib, B, H, C, gw, stride, gran):
     """conv b of the RegNet transform (laud_regnet.py:118-120,188-189): grouped 3x3 + BN + ReLU, optional channel gate
     applied to its input and output, against F.conv2d(groups=...) on fp16-representable data."""
