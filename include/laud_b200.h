@@ -252,7 +252,8 @@ int laud_nhwc_f16_to_nchw_f32(const void* src, int lds, int B, int C, int H, int
  *                                gate ch_mask u8 [B, C/mask_gran] applied to the input (= conv a's gated output, :183)
  *                                and to the output (:189)
  *   laud_se_gate                 SqueezeExcitation gate (:128-132,194) from the pooled features fp32 [B,C]:
- *                                gate = sigmoid(W2 relu(W1 p + b1) + b2)  (p and gate multiplied by ch_mask if given)
+ *                                gate = sigmoid(W2 relu(W1 p + b1) + b2)  (p and gate multiplied by ch_mask if given);
+ *                                w1 fp32 [S][C], w2 fp32 passed TRANSPOSED as [S][C]
  *   laud_scale_channels          x[b,p,c] *= gate[b,c]  (fp16 NHWC, in place)
  * ------------------------------------------------------------------------- */
 int laud_regnet_stem_forward(const void* x_nchw, int B, int H, int W, const void* w, int C0, const float* scale,

@@ -106,7 +106,7 @@ class RegNetEngine:
                         p.sp, p.tp = fold_bn(blk.proj[1])
                     p.se_w1 = f.se.fc1.weight.detach().float().reshape(p.se_width, w_b).contiguous()
                     p.se_b1 = f.se.fc1.bias.detach().float().contiguous()
-                    p.se_w2 = f.se.fc2.weight.detach().float().reshape(w_b, p.se_width).contiguous()
+                    p.se_w2 = f.se.fc2.weight.detach().float().reshape(w_b, p.se_width).t().contiguous()   # [S][w_b]: coalesced gate kernel
                     p.se_b2 = f.se.fc2.bias.detach().float().contiguous()
                     self.plans.append(p)
                     idx += 1

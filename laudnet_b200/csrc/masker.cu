@@ -326,62 +326,79 @@ __global__ void __launch_bounds__(256) masker_spatial_kernel(
     const __half* __restrict__ x, int B, int H, int W, int C, const float* __restrict__ w,
     const float* __restrict__ bias, int g, int S, float* __restrict__ logits_out,
     uint8_t* __restrict__ mask_out, int* __restrict__ total_out) {
+  // lanes = (pixel lane, 16-byte channel vector): narrow layers (C = 32) still issue full-width loads
+  __shared__ int s_ones;
+  if (threadIdx.x == 0) s_ones = 0;
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const long long cell = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (cell >= (long long)B * S * S) return;
-  const int b = (int)(cell / (S * S));
-  const int ci = (int)(cell % (S * S)) / S, cj = (int)(cell % S);
-  int y0, y1, x0, x1;
-  if (S >= H) { y0 = ci; y1 = ci + 1; x0 = cj; x1 = cj + 1; }
-  else {
-    y0 = (ci * H) / S; y1 = ((ci + 1) * H + S - 1) / S;
-    x0 = (cj * W) / S; x1 = ((cj + 1) * W + S - 1) / S;
-  }
-  const float area = (float)((y1 - y0) * (x1 - x0));
-  float keep[4], drop[4];  // g <= 4 handled in registers; larger g loops below
-  // accumulate logits lane-partial: sum_c w[o][c] * pooled[c]
-  float part[8];
+  const bool live = cell < (long long)B * S * S;
+  int ones = 0;
+  if (live) {
+    const int b = (int)(cell / (S * S));
+    const int ci = (int)(cell % (S * S)) / S, cj = (int)(cell % S);
+    int y0, y1, x0, x1;
+    if (S >= H) { y0 = ci; y1 = ci + 1; x0 = cj; x1 = cj + 1; }
+    else {
+      y0 = (ci * H) / S; y1 = ((ci + 1) * H + S - 1) / S;
+      x0 = (cj * W) / S; x1 = ((cj + 1) * W + S - 1) / S;
+    }
+    const int wreg = x1 - x0, npix = (y1 - y0) * wreg;
+    const float area = (float)npix;
+    int nv = 1;
+    while (nv < 32 && nv * 8 < C) nv <<= 1;             // vector lanes per pixel (power of two)
+    const int pl = 32 / nv, vl = lane % nv, pi = lane / nv;
+    float part[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) part[i] = 0.f;
-  const int G2 = 2 * g;
-  for (int c0 = lane * 8; c0 < C; c0 += 256) {
-    float acc[8];
+    for (int i = 0; i < 8; ++i) part[i] = 0.f;
+    const int G2 = 2 * g;
+    for (int cb = 0; cb < C; cb += nv * 8) {
+      const int c0 = cb + vl * 8;
+      float acc[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    for (int yy = y0; yy < y1; ++yy)
-      for (int xx = x0; xx < x1; ++xx) {
-        const uint4 q = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)b * H + yy) * W + xx) * C + c0));
-        const __half2* hh = reinterpret_cast<const __half2*>(&q);
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      if (c0 < C)
+        for (int idx = pi; idx < npix; idx += pl) {
+          const int yy = y0 + idx / wreg, xx = x0 + idx % wreg;
+          const uint4 q = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)b * H + yy) * W + xx) * C + c0));
+          const __half2* hh = reinterpret_cast<const __half2*>(&q);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 f = __half22float2(hh[i]);
-          acc[2 * i] += f.x;
-          acc[2 * i + 1] += f.y;
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(hh[i]);
+            acc[2 * i] += f.x;
+            acc[2 * i + 1] += f.y;
+          }
+        }
+      for (int off = nv; off < 32; off <<= 1) {          // fixed-order tree over the pixel lanes
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
+      }
+      if (pi == 0 && c0 < C) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = (S >= H) ? acc[i] : acc[i] / area;
+        for (int o = 0; o < G2 && o < 8; ++o) {
+          const float* wr = w + (size_t)o * C + c0;
+          float t = part[o];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t = fmaf(wr[i], acc[i], t);
+          part[o] = t;
         }
       }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = (S >= H) ? acc[i] : acc[i] / area;
-    for (int o = 0; o < G2 && o < 8; ++o) {
-      const float* wr = w + (size_t)o * C + c0;
-      float t = part[o];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) t = fmaf(wr[i], acc[i], t);
-      part[o] = t;
+    }
+    for (int o = 0; o < G2 && o < 8; ++o) part[o] = warp_sum(part[o]) + bias[o];
+    if (lane == 0) {
+      for (int o = 0; o < G2; ++o)
+        if (logits_out) logits_out[(((size_t)b * G2 + o) * S + ci) * S + cj] = part[o];
+      for (int q = 0; q < g; ++q) {
+        const int f = part[q] >= part[g + q] ? 1 : 0;
+        mask_out[(((size_t)b * g + q) * S + ci) * S + cj] = (uint8_t)f;
+        ones += f;
+      }
+      if (ones) atomicAdd(&s_ones, ones);
     }
   }
-  (void)keep; (void)drop;
-  int ones = 0;
-  for (int o = 0; o < G2 && o < 8; ++o) part[o] = warp_sum(part[o]) + bias[o];
-  if (lane == 0) {
-    for (int o = 0; o < G2; ++o)
-      if (logits_out) logits_out[(((size_t)b * G2 + o) * S + ci) * S + cj] = part[o];
-    for (int q = 0; q < g; ++q) {
-      const int f = part[q] >= part[g + q] ? 1 : 0;
-      mask_out[(((size_t)b * g + q) * S + ci) * S + cj] = (uint8_t)f;
-      ones += f;
-    }
-    if (total_out && ones) atomicAdd(total_out, ones);
-  }
+  __syncthreads();
+  if (threadIdx.x == 0 && total_out && s_ones) atomicAdd(total_out, s_ones);   // one global atomic per CTA
 }
 
 __global__ void resize_mask_kernel(const uint8_t* __restrict__ m, int B, int g, int S, int Ho,

@@ -8,49 +8,54 @@ namespace laud {
 
 // ---------------------------------------------------------------------------
 // SimpleStemIN: conv3x3/2 (pad 1) + BN + ReLU.  x fp16 NCHW [B,3,H,W] -> y fp16 NHWC [B,H/2,W/2,C0].
-// One thread = one output pixel x 8 channels; the 27 x C0 weights sit in shared memory.
+// One thread = one output pixel (its 27 inputs in registers, all C0 channels); the 27 x C0 weights sit in shared memory.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) regnet_stem_kernel(const __half* __restrict__ x, int B, int H, int W,
                                                           const __half* __restrict__ w, int C0,
                                                           const float* __restrict__ scale,
                                                           const float* __restrict__ shift, __half* __restrict__ y) {
-  extern __shared__ float s_w[];                       // [27][C0]
+  extern __shared__ __align__(16) float s_w[];         // [27][C0]
   for (int i = threadIdx.x; i < 27 * C0; i += 256) {
     const int o = i / 27, t = i % 27;                  // global layout [C0][3][3][3]
     s_w[t * C0 + o] = __half2float(w[i]);
   }
   __syncthreads();
   const int Ho = H / 2, Wo = W / 2, ncg = C0 / 8;
-  const long long total = (long long)B * Ho * Wo * ncg;
-  for (long long it = (long long)blockIdx.x * 256 + threadIdx.x; it < total; it += (long long)gridDim.x * 256) {
-    const int cg = (int)(it % ncg);
-    const long long pix = it / ncg;
+  const long long total = (long long)B * Ho * Wo;       // one thread = one output pixel, all channels
+  for (long long pix = (long long)blockIdx.x * 256 + threadIdx.x; pix < total; pix += (long long)gridDim.x * 256) {
     const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), b = (int)(pix / ((long long)Wo * Ho));
-    float acc[8];
+    float in[27];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
     for (int c = 0; c < 3; ++c)
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky) {
-        const int iy = 2 * oy - 1 + ky;
-        if (iy < 0 || iy >= H) continue;
+      for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-          const int ix = 2 * ox - 1 + kx;
-          if (ix < 0 || ix >= W) continue;
-          const float v = __half2float(x[(((size_t)b * 3 + c) * H + iy) * W + ix]);
-          const float* wr = s_w + ((c * 3 + ky) * 3 + kx) * C0 + cg * 8;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) acc[e] = fmaf(v, wr[e], acc[e]);
+          const int iy = 2 * oy - 1 + ky, ix = 2 * ox - 1 + kx;
+          const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+          in[(c * 3 + ky) * 3 + kx] = ok ? __half2float(x[(((size_t)b * 3 + c) * H + iy) * W + ix]) : 0.f;
         }
-      }
-    __align__(16) __half o8[8];
+    for (int cg = 0; cg < ncg; ++cg) {
+      float acc[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int ch = cg * 8 + e;
-      o8[e] = __float2half(fmaxf(fmaf(acc[e], scale[ch], shift[ch]), 0.f));
+      for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+      for (int t = 0; t < 27; ++t) {
+        const float4 w0 = *reinterpret_cast<const float4*>(s_w + t * C0 + cg * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(s_w + t * C0 + cg * 8 + 4);
+        acc[0] = fmaf(in[t], w0.x, acc[0]); acc[1] = fmaf(in[t], w0.y, acc[1]);
+        acc[2] = fmaf(in[t], w0.z, acc[2]); acc[3] = fmaf(in[t], w0.w, acc[3]);
+        acc[4] = fmaf(in[t], w1.x, acc[4]); acc[5] = fmaf(in[t], w1.y, acc[5]);
+        acc[6] = fmaf(in[t], w1.z, acc[6]); acc[7] = fmaf(in[t], w1.w, acc[7]);
+      }
+      __align__(16) __half o8[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int ch = cg * 8 + e;
+        o8[e] = __float2half(fmaxf(fmaf(acc[e], scale[ch], shift[ch]), 0.f));
+      }
+      *reinterpret_cast<uint4*>(y + (size_t)pix * C0 + cg * 8) = *reinterpret_cast<const uint4*>(o8);
     }
-    *reinterpret_cast<uint4*>(y + (size_t)pix * C0 + cg * 8) = *reinterpret_cast<const uint4*>(o8);
   }
 }
 
@@ -229,7 +234,7 @@ __global__ void __launch_bounds__(128) grouped_conv3x3_mma16_kernel(const __half
 
 // ---------------------------------------------------------------------------
 // Squeeze-Excitation gate (torchvision SqueezeExcitation, laud_regnet.py:194): per sample
-//   s = sigmoid(W2 relu(W1 p + b1) + b2),  p = pooled features [C]  (optionally gated: p *= mask, s *= mask - the
+//   s = sigmoid(W2 relu(W1 p + b1) + b2),  p = pooled features [C], W1 [S][C], W2 passed transposed as [S][C]  (optionally gated: p *= mask, s *= mask - the
 //   channel gate of :189 commutes with the pooling because it is constant over the pixels).
 // One CTA per sample.  dynamic smem: p[C] | h[S]
 // ---------------------------------------------------------------------------
@@ -256,10 +261,9 @@ __global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ 
     if (lane == 0) h[j] = fmaxf(t + b1[j], 0.f);
   }
   __syncthreads();
-  for (int c = tid; c < C; c += 256) {
-    const float* wr = w2 + (size_t)c * S;
+  for (int c = tid; c < C; c += 256) {                 // w2 is stored TRANSPOSED [S][C]: coalesced across the threads
     float t = 0.f;
-    for (int j = 0; j < S; ++j) t = fmaf(wr[j], h[j], t);
+    for (int j = 0; j < S; ++j) t = fmaf(__ldg(w2 + (size_t)j * C + c), h[j], t);
     float s = 1.f / (1.f + __expf(-(t + b2[c])));
     if (ch_mask) s *= (float)ch_mask[(size_t)b * G_mask + c / mask_gran];
     gate[(size_t)b * C + c] = s;
@@ -296,7 +300,7 @@ extern "C" int laud_regnet_stem_forward(const void* x_nchw, int B, int H, int W,
   LAUD_REQUIRE(x_nchw && w && scale && shift && y_nhwc, "laud_regnet_stem_forward: null pointer");
   LAUD_REQUIRE(B > 0 && H % 2 == 0 && W % 2 == 0 && C0 % 8 == 0 && C0 <= 256,
                "laud_regnet_stem_forward: need even H,W and C0 %% 8 == 0, C0 <= 256");
-  const long long total = (long long)B * (H / 2) * (W / 2) * (C0 / 8);
+  const long long total = (long long)B * (H / 2) * (W / 2);
   const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   regnet_stem_kernel<<<grid, 256, sizeof(float) * 27 * C0, (cudaStream_t)stream>>>(
       (const __half*)x_nchw, B, H, W, (const __half*)w, C0, scale, shift, (__half*)y_nhwc);

@@ -647,7 +647,7 @@ def test_squeeze_excitation_vs_oracle(cuda_lib):
     pooled = torch.empty(B, C, device=DEV)
     gate = torch.empty(B, C, device=DEV)
     w1, b1 = sd["se.fc1.weight"].reshape(S, C).contiguous().to(DEV), sd["se.fc1.bias"].to(DEV)
-    w2, b2 = sd["se.fc2.weight"].reshape(C, S).contiguous().to(DEV), sd["se.fc2.bias"].to(DEV)
+    w2, b2 = sd["se.fc2.weight"].reshape(C, S).t().contiguous().to(DEV), sd["se.fc2.bias"].to(DEV)   # passed as [S][C]
     st = _lib.stream_ptr()
     _lib.check(cuda_lib.laud_global_avg_pool(xd.data_ptr(), B, H * H, C, C, partial.data_ptr(), pooled.data_ptr(), st), "gap")
     _lib.check(cuda_lib.laud_se_gate(pooled.data_ptr(), B, C, w1.data_ptr(), b1.data_ptr(), S, w2.data_ptr(), b2.data_ptr(),
