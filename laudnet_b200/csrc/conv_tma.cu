@@ -380,23 +380,30 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
         bool a_more = walker_next(a, pl, T, wa, sa);
         while (a_more && sa.cpt == 0) a_more = walker_next(a, pl, T, wa, sa);
         int a_kq = 0, a_next = 0, g = 0;
+        // issue the next activation tile (chunk a_next of the A stream) into its slot
+        auto issue_a = [&]() {
+          const int slot = a_next & 1;
+          mbar_arrive_expect_tx(&T.afull[slot], (uint32_t)pl.a_tx);
+          tma_load_4d(a_base + slot * pl.a_slot_bytes, &map_a, &T.afull[slot], a_kq * 64, -1, (sa.mt0) * pl.R - 1, sa.b);
+          ++a_next;
+          if (++a_kq >= sa.cpt) {
+            a_kq = 0;
+            a_more = walker_next(a, pl, T, wa, sa);
+            while (a_more && sa.cpt == 0) a_more = walker_next(a, pl, T, wa, sa);
+          }
+        };
         while (walker_next(a, pl, T, wk, s)) {
           for (int kq = 0; kq < s.cpt; ++kq, ++g) {
-            while (a_more && a_next <= g + 1) {
-              const int slot = a_next & 1;
-              mbar_wait(&T.aempty[slot], (uint32_t)((a_next >> 1) & 1) ^ 1u);
-              mbar_arrive_expect_tx(&T.afull[slot], (uint32_t)pl.a_tx);
-              tma_load_4d(a_base + slot * pl.a_slot_bytes, &map_a, &T.afull[slot], a_kq * 64, -1,
-                          (sa.mt0) * pl.R - 1, sa.b);
-              ++a_next;
-              if (++a_kq >= sa.cpt) {
-                a_kq = 0;
-                a_more = walker_next(a, pl, T, wa, sa);
-                while (a_more && sa.cpt == 0) a_more = walker_next(a, pl, T, wa, sa);
-              }
+            while (a_more && a_next <= g) {                       // the tile this chunk's MMAs read: must be on its way
+              mbar_wait(&T.aempty[a_next & 1], (uint32_t)((a_next >> 1) & 1) ^ 1u);
+              issue_a();
             }
             KP_LAP(0);
             for (int tap = 0; tap < taps; ++tap) {
+              // the NEXT chunk's tile goes out as soon as its slot is free - without holding up the weight stream
+              if (a_more && a_next == g + 1 &&
+                  mbar_try(smem_u32(&T.aempty[a_next & 1]), (uint32_t)((a_next >> 1) & 1) ^ 1u))
+                issue_a();
               mbar_wait(&T.empty[stage], phase ^ 1);
               KP_LAP(1);
               mbar_arrive_expect_tx(&T.full[stage], (uint32_t)pl.b_tx);
