@@ -108,6 +108,8 @@ struct Plan {              // host-computed launch geometry
   // output channels are loaded once per CTA (stab_cols floats each, zero padded) - no per-item column tables, no barrier
   int static_cols, stab_cols;
   int dma;                 // 1: slab stores / residual prefetches are issued by two otherwise idle threads (shared-weight layers)
+  int simple;              // 1: nothing per sample (no lists, gathers): Sub fields below are launch constants
+  int c_nfill, c_nk16, c_cpt, c_nchunks, NG;
 };
 
 struct Sub {               // one (sample, m-group, n-tile) unit of work
@@ -126,7 +128,7 @@ __device__ __forceinline__ void walker_init(const ConvArgs& a, const Plan& pl, W
   const int c = (int)blockIdx.x;
   w.t = c * base + min(c, rem);
   w.t_end = w.t + base + (c < rem ? 1 : 0);
-  const int NG = pl.NT / pl.NTI;
+  const int NG = pl.NG;
   w.ng = w.t % NG;
   const int r = w.t / NG;
   w.mg = r % pl.n_mgroups;
@@ -135,6 +137,25 @@ __device__ __forceinline__ void walker_init(const ConvArgs& a, const Plan& pl, W
   w.started = 0;
 }
 __device__ __forceinline__ bool decode_sub(const ConvArgs& a, const Plan& pl, const Tables& T, const Walker& w, Sub& s) {
+  if (pl.simple) {                     // division-free path of the shared-weight layers
+    s.b = w.slot;
+    s.mg = w.mg;
+    s.nt = w.ng * pl.NTI + w.nti;
+    s.Nc = a.C_out;
+    s.Nfill = pl.c_nfill;
+    s.n0 = s.nt * pl.BN;
+    if (s.n0 >= s.Nfill) return false;
+    s.n_valid = min(pl.BN, s.Nfill - s.n0);
+    s.umma_n = (s.n_valid + 15) & ~15;
+    s.Kc = a.C_in;
+    s.nk16 = pl.c_nk16;
+    s.cpt = pl.c_cpt;
+    s.has_bias = 0;
+    s.nchunks = pl.c_nchunks;
+    s.mt0 = w.mg * pl.MT;
+    s.mt_cnt = min(pl.MT, pl.n_mtiles - s.mt0);
+    return true;
+  }
   const int ns = a.sample_cnt ? __ldg(a.sample_cnt) : a.B;
   if (w.slot >= ns) return false;
   s.b = a.sample_idx ? __ldg(a.sample_idx + w.slot) : w.slot;
@@ -165,7 +186,7 @@ __device__ __forceinline__ bool walker_next(const ConvArgs& a, const Plan& pl, c
     } else if (++w.nti >= pl.NTI) {
       w.nti = 0;
       ++w.t;
-      if (++w.ng >= pl.NT / pl.NTI) {
+      if (++w.ng >= pl.NG) {
         w.ng = 0;
         if (++w.mg >= pl.n_mgroups) { w.mg = 0; ++w.slot; }
       }
@@ -1088,6 +1109,12 @@ int conv_forward_tma(const ConvArgs& a_in, cudaStream_t s) {
   const int stg_bytes = pl.omode == OUT_SLAB ? 2 * pl.ring * SLAB_BYTES : (pl.omode == OUT_ROWS ? pl.stg_rows * pl.stg_pitch : 0);
   static const bool no_dma = getenv("LAUD_NO_DMA") != nullptr;
   pl.dma = (!no_dma && pl.omode == OUT_SLAB && pl.bmode == BMODE_TMA) ? 1 : 0;
+  pl.NG = pl.NT / pl.NTI;
+  pl.simple = (!a.k_idx && !a.n_idx && !a.sample_idx && !a.bias_t && pl.bmode == BMODE_TMA) ? 1 : 0;
+  pl.c_nfill = nfill_max;
+  pl.c_nk16 = (a.C_in + 15) >> 4;
+  pl.c_cpt = (pl.c_nk16 + 3) >> 2;
+  pl.c_nchunks = pl.c_cpt * taps;
   pl.static_cols = (pl.omode != OUT_ROWS && !a.n_idx && !a.n_mask) ? 1 : 0;
   pl.stab_cols = round_up(a.C_out, 64) + BN_MAX;              // reads of a partial last tile stay inside the (zero) padding
   int stab_bytes = pl.static_cols ? 2 * pl.stab_cols * 4 : 0;
