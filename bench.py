@@ -65,7 +65,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)],
+                                          "-lms", "50", "-i", str(self.index)],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -231,9 +231,9 @@ def run_graft(args):
                 ms = t.item()
             return ms
 
-        with ClockSampler(local) as clk:
-            ms_total = timed(step_resident, args.steps, args.warmup)
-        clocks = clk.summary()
+        clk = ClockSampler(local)          # sampled across BOTH timed regions (resident and end to end)
+        clk.__enter__()
+        ms_total = timed(step_resident, args.steps, args.warmup)
         ms_step = ms_total / args.steps
         value = world * B * args.steps / (ms_total * 1e-3)
 
@@ -272,6 +272,8 @@ def run_graft(args):
             ev.record()
         ms_e2e = timed(step_e2e, args.steps, args.warmup)
         copy_stream.synchronize()
+        clk.__exit__(None, None, None)
+        clocks = clk.summary()
         e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
         h2d = x_host.numel() * x_host.element_size()
         d2h = logits_host.numel() * logits_host.element_size()
