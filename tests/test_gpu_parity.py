@@ -157,7 +157,7 @@ class TestOperators:
 
 # --------------------------------------------------------------------------- the mask-conditioned convolution
 def _conv_case(seed, B, H, Cin, Cout, k, stride, *, kgather=0, ngather=0, rho=0.6, residual=False, mask_groups=0,
-               prebias=False, rows=False, samples=False, relu=_lib.RELU_ALL, tapbias=False):
+               prebias=False, rows=False, samples=False, relu=_lib.RELU_ALL, tapbias=False, nmaskdense=0):
     """Build one laud_conv_forward case + its fp32 oracle result (F.conv2d on CPU)."""
     r = np.random.RandomState(seed)
     pad = 1 if k == 3 else 0
@@ -202,11 +202,19 @@ def _conv_case(seed, B, H, Cin, Cout, k, stride, *, kgather=0, ngather=0, rho=0.
             kern[0, 0, tap // k, tap % k] = 1.0
             valid = F.conv2d(ones, kern, stride=stride, padding=pad)          # [1,1,Ho,Ho] in {0,1}
             y = y + valid * bt[:, tap].view(B, Cout, 1, 1)
+    if nmaskdense:
+        # masked-dense channel gate: the accumulator of a gated channel is zeroed BEFORE the folded BN (laud_resnet.py:116)
+        nm = gate(Cout // nmaskdense)
+        d["nmask_dense"] = nm
+        y = y * nm.float().repeat_interleave(nmaskdense, dim=1).view(B, Cout, 1, 1)
     y = y * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
     if mask_groups:
         om = torch.from_numpy((r.uniform(size=(B, mask_groups, Ho, Ho)) < 0.5).astype(np.uint8))
         d["out_mask"] = om
-        y = y * om.float().repeat_interleave(Cout // mask_groups, dim=1)
+        if relu == _lib.RELU_WHERE_GATE0:      # the value is kept; ReLU only where the gate is 0
+            y = torch.where(om.bool().repeat_interleave(Cout // mask_groups, dim=1), y, torch.relu(y))
+        else:
+            y = y * om.float().repeat_interleave(Cout // mask_groups, dim=1)
     if residual:
         res = torch.from_numpy(r.standard_normal((B, Cout, Ho, Ho)).astype(np.float32)).half().float()
         d["res"] = res
@@ -222,6 +230,7 @@ def _conv_case(seed, B, H, Cin, Cout, k, stride, *, kgather=0, ngather=0, rho=0.
         sm[0] = True
         d["samplegate"] = torch.from_numpy(sm.astype(np.uint8))
     d["y"] = y
+    d["relu"] = relu
     return d
 
 
@@ -283,7 +292,10 @@ def _run_conv_case(d, impl, use_wt=False):
         sidx = torch.zeros(B, dtype=torch.int32, device=DEV)
         sidx[:len(s)] = s
         kw.update(sample_idx=sidx, sample_cnt=torch.tensor([len(s)], dtype=torch.int32, device=DEV))
-    relu = _lib.RELU_ALL if bool((d["y"] >= 0).all()) else _lib.RELU_NONE
+    relu = d["relu"]
+    if "nmask_dense" in d:
+        nm = d["nmask_dense"]
+        kw.update(n_mask=nm.contiguous().to(DEV), n_mask_gran=Cout // nm.shape[1])
     _engine.run_conv(xd, wd, y, B, H, H, Cin, Ho, Ho, Cout, k, d["stride"], d["pad"], ldx=ldx, ldy=ldy,
                      scale=d["scale"].to(DEV), shift=d["shift"].to(DEV), relu=relu, impl=impl, **kw)
     torch.cuda.synchronize()
@@ -335,6 +347,22 @@ CONV_CASES = {
     "1x1_tail_rows": dict(B=1, H=13, Cin=40, Cout=72, k=1, stride=1),
     "3x3_kn_gather_big": dict(B=3, H=14, Cin=256, Cout=256, k=3, stride=1, kgather=2, ngather=2, prebias=True),
     "1x1_kgather_wide": dict(B=3, H=14, Cin=256, Cout=1024, k=1, stride=1, kgather=2, prebias=True, residual=True),
+    # shapes that exercise the TMA-staged kernel's modes: halo tiles over several m-groups, 256-wide tiles, direct
+    # stores, flat GEMM across sample boundaries, traversal-stride boxes, masked-dense gates, sample lists, gated ReLU
+    "3x3_dense_halo_big": dict(B=3, H=28, Cin=128, Cout=256, k=3, stride=1),
+    "3x3_dense_halo_56": dict(B=1, H=56, Cin=64, Cout=64, k=3, stride=1),
+    "3x3_dense_halo_7": dict(B=5, H=7, Cin=192, Cout=512, k=3, stride=1),
+    "3x3_s2_dense": dict(B=2, H=28, Cin=64, Cout=128, k=3, stride=2),
+    "1x1_flat_res_wide": dict(B=5, H=7, Cin=256, Cout=1024, k=1, stride=1, residual=True),
+    "1x1_flat_partial_N": dict(B=3, H=5, Cin=64, Cout=200, k=1, stride=1, relu=_lib.RELU_NONE),
+    "1x1_flat_longK_direct": dict(B=3, H=14, Cin=1024, Cout=256, k=1, stride=1),
+    "1x1_nmask_dense": dict(B=4, H=14, Cin=128, Cout=256, k=1, stride=1, nmaskdense=2),
+    "1x1_nmask_dense_longK": dict(B=3, H=14, Cin=1024, Cout=256, k=1, stride=1, nmaskdense=2),
+    "3x3_nmask_dense_halo": dict(B=3, H=14, Cin=256, Cout=256, k=3, stride=1, nmaskdense=2),
+    "1x1_samples_res": dict(B=6, H=7, Cin=64, Cout=128, k=1, stride=1, samples=True, residual=True),
+    "3x3_samples": dict(B=5, H=14, Cin=64, Cout=64, k=3, stride=1, samples=True),
+    "1x1_s2_gate0relu": dict(B=3, H=14, Cin=32, Cout=64, k=1, stride=2, mask_groups=1, relu=_lib.RELU_WHERE_GATE0),
+    "1x1_gate0relu": dict(B=3, H=14, Cin=64, Cout=128, k=1, stride=1, mask_groups=1, relu=_lib.RELU_WHERE_GATE0),
 }
 # H1 constants entering as an extra K=16 MMA step (w_t path only)
 TAPBIAS_CASES = {
