@@ -355,7 +355,8 @@ def run_graft(args):
                        "replicated weights, one NCCL all-gather of logits per step" if world > 1 else "single GPU",
                        "l2": "inputs + activations per step (>2 GB) exceed the 126 MB L2; no explicit flush",
                        "weights": "seeded synthetic, BN stats + gate biases calibrated to channel density 0.6",
-                       "cuda_graph": True, "channel_exec": model._engine.channel_exec},
+                       "cuda_graph": True, "channel_exec": model._engine.channel_exec,
+                       "graph_chains": graphed.splits},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": graphed.launches * args.steps, "launches_per_step": graphed.launches,

@@ -575,6 +575,24 @@ def test_sharding_invariance(cuda_lib):
     assert torch.equal(full, torch.cat([a, b]))
 
 
+@pytest.mark.parametrize("name", ["tiny_channel", "tiny_layer"])
+def test_split_chains_match_unsplit_forward(cuda_lib, name):
+    """The CUDA-graphed forward as two parallel chains over the halves of the batch (ResNetEngine.forward_split):
+    logits bit-identical to the single-chain forward, statistics identical (summed counts, whole-batch denominators)."""
+    cfg, sd, x, z = load_case(name)
+    model = _model(cfg, sd)
+    xd = x.to(DEV)
+    with torch.no_grad():
+        logits, stats = model._engine.forward(xd)
+        logits, stats = logits.clone(), stats.clone()
+        g = _engine.GraphedForward(model._engine, xd, splits=2)
+        assert g.splits == 2
+        l2, s2 = g.replay()
+        torch.cuda.synchronize()
+    assert torch.equal(l2, logits)
+    assert torch.equal(s2, stats)
+
+
 def test_resnet50_spatial_bs8_full_size(cuda_lib):
     """BASELINE config 0 (LAUD-ResNet50 spatial-skip, batch 8, 224x224): full-size run through
     size-independent properties (the CPU oracle at this size is exercised by bench.py's cpu leg)."""
