@@ -1,31 +1,38 @@
-// The product kernel of the mask-conditioned convolution (v4): a persistent,
-// warp-specialised gather-GEMM on tcgen05 tensor cores whose dense operands
-// move with TMA tensor-tile copies.
+// The product kernel of the mask-conditioned convolution: a persistent, warp-specialised
+// implicit GEMM on tcgen05 tensor cores whose dense operands move with TMA tensor-tile copies.
 //
 //   D[m, n] = sum_{tap, k} A[m, (tap,k)] * W[n, (tap,k)]
-//     m : output pixels of ONE sample: MT (1|2) tiles of up to 128 pixels share every weight stage
+//     m : output pixels: MT (1|2) tiles of up to 128 pixels share every weight stage.  Tiles belong
+//         to ONE sample when anything is per sample (channel lists / gates, sample lists, 3x3);
+//         a 1x1 layer with nothing per sample is one FLAT GEMM over all B*H*W pixels.
 //     n : output channels of one tile (BN = 64 | 128 | 256)
-//     k : that sample's ACTIVE input channels (compact), per filter tap
+//     k : input channels per filter tap (the sample's ACTIVE ones, compact, in the gathered modes)
 //
-// 512 threads, one CTA per SM, static round-robin over (sample, m-group, n-group):
-//   warps 0-7   epilogue : tcgen05.ld the fp32 accumulators out of TMEM; folded BN / gate /
-//                          residual / ReLU in registers.
-//                          SLAB mode: each half (4 warps) owns a ring of [128 px][64 ch]
-//                          swizzled slabs; residual slabs ARRIVE by TMA (prefetched two tasks
-//                          ahead), the fp16 result overwrites them in place and LEAVES by TMA
-//                          (one cp.async.bulk.tensor per slab instead of one copy per pixel row).
-//                          ROWS mode (K-row-gather with compaction of the active output
-//                          channels): word-swizzled row staging, coalesced cooperative flush.
-//   warp  8     TMA      : one lane issues the A tiles (im2col by 4-d tile boxes whose
-//                          out-of-bounds taps are zero-filled by the TMA unit) and, when the
-//                          weights are not gathered, the B tile.
+// 512 threads, one CTA per SM, one contiguous range of work items (sample, m-group, n-group) per CTA:
+//   warps 0-7   epilogue : tcgen05.ld the fp32 accumulators out of TMEM; folded BN / gates /
+//                          residual / ReLU in registers.  Column tables (scale, shift) are loaded
+//                          once per CTA when they do not depend on the sample.
+//                          SLAB mode: each half (4 warps) owns a ring of [128 px][64 ch] swizzled
+//                          slabs; residual slabs ARRIVE by TMA (kept ring-1 tasks ahead), the fp16
+//                          result overwrites them in place and LEAVES by TMA.
+//                          DIRECT mode (long reductions, no residual): registers -> global.
+//                          ROWS mode (K-row gather + compaction of the active output channels):
+//                          word-swizzled row staging, coalesced cooperative flush.
+//   warp  8     TMA      : one lane issues the activation tiles - 3-d boxes for 1x1 layers, 4-d boxes
+//                          for 3x3 / stride-2 layers (im2col and subsampling by the TMA unit, taps
+//                          that fall outside the image zero-filled) - and the weight tiles when they
+//                          are not gathered.  HALO mode (3x3, stride 1, shared weights): the
+//                          activations of an m-group are staged ONCE per 64-channel chunk with their
+//                          zero halo; the nine taps are that tile read at nine row offsets.
 //   warp  9     MMA      : one lane issues tcgen05.mma (M=128, N<=256, K=16); accumulators in
 //                          TMEM, multi-buffered so the epilogue of one item overlaps the MMAs
 //                          of the next.
 //   warps 10-15 gather   : per-sample weight gathers with cp.async into the UMMA swizzle layout
 //                          (ROWS: active OUTPUT channels of K-major weights; KROWS: active INPUT
 //                          channels of the transposed weights) + the H1-constant K=16 step.
-// Layouts it does not take (stride 2, row lists, per-class pre-bias, KUNITS) run on the v3
+//                          With shared weights two of their lanes are the slab DMA threads: they
+//                          issue the TMA stores / residual loads of the two epilogue halves.
+// Layouts it does not take (row lists, per-class pre-bias, KUNITS gathers) run on the cp.async-staged
 // kernel (conv_umma.cu).  Restates (does not port) laud_resnet.py:115-144 of the reference.
 #include <cuda.h>
 #include <stdlib.h>
@@ -1035,9 +1042,8 @@ int conv_forward_tma(const ConvArgs& a_in, cudaStream_t s) {
   Plan pl{};
   const int HWo = a.H_out * a.W_out;
   const int taps = a.ksize * a.ksize;
-  const int taps_h = taps;
   pl.bmode = a.k_idx ? BMODE_KROWS : (a.n_idx ? BMODE_ROWS : BMODE_TMA);
-  const long long ktotal = (long long)taps_h * a.C_in;
+  const long long ktotal = (long long)taps * a.C_in;
   pl.omode = (a.k_idx && a.n_idx) ? OUT_ROWS : ((!a.residual && ktotal >= 512) ? OUT_DIRECT : OUT_SLAB);
   const bool row_tiles = a.ksize == 3 || a.stride == 2;   // m-tiles of whole output rows: 4-d boxes (im2col / subsampling by TMA)
   static const bool no_halo = getenv("LAUD_NO_HALO") != nullptr;
