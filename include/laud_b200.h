@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define LAUD_ABI_VERSION 2
+#define LAUD_ABI_VERSION 3
 
 enum {
   LAUD_OK = 0,
@@ -96,6 +96,16 @@ int laud_masker_channel_from_pooled(const float* pooled, int B, int C, int layer
                                     const float* w2, const float* b2, int G,
                                     float* logits_out, uint8_t* mask_out, int32_t* idx_out,
                                     int32_t* cnt_out, int32_t* total_out, void* stream);
+
+/* Same decision from the fused-GAP partial sums a producing laud_conv_forward left in
+ * laud_conv_desc::gap_partial (fp32 [B, gap_tiles, C], layout documented there): pooled[b,c] =
+ * (sum of sample b's partials in ascending k) / HW, then MLP -> keep>=drop -> compaction as
+ * laud_masker_channel_mlp.  Replaces the GAP read of Masker_channel_MLP.forward (models/utils.py:113-117). */
+int laud_masker_channel_from_partials(const float* partials, int B, int HW, int C, int gap_tiles, int layers,
+                                      const float* w1, const float* b1, int hidden,
+                                      const float* w2, const float* b2, int G,
+                                      float* pooled_out, float* logits_out, uint8_t* mask_out,
+                                      int32_t* idx_out, int32_t* cnt_out, int32_t* total_out, void* stream);
 
 /* Deterministic global average pool of fp16 [B,HW,ldx] (first C channels) -> fp32 [B,C]. */
 int laud_global_avg_pool(const void* x, int B, int HW, int C, int ldx,
@@ -180,7 +190,14 @@ typedef struct laud_conv_desc {
   const int32_t* sample_idx; const int32_t* sample_cnt;
   const int32_t* row_idx; const int32_t* row_cnt;
   int32_t n_pad_align;      /* 0 | 8 | 16: zero-pad each sample's compact output channels to this multiple */
-  float* gap_partial;       /* optional fused GAP of the OUTPUT: fp32 [B, gap_tiles, C_out] partial sums */
+  float* gap_partial;       /* optional fused global-average-pool of the OUTPUT (feeds the next block's channel masker,
+                               models/utils.py:113-117, without re-reading the activations): fp32
+                               [B, gap_tiles, C_out] PARTIAL SUMS.  The B*H*W output pixels are cut into tiles of 128
+                               consecutive pixels; slot k of sample b holds the sum over the pixels of b inside the
+                               k-th tile that contains any of them (k = tile - (b*H*W)/128; slots past the last
+                               such tile are not written).  Needs gap_tiles >= (H*W-1)/128 + 2.  Only 1x1 stride-1
+                               layers with nothing per sample (no lists, gates, n_mask), C_out % 64 == 0, H*W >= 43;
+                               anything else returns LAUD_E_UNSUPPORTED.  laud_masker_channel_from_partials consumes it. */
   int32_t gap_tiles;
   const void* w_t;          /* optional transposed copy of w: fp16 [ksize*ksize, C_in, C_out].  With k_idx it
                                selects the K-row-gather path (16-byte gathers of the active input channels;

@@ -47,6 +47,12 @@ def round_up(v: int, a: int) -> int:
     return (v + a - 1) // a * a
 
 
+def gap_tiles(hw: int) -> int:
+    """Partial-sum slots per sample of the fused GAP (laud_conv_desc::gap_tiles): 128-pixel tiles of the flat pixel
+    list that can hold pixels of one sample."""
+    return (hw - 1) // 128 + 2
+
+
 class conv_profile:
     """Context manager: bracket every laud_conv_forward launch with CUDA events
     on the launching stream (bench.py's per-kernel timing).  `.total_ms()` after
@@ -78,7 +84,8 @@ def run_conv(x, w, y, B, H_in, W_in, C_in, H_out, W_out, C_out, ksize, stride, p
              k_idx=None, k_cnt=None, k_gran=1, n_idx=None, n_cnt=None, n_gran=1,
              pre_bias=None, pre_bias_classes=0, pre_bias_ld=0, out_mask=None, mask_groups=1,
              sample_idx=None, sample_cnt=None, row_idx=None, row_cnt=None, n_pad_align=0,
-             impl=_lib.CONV_AUTO, tag="conv", w_t=None, bias_t=None, bias_ld=0, n_mask=None, n_mask_gran=1) -> None:
+             impl=_lib.CONV_AUTO, tag="conv", w_t=None, bias_t=None, bias_ld=0, n_mask=None, n_mask_gran=1,
+             gap_partial=None, gap_tiles=0) -> None:
     """Fill a laud_conv_desc and enqueue laud_conv_forward on the current stream."""
     d = ConvDesc()
     d.x, d.ldx = ptr(x), ldx if ldx is not None else x.shape[-1]
@@ -99,7 +106,7 @@ def run_conv(x, w, y, B, H_in, W_in, C_in, H_out, W_out, C_out, ksize, stride, p
     d.sample_idx, d.sample_cnt = ptr(sample_idx), ptr(sample_cnt)
     d.row_idx, d.row_cnt = ptr(row_idx), ptr(row_cnt)
     d.n_pad_align = n_pad_align
-    d.gap_partial, d.gap_tiles = None, 0
+    d.gap_partial, d.gap_tiles = ptr(gap_partial), gap_tiles
     d.w_t = ptr(w_t)
     d.bias_t, d.bias_ld = ptr(bias_t), bias_ld
     d.n_mask, d.n_mask_gran = ptr(n_mask), n_mask_gran
@@ -198,6 +205,8 @@ class ResNetEngine:
         # and the block output is written in place over the block input (skipped samples are untouched: relu(identity)
         # == identity bit-exactly, laud_resnet.py:133-144); "mask" = masked-dense (compute all, zero the gated rows).
         self.layer_exec = os.environ.get("LAUD_LAYER_EXEC", "skip")
+        # conv3 leaves the global-average-pool partial sums of the block output for the next block's channel masker
+        self.fuse_gap = os.environ.get("LAUD_NO_GAP_FUSE") is None
         self._ws: Dict[tuple, dict] = {}
 
     # ------------------------------------------------------------------ prepare
@@ -301,6 +310,8 @@ class ResNetEngine:
             lidx=torch.empty((B * g_max,), **i32), lcnt=torch.empty((B,), **i32),
             stats=torch.empty(nb * 5 + 1, dtype=torch.float32, device=dev),
             logits=None,
+            gap=torch.empty(max(B * gap_tiles(p.H_out * p.H_out) * p.outplanes for p in self.plans), dtype=torch.float32,
+                            device=dev),
         )
         consts = self.stats_consts.clone()
         for i, p in enumerate(self.plans):
@@ -316,8 +327,10 @@ class ResNetEngine:
     # ------------------------------------------------------------------ blocks
     def run_block(self, p: BlockPlan, x: torch.Tensor, out: torch.Tensor, idbuf: torch.Tensor, B: int, ws: dict,
                   keep: Optional[BlockOutputs] = None, forced_channel_mask: Optional[torch.Tensor] = None,
-                  forced_spatial_mask: Optional[torch.Tensor] = None) -> None:
-        """x: fp16 [B,H_in,H_in,inplanes] -> out: fp16 [B,H_out,H_out,outplanes]."""
+                  forced_spatial_mask: Optional[torch.Tensor] = None, gap_in: bool = False, gap_out: bool = False) -> None:
+        """x: fp16 [B,H_in,H_in,inplanes] -> out: fp16 [B,H_out,H_out,outplanes].
+        gap_in: ws["gap"] holds the fused-GAP partial sums of x (left by the previous block's conv3): the channel
+        masker decides from them instead of pooling x.  gap_out: conv3 leaves the partial sums of `out` there."""
         blk = p.module
         L = lib()
         st = stream_ptr()
@@ -340,6 +353,8 @@ class ResNetEngine:
                 gate.pooled = torch.empty((B, x.shape[-1]), dtype=torch.float32, device=x.device)
             if forced_channel_mask is not None:
                 self._force_channel_gate(gate, forced_channel_mask, counts[0:1])
+            elif gap_in:
+                blk.masker_channel.gate_from_partials(ws["gap"], B, Hi * Hi, p.inplanes, gap_tiles(Hi * Hi), counts[0:1], gate)
             else:
                 blk.masker_channel.gate_nhwc(x[:B * Hi * Hi * p.inplanes].view(B, Hi, Hi, p.inplanes), counts[0:1],
                                              out=gate, partial_ws=ws["partial"])
@@ -453,7 +468,8 @@ class ResNetEngine:
                      pre_bias_classes=1 if (sparse_gate and not use_wt) else 0,
                      bias_t=T.view(-1)[9 * p.width:] if use_wt else None, bias_ld=Tn if use_wt else 0,
                      pre_bias_ld=p.outplanes if sparse_gate else 0, out_mask=m3, mask_groups=p.g_spatial if m3 is not None else 1,
-                     w_t=p.w3t if (sparse_gate and use_wt) else None, **ck)
+                     w_t=p.w3t if (sparse_gate and use_wt) else None,
+                     gap_partial=ws["gap"] if gap_out else None, gap_tiles=gap_tiles(Ho * Ho) if gap_out else 0, **ck)
         if keep is not None:
             if gate is not None:
                 keep.channel_mask, keep.channel_idx, keep.channel_cnt = gate.mask.clone(), gate.idx.clone(), gate.cnt.clone()
@@ -462,6 +478,16 @@ class ResNetEngine:
             keep.a2 = a2[:B * Ho * Ho * ld12].view(B, Ho, Ho, ld12).clone()
             keep.out = out[:B * Ho * Ho * p.outplanes].view(B, Ho, Ho, p.outplanes).clone()
         return out          # the buffer that holds the block output (the input buffer for an in-place layer skip)
+
+    def _gap_fusable(self, p: BlockPlan) -> bool:
+        """True if block p's conv3 can leave the GAP partial sums of its output for the NEXT block's channel masker:
+        the next block pools its input for a channel gate, and this conv3 is a flat GEMM (1x1, nothing per sample:
+        masked-dense channel execution, no spatial mask, no layer skip) on the tcgen05 path."""
+        if not self.fuse_gap or p.index + 1 >= len(self.plans) or not self.plans[p.index + 1].use_c:
+            return False
+        if p.use_s or (p.use_c and self.channel_exec != "dense") or self.impl not in (_lib.CONV_AUTO, _lib.CONV_UMMA):
+            return False
+        return p.outplanes % 64 == 0 and p.H_out * p.H_out >= 43
 
     @staticmethod
     def _force_channel_gate(gate, mask: torch.Tensor, total: torch.Tensor) -> None:
@@ -498,6 +524,7 @@ class ResNetEngine:
         check(L.laud_stem_forward(ptr(xh), B, H, W, ptr(self.stem_w), C0, ptr(self.stem_s), ptr(self.stem_t),
                                   ptr(bufs[cur]), st), "laud_stem_forward")
         nvtx = bool(os.environ.get("LAUD_NVTX"))
+        gap_in = False
         for p in self.plans:
             nxt = (cur + 1) % 3
             idb = (cur + 2) % 3
@@ -507,7 +534,9 @@ class ResNetEngine:
                 keep.append(ko)
             if nvtx:
                 torch.cuda.nvtx.range_push(f"blk{p.index}")
-            res_buf = self.run_block(p, bufs[cur], bufs[nxt], bufs[idb], B, ws, ko)
+            gap_out = self._gap_fusable(p)
+            res_buf = self.run_block(p, bufs[cur], bufs[nxt], bufs[idb], B, ws, ko, gap_in=gap_in, gap_out=gap_out)
+            gap_in = gap_out
             if nvtx:
                 torch.cuda.nvtx.range_pop()
             if res_buf is not bufs[cur]:

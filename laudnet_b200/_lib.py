@@ -60,6 +60,7 @@ SIGNATURES = {
     "laud_conv_profile_read": ([C.POINTER(C.c_float)], _i),
     "laud_masker_channel_mlp": ([_vp, _i, _i, _i, _i, _fp, _fp, _i, _fp, _fp, _i, _fp, _fp, _fp, _u8p, _i32p, _i32p, _i32p, _vp], _i),
     "laud_masker_channel_from_pooled": ([_fp, _i, _i, _i, _fp, _fp, _i, _fp, _fp, _i, _fp, _u8p, _i32p, _i32p, _i32p, _vp], _i),
+    "laud_masker_channel_from_partials": ([_fp, _i, _i, _i, _i, _i, _fp, _fp, _i, _fp, _fp, _i, _fp, _fp, _u8p, _i32p, _i32p, _i32p, _vp], _i),
     "laud_global_avg_pool": ([_vp, _i, _i, _i, _i, _fp, _fp, _vp], _i),
     "laud_masker_spatial": ([_vp, _i, _i, _i, _i, _fp, _fp, _i, _i, _fp, _u8p, _i32p, _vp], _i),
     "laud_expand_mask": ([_u8p, _i, _i, _i, _i, _i, _i, _u8p, _i32p, _vp], _i),

@@ -112,7 +112,9 @@ extern "C" int laud_conv_forward(const laud_conv_desc* d, int impl, void* stream
   LAUD_REQUIRE(d->relu_mode >= 0 && d->relu_mode <= 2, "laud_conv_forward: bad relu_mode");
   LAUD_REQUIRE(d->relu_mode != LAUD_RELU_WHERE_GATE0 || d->out_mask, "laud_conv_forward: RELU_WHERE_GATE0 needs out_mask");
   if (d->residual) LAUD_REQUIRE(d->ldr >= d->C_out && !d->n_idx, "laud_conv_forward: residual needs dense output channels");
-  LAUD_REQUIRE(d->gap_partial == nullptr, "laud_conv_forward: fused GAP epilogue not available in this build");
+  if (d->gap_partial)
+    LAUD_REQUIRE(d->gap_tiles >= 1 && (impl == LAUD_CONV_AUTO || impl == LAUD_CONV_UMMA),
+                 "laud_conv_forward: gap_partial needs gap_tiles >= 1 and the tcgen05 path");
   if (d->bias_t)
     LAUD_REQUIRE(d->w_t && d->k_idx && !d->pre_bias && d->bias_ld % 8 == 0 && d->ksize * d->ksize <= 9 &&
                      (reinterpret_cast<uintptr_t>(d->bias_t) & 15) == 0,
@@ -144,6 +146,7 @@ extern "C" int laud_conv_forward(const laud_conv_desc* d, int impl, void* stream
   a.wt = (const __half*)d->w_t;
   a.bias_t = (const __half*)d->bias_t; a.bias_ld = d->bias_ld;
   a.n_mask = d->n_mask; a.n_mask_gran = d->n_mask_gran;
+  a.gap_hw = 0;
 
   cudaStream_t s = (cudaStream_t)stream;
   switch (impl) {
@@ -157,6 +160,10 @@ extern "C" int laud_conv_forward(const laud_conv_desc* d, int impl, void* stream
       {
         static const bool force_v3 = getenv("LAUD_CONV_V3") != nullptr;     // A/B switch for profiling
         if (!force_v3 && conv_tma_supported(a)) return conv_forward_tma(a, s);
+      }
+      if (a.gap_partial) {
+        set_error("laud_conv_forward: fused GAP (gap_partial) is only available on the TMA-staged kernel");
+        return LAUD_E_UNSUPPORTED;
       }
       return conv_forward_umma(a, s);
     case LAUD_CONV_HMMA:

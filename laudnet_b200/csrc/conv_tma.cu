@@ -92,6 +92,7 @@ struct alignas(16) Tables {
   unsigned long long full[MAX_STAGES], empty[MAX_STAGES], tfull[4], tempty[4], rfull[2][MAX_RING];
   unsigned long long afull[2], aempty[2];   // halo mode: ring of activation tiles (one per 64-channel chunk)
   unsigned long long sready[2][MAX_RING], sfree[2][MAX_RING];   // slab hand-off between the epilogue halves and their DMA threads
+  unsigned long long gdone[2][MAX_RING];    // fused GAP: the pooling warps have read the slab
   uint32_t tmem_base;
 };
 
@@ -117,6 +118,8 @@ struct Plan {              // host-computed launch geometry
   int dma;                 // 1: slab stores / residual prefetches are issued by two otherwise idle threads (shared-weight layers)
   int simple;              // 1: nothing per sample (no lists, gathers): Sub fields below are launch constants
   int c_nfill, c_nk16, c_cpt, c_nchunks, NG;
+  int gap;                 // 1: fused global-average-pool partial sums of the output (flat 1x1 layers, OUT_SLAB + dma)
+  int dbg;                 // LAUD_DBG timing experiments (wrong results): 2 no activation loads, 4 no MMAs, 8 no epilogue work
 };
 
 struct Sub {               // one (sample, m-group, n-tile) unit of work
@@ -356,6 +359,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
       for (int i = 0; i < MAX_RING; ++i) {
         mbar_init(&T.sready[h][i], HALF_THREADS);
         mbar_init(&T.sfree[h][i], 1);
+        mbar_init(&T.gdone[h][i], 2);
       }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -411,8 +415,11 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
         // issue the next activation tile (chunk a_next of the A stream) into its slot
         auto issue_a = [&]() {
           const int slot = a_next & 1;
+          if (pl.dbg & 2) mbar_arrive(&T.afull[slot]);
+          else {
           mbar_arrive_expect_tx(&T.afull[slot], (uint32_t)pl.a_tx);
           tma_load_4d(a_base + slot * pl.a_slot_bytes, &map_a, &T.afull[slot], a_kq * 64, -1, (sa.mt0) * pl.R - 1, sa.b);
+          }
           ++a_next;
           if (++a_kq >= sa.cpt) {
             a_kq = 0;
@@ -444,7 +451,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
       } else
       while (walker_next(a, pl, T, wk, s)) {
         KP_LAP(0);                                   // decode
-        const uint32_t tx = (uint32_t)(s.mt_cnt * pl.a_tx + (pl.bmode == BMODE_TMA ? pl.b_tx : 0));
+        const uint32_t tx = (uint32_t)(((pl.dbg & 2) ? 0 : s.mt_cnt * pl.a_tx) + (pl.bmode == BMODE_TMA ? pl.b_tx : 0));
         for (int tap = 0; tap < taps; ++tap) {
           const int ty = tap / a.ksize, tx_ = tap - ty * a.ksize;
           for (int kq = 0; kq < s.cpt; ++kq) {
@@ -453,7 +460,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
             KP_LAP(1);                               // wait for a free stage
             const uint32_t As = smem_base + stage * pl.stage_bytes;
             mbar_arrive_expect_tx(&T.full[stage], tx);
-            for (int m = 0; m < s.mt_cnt; ++m) {
+            for (int m = 0; m < ((pl.dbg & 2) ? 0 : s.mt_cnt); ++m) {
               const int mt = s.mt0 + m;
               if (pl.R) tma_load_4d(As + m * A_TILE_BYTES, &map_a, &T.full[stage], k0, tx_ - a.pad, mt * pl.R * a.stride + ty - a.pad, s.b);
               else tma_load_3d(As + m * A_TILE_BYTES, &map_a, &T.full[stage], k0, mt * BM, s.b);
@@ -505,6 +512,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
                 // tile m, tap (ty,tx): 128 consecutive rows of the padded image starting at row (m R + ty) Wp + tx
                 const uint32_t aaddr = Aslot + (uint32_t)(((m * pl.R + ty) * pl.Wp + tx_) * 128);
                 const uint64_t ad = umma_desc(aaddr, 16, 1024) | (pl.halo_bo ? ((uint64_t)((aaddr >> 7) & 7u) << 49) : 0ull);
+                if (!(pl.dbg & 4))
                 for (int k = 0; k < n16; ++k)
                   umma_f16(d_tmem + m * pl.acc_cols, ad + 2 * k, bd + 2 * k, idesc, (kq | tap | k) ? 1u : 0u);
               }
@@ -530,6 +538,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
           const uint64_t bstep = pl.bmode == BMODE_KROWS ? 128 : 2;
           for (int m = 0; m < s.mt_cnt; ++m) {
             const uint64_t ad = umma_desc(As + m * A_TILE_BYTES, 16, 1024);
+            if (!(pl.dbg & 4))
             for (int k = 0; k < n16; ++k)
               umma_f16(d_tmem + m * pl.acc_cols, ad + 2 * k, bd + bstep * k, idesc, (ch | k) ? 1u : 0u);
           }
@@ -668,7 +677,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
       }
       if (pt == 0) KP_FLUSH(2);
       asm volatile("cp.async.wait_all;" ::: "memory");
-    } else if (pl.dma && warp < GATHER_WARP0 + 2 && lane == 0) {
+    } else if (pl.dma && warp < GATHER_WARP0 + 2 && lane == 0 && !(pl.dbg & 8)) {
       // =========================================================== slab DMA thread of epilogue half h
       // Issues the TMA store of every finished slab and keeps the residual slabs ring - 1 tasks ahead, so the 128
       // epilogue threads of the half never wait for a copy to be ISSUED, only for data (rfull) or space (sfree).
@@ -697,6 +706,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
         if (j >= 1) {
           bulk_wait_read_n<1>();                                 // the PREVIOUS store has been read out of its slab
           const int ps = (j - 1) % pl.ring;
+          if (pl.gap) mbar_wait(&T.gdone[h][ps], (uint32_t)((j - 1) / pl.ring) & 1u);   // ... and pooled
           if (has_res) {
             if (cursor_next(a, pl, T, cl, h)) {                  // refill it: residual of task (j - 1) + ring
               int pm0, prow;
@@ -710,6 +720,73 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
         }
       }
       bulk_wait_all();
+    } else if (pl.gap && warp >= GATHER_WARP0 + 2 && !(pl.dbg & 8)) {
+      // =========================================================== pooling warps (fused GAP of the OUTPUT)
+      // Two warps per epilogue half read every finished slab ([128 px][64 ch] fp16, exactly the values that go to
+      // memory) once more and add up its columns per sample: lane = channel pair, each warp 64 of the 128 rows.
+      // The per-(sample, tile) sums go to gap_partial[sample][k][C_out], k = tile - first tile of the sample; whoever
+      // consumes them adds the (at most gap_tiles) partials of a sample in ascending k: a fixed order.
+      const int gw = warp - (GATHER_WARP0 + 2);
+      const int h = gw >> 1, part = gw & 1;
+      unsigned char* ring = stg + (size_t)h * pl.ring * SLAB_BYTES;
+      float* gp = stab + (pl.static_cols ? 2 * pl.stab_cols : 0) + h * (2 * 4 * 64);   // [task parity][half][part][segment][64 ch]
+      const int hw = a.gap_hw;
+      Cursor cs;
+      walker_init(a, pl, cs.w);
+      cs.mt = 0; cs.sl = 0; cs.have = 0;
+      for (int j = 0; cursor_next(a, pl, T, cs, h); ++j) {
+        const int slot = j % pl.ring;
+        int m0, rows;
+        tile_rows(a, pl, cs.s.mt0 + cs.mt, m0, rows);            // flat layer: m0 = first pixel of the tile in [B*H*W]
+        const int b_first = m0 / hw, b_last = (m0 + rows - 1) / hw;
+        const int nseg = b_last - b_first + 1;                   // <= 4 (host checks hw)
+        const uint32_t slab = smem_u32(ring + slot * SLAB_BYTES);
+        const int r_lo = part * 64, r_hi = min(rows, part * 64 + 64);
+        mbar_wait(&T.sready[h][slot], (uint32_t)(j / pl.ring) & 1u);
+        float* gpj = gp + (j & 1) * (2 * 2 * 4 * 64);            // double-buffered by task parity: one barrier per task
+        const uint32_t lane_off = ((uint32_t)lane & 3u) << 2, lane_chunk = (uint32_t)lane >> 2;
+        for (int sg = 0; sg < nseg; ++sg) {
+          const int lo = max(r_lo, (b_first + sg) * hw - m0), hi = min(r_hi, (b_first + sg + 1) * hw - m0);
+          float acc[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) acc[u] = 0.f;
+          int r = lo;
+#pragma unroll 2
+          for (; r + 3 < hi; r += 4) {                           // four independent rows in flight per step
+            uint32_t wv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              wv[u] = lds_u1(slab + (uint32_t)(r + u) * 128u + ((lane_chunk ^ ((uint32_t)(r + u) & 7u)) << 4) + lane_off);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&wv[u]));
+              acc[2 * u] += f.x;
+              acc[2 * u + 1] += f.y;
+            }
+          }
+          for (; r < hi; ++r) {
+            const uint32_t w0 = lds_u1(slab + (uint32_t)r * 128u + ((lane_chunk ^ ((uint32_t)r & 7u)) << 4) + lane_off);
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w0));
+            acc[0] += f.x;
+            acc[1] += f.y;
+          }
+          *reinterpret_cast<float2*>(gpj + (part * 4 + sg) * 64 + 2 * lane) =
+              make_float2((acc[0] + acc[2]) + (acc[4] + acc[6]), (acc[1] + acc[3]) + (acc[5] + acc[7]));
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&T.gdone[h][slot]);           // the slab may be refilled
+        named_bar_sync(6 + h, 64);                               // (also: everyone is done reading gp of task j - 1)
+        {
+          const int c = part * 32 + lane;
+          const int tile = m0 / BM;
+          for (int sg = 0; sg < nseg; ++sg) {
+            const int bb = b_first + sg;
+            const int k = tile - (bb * hw) / BM;
+            a.gap_partial[((size_t)bb * a.gap_tiles + k) * a.C_out + cs.s.n0 + cs.sl * 64 + c] =
+                gpj[sg * 64 + c] + gpj[(4 + sg) * 64 + c];
+          }
+        }
+      }
     }
   } else {
     // =========================================================== epilogue
@@ -726,7 +803,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
     walker_init(a, pl, cur.w);
     cur.mt = 0; cur.sl = 0; cur.have = 0;
     int pf = 0;                                                  // slab tasks whose residual load has been issued
-    if (pl.omode == OUT_SLAB && a.residual && elected && !pl.dma) {
+    if (pl.omode == OUT_SLAB && a.residual && elected && !pl.dma && !(pl.dbg & 8)) {
       for (; pf < pl.ring - 1; ++pf) {
         if (!cursor_next(a, pl, T, cur, h)) break;
         int m0, rows;
@@ -766,7 +843,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
       const uint32_t tbase = tmem_base + buf * (pl.MT * pl.acc_cols) + ((uint32_t)(q * 32) << 16);
       const bool have_acc = s.nchunks > 0;
 
-      for (int m = 0; m < s.mt_cnt; ++m) {
+      for (int m = 0; m < ((pl.dbg & 8) ? 0 : s.mt_cnt); ++m) {
         int m0, rows;
         tile_rows(a, pl, s.mt0 + m, m0, rows);
         // pixel of this accumulator row inside the tile (halo mode: rows are positions of the padded image)
@@ -1023,12 +1100,15 @@ int conv_forward_tma(const ConvArgs& a_in, cudaStream_t s) {
   // A 1x1 stride-1 layer with nothing per sample (no gather, gate or list) is one flat GEMM over all B*H*W pixels:
   // m-tiles run across sample boundaries, so images smaller than a tile (14x14, 7x7) leave no padded rows.
   ConvArgs a = a_in;
+  bool flat = false;
   static const bool no_flat = getenv("LAUD_NO_FLAT") != nullptr;
   if (!no_flat && a.ksize == 1 && a.stride == 1 && !a.k_idx && !a.n_idx && !a.n_mask && !a.sample_idx && !a.out_mask &&
       !a.bias_t && (long long)a.B * a.H_out * a.W_out < (1ll << 31)) {
+    a.gap_hw = a.H_out * a.W_out;
     a.W_in = a.W_out = a.B * a.H_out * a.W_out;
     a.H_in = a.H_out = 1;
     a.B = 1;
+    flat = true;
   }
   static int num_sms = 0;
   if (num_sms == 0) {
@@ -1081,6 +1161,10 @@ int conv_forward_tma(const ConvArgs& a_in, cudaStream_t s) {
     static const bool slab256 = getenv("LAUD_SLAB_BN128") == nullptr;
     pl.BN = span <= 64 ? 64 : ((span > 128 && (pl.omode == OUT_DIRECT || slab256)) ? 256 : 128);
     if (pl.BN == 256 && pl.omode == OUT_SLAB) pl.MT = 1;   // keep two accumulator buffers: this epilogue must overlap the MMAs
+    {
+      static const int mt1 = getenv("LAUD_MT1") ? atoi(getenv("LAUD_MT1")) : 0;   // experiment: 1 -> 1x1 DIRECT layers, 2 -> 3x3 DIRECT layers
+      if (pl.BN == 256 && pl.omode == OUT_DIRECT && ((a.ksize == 1 && (mt1 & 1)) || (a.ksize == 3 && (mt1 & 2)))) pl.MT = 1;
+    }
     pl.NT = (span + pl.BN - 1) / pl.BN;
     pl.NTI = 1;
   }
@@ -1116,7 +1200,24 @@ int conv_forward_tma(const ConvArgs& a_in, cudaStream_t s) {
   static const bool no_dma = getenv("LAUD_NO_DMA") != nullptr;
   pl.dma = (!no_dma && pl.omode == OUT_SLAB && pl.bmode == BMODE_TMA) ? 1 : 0;
   pl.NG = pl.NT / pl.NTI;
+  // fused GAP of the output: flat layers whose slabs go through the DMA threads; a tile may span at most 4 samples
+  pl.gap = 0;
+  if (a.gap_partial) {
+    const bool can = flat && pl.omode == OUT_SLAB && pl.dma && a.C_out % 64 == 0 && a.gap_hw >= 43 &&
+                     a.gap_tiles >= (a.gap_hw - 1) / BM + 2;
+    if (!can) {
+      set_error("conv_forward_tma: fused GAP needs a flat 1x1 stride-1 layer without per-sample operands, C_out %% 64 == 0, "
+                "H*W >= 43 and gap_tiles >= (H*W - 1) / 128 + 2");
+      return LAUD_E_UNSUPPORTED;
+    }
+    pl.gap = 1;
+  }
+  const int gap_bytes = pl.gap ? 2 * 2 * 2 * 4 * 64 * 4 : 0;
   pl.simple = (!a.k_idx && !a.n_idx && !a.sample_idx && !a.bias_t && pl.bmode == BMODE_TMA) ? 1 : 0;
+  {
+    static const int dbg = getenv("LAUD_DBG") ? atoi(getenv("LAUD_DBG")) : 0;
+    pl.dbg = dbg;
+  }
   pl.c_nfill = nfill_max;
   pl.c_nk16 = (a.C_in + 15) >> 4;
   pl.c_cpt = (pl.c_nk16 + 3) >> 2;
@@ -1124,7 +1225,7 @@ int conv_forward_tma(const ConvArgs& a_in, cudaStream_t s) {
   pl.static_cols = (pl.omode != OUT_ROWS && !a.n_idx && !a.n_mask) ? 1 : 0;
   pl.stab_cols = round_up(a.C_out, 64) + BN_MAX;              // reads of a partial last tile stay inside the (zero) padding
   int stab_bytes = pl.static_cols ? 2 * pl.stab_cols * 4 : 0;
-  int avail = SMEM_LIMIT - 1024 - (int)sizeof(Tables) - stg_bytes - pl.a_region_bytes - stab_bytes;
+  int avail = SMEM_LIMIT - 1024 - (int)sizeof(Tables) - stg_bytes - pl.a_region_bytes - stab_bytes - gap_bytes;
   if (pl.static_cols && avail / pl.stage_bytes < 2) {         // no room beside a two-stage pipeline: per-item tables
     pl.static_cols = 0;
     avail += stab_bytes;
@@ -1132,10 +1233,15 @@ int conv_forward_tma(const ConvArgs& a_in, cudaStream_t s) {
   }
   pl.stages = avail / pl.stage_bytes;
   if (pl.stages > MAX_STAGES) pl.stages = MAX_STAGES;
-  if (pl.stages < 2) return conv_forward_umma(a, s);
+  if (pl.stages < 2) {
+    if (pl.gap) { set_error("conv_forward_tma: no shared memory left for the fused GAP"); return LAUD_E_UNSUPPORTED; }
+    return conv_forward_umma(a, s);
+  }
   pl.full_count = 1 + (pl.bmode == BMODE_TMA ? 0 : GATHER_THREADS);
   const int rows_box = pl.rows_per_tile < HWo ? pl.rows_per_tile : HWo;     // boxes never exceed the tensor extent
-  const int bn_box = pl.BN < a.C_out ? pl.BN : a.C_out;
+  int bn_box = pl.BN < a.C_out ? pl.BN : a.C_out;
+  static const bool dbg_halfb = getenv("LAUD_DBG") && (atoi(getenv("LAUD_DBG")) & 1);   // TIMING EXPERIMENT ONLY (wrong results): half of every weight tile
+  if (dbg_halfb && pl.bmode == BMODE_TMA) bn_box /= 2;
   pl.a_tx = pl.halo ? 128 * pl.Wp * halo_box_rows : 128 * rows_box;
   pl.b_tx = 128 * bn_box;
   pl.r_tx = 128 * rows_box;
@@ -1176,9 +1282,12 @@ int conv_forward_tma(const ConvArgs& a_in, cudaStream_t s) {
       ok = ok && make_map(&map_r, a.residual, 3, rdims, rstr, box);
     }
   }
-  if (!ok) return conv_forward_umma(a, s);       // the driver refused a descriptor: v3 takes every layout v4 does
+  if (!ok) {                                     // the driver refused a descriptor: v3 takes every layout v4 does
+    if (pl.gap) { set_error("conv_forward_tma: tensor map refused"); return LAUD_E_UNSUPPORTED; }
+    return conv_forward_umma(a, s);
+  }
 
-  const size_t smem = 1024 + (size_t)pl.a_region_bytes + (size_t)pl.stages * pl.stage_bytes + stg_bytes + sizeof(Tables) + stab_bytes;
+  const size_t smem = 1024 + (size_t)pl.a_region_bytes + (size_t)pl.stages * pl.stage_bytes + stg_bytes + sizeof(Tables) + stab_bytes + gap_bytes;
   const int grid = (int)(total < num_sms ? total : num_sms);
   g_conv_paths[0].fetch_add(1, std::memory_order_relaxed);
   g_conv_tma_launches.fetch_add(1, std::memory_order_relaxed);

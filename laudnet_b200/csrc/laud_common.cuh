@@ -79,6 +79,7 @@ struct ConvArgs {
   const __half* wt;
   const __half* bias_t; int bias_ld;
   const uint8_t* n_mask; int n_mask_gran;
+  int gap_hw;               // internal: pixels per sample of the layer (set by the launcher when gap_partial is used)
 };
 
 // Per-launch CUDA-event timing of the convolution kernels (bench.py's roofline leg): when enabled through

@@ -190,7 +190,8 @@ __global__ void __launch_bounds__(MF_THREADS) masker_channel_fused_kernel(
     const __half* __restrict__ x, int HW, int C, int layers, const float* __restrict__ w1,
     const float* __restrict__ b1, int hidden, const float* __restrict__ w2, const float* __restrict__ b2, int G,
     float* __restrict__ pooled_out, float* __restrict__ logits_out, uint8_t* __restrict__ mask_out,
-    int* __restrict__ idx_out, int* __restrict__ cnt_out, int* __restrict__ total_out) {
+    int* __restrict__ idx_out, int* __restrict__ cnt_out, int* __restrict__ total_out,
+    const float* __restrict__ part, int gap_tiles) {
   extern __shared__ float sm[];
   float* red = sm;
   float* p = red + MF_THREADS * 8;
@@ -207,6 +208,20 @@ __global__ void __launch_bounds__(MF_THREADS) masker_channel_fused_kernel(
   const __half* xb = x + (size_t)b * HW * C;
   const float inv = 1.0f / (float)HW;
 
+  if (part) {
+    // pooled features from the partial sums the producing convolution left (laud_conv_desc::gap_partial):
+    // the tiles of 128 consecutive pixels of the flat [B*HW] list that hold pixels of sample b, ascending
+    const int t_first = (int)(((long long)b * HW) / 128), t_last = (int)(((long long)(b + 1) * HW - 1) / 128);
+    const int nk = min(t_last - t_first + 1, gap_tiles);
+    const float* pb = part + (size_t)b * gap_tiles * C;
+    for (int c = tid; c < C; c += MF_THREADS) {
+      float t = 0.f;
+      for (int k = 0; k < nk; ++k) t += __ldg(pb + (size_t)k * C + c);
+      t *= inv;
+      p[c] = t;
+      if (pooled_out) pooled_out[(size_t)b * C + c] = t;
+    }
+  } else
   for (int vbase = 0; vbase < nvec; vbase += vt) {
     const int v = vbase + v0;
     float acc[8];
@@ -535,6 +550,8 @@ static int launch_decide(const float* partial, const float* pooled_in, int B, in
   return check_launch("masker_decide_kernel");
 }
 
+static size_t g_fused_smem_set = 48 * 1024;     // largest dynamic shared memory size set on the fused kernel so far
+
 extern "C" int laud_masker_channel_mlp(const void* x, int B, int HW, int C, int layers, const float* w1,
                                        const float* b1, int hidden, const float* w2, const float* b2, int G,
                                        float* partial_ws, float* pooled_out, float* logits_out,
@@ -549,14 +566,38 @@ extern "C" int laud_masker_channel_mlp(const void* x, int B, int HW, int C, int 
   LAUD_REQUIRE(G > 0, "channel masker: G must be positive");
   const size_t smem = sizeof(float) * MF_THREADS * 8 + decide_smem(C, layers == 2 ? hidden : 0, G);
   LAUD_REQUIRE(smem <= 200 * 1024, "channel masker: C/G too large for shared memory");
-  static size_t fused_smem_set = 48 * 1024;
-  if (smem > fused_smem_set) {
+  if (smem > g_fused_smem_set) {
     LAUD_CUDA(cudaFuncSetAttribute(masker_channel_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fused_smem_set = smem;
+    g_fused_smem_set = smem;
   }
   masker_channel_fused_kernel<<<B, MF_THREADS, smem, s>>>((const __half*)x, HW, C, layers, w1, b1,
                                                           layers == 2 ? hidden : 0, w2, b2, G, pooled_out, logits_out,
-                                                          mask_out, idx_out, cnt_out, total_out);
+                                                          mask_out, idx_out, cnt_out, total_out, nullptr, 0);
+  return check_launch("masker_channel_fused_kernel");
+}
+
+extern "C" int laud_masker_channel_from_partials(const float* partials, int B, int HW, int C, int gap_tiles, int layers,
+                                                 const float* w1, const float* b1, int hidden, const float* w2,
+                                                 const float* b2, int G, float* pooled_out, float* logits_out,
+                                                 uint8_t* mask_out, int32_t* idx_out, int32_t* cnt_out,
+                                                 int32_t* total_out, void* stream) {
+  LAUD_REQUIRE(partials, "laud_masker_channel_from_partials: null pointer");
+  LAUD_REQUIRE(B > 0 && HW > 0 && C > 0 && C % 8 == 0, "laud_masker_channel_from_partials: need C %% 8 == 0 (C=%d)", C);
+  LAUD_REQUIRE(gap_tiles >= (HW - 1) / 128 + 2, "laud_masker_channel_from_partials: gap_tiles %d < (HW-1)/128 + 2", gap_tiles);
+  cudaStream_t s = (cudaStream_t)stream;
+  LAUD_REQUIRE(layers == 1 || layers == 2, "channel masker: layers must be 1 or 2 (got %d)", layers);
+  LAUD_REQUIRE(w1 && b1 && mask_out && idx_out && cnt_out, "channel masker: null pointer");
+  LAUD_REQUIRE(layers == 1 || (w2 && b2 && hidden > 0), "channel masker: 2-layer MLP needs w2,b2,hidden");
+  LAUD_REQUIRE(G > 0, "channel masker: G must be positive");
+  const size_t smem = sizeof(float) * MF_THREADS * 8 + decide_smem(C, layers == 2 ? hidden : 0, G);
+  LAUD_REQUIRE(smem <= 200 * 1024, "channel masker: C/G too large for shared memory");
+  if (smem > g_fused_smem_set) {
+    LAUD_CUDA(cudaFuncSetAttribute(masker_channel_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    g_fused_smem_set = smem;
+  }
+  masker_channel_fused_kernel<<<B, MF_THREADS, smem, s>>>(nullptr, HW, C, layers, w1, b1, layers == 2 ? hidden : 0, w2,
+                                                          b2, G, pooled_out, logits_out, mask_out, idx_out, cnt_out,
+                                                          total_out, partials, gap_tiles);
   return check_launch("masker_channel_fused_kernel");
 }
 

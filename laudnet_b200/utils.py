@@ -214,6 +214,17 @@ class Masker_channel_MLP(nn.Module):
               "laud_masker_channel_mlp")
         return out
 
+    def gate_from_partials(self, partials: torch.Tensor, b: int, hw: int, c: int, gap_tiles: int,
+                           total: Optional[torch.Tensor], out: _ChannelGate) -> _ChannelGate:
+        """Same decision from the fused-GAP partial sums [B,gap_tiles,C] the producing convolution left
+        (laud_conv_desc::gap_partial): the activations are not read again."""
+        w1, b1, hidden, w2, b2 = self._weights()
+        check(lib().laud_masker_channel_from_partials(ptr(partials), b, hw, c, gap_tiles, self.layers, ptr(w1), ptr(b1),
+                                                      hidden, ptr(w2), ptr(b2), self.channel_dyn_group, ptr(out.pooled),
+                                                      ptr(out.logits), ptr(out.mask), ptr(out.idx), ptr(out.cnt),
+                                                      ptr(total), stream_ptr()), "laud_masker_channel_from_partials")
+        return out
+
     def forward(self, x, temperature):
         _no_training(self, "Masker_channel_MLP")
         _lib.require_cuda(x, "Masker_channel_MLP")

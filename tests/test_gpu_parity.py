@@ -392,6 +392,78 @@ def test_conv_forward_krows_vs_oracle(cuda_lib, name):
     assert err <= ACT_TOL, f"{name}: normalised max error {err:.2e} > {ACT_TOL}"
 
 
+@pytest.mark.parametrize("B,H,Cin,Cout", [(5, 7, 256, 1024), (7, 14, 64, 256), (3, 28, 64, 128), (2, 56, 32, 64)])
+def test_conv_fused_gap_feeds_the_channel_masker(cuda_lib, B, H, Cin, Cout):
+    """conv3 + residual + ReLU with gap_partial: (a) the output is unchanged, (b) the partial sums add up to the global
+    average pool of the STORED fp16 output, (c) laud_masker_channel_from_partials takes the same decision as
+    laud_masker_channel_mlp pooling that output (utils.py:113-131)."""
+    d = _conv_case(B * 1000 + H, B=B, H=H, Cin=Cin, Cout=Cout, k=1, stride=1, residual=True)
+    HW = H * H
+    K = _engine.gap_tiles(HW)
+    xd = d["x"].permute(0, 2, 3, 1).contiguous().half().to(DEV)
+    wd = _engine.pack_conv_weight(d["w"]).to(DEV)
+    res = d["res"].permute(0, 2, 3, 1).contiguous().half().to(DEV)
+    y = torch.empty((B, H, H, Cout), dtype=torch.float16, device=DEV)
+    part = torch.full((B, K, Cout), float("nan"), dtype=torch.float32, device=DEV)
+    _engine.run_conv(xd, wd, y, B, H, H, Cin, H, H, Cout, 1, 1, 0, scale=d["scale"].to(DEV), shift=d["shift"].to(DEV),
+                     relu=_lib.RELU_ALL, residual=res, ldr=Cout, gap_partial=part, gap_tiles=K)
+    torch.cuda.synchronize()
+    want = d["y"].permute(0, 2, 3, 1)
+    assert (y.float().cpu() - want).abs().max().item() / want.abs().max().item() <= ACT_TOL
+    # slots a sample does not use stay untouched; the used ones add up to the pool of the stored values
+    pc = part.cpu()
+    pooled = torch.zeros(B, Cout)
+    for b in range(B):
+        nk = ((b + 1) * HW - 1) // 128 - (b * HW) // 128 + 1
+        assert nk <= K and not torch.isnan(pc[b, :nk]).any() and torch.isnan(pc[b, nk:]).all()
+        pooled[b] = pc[b, :nk].sum(0) / HW
+    ref = y.float().cpu().view(B, HW, Cout).mean(1)
+    assert (pooled - ref).abs().max().item() <= 1e-5 * max(ref.abs().max().item(), 1.0)
+    # the masker from the partial sums == the masker that pools the activations
+    r = np.random.RandomState(B + H)
+    G, hidden = Cout // 2, max(Cout // 16, 8)
+    w1 = torch.from_numpy((r.standard_normal((hidden, Cout)) / np.sqrt(Cout)).astype(np.float32)).to(DEV)
+    b1 = torch.from_numpy(r.standard_normal(hidden).astype(np.float32) * 0.1).to(DEV)
+    w2 = torch.from_numpy((r.standard_normal((2 * G, hidden)) / np.sqrt(hidden)).astype(np.float32)).to(DEV)
+    b2 = torch.from_numpy(r.standard_normal(2 * G).astype(np.float32) * 0.1).to(DEV)
+    outs = []
+    for use_part in (False, True):
+        mask = torch.empty((B, G), dtype=torch.uint8, device=DEV)
+        idx = torch.empty((B, G), dtype=torch.int32, device=DEV)
+        cnt = torch.empty((B,), dtype=torch.int32, device=DEV)
+        tot = torch.zeros(1, dtype=torch.int32, device=DEV)
+        logits = torch.empty((B, 2 * G), dtype=torch.float32, device=DEV)
+        if use_part:
+            _lib.check(_lib.lib().laud_masker_channel_from_partials(_lib.ptr(part), B, HW, Cout, K, 2, _lib.ptr(w1), _lib.ptr(b1), hidden,
+                                                              _lib.ptr(w2), _lib.ptr(b2), G, None, _lib.ptr(logits), _lib.ptr(mask),
+                                                              _lib.ptr(idx), _lib.ptr(cnt), _lib.ptr(tot), _lib.stream_ptr()), "from_partials")
+        else:
+            ws = torch.empty((B, _lib.GAP_SPLITS + 1, Cout), dtype=torch.float32, device=DEV)
+            _lib.check(_lib.lib().laud_masker_channel_mlp(_lib.ptr(y), B, HW, Cout, 2, _lib.ptr(w1), _lib.ptr(b1), hidden, _lib.ptr(w2),
+                                                    _lib.ptr(b2), G, _lib.ptr(ws), None, _lib.ptr(logits), _lib.ptr(mask), _lib.ptr(idx),
+                                                    _lib.ptr(cnt), _lib.ptr(tot), _lib.stream_ptr()), "mlp")
+        torch.cuda.synchronize()
+        outs.append((mask.cpu(), idx.cpu(), cnt.cpu(), int(tot.item()), logits.cpu()))
+    (m0, i0, c0, t0, l0), (m1, i1, c1, t1, l1) = outs
+    assert (l0 - l1).abs().max().item() <= 1e-4
+    margin = (l0[:, :G] - l0[:, G:]).abs()                      # decisions may differ only where keep == drop to rounding
+    assert torch.equal(m0[margin > 1e-4], m1[margin > 1e-4])
+    if torch.equal(m0, m1):
+        assert torch.equal(i0, i1) and torch.equal(c0, c1) and t0 == t1
+
+
+def test_conv_fused_gap_rejects_layers_it_cannot_take(cuda_lib):
+    x = torch.zeros(2, 14, 14, 64, dtype=torch.float16, device=DEV)
+    w = torch.zeros(9 * 64, 64, dtype=torch.float16, device=DEV).view(64, 9, 64)
+    y = torch.zeros(2, 14, 14, 64, dtype=torch.float16, device=DEV)
+    part = torch.zeros(2, 3, 64, dtype=torch.float32, device=DEV)
+    with pytest.raises(L.LaudError, match="GAP"):        # 3x3: not a flat GEMM
+        _engine.run_conv(x, w, y, 2, 14, 14, 64, 14, 14, 64, 3, 1, 1, gap_partial=part, gap_tiles=3)
+    w1 = torch.zeros(64, 1, 64, dtype=torch.float16, device=DEV)
+    with pytest.raises(L.LaudError, match="GAP|gap"):    # too few slots per sample
+        _engine.run_conv(x, w1, y, 2, 14, 14, 64, 14, 14, 64, 1, 1, 0, residual=x, ldr=64, gap_partial=part, gap_tiles=1)
+
+
 def test_conv_rejects_bad_arguments(cuda_lib):
     x = torch.zeros(1, 4, 4, 12, dtype=torch.float16, device=DEV)
     w = torch.zeros(8, 1, 12, dtype=torch.float16, device=DEV)
