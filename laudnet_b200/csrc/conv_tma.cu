@@ -126,6 +126,21 @@ struct Sub {               // one (sample, m-group, n-tile) unit of work
   int b, mg, nt, n0, n_valid, umma_n, Nc, Nfill, Kc, nk16, cpt, nchunks, has_bias, mt0, mt_cnt;
 };
 
+// Kernel specialisations.  The generic kernel (SPEC 0) carries every mode; its code is far larger than the instruction
+// caches, and each warp role pays for that at every item.  The shared-weight layers with nothing per sample - all
+// convolutions of the masked-dense network - run on instantiations with their modes fixed at compile time:
+//   1: OUT_SLAB through the DMA threads (conv3, downsample)   2: OUT_DIRECT (conv1)   3: OUT_DIRECT, halo tiles (3x3)
+template <int SPEC>
+struct Mode {
+  static __device__ __forceinline__ int bmode(const Plan& pl) { return SPEC == 0 ? pl.bmode : (int)BMODE_TMA; }
+  static __device__ __forceinline__ int omode(const Plan& pl) {
+    return SPEC == 0 ? pl.omode : (SPEC == 1 ? (int)OUT_SLAB : (int)OUT_DIRECT);
+  }
+  static __device__ __forceinline__ bool halo(const Plan& pl) { return SPEC == 0 ? pl.halo != 0 : SPEC == 3; }
+  static __device__ __forceinline__ bool dma(const Plan& pl) { return SPEC == 0 ? pl.dma != 0 : SPEC == 1; }
+  static __device__ __forceinline__ bool simple(const Plan& pl) { return SPEC == 0 ? pl.simple != 0 : true; }
+};
+
 // Every role walks the same CONTIGUOUS range of items (sample slot, m-group, n-group) of its CTA, and the
 // n-tiles inside an item, in the same order; consecutive sub-items mostly share the sample.
 struct Walker {
@@ -146,8 +161,9 @@ __device__ __forceinline__ void walker_init(const ConvArgs& a, const Plan& pl, W
   w.nti = 0;
   w.started = 0;
 }
+template <class M>
 __device__ __forceinline__ bool decode_sub(const ConvArgs& a, const Plan& pl, const Tables& T, const Walker& w, Sub& s) {
-  if (pl.simple) {                     // division-free path of the shared-weight layers
+  if (M::simple(pl)) {                     // division-free path of the shared-weight layers
     s.b = w.slot;
     s.mg = w.mg;
     s.nt = w.ng * pl.NTI + w.nti;
@@ -174,7 +190,7 @@ __device__ __forceinline__ bool decode_sub(const ConvArgs& a, const Plan& pl, co
   s.Nc = a.n_idx ? (pl.cnt_cached ? T.ncnt[s.b] : __ldg(a.n_cnt + s.b)) * a.n_gran : a.C_out;
   s.Nfill = round_up(s.Nc, a.n_pad_align);
   // KROWS tiles span REAL output channels (the epilogue compacts); the others span the stored row
-  const int span = (pl.bmode == BMODE_KROWS) ? a.C_out : s.Nfill;
+  const int span = (M::bmode(pl) == BMODE_KROWS) ? a.C_out : s.Nfill;
   s.n0 = s.nt * pl.BN;
   if (s.n0 >= span) return false;
   s.n_valid = min(pl.BN, span - s.n0);
@@ -189,6 +205,7 @@ __device__ __forceinline__ bool decode_sub(const ConvArgs& a, const Plan& pl, co
   return true;
 }
 // advance to the next valid sub-item of this CTA; false when the range is exhausted
+template <class M>
 __device__ __forceinline__ bool walker_next(const ConvArgs& a, const Plan& pl, const Tables& T, Walker& w, Sub& s) {
   while (true) {
     if (!w.started) {
@@ -202,7 +219,7 @@ __device__ __forceinline__ bool walker_next(const ConvArgs& a, const Plan& pl, c
       }
     }
     if (w.t >= w.t_end) return false;
-    if (decode_sub(a, pl, T, w, s)) return true;
+    if (decode_sub<M>(a, pl, T, w, s)) return true;
   }
 }
 
@@ -224,6 +241,7 @@ struct Cursor {
   Sub s;
   int mt, sl, have;
 };
+template <class M>
 __device__ __forceinline__ bool cursor_next(const ConvArgs& a, const Plan& pl, const Tables& T, Cursor& c, int h) {
   if (c.have) {
     c.sl += 2;
@@ -232,7 +250,7 @@ __device__ __forceinline__ bool cursor_next(const ConvArgs& a, const Plan& pl, c
     if (++c.mt < c.s.mt_cnt) return true;
     c.have = 0;
   }
-  while (walker_next(a, pl, T, c.w, c.s)) {          // next sub-item in which this half has a slab
+  while (walker_next<M>(a, pl, T, c.w, c.s)) {          // next sub-item in which this half has a slab
     if (h * 64 < c.s.n_valid) {
       c.have = 1;
       c.mt = 0;
@@ -244,13 +262,14 @@ __device__ __forceinline__ bool cursor_next(const ConvArgs& a, const Plan& pl, c
 }
 
 // epilogue column tables of one sub-item: folded-BN scale / shift of tile column c and (OUT_ROWS) its compact position
+template <class M>
 __device__ __forceinline__ void column_entry(const ConvArgs& a, const Plan& pl, const Sub& s, int c, float& sc, float& sh,
                                              int& pos) {
   const int jj = s.n0 + c;
   int o = -1;
   pos = -1;
   if (c < s.n_valid) {
-    if (pl.omode == OUT_ROWS) {
+    if (M::omode(pl) == OUT_ROWS) {
       // real channel jj: active iff its group is in the sample's ascending list; its rank is the compact position
       if (a.n_idx) {
         const int grp = jj / a.n_gran, na = s.Nc / a.n_gran;
@@ -325,14 +344,16 @@ __device__ __forceinline__ void slab_pass(float* v, uint32_t t_scale, uint32_t t
 }
 
 // ------------------------------------------------------------------ the kernel
+template <int SPEC>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan pl,
                 const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_r) {
+  using M = Mode<SPEC>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
   unsigned char* stg = smem + pl.a_region_bytes + (size_t)pl.stages * pl.stage_bytes;   // slab rings / row staging (1024-aligned)
-  const int stg_bytes = pl.omode == OUT_SLAB ? 2 * pl.ring * SLAB_BYTES : (pl.omode == OUT_ROWS ? pl.stg_rows * pl.stg_pitch : 0);
+  const int stg_bytes = M::omode(pl) == OUT_SLAB ? 2 * pl.ring * SLAB_BYTES : (M::omode(pl) == OUT_ROWS ? pl.stg_rows * pl.stg_pitch : 0);
   Tables& T = *reinterpret_cast<Tables*>(stg + stg_bytes);
   const uint32_t a_base = smem_u32(smem);                           // halo mode: two activation slots in front of the stages
   const uint32_t smem_base = a_base + pl.a_region_bytes;
@@ -347,7 +368,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&T.tfull[i], 1);
-      mbar_init(&T.tempty[i], EPI_THREADS);
+      mbar_init(&T.tempty[i], EPI_WARPS);        // one arrival per epilogue warp (256 arrivals on one word serialise)
     }
     for (int h = 0; h < 2; ++h)
       for (int i = 0; i < MAX_RING; ++i) mbar_init(&T.rfull[h][i], 1);
@@ -357,7 +378,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
     }
     for (int h = 0; h < 2; ++h)
       for (int i = 0; i < MAX_RING; ++i) {
-        mbar_init(&T.sready[h][i], HALF_THREADS);
+        mbar_init(&T.sready[h][i], EPI_WARPS / 2);
         mbar_init(&T.sfree[h][i], 1);
         mbar_init(&T.gdone[h][i], 2);
       }
@@ -377,9 +398,9 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
     }
   if (warp == TMA_WARP && lane == 0) {
     tma_prefetch_desc(&map_a);
-    if (pl.bmode == BMODE_TMA) tma_prefetch_desc(&map_b);
+    if (M::bmode(pl) == BMODE_TMA) tma_prefetch_desc(&map_b);
   }
-  if (warp == 0 && lane == 0 && pl.omode == OUT_SLAB) {
+  if (warp == 0 && lane == 0 && M::omode(pl) == OUT_SLAB) {
     tma_prefetch_desc(&map_y);
     if (a.residual) tma_prefetch_desc(&map_r);
   }
@@ -403,14 +424,14 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
       int stage = 0;
       uint32_t phase = 0;
       KP_DECL;
-      if (pl.halo) {
+      if (M::halo(pl)) {
         // two streams issued by this one thread: activation tiles (one per sub-item and 64-channel chunk, kept one
         // chunk ahead, also across sub-items) and weight tiles (one per chunk and tap)
         Walker wa;
         walker_init(a, pl, wa);
         Sub sa;
-        bool a_more = walker_next(a, pl, T, wa, sa);
-        while (a_more && sa.cpt == 0) a_more = walker_next(a, pl, T, wa, sa);
+        bool a_more = walker_next<M>(a, pl, T, wa, sa);
+        while (a_more && sa.cpt == 0) a_more = walker_next<M>(a, pl, T, wa, sa);
         int a_kq = 0, a_next = 0, g = 0;
         // issue the next activation tile (chunk a_next of the A stream) into its slot
         auto issue_a = [&]() {
@@ -423,11 +444,11 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
           ++a_next;
           if (++a_kq >= sa.cpt) {
             a_kq = 0;
-            a_more = walker_next(a, pl, T, wa, sa);
-            while (a_more && sa.cpt == 0) a_more = walker_next(a, pl, T, wa, sa);
+            a_more = walker_next<M>(a, pl, T, wa, sa);
+            while (a_more && sa.cpt == 0) a_more = walker_next<M>(a, pl, T, wa, sa);
           }
         };
-        while (walker_next(a, pl, T, wk, s)) {
+        while (walker_next<M>(a, pl, T, wk, s)) {
           for (int kq = 0; kq < s.cpt; ++kq, ++g) {
             while (a_more && a_next <= g) {                       // the tile this chunk's MMAs read: must be on its way
               mbar_wait(&T.aempty[a_next & 1], (uint32_t)((a_next >> 1) & 1) ^ 1u);
@@ -449,9 +470,9 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
           }
         }
       } else
-      while (walker_next(a, pl, T, wk, s)) {
+      while (walker_next<M>(a, pl, T, wk, s)) {
         KP_LAP(0);                                   // decode
-        const uint32_t tx = (uint32_t)(((pl.dbg & 2) ? 0 : s.mt_cnt * pl.a_tx) + (pl.bmode == BMODE_TMA ? pl.b_tx : 0));
+        const uint32_t tx = (uint32_t)(((pl.dbg & 2) ? 0 : s.mt_cnt * pl.a_tx) + (M::bmode(pl) == BMODE_TMA ? pl.b_tx : 0));
         for (int tap = 0; tap < taps; ++tap) {
           const int ty = tap / a.ksize, tx_ = tap - ty * a.ksize;
           for (int kq = 0; kq < s.cpt; ++kq) {
@@ -465,7 +486,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
               if (pl.R) tma_load_4d(As + m * A_TILE_BYTES, &map_a, &T.full[stage], k0, tx_ - a.pad, mt * pl.R * a.stride + ty - a.pad, s.b);
               else tma_load_3d(As + m * A_TILE_BYTES, &map_a, &T.full[stage], k0, mt * BM, s.b);
             }
-            if (pl.bmode == BMODE_TMA)
+            if (M::bmode(pl) == BMODE_TMA)
               tma_load_2d(As + pl.b_off, &map_b, &T.full[stage], tap * a.C_in + k0, s.n0);
             if (++stage == pl.stages) { stage = 0; phase ^= 1; }
             KP_LAP(2);                               // issue
@@ -487,14 +508,14 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
       int stage = 0, buf = 0, hg = 0;
       uint32_t phase = 0, bphase = 0;
       KP_DECL;
-      while (walker_next(a, pl, T, wk, s)) {
+      while (walker_next<M>(a, pl, T, wk, s)) {
         KP_LAP(0);                                               // decode
         mbar_wait(&T.tempty[buf], bphase ^ 1);                   // epilogue has drained this buffer
         KP_LAP(1);                                               // wait for a free accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * (pl.MT * pl.acc_cols);
-        const uint32_t idesc = umma_idesc_f16(s.umma_n, pl.bmode == BMODE_KROWS);
-        if (pl.halo) {
+        const uint32_t idesc = umma_idesc_f16(s.umma_n, M::bmode(pl) == BMODE_KROWS);
+        if (M::halo(pl)) {
           for (int kq = 0; kq < s.cpt; ++kq, ++hg) {
             const int aslot = hg & 1;
             const int n16 = min(4, s.nk16 - kq * 4);
@@ -529,13 +550,13 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
           const int n16 = bias_step ? 1 : min(4, s.nk16 - (ch % s.cpt) * 4);
           mbar_wait(&T.full[stage], phase);
           KP_LAP(2);                                             // wait for operands
-          if (pl.bmode != BMODE_TMA) fence_proxy_async();        // cp.async (generic proxy) writes -> async proxy
+          if (M::bmode(pl) != BMODE_TMA) fence_proxy_async();        // cp.async (generic proxy) writes -> async proxy
           tc_fence_after();
           KP_LAP(4);                                             // fences
           const uint32_t As = smem_base + stage * pl.stage_bytes;
           const uint32_t Bs = As + pl.b_off;
-          const uint64_t bd = pl.bmode == BMODE_KROWS ? umma_desc(Bs, 8192, 1024) : umma_desc(Bs, 16, 1024);
-          const uint64_t bstep = pl.bmode == BMODE_KROWS ? 128 : 2;
+          const uint64_t bd = M::bmode(pl) == BMODE_KROWS ? umma_desc(Bs, 8192, 1024) : umma_desc(Bs, 16, 1024);
+          const uint64_t bstep = M::bmode(pl) == BMODE_KROWS ? 128 : 2;
           for (int m = 0; m < s.mt_cnt; ++m) {
             const uint64_t ad = umma_desc(As + m * A_TILE_BYTES, 16, 1024);
             if (!(pl.dbg & 4))
@@ -556,7 +577,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
     __syncwarp();
   } else if (warp >= GATHER_WARP0) {
     // =========================================================== weight gather (cp.async)
-    if (pl.bmode != BMODE_TMA) {
+    if (M::bmode(pl) != BMODE_TMA) {
       const int pt = threadIdx.x - GATHER_WARP0 * 32;            // 0..191
       const int pw = pt >> 5;
       const int ac = pt & 7, ar0 = pt >> 3;                      // ROWS: 16-byte chunk, first row (rows ar0 + 24 i)
@@ -564,7 +585,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
       uint32_t phase = 0;
       int last_b = -1, last_mg = -1;
       KP_DECL;
-      while (walker_next(a, pl, T, wk, s)) {
+      while (walker_next<M>(a, pl, T, wk, s)) {
         KP_LAP(0);                                               // decode
         const int cpr = s.umma_n >> 3;                           // 16-byte chunks per k-row (KROWS)
         int cpr2 = 2;
@@ -574,7 +595,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
         const bool kc_ok = kc < cpr && s.n0 + kc * 8 < a.C_out;
         const uint32_t kdst0 = (uint32_t)((kc >> 3) * 8192 + ((kc & 7) << 4));   // n-block + chunk (pre-swizzle)
         int browr[11];
-        if (pl.bmode == BMODE_ROWS) {
+        if (M::bmode(pl) == BMODE_ROWS) {
 #pragma unroll
           for (int i = 0; i < 11; ++i) {
             const int row = ar0 + 24 * i, jj = s.n0 + row;
@@ -620,7 +641,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
             mbar_wait(&T.empty[stage], phase ^ 1);
             KP_LAP(2);                                           // wait for a free stage
             const uint32_t Bs = smem_base + stage * pl.stage_bytes + pl.b_off;
-            if (pl.bmode == BMODE_ROWS) {
+            if (M::bmode(pl) == BMODE_ROWS) {
               if (ac < 2 * n16) {
                 const int k = k0 + ac * 8;
                 const bool kok = k < a.C_in;
@@ -677,7 +698,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
       }
       if (pt == 0) KP_FLUSH(2);
       asm volatile("cp.async.wait_all;" ::: "memory");
-    } else if (pl.dma && warp < GATHER_WARP0 + 2 && lane == 0 && !(pl.dbg & 8)) {
+    } else if (M::dma(pl) && warp < GATHER_WARP0 + 2 && lane == 0 && !(pl.dbg & 8)) {
       // =========================================================== slab DMA thread of epilogue half h
       // Issues the TMA store of every finished slab and keeps the residual slabs ring - 1 tasks ahead, so the 128
       // epilogue threads of the half never wait for a copy to be ISSUED, only for data (rfull) or space (sfree).
@@ -690,13 +711,13 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
       cl = cs;
       if (has_res)
         for (int t = 0; t < pl.ring; ++t) {
-          if (!cursor_next(a, pl, T, cl, h)) break;
+          if (!cursor_next<M>(a, pl, T, cl, h)) break;
           int m0, rows;
           tile_rows(a, pl, cl.s.mt0 + cl.mt, m0, rows);
           mbar_arrive_expect_tx(&T.rfull[h][t], (uint32_t)pl.r_tx);
           tma_load_3d(smem_u32(ring + t * SLAB_BYTES), &map_r, &T.rfull[h][t], cl.s.n0 + cl.sl * 64, m0, cl.s.b);
         }
-      for (int j = 0; cursor_next(a, pl, T, cs, h); ++j) {
+      for (int j = 0; cursor_next<M>(a, pl, T, cs, h); ++j) {
         const int slot = j % pl.ring;
         int m0, rows;
         tile_rows(a, pl, cs.s.mt0 + cs.mt, m0, rows);
@@ -708,7 +729,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
           const int ps = (j - 1) % pl.ring;
           if (pl.gap) mbar_wait(&T.gdone[h][ps], (uint32_t)((j - 1) / pl.ring) & 1u);   // ... and pooled
           if (has_res) {
-            if (cursor_next(a, pl, T, cl, h)) {                  // refill it: residual of task (j - 1) + ring
+            if (cursor_next<M>(a, pl, T, cl, h)) {                  // refill it: residual of task (j - 1) + ring
               int pm0, prow;
               tile_rows(a, pl, cl.s.mt0 + cl.mt, pm0, prow);
               mbar_arrive_expect_tx(&T.rfull[h][ps], (uint32_t)pl.r_tx);
@@ -734,7 +755,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
       Cursor cs;
       walker_init(a, pl, cs.w);
       cs.mt = 0; cs.sl = 0; cs.have = 0;
-      for (int j = 0; cursor_next(a, pl, T, cs, h); ++j) {
+      for (int j = 0; cursor_next<M>(a, pl, T, cs, h); ++j) {
         const int slot = j % pl.ring;
         int m0, rows;
         tile_rows(a, pl, cs.s.mt0 + cs.mt, m0, rows);            // flat layer: m0 = first pixel of the tile in [B*H*W]
@@ -803,9 +824,9 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
     walker_init(a, pl, cur.w);
     cur.mt = 0; cur.sl = 0; cur.have = 0;
     int pf = 0;                                                  // slab tasks whose residual load has been issued
-    if (pl.omode == OUT_SLAB && a.residual && elected && !pl.dma && !(pl.dbg & 8)) {
+    if (M::omode(pl) == OUT_SLAB && a.residual && elected && !M::dma(pl) && !(pl.dbg & 8)) {
       for (; pf < pl.ring - 1; ++pf) {
-        if (!cursor_next(a, pl, T, cur, h)) break;
+        if (!cursor_next<M>(a, pl, T, cur, h)) break;
         int m0, rows;
         tile_rows(a, pl, cur.s.mt0 + cur.mt, m0, rows);
         mbar_arrive_expect_tx(&T.rfull[h][pf % pl.ring], (uint32_t)pl.r_tx);
@@ -816,22 +837,22 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
     KP_DECL;
     // column tables: entry `et` of the NEXT sub-item is fetched into registers while the current one is processed
     Sub nx;
-    bool more = walker_next(a, pl, T, wk, nx);
+    bool more = walker_next<M>(a, pl, T, wk, nx);
     int par = 0;
     const bool dyn_cols = !pl.static_cols;
     if (more && dyn_cols) {
       float sc, sh;
       int pos;
-      column_entry(a, pl, nx, et, sc, sh, pos);
+      column_entry<M>(a, pl, nx, et, sc, sh, pos);
       T.scale[0][et] = sc; T.shift[0][et] = sh; T.cpos[0][et] = pos;
     }
     while (more) {
       s = nx;
       if (dyn_cols) named_bar_sync(2, EPI_THREADS);   // tables[par] are complete; nobody still reads tables[par ^ 1]
-      more = walker_next(a, pl, T, wk, nx);
+      more = walker_next<M>(a, pl, T, wk, nx);
       float nsc = 0.f, nsh = 0.f;
       int npos = -1;
-      if (more && dyn_cols) column_entry(a, pl, nx, et, nsc, nsh, npos);
+      if (more && dyn_cols) column_entry<M>(a, pl, nx, et, nsc, nsh, npos);
       KP_LAP(1);                                                 // decode + next table entry (loads in flight)
       // shared-space addresses of this sub-item's column tables
       const uint32_t t_scale = dyn_cols ? smem_u32(&T.scale[par][0]) : smem_u32(stab) + (uint32_t)s.n0 * 4u;
@@ -849,12 +870,12 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
         // pixel of this accumulator row inside the tile (halo mode: rows are positions of the padded image)
         int prow = row;
         bool pvalid = row < rows;
-        if (pl.halo) {
+        if (M::halo(pl)) {
           const int oyl = row / pl.Wp, ox = row - oyl * pl.Wp;
           prow = oyl * a.W_out + ox;
           pvalid = ox < a.W_out && prow < rows;
         }
-        if (pl.omode == OUT_SLAB) {
+        if (M::omode(pl) == OUT_SLAB) {
           bool row_on = true;                                    // spatial / layer gate of this pixel (one mask group)
           if (a.out_mask) row_on = pvalid && a.out_mask[(size_t)s.b * HWo + m0 + prow] != 0;
           for (int sl = h; sl * 64 < s.n_valid; sl += 2, ++task) {
@@ -864,7 +885,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
             const uint32_t sw = (uint32_t)(prow & 7);
             const bool has_res = a.residual != nullptr;
             if (has_res) mbar_wait(&T.rfull[h][slot], (uint32_t)(task / pl.ring) & 1u);
-            else if (pl.dma && task >= pl.ring) mbar_wait(&T.sfree[h][slot], (uint32_t)(task / pl.ring - 1) & 1u);
+            else if (M::dma(pl) && task >= pl.ring) mbar_wait(&T.sfree[h][slot], (uint32_t)(task / pl.ring - 1) & 1u);
             KP_LAP(3);                                           // wait for the residual slab
 #pragma unroll
             for (int p = 0; p < 2; ++p) {
@@ -877,7 +898,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
 #pragma unroll
                 for (int e = 0; e < 32; ++e) v[e] = 0.f;
               }
-              if (!(pl.halo && !pvalid)) {                       // (padding column of the padded image: not a pixel)
+              if (!(M::halo(pl) && !pvalid)) {                       // (padding column of the padded image: not a pixel)
                 // a gated-off VALID pixel has a finite accumulator, so multiplying by 0 zeroes it exactly;
                 // RELU_WHERE_GATE0 keeps the value and applies the ReLU only where the gate is 0
                 const bool gate0_relu = a.relu_mode == LAUD_RELU_WHERE_GATE0;
@@ -894,8 +915,9 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
             }
             KP_LAP(4);                                           // TMEM -> registers -> slab
             fence_proxy_async();                                 // generic-proxy slab writes -> visible to the TMA store
-            if (pl.dma) {
-              mbar_arrive(&T.sready[h][slot]);                   // hand the slab to this half's DMA thread
+            if (M::dma(pl)) {
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&T.sready[h][slot]);    // hand the slab to this half's DMA thread
               KP_LAP(5);
               continue;
             }
@@ -909,7 +931,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
               if (a.residual) {
                 // slab of task-1 is free once its store has been read out; refill it for task + ring - 1
                 bulk_wait_read_n<1>();
-                if (pf == task + pl.ring - 1 && cursor_next(a, pl, T, cur, h)) {
+                if (pf == task + pl.ring - 1 && cursor_next<M>(a, pl, T, cur, h)) {
                   int pm0, prow;
                   tile_rows(a, pl, cur.s.mt0 + cur.mt, pm0, prow);
                   const int ps = pf % pl.ring;
@@ -922,7 +944,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
             }
             KP_LAP(5);                                           // barrier + store + prefetch
           }
-        } else if (pl.omode == OUT_DIRECT) {
+        } else if (M::omode(pl) == OUT_DIRECT) {
           // ---- OUT_DIRECT: long-K layers whose epilogue is a small share of the item: registers -> global,
           //      16 bytes per store, no staging (all shared memory goes to the operand pipeline)
           const bool valid = pvalid;
@@ -1016,13 +1038,16 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
           }
         }
       }
+      KP_LAP(0);                                                 // loop exit
       tc_fence_before();
-      mbar_arrive(&T.tempty[buf]);                               // accumulators drained: the MMA warp may reuse them
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&T.tempty[buf]);                // accumulators drained: the MMA warp may reuse them
+      KP_LAP(7);                                                 // fence + arrive
       if (++buf == pl.nbuf) { buf = 0; bphase ^= 1; }
       par ^= 1;
       if (more && dyn_cols) { T.scale[par][et] = nsc; T.shift[par][et] = nsh; T.cpos[par][et] = npos; }
     }
-    if (pl.omode == OUT_SLAB && !pl.dma) bulk_wait_all();
+    if (M::omode(pl) == OUT_SLAB && !M::dma(pl)) bulk_wait_all();
     KP_LAP(6);
     if (et == 0) KP_FLUSH(3);
     if (et == HALF_THREADS) KP_FLUSH(4);
@@ -1115,7 +1140,10 @@ int conv_forward_tma(const ConvArgs& a_in, cudaStream_t s) {
     int dev = 0;
     LAUD_CUDA(cudaGetDevice(&dev));
     LAUD_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    LAUD_CUDA(cudaFuncSetAttribute(conv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    LAUD_CUDA(cudaFuncSetAttribute(conv_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    LAUD_CUDA(cudaFuncSetAttribute(conv_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    LAUD_CUDA(cudaFuncSetAttribute(conv_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    LAUD_CUDA(cudaFuncSetAttribute(conv_tma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     vtab4_init_kernel<<<32, 256, 0, s>>>();
     if (int e = check_launch("vtab4_init_kernel")) return e;
   }
@@ -1293,7 +1321,18 @@ int conv_forward_tma(const ConvArgs& a_in, cudaStream_t s) {
   g_conv_tma_launches.fetch_add(1, std::memory_order_relaxed);
   {
     ConvProfScope prof(s);
-    conv_tma_kernel<<<grid, NUM_THREADS, smem, s>>>(a, pl, map_a, map_b, map_y, map_r);
+    static const bool no_spec = getenv("LAUD_NO_SPEC") != nullptr;      // A/B switch: always the generic kernel
+    int spec = 0;
+    if (!no_spec && pl.simple && pl.bmode == BMODE_TMA) {
+      if (pl.omode == OUT_SLAB && pl.dma && !pl.halo) spec = 1;
+      else if (pl.omode == OUT_DIRECT) spec = pl.halo ? 3 : 2;
+    }
+    switch (spec) {
+      case 1: conv_tma_kernel<1><<<grid, NUM_THREADS, smem, s>>>(a, pl, map_a, map_b, map_y, map_r); break;
+      case 2: conv_tma_kernel<2><<<grid, NUM_THREADS, smem, s>>>(a, pl, map_a, map_b, map_y, map_r); break;
+      case 3: conv_tma_kernel<3><<<grid, NUM_THREADS, smem, s>>>(a, pl, map_a, map_b, map_y, map_r); break;
+      default: conv_tma_kernel<0><<<grid, NUM_THREADS, smem, s>>>(a, pl, map_a, map_b, map_y, map_r); break;
+    }
   }
   return check_launch("conv_tma_kernel");
 }

@@ -21,8 +21,8 @@ SITES = {
     "tma": ["decode", "wait_empty", "issue"],
     "mma": ["decode", "wait_tempty", "wait_full", "issue", "fences", "commit"],
     "gather": ["decode", "tables", "wait_empty", "issue", "h1step"],
-    "epi0": ["decode", "tables", "wait_tfull", "wait_rfull", "compute", "store", "drain"],
-    "epi1": ["decode", "tables", "wait_tfull", "wait_rfull", "compute", "store", "drain"],
+    "epi0": ["loop_exit", "tables", "wait_tfull", "wait_rfull", "compute", "store", "drain", "release"],
+    "epi1": ["loop_exit", "tables", "wait_tfull", "wait_rfull", "compute", "store", "drain", "release"],
 }
 
 blocks = [int(v) for v in sys.argv[1:]] or [1, 8]
