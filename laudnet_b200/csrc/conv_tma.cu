@@ -129,16 +129,23 @@ struct Sub {               // one (sample, m-group, n-tile) unit of work
 // Kernel specialisations.  The generic kernel (SPEC 0) carries every mode; its code is far larger than the instruction
 // caches, and each warp role pays for that at every item.  The shared-weight layers with nothing per sample - all
 // convolutions of the masked-dense network - run on instantiations with their modes fixed at compile time:
-//   1: OUT_SLAB through the DMA threads (conv3, downsample)   2: OUT_DIRECT (conv1)   3: OUT_DIRECT, halo tiles (3x3)
+//   1: OUT_SLAB through the DMA threads   2: OUT_DIRECT (conv1)   3: OUT_DIRECT, halo tiles (3x3)
+//   4: as 1 with residual + ReLU and no pixel gate (conv3)   5: as 1 without residual / ReLU / gate (downsample)
 template <int SPEC>
 struct Mode {
+  static constexpr bool SLAB_FIXED = SPEC == 4 || SPEC == 5;
   static __device__ __forceinline__ int bmode(const Plan& pl) { return SPEC == 0 ? pl.bmode : (int)BMODE_TMA; }
   static __device__ __forceinline__ int omode(const Plan& pl) {
-    return SPEC == 0 ? pl.omode : (SPEC == 1 ? (int)OUT_SLAB : (int)OUT_DIRECT);
+    return SPEC == 0 ? pl.omode : ((SPEC == 1 || SLAB_FIXED) ? (int)OUT_SLAB : (int)OUT_DIRECT);
   }
   static __device__ __forceinline__ bool halo(const Plan& pl) { return SPEC == 0 ? pl.halo != 0 : SPEC == 3; }
-  static __device__ __forceinline__ bool dma(const Plan& pl) { return SPEC == 0 ? pl.dma != 0 : SPEC == 1; }
+  static __device__ __forceinline__ bool dma(const Plan& pl) { return SPEC == 0 ? pl.dma != 0 : (SPEC == 1 || SLAB_FIXED); }
   static __device__ __forceinline__ bool simple(const Plan& pl) { return SPEC == 0 ? pl.simple != 0 : true; }
+  static __device__ __forceinline__ bool has_res(const ConvArgs& a) { return SLAB_FIXED ? SPEC == 4 : a.residual != nullptr; }
+  static __device__ __forceinline__ int relu_mode(const ConvArgs& a) {
+    return SLAB_FIXED ? (SPEC == 4 ? (int)LAUD_RELU_ALL : (int)LAUD_RELU_NONE) : a.relu_mode;
+  }
+  static __device__ __forceinline__ const uint8_t* out_mask(const ConvArgs& a) { return SLAB_FIXED ? nullptr : a.out_mask; }
 };
 
 // Every role walks the same CONTIGUOUS range of items (sample slot, m-group, n-group) of its CTA, and the
@@ -402,7 +409,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
   }
   if (warp == 0 && lane == 0 && M::omode(pl) == OUT_SLAB) {
     tma_prefetch_desc(&map_y);
-    if (a.residual) tma_prefetch_desc(&map_r);
+    if (M::has_res(a)) tma_prefetch_desc(&map_r);
   }
   if (warp == MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&T.tmem_base)),
@@ -704,7 +711,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
       // epilogue threads of the half never wait for a copy to be ISSUED, only for data (rfull) or space (sfree).
       const int h = warp - GATHER_WARP0;
       unsigned char* ring = stg + (size_t)h * pl.ring * SLAB_BYTES;
-      const bool has_res = a.residual != nullptr;
+      const bool has_res = M::has_res(a);
       Cursor cs, cl;
       walker_init(a, pl, cs.w);
       cs.mt = 0; cs.sl = 0; cs.have = 0;
@@ -816,7 +823,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
     const int row = q * 32 + lane;                               // accumulator row (TMEM lane) of this thread
     const bool elected = (warp == 4 * h) && lane == 0;           // issues this half's TMA copies
     unsigned char* ring = stg + (size_t)h * pl.ring * SLAB_BYTES;
-    const bool relu_all = a.relu_mode == LAUD_RELU_ALL;
+    const bool relu_all = M::relu_mode(a) == LAUD_RELU_ALL;
     int buf = 0;
     uint32_t bphase = 0;
     int task = 0;                                                // slab tasks done by this half
@@ -824,7 +831,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
     walker_init(a, pl, cur.w);
     cur.mt = 0; cur.sl = 0; cur.have = 0;
     int pf = 0;                                                  // slab tasks whose residual load has been issued
-    if (M::omode(pl) == OUT_SLAB && a.residual && elected && !M::dma(pl) && !(pl.dbg & 8)) {
+    if (M::omode(pl) == OUT_SLAB && M::has_res(a) && elected && !M::dma(pl) && !(pl.dbg & 8)) {
       for (; pf < pl.ring - 1; ++pf) {
         if (!cursor_next<M>(a, pl, T, cur, h)) break;
         int m0, rows;
@@ -877,13 +884,13 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
         }
         if (M::omode(pl) == OUT_SLAB) {
           bool row_on = true;                                    // spatial / layer gate of this pixel (one mask group)
-          if (a.out_mask) row_on = pvalid && a.out_mask[(size_t)s.b * HWo + m0 + prow] != 0;
+          if (M::out_mask(a)) row_on = pvalid && M::out_mask(a)[(size_t)s.b * HWo + m0 + prow] != 0;
           for (int sl = h; sl * 64 < s.n_valid; sl += 2, ++task) {
             const int slot = task % pl.ring;
             unsigned char* slab = ring + slot * SLAB_BYTES;
             const uint32_t srow = smem_u32(slab) + (uint32_t)prow * 128u;
             const uint32_t sw = (uint32_t)(prow & 7);
-            const bool has_res = a.residual != nullptr;
+            const bool has_res = M::has_res(a);
             if (has_res) mbar_wait(&T.rfull[h][slot], (uint32_t)(task / pl.ring) & 1u);
             else if (M::dma(pl) && task >= pl.ring) mbar_wait(&T.sfree[h][slot], (uint32_t)(task / pl.ring - 1) & 1u);
             KP_LAP(3);                                           // wait for the residual slab
@@ -901,7 +908,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
               if (!(M::halo(pl) && !pvalid)) {                       // (padding column of the padded image: not a pixel)
                 // a gated-off VALID pixel has a finite accumulator, so multiplying by 0 zeroes it exactly;
                 // RELU_WHERE_GATE0 keeps the value and applies the ReLU only where the gate is 0
-                const bool gate0_relu = a.relu_mode == LAUD_RELU_WHERE_GATE0;
+                const bool gate0_relu = M::relu_mode(a) == LAUD_RELU_WHERE_GATE0;
                 const float gate = (row_on || gate0_relu) ? 1.f : 0.f;
                 const bool relu_row = relu_all || (gate0_relu && !row_on);
                 if (has_res) {
@@ -921,14 +928,14 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
               KP_LAP(5);
               continue;
             }
-            if (elected && !a.residual) {                        // the NEXT task's slab must have left shared memory
+            if (elected && !M::has_res(a)) {                        // the NEXT task's slab must have left shared memory
               if (pl.ring == 3) bulk_wait_read_n<1>(); else bulk_wait_read_n<0>();
             }
             named_bar_sync(3 + h, HALF_THREADS);
             if (elected) {
               tma_store_3d(&map_y, smem_u32(slab), s.n0 + sl * 64, m0, s.b);
               bulk_commit();
-              if (a.residual) {
+              if (M::has_res(a)) {
                 // slab of task-1 is free once its store has been read out; refill it for task + ring - 1
                 bulk_wait_read_n<1>();
                 if (pf == task + pl.ring - 1 && cursor_next<M>(a, pl, T, cur, h)) {
@@ -1144,6 +1151,8 @@ int conv_forward_tma(const ConvArgs& a_in, cudaStream_t s) {
     LAUD_CUDA(cudaFuncSetAttribute(conv_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     LAUD_CUDA(cudaFuncSetAttribute(conv_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     LAUD_CUDA(cudaFuncSetAttribute(conv_tma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    LAUD_CUDA(cudaFuncSetAttribute(conv_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    LAUD_CUDA(cudaFuncSetAttribute(conv_tma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     vtab4_init_kernel<<<32, 256, 0, s>>>();
     if (int e = check_launch("vtab4_init_kernel")) return e;
   }
@@ -1324,13 +1333,19 @@ int conv_forward_tma(const ConvArgs& a_in, cudaStream_t s) {
     static const bool no_spec = getenv("LAUD_NO_SPEC") != nullptr;      // A/B switch: always the generic kernel
     int spec = 0;
     if (!no_spec && pl.simple && pl.bmode == BMODE_TMA) {
-      if (pl.omode == OUT_SLAB && pl.dma && !pl.halo) spec = 1;
+      if (pl.omode == OUT_SLAB && pl.dma && !pl.halo) {
+        spec = 1;
+        if (!a.out_mask && a.residual && a.relu_mode == LAUD_RELU_ALL) spec = 4;
+        else if (!a.out_mask && !a.residual && a.relu_mode == LAUD_RELU_NONE) spec = 5;
+      }
       else if (pl.omode == OUT_DIRECT) spec = pl.halo ? 3 : 2;
     }
     switch (spec) {
       case 1: conv_tma_kernel<1><<<grid, NUM_THREADS, smem, s>>>(a, pl, map_a, map_b, map_y, map_r); break;
       case 2: conv_tma_kernel<2><<<grid, NUM_THREADS, smem, s>>>(a, pl, map_a, map_b, map_y, map_r); break;
       case 3: conv_tma_kernel<3><<<grid, NUM_THREADS, smem, s>>>(a, pl, map_a, map_b, map_y, map_r); break;
+      case 4: conv_tma_kernel<4><<<grid, NUM_THREADS, smem, s>>>(a, pl, map_a, map_b, map_y, map_r); break;
+      case 5: conv_tma_kernel<5><<<grid, NUM_THREADS, smem, s>>>(a, pl, map_a, map_b, map_y, map_r); break;
       default: conv_tma_kernel<0><<<grid, NUM_THREADS, smem, s>>>(a, pl, map_a, map_b, map_y, map_r); break;
     }
   }
