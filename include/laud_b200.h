@@ -252,6 +252,11 @@ int laud_stem_forward(const void* x_nchw, int B, int H, int W, const void* w, in
                       const float* scale, const float* shift, void* y_nhwc, void* stream);
 int laud_head_forward(const void* x, int B, int HW, int C, const void* w, const float* bias,
                       int n_cls, float* pooled_ws /* [B,C] */, float* logits, void* stream);
+/* The head from the fused-GAP partial sums the last convolution left (laud_conv_desc::gap_partial,
+ * fp32 [B, gap_tiles, C]): pooled_ws fp32 [B, C] receives the pooled features, then the same fc. */
+int laud_head_forward_from_partials(const float* partials, int B, int HW, int C, int gap_tiles,
+                                    const void* w, const float* bias, int n_cls,
+                                    float* pooled_ws, float* logits, void* stream);
 
 /* Layout helpers (operator-level API / tests): fp32|fp16 NCHW <-> fp16 NHWC. */
 int laud_nchw_to_nhwc_f16(const void* src, int src_is_f32, int B, int C, int H, int W,

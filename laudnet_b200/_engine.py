@@ -483,8 +483,8 @@ class ResNetEngine:
         """True if block p's conv3 can leave the GAP partial sums of its output for the NEXT block's channel masker:
         the next block pools its input for a channel gate, and this conv3 is a flat GEMM (1x1, nothing per sample:
         masked-dense channel execution, no spatial mask, no layer skip) on the tcgen05 path."""
-        if not self.fuse_gap or p.index + 1 >= len(self.plans) or not self.plans[p.index + 1].use_c:
-            return False
+        if not self.fuse_gap or (p.index + 1 < len(self.plans) and not self.plans[p.index + 1].use_c):
+            return False                 # (the last block's pool feeds the head)
         if p.use_s or (p.use_c and self.channel_exec != "dense") or self.impl not in (_lib.CONV_AUTO, _lib.CONV_UMMA):
             return False
         return p.outplanes % 64 == 0 and p.H_out * p.H_out >= 43
@@ -545,8 +545,13 @@ class ResNetEngine:
         feat = last.outplanes
         ncls = m.fc.weight.shape[0]
         logits = logits_out if logits_out is not None else torch.empty((B, ncls), dtype=torch.float32, device=x.device)
-        check(L.laud_head_forward(ptr(bufs[cur]), B, last.H_out * last.H_out, feat, ptr(self.fc_w), ptr(self.fc_b),
-                                  ncls, ptr(ws["partial"]), ptr(logits), st), "laud_head_forward")
+        if gap_in:      # the last conv3 left the pool of its output
+            check(L.laud_head_forward_from_partials(ptr(ws["gap"]), B, last.H_out * last.H_out, feat,
+                                                    gap_tiles(last.H_out * last.H_out), ptr(self.fc_w), ptr(self.fc_b), ncls,
+                                                    ptr(ws["partial"]), ptr(logits), st), "laud_head_forward_from_partials")
+        else:
+            check(L.laud_head_forward(ptr(bufs[cur]), B, last.H_out * last.H_out, feat, ptr(self.fc_w), ptr(self.fc_b),
+                                      ncls, ptr(ws["partial"]), ptr(logits), st), "laud_head_forward")
         if not want_stats:
             return logits, None
         stats = torch.empty_like(ws["stats"])

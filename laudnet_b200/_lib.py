@@ -76,6 +76,7 @@ SIGNATURES = {
     "laud_scale_channels": ([_vp, _i, _i, _i, _fp, _vp], _i),
     "laud_stem_forward": ([_vp, _i, _i, _i, _vp, _i, _fp, _fp, _vp, _vp], _i),
     "laud_head_forward": ([_vp, _i, _i, _i, _vp, _fp, _i, _fp, _fp, _vp], _i),
+    "laud_head_forward_from_partials": ([_fp, _i, _i, _i, _i, _vp, _fp, _i, _fp, _fp, _vp], _i),
     "laud_nchw_to_nhwc_f16": ([_vp, _i, _i, _i, _i, _i, _vp, _i, _vp], _i),
     "laud_nhwc_f16_to_nchw_f32": ([_vp, _i, _i, _i, _i, _i, _fp, _vp], _i),
     "laud_forward_stats": ([_i32p, _vp, _i, _i64, _i64, _i64, _fp, _vp], _i),

@@ -369,6 +369,74 @@ __global__ void __launch_bounds__(128) head_fc_tiled_kernel(const float* __restr
         logits[(size_t)(s0 + ts + i) * n_cls + o0 + to + j] = acc[i][j] + bias[o0 + to + j];
 }
 
+// Head fc on the warp-level tensor cores with fp32-accurate products: the fp32 feature p is split into
+// hi = fp16(p) and lo = fp16(p - hi) (p = hi + lo to ~2^-22), the fp16 weight is exact, so
+// w*hi + w*lo accumulated in fp32 equals the fp32 product to rounding.  Fragments come straight from
+// global memory (features 2 MB, weights 4 MB: L2 resident); warp tile = 16 samples x 32 classes,
+// CTA = 4 warps = 64 samples x 32 classes.
+__global__ void __launch_bounds__(128) head_fc_mma_kernel(const float* __restrict__ pooled, int B, int C,
+                                                          const __half* __restrict__ w,
+                                                          const float* __restrict__ bias, int n_cls,
+                                                          float* __restrict__ logits) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int s0 = blockIdx.y * 64 + warp * 16, o0 = blockIdx.x * 32;
+  if (s0 >= B) return;
+  const float* p0 = pooled + (size_t)min(s0 + g, B - 1) * C + 2 * t;          // clamped rows are computed and dropped
+  const float* p1 = pooled + (size_t)min(s0 + g + 8, B - 1) * C + 2 * t;
+  const __half* wr[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) wr[j] = w + (size_t)min(o0 + j * 8 + g, n_cls - 1) * C + 2 * t;
+  float acc[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+#pragma unroll 4
+  for (int k0 = 0; k0 < C; k0 += 16) {
+    const float2 f[4] = {__ldg(reinterpret_cast<const float2*>(p0 + k0)), __ldg(reinterpret_cast<const float2*>(p1 + k0)),
+                         __ldg(reinterpret_cast<const float2*>(p0 + k0 + 8)), __ldg(reinterpret_cast<const float2*>(p1 + k0 + 8))};
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __half2 h = __floats2half2_rn(f[e].x, f[e].y);
+      const float2 hf = __half22float2(h);
+      const __half2 l = __floats2half2_rn(f[e].x - hf.x, f[e].y - hf.y);
+      hi[e] = *reinterpret_cast<const uint32_t*>(&h);
+      lo[e] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t b0 = __ldg(reinterpret_cast<const unsigned int*>(wr[j] + k0));
+      const uint32_t b1 = __ldg(reinterpret_cast<const unsigned int*>(wr[j] + k0 + 8));
+      mma_16816(acc[j], hi, b0, b1);
+      mma_16816(acc[j], lo, b0, b1);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int o = o0 + j * 8 + 2 * t;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int sidx = s0 + g + (e >> 1) * 8, oo = o + (e & 1);
+      if (sidx < B && oo < n_cls) logits[(size_t)sidx * n_cls + oo] = acc[j][e] + bias[oo];
+    }
+  }
+}
+
+// pooled[b, c] = (sum over the tiles of sample b, ascending, of the fused-GAP partial sums) / HW
+__global__ void head_pool_partials_kernel(const float* __restrict__ part, int B, int HW, int C, int gap_tiles,
+                                          float* __restrict__ pooled) {
+  const int b = blockIdx.y;
+  const int t_first = (int)(((long long)b * HW) / 128), t_last = (int)(((long long)(b + 1) * HW - 1) / 128);
+  const int nk = min(t_last - t_first + 1, gap_tiles);
+  const float inv = 1.0f / (float)HW;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+    float v = 0.f;
+    for (int k = 0; k < nk; ++k) v += part[((size_t)b * gap_tiles + k) * C + c];
+    pooled[(size_t)b * C + c] = v * inv;
+  }
+}
+
 // ---------------------------------------------------------------------------
 // H1 constants (see laud_b200.h).  The per-sample sums over MASKED channels
 //   T2[b,tap,o] = sum_k inact[b,k] * relu(shift1[k]) * w2[o,tap,k]
@@ -537,6 +605,18 @@ extern "C" int laud_stem_forward(const void* x, int B, int H, int W, const void*
   return check_launch("stem_kernel");
 }
 
+static int launch_head_fc(const float* pooled, int B, int C, const void* w, const float* bias, int n_cls, float* logits,
+                          cudaStream_t s) {
+  if (C % 16 == 0) {
+    head_fc_mma_kernel<<<dim3((n_cls + 31) / 32, (B + 63) / 64), 128, 0, s>>>(pooled, B, C, (const __half*)w, bias, n_cls,
+                                                                             logits);
+    return check_launch("head_fc_mma_kernel");
+  }
+  dim3 grid((n_cls + HF_BO - 1) / HF_BO, (B + HF_BS - 1) / HF_BS);
+  head_fc_tiled_kernel<<<grid, 128, 0, s>>>(pooled, B, C, (const __half*)w, bias, n_cls, logits);
+  return check_launch("head_fc_tiled_kernel");
+}
+
 extern "C" int laud_head_forward(const void* x, int B, int HW, int C, const void* w, const float* bias, int n_cls,
                                  float* pooled_ws, float* logits, void* stream) {
   LAUD_REQUIRE(x && w && bias && pooled_ws && logits, "laud_head_forward: null pointer");
@@ -544,9 +624,19 @@ extern "C" int laud_head_forward(const void* x, int B, int HW, int C, const void
   // pooled_ws: [B, LAUD_GAP_SPLITS + 1, C]: partial sums followed by the pooled features
   float* pooled = pooled_ws + (size_t)B * LAUD_GAP_SPLITS * C;
   if (int e = laud_global_avg_pool(x, B, HW, C, C, pooled_ws, pooled, stream)) return e;
-  dim3 grid((n_cls + HF_BO - 1) / HF_BO, (B + HF_BS - 1) / HF_BS);
-  head_fc_tiled_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(pooled, B, C, (const __half*)w, bias, n_cls, logits);
-  return check_launch("head_fc_tiled_kernel");
+  return launch_head_fc(pooled, B, C, w, bias, n_cls, logits, (cudaStream_t)stream);
+}
+
+extern "C" int laud_head_forward_from_partials(const float* partials, int B, int HW, int C, int gap_tiles, const void* w,
+                                               const float* bias, int n_cls, float* pooled_ws, float* logits,
+                                               void* stream) {
+  LAUD_REQUIRE(partials && w && bias && pooled_ws && logits, "laud_head_forward_from_partials: null pointer");
+  LAUD_REQUIRE(B > 0 && HW > 0 && C % 8 == 0 && C <= 8192, "laud_head_forward_from_partials: need C %% 8 == 0 and C <= 8192 (C=%d)", C);
+  LAUD_REQUIRE(gap_tiles >= (HW - 1) / 128 + 2, "laud_head_forward_from_partials: gap_tiles %d < (HW-1)/128 + 2", gap_tiles);
+  head_pool_partials_kernel<<<dim3((C + 255) / 256, B), 256, 0, (cudaStream_t)stream>>>(partials, B, HW, C, gap_tiles,
+                                                                                      pooled_ws);
+  if (int e = check_launch("head_pool_partials_kernel")) return e;
+  return launch_head_fc(pooled_ws, B, C, w, bias, n_cls, logits, (cudaStream_t)stream);
 }
 
 extern "C" int laud_gate_inactive(const uint8_t* mask, int B, int G, int gran, void* inact_f16, void* stream) {
