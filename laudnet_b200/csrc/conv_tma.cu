@@ -119,7 +119,7 @@ struct Plan {              // host-computed launch geometry
   int simple;              // 1: nothing per sample (no lists, gathers): Sub fields below are launch constants
   int c_nfill, c_nk16, c_cpt, c_nchunks, NG;
   int gap;                 // 1: fused global-average-pool partial sums of the output (flat 1x1 layers, OUT_SLAB + dma)
-  int dbg;                 // LAUD_DBG timing experiments (wrong results): 2 no activation loads, 4 no MMAs, 8 no epilogue work
+  int dbg;                 // LAUD_DBG timing experiments (wrong results): 2 no activation loads, 4 no MMAs, 8 no epilogue work, 16 half-N MMAs
 };
 
 struct Sub {               // one (sample, m-group, n-tile) unit of work
@@ -514,7 +514,8 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
     __syncwarp();
   } else if (warp == MMA_WARP) {
     // =========================================================== MMA issuer
-    if (lane == 0) {
+    // The whole warp runs this loop with identical values and an elected lane issues (see umma_f16_elect).
+    {
       int stage = 0, buf = 0, hg = 0;
       uint32_t phase = 0, bphase = 0;
       KP_DECL;
@@ -524,7 +525,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
         KP_LAP(1);                                               // wait for a free accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * (pl.MT * pl.acc_cols);
-        const uint32_t idesc = umma_idesc_f16(s.umma_n, M::bmode(pl) == BMODE_KROWS);
+        const uint32_t idesc = umma_idesc_f16((pl.dbg & 16) ? s.umma_n / 2 : s.umma_n, M::bmode(pl) == BMODE_KROWS);   // (dbg 16: half-N MMAs, timing only)
         if (M::halo(pl)) {
           for (int kq = 0; kq < s.cpt; ++kq, ++hg) {
             const int aslot = hg & 1;
@@ -539,50 +540,53 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
               KP_LAP(2);
               tc_fence_after();
               const uint64_t bd = umma_desc(smem_base + stage * pl.stage_bytes, 16, 1024);
+              if (!(pl.dbg & 4))
               for (int m = 0; m < s.mt_cnt; ++m) {
                 // tile m, tap (ty,tx): 128 consecutive rows of the padded image starting at row (m R + ty) Wp + tx
                 const uint32_t aaddr = Aslot + (uint32_t)(((m * pl.R + ty) * pl.Wp + tx_) * 128);
                 const uint64_t ad = umma_desc(aaddr, 16, 1024) | (pl.halo_bo ? ((uint64_t)((aaddr >> 7) & 7u) << 49) : 0ull);
-                if (!(pl.dbg & 4))
                 for (int k = 0; k < n16; ++k)
-                  umma_f16(d_tmem + m * pl.acc_cols, ad + 2 * k, bd + 2 * k, idesc, (kq | tap | k) ? 1u : 0u);
+                  umma_f16_elect(d_tmem + m * pl.acc_cols, ad + 2 * k, bd + 2 * k, idesc, (kq | tap | k) ? 1u : 0u);
               }
               KP_LAP(3);
-              umma_commit(&T.empty[stage]);
+              umma_commit_elect(&T.empty[stage]);
               if (++stage == pl.stages) { stage = 0; phase ^= 1; }
               KP_LAP(5);
             }
-            umma_commit(&T.aempty[aslot]);                         // the activation slot is free once these MMAs retire
+            umma_commit_elect(&T.aempty[aslot]);                   // the activation slot is free once these MMAs retire
           }
-        } else
-        for (int ch = 0; ch < s.nchunks; ++ch) {
-          const bool bias_step = s.has_bias && ch == s.nchunks - 1;
-          const int n16 = bias_step ? 1 : min(4, s.nk16 - (ch % s.cpt) * 4);
-          mbar_wait(&T.full[stage], phase);
-          KP_LAP(2);                                             // wait for operands
-          if (M::bmode(pl) != BMODE_TMA) fence_proxy_async();        // cp.async (generic proxy) writes -> async proxy
-          tc_fence_after();
-          KP_LAP(4);                                             // fences
-          const uint32_t As = smem_base + stage * pl.stage_bytes;
-          const uint32_t Bs = As + pl.b_off;
-          const uint64_t bd = M::bmode(pl) == BMODE_KROWS ? umma_desc(Bs, 8192, 1024) : umma_desc(Bs, 16, 1024);
-          const uint64_t bstep = M::bmode(pl) == BMODE_KROWS ? 128 : 2;
-          for (int m = 0; m < s.mt_cnt; ++m) {
-            const uint64_t ad = umma_desc(As + m * A_TILE_BYTES, 16, 1024);
+        } else {
+          int kq = 0;                                            // 64-channel chunk within the tap
+          for (int ch = 0; ch < s.nchunks; ++ch) {
+            const bool bias_step = s.has_bias && ch == s.nchunks - 1;
+            const int n16 = bias_step ? 1 : min(4, s.nk16 - kq * 4);
+            if (++kq == s.cpt) kq = 0;
+            mbar_wait(&T.full[stage], phase);
+            KP_LAP(2);                                           // wait for operands
+            if (M::bmode(pl) != BMODE_TMA) fence_proxy_async();  // cp.async (generic proxy) writes -> async proxy
+            tc_fence_after();
+            KP_LAP(4);                                           // fences
+            const uint32_t As = smem_base + stage * pl.stage_bytes;
+            const uint32_t Bs = As + pl.b_off;
+            const uint64_t bd = M::bmode(pl) == BMODE_KROWS ? umma_desc(Bs, 8192, 1024) : umma_desc(Bs, 16, 1024);
+            const uint64_t bstep = M::bmode(pl) == BMODE_KROWS ? 128 : 2;
             if (!(pl.dbg & 4))
-            for (int k = 0; k < n16; ++k)
-              umma_f16(d_tmem + m * pl.acc_cols, ad + 2 * k, bd + bstep * k, idesc, (ch | k) ? 1u : 0u);
+            for (int m = 0; m < s.mt_cnt; ++m) {
+              const uint64_t ad = umma_desc(As + m * A_TILE_BYTES, 16, 1024);
+              for (int k = 0; k < n16; ++k)
+                umma_f16_elect(d_tmem + m * pl.acc_cols, ad + 2 * k, bd + bstep * k, idesc, (ch | k) ? 1u : 0u);
+            }
+            KP_LAP(3);                                           // issue
+            umma_commit_elect(&T.empty[stage]);                  // frees the stage when these MMAs retire
+            if (++stage == pl.stages) { stage = 0; phase ^= 1; }
+            KP_LAP(5);                                           // commit
           }
-          KP_LAP(3);                                             // issue
-          umma_commit(&T.empty[stage]);                          // frees the stage when these MMAs retire
-          if (++stage == pl.stages) { stage = 0; phase ^= 1; }
-          KP_LAP(5);                                             // commit
         }
-        if (s.nchunks > 0) umma_commit(&T.tfull[buf]);
-        else mbar_arrive(&T.tfull[buf]);                         // no active input channel: accumulator unused
+        if (s.nchunks > 0) umma_commit_elect(&T.tfull[buf]);
+        else if (lane == 0) mbar_arrive(&T.tfull[buf]);          // no active input channel: accumulator unused
         if (++buf == pl.nbuf) { buf = 0; bphase ^= 1; }
       }
-      KP_FLUSH(1);
+      if (lane == 0) KP_FLUSH(1);
     }
     __syncwarp();
   } else if (warp >= GATHER_WARP0) {
@@ -1291,6 +1295,10 @@ int conv_forward_tma(const ConvArgs& a_in, cudaStream_t s) {
   }
   pl.stages = avail / pl.stage_bytes;
   if (pl.stages > MAX_STAGES) pl.stages = MAX_STAGES;
+  {
+    static const int cap = getenv("LAUD_MAX_STAGES") ? atoi(getenv("LAUD_MAX_STAGES")) : 0;   // experiment: pipeline-depth sensitivity
+    if (cap >= 2 && pl.stages > cap) pl.stages = cap;
+  }
   if (pl.stages < 2) {
     if (pl.gap) { set_error("conv_forward_tma: no shared memory left for the fused GAP"); return LAUD_E_UNSUPPORTED; }
     return conv_forward_umma(a, s);
