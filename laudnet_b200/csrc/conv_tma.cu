@@ -714,7 +714,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
       asm volatile("cp.async.wait_all;" ::: "memory");
     } else if (M::dma(pl) && warp < GATHER_WARP0 + 2 && lane == 0 && !(pl.dbg & 8)) {
       // =========================================================== slab DMA thread of epilogue half h
-      // Issues the TMA store of every finished slab and keeps the residual slabs ring - 1 tasks ahead, so the 128
+      // Issues the TMA store of every finished slab and keeps the residual slabs ahead of the epilogue, so the 128
       // epilogue threads of the half never wait for a copy to be ISSUED, only for data (rfull) or space (sfree).
       const int h = warp - GATHER_WARP0;
       unsigned char* ring = stg + (size_t)h * pl.ring * SLAB_BYTES;
@@ -738,20 +738,19 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
         mbar_wait(&T.sready[h][slot], (uint32_t)(j / pl.ring) & 1u);
         tma_store_3d(&map_y, smem_u32(ring + slot * SLAB_BYTES), cs.s.n0 + cs.sl * 64, m0, cs.s.b);
         bulk_commit();
-        if (j >= 1) {
-          bulk_wait_read_n<1>();                                 // the PREVIOUS store has been read out of its slab
-          const int ps = (j - 1) % pl.ring;
-          if (pl.gap) mbar_wait(&T.gdone[h][ps], (uint32_t)((j - 1) / pl.ring) & 1u);   // ... and pooled
-          if (has_res) {
-            if (cursor_next<M>(a, pl, T, cl, h)) {                  // refill it: residual of task (j - 1) + ring
-              int pm0, prow;
-              tile_rows(a, pl, cl.s.mt0 + cl.mt, pm0, prow);
-              mbar_arrive_expect_tx(&T.rfull[h][ps], (uint32_t)pl.r_tx);
-              tma_load_3d(smem_u32(ring + ps * SLAB_BYTES), &map_r, &T.rfull[h][ps], cl.s.n0 + cl.sl * 64, pm0, cl.s.b);
-            }
-          } else {
-            mbar_arrive(&T.sfree[h][ps]);
+        // wait until THIS store has been read out of its slab (a few hundred cycles; the next slab is ~2k cycles away)
+        // and refill the slot at once: the residual of task j + ring is requested two task times before it is needed
+        bulk_wait_read_n<0>();
+        if (pl.gap) mbar_wait(&T.gdone[h][slot], (uint32_t)(j / pl.ring) & 1u);   // ... and pooled
+        if (has_res) {
+          if (cursor_next<M>(a, pl, T, cl, h)) {
+            int pm0, prow;
+            tile_rows(a, pl, cl.s.mt0 + cl.mt, pm0, prow);
+            mbar_arrive_expect_tx(&T.rfull[h][slot], (uint32_t)pl.r_tx);
+            tma_load_3d(smem_u32(ring + slot * SLAB_BYTES), &map_r, &T.rfull[h][slot], cl.s.n0 + cl.sl * 64, pm0, cl.s.b);
           }
+        } else {
+          mbar_arrive(&T.sfree[h][slot]);
         }
       }
       bulk_wait_all();
