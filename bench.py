@@ -298,11 +298,11 @@ def run_graft(args):
 
     peaks = _peaks()
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01z_conv_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r01B_conv_traffic.json")
     if os.path.exists(tpath):                  # dram__bytes_read+write of the conv launches from the committed ncu capture
         tj = json.load(open(tpath))
         traffic = tj["dram_bytes_per_launch_avg"]
-        traffic_src = "profiles/r01z_conv_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, average per conv launch)"
+        traffic_src = "profiles/r01B_conv_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, average per conv launch)"
     conv_bytes = work.conv_bytes_per_image * B
     conv_flops = work.conv_flops_per_image * B
     ach_gbs = conv_bytes / (conv_ms_step * 1e-3) / 1e9
