@@ -462,6 +462,20 @@ def test_conv_fused_gap_rejects_layers_it_cannot_take(cuda_lib):
     w1 = torch.zeros(64, 1, 64, dtype=torch.float16, device=DEV)
     with pytest.raises(L.LaudError, match="GAP|gap"):    # too few slots per sample
         _engine.run_conv(x, w1, y, 2, 14, 14, 64, 14, 14, 64, 1, 1, 0, residual=x, ldr=64, gap_partial=part, gap_tiles=1)
+    # the consumers check the slot count against H*W as well
+    f32 = dict(dtype=torch.float32, device=DEV)
+    w, b = torch.zeros(8, 64, **f32), torch.zeros(8, **f32)
+    mask = torch.empty((2, 4), dtype=torch.uint8, device=DEV)
+    idx = torch.empty((2, 4), dtype=torch.int32, device=DEV)
+    cnt = torch.empty((2,), dtype=torch.int32, device=DEV)
+    rc = _lib.lib().laud_masker_channel_from_partials(_lib.ptr(part), 2, 196, 64, 2, 1, _lib.ptr(w), _lib.ptr(b), 0, None, None, 4,
+                                                      None, None, _lib.ptr(mask), _lib.ptr(idx), _lib.ptr(cnt), None,
+                                                      _lib.stream_ptr())
+    assert rc == -1 and b"gap_tiles" in _lib.lib().laud_last_error()
+    logits = torch.empty((2, 8), **f32)
+    rc = _lib.lib().laud_head_forward_from_partials(_lib.ptr(part), 2, 196, 64, 2, _lib.ptr(torch.zeros(8, 64, dtype=torch.float16, device=DEV)),
+                                                    _lib.ptr(b), 8, _lib.ptr(torch.empty(2, 64, **f32)), _lib.ptr(logits), _lib.stream_ptr())
+    assert rc == -1 and b"gap_tiles" in _lib.lib().laud_last_error()
 
 
 def test_conv_rejects_bad_arguments(cuda_lib):
@@ -663,6 +677,41 @@ def test_split_chains_match_unsplit_forward(cuda_lib, name):
         torch.cuda.synchronize()
     assert torch.equal(l2, logits)
     assert torch.equal(s2, stats)
+
+
+def test_headline_r101_channel_full_size_fused_gap_equals_standalone_masker(cuda_lib):
+    """BASELINE configs[1] architecture (LAUD-ResNet101 channel-2222) at full resolution, batch 6: the forward whose
+    channel maskers (and head) pool from conv3's fused-GAP partial sums takes the same decisions as the forward whose
+    maskers read the activations (utils.py:113-131) - every gate of every block, except where keep == drop to rounding -
+    and the logits agree to rounding; the 7-tuple statistics follow from the gates."""
+    model = L.uni_resnet101(**synth.HEADLINE_KWARGS)
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    model.load_state_dict(synth.synth_state_dict(shapes, 11))
+    model = model.to(DEV).eval()
+    x = synth.synth_images(6, 224, 11).to(DEV)
+    eng = model._engine
+    assert eng.fuse_gap and eng.channel_exec == "dense"
+    runs = []
+    with torch.no_grad():
+        for fuse in (True, False):
+            eng.fuse_gap = fuse
+            keep = []
+            before = _lib.lib().laud_conv_tma_launch_count()
+            out = model(x, 1.0, keep=keep)
+            torch.cuda.synchronize()
+            assert _lib.lib().laud_conv_tma_launch_count() > before          # the tcgen05 / TMA kernel ran
+            runs.append((out[0].float().cpu(), [k.channel_mask.cpu() for k in keep], [k.channel_logits.cpu() for k in keep]))
+    eng.fuse_gap = True
+    (lf, mf, gf), (ls, ms, gs) = runs
+    assert len(mf) == 33
+    flips = 0
+    for i, (a, b, ga, gb) in enumerate(zip(mf, ms, gf, gs)):
+        G = a.shape[1]
+        margin = (gb[:, :G] - gb[:, G:]).abs()
+        assert torch.equal(a[margin > 1e-4], b[margin > 1e-4]), f"block {i}: a gate with a clear margin differs"
+        flips += int((a != b).sum())
+    if flips == 0:
+        assert (lf - ls).abs().max().item() <= 2e-3 * max(ls.abs().max().item(), 1.0)
 
 
 def test_resnet50_spatial_bs8_full_size(cuda_lib):
