@@ -118,6 +118,7 @@ struct Plan {              // host-computed launch geometry
   int dma;                 // 1: slab stores / residual prefetches are issued by two otherwise idle threads (shared-weight layers)
   int simple;              // 1: nothing per sample (no lists, gathers): Sub fields below are launch constants
   int c_nfill, c_nk16, c_cpt, c_nchunks, NG;
+  int st256;               // 1: OUT_DIRECT may use 32-byte global stores (y 32-byte aligned, ldy and C_out multiples of 16)
   int gap;                 // 1: fused global-average-pool partial sums of the output (flat 1x1 layers, OUT_SLAB + dma)
   int dbg;                 // LAUD_DBG timing experiments (wrong results): 2 no activation loads, 4 no MMAs, 8 no epilogue work, 16 half-N MMAs
 };
@@ -973,6 +974,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
               for (int e = 0; e < 32; ++e) v[e] = 0.f;
             }
             if (valid) {
+              uint4 o_prev = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
               for (int g4 = 0; g4 < 4; ++g4) {
                 if (c0 + g4 * 8 < s.n_valid) {
@@ -998,7 +1000,15 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
 #pragma unroll
                     for (int e = 0; e < 4; ++e) oh[e] = __hmax2(oh[e], z);
                   }
-                  *reinterpret_cast<uint4*>(yrow + c0 + g4 * 8) = o4;
+                  // 32-byte stores where two pieces are complete and aligned: the scattered rows make this epilogue
+                  // LSU-bound (one line per thread and instruction), so half the store instructions is half its time
+                  if (pl.st256 && (g4 & 1) == 0 && c0 + g4 * 8 + 16 <= s.n_valid) {
+                    o_prev = o4;
+                  } else if (pl.st256 && (g4 & 1) == 1) {
+                    stg256(yrow + c0 + (g4 - 1) * 8, o_prev, o4);
+                  } else {
+                    *reinterpret_cast<uint4*>(yrow + c0 + g4 * 8) = o4;
+                  }
                 }
               }
             }
@@ -1261,6 +1271,10 @@ int conv_forward_tma(const ConvArgs& a_in, cudaStream_t s) {
   static const bool no_dma = getenv("LAUD_NO_DMA") != nullptr;
   pl.dma = (!no_dma && pl.omode == OUT_SLAB && pl.bmode == BMODE_TMA) ? 1 : 0;
   pl.NG = pl.NT / pl.NTI;
+  {
+    static const bool no256 = getenv("LAUD_NO_ST256") != nullptr;
+    pl.st256 = (!no256 && (reinterpret_cast<uintptr_t>(a.y) & 31) == 0 && a.ldy % 16 == 0 && a.C_out % 16 == 0 && pl.BN % 16 == 0) ? 1 : 0;
+  }
   // fused GAP of the output: flat layers whose slabs go through the DMA threads; a tile may span at most 4 samples
   pl.gap = 0;
   if (a.gap_partial) {
