@@ -162,12 +162,34 @@ __global__ void __launch_bounds__(256, 2) stem_mma_kernel(const __half* __restri
     const int cy0 = 2 * py0 - 1, cx0 = 2 * px0 - 1;       // conv-tile origin (may be -1)
     const int iy0 = 2 * cy0 - 3, ix0 = 2 * cx0 - 3;       // input-patch origin
     __syncthreads();                                      // previous item's pooling has finished with s_c / s_in
+    if ((W & 1) == 0) {
+      // one patch row per warp and pass: ix0 is odd, so patch columns 1.. are pairs of an even-aligned input column and
+      // its successor: 32-bit global loads (both inside or both outside the image, W even), 16-bit shared stores
+      for (int row = warp; row < 3 * S2_IH; row += 8) {
+        const int c = row / S2_IH, rr = row - c * S2_IH;
+        const int iy = iy0 + rr;
+        const bool yok = iy >= 0 && iy < H;
+        const __half* src = x + (((size_t)b * 3 + c) * H + (yok ? iy : 0)) * W;
+        __half* dst = s_in + row * S2_IWP;
+        const int q = 1 + 2 * lane, ix = ix0 + q;                 // lanes 0..30: columns 1..62; lane 31: column 0 (and 63: pad)
+        if (lane < 31) {
+          __half2 v = __float2half2_rn(0.f);
+          if (yok && ix >= 0 && ix + 1 < W) v = *reinterpret_cast<const __half2*>(src + ix);
+          dst[q] = __low2half(v);
+          dst[q + 1] = __high2half(v);
+        } else {
+          dst[0] = (yok && ix0 >= 0 && ix0 < W) ? src[ix0] : __float2half(0.f);
+          dst[S2_IWP - 1] = __float2half(0.f);
+        }
+      }
+    } else {
     for (int i = tid; i < 3 * S2_IH * S2_IWP; i += 256) {
       const int c = i / (S2_IH * S2_IWP), rr = (i / S2_IWP) % S2_IH, q = i % S2_IWP;
       const int iy = iy0 + rr, ix = ix0 + q;
       __half v = __float2half(0.f);
       if (iy >= 0 && ix >= 0 && iy < H && ix < W) v = x[(((size_t)b * 3 + c) * H + iy) * W + ix];
       s_in[i] = v;
+    }
     }
     __syncthreads();
 
