@@ -172,7 +172,7 @@ __device__ __forceinline__ void walker_init(const ConvArgs& a, const Plan& pl, W
 template <class M>
 __device__ __forceinline__ bool decode_sub(const ConvArgs& a, const Plan& pl, const Tables& T, const Walker& w, Sub& s) {
   if (M::simple(pl)) {                     // division-free path of the shared-weight layers
-    s.b = w.slot;
+    s.b = a.sample_idx ? __ldg(a.sample_idx + w.slot) : w.slot;      // (walker_init hands out the ACTIVE samples' items only)
     s.mg = w.mg;
     s.nt = w.ng * pl.NTI + w.nti;
     s.Nc = a.C_out;
@@ -1288,7 +1288,7 @@ int conv_forward_tma(const ConvArgs& a_in, cudaStream_t s) {
     pl.gap = 1;
   }
   const int gap_bytes = pl.gap ? 2 * 2 * 2 * 4 * 64 * 4 : 0;
-  pl.simple = (!a.k_idx && !a.n_idx && !a.sample_idx && !a.bias_t && pl.bmode == BMODE_TMA) ? 1 : 0;
+  pl.simple = (!a.k_idx && !a.n_idx && !a.bias_t && pl.bmode == BMODE_TMA) ? 1 : 0;
   {
     static const int dbg = getenv("LAUD_DBG") ? atoi(getenv("LAUD_DBG")) : 0;
     pl.dbg = dbg;
