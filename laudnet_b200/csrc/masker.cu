@@ -219,7 +219,17 @@ __global__ void __launch_bounds__(MF_THREADS) masker_channel_fused_kernel(
     const float* pb = part + (size_t)b * gap_tiles * C;
     for (int c = tid; c < C; c += MF_THREADS) {
       float t = 0.f;
-      for (int k = 0; k < nk; ++k) t += __ldg(pb + (size_t)k * C + c);
+      if (nk <= 4) {                                         // all partials of the channel in flight at once; same ascending order
+        float q[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) q[k] = k < nk ? __ldg(pb + (size_t)k * C + c) : 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < nk) t += q[k];
+      } else {
+#pragma unroll 4
+        for (int k = 0; k < nk; ++k) t += __ldg(pb + (size_t)k * C + c);
+      }
       t *= inv;
       p[c] = t;
       if (pooled_out) pooled_out[(size_t)b * C + c] = t;
@@ -284,7 +294,15 @@ __global__ void __launch_bounds__(MF_THREADS) masker_channel_fused_kernel(
   for (int j = warp; j < rows1; j += NW) {
     const float* wr = w1 + (size_t)j * C;
     float t = 0.f;
-    for (int c = lane; c < C; c += 32) t = fmaf(__ldg(wr + c), p[c], t);
+    int c = lane;
+    for (; c + 224 < C; c += 256) {                          // eight loads in flight; the fmaf chain keeps its order
+      float wv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) wv[u] = __ldg(wr + c + 32 * u);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t = fmaf(wv[u], p[c + 32 * u], t);
+    }
+    for (; c < C; c += 32) t = fmaf(__ldg(wr + c), p[c], t);
     t = warp_sum(t);
     if (lane == 0) {
       t += b1[j];
@@ -296,7 +314,24 @@ __global__ void __launch_bounds__(MF_THREADS) masker_channel_fused_kernel(
     for (int o = tid; o < 2 * G; o += MF_THREADS) {
       const float* wr = w2 + (size_t)o * hidden;
       float t = 0.f;
-      for (int j = 0; j < hidden; ++j) t = fmaf(__ldg(wr + j), h[j], t);
+      if ((hidden & 3) == 0 && (reinterpret_cast<uintptr_t>(w2) & 15) == 0) {
+        // whole row in flight (hidden is 16 for every LAUD-ResNet stage); the fmaf chain keeps its order
+        const float4* w4 = reinterpret_cast<const float4*>(wr);
+        int j = 0;
+        for (; j + 16 <= hidden; j += 16) {
+          const float4 q0 = __ldg(w4 + (j >> 2)), q1 = __ldg(w4 + (j >> 2) + 1), q2 = __ldg(w4 + (j >> 2) + 2), q3 = __ldg(w4 + (j >> 2) + 3);
+          t = fmaf(q0.x, h[j], t); t = fmaf(q0.y, h[j + 1], t); t = fmaf(q0.z, h[j + 2], t); t = fmaf(q0.w, h[j + 3], t);
+          t = fmaf(q1.x, h[j + 4], t); t = fmaf(q1.y, h[j + 5], t); t = fmaf(q1.z, h[j + 6], t); t = fmaf(q1.w, h[j + 7], t);
+          t = fmaf(q2.x, h[j + 8], t); t = fmaf(q2.y, h[j + 9], t); t = fmaf(q2.z, h[j + 10], t); t = fmaf(q2.w, h[j + 11], t);
+          t = fmaf(q3.x, h[j + 12], t); t = fmaf(q3.y, h[j + 13], t); t = fmaf(q3.z, h[j + 14], t); t = fmaf(q3.w, h[j + 15], t);
+        }
+        for (; j < hidden; j += 4) {
+          const float4 q0 = __ldg(w4 + (j >> 2));
+          t = fmaf(q0.x, h[j], t); t = fmaf(q0.y, h[j + 1], t); t = fmaf(q0.z, h[j + 2], t); t = fmaf(q0.w, h[j + 3], t);
+        }
+      } else {
+        for (int j = 0; j < hidden; ++j) t = fmaf(__ldg(wr + j), h[j], t);
+      }
       l[o] = t + b2[o];
     }
     __syncthreads();
