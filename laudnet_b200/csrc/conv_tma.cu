@@ -24,14 +24,21 @@
 //                          are not gathered.  HALO mode (3x3, stride 1, shared weights): the
 //                          activations of an m-group are staged ONCE per 64-channel chunk with their
 //                          zero halo; the nine taps are that tile read at nine row offsets.
-//   warp  9     MMA      : one lane issues tcgen05.mma (M=128, N<=256, K=16); accumulators in
-//                          TMEM, multi-buffered so the epilogue of one item overlaps the MMAs
-//                          of the next.
+//   warp  9     MMA      : the whole warp runs the issue loop with identical values and an elected lane
+//                          issues tcgen05.mma (M=128, N<=256, K=16) - issued from a lane-0 region every
+//                          UTCHMMA is wrapped in an ELECT / R2UR / BRA.U.ANY loop that costs as much as the
+//                          MMA; accumulators in TMEM, multi-buffered so the epilogue of one item overlaps
+//                          the MMAs of the next.
 //   warps 10-15 gather   : per-sample weight gathers with cp.async into the UMMA swizzle layout
 //                          (ROWS: active OUTPUT channels of K-major weights; KROWS: active INPUT
 //                          channels of the transposed weights) + the H1-constant K=16 step.
 //                          With shared weights two of their lanes are the slab DMA threads: they
-//                          issue the TMA stores / residual loads of the two epilogue halves.
+//                          issue the TMA stores / residual loads of the two epilogue halves; four of the
+//                          warps are the POOLING warps of the fused global average pool (gap_partial):
+//                          they add up the columns of every finished output slab per sample, so the next
+//                          block's channel masker never reads the activations.
+// The generic kernel (SPEC 0) is ~160 KB of code; the shared-weight layers run on instantiations with their
+// modes fixed at compile time (Mode<SPEC>): instruction-cache misses cost every role 0.5-1.4k cycles per item.
 // Layouts it does not take (row lists, per-class pre-bias, KUNITS gathers) run on the cp.async-staged
 // kernel (conv_umma.cu).  Restates (does not port) laud_resnet.py:115-144 of the reference.
 #include <cuda.h>
