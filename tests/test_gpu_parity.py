@@ -679,6 +679,47 @@ def test_split_chains_match_unsplit_forward(cuda_lib, name):
     assert torch.equal(s2, stats)
 
 
+@pytest.mark.parametrize("channel_exec", ["dense", "sparse"])
+def test_headline_r101_blocks_full_size_teacher_forced(cuda_lib, channel_exec):
+    """BASELINE configs[1] architecture at FULL resolution (224x224 input: 56/28/14/7 feature maps, widths 64..512), batch 3:
+    the first two bottlenecks of every stage - every distinct layer shape of LAUD-ResNet101 (downsample / stride-2 blocks and
+    the repeated shape) - fed the ORACLE's block input and channel gate: block output within ACT_TOL of the oracle
+    (laud_resnet.py:112-147), densities and flops fraction equal.  The oracle walks the whole trunk in between."""
+    kw = dict(synth.HEADLINE_KWARGS)
+    model = L.uni_resnet101(**kw)
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    sd = synth.synth_state_dict(shapes, 21)
+    model.load_state_dict(sd)
+    model = model.to(DEV).eval()
+    cfg = O.ResNetCfg()
+    x = synth.synth_images(3, 224, 21)
+    geoms = O.resnet_geometry(cfg)
+    blocks = [b for s in range(4) for b in getattr(model, f"layer{s + 1}")]
+    first = {0: 0, 1: 3, 2: 7, 3: 30}                          # index of each stage's first block (3/4/23/3)
+    wanted = {first[s] + d for s in range(4) for d in (0, 1)}
+    checked = 0
+    with torch.no_grad():
+        feat, _ = O.stem_forward(x, sd)
+        for i, (g, blk) in enumerate(zip(geoms, blocks)):
+            xin = feat.half().float()
+            tr = O.BlockTrace()
+            out_o = O.bottleneck_forward(xin, sd, g, tr)
+            if i in wanted:
+                blk._plan()
+                blk._solo_engine.channel_exec = channel_exec
+                state = (xin.to(DEV), None, None, None, None, None, torch.zeros((), device=DEV))
+                res = blk(state, 1.0, forced_channel_mask=tr.channel_mask.to(DEV), forced_spatial_mask=None)
+                err = _rel_err(res[0], out_o[0])
+                assert err <= ACT_TOL, f"{g.prefix} ({channel_exec}): block output error {err:.2e}"
+                assert abs(res[4][-1].item() - float(out_o[4])) < 1e-6                 # channel density
+                assert abs(res[5][-1].item() - float(out_o[5] / out_o[6])) < 1e-5     # flops fraction
+                checked += 1
+            feat = out_o[0]
+            if i > max(wanted):
+                break
+    assert checked == 8
+
+
 def test_headline_r101_channel_full_size_fused_gap_equals_standalone_masker(cuda_lib):
     """BASELINE configs[1] architecture (LAUD-ResNet101 channel-2222) at full resolution, batch 6: the forward whose
     channel maskers (and head) pool from conv3's fused-GAP partial sums takes the same decisions as the forward whose
