@@ -165,21 +165,42 @@ __global__ void __launch_bounds__(256, 2) stem_mma_kernel(const __half* __restri
     if ((W & 1) == 0) {
       // one patch row per warp and pass: ix0 is odd, so patch columns 1.. are pairs of an even-aligned input column and
       // its successor: 32-bit global loads (both inside or both outside the image, W even), 16-bit shared stores
-      for (int row = warp; row < 3 * S2_IH; row += 8) {
-        const int c = row / S2_IH, rr = row - c * S2_IH;
-        const int iy = iy0 + rr;
-        const bool yok = iy >= 0 && iy < H;
-        const __half* src = x + (((size_t)b * 3 + c) * H + (yok ? iy : 0)) * W;
-        __half* dst = s_in + row * S2_IWP;
-        const int q = 1 + 2 * lane, ix = ix0 + q;                 // lanes 0..30: columns 1..62; lane 31: column 0 (and 63: pad)
-        if (lane < 31) {
-          __half2 v = __float2half2_rn(0.f);
-          if (yok && ix >= 0 && ix + 1 < W) v = *reinterpret_cast<const __half2*>(src + ix);
-          dst[q] = __low2half(v);
-          dst[q + 1] = __high2half(v);
-        } else {
-          dst[0] = (yok && ix0 >= 0 && ix0 < W) ? src[ix0] : __float2half(0.f);
-          dst[S2_IWP - 1] = __float2half(0.f);
+      // all of this warp's rows are requested before the first one is stored: one memory latency per item, not fifteen
+      constexpr int RPW = (3 * S2_IH + 7) / 8;               // rows per warp (15)
+      __half2 pv[RPW];
+      __half p0[RPW];
+      const int q = 1 + 2 * lane, ix = ix0 + q;               // lanes 0..30: columns 1..62; lane 31: column 0 (and 63: pad)
+      const bool xok = ix >= 0 && ix + 1 < W, x0ok = ix0 >= 0 && ix0 < W;
+#pragma unroll
+      for (int u = 0; u < RPW; ++u) {
+        const int row = warp + 8 * u;
+        pv[u] = __float2half2_rn(0.f);
+        p0[u] = __float2half(0.f);
+        if (row < 3 * S2_IH) {
+          const int c = row / S2_IH, rr = row - c * S2_IH;
+          const int iy = iy0 + rr;
+          if (iy >= 0 && iy < H) {
+            const __half* src = x + (((size_t)b * 3 + c) * H + iy) * W;
+            if (lane < 31) {
+              if (xok) pv[u] = *reinterpret_cast<const __half2*>(src + ix);
+            } else if (x0ok) {
+              p0[u] = src[ix0];
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < RPW; ++u) {
+        const int row = warp + 8 * u;
+        if (row < 3 * S2_IH) {
+          __half* dst = s_in + row * S2_IWP;
+          if (lane < 31) {
+            dst[q] = __low2half(pv[u]);
+            dst[q + 1] = __high2half(pv[u]);
+          } else {
+            dst[0] = p0[u];
+            dst[S2_IWP - 1] = __float2half(0.f);
+          }
         }
       }
     } else {
