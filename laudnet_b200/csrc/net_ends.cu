@@ -148,6 +148,11 @@ __global__ void __launch_bounds__(256, 2) stem_mma_kernel(const __half* __restri
   const int total = B * tiles_x * tiles_y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
 
+  __shared__ float2 s_bn[2][C0 / 2];                         // folded BN scale / shift as channel pairs
+  for (int i = tid; i < C0; i += 256) {
+    reinterpret_cast<float*>(s_bn[0])[i] = scale[i];
+    reinterpret_cast<float*>(s_bn[1])[i] = shift[i];
+  }
   // weights [C0][3][7][7] -> [C0][(c,ky) x 8 + kx], zero padded
   for (int i = tid; i < C0 * S2_KP; i += 256) {
     const int o = i / S2_KP, k = i - o * S2_KP;
@@ -269,8 +274,9 @@ __global__ void __launch_bounds__(256, 2) stem_mma_kernel(const __half* __restri
               const int n = j * 8 + 2 * t;
               float v0 = 0.f, v1 = 0.f;
               if (inside) {
-                v0 = fmaxf(fmaf(acc[m][j][2 * h], __ldg(scale + n), __ldg(shift + n)), 0.f);
-                v1 = fmaxf(fmaf(acc[m][j][2 * h + 1], __ldg(scale + n + 1), __ldg(shift + n + 1)), 0.f);
+                const float2 sc = s_bn[0][n >> 1], sh = s_bn[1][n >> 1];
+                v0 = fmaxf(fmaf(acc[m][j][2 * h], sc.x, sh.x), 0.f);
+                v1 = fmaxf(fmaf(acc[m][j][2 * h + 1], sc.y, sh.y), 0.f);
               }
               *reinterpret_cast<__half2*>(s_c + p * CP + n) = __floats2half2_rn(v0, v1);
             }
