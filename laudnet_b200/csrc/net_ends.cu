@@ -569,13 +569,25 @@ __global__ void nhwc_to_nchw_kernel(const __half* src, int lds, int B, int C, in
 __global__ void forward_stats_kernel(const int* __restrict__ counts, const long long* __restrict__ consts,
                                      int n_blocks, long long stem_flops, long long pool_flops,
                                      long long fc_flops, float* __restrict__ out) {
-  if (threadIdx.x || blockIdx.x) return;
+  // the warp stages every block's constants and counts in shared memory (loads in flight together); thread 0 then
+  // walks the blocks in order - the accumulation itself must stay serial to reproduce the reference's rounding
+  constexpr int SMAX = 64;
+  __shared__ long long s_k[SMAX * 12];
+  __shared__ int s_c[SMAX * 4];
+  if (blockIdx.x) return;
+  const bool staged = n_blocks <= SMAX;
+  if (staged) {
+    for (int i = threadIdx.x; i < n_blocks * 12; i += blockDim.x) s_k[i] = consts[i];
+    for (int i = threadIdx.x; i < n_blocks * 4; i += blockDim.x) s_c[i] = counts[i];
+  }
+  __syncthreads();
+  if (threadIdx.x) return;
   float flops = 0.f;
   bool flops_is_tensor = false;
   long long flops_int = stem_flops;
   for (int i = 0; i < n_blocks; ++i) {
-    const long long* k = consts + (size_t)i * 12;
-    const int* c = counts + (size_t)i * 4;
+    const long long* k = staged ? s_k + i * 12 : consts + (size_t)i * 12;
+    const int* c = staged ? s_c + i * 4 : counts + (size_t)i * 4;
     const bool use_c = k[10] & 1, use_s = k[10] & 2;
     const float rc = use_c ? __fdiv_rn((float)c[0], (float)k[6]) : 1.0f;
     const float r3 = use_s ? __fdiv_rn((float)c[1], (float)k[7]) : 1.0f;
