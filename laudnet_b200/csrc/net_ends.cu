@@ -440,26 +440,56 @@ __global__ void __launch_bounds__(128) head_fc_mma_kernel(const float* __restric
   for (int j = 0; j < 4; ++j)
 #pragma unroll
     for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
-#pragma unroll 4
-  for (int k0 = 0; k0 < C; k0 += 16) {
-    const float2 f[4] = {__ldg(reinterpret_cast<const float2*>(p0 + k0)), __ldg(reinterpret_cast<const float2*>(p1 + k0)),
-                         __ldg(reinterpret_cast<const float2*>(p0 + k0 + 8)), __ldg(reinterpret_cast<const float2*>(p1 + k0 + 8))};
+  // four k16 steps per round: all 48 operand loads of the round are issued before the first MMA consumes one
+  auto mma_step = [&](const float2* f, const uint32_t* bq) {
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const __half2 h = __floats2half2_rn(f[e].x, f[e].y);
-      const float2 hf = __half22float2(h);
-      const __half2 l = __floats2half2_rn(f[e].x - hf.x, f[e].y - hf.y);
-      hi[e] = *reinterpret_cast<const uint32_t*>(&h);
-      lo[e] = *reinterpret_cast<const uint32_t*>(&l);
+      const __half2 hh = __floats2half2_rn(f[e].x, f[e].y);
+      const float2 hf = __half22float2(hh);
+      const __half2 ll = __floats2half2_rn(f[e].x - hf.x, f[e].y - hf.y);
+      hi[e] = *reinterpret_cast<const uint32_t*>(&hh);
+      lo[e] = *reinterpret_cast<const uint32_t*>(&ll);
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const uint32_t b0 = __ldg(reinterpret_cast<const unsigned int*>(wr[j] + k0));
-      const uint32_t b1 = __ldg(reinterpret_cast<const unsigned int*>(wr[j] + k0 + 8));
-      mma_16816(acc[j], hi, b0, b1);
-      mma_16816(acc[j], lo, b0, b1);
+      mma_16816(acc[j], hi, bq[2 * j], bq[2 * j + 1]);
+      mma_16816(acc[j], lo, bq[2 * j], bq[2 * j + 1]);
     }
+  };
+  int k0 = 0;
+  for (; k0 + 64 <= C; k0 += 64) {
+    float2 f[4][4];
+    uint32_t bq[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int kk = k0 + 16 * u;
+      f[u][0] = __ldg(reinterpret_cast<const float2*>(p0 + kk));
+      f[u][1] = __ldg(reinterpret_cast<const float2*>(p1 + kk));
+      f[u][2] = __ldg(reinterpret_cast<const float2*>(p0 + kk + 8));
+      f[u][3] = __ldg(reinterpret_cast<const float2*>(p1 + kk + 8));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        bq[u][2 * j] = __ldg(reinterpret_cast<const unsigned int*>(wr[j] + kk));
+        bq[u][2 * j + 1] = __ldg(reinterpret_cast<const unsigned int*>(wr[j] + kk + 8));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) mma_step(f[u], bq[u]);
+  }
+  for (; k0 < C; k0 += 16) {
+    float2 f[4];
+    uint32_t bq[8];
+    f[0] = __ldg(reinterpret_cast<const float2*>(p0 + k0));
+    f[1] = __ldg(reinterpret_cast<const float2*>(p1 + k0));
+    f[2] = __ldg(reinterpret_cast<const float2*>(p0 + k0 + 8));
+    f[3] = __ldg(reinterpret_cast<const float2*>(p1 + k0 + 8));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      bq[2 * j] = __ldg(reinterpret_cast<const unsigned int*>(wr[j] + k0));
+      bq[2 * j + 1] = __ldg(reinterpret_cast<const unsigned int*>(wr[j] + k0 + 8));
+    }
+    mma_step(f, bq);
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
