@@ -298,11 +298,11 @@ def run_graft(args):
 
     peaks = _peaks()
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01C_conv_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r01E_conv_traffic.json")
     if os.path.exists(tpath):                  # dram__bytes_read+write of the conv launches from the committed ncu capture
         tj = json.load(open(tpath))
         traffic = tj["dram_bytes_per_launch_avg"]
-        traffic_src = "profiles/r01C_conv_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, average per conv launch)"
+        traffic_src = "profiles/r01E_conv_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, average per conv launch)"
     conv_bytes = work.conv_bytes_per_image * B
     conv_flops = work.conv_flops_per_image * B
     ach_gbs = conv_bytes / (conv_ms_step * 1e-3) / 1e9
@@ -316,7 +316,7 @@ def run_graft(args):
         "share_of_step": conv_ms_step / ms_step,
         "share_note": "summed device time of the conv launches (eager, one stream) over the CUDA-graphed step: the graph runs two "
                       "chains whose kernels overlap, so this exceeds the serialised share of the ncu launch list "
-                      "(profiles/r01C_launch_summary.txt: conv 87 %, masker 6 %, stem 6 %, head 1 %)",
+                      "(profiles/r01E_launch_summary.txt: conv 89 %, masker 5 %, stem 4 %, head 1 %)",
         "tensor": {"achieved": conv_flops / (conv_ms_step * 1e-3) / 1e12, "peak": peaks["tflops"], "unit": "TFLOP/s",
                    "frac": conv_flops / (conv_ms_step * 1e-3) / 1e12 / peaks["tflops"],
                    "note": "sparsity-adjusted algorithmic FLOPs (2 x reference counter, conv terms)"},
