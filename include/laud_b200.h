@@ -197,7 +197,9 @@ typedef struct laud_conv_desc {
                                k-th tile that contains any of them (k = tile - (b*H*W)/128; slots past the last
                                such tile are not written).  Needs gap_tiles >= (H*W-1)/128 + 2.  Only 1x1 stride-1
                                layers with nothing per sample (no lists, gates, n_mask), C_out % 64 == 0, H*W >= 43;
-                               anything else returns LAUD_E_UNSUPPORTED.  laud_masker_channel_from_partials consumes it. */
+                               anything else returns LAUD_E_UNSUPPORTED.  laud_masker_channel_from_partials consumes it.
+                               Deterministic (no atomics); the fp32 grouping of a sample's sum follows the tile
+                               boundaries, i.e. depends on the sample's offset in the batch. */
   int32_t gap_tiles;
   const void* w_t;          /* optional transposed copy of w: fp16 [ksize*ksize, C_in, C_out].  With k_idx it
                                selects the K-row-gather path (16-byte gathers of the active input channels;
