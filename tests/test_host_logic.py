@@ -190,3 +190,29 @@ def test_allgather_logits_gloo_world2(batch):
 def test_allgather_single_process_is_identity():
     x = torch.randn(3, 4)
     assert ldist.allgather_logits(x, 3) is x
+
+
+def test_gap_partial_slot_arithmetic():
+    """Layout contract of laud_conv_desc::gap_partial (include/laud_b200.h): the flat [B*HW] pixel list is cut into
+    128-pixel tiles; slot k of sample b is tile (b*HW)//128 + k.  For every feature-map size of the supported networks
+    the tiles that hold pixels of a sample are contiguous, fit in gap_tiles(HW) slots, a tile spans at most 4 samples
+    (the kernel's segment limit, HW >= 43), and every pixel is counted exactly once."""
+    from laudnet_b200._engine import gap_tiles
+    import numpy as np
+    for hw in (43, 49, 64, 100, 196, 784, 3136, 12544):
+        K = gap_tiles(hw)
+        assert K == (hw - 1) // 128 + 2
+        B = 37
+        tile_of = np.arange(B * hw) // 128
+        sample_of = np.arange(B * hw) // hw
+        counted = np.zeros(B, dtype=np.int64)
+        for b in range(B):
+            tiles = np.unique(tile_of[sample_of == b])
+            first = (b * hw) // 128
+            assert tiles[0] == first and tiles[-1] == ((b + 1) * hw - 1) // 128
+            assert np.array_equal(tiles, np.arange(tiles[0], tiles[-1] + 1)) and len(tiles) <= K
+            for t in tiles:                                   # what one pooling task adds to slot t - first
+                counted[b] += int(np.sum((tile_of == t) & (sample_of == b)))
+        assert np.all(counted == hw)
+        spans = [len(np.unique(sample_of[tile_of == t])) for t in np.unique(tile_of)]
+        assert max(spans) <= 4
