@@ -485,6 +485,8 @@ class ResNetEngine:
         masked-dense channel execution, no spatial mask, no layer skip) on the tcgen05 path."""
         if not self.fuse_gap or (p.index + 1 < len(self.plans) and not self.plans[p.index + 1].use_c):
             return False                 # (the last block's pool feeds the head)
+        if os.environ.get("LAUD_CONV_V3") or os.environ.get("LAUD_NO_FLAT") or os.environ.get("LAUD_NO_DMA"):
+            return False                 # A/B switches that take conv3 off the flat slab path of the TMA-staged kernel
         if p.use_s or (p.use_c and self.channel_exec != "dense") or self.impl not in (_lib.CONV_AUTO, _lib.CONV_UMMA):
             return False
         return p.outplanes % 64 == 0 and p.H_out * p.H_out >= 43
