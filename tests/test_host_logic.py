@@ -216,3 +216,32 @@ def test_gap_partial_slot_arithmetic():
         assert np.all(counted == hw)
         spans = [len(np.unique(sample_of[tile_of == t])) for t in np.unique(tile_of)]
         assert max(spans) <= 4
+
+
+def test_engine_decides_where_the_gap_is_fused(monkeypatch):
+    """ResNetEngine._gap_fusable (host logic, no device): conv3 leaves the pool of its output for the next block's channel
+    masker (or, in the last block, for the head) only when conv3 is a flat GEMM - masked-dense channel execution, no
+    spatial / layer gate in the producing block - and the feature map is large enough for the kernel's segment limit."""
+    from laudnet_b200 import _lib
+    from laudnet_b200._engine import BlockPlan, ResNetEngine
+    for var in ("LAUD_CONV_V3", "LAUD_NO_FLAT", "LAUD_NO_DMA"):
+        monkeypatch.delenv(var, raising=False)
+
+    def plans(modes, hw=(56, 28, 14, 7)):
+        return [BlockPlan(index=i, stage=i, inplanes=64, width=64, outplanes=256, stride=1, H_in=h, H_out=h, mode=m, gran=2, G=32,
+                          g_spatial=1, mask_size=1) for i, (m, h) in enumerate(zip(modes, hw))]
+
+    eng = ResNetEngine.__new__(ResNetEngine)
+    eng.fuse_gap, eng.channel_exec, eng.impl = True, "dense", _lib.CONV_AUTO
+    eng.plans = plans(["channel"] * 4)
+    assert [eng._gap_fusable(p) for p in eng.plans] == [True, True, True, True]          # the last one feeds the head
+    eng.plans = plans(["channel", "spatial", "channel", "layer"])
+    assert [eng._gap_fusable(p) for p in eng.plans] == [False, False, False, False]      # next has no channel gate / own spatial gate
+    eng.plans = plans(["channel"] * 4, hw=(56, 28, 14, 6))
+    assert [eng._gap_fusable(p) for p in eng.plans] == [True, True, True, False]         # 36 pixels: a tile could span > 4 samples
+    eng.plans = plans(["channel"] * 4)
+    eng.channel_exec = "sparse"
+    assert not any(eng._gap_fusable(p) for p in eng.plans)                               # gathered conv3 is not a flat GEMM
+    eng.channel_exec = "dense"
+    monkeypatch.setenv("LAUD_NO_FLAT", "1")
+    assert not any(eng._gap_fusable(p) for p in eng.plans)
