@@ -154,6 +154,15 @@ class BlockPlan:
     module: nn.Module = None
 
     @property
+    def masker_kind(self) -> Optional[str]:
+        """'MLP' (pools the block input: its GAP can be fused into the producing conv3) or 'conv_linear' (pools
+        relu(bn(conv1x1(x))), utils.py:150-169: needs the activations)."""
+        mk = getattr(self.module, "masker_channel", None)
+        if mk is None:
+            return None
+        return "MLP" if hasattr(mk, "gate_from_partials") else "conv_linear"
+
+    @property
     def use_c(self) -> bool:
         return self.mode in ("channel", "both")
 
@@ -247,6 +256,11 @@ class ResNetEngine:
         self.stats_consts = self._stats_consts(dev)
         self.prepared_for = dev
         self._ws.clear()
+        for g in getattr(self, "_graphs", []):       # captured graphs hold raw pointers to the tensors just replaced
+            gf = g()
+            if gf is not None:
+                gf.valid = False
+        self._graphs = []
 
     def _stats_consts(self, dev) -> torch.Tensor:
         rows = []
@@ -313,6 +327,13 @@ class ResNetEngine:
             gap=torch.empty(max(B * gap_tiles(p.H_out * p.H_out) * p.outplanes for p in self.plans), dtype=torch.float32,
                             device=dev),
         )
+        cl = [p for p in self.plans if p.masker_kind == "conv_linear"]
+        if cl:      # Masker_channel_conv_linear: reduced-width feature map and its pool
+            cr = lambda p: p.module.masker_channel.conv[0].weight.shape[0]
+            ws["mkz"] = torch.empty(max(B * p.H_in * p.H_in * cr(p) for p in cl), **f16)
+            ws["mkpool"] = torch.empty(max(B * cr(p) for p in cl), dtype=torch.float32, device=dev)
+        else:
+            ws["mkz"] = ws["mkpool"] = None
         consts = self.stats_consts.clone()
         for i, p in enumerate(self.plans):
             S = min(p.mask_size, p.H_in)
@@ -355,6 +376,11 @@ class ResNetEngine:
                 self._force_channel_gate(gate, forced_channel_mask, counts[0:1])
             elif gap_in:
                 blk.masker_channel.gate_from_partials(ws["gap"], B, Hi * Hi, p.inplanes, gap_tiles(Hi * Hi), counts[0:1], gate)
+            elif p.masker_kind == "conv_linear":
+                # conv 1x1 + BN + ReLU at full resolution, then pool (utils.py:150-169): pre-packed weights, workspaces
+                blk.masker_channel.gate_nhwc(x[:B * Hi * Hi * p.inplanes].view(B, Hi, Hi, p.inplanes), counts[0:1],
+                                             out=gate, partial_ws=ws["partial"], impl=self.impl, z_ws=ws["mkz"],
+                                             pooled_ws=ws["mkpool"])
             else:
                 blk.masker_channel.gate_nhwc(x[:B * Hi * Hi * p.inplanes].view(B, Hi, Hi, p.inplanes), counts[0:1],
                                              out=gate, partial_ws=ws["partial"])
@@ -382,17 +408,17 @@ class ResNetEngine:
                 slog = None
             else:
                 slog = torch.empty((B, 2 * g, S, S), dtype=torch.float32, device=x.device) if keep is not None else None
-                wt = blk.masker_spatial.conv.weight.detach().reshape(2 * g, p.inplanes)
+                wt, wbias = blk.masker_spatial._weights()
                 if S == 1 and "lidx" in ws:
                     # one gate per sample (layer skip): global pool -> 2g-row linear -> keep>=drop is exactly the
                     # one-layer channel masker; its fused one-CTA-per-sample kernel pools at HBM speed
                     check(L.laud_masker_channel_mlp(ptr(x), B, Hi * Hi, p.inplanes, 1, ptr(wt),
-                                                    ptr(blk.masker_spatial.conv.bias.detach()), 0, None, None, g,
+                                                    ptr(wbias), 0, None, None, g,
                                                     ptr(ws["partial"]), None, ptr(slog), ptr(small), ptr(ws["lidx"]),
                                                     ptr(ws["lcnt"]), ptr(counts[1:2]), st), "laud_masker_channel_mlp")
                 else:
                     check(L.laud_masker_spatial(ptr(x), B, Hi, Hi, p.inplanes, ptr(wt),
-                                                ptr(blk.masker_spatial.conv.bias.detach()), g, S, ptr(slog), ptr(small),
+                                                ptr(wbias), g, S, ptr(slog), ptr(small),
                                                 ptr(counts[1:2]), st), "laud_masker_spatial")
             m3 = ws["m3"][:B * g * Ho * Ho].view(B, g, Ho, Ho)
             m2 = ws["m2"][:B * g * Ho * Ho].view(B, g, Ho, Ho)
@@ -415,7 +441,9 @@ class ResNetEngine:
                 keep.mask_conv3, keep.mask_conv2, keep.mask_conv1 = m3.clone(), m2.clone(), m1.clone()
 
         # layer skip: ordered list of the active samples; convolutions take it as their work list
-        skip = (p.mode == "layer" and self.layer_exec == "skip" and gate is None and "srows" in ws)
+        # (one gate per SAMPLE: with spatial_mask_channel_group > 1 the gate is per (sample, channel group) and the
+        #  block runs masked-dense with the grouped out_mask, as laud_resnet.py:133 / utils.py:27-33 do)
+        skip = (p.mode == "layer" and self.layer_exec == "skip" and gate is None and "srows" in ws and p.g_spatial == 1)
         sl = {}
         if skip:
             if not fast_layer:
@@ -483,8 +511,12 @@ class ResNetEngine:
         """True if block p's conv3 can leave the GAP partial sums of its output for the NEXT block's channel masker:
         the next block pools its input for a channel gate, and this conv3 is a flat GEMM (1x1, nothing per sample:
         masked-dense channel execution, no spatial mask, no layer skip) on the tcgen05 path."""
-        if not self.fuse_gap or (p.index + 1 < len(self.plans) and not self.plans[p.index + 1].use_c):
-            return False                 # (the last block's pool feeds the head)
+        if not self.fuse_gap:
+            return False
+        if p.index + 1 < len(self.plans):        # (the last block's pool feeds the head)
+            nxt = self.plans[p.index + 1]
+            if not nxt.use_c or nxt.masker_kind != "MLP":
+                return False             # conv_linear pools relu(bn(conv(x))), not x: it must read the activations
         if os.environ.get("LAUD_CONV_V3") or os.environ.get("LAUD_NO_FLAT") or os.environ.get("LAUD_NO_DMA"):
             return False                 # A/B switches that take conv3 off the flat slab path of the TMA-staged kernel
         if p.use_s or (p.use_c and self.channel_exec != "dense") or self.impl not in (_lib.CONV_AUTO, _lib.CONV_UMMA):
@@ -505,9 +537,13 @@ class ResNetEngine:
     # ----------------------------------------------------------------- forward
     def forward(self, x: torch.Tensor, keep: Optional[List[BlockOutputs]] = None, slot: int = 0,
                 logits_out: Optional[torch.Tensor] = None, want_stats: bool = True):
-        m = self.model
         if x.device.type != "cuda":
             raise LaudError("ResNet.forward: expected a CUDA tensor - there is no CPU path")
+        with torch.cuda.device(x.device):        # launches go to the current stream of the INPUT's device
+            return self._forward(x, keep, slot, logits_out, want_stats)
+
+    def _forward(self, x, keep, slot, logits_out, want_stats):
+        m = self.model
         if self.prepared_for != x.device:
             self.prepare()
         if x.dtype not in (torch.float16, torch.float32):
@@ -575,6 +611,10 @@ class ResNetEngine:
         of a 256-image batch otherwise leave ~14 % of the 148 SMs idle in every second wave.  Logits land in one
         tensor; the statistics are computed from the summed counts with the whole batch's denominators, so they equal
         the unsplit forward's."""
+        with torch.cuda.device(x.device):
+            return self._forward_split(x, splits)
+
+    def _forward_split(self, x: torch.Tensor, splits: int):
         if self.prepared_for != x.device:
             self.prepare()
         B, _, H, W = x.shape
@@ -651,6 +691,10 @@ class GraphedForward:
         self.splits = splits
         fwd = (lambda xx: engine.forward_split(xx, splits)) if splits > 1 else engine.forward
         self.engine = engine
+        self.valid = True
+        self.device = x_example.device
+        if engine.prepared_for != x_example.device:
+            engine.prepare()
         self.static_x = x_example.detach().to(torch.float16).contiguous().clone()
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
@@ -665,8 +709,18 @@ class GraphedForward:
         with torch.cuda.graph(self.graph):
             self.logits, self.stats = fwd(self.static_x)
         self.launches = _lib.launch_count() - n0     # kernels of ours inside one replay
+        # the graph replays raw device pointers: keep the prepared tensors and workspaces alive with it, and let the
+        # engine mark it stale when prepare() replaces them (load_state_dict, .to(), in-place edits + prepare())
+        self._keepalive = (list(engine.plans), dict(engine._ws), getattr(engine, "stem_w", None), getattr(engine, "fc_w", None))
+        import weakref
+        if not hasattr(engine, "_graphs"):
+            engine._graphs = []
+        engine._graphs.append(weakref.ref(self))
 
     def replay(self):
+        if not self.valid or self.engine.prepared_for != self.device:
+            raise LaudError("GraphedForward: the model was re-prepared (load_state_dict / .to() / prepare()) after this "
+                            "graph was captured; capture() it again")
         self.graph.replay()
         return self.logits, self.stats
 

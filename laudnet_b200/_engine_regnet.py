@@ -215,8 +215,8 @@ class RegNetEngine:
                 slog = None
             else:
                 slog = torch.empty((B, 2 * g, S, S), dtype=torch.float32, device=x.device) if keep is not None else None
-                wt = f.masker_spatial.conv.weight.detach().reshape(2 * g, p.w_in)
-                check(L.laud_masker_spatial(ptr(x), B, Hi, Hi, p.w_in, ptr(wt), ptr(f.masker_spatial.conv.bias.detach()),
+                wt, wbias = f.masker_spatial._weights()
+                check(L.laud_masker_spatial(ptr(x), B, Hi, Hi, p.w_in, ptr(wt), ptr(wbias),
                                             g, S, ptr(slog), ptr(small), ptr(counts[1:2]), st), "laud_masker_spatial")
             m3 = ws["m3"][:B * g * Ho * Ho].view(B, g, Ho, Ho)
             m2 = ws["m2"][:B * g * Ho * Ho].view(B, g, Ho, Ho)
@@ -265,9 +265,13 @@ class RegNetEngine:
 
     # ----------------------------------------------------------------- forward
     def forward(self, x: torch.Tensor, keep: Optional[List[BlockOutputs]] = None):
-        m = self.model
         if x.device.type != "cuda":
             raise LaudError("LAD_RegNet.forward: expected a CUDA tensor - there is no CPU path")
+        with torch.cuda.device(x.device):        # launches go to the current stream of the INPUT's device
+            return self._forward(x, keep)
+
+    def _forward(self, x, keep):
+        m = self.model
         if self.prepared_for != x.device:
             self.prepare()
         if x.dtype not in (torch.float16, torch.float32):

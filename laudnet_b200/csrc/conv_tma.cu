@@ -1183,11 +1183,11 @@ int conv_forward_tma(const ConvArgs& a_in, cudaStream_t s) {
     a.B = 1;
     flat = true;
   }
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    LAUD_CUDA(cudaGetDevice(&dev));
-    LAUD_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  static int num_sms_dev[MAX_DEVICES] = {0};
+  const int dev = current_device();
+  if (num_sms_dev[dev] == 0) {
+    int n = 0;
+    LAUD_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
     LAUD_CUDA(cudaFuncSetAttribute(conv_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     LAUD_CUDA(cudaFuncSetAttribute(conv_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     LAUD_CUDA(cudaFuncSetAttribute(conv_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
@@ -1196,7 +1196,10 @@ int conv_forward_tma(const ConvArgs& a_in, cudaStream_t s) {
     LAUD_CUDA(cudaFuncSetAttribute(conv_tma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     vtab4_init_kernel<<<32, 256, 0, s>>>();
     if (int e = check_launch("vtab4_init_kernel")) return e;
+    if (int e = finish_first_call_init(s, "conv_forward_tma")) return e;
+    num_sms_dev[dev] = n;
   }
+  const int num_sms = num_sms_dev[dev];
   Plan pl{};
   const int HWo = a.H_out * a.W_out;
   const int taps = a.ksize * a.ksize;

@@ -588,15 +588,18 @@ bool conv_umma_supported(const ConvArgs& a) {
 
 int conv_forward_umma(const ConvArgs& a, cudaStream_t s) {
   if (!conv_umma_supported(a)) return conv_forward_hmma(a, s);
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    LAUD_CUDA(cudaGetDevice(&dev));
-    LAUD_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  static int num_sms_dev[MAX_DEVICES] = {0};
+  const int dev = current_device();
+  if (num_sms_dev[dev] == 0) {
+    int n = 0;
+    LAUD_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
     LAUD_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    vtab_init_kernel<<<32, 256, 0, s>>>();      // tap-validity table of the H1-constant K-step (once per process)
+    vtab_init_kernel<<<32, 256, 0, s>>>();      // tap-validity table of the H1-constant K-step (once per device)
     if (int e = check_launch("vtab_init_kernel")) return e;
+    if (int e = finish_first_call_init(s, "conv_forward_umma")) return e;
+    num_sms_dev[dev] = n;
   }
+  const int num_sms = num_sms_dev[dev];
   Plan pl;
   pl.mode = (a.k_idx && a.wt && aligned16(a.wt)) ? MODE_KROWS : (a.k_idx ? MODE_KUNITS : MODE_ROWS);
   const long long HWo = (long long)a.H_out * a.W_out;

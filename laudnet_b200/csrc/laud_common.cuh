@@ -41,6 +41,29 @@ inline int check_launch(const char* what) {
     }                                                                        \
   } while (0)
 
+// Per-device one-time state (function attributes, SM count, device tables): a process may drive several GPUs.
+constexpr int MAX_DEVICES = 64;
+inline int current_device() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= MAX_DEVICES) d = 0;
+  return d;
+}
+// One-time device-table initialisation kernels are launched on the caller's stream and waited for, so that launches
+// on OTHER streams (parallel graph chains) are ordered after them.  Not possible inside a stream capture.
+inline int finish_first_call_init(cudaStream_t s, const char* what) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone) {
+    set_error("%s: the first call on a device must not be inside a CUDA-graph capture (run one eager forward first)", what);
+    return LAUD_E_UNSUPPORTED;
+  }
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return LAUD_E_CUDA;
+  }
+  return LAUD_OK;
+}
+
 __host__ __device__ __forceinline__ int round_up(int v, int a) { return a > 0 ? (v + a - 1) / a * a : v; }
 
 __device__ __forceinline__ float warp_sum(float v) {

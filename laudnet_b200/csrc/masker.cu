@@ -577,10 +577,11 @@ static int launch_decide(const float* partial, const float* pooled_in, int B, in
   LAUD_REQUIRE(G > 0, "channel masker: G must be positive");
   const size_t smem = decide_smem(C, layers == 2 ? hidden : 0, G);
   LAUD_REQUIRE(smem <= 200 * 1024, "channel masker: C/G too large for shared memory");
-  static size_t decide_smem_set = 48 * 1024;
-  if (smem > decide_smem_set) {
+  static size_t decide_smem_set[MAX_DEVICES] = {0};    // per device; sizes up to 48 KB need no attribute
+  const int dev = current_device();
+  if (smem > 48 * 1024 && smem > decide_smem_set[dev]) {
     LAUD_CUDA(cudaFuncSetAttribute(masker_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    decide_smem_set = smem;
+    decide_smem_set[dev] = smem;
   }
   masker_decide_kernel<<<B, 256, smem, s>>>(partial, pooled_in, C, LAUD_GAP_SPLITS, HW, layers, w1, b1,
                                             layers == 2 ? hidden : 0, w2, b2, G, pooled_out, logits_out,
@@ -588,7 +589,7 @@ static int launch_decide(const float* partial, const float* pooled_in, int B, in
   return check_launch("masker_decide_kernel");
 }
 
-static size_t g_fused_smem_set = 48 * 1024;     // largest dynamic shared memory size set on the fused kernel so far
+static size_t g_fused_smem_set[MAX_DEVICES] = {0};     // largest dynamic shared memory size set on the fused kernel so far, per device
 
 // launched with programmatic stream serialization: the kernel's first instructions overlap the predecessor's tail
 static void launch_masker_fused(int B, size_t smem, cudaStream_t s, const __half* x, int HW, int C, int layers,
@@ -625,9 +626,9 @@ extern "C" int laud_masker_channel_mlp(const void* x, int B, int HW, int C, int 
   LAUD_REQUIRE(G > 0, "channel masker: G must be positive");
   const size_t smem = sizeof(float) * MF_THREADS * 8 + decide_smem(C, layers == 2 ? hidden : 0, G);
   LAUD_REQUIRE(smem <= 200 * 1024, "channel masker: C/G too large for shared memory");
-  if (smem > g_fused_smem_set) {
+  if (smem > 48 * 1024 && smem > g_fused_smem_set[current_device()]) {
     LAUD_CUDA(cudaFuncSetAttribute(masker_channel_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    g_fused_smem_set = smem;
+    g_fused_smem_set[current_device()] = smem;
   }
   launch_masker_fused(B, smem, s, (const __half*)x, HW, C, layers, w1, b1, layers == 2 ? hidden : 0, w2, b2, G, pooled_out,
                       logits_out, mask_out, idx_out, cnt_out, total_out, nullptr, 0);
@@ -649,9 +650,9 @@ extern "C" int laud_masker_channel_from_partials(const float* partials, int B, i
   LAUD_REQUIRE(G > 0, "channel masker: G must be positive");
   const size_t smem = sizeof(float) * MF_THREADS * 8 + decide_smem(C, layers == 2 ? hidden : 0, G);
   LAUD_REQUIRE(smem <= 200 * 1024, "channel masker: C/G too large for shared memory");
-  if (smem > g_fused_smem_set) {
+  if (smem > 48 * 1024 && smem > g_fused_smem_set[current_device()]) {
     LAUD_CUDA(cudaFuncSetAttribute(masker_channel_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    g_fused_smem_set = smem;
+    g_fused_smem_set[current_device()] = smem;
   }
   launch_masker_fused(B, smem, s, nullptr, HW, C, layers, w1, b1, layers == 2 ? hidden : 0, w2, b2, G, pooled_out, logits_out,
                       mask_out, idx_out, cnt_out, total_out, partials, gap_tiles);

@@ -313,15 +313,15 @@ int launch_stem_mma(const __half* x, int B, int H, int W, const __half* w, const
                     __half* y, cudaStream_t s) {
   constexpr int C0 = 8 * NT;
   const size_t smem = sizeof(__half) * ((size_t)C0 * S2_KP + 3 * S2_IH * S2_IWP + (size_t)S2_NPIX * (C0 + 8));
-  static bool attr_set = false;
-  static int num_sms = 0;
-  if (!attr_set) {
-    int dev = 0;
-    LAUD_CUDA(cudaGetDevice(&dev));
-    LAUD_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  static int num_sms_dev[MAX_DEVICES] = {0};
+  const int dev = current_device();
+  if (num_sms_dev[dev] == 0) {
+    int n = 0;
+    LAUD_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
     LAUD_CUDA(cudaFuncSetAttribute(stem_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    num_sms_dev[dev] = n;
   }
+  const int num_sms = num_sms_dev[dev];
   const int Hp = H / 4, Wp = W / 4;
   const long long total = (long long)B * ((Wp + S2_PW - 1) / S2_PW) * ((Hp + S2_PH - 1) / S2_PH);
   const int grid = (int)(total < 2ll * num_sms ? total : 2ll * num_sms);
@@ -685,10 +685,11 @@ extern "C" int laud_stem_forward(const void* x, int B, int H, int W, const void*
   const int Hp = H / 4, Wp = W / 4;
   const size_t smem = sizeof(float) * 3 * ST_IH * ST_IWP + sizeof(__half) * (147 + ST_CH * ST_CW) * (size_t)C0;
   LAUD_REQUIRE(smem <= 200 * 1024, "laud_stem_forward: stem width %d too large", C0);
-  static size_t stem_smem_set = 0;      // set once per size: keeps the launch path free of attribute calls (graph capture)
-  if (smem > stem_smem_set) {
+  static size_t stem_smem_set[MAX_DEVICES] = {0};      // set once per size and device: keeps the launch path free of attribute calls (graph capture)
+  const int dev = current_device();
+  if (smem > stem_smem_set[dev]) {
     LAUD_CUDA(cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    stem_smem_set = smem;
+    stem_smem_set[dev] = smem;
   }
   dim3 grid((Wp + ST_PW - 1) / ST_PW, (Hp + ST_PH - 1) / ST_PH, B);
   stem_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const __half*)x, H, W, (const __half*)w, C0, scale, shift,

@@ -91,6 +91,10 @@ class Bottleneck(nn.Module):
         if self.training:
             raise LaudError("Bottleneck: training mode is not part of the CUDA inference path; call .eval()")
         _lib.require_cuda(x, "Bottleneck")
+        with torch.cuda.device(x.device):
+            return self._forward_cuda(x, l3, l2, l1, lc, lperc, flops, forced_channel_mask, forced_spatial_mask, keep)
+
+    def _forward_cuda(self, x, l3, l2, l1, lc, lperc, flops, forced_channel_mask, forced_spatial_mask, keep):
         plan = self._plan()
         B, C, H, W = x.shape
         if C != plan.inplanes or H != plan.H_in or W != plan.H_in:
@@ -170,7 +174,7 @@ class _SoloEngine(ResNetEngine):
                 m1=torch.empty(B * p.g_spatial * hw, dtype=torch.uint8, device=dev),
                 srows=torch.empty((B,), **i32), scnt=torch.zeros((1,), **i32), cws=torch.zeros((64,), **i32),
                 lidx=torch.empty((B * p.g_spatial,), **i32), lcnt=torch.empty((B,), **i32),
-                counts=torch.zeros((1, 4), **i32))
+                counts=torch.zeros((1, 4), **i32), mkz=None, mkpool=None)
             consts = self.stats_consts.clone()
             S = min(p.mask_size, p.H_in)
             consts[0, 6] = B * p.G

@@ -111,6 +111,23 @@ class Masker_spatial(nn.Module):
             self.conv.bias[:mask_channel_group] = 5.0
             self.conv.bias[mask_channel_group + 1:] = 0.0
 
+    def _weights(self):
+        """(weight fp32 [2g, C] contiguous, bias fp32 [2g]) - packed once, see Masker_channel_MLP._weights."""
+        pk = getattr(self, "_packed", None)
+        if pk is None:
+            w = self.conv.weight.detach()
+            pk = (w.reshape(w.shape[0], w.shape[1]).float().contiguous(), self.conv.bias.detach().float().contiguous())
+            self._packed = pk
+        return pk
+
+    def _apply(self, fn, *a, **kw):
+        self._packed = None
+        return super()._apply(fn, *a, **kw)
+
+    def _load_from_state_dict(self, *a, **kw):
+        self._packed = None
+        return super()._load_from_state_dict(*a, **kw)
+
     def gate_nhwc(self, x: torch.Tensor, total: Optional[torch.Tensor] = None,
                   want_logits: bool = False):
         """x fp16 [B,H,W,C] -> (mask u8 [B,g,S,S], logits fp32 [B,2g,S,S] | None)."""
@@ -119,8 +136,8 @@ class Masker_spatial(nn.Module):
         s = self.mask_size if self.mask_size < h else h
         mask = torch.empty((b, g, s, s), dtype=torch.uint8, device=x.device)
         logits = torch.empty((b, 2 * g, s, s), dtype=torch.float32, device=x.device) if want_logits else None
-        wt = self.conv.weight.detach().reshape(2 * g, c).contiguous()
-        check(lib().laud_masker_spatial(ptr(x), b, h, w, c, ptr(wt), ptr(self.conv.bias.detach()), g, s,
+        wt, bias = self._weights()
+        check(lib().laud_masker_spatial(ptr(x), b, h, w, c, ptr(wt), ptr(bias), g, s,
                                         ptr(logits), ptr(mask), ptr(total), stream_ptr()), "laud_masker_spatial")
         return mask, logits
 
@@ -186,10 +203,27 @@ class Masker_channel_MLP(nn.Module):
             last.bias[channel_dyn_group + 1:] = -2.0
 
     def _weights(self):
-        if self.layers == 2:
-            l1, l2 = self.conv[0], self.conv[2]
-            return l1.weight.detach(), l1.bias.detach(), l1.weight.shape[0], l2.weight.detach(), l2.bias.detach()
-        return self.conv.weight.detach(), self.conv.bias.detach(), 0, None, None
+        """fp32 contiguous views of the MLP parameters (the kernels read `const float*`): the parameters themselves
+        for an fp32 model, packed copies after `.half()` / `.bfloat16()`.  Cached until the parameters move or are
+        reloaded (`_apply`, load_state_dict) - the engine's `prepare()` refreshes the cache."""
+        pk = getattr(self, "_packed", None)
+        if pk is None:
+            f = lambda t: t.detach().float().contiguous()
+            if self.layers == 2:
+                l1, l2 = self.conv[0], self.conv[2]
+                pk = (f(l1.weight), f(l1.bias), l1.weight.shape[0], f(l2.weight), f(l2.bias))
+            else:
+                pk = (f(self.conv.weight), f(self.conv.bias), 0, None, None)
+            self._packed = pk
+        return pk
+
+    def _apply(self, fn, *a, **kw):
+        self._packed = None
+        return super()._apply(fn, *a, **kw)
+
+    def _load_from_state_dict(self, *a, **kw):
+        self._packed = None
+        return super()._load_from_state_dict(*a, **kw)
 
     def gate_nhwc(self, x: torch.Tensor, total: Optional[torch.Tensor] = None, want_logits: bool = False,
                   out: Optional[_ChannelGate] = None, partial_ws: Optional[torch.Tensor] = None) -> _ChannelGate:
@@ -249,22 +283,45 @@ class Masker_channel_conv_linear(nn.Module):
             self.linear.bias[channel_dyn_group + 1:] = -2.0
         self.masker_flops = in_channels * in_channels // reduction + in_channels // reduction * channel_dyn_group * 2
 
+    def _weights(self):
+        """Packed once (fp16 K-major 1x1 conv weight, folded BN scale / shift, fp32 linear weight / bias): the gate is
+        then allocation-free apart from its workspaces and safe to capture in a CUDA graph."""
+        pk = getattr(self, "_packed", None)
+        if pk is None:
+            from ._engine import fold_bn, pack_conv_weight     # local import: engine depends on this module
+            scale, shift = fold_bn(self.conv[1])
+            pk = (pack_conv_weight(self.conv[0].weight), scale, shift,
+                  self.linear.weight.detach().float().contiguous(), self.linear.bias.detach().float().contiguous())
+            self._packed = pk
+        return pk
+
+    def _apply(self, fn, *a, **kw):
+        self._packed = None
+        return super()._apply(fn, *a, **kw)
+
+    def _load_from_state_dict(self, *a, **kw):
+        self._packed = None
+        return super()._load_from_state_dict(*a, **kw)
+
     def gate_nhwc(self, x: torch.Tensor, total: Optional[torch.Tensor] = None, want_logits: bool = False,
-                  out: Optional[_ChannelGate] = None, partial_ws=None, impl: int = _lib.CONV_AUTO) -> _ChannelGate:
-        """1x1 conv + BN + ReLU (the conv kernel) -> deterministic GAP -> Linear -> decision."""
-        from ._engine import fold_bn, pack_conv_weight, run_conv     # local import: engine depends on this module
+                  out: Optional[_ChannelGate] = None, partial_ws=None, impl: int = _lib.CONV_AUTO,
+                  z_ws: Optional[torch.Tensor] = None, pooled_ws: Optional[torch.Tensor] = None) -> _ChannelGate:
+        """1x1 conv + BN + ReLU (the conv kernel) -> deterministic GAP -> Linear -> decision (utils.py:150-169).
+        z_ws / pooled_ws / partial_ws: caller-owned workspaces (fp16 >= B*H*W*C/r, fp32 >= B*C/r, fp32 >=
+        B*GAP_SPLITS*C/r); allocated here when absent."""
+        from ._engine import run_conv
         b, h, w, c = x.shape
         cr = self.conv[0].weight.shape[0]
         if cr % 8:
             raise LaudError(f"Masker_channel_conv_linear: reduced width {cr} must be a multiple of 8")
         G = self.channel_dyn_group
         dev = x.device
-        scale, shift = fold_bn(self.conv[1])
-        z = torch.empty((b, h, w, cr), dtype=torch.float16, device=dev)
-        run_conv(x, pack_conv_weight(self.conv[0].weight), z, b, h, w, c, h, w, cr, 1, 1, 0,
-                 scale=scale, shift=shift, relu=_lib.RELU_ALL, impl=impl)
-        pooled = torch.empty((b, cr), dtype=torch.float32, device=dev)
-        pws = torch.empty((b, _lib.GAP_SPLITS, cr), dtype=torch.float32, device=dev)
+        wc, scale, shift, wl, bl = self._weights()
+        z = (z_ws[:b * h * w * cr] if z_ws is not None else torch.empty(b * h * w * cr, dtype=torch.float16, device=dev)).view(b, h, w, cr)
+        run_conv(x, wc, z, b, h, w, c, h, w, cr, 1, 1, 0, scale=scale, shift=shift, relu=_lib.RELU_ALL, impl=impl,
+                 tag="masker.conv")
+        pooled = (pooled_ws[:b * cr] if pooled_ws is not None else torch.empty(b * cr, dtype=torch.float32, device=dev)).view(b, cr)
+        pws = partial_ws if partial_ws is not None else torch.empty((b, _lib.GAP_SPLITS, cr), dtype=torch.float32, device=dev)
         check(lib().laud_global_avg_pool(ptr(z), b, h * w, cr, cr, ptr(pws), ptr(pooled), stream_ptr()),
               "laud_global_avg_pool")
         if out is None:
@@ -273,8 +330,7 @@ class Masker_channel_conv_linear(nn.Module):
                                torch.empty((b,), dtype=torch.int32, device=dev),
                                torch.empty((b, 2 * G), dtype=torch.float32, device=dev) if want_logits else None,
                                pooled)
-        check(lib().laud_masker_channel_from_pooled(ptr(pooled), b, cr, 1, ptr(self.linear.weight.detach()),
-                                                    ptr(self.linear.bias.detach()), 0, None, None, G,
+        check(lib().laud_masker_channel_from_pooled(ptr(pooled), b, cr, 1, ptr(wl), ptr(bl), 0, None, None, G,
                                                     ptr(out.logits), ptr(out.mask), ptr(out.idx), ptr(out.cnt),
                                                     ptr(total), stream_ptr()), "laud_masker_channel_from_pooled")
         return out

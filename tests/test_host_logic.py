@@ -227,9 +227,22 @@ def test_engine_decides_where_the_gap_is_fused(monkeypatch):
     for var in ("LAUD_CONV_V3", "LAUD_NO_FLAT", "LAUD_NO_DMA"):
         monkeypatch.delenv(var, raising=False)
 
-    def plans(modes, hw=(56, 28, 14, 7)):
+    class _MLP:                     # stands in for Masker_channel_MLP: pools the block input itself
+        def gate_from_partials(self):
+            pass
+
+    class _ConvLinear:              # Masker_channel_conv_linear: pools relu(bn(conv1x1(x))) - needs the activations
+        pass
+
+    class _Blk:
+        def __init__(self, mk):
+            self.masker_channel = mk
+
+    def plans(modes, hw=(56, 28, 14, 7), maskers=None):
+        maskers = maskers or [_MLP()] * len(modes)
         return [BlockPlan(index=i, stage=i, inplanes=64, width=64, outplanes=256, stride=1, H_in=h, H_out=h, mode=m, gran=2, G=32,
-                          g_spatial=1, mask_size=1) for i, (m, h) in enumerate(zip(modes, hw))]
+                          g_spatial=1, mask_size=1, module=_Blk(mk if m in ("channel", "both") else None))
+                for i, (m, h, mk) in enumerate(zip(modes, hw, maskers))]
 
     eng = ResNetEngine.__new__(ResNetEngine)
     eng.fuse_gap, eng.channel_exec, eng.impl = True, "dense", _lib.CONV_AUTO
@@ -239,6 +252,10 @@ def test_engine_decides_where_the_gap_is_fused(monkeypatch):
     assert [eng._gap_fusable(p) for p in eng.plans] == [False, False, False, False]      # next has no channel gate / own spatial gate
     eng.plans = plans(["channel"] * 4, hw=(56, 28, 14, 6))
     assert [eng._gap_fusable(p) for p in eng.plans] == [True, True, True, False]         # 36 pixels: a tile could span > 4 samples
+    # the Bottleneck default masker (reference laud_resnet.py:36) cannot decide from the pool of x: ADVICE r1 (high)
+    eng.plans = plans(["channel"] * 4, maskers=[_MLP(), _ConvLinear(), _MLP(), _ConvLinear()])
+    assert [eng._gap_fusable(p) for p in eng.plans] == [False, True, False, True]
+    assert [p.masker_kind for p in eng.plans] == ["MLP", "conv_linear", "MLP", "conv_linear"]
     eng.plans = plans(["channel"] * 4)
     eng.channel_exec = "sparse"
     assert not any(eng._gap_fusable(p) for p in eng.plans)                               # gathered conv3 is not a flat GEMM
