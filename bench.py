@@ -1,25 +1,27 @@
 #!/usr/bin/env python
-"""Benchmark of the LAUD hot path: images/sec of LAUD-ResNet101 channel-2222
-target-0.5 at batch 256 per GPU (BASELINE.json metric, configs[1]).
+"""Benchmark of the LAUD hot path (BASELINE.json metric): images/sec of LAUD-ResNet101 channel-2222 target-0.5 at
+batch 256 per GPU (configs[1]) - or, with --config, one of the other BASELINE configurations.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl graft|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl graft|reference] [--config 0|1|2|4]
 
-One JSON line on stdout (rank 0).  A "step" is one forward pass of the hot path
-over one synthetic batch of 256 images per GPU:
-  * value : whole-job images/s, inputs already resident in HBM, CUDA-graphed forward
-            (+ the logits all-gather when N > 1), device-timed with CUDA events;
-  * e2e   : the same through the public module API from PINNED HOST memory:
-            H2D copy of the batch and D2H read of the logits inside the timed region;
-  * roofline : the mask-conditioned conv kernel (all launches of one step), algorithmic
-            bytes / summed per-launch CUDA-event time, against MEASURED_PEAKS.json;
+One JSON line on stdout (rank 0).  A "step" is one forward pass of the hot path over one synthetic batch:
+  * value : whole-job images/s, inputs already resident in HBM, CUDA-graphed forward (two parallel chains at batch
+            >= 128; + the logits all-gather, captured in the same graph, when N > 1), device-timed with CUDA events;
+  * e2e   : the same through the public module API from PINNED HOST memory: H2D copy of the batch and D2H read of
+            this rank's logits inside the timed region;
+  * parity: the graphed logits and every gating decision of the CPU-sample images against the CPU oracle;
+  * roofline : the mask-conditioned conv kernel (all launches of one step) timed INSIDE a graph execution (event-record
+            nodes around every conv kernel of a single-chain graph): algorithmic bytes / summed kernel time against
+            MEASURED_PEAKS.json, and per layer class (conv1 / conv2 / conv3 / downsample per stage) achieved GB/s,
+            executed and credited (sparsity-adjusted) TFLOP/s;
+  * gpu_baseline : stock PyTorch/cuDNN running the reference's masked-dense scheme (fp16, channels_last, CUDA graph);
   * cpu_baseline : the CPU oracle (a port of the reference's PyTorch path) on a bounded sample.
-`--impl reference` times that CPU oracle alone (the reference is pure Python and cannot travel
-to the GPU box; oracle/laud_oracle.py is its restatement, pinned to it by tests/golden/).
+`--impl reference` times that CPU oracle alone (the reference is pure Python and does not exist on the GPU box;
+oracle/laud_oracle.py is its restatement, pinned to the reference's own outputs by tests/golden/).
 """
 from __future__ import annotations
 
 import argparse
-import ctypes
 import json
 import os
 import statistics
@@ -35,11 +37,25 @@ if ROOT not in sys.path:
 import torch
 import torch.distributed as dist
 
-METRIC = "images/sec LAUD-ResNet101 ch-2222 t0.5 bs256"
 UNIT = "images/s"
-BATCH = 256
 SEED = 1
 CALIB_IMAGES = 32
+
+# BASELINE.json configs (index = position in `configs`); configs[3] (AdaViT) has no reference code in the tree.
+CONFIGS = {
+    0: dict(metric="images/sec LAUD-ResNet50 spatial t0.5 bs8", arch="resnet50", kw="SPATIAL", batch=8,
+            rates=dict(spatial_rate=0.4),
+            workload="LAUD-ResNet50 spatial-skip 4-4-2-1 target-0.5, batch 8 x 3x224x224 (configs[0])"),
+    1: dict(metric="images/sec LAUD-ResNet101 ch-2222 t0.5 bs256", arch="resnet101", kw="HEADLINE", batch=256,
+            rates=dict(channel_rate=0.6),
+            workload="LAUD-ResNet101 channel-2222 target-0.5, batch 256 x 3x224x224 per GPU (configs[1])"),
+    2: dict(metric="images/sec LAUD-ResNet101 layer-skip t0.5 bs256", arch="resnet101", kw="LAYER", batch=256,
+            rates=dict(layer_rate=0.47),
+            workload="LAUD-ResNet101 layer-skip target-0.5, batch 256 x 3x224x224 per GPU (configs[2])"),
+    4: dict(metric="images/sec LAUD-RegNetY-800MF spatial t0.3 bs2048/8", arch="regnety800", kw="SPATIAL", batch=256,
+            rates=dict(spatial_rate=0.22),
+            workload="LAUD-RegNetY-800MF spatial-skip 4-4-2-1 target-0.3, batch 256 x 3x224x224 per GPU = 2048 over 8 GPUs (configs[4])"),
+}
 
 
 def _peaks():
@@ -102,75 +118,123 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def build_model(device):
+# ----------------------------------------------------------------------------- workload
+def build_model(conf, device):
+    """Drop-in model of this configuration with seeded synthetic weights; BatchNorm statistics and gate biases are
+    calibrated on a seeded batch on `device` (weight synthesis - stands in for training)."""
     import laudnet_b200 as L
     from laudnet_b200 import synth
-    model = L.uni_resnet101(**synth.HEADLINE_KWARGS)
-    calib = synth.synth_images(CALIB_IMAGES, 224, SEED + 100).to(device)
-    sd = synth.synth_calibrated_state_dict(model, SEED, calib, channel_rate=0.6)
+    kw = dict({"HEADLINE": synth.HEADLINE_KWARGS, "SPATIAL": synth.SPATIAL_KWARGS, "LAYER": synth.LAYER_KWARGS}[conf["kw"]])
+    if conf["arch"] == "regnety800":
+        kw.pop("lr_mult", None)
+        model = L.lad_regnet_y_800mf(**kw)
+    else:
+        model = (L.uni_resnet50 if conf["arch"] == "resnet50" else L.uni_resnet101)(**kw)
+    calib = synth.synth_images(CALIB_IMAGES if device.type == "cuda" else 8, 224, SEED + 100).to(device)
+    sd = synth.synth_calibrated_state_dict(model, SEED, calib, **conf["rates"])
     model.load_state_dict(sd)
-    return model, sd
+    return model, sd, kw
 
 
-# ----------------------------------------------------------------------------- CPU oracle arm
-def cpu_oracle_rate(sd, n_images: int, repeats: int):
-    """img/s of the CPU restatement of the reference forward (masked-dense fp32 torch)."""
-    from laudnet_b200 import synth
+def oracle_cfg(conf, kw):
     from oracle import laud_oracle as O
+    t = {k: tuple(v) if isinstance(v, list) else v for k, v in kw.items() if k != "lr_mult"}
+    if conf["arch"] == "regnety800":
+        return O.RegNetCfg(**t), O.regnet_forward
+    layers = (3, 4, 6, 3) if conf["arch"] == "resnet50" else (3, 4, 23, 3)
+    return O.ResNetCfg(layers=layers, **t), O.resnet_forward
+
+
+def cpu_oracle(conf, kw, sd, n_images: int, repeats: int):
+    """The CPU restatement of the reference forward (masked-dense fp32 torch) on the first `n_images` images:
+    -> (img/s, cores, outputs of the last forward, per-block traces)."""
+    from laudnet_b200 import synth
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = O.ResNetCfg()                                           # ResNet-101 channel-2222 defaults
+    cfg, fwd = oracle_cfg(conf, kw)
     sd_cpu = {k: v.cpu() for k, v in sd.items()}
     x = synth.synth_images(n_images, 224, SEED)
     with torch.no_grad():
-        O.resnet_forward(sd_cpu, cfg, x)   # warm-up at the timed shape (oneDNN primitives are created per shape)
+        fwd(sd_cpu, cfg, x)        # warm-up at the timed shape (oneDNN primitives are created per shape)
         times = []
         for _ in range(repeats):
+            traces = []
             t0 = time.perf_counter()
-            out = O.resnet_forward(sd_cpu, cfg, x)
+            out = fwd(sd_cpu, cfg, x, traces)
             times.append(time.perf_counter() - t0)
-    flops_ratio = float(out[6]) / float(O.dense_flops(cfg))
-    return n_images / statistics.median(times), cores, flops_ratio
+    return n_images / statistics.median(times), cores, out, traces
 
 
-def run_reference(args):
+def run_reference(args, conf):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import laudnet_b200 as L
+    model, sd, kw = build_model(conf, torch.device("cpu"))
     from laudnet_b200 import synth
-    model = L.uni_resnet101(**synth.HEADLINE_KWARGS)
-    calib = synth.synth_images(8, 224, SEED + 100)
-    sd = synth.synth_calibrated_state_dict(model, SEED, calib, channel_rate=0.6)
-    from oracle import laud_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = O.ResNetCfg()
-    n = args.cpu_sample
+    cfg, fwd = oracle_cfg(conf, kw)
+    n = min(args.cpu_sample, conf["batch"])
     x = synth.synth_images(n, 224, SEED)
     with torch.no_grad():
         for _ in range(args.warmup):
-            O.resnet_forward(sd, cfg, x)
+            fwd(sd, cfg, x)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            O.resnet_forward(sd, cfg, x)
+            fwd(sd, cfg, x)
         dt = time.perf_counter() - t0
     v = n * args.steps / dt
-    sample = f"{n} of the 256 images per step (fp32, torch {torch.__version__} CPU, {cores} threads)"
+    sample = f"{n} of the {conf['batch']} images per step (fp32, torch {torch.__version__} CPU, {cores} threads)"
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": conf["metric"], "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "LAUD-ResNet101 channel-2222 target-0.5, 3x224x224 synthetic, CPU oracle port of the "
-                               "reference PyTorch masked-dense path", "batch_per_step": n},
+        "config": {"workload": conf["workload"] + ", CPU oracle port of the reference PyTorch masked-dense path",
+                   "batch_per_step": n},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
+# ----------------------------------------------------------------------------- parity of the benched path
+def parity_report(model, graphed_logits, x_dev, oracle_out, traces, n):
+    """Graphed logits of the first n images and every gating decision of an eager forward over them vs the oracle."""
+    MARGIN_TOL = 1e-4
+    keep = []
+    with torch.no_grad():
+        model(x_dev[:n], 1.0, keep=keep)
+        torch.cuda.synchronize()
+    total = noise = clear = 0
+    for ko, tr in zip(keep, traces):
+        for got_t, want_t, logit_t in ((ko.channel_mask, tr.channel_mask, tr.channel_logits),
+                                       (ko.spatial_mask_small, tr.spatial_mask_small, tr.spatial_logits)):
+            if got_t is None:
+                continue
+            G = logit_t.shape[1] // 2
+            got = got_t.cpu().reshape(-1) != 0
+            want = want_t.reshape(-1) != 0
+            margin = (logit_t[:, :G] - logit_t[:, G:]).abs().reshape(-1)
+            is_clear = margin > MARGIN_TOL * float(logit_t.abs().max())
+            diff = got != want
+            total += diff.numel()
+            noise += int((diff & ~is_clear).sum())
+            clear += int((diff & is_clear).sum())
+    ref = oracle_out[0].double()
+    ours = graphed_logits[:n].double().cpu()
+    err = ((ours - ref).abs().max() / ref.abs().max().clamp_min(1e-12)).item()
+    return {"images": n, "max_rel_err": err, "logits_tolerance": 5e-3, "n_gates": total, "gate_flips": noise + clear,
+            "gate_flips_clear_margin": clear, "gate_flips_within_noise": noise,
+            "top1_agree": float((ours.argmax(1) == ref.argmax(1)).float().mean()),
+            "within_tolerance": bool(err <= 5e-3), "ok": bool(clear == 0),
+            "how": "graphed forward (the timed path) logits rows [0:n] vs the fp32 CPU oracle; gates of an eager forward over the "
+                   "same images vs the oracle's, bit-exact wherever the oracle's logit margin exceeds 1e-4 of its scale"}
+
+
 # ----------------------------------------------------------------------------- GPU arm
-def run_graft(args):
-    from laudnet_b200 import _engine, _lib, dist as ldist, roofline, synth
+def run_graft(args, conf):
+    from laudnet_b200 import _engine, _lib, roofline
+    from laudnet_b200 import synth
+    from laudnet_b200.build import source_hash
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -182,13 +246,15 @@ def run_graft(args):
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     _lib.lib()                                               # fail loudly when the extension is missing
-    B = args.batch
-    model, sd = build_model(dev)
+    B = args.batch or conf["batch"]
+    is_resnet = conf["arch"] != "regnety800"
+    model, sd, kw = build_model(conf, dev)
     model = model.to(dev).eval()
     lo = rank * B                                            # weak scaling: every rank owns B images
     x_host = synth.synth_images(B, 224, SEED, start=lo).to(torch.float16).pin_memory()
     x_dev = x_host.to(dev)
-    gathered = torch.empty((world * B, 1000), dtype=torch.float32, device=dev) if world > 1 else None
+    ncls = 1000
+    gathered = torch.empty((world * B, ncls), dtype=torch.float16, device=dev) if world > 1 else None
 
     with torch.no_grad():
         # one eager forward: statistics (measured densities) + launch census
@@ -199,15 +265,35 @@ def run_graft(args):
         rho_c = torch.cat(out[4]).tolist()
         r3, r2, r1 = (torch.cat(out[i]).tolist() for i in (1, 2, 3))
         flops_ref_counter = float(out[6])
-        plans = model._engine.plans
-        work = roofline.network_work(plans, rho_c, r3, r2, r1, 224, 64, 1000, B)
+        eng = model._engine
+        work = roofline.network_work(eng.plans, rho_c, r3, r2, r1, 224, 64, ncls, B) if is_resnet else None
 
-        graphed = model.capture(x_dev)
+        # ---- the timed graph: forward (+ fp16 logits all-gather over NVLink inside the same graph when sharded)
+        gather_in_graph = False
+        post = None
+        if world > 1:
+            warm = torch.zeros((B, ncls), dtype=torch.float16, device=dev)
+            dist.all_gather_into_tensor(gathered, warm)       # communicator set-up outside any capture
+            torch.cuda.synchronize()
+            if not os.environ.get("LAUD_EAGER_ALLGATHER"):
+                def post(logits):
+                    lh = logits.to(torch.float16)
+                    dist.all_gather_into_tensor(gathered, lh)
+                    return lh
+        try:
+            graphed = _engine.GraphedForward(eng, x_dev, post=post)
+            gather_in_graph = post is not None
+        except Exception as e:                                # NCCL refused the capture: gather after the replay
+            if post is None:
+                raise
+            sys.stderr.write(f"[bench] all-gather capture failed ({type(e).__name__}: {e}); gathering eagerly\n")
+            torch.cuda.synchronize()
+            graphed = _engine.GraphedForward(eng, x_dev)
 
         def step_resident():
             logits, _ = graphed.replay()
-            if world > 1:
-                dist.all_gather_into_tensor(gathered, logits)
+            if world > 1 and not gather_in_graph:
+                dist.all_gather_into_tensor(gathered, logits.to(torch.float16))
             return logits
 
         def timed(fn, steps, warmup):
@@ -236,10 +322,11 @@ def run_graft(args):
         ms_total = timed(step_resident, args.steps, args.warmup)
         ms_step = ms_total / args.steps
         value = world * B * args.steps / (ms_total * 1e-3)
+        graphed_logits = graphed.logits.float().clone()
 
-        # ---- end to end from pinned host memory, double-buffered H2D on a copy stream
+        # ---- end to end from pinned host memory, double-buffered H2D on a copy stream; D2H of this rank's logits
         copy_stream = torch.cuda.Stream()
-        logits_host = torch.empty((B if world == 1 else world * B, 1000), dtype=torch.float32).pin_memory()
+        logits_host = torch.empty((B, ncls), dtype=torch.float32).pin_memory()
         stage = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
         ready = [torch.cuda.Event(), torch.cuda.Event()]
         consumed = [torch.cuda.Event(), torch.cuda.Event()]
@@ -261,11 +348,9 @@ def run_graft(args):
             graphed.static_x.copy_(stage[i % 2], non_blocking=True)
             consumed[i % 2].record(cur)
             logits, _ = graphed.replay()
-            src = logits
-            if world > 1:
-                dist.all_gather_into_tensor(gathered, logits)
-                src = gathered
-            logits_host.copy_(src, non_blocking=True)       # D2H of the step's result
+            if world > 1 and not gather_in_graph:
+                dist.all_gather_into_tensor(gathered, logits.to(torch.float16))
+            logits_host.copy_(logits, non_blocking=True)    # D2H of the step's result (this rank's rows)
             state["i"] = i + 1
 
         for ev in consumed:
@@ -278,62 +363,98 @@ def run_graft(args):
         h2d = x_host.numel() * x_host.element_size()
         d2h = logits_host.numel() * logits_host.element_size()
 
-        # ---- per-kernel timing of the conv launches of one step: the library brackets each kernel (only the
-        #      kernel, not the host-side descriptor encoding) with CUDA events on the launching stream
-        conv_ms, by_tag, n_conv = [], {}, 0
-        L = _lib.lib()
-        for _ in range(3):
-            L.laud_conv_profile(1)
-            model.forward_logits(x_dev)
-            torch.cuda.synchronize()
-            tot = ctypes.c_float(0.0)
-            n_conv = L.laud_conv_profile_read(ctypes.byref(tot))
-            conv_ms.append(tot.value)
-            L.laud_conv_profile(0)
-        with _engine.conv_profile() as prof:            # per-layer split (includes host launch gaps: shares only)
-            model.forward_logits(x_dev)
-            torch.cuda.synchronize()
-        by_tag = prof.by_tag()
-        conv_ms_step = statistics.median(conv_ms)
+        # ---- the conv kernels timed INSIDE a graph execution: a single-chain graph whose conv launches are bracketed
+        #      by event-record nodes; kernel_ms_per_step is therefore <= that graph's step time by construction
+        roof = None
+        if rank == 0:
+            pg = _engine.GraphedForward(eng, x_dev, splits=1, profile_convs=True)
+            per_launch, pg_ms = [], []
+            for it in range(2 + 5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                pg.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                if it >= 2:
+                    per_launch.append(pg.conv_times())
+                    pg_ms.append(e0.elapsed_time(e1))
+            tags = pg.conv_tags
+            med = [statistics.median(col) for col in zip(*per_launch)]
+            _lib.lib().laud_conv_profile(0)
+            conv_ms_step = sum(med)
+            pg_step = statistics.median(pg_ms)
+            by_tag = {}
+            for t, ms in zip(tags, med):
+                n_, s_ = by_tag.get(t, (0, 0.0))
+                by_tag[t] = (n_ + 1, s_ + ms)
+            peaks = _peaks()
+            roof = {
+                "kernel": "laud::conv_tma_kernel (mask-conditioned tcgen05 conv, TMA-staged; all %d launches of one step)" % len(tags),
+                "bound": "hbm", "peak": peaks["hbm_gbs"], "unit": "GB/s", "peak_source": peaks["source"],
+                "launches_per_step": len(tags), "avg_launch_us": 1e3 * conv_ms_step / max(len(tags), 1),
+                "kernel_ms_per_step": conv_ms_step, "graph_ms_per_step_single_chain": pg_step,
+                "share_of_step": conv_ms_step / pg_step,
+                "timing": "event-record nodes around every conv kernel inside a single-chain CUDA graph, median of 5 replays; "
+                          "`value` times the production graph (chains: %d)" % graphed.splits,
+            }
+            if work is not None:
+                conv_bytes = work.conv_bytes_per_image * B
+                conv_flops = work.conv_flops_per_image * B
+                ach = conv_bytes / (conv_ms_step * 1e-3) / 1e9
+                roof.update({"achieved": ach, "frac": ach / peaks["hbm_gbs"], "algorithmic_bytes_per_step": conv_bytes,
+                             "tensor": {"achieved": conv_flops / (conv_ms_step * 1e-3) / 1e12, "peak": peaks["tflops"],
+                                        "unit": "TFLOP/s", "frac": conv_flops / (conv_ms_step * 1e-3) / 1e12 / peaks["tflops"],
+                                        "note": "sparsity-adjusted algorithmic FLOPs (2 x reference counter, conv terms) - the CREDITED rate"}})
+                classes = {}
+                # MACs the kernels really execute: all of them when a gate is executed masked-dense, the gated share when it
+                # is executed as a skip (layer skip over sample lists, gathered channel execution)
+                skipping = ((conf["kw"] == "LAYER" and eng.layer_exec == "skip") or
+                            (conf["kw"] == "HEADLINE" and eng.channel_exec != "dense") or
+                            (conf["kw"] == "SPATIAL" and getattr(eng, "spatial_exec", "mask") != "mask"))
+                roof["executes"] = "gated work skipped" if skipping else "masked-dense (every MAC executed, gates applied in the epilogue)"
+                for t, (n_, ms) in sorted(by_tag.items()):
+                    w = work.by_class.get(t)
+                    if w is None:
+                        classes[t] = {"launches": n_, "ms": round(ms, 4)}
+                        continue
+                    sec = ms * 1e-3
+                    gbs = w["bytes"] * B / sec / 1e9
+                    classes[t] = {"launches": n_, "ms": round(ms, 4), "achieved_gbs": round(gbs, 1),
+                                  "hbm_frac": round(gbs / peaks["hbm_gbs"], 4),
+                                  "executed_tflops": round(2 * (w["macs"] if skipping else w["macs_dense"]) * B / sec / 1e12, 1),
+                                  "credited_tflops": round(2 * w["macs"] * B / sec / 1e12, 1)}
+                roof["by_layer_class"] = classes
+            else:
+                roof.update({"achieved": None, "frac": None,
+                             "by_layer_ms": {t: round(ms, 4) for t, (n_, ms) in sorted(by_tag.items())}})
+            # DRAM traffic of the same launches: from the committed ncu capture of THIS build (hash-checked), else null
+            traffic, traffic_src = None, "no ncu capture of this build (profiles/conv_traffic.json absent or of another build)"
+            tpath = os.path.join(ROOT, "profiles", "conv_traffic.json")
+            if os.path.exists(tpath) and args.config == 1:
+                tj = json.load(open(tpath))
+                if tj.get("build_source_hash") == source_hash():
+                    traffic = tj["dram_bytes_per_launch_avg"]
+                    traffic_src = ("profiles/conv_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, average per conv "
+                                   "launch; capture of build %s)" % tj["build_source_hash"])
+            roof["traffic"], roof["traffic_source"] = traffic, traffic_src
 
-    peaks = _peaks()
-    traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01E_conv_traffic.json")
-    if os.path.exists(tpath):                  # dram__bytes_read+write of the conv launches from the committed ncu capture
-        tj = json.load(open(tpath))
-        traffic = tj["dram_bytes_per_launch_avg"]
-        traffic_src = "profiles/r01E_conv_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, average per conv launch)"
-    conv_bytes = work.conv_bytes_per_image * B
-    conv_flops = work.conv_flops_per_image * B
-    ach_gbs = conv_bytes / (conv_ms_step * 1e-3) / 1e9
-    roof = {
-        "kernel": "laud::conv_tma_kernel (mask-conditioned tcgen05 conv, TMA-staged; all %d launches of one step)" % n_conv,
-        "bound": "hbm", "achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-        "frac": ach_gbs / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
-        "peak_source": peaks["source"],
-        "launches_per_step": n_conv, "avg_launch_us": 1e3 * conv_ms_step / max(n_conv, 1),
-        "algorithmic_bytes_per_step": conv_bytes, "kernel_ms_per_step": conv_ms_step,
-        "share_of_step": conv_ms_step / ms_step,
-        "share_note": "summed device time of the conv launches (eager, one stream) over the CUDA-graphed step: the graph runs two "
-                      "chains whose kernels overlap, so this exceeds the serialised share of the ncu launch list "
-                      "(profiles/r01E_launch_summary.txt: conv 89 %, masker 5 %, stem 4 %, head 1 %)",
-        "tensor": {"achieved": conv_flops / (conv_ms_step * 1e-3) / 1e12, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                   "frac": conv_flops / (conv_ms_step * 1e-3) / 1e12 / peaks["tflops"],
-                   "note": "sparsity-adjusted algorithmic FLOPs (2 x reference counter, conv terms)"},
-        "by_layer_ms": {k: round(t, 4) for k, (n, t) in sorted(by_tag.items())},
-    }
-    net = {
-        "flops_per_image": work.flops_per_image, "dense_flops_per_image": work.dense_flops_per_image,
-        "flops_ratio": work.flops_per_image / work.dense_flops_per_image,
-        "reference_counter_flops": 2.0 * flops_ref_counter, "bytes_per_image": work.bytes_per_image,
-        "hbm_frac_whole_net": work.bytes_per_image * value / world / 1e9 / peaks["hbm_gbs"],
-        "tensor_frac_whole_net": work.flops_per_image * value / world / 1e12 / peaks["tflops"],
-        "mean_channel_density": sum(rho_c) / len(rho_c),
-    }
+    net = None
+    if work is not None:
+        peaks = _peaks()
+        net = {
+            "flops_per_image": work.flops_per_image, "dense_flops_per_image": work.dense_flops_per_image,
+            "flops_ratio": work.flops_per_image / work.dense_flops_per_image,
+            "reference_counter_flops": 2.0 * flops_ref_counter, "bytes_per_image": work.bytes_per_image,
+            "hbm_frac_whole_net": work.bytes_per_image * value / world / 1e9 / peaks["hbm_gbs"],
+            "tensor_frac_whole_net": work.flops_per_image * value / world / 1e12 / peaks["tflops"],
+            "mean_channel_density": sum(rho_c) / len(rho_c), "mean_conv3_density": sum(r3) / len(r3),
+        }
+    else:
+        net = {"reference_counter_flops": 2.0 * flops_ref_counter, "mean_conv3_density": sum(r3) / len(r3)}
 
     dynet = None
     dpath = os.path.join(ROOT, "profiles", "dynet_prediction_b200.json")
-    if os.path.exists(dpath):        # the reference's own analytic latency model, evaluated in the build container
+    if os.path.exists(dpath) and args.config == 1:        # the reference's own analytic latency model, evaluated in the build container
         dj = json.load(open(dpath))
         key = "channel_2222_density_0.587_measured_mean"
         dynet = {"predicted_images_per_s_per_gpu": dj[key]["images_per_s"],
@@ -341,33 +462,57 @@ def run_graft(args):
                  "measured_images_per_s_per_gpu": value / world, "hardware_parameters": dj["hardware_parameters"],
                  "scope": dj["network"], "caveat": dj["caveat"], "source": "profiles/dynet_prediction_b200.json "
                  "(scripts/make_dynet_prediction.py: DyNetSimulator imported unchanged from the reference)"}
-    cpu = None
+        if "per_block" in dj:
+            dynet["per_block_source"] = "profiles/dynet_per_block_b200.json"
+
+    cpu = parity = gpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        v, cores, ratio = cpu_oracle_rate(sd, args.cpu_sample, 2)
+        n = min(args.cpu_sample, B)
+        v, cores, o_out, traces = cpu_oracle(conf, kw, sd, n, 2)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_sample} of the 256 images, 2 timed forwards after a warm-up (fp32 torch CPU oracle, "
-                         f"{cores} threads; flops ratio {ratio:.3f})"}
+               "sample": f"{n} of the {B} images, 2 timed forwards after a warm-up (fp32 torch CPU oracle, {cores} threads)"}
+        parity = parity_report(model, graphed_logits, x_dev, o_out, traces, n)
+    if rank == 0 and world == 1 and is_resnet and not args.no_gpu_baseline:
+        try:
+            from laudnet_b200.torch_baseline import TorchMaskedDenseResNet
+            tb = TorchMaskedDenseResNet(model, dev)
+            rate, ms_b, lg = tb.measure(x_dev, steps=10, warmup=3)
+            agree = float((lg.argmax(1) == graphed_logits.argmax(1)).float().mean())
+            gpu_base = {"value": rate, "unit": UNIT, "ms_per_step": ms_b, "kind": "stock PyTorch/cuDNN masked-dense (the reference's "
+                        "execution scheme): fp16 weights + activations, channels_last, cudnn.benchmark, CUDA graph, batch %d" % B,
+                        "torch": torch.__version__, "top1_agree_with_ours": agree}
+            del tb
+        except Exception as e:
+            gpu_base = {"unavailable": f"{type(e).__name__}: {e}"}
+
     if rank == 0:
         sys.stdout.flush()
         os.write(out_fd, (json.dumps({
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": conf["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": {"workload": "LAUD-ResNet101 channel-2222 target-0.5, batch 256 x 3x224x224 per GPU (configs[1])",
-                       "batch_per_gpu": B, "global_batch": world * B, "parallelism": f"batch-sharded x{world}, "
-                       "replicated weights, one NCCL all-gather of logits per step" if world > 1 else "single GPU",
-                       "l2": "inputs + activations per step (>2 GB) exceed the 126 MB L2; no explicit flush",
-                       "weights": "seeded synthetic, BN stats + gate biases calibrated to channel density 0.6",
-                       "cuda_graph": True, "channel_exec": model._engine.channel_exec,
+            "config": {"workload": conf["workload"], "baseline_config_index": args.config,
+                       "batch_per_gpu": B, "global_batch": world * B,
+                       "parallelism": (f"batch-sharded x{world}, replicated weights, one NCCL all-gather of fp16 logits per step "
+                                       f"({'captured in the CUDA graph' if gather_in_graph else 'after the graph replay'})")
+                       if world > 1 else "single GPU",
+                       "l2": "inputs + activations per step exceed the 126 MB L2; no explicit flush",
+                       "weights": "seeded synthetic, BN stats + gate biases calibrated (%s)" % ", ".join(f"{k}={v}" for k, v in conf["rates"].items()),
+                       "cuda_graph": True, "channel_exec": getattr(eng, "channel_exec", None),
+                       "layer_exec": getattr(eng, "layer_exec", None), "spatial_exec": getattr(eng, "spatial_exec", None),
                        "graph_chains": graphed.splits},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": graphed.launches * args.steps, "launches_per_step": graphed.launches,
             "eager_launches_per_step": launches_per_step, "conv_paths": _lib.conv_path_counts(),
-            "clocks": clocks, "roofline": roof, "net": net, "dynet_simulator": dynet, "cpu_baseline": cpu,
+            "clocks": clocks, "parity": parity, "roofline": roof, "net": net, "gpu_baseline": gpu_base,
+            "dynet_simulator": dynet, "cpu_baseline": cpu,
         }) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        sys.stderr.write("[bench] PARITY FAILURE: %s\n" % json.dumps(parity))
+        sys.exit(3)
 
 
 def main():
@@ -376,15 +521,19 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH, help="images per GPU per step (metric is quoted at 256)")
+    ap.add_argument("--config", type=int, default=1, choices=sorted(CONFIGS),
+                    help="index into BASELINE.json configs (default 1: the configuration the metric is quoted on)")
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: the configuration's)")
     ap.add_argument("--cpu-sample", type=int, default=16)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "graft" else args.warmup
+    conf = CONFIGS[args.config]
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, conf)
     else:
-        run_graft(args)
+        run_graft(args, conf)
 
 
 if __name__ == "__main__":

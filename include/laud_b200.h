@@ -62,9 +62,13 @@ void laud_conv_path_counts(unsigned long long out[3]);
 unsigned long long laud_conv_tma_launch_count(void);
 /* Measurement aid: while enabled, every tcgen05 conv launch is bracketed - the kernel only, not the host-side
  * descriptor encoding - by CUDA events on its stream.  laud_conv_profile_read (after a synchronize) returns the
- * number of recorded launches and their summed device time.  Not for use during CUDA-graph capture. */
-void laud_conv_profile(int enable);
+ * number of recorded launches and their summed device time. */
+void laud_conv_profile(int enable);   /* 1 start (drops old records), 2 stop but keep the records, 0 stop and drop */
 int laud_conv_profile_read(float* total_ms);
+/* per-launch device times in launch order.  When the launches were CAPTURED into a CUDA graph while profiling was on,
+ * the event records are nodes of that graph: call this after a replay (and a synchronize) to read the times of the
+ * kernels inside that graph execution. */
+int laud_conv_profile_read_all(float* ms_out, int cap);
 
 /* ---------------------------------------------------------------------------
  * (a1) channel masker.  Replaces Masker_channel_MLP.forward, eval branch

@@ -79,6 +79,9 @@ class conv_profile:
         return out
 
 
+conv_tags: Optional[list] = None      # when a list: every run_conv appends its tag (launch order of laud_conv_profile records)
+
+
 def run_conv(x, w, y, B, H_in, W_in, C_in, H_out, W_out, C_out, ksize, stride, pad, *,
              ldx=None, ldy=None, scale=None, shift=None, relu=_lib.RELU_NONE, residual=None, ldr=0,
              k_idx=None, k_cnt=None, k_gran=1, n_idx=None, n_cnt=None, n_gran=1,
@@ -110,6 +113,8 @@ def run_conv(x, w, y, B, H_in, W_in, C_in, H_out, W_out, C_out, ksize, stride, p
     d.w_t = ptr(w_t)
     d.bias_t, d.bias_ld = ptr(bias_t), bias_ld
     d.n_mask, d.n_mask_gran = ptr(n_mask), n_mask_gran
+    if conv_tags is not None:
+        conv_tags.append(tag)
     prof = conv_profile.active
     if prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -681,7 +686,12 @@ class GraphedForward:
     device, or host to device when x is pinned host memory), replays the graph
     and returns the static logits / stats tensors (overwritten by the next run)."""
 
-    def __init__(self, engine: ResNetEngine, x_example: torch.Tensor, splits: Optional[int] = None):
+    def __init__(self, engine: ResNetEngine, x_example: torch.Tensor, splits: Optional[int] = None, post=None,
+                 profile_convs: bool = False):
+        """post: optional callable(logits) captured at the end of the graph (e.g. the logits all-gather of a sharded
+        batch); its return value is kept as `self.post_out`.  profile_convs: capture the graph with every convolution
+        kernel bracketed by event-record nodes (laud_conv_profile): `conv_times()` after a replay returns the device
+        time of each conv launch INSIDE that graph execution, `conv_tags` their layer tags."""
         if x_example.device.type != "cuda":
             raise LaudError("capture(): expected a CUDA example input")
         if splits is None:       # measured on B200 at batch 256: 2 chains +2.5 %, 3 chains +0.5 %, 4 chains -2 %
@@ -706,8 +716,21 @@ class GraphedForward:
         torch.cuda.synchronize()
         n0 = _lib.launch_count()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.logits, self.stats = fwd(self.static_x)
+        self.conv_tags = None
+        self.post_out = None
+        global conv_tags
+        if profile_convs:
+            lib().laud_conv_profile(1)
+            conv_tags = []
+        try:
+            with torch.cuda.graph(self.graph):
+                self.logits, self.stats = fwd(self.static_x)
+                if post is not None:
+                    self.post_out = post(self.logits)
+        finally:
+            if profile_convs:
+                lib().laud_conv_profile(2)           # stop collecting, keep the (graph-owned) records
+                self.conv_tags, conv_tags = conv_tags, None
         self.launches = _lib.launch_count() - n0     # kernels of ours inside one replay
         # the graph replays raw device pointers: keep the prepared tensors and workspaces alive with it, and let the
         # engine mark it stale when prepare() replaces them (load_state_dict, .to(), in-place edits + prepare())
@@ -727,3 +750,14 @@ class GraphedForward:
     def run(self, x: torch.Tensor):
         self.static_x.copy_(x, non_blocking=True)
         return self.replay()
+
+    def conv_times(self):
+        """After a replay and a synchronize of a `profile_convs` graph: ms of every conv launch, in `conv_tags` order."""
+        if self.conv_tags is None:
+            raise LaudError("GraphedForward.conv_times(): capture with profile_convs=True")
+        n = len(self.conv_tags)
+        buf = (C.c_float * n)()
+        got = lib().laud_conv_profile_read_all(buf, n)
+        if got != n:
+            raise LaudError(f"conv profile holds {got} records, the graph has {n} conv launches (another profile was started)")
+        return list(buf)

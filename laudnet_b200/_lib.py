@@ -58,6 +58,7 @@ SIGNATURES = {
     "laud_conv_tma_launch_count": ([], C.c_ulonglong),
     "laud_conv_profile": ([_i], None),
     "laud_conv_profile_read": ([C.POINTER(C.c_float)], _i),
+    "laud_conv_profile_read_all": ([C.POINTER(C.c_float), _i], _i),
     "laud_masker_channel_mlp": ([_vp, _i, _i, _i, _i, _fp, _fp, _i, _fp, _fp, _i, _fp, _fp, _fp, _u8p, _i32p, _i32p, _i32p, _vp], _i),
     "laud_masker_channel_from_pooled": ([_fp, _i, _i, _i, _fp, _fp, _i, _fp, _fp, _i, _fp, _u8p, _i32p, _i32p, _i32p, _vp], _i),
     "laud_masker_channel_from_partials": ([_fp, _i, _i, _i, _i, _i, _fp, _fp, _i, _fp, _fp, _i, _fp, _fp, _u8p, _i32p, _i32p, _i32p, _vp], _i),

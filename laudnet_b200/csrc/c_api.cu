@@ -24,17 +24,26 @@ void set_error(const char* fmt, ...) {
 static bool g_prof_on = false;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
 
+// Inside a stream capture the records become EVENT-RECORD NODES of the graph (cudaEventRecordExternal): every replay
+// re-records the same events, so the kernels are timed inside the very graph execution that is being measured.
+static void prof_record(cudaEvent_t e, cudaStream_t s) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone)
+    cudaEventRecordWithFlags(e, s, cudaEventRecordExternal);
+  else
+    cudaEventRecord(e, s);
+}
 ConvProfScope::ConvProfScope(cudaStream_t stream) : s(stream), e0(nullptr), on(g_prof_on) {
   if (on) {
     cudaEventCreate(&e0);
-    cudaEventRecord(e0, s);
+    prof_record(e0, s);
   }
 }
 ConvProfScope::~ConvProfScope() {
   if (on) {
     cudaEvent_t e1;
     cudaEventCreate(&e1);
-    cudaEventRecord(e1, s);
+    prof_record(e1, s);
     g_prof_events.emplace_back(e0, e1);
   }
 }
@@ -43,14 +52,30 @@ ConvProfScope::~ConvProfScope() {
 
 using namespace laud;
 
-// enable != 0: start collecting (drops earlier records); 0: stop.
+// 1: start collecting (drops earlier records); 2: stop collecting but KEEP the records (a captured graph keeps
+// re-recording them at every replay); 0: stop and drop.
 extern "C" void laud_conv_profile(int enable) {
+  if (enable == 2) {
+    g_prof_on = false;
+    return;
+  }
   for (auto& pr : g_prof_events) {
     cudaEventDestroy(pr.first);
     cudaEventDestroy(pr.second);
   }
   g_prof_events.clear();
   g_prof_on = enable != 0;
+}
+// After a synchronize: device time in ms of every recorded conv launch, in launch order (up to `cap`); returns the
+// number of records.
+extern "C" int laud_conv_profile_read_all(float* ms_out, int cap) {
+  int i = 0;
+  for (auto& pr : g_prof_events) {
+    float ms = 0.f;
+    if (i < cap && ms_out) ms_out[i] = cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess ? ms : -1.f;
+    ++i;
+  }
+  return i;
 }
 // After a synchronize: number of recorded conv launches and their summed device time in ms.
 extern "C" int laud_conv_profile_read(float* total_ms) {

@@ -39,6 +39,7 @@ class NetWork:
     conv_bytes_per_image: float
     weight_bytes: float
     blocks: List[BlockWork]
+    by_class: dict = None     # "s<stage>.<conv1|conv2|conv3|down>" -> {bytes, macs (credited, sparse), macs_dense} per image
 
 
 def network_work(plans: Sequence, rho_c: Sequence[float], rho_3: Sequence[float], rho_2: Sequence[float],
@@ -54,6 +55,14 @@ def network_work(plans: Sequence, rho_c: Sequence[float], rho_3: Sequence[float]
     conv_macs_total = conv_bytes_total = 0.0
     weight_bytes = 2.0 * (3 * stem_c * 49 + feat * n_classes)
     blocks = []
+    by_class = {}
+
+    def add(tag, byts_, macs_, dense_):
+        d = by_class.setdefault(tag, {"bytes": 0.0, "macs": 0.0, "macs_dense": 0.0})
+        d["bytes"] += byts_
+        d["macs"] += macs_
+        d["macs_dense"] += dense_
+
     for i, p in enumerate(plans):
         rc, r3, r2, r1 = rho_c[i], rho_3[i], rho_2[i], rho_1[i]
         hi, ho = p.H_in, p.H_out
@@ -72,10 +81,13 @@ def network_work(plans: Sequence, rho_c: Sequence[float], rho_3: Sequence[float]
         if p.use_s:
             S = min(p.mask_size, hi)
             m_macs += p.inplanes * S * S + blk.masker_spatial.conv_flops_pp * S * S
-        conv = c1 * rc * r1 + c2 * rc * rc * r2 + c3 * rc * r3 + ds
+        mac1, mac2, mac3 = c1 * rc * r1, c2 * rc * rc * r2, c3 * rc * r3
+        conv = mac1 + mac2 + mac3 + ds
         conv_dense = c1 + c2 + c3 + ds
         gate = r3 if p.mode == "layer" else 1.0          # per-sample skip: nothing of the block is touched
         ident = 2 * O if p.wd is not None else X
+        if p.mode == "layer":          # all-or-nothing per sample: the per-sample gate rate scales the block once
+            r1 = r2 = 1.0
         conv_b = 2.0 * (X * r1 + 2 * I1 * rc * r1 + 2 * I2 * rc * r2 + O)
         if p.mode == "layer":
             conv_b = conv_b * gate + 2.0 * (ident if p.wd is not None else X * gate)
@@ -83,6 +95,15 @@ def network_work(plans: Sequence, rho_c: Sequence[float], rho_3: Sequence[float]
             conv_b += 2.0 * ident
         masker_b = 2.0 * X
         w_b = 2.0 * (c1 / (hi * hi) + c2 / (ho * ho) + c3 / (ho * ho) + (ds / (ho * ho) if ds else 0))
+        # the same bytes / MACs split by launch (sums to conv_b / conv): conv1 reads X writes a1, conv2 reads a1 writes a2,
+        # conv3 reads a2 + the identity and writes O, the downsample writes O (its read of X is the one already counted)
+        st = f"s{p.stage + 1}."
+        wsh = 2.0 / max(batch, 1)
+        add(st + "conv1", 2.0 * gate * (X * r1 + I1 * rc * r1) + wsh * c1 / (hi * hi), mac1, c1)
+        add(st + "conv2", 2.0 * gate * (I1 * rc * r1 + I2 * rc * r2) + wsh * c2 / (ho * ho), mac2, c2)
+        add(st + "conv3", 2.0 * gate * (I2 * rc * r2 + O + (O if p.wd is not None else X)) + wsh * c3 / (ho * ho), mac3, c3)
+        if p.wd is not None:
+            add(st + "down", 2.0 * O + (2.0 * O * (1.0 - gate) if p.mode == "layer" else 0.0) + wsh * ds / (ho * ho), ds, ds)
         weight_bytes += w_b
         macs += m_macs + conv
         dense += m_macs + conv_dense
@@ -94,4 +115,4 @@ def network_work(plans: Sequence, rho_c: Sequence[float], rho_3: Sequence[float]
     return NetWork(flops_per_image=2.0 * macs, dense_flops_per_image=2.0 * dense, bytes_per_image=byts,
                    conv_flops_per_image=2.0 * conv_macs_total,
                    conv_bytes_per_image=conv_bytes_total + (weight_bytes / max(batch, 1)),
-                   weight_bytes=weight_bytes, blocks=blocks)
+                   weight_bytes=weight_bytes, blocks=blocks, by_class=by_class)

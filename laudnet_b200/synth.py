@@ -344,6 +344,36 @@ def geometry_of(model):
             for s in range(4) for i, blk in enumerate(getattr(model, f"layer{s + 1}"))]
 
 
+class _RegGeom:
+    """ResBottleneckBlock geometry read off a drop-in LAD_RegNet (attribute names of the oracle's RegBlockGeom)."""
+
+    def __init__(self, prefix, blk):
+        f = blk.f
+        self.prefix = prefix
+        self.w_in, self.w_out, self.stride = blk.width_in, blk.width_out, blk.stride
+        self.w_b = f.a[0].weight.shape[0]
+        self.conv_groups = f.b[0].groups
+        self.output_size, self.mask_size, self.dyn_mode = f.output_size, f.mask_size, f.dyn_mode
+        self.groups_channel, self.groups_spatial = f.channel_dyn_group, f.spatial_mask_channel_group
+        mk = f.masker_channel
+        self.masker_kind = "MLP" if (mk is None or hasattr(mk, "layers")) else "conv_linear"
+        self.masker_layers = getattr(mk, "layers", 2)
+        self.has_proj = blk.proj is not None
+        self.se_width = f.se.fc1.weight.shape[0]
+
+
+def regnet_geometry_of(model):
+    return [_RegGeom(f"trunk_output.{sname}.{bname}.", blk)
+            for sname, stage in model.trunk_output.named_children() for bname, blk in stage.named_children()]
+
+
+SPATIAL_KWARGS = dict(           # spatial 4-4-2-1, one mask group (BASELINE configs[0] / [4])
+    input_size=224, dyn_mode=["spatial"] * 4, mask_spatial_granularity=[4, 4, 2, 1],
+    spatial_mask_channel_group=[1] * 4, channel_dyn_granularity=[1] * 4, channel_masker=["MLP"] * 4,
+    channel_masker_layers=[2] * 4, reduction_ratio=[16] * 4)
+LAYER_KWARGS = dict(SPATIAL_KWARGS, dyn_mode=["layer"] * 4, mask_spatial_granularity=[56, 28, 14, 7])   # train_scripts.sh:22
+
+
 HEADLINE_KWARGS = dict(          # LAUD-ResNet101 channel-2222 (SURVEY appendix B.3)
     input_size=224, dyn_mode=["channel"] * 4, channel_dyn_granularity=[2, 2, 2, 2],
     channel_masker=["MLP"] * 4, channel_masker_layers=[2] * 4, reduction_ratio=[16] * 4,
@@ -356,5 +386,8 @@ def synth_calibrated_state_dict(model, seed: int, calib_images: torch.Tensor, ch
     calibrated on `calib_images` (on that tensor's device, stock torch ops)."""
     shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
     sd = synth_state_dict(shapes, seed)
+    if hasattr(model, "trunk_output"):           # LAUD-RegNet-Y
+        return calibrate_regnet(sd, regnet_geometry_of(model), calib_images, seed, channel_rate=channel_rate,
+                                spatial_rate=spatial_rate)
     return calibrate_resnet(sd, geometry_of(model), calib_images, seed, channel_rate=channel_rate,
                             spatial_rate=spatial_rate, layer_rate=layer_rate)

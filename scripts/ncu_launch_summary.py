@@ -3,7 +3,11 @@ sm__pipe_tensor_cycles_active...) per kernel:  python scripts/ncu_launch_summary
 import collections
 import csv
 import json
+import os
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from laudnet_b200.build import source_hash      # noqa: E402
 
 rows = list(csv.reader(open(sys.argv[1])))
 hdr = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
@@ -41,7 +45,7 @@ if len(sys.argv) > 3:
     n = sum(a[0] for a in conv)
     rd, wr, tm = sum(a[2] for a in conv), sum(a[3] for a in conv), sum(a[1] for a in conv)
     json.dump({"source": sys.argv[1] + " (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum; one eager "
-               "forward, batch 256)", "kernel": "laud::conv_tma_kernel<*>", "launches_per_step": n,
+               "forward, batch 256)", "kernel": "laud::conv_tma_kernel<*>", "build_source_hash": source_hash(), "launches_per_step": n,
                "dram_bytes_read_per_step": rd, "dram_bytes_write_per_step": wr, "dram_bytes_per_launch_avg": (rd + wr) / n,
                "tensor_pipe_active_pct_time_weighted": sum(a[4] for a in conv) / tm, "kernel_time_ms_per_step_ncu": tm / 1e3},
               open(sys.argv[3], "w"), indent=1)

@@ -34,6 +34,52 @@ CASES = {
 }
 
 
+# FULL-SIZE cases (224x224, the BASELINE.json architectures): name -> (kind, cfg, calibration batch, golden batch, seed).
+# The golden images are synth_images(batch, 224, seed); calibration runs on synth_images(calib, 224, seed + 1000).
+# Fixtures hold only what calibration changed in the state_dict plus the reference's outputs
+# (tests/golden/make_golden_fullsize.py): the input and the seeded weights are regenerated from the seed.
+_R50 = (3, 4, 6, 3)
+FULL_CASES = {
+    # BASELINE configs[1]: LAUD-ResNet101 channel-2222, MLP masker (2 layers, reduction 16)
+    "full_r101_channel": ("resnet", O.ResNetCfg(), 8, 2, 31),
+    # BASELINE configs[0]: LAUD-ResNet50 spatial 4-4-2-1
+    "full_r50_spatial": ("resnet", O.ResNetCfg(layers=_R50, dyn_mode=("spatial",) * 4, channel_dyn_granularity=(1,) * 4,
+                                               mask_spatial_granularity=(4, 4, 2, 1)), 8, 2, 32),
+    # BASELINE configs[2]: LAUD-ResNet101 layer skip
+    "full_r101_layer": ("resnet", O.ResNetCfg(dyn_mode=("layer",) * 4, channel_dyn_granularity=(1,) * 4,
+                                              mask_spatial_granularity=(56, 28, 14, 7)), 8, 2, 33),
+    # the reference Bottleneck's DEFAULT channel masker (laud_resnet.py:36): conv_linear, channel mode, ResNet-50
+    "full_r50_convlinear": ("resnet", O.ResNetCfg(layers=_R50, channel_masker=("conv_linear",) * 4), 8, 2, 34),
+    # BASELINE configs[4]: LAUD-RegNetY-800MF spatial 4-4-2-1 (target 0.3)
+    "full_regnety800_spatial": ("regnet", O.RegNetCfg(), 8, 2, 35),
+}
+
+
+def full_case_state_dict(name, z=None):
+    """-> (kind, cfg, state_dict, golden npz) of a full-size case: seeded weights + the calibrated tensors of the fixture."""
+    kind, cfg, calib, batch, seed = FULL_CASES[name]
+    if z is None:
+        z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    if kind == "resnet":
+        shapes = model_shapes(cfg)
+    else:
+        from laudnet_b200.laud_regnet import lad_regnet_y_800mf
+        shapes = {k: tuple(v.shape) for k, v in lad_regnet_y_800mf(**cfg.kwargs()).state_dict().items()}
+    sd = synth.synth_state_dict(shapes, int(z["seed"]))
+    for k in z.files:
+        if k.startswith("sd."):
+            sd[k[3:]] = torch.from_numpy(z[k])
+    assert state_dict_digest(sd) == z["sd_sha256"].tobytes(), f"{name}: regenerated state_dict differs from the fixture's"
+    return kind, cfg, sd, z
+
+
+def load_full_case(name):
+    """-> (kind, cfg, state_dict, x[fp32, fp16-representable], golden npz dict)."""
+    kind, cfg, sd, z = full_case_state_dict(name)
+    _, _, calib, batch, seed = FULL_CASES[name]
+    return kind, cfg, sd, synth.synth_images(batch, cfg.input_size, seed), z
+
+
 # LAUD-RegNet-Y cases: (design-space parameters of BlockParams.from_init_params, cfg overrides, batch, seed).  The stage
 # widths / depths the reference derives from the parameters are stored in the fixture and compared with
 # laudnet_b200.laud_regnet.stage_params by the tests.

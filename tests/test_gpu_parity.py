@@ -627,6 +627,7 @@ def test_network_free_running_vs_golden(cuda_lib, name, channel_exec):
         assert err <= 5e-3, f"{name}: logits error {err:.2e} (33-block fp16 chain, identical masks)"
     frac = excused / max(total, 1)
     print(f"{name}: {total} gating decisions, {excused} within-noise flips, exact_elsewhere={exact}")
+    assert exact, f"{name}: a gating decision with a clear margin differs from the reference's"
     assert frac <= 2e-3, f"{name}: {excused}/{total} decisions flipped (fp16 upstream noise budget exceeded)"
 
 
@@ -755,32 +756,165 @@ def test_headline_r101_channel_full_size_fused_gap_equals_standalone_masker(cuda
         assert (lf - ls).abs().max().item() <= 2e-3 * max(ls.abs().max().item(), 1.0)
 
 
-def test_resnet50_spatial_bs8_full_size(cuda_lib):
-    """BASELINE config 0 (LAUD-ResNet50 spatial-skip, batch 8, 224x224): full-size run through
-    size-independent properties (the CPU oracle at this size is exercised by bench.py's cpu leg)."""
-    kw = dict(input_size=224, dyn_mode=["spatial"] * 4, mask_spatial_granularity=[4, 4, 2, 1],
-              spatial_mask_channel_group=[1] * 4, channel_dyn_granularity=[1] * 4, channel_masker=["MLP"] * 4,
-              channel_masker_layers=[2] * 4, reduction_ratio=[16] * 4)
-    m = L.uni_resnet50(**kw)
-    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
-    sd = synth.synth_state_dict(shapes, 5)
-    m.load_state_dict(sd)
-    m = m.to(DEV).eval()
-    x = synth.synth_images(8, 224, 5).to(DEV)
+# --------------------------------------------------------------------------- BASELINE configurations at FULL size
+from tests.golden_cases import FULL_CASES, load_full_case       # noqa: E402
+from tests.test_oracle_golden import unpack_mask                # noqa: E402
+
+LOGIT_TOL = 5e-3      # normalised max error of the logits after the whole fp16 trunk (33 blocks), identical gates
+
+
+def _full_model(kind, cfg, sd):
+    if kind == "resnet":
+        m = L.ResNet(L.Bottleneck, list(cfg.layers), **cfg.kwargs())
+    else:
+        m = L.lad_regnet_y_800mf(**cfg.kwargs())
+    m.load_state_dict(sd, strict=True)
+    return m.to(DEV).eval()
+
+
+def _oracle(kind, cfg, sd, x, traces=None):
+    with torch.no_grad():
+        return (O.resnet_forward if kind == "resnet" else O.regnet_forward)(sd, cfg, x, traces)
+
+
+def _gate_report(keep, traces, want_masks=None):
+    """Compare every gating decision of a free-running forward with the oracle's (or the reference's golden masks).
+    -> (total decisions, flips whose oracle margin is within noise, flips with a CLEAR margin)."""
+    total = noise = clear_flips = 0
+    for i, (ko, tr) in enumerate(zip(keep, traces)):
+        for got_t, want_t, logit_t in ((ko.channel_mask, tr.channel_mask, tr.channel_logits),
+                                       (ko.spatial_mask_small, tr.spatial_mask_small, tr.spatial_logits)):
+            if got_t is None:
+                continue
+            G = logit_t.shape[1] // 2
+            got = got_t.cpu().numpy().astype(np.uint8)
+            want = want_t.numpy().astype(np.uint8).reshape(got.shape)
+            if want_masks is not None:
+                key = want_masks[1][i] + (".channel_mask" if got_t is ko.channel_mask else ".spatial_mask")
+                np.testing.assert_array_equal(want, unpack_mask(want_masks[0], key).reshape(got.shape))   # oracle == reference
+            margin = (logit_t[:, :G] - logit_t[:, G:]).abs().numpy().reshape(got.shape)
+            clear = margin > MARGIN_TOL * float(logit_t.abs().max())
+            diff = got != want
+            total += diff.size
+            noise += int((diff & ~clear).sum())
+            clear_flips += int((diff & clear).sum())
+    return total, noise, clear_flips
+
+
+@pytest.mark.parametrize("name", list(FULL_CASES))
+def test_full_size_free_running_vs_reference_golden(cuda_lib, name):
+    """Every BASELINE architecture at 224x224 (ResNet-101 channel-2222 / layer, ResNet-50 spatial / conv_linear,
+    RegNetY-800MF spatial), calibrated weights, the 2 golden images of tests/golden/full_*.npz - outputs of the
+    unmodified REFERENCE: every gating decision of every block bit-exact (wherever the margin is clear), the
+    sparsity lists / flops_perc / flops equal, logits within LOGIT_TOL."""
+    kind, cfg, sd, x, z = load_full_case(name)
+    model = _full_model(kind, cfg, sd)
+    keep, traces = [], []
+    with torch.no_grad():
+        logits, r3, r2, r1, rc, perc, flops = model(x.to(DEV), 1.0, keep=keep)
+        torch.cuda.synchronize()
+    _oracle(kind, cfg, sd, x, traces)
+    tags = (["ref." + g.prefix[:-1] for g in O.resnet_geometry(cfg)] if kind == "resnet"
+            else ["ref." + g.prefix.split(".")[2] for g in O.regnet_geometry(cfg)])
+    total, noise, clear_flips = _gate_report(keep, traces, (z, tags))
+    err = _rel_err(logits, torch.from_numpy(z["logits"]))
+    print(f"{name}: {total} gating decisions, {noise} within-noise flips, {clear_flips} clear flips, logits err {err:.2e}")
+    assert clear_flips == 0, f"{name}: a gating decision with a clear margin differs from the reference's"
+    assert noise <= 2e-3 * total
+    if noise == 0:
+        for key, lst in (("rho3", r3), ("rhoc", rc)):
+            np.testing.assert_array_equal(np.concatenate([t.cpu().numpy() for t in lst]),
+                                          np.concatenate([z[f"{key}.{s}"] for s in range(4)]))
+        np.testing.assert_allclose(perc.cpu().numpy(), z["flops_perc"], rtol=1e-6)
+        np.testing.assert_allclose(flops.item(), float(z["flops"]), rtol=1e-6)
+        assert err <= LOGIT_TOL, f"{name}: logits error {err:.2e}"
+
+
+def _bs8_vs_oracle(name, graphed_chains=0, setup=None):
+    """Batch 8 (the 2 golden images + 6 more of the same seeded stream), free-running, against the CPU oracle."""
+    kind, cfg, sd, x2, z = load_full_case(name)
+    seed = FULL_CASES[name][4]
+    x = synth.synth_images(8, cfg.input_size, seed)
+    assert torch.equal(x[:2], x2)
+    model = _full_model(kind, cfg, sd)
+    if setup:
+        setup(model)
+    traces = []
+    ref = _oracle(kind, cfg, sd, x, traces)
     keep = []
     with torch.no_grad():
-        logits, r3, r2, r1, rc, perc, flops = m(x, 1.0, keep=keep)
-    assert logits.shape == (8, 1000) and torch.isfinite(logits).all()
-    assert [len(t) for t in r3] == [3, 4, 6, 3] and perc.shape == (16,)
-    for ko, dens3, dens2, dens1 in zip(keep, torch.cat(r3).tolist(), torch.cat(r2).tolist(), torch.cat(r1).tolist()):
-        m3, m2, m1 = ko.mask_conv3.float(), ko.mask_conv2.float(), ko.mask_conv1.float()
-        assert abs(ko.spatial_mask_small.float().mean().item() - dens3) < 1e-6
-        assert abs(m2.mean().item() - dens2) < 1e-6 and abs(m1.mean().item() - dens1) < 1e-6
-        # dilation is monotone: conv1's mask covers conv2's footprint
-        s = m1.shape[-1] // m2.shape[-1]
-        assert torch.all(m1[:, :, ::s, ::s] >= m2)
-        out = ko.out.float()                      # [B,H,W,C]
-        assert torch.isfinite(out).all() and (out >= 0).all()
+        out = model(x.to(DEV), 1.0, keep=keep)
+        torch.cuda.synchronize()
+    total, noise, clear_flips = _gate_report(keep, traces)
+    err = _rel_err(out[0], ref[0])
+    print(f"{name} bs8: {total} gating decisions, {noise} within-noise flips, {clear_flips} clear flips, logits err {err:.2e}")
+    assert clear_flips == 0 and noise <= 2e-3 * total
+    # the reference's own 2-image outputs are rows 0-1 of this batch (samples are independent in eval mode)
+    assert _rel_err(out[0][:2], torch.from_numpy(z["logits"])) <= LOGIT_TOL or noise > 0
+    if noise == 0:
+        assert err <= LOGIT_TOL, f"{name}: logits error {err:.2e}"
+        for i in (1, 2, 3, 4):                                      # rho3 / rho2 / rho1 / rho_c per block
+            np.testing.assert_array_equal(np.concatenate([t.cpu().numpy() for t in out[i]]),
+                                          np.concatenate([t.numpy() for t in ref[i]]))
+        np.testing.assert_allclose(out[5].cpu().numpy(), ref[5].numpy(), rtol=1e-6)
+        np.testing.assert_allclose(out[6].item(), ref[6].item(), rtol=1e-6)
+    if graphed_chains:
+        # the serving path that bench.py times: CUDA graph, `graphed_chains` parallel chains over slices of the batch
+        with torch.no_grad():
+            g = _engine.GraphedForward(model._engine, x.to(DEV), splits=graphed_chains)
+            assert g.splits == graphed_chains
+            lg, st = g.replay()
+            torch.cuda.synchronize()
+            lg2, st2 = (t.clone() for t in g.run(x.to(DEV)))
+            torch.cuda.synchronize()
+        assert torch.equal(lg, lg2) and torch.equal(st, st2), "graph replays must be repeatable"
+        gr3, gr2, gr1, grc, gperc, gflops = model._engine.split_stats(st)
+        gerr = _rel_err(lg, ref[0])
+        print(f"{name} bs8 graphed x{graphed_chains}: logits err {gerr:.2e}")
+        if noise == 0:
+            assert gerr <= LOGIT_TOL
+            np.testing.assert_array_equal(torch.cat(grc).cpu().numpy(), torch.cat(list(ref[4])).numpy())
+            np.testing.assert_array_equal(torch.cat(gr3).cpu().numpy(), torch.cat(list(ref[1])).numpy())
+            np.testing.assert_allclose(gflops.item(), ref[6].item(), rtol=1e-6)
+        # chains see the same samples at different batch offsets: identical decisions except at exact ties
+        assert _rel_err(lg, out[0].float().cpu()) <= 2e-3
+    return model
+
+
+def test_headline_r101_channel_bs8_graphed_two_chains_vs_oracle(cuda_lib):
+    """BASELINE configs[1] (LAUD-ResNet101 channel-2222, calibrated weights) at batch 8: eager forward with every
+    gate checked, then the CUDA-graphed two-chain forward that bench.py times - both against the CPU oracle."""
+    m = _bs8_vs_oracle("full_r101_channel", graphed_chains=2)
+    assert m._engine.channel_exec in ("dense", "sparse", "auto")
+
+
+@pytest.mark.parametrize("channel_exec", ["sparse", "dense"])
+def test_headline_r101_channel_bs8_both_executions_vs_oracle(cuda_lib, channel_exec):
+    _bs8_vs_oracle("full_r101_channel", setup=lambda m: setattr(m._engine, "channel_exec", channel_exec))
+
+
+def test_resnet50_spatial_bs8_full_size_vs_oracle(cuda_lib):
+    """BASELINE configs[0] (LAUD-ResNet50 spatial 4-4-2-1, batch 8, 224x224) against the CPU oracle: spatial gates,
+    dilated masks' densities, logits, flops."""
+    _bs8_vs_oracle("full_r50_spatial", graphed_chains=1)
+
+
+@pytest.mark.parametrize("layer_exec", ["skip", "mask"])
+def test_resnet101_layer_bs8_full_size_vs_oracle(cuda_lib, layer_exec):
+    """BASELINE configs[2] (LAUD-ResNet101 layer skip) at batch 8 against the CPU oracle, real skip and masked-dense;
+    the graphed serving path (no per-block capture => in-place skip lists) included."""
+    _bs8_vs_oracle("full_r101_layer", graphed_chains=2, setup=lambda m: setattr(m._engine, "layer_exec", layer_exec))
+
+
+def test_resnet50_conv_linear_channel_bs8_full_size_vs_oracle(cuda_lib):
+    """channel mode with the reference Bottleneck's DEFAULT masker (conv_linear, laud_resnet.py:36) at full size: the
+    engine must not fuse the GAP into the previous conv3 and the gate runs from pre-packed weights."""
+    m = _bs8_vs_oracle("full_r50_convlinear", graphed_chains=2)
+    assert not any(m._engine._gap_fusable(p) for p in m._engine.plans[:-1])
+
+
+def test_regnet_y_800mf_spatial_bs8_full_size_vs_oracle(cuda_lib):
+    _bs8_vs_oracle("full_regnety800_spatial")
 
 
 # =========================================================================== LAUD-RegNet-Y (laud_regnet.py)

@@ -177,3 +177,48 @@ def test_regnet_y_800mf_geometry():
     from laudnet_b200.laud_regnet import stage_params
     assert stage_params(depth=14, w_0=56, w_a=38.84, w_m=2.4, group_width=16) == ([64, 144, 320, 784], [1, 3, 8, 2], [16] * 4)
     assert stage_params(depth=16, w_0=48, w_a=27.89, w_m=2.09, group_width=8) == ([48, 104, 208, 440], [1, 3, 6, 6], [8] * 4)
+
+
+# --------------------------------------------------------------------------- full-size pins (224x224, BASELINE architectures)
+from tests.golden_cases import FULL_CASES, load_full_case       # noqa: E402
+
+
+def unpack_mask(z, key):
+    shape = tuple(int(v) for v in z[key + ".shape"])
+    return np.unpackbits(z[key + ".bits"])[:int(np.prod(shape))].reshape(shape)
+
+
+@pytest.mark.parametrize("name", list(FULL_CASES))
+def test_full_size_network_matches_reference(name):
+    """The oracle against the reference ITSELF at the real shapes of the BASELINE.json architectures (ResNet-101
+    channel-2222 / layer, ResNet-50 spatial / conv_linear, RegNetY-800MF spatial; 2 images, 224x224): logits, every
+    gating decision of every block, the sparsity lists, flops_perc and flops (tests/golden/make_golden_fullsize.py)."""
+    kind, cfg, sd, x, z = load_full_case(name)
+    traces = []
+    with torch.no_grad():
+        if kind == "resnet":
+            out = O.resnet_forward(sd, cfg, x, traces)
+            tags = ["ref." + g.prefix[:-1] for g in O.resnet_geometry(cfg)]
+        else:
+            out = O.regnet_forward(sd, cfg, x, traces)
+            tags = ["ref." + g.prefix.split(".")[2] for g in O.regnet_geometry(cfg)]
+    logits, r3, r2, r1, rc, perc, flops = out
+    np.testing.assert_allclose(logits.numpy(), z["logits"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(perc.numpy(), z["flops_perc"], rtol=1e-6)
+    np.testing.assert_allclose(flops.item(), z["flops"], rtol=1e-6)
+    for key, lst in (("rho3", r3), ("rho2", r2), ("rho1", r1), ("rhoc", rc)):
+        for s in range(4):
+            np.testing.assert_array_equal(lst[s].numpy(), z[f"{key}.{s}"])
+    assert len(tags) == len(traces)
+    n_gates = 0
+    for tag, tr in zip(tags, traces):
+        if tr.channel_mask is not None:
+            np.testing.assert_array_equal(tr.channel_mask.numpy().astype(np.uint8), unpack_mask(z, tag + ".channel_mask"))
+            n_gates += tr.channel_mask.numel()
+        if tr.spatial_mask_small is not None:
+            np.testing.assert_array_equal(tr.spatial_mask_small.numpy().astype(np.uint8), unpack_mask(z, tag + ".spatial_mask"))
+            n_gates += tr.spatial_mask_small.numel()
+        o = tr.out.double()
+        stats = np.array([o.mean().item(), o.abs().mean().item(), o.abs().max().item()])
+        np.testing.assert_allclose(stats, z[tag + ".out_stats"], rtol=1e-4)
+    assert n_gates > 0
