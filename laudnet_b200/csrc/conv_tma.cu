@@ -127,6 +127,12 @@ struct Plan {              // host-computed launch geometry
   int c_nfill, c_nk16, c_cpt, c_nchunks, NG;
   int st256;               // 1: OUT_DIRECT may use 32-byte global stores (y 32-byte aligned, ldy and C_out multiples of 16)
   int gap;                 // 1: fused global-average-pool partial sums of the output (flat 1x1 layers, OUT_SLAB + dma)
+  int flat;                // 1: the layer runs as ONE GEMM over all B*H*W pixels (a.B == 1, a.gap_hw = pixels per sample)
+  int nm;                  // 1: masked-dense channel gate (n_mask) looked up per accumulator ROW in the epilogue - the column
+                           //    tables stay static, so a gated 1x1 layer can still be flat;  nm_fast: granularity 2, 16-byte rows
+  int nm_fast;
+  int tsplit;              // 1: (flat, one n-group, MT == 2) CTAs own contiguous ranges of m-TILES, processed two at a time:
+                           //    the critical path is ceil(tiles / CTAs) tiles instead of 2 x ceil(tile pairs / CTAs)
   int dbg;                 // LAUD_DBG timing experiments (wrong results): 2 no activation loads, 4 no MMAs, 8 no epilogue work, 16 half-N MMAs
 };
 
@@ -162,6 +168,14 @@ struct Walker {
   int t, t_end, slot, mg, ng, nti, started;
 };
 __device__ __forceinline__ void walker_init(const ConvArgs& a, const Plan& pl, Walker& w) {
+  if (pl.tsplit) {                           // t counts m-tiles; an item is up to MT consecutive tiles of the CTA's range
+    const int base = pl.n_mtiles / (int)gridDim.x, rem = pl.n_mtiles % (int)gridDim.x;
+    const int c = (int)blockIdx.x;
+    w.t = c * base + min(c, rem);
+    w.t_end = w.t + base + (c < rem ? 1 : 0);
+    w.ng = 0; w.mg = 0; w.slot = 0; w.nti = 0; w.started = 0;
+    return;
+  }
   // with a device-side sample list only the ACTIVE samples' items are partitioned, so every CTA gets its share
   const int total = a.sample_cnt ? min(__ldg(a.sample_cnt), a.B) * (pl.total_items / a.B) : pl.total_items;
   const int base = total / (int)gridDim.x, rem = total % (int)gridDim.x;
@@ -195,6 +209,10 @@ __device__ __forceinline__ bool decode_sub(const ConvArgs& a, const Plan& pl, co
     s.nchunks = pl.c_nchunks;
     s.mt0 = w.mg * pl.MT;
     s.mt_cnt = min(pl.MT, pl.n_mtiles - s.mt0);
+    if (pl.tsplit) {
+      s.mt0 = w.t;
+      s.mt_cnt = min(pl.MT, w.t_end - w.t);
+    }
     return true;
   }
   const int ns = a.sample_cnt ? __ldg(a.sample_cnt) : a.B;
@@ -225,6 +243,8 @@ __device__ __forceinline__ bool walker_next(const ConvArgs& a, const Plan& pl, c
   while (true) {
     if (!w.started) {
       w.started = 1;
+    } else if (pl.tsplit) {
+      w.t += pl.MT;
     } else if (++w.nti >= pl.NTI) {
       w.nti = 0;
       ++w.t;
@@ -308,12 +328,32 @@ __device__ __forceinline__ void column_entry(const ConvArgs& a, const Plan& pl, 
   if (o >= 0 && a.n_mask && __ldg(a.n_mask + (size_t)s.b * (a.C_out / a.n_mask_gran) + o / a.n_mask_gran) == 0) sc = 0.f;   // mask before BN
 }
 
+// Masked-dense channel gate of 32 consecutive output channels [ch0, ch0 + 32) of one sample: bit e set = channel ch0 + e
+// is kept.  `mrow` = the sample's row of n_mask (one byte per group of `gran` channels).  fast16: gran == 2 and the 16
+// bytes are aligned - one load.
+__device__ __forceinline__ uint32_t nmask_bits(const uint8_t* mrow, int ch0, int gran, int c_out, bool fast16) {
+  uint32_t keep = 0u;
+  if (fast16) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(mrow + (ch0 >> 1)));
+    const uint32_t wv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if ((wv[i] >> (8 * j)) & 0xffu) keep |= 3u << (2 * (4 * i + j));
+  } else {
+    for (int e = 0; e < 32; ++e)
+      if (ch0 + e < c_out && __ldg(mrow + (ch0 + e) / gran) != 0) keep |= 1u << e;
+  }
+  return keep;
+}
+
 // One 32-column pass of the slab epilogue for this thread's pixel row: accumulator (registers) -> folded BN ->
 // gate -> (+ residual from the slab) -> fp16 -> ReLU -> back into the slab.  The flags are template parameters so the
 // eight 16-byte groups are straight-line code: the table / residual loads of all groups issue back to back.
 template <bool RES, bool RELU>
 __device__ __forceinline__ void slab_pass(float* v, uint32_t t_scale, uint32_t t_shift, int c0, uint32_t srow, uint32_t sw,
-                                          int p, float gate) {
+                                          int p, float gate, uint32_t keep = 0xffffffffu) {
 #pragma unroll
   for (int gp = 0; gp < 4; gp += 2) {             // two 16-byte groups at a time: loads first, then arithmetic
     float4 s0[2], s1[2], h0[2], h1[2];
@@ -331,6 +371,11 @@ __device__ __forceinline__ void slab_pass(float* v, uint32_t t_scale, uint32_t t
     for (int j = 0; j < 2; ++j) {
       const int g4 = gp + j;
       float* w = v + g4 * 8;
+      if (keep != 0xffffffffu) {                   // masked-dense channel gate: a gated channel's accumulator counts as 0
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (!((keep >> (g4 * 8 + e)) & 1u)) w[e] = 0.f;
+      }
       w[0] = fmaf(w[0], s0[j].x, h0[j].x) * gate; w[1] = fmaf(w[1], s0[j].y, h0[j].y) * gate;
       w[2] = fmaf(w[2], s0[j].z, h0[j].z) * gate; w[3] = fmaf(w[3], s0[j].w, h0[j].w) * gate;
       w[4] = fmaf(w[4], s1[j].x, h1[j].x) * gate; w[5] = fmaf(w[5], s1[j].y, h1[j].y) * gate;
@@ -896,6 +941,12 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
           prow = oyl * a.W_out + ox;
           pvalid = ox < a.W_out && prow < rows;
         }
+        // masked-dense channel gate looked up per row (static column tables): this row's sample and its n_mask row
+        const uint8_t* mrow = nullptr;
+        if (!M::SLAB_FIXED && pl.nm && pvalid) {
+          const int bb = pl.flat ? (m0 + prow) / a.gap_hw : s.b;
+          mrow = a.n_mask + (size_t)bb * (a.C_out / a.n_mask_gran);
+        }
         if (M::omode(pl) == OUT_SLAB) {
           bool row_on = true;                                    // spatial / layer gate of this pixel (one mask group)
           if (M::out_mask(a)) row_on = pvalid && M::out_mask(a)[(size_t)s.b * HWo + m0 + prow] != 0;
@@ -925,12 +976,14 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
                 const bool gate0_relu = M::relu_mode(a) == LAUD_RELU_WHERE_GATE0;
                 const float gate = (row_on || gate0_relu) ? 1.f : 0.f;
                 const bool relu_row = relu_all || (gate0_relu && !row_on);
+                uint32_t keep = 0xffffffffu;
+                if (!M::SLAB_FIXED && mrow) keep = nmask_bits(mrow, s.n0 + c0, a.n_mask_gran, a.C_out, pl.nm_fast != 0);
                 if (has_res) {
-                  if (relu_row) slab_pass<true, true>(v, t_scale, t_shift, c0, srow, sw, p, gate);
-                  else slab_pass<true, false>(v, t_scale, t_shift, c0, srow, sw, p, gate);
+                  if (relu_row) slab_pass<true, true>(v, t_scale, t_shift, c0, srow, sw, p, gate, keep);
+                  else slab_pass<true, false>(v, t_scale, t_shift, c0, srow, sw, p, gate, keep);
                 } else {
-                  if (relu_row) slab_pass<false, true>(v, t_scale, t_shift, c0, srow, sw, p, gate);
-                  else slab_pass<false, false>(v, t_scale, t_shift, c0, srow, sw, p, gate);
+                  if (relu_row) slab_pass<false, true>(v, t_scale, t_shift, c0, srow, sw, p, gate, keep);
+                  else slab_pass<false, false>(v, t_scale, t_shift, c0, srow, sw, p, gate, keep);
                 }
               }
             }
@@ -982,6 +1035,8 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
             }
             if (valid) {
               uint4 o_prev = make_uint4(0u, 0u, 0u, 0u);
+              uint32_t keep = 0xffffffffu;
+              if (mrow) keep = nmask_bits(mrow, s.n0 + c0, a.n_mask_gran, a.C_out, pl.nm_fast != 0);
 #pragma unroll
               for (int g4 = 0; g4 < 4; ++g4) {
                 if (c0 + g4 * 8 < s.n_valid) {
@@ -990,6 +1045,11 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
                   const float4 h0 = lds_f4(t_shift + (uint32_t)(c0 + g4 * 8) * 4u);
                   const float4 h1 = lds_f4(t_shift + (uint32_t)(c0 + g4 * 8 + 4) * 4u);
                   float* w = v + g4 * 8;
+                  if (keep != 0xffffffffu) {        // gated channel: accumulator counts as 0 (conv -> x mask -> bn)
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                      if (!((keep >> (g4 * 8 + e)) & 1u)) w[e] = 0.f;
+                  }
                   w[0] = fmaf(w[0], s0.x, h0.x); w[1] = fmaf(w[1], s0.y, h0.y);
                   w[2] = fmaf(w[2], s0.z, h0.z); w[3] = fmaf(w[3], s0.w, h0.w);
                   w[4] = fmaf(w[4], s1.x, h1.x); w[5] = fmaf(w[5], s1.y, h1.y);
@@ -1169,14 +1229,21 @@ bool conv_tma_supported(const ConvArgs& a) {
   return encode_fn() != nullptr;
 }
 
-int conv_forward_tma(const ConvArgs& a_in, cudaStream_t s) {
+static int conv_forward_tma_x(const ConvArgs& a_in, cudaStream_t s, bool allow_row_gate);
+int conv_forward_tma(const ConvArgs& a_in, cudaStream_t s) { return conv_forward_tma_x(a_in, s, true); }
+
+// allow_row_gate: the masked-dense channel gate (n_mask) may be looked up per accumulator row with static column
+// tables (lets a gated 1x1 layer run flat); false = per-item column tables, per-sample items (the earlier scheme).
+static int conv_forward_tma_x(const ConvArgs& a_in, cudaStream_t s, bool allow_row_gate) {
   // A 1x1 stride-1 layer with nothing per sample (no gather, gate or list) is one flat GEMM over all B*H*W pixels:
   // m-tiles run across sample boundaries, so images smaller than a tile (14x14, 7x7) leave no padded rows.
   ConvArgs a = a_in;
   bool flat = false;
   static const bool no_flat = getenv("LAUD_NO_FLAT") != nullptr;
-  if (!no_flat && a.ksize == 1 && a.stride == 1 && !a.k_idx && !a.n_idx && !a.n_mask && !a.sample_idx && !a.out_mask &&
-      !a.bias_t && (long long)a.B * a.H_out * a.W_out < (1ll << 31)) {
+  static const bool no_row_gate = getenv("LAUD_NO_ROW_GATE") != nullptr;        // A/B switch
+  if (no_row_gate) allow_row_gate = false;
+  if (!no_flat && a.ksize == 1 && a.stride == 1 && !a.k_idx && !a.n_idx && (!a.n_mask || allow_row_gate) && !a.sample_idx &&
+      !a.out_mask && !a.bias_t && (long long)a.B * a.H_out * a.W_out < (1ll << 31)) {
     a.gap_hw = a.H_out * a.W_out;
     a.W_in = a.W_out = a.B * a.H_out * a.W_out;
     a.H_in = a.H_out = 1;
@@ -1307,14 +1374,22 @@ int conv_forward_tma(const ConvArgs& a_in, cudaStream_t s) {
   pl.c_nk16 = (a.C_in + 15) >> 4;
   pl.c_cpt = (pl.c_nk16 + 3) >> 2;
   pl.c_nchunks = pl.c_cpt * taps;
-  pl.static_cols = (pl.omode != OUT_ROWS && !a.n_idx && !a.n_mask) ? 1 : 0;
+  pl.flat = flat ? 1 : 0;
+  pl.static_cols = (pl.omode != OUT_ROWS && !a.n_idx && (!a.n_mask || allow_row_gate)) ? 1 : 0;
   pl.stab_cols = round_up(a.C_out, 64) + BN_MAX;              // reads of a partial last tile stay inside the (zero) padding
   int stab_bytes = pl.static_cols ? 2 * pl.stab_cols * 4 : 0;
   int avail = SMEM_LIMIT - 1024 - (int)sizeof(Tables) - stg_bytes - pl.a_region_bytes - stab_bytes - gap_bytes;
   if (pl.static_cols && avail / pl.stage_bytes < 2) {         // no room beside a two-stage pipeline: per-item tables
+    if (a.n_mask) return conv_forward_tma_x(a_in, s, false);  // (the row gate needs the static tables)
     pl.static_cols = 0;
     avail += stab_bytes;
     stab_bytes = 0;
+  }
+  pl.nm = (a.n_mask && pl.static_cols) ? 1 : 0;
+  pl.nm_fast = (pl.nm && a.n_mask_gran == 2 && a.C_out % 32 == 0 && (reinterpret_cast<uintptr_t>(a.n_mask) & 15) == 0) ? 1 : 0;
+  {
+    static const bool no_tsplit = getenv("LAUD_NO_TSPLIT") != nullptr;         // A/B switch
+    pl.tsplit = (!no_tsplit && flat && pl.NG == 1 && pl.NTI == 1 && pl.MT == 2 && pl.omode == OUT_DIRECT && !pl.gap) ? 1 : 0;
   }
   pl.stages = avail / pl.stage_bytes;
   if (pl.stages > MAX_STAGES) pl.stages = MAX_STAGES;
@@ -1377,7 +1452,8 @@ int conv_forward_tma(const ConvArgs& a_in, cudaStream_t s) {
   }
 
   const size_t smem = 1024 + (size_t)pl.a_region_bytes + (size_t)pl.stages * pl.stage_bytes + stg_bytes + sizeof(Tables) + stab_bytes + gap_bytes;
-  const int grid = (int)(total < num_sms ? total : num_sms);
+  const long long units = pl.tsplit ? pl.n_mtiles : total;                    // what the CTAs partition
+  const int grid = (int)(units < num_sms ? units : num_sms);
   g_conv_paths[0].fetch_add(1, std::memory_order_relaxed);
   g_conv_tma_launches.fetch_add(1, std::memory_order_relaxed);
   {
@@ -1387,8 +1463,8 @@ int conv_forward_tma(const ConvArgs& a_in, cudaStream_t s) {
     if (!no_spec && pl.simple && pl.bmode == BMODE_TMA) {
       if (pl.omode == OUT_SLAB && pl.dma && !pl.halo) {
         spec = 1;
-        if (!a.out_mask && a.residual && a.relu_mode == LAUD_RELU_ALL) spec = 4;
-        else if (!a.out_mask && !a.residual && a.relu_mode == LAUD_RELU_NONE) spec = 5;
+        if (!a.out_mask && !a.n_mask && a.residual && a.relu_mode == LAUD_RELU_ALL) spec = 4;
+        else if (!a.out_mask && !a.n_mask && !a.residual && a.relu_mode == LAUD_RELU_NONE) spec = 5;
       }
       else if (pl.omode == OUT_DIRECT) spec = pl.halo ? 3 : 2;
     }
