@@ -334,7 +334,7 @@ class ResNetEngine:
         )
         cl = [p for p in self.plans if p.masker_kind == "conv_linear"]
         if cl:      # Masker_channel_conv_linear: reduced-width feature map and its pool
-            cr = lambda p: p.module.masker_channel.conv[0].weight.shape[0]
+            cr = lambda p: (p.module.masker_channel.conv[0].weight.shape[0] + 7) // 8 * 8
             ws["mkz"] = torch.empty(max(B * p.H_in * p.H_in * cr(p) for p in cl), **f16)
             ws["mkpool"] = torch.empty(max(B * cr(p) for p in cl), dtype=torch.float32, device=dev)
         else:
@@ -541,13 +541,15 @@ class ResNetEngine:
 
     # ----------------------------------------------------------------- forward
     def forward(self, x: torch.Tensor, keep: Optional[List[BlockOutputs]] = None, slot: int = 0,
-                logits_out: Optional[torch.Tensor] = None, want_stats: bool = True):
+                logits_out: Optional[torch.Tensor] = None, want_stats: bool = True, forced=None):
+        """forced (tests): per block a pair (channel mask [B,G] | None, spatial mask [B,g,S,S] | None) installed
+        instead of the block's own gating decision - the teacher-forced network forward."""
         if x.device.type != "cuda":
             raise LaudError("ResNet.forward: expected a CUDA tensor - there is no CPU path")
         with torch.cuda.device(x.device):        # launches go to the current stream of the INPUT's device
-            return self._forward(x, keep, slot, logits_out, want_stats)
+            return self._forward(x, keep, slot, logits_out, want_stats, forced)
 
-    def _forward(self, x, keep, slot, logits_out, want_stats):
+    def _forward(self, x, keep, slot, logits_out, want_stats, forced=None):
         m = self.model
         if self.prepared_for != x.device:
             self.prepare()
@@ -578,7 +580,9 @@ class ResNetEngine:
             if nvtx:
                 torch.cuda.nvtx.range_push(f"blk{p.index}")
             gap_out = self._gap_fusable(p)
-            res_buf = self.run_block(p, bufs[cur], bufs[nxt], bufs[idb], B, ws, ko, gap_in=gap_in, gap_out=gap_out)
+            fc, fs = forced[p.index] if forced is not None else (None, None)
+            res_buf = self.run_block(p, bufs[cur], bufs[nxt], bufs[idb], B, ws, ko, gap_in=gap_in, gap_out=gap_out,
+                                     forced_channel_mask=fc, forced_spatial_mask=fs)
             gap_in = gap_out
             if nvtx:
                 torch.cuda.nvtx.range_pop()

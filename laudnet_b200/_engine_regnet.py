@@ -264,13 +264,13 @@ class RegNetEngine:
         return out
 
     # ----------------------------------------------------------------- forward
-    def forward(self, x: torch.Tensor, keep: Optional[List[BlockOutputs]] = None):
+    def forward(self, x: torch.Tensor, keep: Optional[List[BlockOutputs]] = None, forced=None):
         if x.device.type != "cuda":
             raise LaudError("LAD_RegNet.forward: expected a CUDA tensor - there is no CPU path")
         with torch.cuda.device(x.device):        # launches go to the current stream of the INPUT's device
-            return self._forward(x, keep)
+            return self._forward(x, keep, forced)
 
-    def _forward(self, x, keep):
+    def _forward(self, x, keep, forced=None):
         m = self.model
         if self.prepared_for != x.device:
             self.prepare()
@@ -295,7 +295,8 @@ class RegNetEngine:
             if keep is not None:
                 ko = BlockOutputs()
                 keep.append(ko)
-            self.run_block(p, bufs[cur], bufs[nxt], bufs[idb], B, ws, ko)
+            fc, fs = forced[p.index] if forced is not None else (None, None)
+            self.run_block(p, bufs[cur], bufs[nxt], bufs[idb], B, ws, ko, fc, fs)
             cur = nxt
         last = self.plans[-1]
         ncls = m.fc.weight.shape[0]

@@ -1230,7 +1230,16 @@ bool conv_tma_supported(const ConvArgs& a) {
 }
 
 static int conv_forward_tma_x(const ConvArgs& a_in, cudaStream_t s, bool allow_row_gate);
-int conv_forward_tma(const ConvArgs& a_in, cudaStream_t s) { return conv_forward_tma_x(a_in, s, true); }
+// The per-row gate pays where a sample's pixels fill less than half an m-tile (7x7 maps: the flat GEMM packs 2.6 samples
+// into a tile); measured on B200 (profiles/r02b_*): stage-4 conv1 -26 %, but +8 % on the 3x3 layers and +17 % on the 56x56
+// slab layers, whose epilogues are issue-bound - those keep the per-item column tables.  LAUD_ROW_GATE=all|none overrides.
+int conv_forward_tma(const ConvArgs& a_in, cudaStream_t s) {
+  static const char* mode = getenv("LAUD_ROW_GATE");
+  bool row_gate = a_in.ksize == 1 && a_in.stride == 1 && a_in.H_out * a_in.W_out <= 64;
+  if (mode && !strcmp(mode, "all")) row_gate = true;
+  if (mode && !strcmp(mode, "none")) row_gate = false;
+  return conv_forward_tma_x(a_in, s, row_gate);
+}
 
 // allow_row_gate: the masked-dense channel gate (n_mask) may be looked up per accumulator row with static column
 // tables (lets a gated 1x1 layer run flat); false = per-item column tables, per-sample items (the earlier scheme).

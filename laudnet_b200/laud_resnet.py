@@ -269,11 +269,11 @@ class ResNet(nn.Module):
         self._engine.impl = impl
         return self
 
-    def forward(self, x, temperature=1.0, keep=None):
+    def forward(self, x, temperature=1.0, keep=None, forced=None):
         if self.training:
             raise LaudError("ResNet: training mode (Gumbel gates, reference utils.py:56-58) is not part of the "
                             "CUDA inference path; call .eval()")
-        logits, stats = self._engine.forward(x, keep)
+        logits, stats = self._engine.forward(x, keep, forced=forced)
         r3, r2, r1, rc, perc, flops = self._engine.split_stats(stats)
         return logits, r3, r2, r1, rc, perc, flops
 

@@ -290,8 +290,20 @@ class Masker_channel_conv_linear(nn.Module):
         if pk is None:
             from ._engine import fold_bn, pack_conv_weight     # local import: engine depends on this module
             scale, shift = fold_bn(self.conv[1])
-            pk = (pack_conv_weight(self.conv[0].weight), scale, shift,
-                  self.linear.weight.detach().float().contiguous(), self.linear.bias.detach().float().contiguous())
+            wc = pack_conv_weight(self.conv[0].weight)
+            wl = self.linear.weight.detach().float().contiguous()
+            cr = wc.shape[0]
+            crp = (cr + 7) // 8 * 8
+            if crp != cr:
+                # the fp16 kernels take channel counts in multiples of 8 (64 input channels / reduction 16 = 4, the
+                # reference Bottleneck default at stage 1): pad with channels that are exactly 0 after BN + ReLU
+                # (zero weights, scale = shift = 0) and give them zero columns in the linear layer
+                pad = crp - cr
+                wc = torch.cat([wc, wc.new_zeros((pad,) + tuple(wc.shape[1:]))]).contiguous()
+                scale = torch.cat([scale, scale.new_zeros(pad)]).contiguous()
+                shift = torch.cat([shift, shift.new_zeros(pad)]).contiguous()
+                wl = torch.cat([wl, wl.new_zeros(wl.shape[0], pad)], dim=1).contiguous()
+            pk = (wc, scale, shift, wl, self.linear.bias.detach().float().contiguous())
             self._packed = pk
         return pk
 
@@ -311,12 +323,10 @@ class Masker_channel_conv_linear(nn.Module):
         B*GAP_SPLITS*C/r); allocated here when absent."""
         from ._engine import run_conv
         b, h, w, c = x.shape
-        cr = self.conv[0].weight.shape[0]
-        if cr % 8:
-            raise LaudError(f"Masker_channel_conv_linear: reduced width {cr} must be a multiple of 8")
         G = self.channel_dyn_group
         dev = x.device
         wc, scale, shift, wl, bl = self._weights()
+        cr = wc.shape[0]                           # reduced width, padded to a multiple of 8
         z = (z_ws[:b * h * w * cr] if z_ws is not None else torch.empty(b * h * w * cr, dtype=torch.float16, device=dev)).view(b, h, w, cr)
         run_conv(x, wc, z, b, h, w, c, h, w, cr, 1, 1, 0, scale=scale, shift=shift, relu=_lib.RELU_ALL, impl=impl,
                  tag="masker.conv")

@@ -262,3 +262,88 @@ def test_engine_decides_where_the_gap_is_fused(monkeypatch):
     eng.channel_exec = "dense"
     monkeypatch.setenv("LAUD_NO_FLAT", "1")
     assert not any(eng._gap_fusable(p) for p in eng.plans)
+
+
+# --------------------------------------------------------------------------- validate()-compatible caller
+class _FakeLaud(torch.nn.Module):
+    """Stand-in for a LAUD model on CPU: deterministic 7-tuple from the images (host logic of validate() only)."""
+
+    def __init__(self, n_blocks=(2, 3, 1, 2), ncls=7):
+        super().__init__()
+        self.n_blocks, self.ncls = n_blocks, ncls
+        g = torch.Generator().manual_seed(5)
+        self.w = torch.randn(12, ncls, generator=g)
+
+    def forward(self, images, temperature=1.0):
+        feat = images.reshape(images.shape[0], -1)[:, :12]
+        logits = feat @ self.w
+        m = feat.mean()
+        lists = [[torch.sigmoid(m * (k + 1) + torch.arange(n, dtype=torch.float32) * 0.1 * (j + 1)) for j, n in enumerate(self.n_blocks)]
+                 for k in range(4)]
+        perc = torch.sigmoid(m + torch.arange(sum(self.n_blocks), dtype=torch.float32) * 0.05)
+        flops = (2.0e9 + 1e8 * m).reshape(())
+        return (logits, *lists, perc, flops)
+
+
+def _reference_validate_restated(batches, model, criterion, sparsity_criterion, args, epoch, world):
+    """Literal restatement of the reference loop (train/main.py:627-757): per-batch all_reduce / world_size of every
+    scalar, AverageMeter updates weighted by the local batch size, rank-local densities (the dead list-vs-string guard)."""
+    from laudnet_b200.validate import AverageMeter, accuracy
+    meters = {k: AverageMeter(k) for k in ("cls", "flops_loss", "loss", "act", "flops", "top1", "top5")}
+    dens_sum, n = None, 0
+    for images, target in batches:
+        bs = images.size(0)
+        n += bs
+        out, r3, r2, r1, rc, perc, flops = model(images, temperature=args.t_last)
+        d = torch.stack([torch.cat(l) for l in (r3, r2, r1, rc)]) * bs
+        dens_sum = d if dens_sum is None else dens_sum + d
+        flops = flops / 1e9
+        vals = dict(cls=criterion(out, target), act=perc.mean(), flops=flops)
+        vals["flops_loss"] = sparsity_criterion(epoch, perc, flops)
+        vals["loss"] = vals["cls"] + args.lambda_act * vals["flops_loss"]
+        vals["top1"], vals["top5"] = (a.reshape(()) for a in accuracy(out, target, topk=(1, 5)))
+        for k, v in vals.items():
+            v = v.clone().float()
+            dist.all_reduce(v)
+            meters[k].update((v / world).item(), bs)
+    return (meters["top1"].avg, meters["top5"].avg, meters["loss"].avg, meters["act"].avg, meters["flops"].avg,
+            (dens_sum / n).numpy())
+
+
+def _validate_worker(rank, world, port, q):
+    import types
+    from laudnet_b200.validate import SparsityCriterion_bounds, validate
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(100 + rank)
+        batches = [(torch.randn(bs, 3, 4, 4, generator=g), torch.randint(0, 7, (bs,), generator=g)) for bs in (6, 6, 3)]
+        model = _FakeLaud()
+        args = types.SimpleNamespace(device="cpu", t_last=0.01, lambda_act=0.1, sparse=True, use_cuda_graph=False)
+        crit = torch.nn.CrossEntropyLoss()
+        sc = SparsityCriterion_bounds(0.5, 100, 4.1)
+        got = validate(batches, model, crit, sc, args, epoch=40)
+        want = _reference_validate_restated(batches, model, crit, sc, args, 40, world)
+        ok = all(abs(a - b) <= 1e-5 * max(1.0, abs(b)) for a, b in zip(got[:5], want[:5]))
+        ok_d = bool(np.allclose(got[5], want[5], rtol=1e-6, atol=1e-7)) and got[5].shape == (4, 8)
+        red = validate(batches, model, crit, sc, args, epoch=40, reduce_density=True)[5]
+        q.put((rank, ok, ok_d, red.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_validate_matches_reference_loop_gloo_world2():
+    """laudnet_b200.validate.validate (one all-reduce at the end) == the reference's per-batch all-reduce loop, on two
+    gloo ranks with different data; reduce_density=True gives both ranks the same rank-averaged densities."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_validate_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r[:3] for r in res] == [(0, True, True), (1, True, True)]
+    assert np.allclose(res[0][3], res[1][3])
