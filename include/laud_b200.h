@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define LAUD_ABI_VERSION 3
+#define LAUD_ABI_VERSION 4
 
 enum {
   LAUD_OK = 0,
@@ -220,6 +220,18 @@ typedef struct laud_conv_desc {
                                if its accumulator were 0, i.e. the BN constant shift[o] (then ReLU) - the same values
                                the gathered path reproduces through the H1 constants.  Exclusive with n_idx / k_idx. */
   int32_t n_mask_gran;
+  int32_t n_expand;         /* with n_idx (and no k_idx): CHANNEL SKIPPING WITH A DENSE RESULT.  Only the sample's ACTIVE
+                               output channels are computed - their weight rows are gathered by the TMA unit
+                               (cp.async.bulk.tensor ... tile::gather4 over w, four rows per instruction, indices from
+                               n_idx) so the tcgen05 MMAs run over N = 2*n_cnt[b] columns instead of C_out - and the
+                               epilogue EXPANDS them to their real positions of a dense row y[b,p,0:C_out]; a gated
+                               channel is written as its BN constant shift[o] (then ReLU), exactly what n_mask
+                               produces with every MMA executed (reference laud_resnet.py:123-126: conv -> x mask ->
+                               bn -> relu).  The consumer therefore reads ordinary dense activations and keeps shared
+                               weights.  Needs: 3x3, stride 1, pad 1, W_out + 2 <= 128, even n_gran, scale/shift,
+                               relu_mode NONE | ALL, no residual / out_mask / lists; n_idx rows hold ALL group ids
+                               (active ascending, then inactive - the layout the maskers emit), n_ld == C_out/n_gran.
+                               Anything else returns LAUD_E_UNSUPPORTED. */
 } laud_conv_desc;
 
 int laud_conv_forward(const laud_conv_desc* desc /* host */, int impl, void* stream);

@@ -88,7 +88,7 @@ def run_conv(x, w, y, B, H_in, W_in, C_in, H_out, W_out, C_out, ksize, stride, p
              pre_bias=None, pre_bias_classes=0, pre_bias_ld=0, out_mask=None, mask_groups=1,
              sample_idx=None, sample_cnt=None, row_idx=None, row_cnt=None, n_pad_align=0,
              impl=_lib.CONV_AUTO, tag="conv", w_t=None, bias_t=None, bias_ld=0, n_mask=None, n_mask_gran=1,
-             gap_partial=None, gap_tiles=0) -> None:
+             gap_partial=None, gap_tiles=0, n_expand=0) -> None:
     """Fill a laud_conv_desc and enqueue laud_conv_forward on the current stream."""
     d = ConvDesc()
     d.x, d.ldx = ptr(x), ldx if ldx is not None else x.shape[-1]
@@ -113,6 +113,7 @@ def run_conv(x, w, y, B, H_in, W_in, C_in, H_out, W_out, C_out, ksize, stride, p
     d.w_t = ptr(w_t)
     d.bias_t, d.bias_ld = ptr(bias_t), bias_ld
     d.n_mask, d.n_mask_gran = ptr(n_mask), n_mask_gran
+    d.n_expand = n_expand
     if conv_tags is not None:
         conv_tags.append(tag)
     prof = conv_profile.active
@@ -213,8 +214,12 @@ class ResNetEngine:
         self.impl = _lib.CONV_AUTO
         # How a channel-gated block executes (both reproduce laud_resnet.py:115-126 exactly):
         #   "sparse": gathered GEMMs over the active channels only + H1 constants (compact a1 / a2);
-        #   "dense" : masked-dense - weights shared by all samples, gated channels emitted as their BN constant.
-        self.channel_exec = os.environ.get("LAUD_CHANNEL_EXEC", "dense")     # measured faster at every ResNet-101 stage (profiles/)
+        #   "dense" : masked-dense - weights shared by all samples, gated channels emitted as their BN constant;
+        #   "nskip" : as "dense", but the 3x3 convolutions compute only the sample's ACTIVE output channels: their weight
+        #             rows arrive by TMA gather4, the MMAs run over N = active columns, the epilogue expands them to dense
+        #             rows with the BN constants of the gated channels (laud_conv_desc.n_expand) - the consumer still reads
+        #             ordinary dense activations with shared weights.
+        self.channel_exec = os.environ.get("LAUD_CHANNEL_EXEC", "dense")     # measured (profiles/)
         # How a layer-gated block executes: "skip" = the convolutions run only on the device-side list of ACTIVE samples
         # and the block output is written in place over the block input (skipped samples are untouched: relu(identity)
         # == identity bit-exactly, laud_resnet.py:133-144); "mask" = masked-dense (compute all, zero the gated rows).
@@ -389,7 +394,7 @@ class ResNetEngine:
             else:
                 blk.masker_channel.gate_nhwc(x[:B * Hi * Hi * p.inplanes].view(B, Hi, Hi, p.inplanes), counts[0:1],
                                              out=gate, partial_ws=ws["partial"])
-            dense_gate = self.channel_exec == "dense"
+            dense_gate = self.channel_exec in ("dense", "nskip")
             if not dense_gate:
                 # H1 constants: 0/1 indicator of the masked channels -> one dense GEMM -> fold taps into border classes
                 use_wt = p.krows_ok and self.impl in (_lib.CONV_AUTO, _lib.CONV_UMMA)
@@ -465,7 +470,14 @@ class ResNetEngine:
         run_conv(x, p.w1, a1, B, Hi, Hi, p.inplanes, Hi, Hi, p.width, 1, 1, 0, ldx=p.inplanes, ldy=ld12,
                  scale=p.s1, shift=p.t1, relu=_lib.RELU_ALL, impl=self.impl, tag=f"s{p.stage + 1}.conv1", **cn, **nm, **sl)
         # conv2 3x3/stride (+ mask) + bn2 + relu     laud_resnet.py:123-126
-        run_conv(a1, p.w2, a2, B, Hi, Hi, p.width, Ho, Ho, p.width, 3, p.stride, 1, ldx=ld12, ldy=ld12,
+        if (dense_gate and self.channel_exec == "nskip" and p.stride == 1 and Ho + 2 <= 128 and p.gran % 2 == 0
+                and p.width >= 128 and self.impl in (_lib.CONV_AUTO, _lib.CONV_UMMA) and not sl):
+            # channel skipping with a dense result: active weight rows by TMA gather4, N = active columns, expanded rows
+            run_conv(a1, p.w2, a2, B, Hi, Hi, p.width, Ho, Ho, p.width, 3, 1, 1, ldx=p.width, ldy=p.width,
+                     scale=p.s2, shift=p.t2, relu=_lib.RELU_ALL, impl=self.impl, tag=f"s{p.stage + 1}.conv2",
+                     n_idx=gate.idx, n_cnt=gate.cnt, n_gran=p.gran, n_pad_align=16, n_expand=1)
+        else:
+          run_conv(a1, p.w2, a2, B, Hi, Hi, p.width, Ho, Ho, p.width, 3, p.stride, 1, ldx=ld12, ldy=ld12,
                  scale=p.s2, shift=p.t2, relu=_lib.RELU_ALL, impl=self.impl, tag=f"s{p.stage + 1}.conv2",
                  pre_bias=ws["pb2"] if (sparse_gate and not use_wt) else None,
                  pre_bias_classes=16 if (sparse_gate and not use_wt) else 0,
@@ -524,7 +536,7 @@ class ResNetEngine:
                 return False             # conv_linear pools relu(bn(conv(x))), not x: it must read the activations
         if os.environ.get("LAUD_CONV_V3") or os.environ.get("LAUD_NO_FLAT") or os.environ.get("LAUD_NO_DMA"):
             return False                 # A/B switches that take conv3 off the flat slab path of the TMA-staged kernel
-        if p.use_s or (p.use_c and self.channel_exec != "dense") or self.impl not in (_lib.CONV_AUTO, _lib.CONV_UMMA):
+        if p.use_s or (p.use_c and self.channel_exec not in ("dense", "nskip")) or self.impl not in (_lib.CONV_AUTO, _lib.CONV_UMMA):
             return False
         return p.outplanes % 64 == 0 and p.H_out * p.H_out >= 43
 

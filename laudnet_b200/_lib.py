@@ -46,6 +46,7 @@ class ConvDesc(C.Structure):
         ("w_t", _vp),
         ("bias_t", _vp), ("bias_ld", C.c_int32),
         ("n_mask", _vp), ("n_mask_gran", C.c_int32),
+        ("n_expand", C.c_int32),
     ]
 
 

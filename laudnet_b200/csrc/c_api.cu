@@ -147,6 +147,14 @@ extern "C" int laud_conv_forward(const laud_conv_desc* d, int impl, void* stream
   if (d->n_mask)
     LAUD_REQUIRE(!d->n_idx && !d->k_idx && !d->pre_bias && d->n_mask_gran >= 1 && d->C_out % d->n_mask_gran == 0,
                  "laud_conv_forward: n_mask (masked-dense gate) excludes n_idx / k_idx / pre_bias and needs C_out %% n_mask_gran == 0");
+  if (d->n_expand) {
+    LAUD_REQUIRE(d->n_idx && d->n_cnt && !d->k_idx && !d->residual && !d->out_mask && !d->sample_idx && !d->row_idx &&
+                     !d->pre_bias && !d->bias_t && !d->gap_partial && d->scale && (d->n_gran & 1) == 0 &&
+                     d->relu_mode != LAUD_RELU_WHERE_GATE0 && d->ldy >= d->C_out,
+                 "laud_conv_forward: n_expand needs n_idx/n_cnt with an even granularity, scale/shift, ldy >= C_out and excludes "
+                 "k_idx / residual / out_mask / lists / pre_bias / bias_t / gap_partial");
+    LAUD_REQUIRE(impl == LAUD_CONV_AUTO || impl == LAUD_CONV_UMMA, "laud_conv_forward: n_expand is a tcgen05-path argument");
+  }
   if (d->w_t && d->k_idx)
     LAUD_REQUIRE(impl == LAUD_CONV_AUTO || impl == LAUD_CONV_UMMA,
                  "laud_conv_forward: w_t (K-row-gather path, real-channel pre_bias) is a tcgen05-path argument");
@@ -171,6 +179,7 @@ extern "C" int laud_conv_forward(const laud_conv_desc* d, int impl, void* stream
   a.wt = (const __half*)d->w_t;
   a.bias_t = (const __half*)d->bias_t; a.bias_ld = d->bias_ld;
   a.n_mask = d->n_mask; a.n_mask_gran = d->n_mask_gran;
+  a.n_expand = d->n_expand;
   a.gap_hw = 0;
 
   cudaStream_t s = (cudaStream_t)stream;
@@ -188,6 +197,11 @@ extern "C" int laud_conv_forward(const laud_conv_desc* d, int impl, void* stream
       }
       if (a.gap_partial) {
         set_error("laud_conv_forward: fused GAP (gap_partial) is only available on the TMA-staged kernel");
+        return LAUD_E_UNSUPPORTED;
+      }
+      if (a.n_expand) {
+        set_error("laud_conv_forward: n_expand (gather4 channel skipping) needs a 3x3 stride-1 layer with W_out + 2 <= 128 on the "
+                  "TMA-staged kernel");
         return LAUD_E_UNSUPPORTED;
       }
       return conv_forward_umma(a, s);

@@ -63,9 +63,12 @@ constexpr int MAX_RING = 3;
 constexpr int BN_MAX = 256;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr int SMEM_LIMIT = 232448;
+constexpr int XW_MAX = 512;                      // OUT_EXPAND: channel pairs of a dense row (C_out <= 1024)
+constexpr int G4_BN = 192;                       // gather4 path: compact columns per n-tile (a 24 KB stage; typical active
+                                                 // counts of a 256-channel layer at density 0.6 fit one tile)
 
-enum { BMODE_TMA = 0, BMODE_ROWS = 1, BMODE_KROWS = 2 };
-enum { OUT_SLAB = 0, OUT_ROWS = 1, OUT_DIRECT = 2 };
+enum { BMODE_TMA = 0, BMODE_ROWS = 1, BMODE_KROWS = 2, BMODE_G4 = 3 };   // G4: active weight rows by TMA tile::gather4
+enum { OUT_SLAB = 0, OUT_ROWS = 1, OUT_DIRECT = 2, OUT_EXPAND = 3 };     // EXPAND: compact columns -> dense rows + BN constants
 
 // Optional in-kernel lap timers (-DLAUD_KPROF, scripts/kprof.py): cycles each warp role spends per phase.
 #ifdef LAUD_KPROF
@@ -101,6 +104,10 @@ struct alignas(16) Tables {
   unsigned long long sready[2][MAX_RING], sfree[2][MAX_RING];   // slab hand-off between the epilogue halves and their DMA threads
   unsigned long long gdone[2][MAX_RING];    // fused GAP: the pooling warps have read the slab
   uint32_t tmem_base;
+  // OUT_EXPAND: per sample, for every 32-bit word (channel pair) of a dense output row: the word of the compact
+  // staging row that holds it, or -1 = gated -> the BN constant pair cw
+  short wsrc[XW_MAX];
+  uint32_t cw[XW_MAX];
 };
 
 struct Plan {              // host-computed launch geometry
@@ -111,7 +118,8 @@ struct Plan {              // host-computed launch geometry
   int rows_per_tile;       // pixels of a full m-tile: 128 (1x1) or R*W_out
   int nbuf, acc_cols;      // accumulator buffers; TMEM columns of one accumulator
   int ring;                // slabs per half (OUT_SLAB)
-  int stg_pitch, stg_rows; // OUT_ROWS: bytes per staging row (multiple of 128), rows
+  int stg_pitch, stg_rows; // OUT_ROWS / OUT_EXPAND: bytes per staging row, rows
+  int stg_bytes;           // bytes of the slab rings / row staging in front of the tables
   int full_count;          // arrivals that complete a stage
   int a_tx, b_tx, r_tx;    // bytes one A-tile / B-tile / residual-slab TMA copy delivers
   int cnt_cached;          // 1: Tables::kcnt / ncnt hold k_cnt / n_cnt of every sample
@@ -147,14 +155,17 @@ struct Sub {               // one (sample, m-group, n-tile) unit of work
 //   4: as 1 with residual + ReLU and no pixel gate (conv3)   5: as 1 without residual / ReLU / gate (downsample)
 template <int SPEC>
 struct Mode {
+//   6: channel skipping with a dense result (n_expand): halo tiles, the sample's ACTIVE weight rows by TMA gather4,
+//      compact accumulator columns expanded to dense rows in the epilogue
   static constexpr bool SLAB_FIXED = SPEC == 4 || SPEC == 5;
-  static __device__ __forceinline__ int bmode(const Plan& pl) { return SPEC == 0 ? pl.bmode : (int)BMODE_TMA; }
+  static constexpr bool G4 = SPEC == 6;
+  static __device__ __forceinline__ int bmode(const Plan& pl) { return SPEC == 0 ? pl.bmode : (G4 ? (int)BMODE_G4 : (int)BMODE_TMA); }
   static __device__ __forceinline__ int omode(const Plan& pl) {
-    return SPEC == 0 ? pl.omode : ((SPEC == 1 || SLAB_FIXED) ? (int)OUT_SLAB : (int)OUT_DIRECT);
+    return SPEC == 0 ? pl.omode : (G4 ? (int)OUT_EXPAND : ((SPEC == 1 || SLAB_FIXED) ? (int)OUT_SLAB : (int)OUT_DIRECT));
   }
-  static __device__ __forceinline__ bool halo(const Plan& pl) { return SPEC == 0 ? pl.halo != 0 : SPEC == 3; }
+  static __device__ __forceinline__ bool halo(const Plan& pl) { return SPEC == 0 ? pl.halo != 0 : (SPEC == 3 || G4); }
   static __device__ __forceinline__ bool dma(const Plan& pl) { return SPEC == 0 ? pl.dma != 0 : (SPEC == 1 || SLAB_FIXED); }
-  static __device__ __forceinline__ bool simple(const Plan& pl) { return SPEC == 0 ? pl.simple != 0 : true; }
+  static __device__ __forceinline__ bool simple(const Plan& pl) { return SPEC == 0 ? pl.simple != 0 : !G4; }
   static __device__ __forceinline__ bool has_res(const ConvArgs& a) { return SLAB_FIXED ? SPEC == 4 : a.residual != nullptr; }
   static __device__ __forceinline__ int relu_mode(const ConvArgs& a) {
     return SLAB_FIXED ? (SPEC == 4 ? (int)LAUD_RELU_ALL : (int)LAUD_RELU_NONE) : a.relu_mode;
@@ -223,7 +234,8 @@ __device__ __forceinline__ bool decode_sub(const ConvArgs& a, const Plan& pl, co
   s.Nc = a.n_idx ? (pl.cnt_cached ? T.ncnt[s.b] : __ldg(a.n_cnt + s.b)) * a.n_gran : a.C_out;
   s.Nfill = round_up(s.Nc, a.n_pad_align);
   // KROWS tiles span REAL output channels (the epilogue compacts); the others span the stored row
-  const int span = (M::bmode(pl) == BMODE_KROWS) ? a.C_out : s.Nfill;
+  // (gather4 path: a sample without any active channel still gets one 16-column tile - its rows are all constants)
+  const int span = (M::bmode(pl) == BMODE_KROWS) ? a.C_out : (M::bmode(pl) == BMODE_G4 ? max(s.Nfill, 16) : s.Nfill);
   s.n0 = s.nt * pl.BN;
   if (s.n0 >= span) return false;
   s.n_valid = min(pl.BN, span - s.n0);
@@ -320,6 +332,7 @@ __device__ __forceinline__ void column_entry(const ConvArgs& a, const Plan& pl, 
       }
     } else if (jj < s.Nc) {
       o = a.n_idx ? __ldg(a.n_idx + (size_t)s.b * a.n_ld + jj / a.n_gran) * a.n_gran + jj % a.n_gran : jj;
+      pos = o;
     }
   }
   sc = o >= 0 ? 1.f : 0.f;                                       // inactive / pad columns come out as exact zeros
@@ -413,8 +426,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
   unsigned char* stg = smem + pl.a_region_bytes + (size_t)pl.stages * pl.stage_bytes;   // slab rings / row staging (1024-aligned)
-  const int stg_bytes = M::omode(pl) == OUT_SLAB ? 2 * pl.ring * SLAB_BYTES : (M::omode(pl) == OUT_ROWS ? pl.stg_rows * pl.stg_pitch : 0);
-  Tables& T = *reinterpret_cast<Tables*>(stg + stg_bytes);
+  Tables& T = *reinterpret_cast<Tables*>(stg + pl.stg_bytes);
   const uint32_t a_base = smem_u32(smem);                           // halo mode: two activation slots in front of the stages
   const uint32_t smem_base = a_base + pl.a_region_bytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -483,6 +495,66 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
 
   if (warp == TMA_WARP) {
     // =========================================================== TMA producer
+    if (M::bmode(pl) == BMODE_G4) {
+      // ---- channel skipping: the WHOLE warp produces.  Lane 0 stages the activation tiles (halo mode, as below); every
+      //      lane issues the tile::gather4 copies of its four-row groups of the sample's ACTIVE weight rows: group j of
+      //      a stage lands at byte j * 512 of the B tile - rows 4j .. 4j+3 of a K-major SWIZZLE_128B tile (the swizzle
+      //      is a function of the shared-memory address, measured: scripts/mma_rate.cu, profiles/r02b_mma_rate.txt).
+      int stage = 0;
+      uint32_t phase = 0;
+      Walker wa;
+      walker_init(a, pl, wa);
+      Sub sa;
+      bool a_more = walker_next<M>(a, pl, T, wa, sa);
+      int a_kq = 0, a_next = 0, g = 0;
+      auto issue_a = [&]() {                                       // (all lanes keep the same cursor state)
+        const int slot = a_next & 1;
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&T.afull[slot], (uint32_t)pl.a_tx);
+          tma_load_4d(a_base + slot * pl.a_slot_bytes, &map_a, &T.afull[slot], a_kq * 64, -1, (sa.mt0) * pl.R - 1, sa.b);
+        }
+        ++a_next;
+        if (++a_kq >= sa.cpt) {
+          a_kq = 0;
+          a_more = walker_next<M>(a, pl, T, wa, sa);
+        }
+      };
+      while (walker_next<M>(a, pl, T, wk, s)) {
+        // this lane's weight rows for the sub-item: compact columns n0 + 4 (32 q + lane) + e, e < 4, q < 2
+        const int real = max(0, min(s.Nc - s.n0, pl.BN));            // active columns of this tile
+        const int ngath = (real + 3) >> 2;                           // gather4 copies per stage
+        int rows[2][4];
+#pragma unroll
+        for (int q2 = 0; q2 < 2; ++q2)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int jj = s.n0 + 4 * (32 * q2 + lane) + e;
+            rows[q2][e] = jj < s.Nc ? __ldg(a.n_idx + (size_t)s.b * a.n_ld + jj / a.n_gran) * a.n_gran + jj % a.n_gran : 0;
+          }
+        const uint32_t tx = (uint32_t)ngath * 512u;
+        for (int kq = 0; kq < s.cpt; ++kq, ++g) {
+          while (a_more && a_next <= g) {                            // the tile this chunk's MMAs read: must be on its way
+            mbar_wait(&T.aempty[a_next & 1], (uint32_t)((a_next >> 1) & 1) ^ 1u);
+            issue_a();
+          }
+          for (int tap = 0; tap < taps; ++tap) {
+            if (a_more && a_next == g + 1) {                         // next chunk's tile as soon as its slot is free
+              const uint32_t ok = mbar_try(smem_u32(&T.aempty[a_next & 1]), (uint32_t)((a_next >> 1) & 1) ^ 1u);
+              if (__shfl_sync(0xffffffffu, ok, 0)) issue_a();
+            }
+            mbar_wait(&T.empty[stage], phase ^ 1);
+            if (lane == 0) mbar_arrive_expect_tx(&T.full[stage], tx);
+            __syncwarp();
+            const uint32_t Bs = smem_base + stage * pl.stage_bytes;
+            const int col = tap * a.C_in + kq * 64;
+            if (lane < ngath) tma_gather4(Bs + (uint32_t)lane * 512u, &map_b, &T.full[stage], col, rows[0][0], rows[0][1], rows[0][2], rows[0][3]);
+            if (32 + lane < ngath)
+              tma_gather4(Bs + (uint32_t)(32 + lane) * 512u, &map_b, &T.full[stage], col, rows[1][0], rows[1][1], rows[1][2], rows[1][3]);
+            if (++stage == pl.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    } else
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -912,9 +984,28 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
       column_entry<M>(a, pl, nx, et, sc, sh, pos);
       T.scale[0][et] = sc; T.shift[0][et] = sh; T.cpos[0][et] = pos;
     }
+    int xb = -1;                                                 // OUT_EXPAND: sample whose expansion tables are built
     while (more) {
       s = nx;
       if (dyn_cols) named_bar_sync(2, EPI_THREADS);   // tables[par] are complete; nobody still reads tables[par ^ 1]
+      if (M::omode(pl) == OUT_EXPAND && s.b != xb) {
+        // dense word (channel pair) -> compact staging word, or the BN constant of a gated pair.  n_idx rows list every
+        // group once (active ascending, then inactive); the previous sample's flush ended with a barrier of all epilogue
+        // threads, and the flush that reads these tables starts with one.
+        const int hw2 = a.n_gran >> 1, cnt = s.Nc / a.n_gran;
+        for (int j = et; j < a.n_ld; j += EPI_THREADS) {
+          const int grp = __ldg(a.n_idx + (size_t)s.b * a.n_ld + j);
+          for (int t = 0; t < hw2; ++t) {
+            const int w = grp * hw2 + t;
+            float c0 = __ldg(a.shift + 2 * w), c1 = __ldg(a.shift + 2 * w + 1);
+            if (relu_all) { c0 = fmaxf(c0, 0.f); c1 = fmaxf(c1, 0.f); }
+            const __half2 hc = __floats2half2_rn(c0, c1);
+            T.wsrc[w] = j < cnt ? (short)(j * hw2 + t) : (short)-1;
+            T.cw[w] = *reinterpret_cast<const uint32_t*>(&hc);
+          }
+        }
+        xb = s.b;
+      }
       more = walker_next<M>(a, pl, T, wk, nx);
       float nsc = 0.f, nsh = 0.f;
       int npos = -1;
@@ -1081,6 +1172,65 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
             }
           }
           KP_LAP(4);
+        } else if (M::omode(pl) == OUT_EXPAND) {
+          // ---- OUT_EXPAND: the accumulator columns are the sample's ACTIVE channels in ascending order.  Stage them
+          //      compactly (fp16, folded BN + ReLU applied), then flush DENSE rows: every channel pair of the row comes
+          //      from its compact word or, where gated, is the BN constant - coalesced 128-byte stores.
+          const uint32_t srow = smem_u32(stg) + (uint32_t)prow * (uint32_t)pl.stg_pitch;
+          for (int c0 = h * 32; c0 < s.n_valid; c0 += 64) {
+            float v[32];
+            tmem_ld32(tbase + m * pl.acc_cols + c0, v);
+            if (pvalid) {
+#pragma unroll
+              for (int g4 = 0; g4 < 4; ++g4) {
+                if (c0 + g4 * 8 < s.n_valid) {
+                  const float4 s0 = lds_f4(t_scale + (uint32_t)(c0 + g4 * 8) * 4u);
+                  const float4 s1 = lds_f4(t_scale + (uint32_t)(c0 + g4 * 8 + 4) * 4u);
+                  const float4 h0 = lds_f4(t_shift + (uint32_t)(c0 + g4 * 8) * 4u);
+                  const float4 h1 = lds_f4(t_shift + (uint32_t)(c0 + g4 * 8 + 4) * 4u);
+                  float* w = v + g4 * 8;
+                  w[0] = fmaf(w[0], s0.x, h0.x); w[1] = fmaf(w[1], s0.y, h0.y);
+                  w[2] = fmaf(w[2], s0.z, h0.z); w[3] = fmaf(w[3], s0.w, h0.w);
+                  w[4] = fmaf(w[4], s1.x, h1.x); w[5] = fmaf(w[5], s1.y, h1.y);
+                  w[6] = fmaf(w[6], s1.z, h1.z); w[7] = fmaf(w[7], s1.w, h1.w);
+                  uint4 o4;
+                  __half2* oh = reinterpret_cast<__half2*>(&o4);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(w[2 * e], w[2 * e + 1]);
+                  if (relu_all) {
+                    const __half2 z = __float2half2_rn(0.f);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) oh[e] = __hmax2(oh[e], z);
+                  }
+                  sts128(srow + (uint32_t)(c0 + g4 * 8) * 2u, o4);          // column c of THIS n-tile
+                }
+              }
+            }
+          }
+          KP_LAP(4);
+          if (m == s.mt_cnt - 1) {                               // accumulators drained: the next sub-item's MMAs overlap the flush
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&T.tempty[buf]);
+          }
+          // flush this n-tile's share of the dense rows: the words whose compact position lies in [n0, n0 + n_valid) and,
+          // with the sample's first n-tile, the BN constants of every gated pair
+          named_bar_sync(5, EPI_THREADS);
+          {
+            const int nw = a.C_out >> 1, klo = s.n0 >> 1, khi = (s.n0 + s.n_valid) >> 1;
+            const bool consts = s.n0 == 0;
+            for (int r = warp; r < rows; r += EPI_WARPS) {
+              const uint32_t src = smem_u32(stg) + (uint32_t)r * (uint32_t)pl.stg_pitch;
+              uint32_t* dst = reinterpret_cast<uint32_t*>(a.y + ((size_t)s.b * HWo + m0 + r) * a.ldy);
+              for (int w = lane; w < nw; w += 32) {
+                const int k = T.wsrc[w];
+                if (k >= klo && k < khi) dst[w] = lds_u1(src + (uint32_t)(k - klo) * 4u);
+                else if (k < 0 && consts) dst[w] = T.cw[w];
+              }
+            }
+          }
+          named_bar_sync(5, EPI_THREADS);                        // staging may be overwritten by the next tile
+          KP_LAP(5);
         } else {
           // ---- OUT_ROWS: compact the active real channels of this pixel row into the staging row
           const uint32_t srow = smem_u32(stg) + (uint32_t)row * (uint32_t)pl.stg_pitch;
@@ -1131,7 +1281,8 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
       KP_LAP(0);                                                 // loop exit
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&T.tempty[buf]);                // accumulators drained: the MMA warp may reuse them
+      if (lane == 0 && M::omode(pl) != OUT_EXPAND) mbar_arrive(&T.tempty[buf]);   // accumulators drained: the MMA warp may reuse them
+                                                                 // (OUT_EXPAND arrived before its last flush)
       KP_LAP(7);                                                 // fence + arrive
       if (++buf == pl.nbuf) { buf = 0; bphase ^= 1; }
       par ^= 1;
@@ -1221,6 +1372,10 @@ bool conv_tma_supported(const ConvArgs& a) {
   if (a.k_idx && !(a.wt && aligned16(a.wt))) return false;        // KUNITS layout
   if (a.k_idx && a.n_idx && (a.residual || a.out_mask || (a.n_gran & 1))) return false;
   if (a.n_idx && !a.k_idx && a.wt) return false;
+  if (a.n_expand && !(a.n_idx && !a.k_idx && a.ksize == 3 && a.stride == 1 && a.pad == 1 && a.W_out + 2 <= BM && a.scale &&
+                      !(a.n_gran & 1) && a.C_out <= 2 * XW_MAX && a.C_out % 8 == 0 && a.n_ld * a.n_gran == a.C_out &&
+                      a.ldy >= a.C_out && (a.ldy & 1) == 0 && a.relu_mode != LAUD_RELU_WHERE_GATE0 && !a.residual && !a.out_mask))
+    return false;
   if ((a.ksize == 3 || a.stride == 2) && a.W_out > BM) return false;
   if (a.ksize == 3 && a.stride == 1 && (a.H_in != a.H_out || a.W_in != a.W_out)) return false;
   if (a.k_idx && a.n_idx && round_up(a.C_out, 16) * 2 > 1024) return false;   // staging row
@@ -1270,6 +1425,7 @@ static int conv_forward_tma_x(const ConvArgs& a_in, cudaStream_t s, bool allow_r
     LAUD_CUDA(cudaFuncSetAttribute(conv_tma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     LAUD_CUDA(cudaFuncSetAttribute(conv_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     LAUD_CUDA(cudaFuncSetAttribute(conv_tma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    LAUD_CUDA(cudaFuncSetAttribute(conv_tma_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     vtab4_init_kernel<<<32, 256, 0, s>>>();
     if (int e = check_launch("vtab4_init_kernel")) return e;
     if (int e = finish_first_call_init(s, "conv_forward_tma")) return e;
@@ -1279,12 +1435,13 @@ static int conv_forward_tma_x(const ConvArgs& a_in, cudaStream_t s, bool allow_r
   Plan pl{};
   const int HWo = a.H_out * a.W_out;
   const int taps = a.ksize * a.ksize;
-  pl.bmode = a.k_idx ? BMODE_KROWS : (a.n_idx ? BMODE_ROWS : BMODE_TMA);
+  pl.bmode = a.k_idx ? BMODE_KROWS : (a.n_idx ? (a.n_expand ? BMODE_G4 : BMODE_ROWS) : BMODE_TMA);
   const long long ktotal = (long long)taps * a.C_in;
-  pl.omode = (a.k_idx && a.n_idx) ? OUT_ROWS : ((!a.residual && ktotal >= 512) ? OUT_DIRECT : OUT_SLAB);
+  pl.omode = a.n_expand ? OUT_EXPAND : ((a.k_idx && a.n_idx) ? OUT_ROWS : ((!a.residual && ktotal >= 512) ? OUT_DIRECT : OUT_SLAB));
   const bool row_tiles = a.ksize == 3 || a.stride == 2;   // m-tiles of whole output rows: 4-d boxes (im2col / subsampling by TMA)
   static const bool no_halo = getenv("LAUD_NO_HALO") != nullptr;
-  pl.halo = (!no_halo && a.ksize == 3 && a.stride == 1 && pl.bmode == BMODE_TMA && !a.bias_t && a.W_out + 2 <= BM) ? 1 : 0;
+  pl.halo = ((!no_halo || pl.bmode == BMODE_G4) && a.ksize == 3 && a.stride == 1 && (pl.bmode == BMODE_TMA || pl.bmode == BMODE_G4) &&
+             !a.bias_t && a.W_out + 2 <= BM) ? 1 : 0;
   pl.Wp = a.W_out + 2;
   {
     const char* e = getenv("LAUD_HALO_BO");
@@ -1306,7 +1463,13 @@ static int conv_forward_tma_x(const ConvArgs& a_in, cudaStream_t s, bool allow_r
   pl.MT = pl.n_mtiles >= 2 ? 2 : 1;
   const int nfill_max = round_up(a.C_out, a.n_pad_align);
   const int span = pl.bmode == BMODE_KROWS ? a.C_out : nfill_max;
-  if (pl.omode == OUT_ROWS) {
+  if (pl.omode == OUT_EXPAND) {
+    // compact columns in tiles of G4_BN: a sample's active count decides how many of its n-tiles exist (typically one);
+    // all n-tiles of an m-group run inside ONE item, so consecutive sub-items share the activation tiles in L2
+    pl.BN = span <= G4_BN ? round_up(span, 16) : G4_BN;
+    pl.NT = (span + pl.BN - 1) / pl.BN;
+    pl.NTI = pl.NT;                            // (every n-tile flushes its own columns: MT stays 2)
+  } else if (pl.omode == OUT_ROWS) {
     pl.BN = span <= BN_MAX ? round_up(span, 16) : BN_MAX;
     pl.NT = (span + pl.BN - 1) / pl.BN;
     pl.NTI = pl.NT;
@@ -1335,7 +1498,7 @@ static int conv_forward_tma_x(const ConvArgs& a_in, cudaStream_t s, bool allow_r
   pl.acc_cols = pl.BN <= 64 ? 64 : (pl.BN <= 128 ? 128 : 256);
   pl.nbuf = (int)TMEM_COLS / (pl.MT * pl.acc_cols);
   if (pl.nbuf > 4) pl.nbuf = 4;
-  const int b_bytes = pl.bmode == BMODE_KROWS ? ((pl.BN + 63) / 64) * 8192 : pl.BN * 128;
+  const int b_bytes = pl.bmode == BMODE_KROWS ? ((pl.BN + 63) / 64) * 8192 : round_up(pl.BN, 4) * 128;
   pl.b_off = pl.halo ? 0 : pl.MT * A_TILE_BYTES;
   pl.stage_bytes = pl.b_off + round_up(b_bytes, 1024);
   int halo_box_rows = 0;
@@ -1352,8 +1515,18 @@ static int conv_forward_tma_x(const ConvArgs& a_in, cudaStream_t s, bool allow_r
   pl.stg_pitch = round_up(round_up(nfill_max, 16) * 2, 128);
   pl.stg_rows = pl.rows_per_tile <= 64 ? 64 : BM;            // small images (7x7): half-height staging
   if (HWo < pl.stg_rows) pl.stg_rows = round_up(HWo, 32);
+  if (pl.omode == OUT_EXPAND) {
+    if (!pl.halo) {
+      set_error("conv_forward_tma: n_expand needs the halo layout (3x3 stride 1, W_out + 2 <= 128)");
+      return LAUD_E_UNSUPPORTED;
+    }
+    pl.stg_pitch = pl.BN * 2 + 16;                           // one n-tile's fp16 columns + 16 bytes: the 16-byte row stores
+    pl.stg_rows = round_up(pl.rows_per_tile, 8);             // of a warp's 32 lanes fall on distinct banks
+  }
   pl.cnt_cached = a.B <= CNT_CACHE ? 1 : 0;
-  const int stg_bytes = pl.omode == OUT_SLAB ? 2 * pl.ring * SLAB_BYTES : (pl.omode == OUT_ROWS ? pl.stg_rows * pl.stg_pitch : 0);
+  const int stg_bytes = pl.omode == OUT_SLAB ? 2 * pl.ring * SLAB_BYTES
+                                             : ((pl.omode == OUT_ROWS || pl.omode == OUT_EXPAND) ? round_up(pl.stg_rows * pl.stg_pitch, 1024) : 0);
+  pl.stg_bytes = stg_bytes;
   static const bool no_dma = getenv("LAUD_NO_DMA") != nullptr;
   pl.dma = (!no_dma && pl.omode == OUT_SLAB && pl.bmode == BMODE_TMA) ? 1 : 0;
   pl.NG = pl.NT / pl.NTI;
@@ -1384,7 +1557,7 @@ static int conv_forward_tma_x(const ConvArgs& a_in, cudaStream_t s, bool allow_r
   pl.c_cpt = (pl.c_nk16 + 3) >> 2;
   pl.c_nchunks = pl.c_cpt * taps;
   pl.flat = flat ? 1 : 0;
-  pl.static_cols = (pl.omode != OUT_ROWS && !a.n_idx && (!a.n_mask || allow_row_gate)) ? 1 : 0;
+  pl.static_cols = (pl.omode != OUT_ROWS && pl.omode != OUT_EXPAND && !a.n_idx && (!a.n_mask || allow_row_gate)) ? 1 : 0;
   pl.stab_cols = round_up(a.C_out, 64) + BN_MAX;              // reads of a partial last tile stay inside the (zero) padding
   int stab_bytes = pl.static_cols ? 2 * pl.stab_cols * 4 : 0;
   int avail = SMEM_LIMIT - 1024 - (int)sizeof(Tables) - stg_bytes - pl.a_region_bytes - stab_bytes - gap_bytes;
@@ -1408,9 +1581,10 @@ static int conv_forward_tma_x(const ConvArgs& a_in, cudaStream_t s, bool allow_r
   }
   if (pl.stages < 2) {
     if (pl.gap) { set_error("conv_forward_tma: no shared memory left for the fused GAP"); return LAUD_E_UNSUPPORTED; }
+    if (pl.omode == OUT_EXPAND) { set_error("conv_forward_tma: no shared memory left for the n_expand pipeline"); return LAUD_E_UNSUPPORTED; }
     return conv_forward_umma(a, s);
   }
-  pl.full_count = 1 + (pl.bmode == BMODE_TMA ? 0 : GATHER_THREADS);
+  pl.full_count = 1 + ((pl.bmode == BMODE_TMA || pl.bmode == BMODE_G4) ? 0 : GATHER_THREADS);
   const int rows_box = pl.rows_per_tile < HWo ? pl.rows_per_tile : HWo;     // boxes never exceed the tensor extent
   int bn_box = pl.BN < a.C_out ? pl.BN : a.C_out;
   static const bool dbg_halfb = getenv("LAUD_DBG") && (atoi(getenv("LAUD_DBG")) & 1);   // TIMING EXPERIMENT ONLY (wrong results): half of every weight tile
@@ -1443,6 +1617,11 @@ static int conv_forward_tma_x(const ConvArgs& a_in, cudaStream_t s, bool allow_r
     const long long str[1] = {(long long)taps * a.C_in};
     const int box[2] = {64, bn_box};
     ok = ok && make_map(&map_b, a.w, 2, dims, str, box);
+  } else if (pl.bmode == BMODE_G4) {            // tile::gather4: 2-d map, box {64 columns, 1 row}; four rows per copy
+    const long long dims[2] = {(long long)taps * a.C_in, a.C_out};
+    const long long str[1] = {(long long)taps * a.C_in};
+    const int box[2] = {64, 1};
+    ok = ok && make_map(&map_b, a.w, 2, dims, str, box);
   }
   if (pl.omode == OUT_SLAB) {
     const long long dims[3] = {a.ldy, HWo, a.B};
@@ -1456,7 +1635,7 @@ static int conv_forward_tma_x(const ConvArgs& a_in, cudaStream_t s, bool allow_r
     }
   }
   if (!ok) {                                     // the driver refused a descriptor: v3 takes every layout v4 does
-    if (pl.gap) { set_error("conv_forward_tma: tensor map refused"); return LAUD_E_UNSUPPORTED; }
+    if (pl.gap || pl.omode == OUT_EXPAND) { set_error("conv_forward_tma: tensor map refused"); return LAUD_E_UNSUPPORTED; }
     return conv_forward_umma(a, s);
   }
 
@@ -1477,6 +1656,7 @@ static int conv_forward_tma_x(const ConvArgs& a_in, cudaStream_t s, bool allow_r
       }
       else if (pl.omode == OUT_DIRECT) spec = pl.halo ? 3 : 2;
     }
+    if (pl.bmode == BMODE_G4) spec = 6;
     static const bool pdl = getenv("LAUD_PDL") != nullptr;   // opt-in: measured -2.5 % with the two graph chains (early CTAs of one chain sit on SMs the other chain could use), +0.8 % with one
     switch (spec) {
       case 1: launch_conv_tma<1>(grid, smem, s, pdl, a, pl, map_a, map_b, map_y, map_r); break;
@@ -1484,6 +1664,7 @@ static int conv_forward_tma_x(const ConvArgs& a_in, cudaStream_t s, bool allow_r
       case 3: launch_conv_tma<3>(grid, smem, s, pdl, a, pl, map_a, map_b, map_y, map_r); break;
       case 4: launch_conv_tma<4>(grid, smem, s, pdl, a, pl, map_a, map_b, map_y, map_r); break;
       case 5: launch_conv_tma<5>(grid, smem, s, pdl, a, pl, map_a, map_b, map_y, map_r); break;
+      case 6: launch_conv_tma<6>(grid, smem, s, pdl, a, pl, map_a, map_b, map_y, map_r); break;
       default: launch_conv_tma<0>(grid, smem, s, pdl, a, pl, map_a, map_b, map_y, map_r); break;
     }
   }

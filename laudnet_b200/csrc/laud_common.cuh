@@ -102,6 +102,7 @@ struct ConvArgs {
   const __half* wt;
   const __half* bias_t; int bias_ld;
   const uint8_t* n_mask; int n_mask_gran;
+  int n_expand;
   int gap_hw;               // internal: pixels per sample of the layer (set by the launcher when gap_partial is used)
 };
 

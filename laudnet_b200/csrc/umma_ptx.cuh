@@ -162,6 +162,16 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* map, unsig
       ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// TMA row gather: four rows r0..r3 of a 2-d tensor (box {cols, 1}), columns [col, col + box) each, land as four
+// consecutive box-rows at dst (sm_100a; measured: SWIZZLE_128B is applied by shared-memory ADDRESS, so groups of four
+// rows written at consecutive 512-byte offsets form a regular K-major swizzled tile).
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const void* map, unsigned long long* bar, int col, int r0, int r1,
+                                            int r2, int r3) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+      : "memory");
+}
 __device__ __forceinline__ void tma_store_3d(const void* map, uint32_t src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
                "r"(src), "r"(c0), "r"(c1), "r"(c2)

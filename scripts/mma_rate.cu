@@ -68,14 +68,6 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int iters, int 
 }
 
 // ---------------------------------------------------------------------------------------------------------- gather4
-__device__ __forceinline__ void tma_gather4(uint32_t dst, const void* map, unsigned long long* bar, int col, int r0, int r1, int r2,
-                                            int r3) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
-      : "memory");
-}
-
 __global__ void gather4_kernel(const __grid_constant__ CUtensorMap map, int r0, int r1, int r2, int r3, int col, int dst_off,
                                __half* out /* 1024 halfs = 2 KB */, int* status) {
   extern __shared__ unsigned char raw[];

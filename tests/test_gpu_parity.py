@@ -492,6 +492,67 @@ def test_conv_rejects_bad_arguments(cuda_lib):
         _engine.run_conv(x, w, y, 1, 4, 4, 16, 3, 3, 8, 1, 1, 0)
 
 
+# --------------------------------------------------------------------------- channel skipping with a dense result (n_expand)
+@pytest.mark.parametrize("B,H,C,gran,rates", [
+    (5, 14, 256, 2, (0.6, 0.0, 1.0, 0.95, 0.3)),        # stage-3 shape: typical, none, all, > 192 active (two n-tiles), few
+    (3, 7, 512, 2, (0.6, 0.9, 0.1)),                    # stage-4 shape: up to three n-tiles, one m-tile
+    (2, 28, 128, 2, (0.6, 0.5)),                        # stage-2 shape: 7 m-tiles of 4 rows
+    (2, 56, 64, 2, (0.6, 1.0)),                         # stage-1 shape: 2-row tiles
+    (3, 9, 48, 4, (0.5, 0.25, 0.75)),                   # ragged: C_out not a multiple of 64, granularity 4, odd map
+    (2, 6, 16, 2, (0.5, 0.0)),                          # tiny-net width
+])
+def test_conv_n_expand_equals_masked_dense_and_oracle(cuda_lib, B, H, C, gran, rates):
+    """laud_conv_desc.n_expand (3x3 stride 1): only the ACTIVE output channels are computed (weight rows by TMA gather4,
+    MMAs over N = active columns) and expanded to dense rows with the BN constants of the gated channels.  Must equal the
+    masked-dense execution (n_mask: every MMA executed) BIT FOR BIT - same products, same accumulation order - and the
+    oracle's conv -> x mask -> bn -> relu (laud_resnet.py:123-126) within ACT_TOL."""
+    gen = torch.Generator().manual_seed(B * 1000 + H * 10 + C + gran)
+    G = C // gran
+    x = torch.relu(torch.randn(B, C, H, H, generator=gen)).half().float()
+    w = (torch.randn(C, C, 3, 3, generator=gen) * (2.0 / (9 * C)) ** 0.5).half().float()
+    scale = torch.randn(C, generator=gen) * 0.2 + 1.0
+    shift = torch.randn(C, generator=gen) * 0.5
+    mask = torch.stack([(torch.rand(G, generator=gen) < r).float() if 0.0 < r < 1.0 else torch.full((G,), float(r))
+                        for r in rates])
+    ref = torch.relu(O.apply_channel_mask(F.conv2d(x, w, padding=1), mask) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    xd = x.permute(0, 2, 3, 1).contiguous().half().to(DEV)
+    wd = _engine.pack_conv_weight(w).to(DEV)
+    sc, sh = scale.to(DEV), shift.to(DEV)
+    m8 = mask.to(torch.uint8).to(DEV)
+    order = torch.argsort(1 - mask.to(torch.int32), dim=1, stable=True).to(torch.int32).to(DEV)     # actives first, ascending
+    cnt = mask.sum(dim=1).to(torch.int32).to(DEV)
+    y_dense = torch.full((B, H, H, C), float("nan"), dtype=torch.float16, device=DEV)
+    y_skip = torch.full((B, H, H, C), float("nan"), dtype=torch.float16, device=DEV)
+    n0 = cuda_lib.laud_conv_tma_launch_count()
+    _engine.run_conv(xd, wd, y_dense, B, H, H, C, H, H, C, 3, 1, 1, scale=sc, shift=sh, relu=_lib.RELU_ALL,
+                     n_mask=m8, n_mask_gran=gran)
+    _engine.run_conv(xd, wd, y_skip, B, H, H, C, H, H, C, 3, 1, 1, scale=sc, shift=sh, relu=_lib.RELU_ALL,
+                     n_idx=order, n_cnt=cnt, n_gran=gran, n_pad_align=16, n_expand=1)
+    torch.cuda.synchronize()
+    assert cuda_lib.laud_conv_tma_launch_count() == n0 + 2
+    assert torch.isfinite(y_skip.float()).all(), "unwritten (NaN) outputs"
+    assert torch.equal(y_skip, y_dense), f"max diff {(y_skip.float() - y_dense.float()).abs().max().item():.3e}"
+    assert _rel_err(y_skip.float().permute(0, 3, 1, 2), ref) <= ACT_TOL
+
+
+def test_conv_n_expand_rejects_what_it_cannot_take(cuda_lib):
+    B, H, C = 2, 8, 32
+    x = torch.zeros(B, H, H, C, dtype=torch.float16, device=DEV)
+    w = torch.zeros(C, 9, C, dtype=torch.float16, device=DEV)
+    y = torch.zeros(B, H // 2, H // 2, C, dtype=torch.float16, device=DEV)
+    sc = torch.ones(C, device=DEV)
+    idx = torch.arange(C // 2, dtype=torch.int32, device=DEV).repeat(B, 1)
+    cnt = torch.full((B,), C // 2, dtype=torch.int32, device=DEV)
+    with pytest.raises(_lib.LaudError):      # stride 2: no halo layout
+        _engine.run_conv(x, w, y, B, H, H, C, H // 2, H // 2, C, 3, 2, 1, scale=sc, shift=sc, relu=_lib.RELU_ALL,
+                         n_idx=idx, n_cnt=cnt, n_gran=2, n_pad_align=16, n_expand=1)
+    y1 = torch.zeros(B, H, H, C, dtype=torch.float16, device=DEV)
+    with pytest.raises(_lib.LaudError):      # odd granularity
+        _engine.run_conv(x, w, y1, B, H, H, C, H, H, C, 3, 1, 1, scale=sc, shift=sc, relu=_lib.RELU_ALL,
+                         n_idx=torch.arange(C, dtype=torch.int32, device=DEV).repeat(B, 1), n_cnt=cnt, n_gran=1,
+                         n_pad_align=16, n_expand=1)
+
+
 # --------------------------------------------------------------------------- network ends
 @pytest.mark.parametrize("B,size,C0", [(2, 224, 64), (3, 64, 16), (1, 96, 32), (2, 72, 64), (1, 64, 24)])
 def test_stem_vs_oracle(cuda_lib, B, size, C0):
@@ -572,15 +633,16 @@ def test_layer_skip_leaves_skipped_samples_bit_exact(cuda_lib):
 
 
 # --------------------------------------------------------------------------- whole networks vs the reference's golden outputs
-@pytest.mark.parametrize("channel_exec", ["sparse", "dense"])
+@pytest.mark.parametrize("channel_exec", ["sparse", "dense", "nskip"])
 @pytest.mark.parametrize("name", list(CASES))
 def test_network_free_running_vs_golden(cuda_lib, name, channel_exec):
     """Both executions of the channel gate (gathered GEMMs + H1 constants / masked-dense) against the reference."""
     cfg, sd, x, z = load_case(name)
-    if channel_exec == "dense" and not any(m in ("channel", "both") for m in cfg.dyn_mode):
+    if channel_exec != "sparse" and not any(m in ("channel", "both") for m in cfg.dyn_mode):
         pytest.skip("no channel gate in this configuration")
     model = _model(cfg, sd)
     model._engine.channel_exec = channel_exec
+    model._engine.nskip_min_width = 0            # (tiny widths: exercise the gather4 path)
     keep = []
     with torch.no_grad():
         logits, r3, r2, r1, rc, perc, flops = model(x.to(DEV), 1.0, keep=keep)
@@ -901,7 +963,7 @@ def test_headline_r101_channel_bs8_graphed_two_chains_vs_oracle(cuda_lib):
     assert m._engine.channel_exec in ("dense", "sparse", "auto")
 
 
-@pytest.mark.parametrize("channel_exec", ["sparse", "dense"])
+@pytest.mark.parametrize("channel_exec", ["sparse", "dense", "nskip"])
 def test_headline_r101_channel_bs8_both_executions_vs_oracle(cuda_lib, channel_exec):
     _bs8_vs_oracle("full_r101_channel", setup=lambda m: setattr(m._engine, "channel_exec", channel_exec))
 

@@ -104,7 +104,7 @@ def test_library_builds_and_exports_every_symbol():
     for name in _declared_symbols():
         assert hasattr(handle, name), f"{name} not exported"
     handle.laud_abi_version.restype = ctypes.c_int
-    assert handle.laud_abi_version() == 3       # pure host call, no device needed (LAUD_ABI_VERSION)
+    assert handle.laud_abi_version() == 4       # pure host call, no device needed (LAUD_ABI_VERSION)
     lib = _lib.lib()                            # binding sets argtypes for every symbol
     assert lib.laud_launch_count() == 0
 
