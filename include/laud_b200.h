@@ -150,6 +150,17 @@ int laud_compact_rows(const uint8_t* gate, int B, int g, int HW,
 int laud_layer_gate_lists(const uint8_t* gate /* [B] */, int B, int hw_out, int hw_in, int32_t* counts4,
                           int32_t* rows_out /* [B] */, int32_t* count_out /* [1] */, void* stream);
 
+/* (f4) Training-mode gate with SUPPLIED Gumbel noise.  Replaces
+ *   F.gumbel_softmax(logits.view(b,2,...), dim=1, tau=temperature, hard=True)[:, 0]
+ * of Masker_spatial / Masker_channel_MLP / Masker_channel_conv_linear.forward in training mode (models/utils.py:56-58,
+ * 123-125, 161-163) for a noise tensor given by the caller (torch's Philox stream cannot be reproduced in a kernel):
+ *   keep <=> (l_keep + g_keep) / tau >= (l_drop + g_drop) / tau        (ties keep, as argmax does)
+ * logits / noise fp32 [B, 2, G, inner] (the logits the maskers emit through their logits_out argument; noise may be
+ * NULL = the eval decision); mask_out u8 [B, G, inner]; for channel gates (inner == 1) idx_out [B, G] / cnt_out [B] in
+ * the maskers' layout (active ids ascending, then inactive); total_out += number of kept decisions. */
+int laud_gate_from_logits(const float* logits, const float* noise, int B, int G, int inner, float tau, uint8_t* mask_out,
+                          int32_t* idx_out, int32_t* cnt_out, int32_t* total_out, void* stream);
+
 /* ---------------------------------------------------------------------------
  * (a5-a7) the mask-conditioned convolution: implicit-GEMM conv (1x1 or 3x3)
  * + folded BatchNorm + mask + residual + ReLU, with per-sample channel

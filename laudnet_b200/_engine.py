@@ -358,8 +358,12 @@ class ResNetEngine:
     # ------------------------------------------------------------------ blocks
     def run_block(self, p: BlockPlan, x: torch.Tensor, out: torch.Tensor, idbuf: torch.Tensor, B: int, ws: dict,
                   keep: Optional[BlockOutputs] = None, forced_channel_mask: Optional[torch.Tensor] = None,
-                  forced_spatial_mask: Optional[torch.Tensor] = None, gap_in: bool = False, gap_out: bool = False) -> None:
+                  forced_spatial_mask: Optional[torch.Tensor] = None, gap_in: bool = False, gap_out: bool = False,
+                  noise=None, tau: float = 1.0) -> None:
         """x: fp16 [B,H_in,H_in,inplanes] -> out: fp16 [B,H_out,H_out,outplanes].
+        noise = (channel Gumbel sample [B,2G] | None, spatial [B,2g,S,S] | None): the gates take the reference's TRAINING
+        branch (hard Gumbel-softmax at temperature tau, utils.py:56-58,123-125) with the given samples; BatchNorm stays
+        in eval mode (the mmdet backbones' norm_eval configuration).
         gap_in: ws["gap"] holds the fused-GAP partial sums of x (left by the previous block's conv3): the channel
         masker decides from them instead of pooling x.  gap_out: conv3 leaves the partial sums of `out` there."""
         blk = p.module
@@ -379,21 +383,26 @@ class ResNetEngine:
             G = p.G
             gate = _ChannelGate(ws["cmask"].view(-1)[:B * G].view(B, G), ws["cidx"].view(-1)[:B * G].view(B, G),
                                 ws["ccnt"], None, None)
-            if keep is not None:
+            nz_c = noise[0] if noise is not None else None
+            if keep is not None or nz_c is not None:
                 gate.logits = torch.empty((B, 2 * G), dtype=torch.float32, device=x.device)
                 gate.pooled = torch.empty((B, x.shape[-1]), dtype=torch.float32, device=x.device)
+            ctot = counts[0:1] if nz_c is None else None         # (the Gumbel decision below does the counting)
             if forced_channel_mask is not None:
                 self._force_channel_gate(gate, forced_channel_mask, counts[0:1])
             elif gap_in:
-                blk.masker_channel.gate_from_partials(ws["gap"], B, Hi * Hi, p.inplanes, gap_tiles(Hi * Hi), counts[0:1], gate)
+                blk.masker_channel.gate_from_partials(ws["gap"], B, Hi * Hi, p.inplanes, gap_tiles(Hi * Hi), ctot, gate)
             elif p.masker_kind == "conv_linear":
                 # conv 1x1 + BN + ReLU at full resolution, then pool (utils.py:150-169): pre-packed weights, workspaces
-                blk.masker_channel.gate_nhwc(x[:B * Hi * Hi * p.inplanes].view(B, Hi, Hi, p.inplanes), counts[0:1],
+                blk.masker_channel.gate_nhwc(x[:B * Hi * Hi * p.inplanes].view(B, Hi, Hi, p.inplanes), ctot,
                                              out=gate, partial_ws=ws["partial"], impl=self.impl, z_ws=ws["mkz"],
                                              pooled_ws=ws["mkpool"])
             else:
-                blk.masker_channel.gate_nhwc(x[:B * Hi * Hi * p.inplanes].view(B, Hi, Hi, p.inplanes), counts[0:1],
+                blk.masker_channel.gate_nhwc(x[:B * Hi * Hi * p.inplanes].view(B, Hi, Hi, p.inplanes), ctot,
                                              out=gate, partial_ws=ws["partial"])
+            if nz_c is not None and forced_channel_mask is None:
+                from .utils import gate_from_logits
+                gate_from_logits(gate.logits, nz_c, tau, G, 1, gate.mask, gate.idx, gate.cnt, counts[0:1])
             dense_gate = self.channel_exec in ("dense", "nskip")
             if not dense_gate:
                 # H1 constants: 0/1 indicator of the masked channels -> one dense GEMM -> fold taps into border classes
@@ -417,7 +426,10 @@ class ResNetEngine:
                 counts[1:2].copy_(small.sum().to(torch.int32).view(1))
                 slog = None
             else:
-                slog = torch.empty((B, 2 * g, S, S), dtype=torch.float32, device=x.device) if keep is not None else None
+                nz_s = noise[1] if noise is not None else None
+                slog = (torch.empty((B, 2 * g, S, S), dtype=torch.float32, device=x.device)
+                        if (keep is not None or nz_s is not None) else None)
+                stot = counts[1:2] if nz_s is None else None
                 wt, wbias = blk.masker_spatial._weights()
                 if S == 1 and "lidx" in ws:
                     # one gate per sample (layer skip): global pool -> 2g-row linear -> keep>=drop is exactly the
@@ -425,11 +437,14 @@ class ResNetEngine:
                     check(L.laud_masker_channel_mlp(ptr(x), B, Hi * Hi, p.inplanes, 1, ptr(wt),
                                                     ptr(wbias), 0, None, None, g,
                                                     ptr(ws["partial"]), None, ptr(slog), ptr(small), ptr(ws["lidx"]),
-                                                    ptr(ws["lcnt"]), ptr(counts[1:2]), st), "laud_masker_channel_mlp")
+                                                    ptr(ws["lcnt"]), ptr(stot), st), "laud_masker_channel_mlp")
                 else:
                     check(L.laud_masker_spatial(ptr(x), B, Hi, Hi, p.inplanes, ptr(wt),
                                                 ptr(wbias), g, S, ptr(slog), ptr(small),
-                                                ptr(counts[1:2]), st), "laud_masker_spatial")
+                                                ptr(stot), st), "laud_masker_spatial")
+                if nz_s is not None:
+                    from .utils import gate_from_logits
+                    gate_from_logits(slog, nz_s, tau, g, S * S, small, total=counts[1:2])
             m3 = ws["m3"][:B * g * Ho * Ho].view(B, g, Ho, Ho)
             m2 = ws["m2"][:B * g * Ho * Ho].view(B, g, Ho, Ho)
             m1 = ws["m1"][:B * g * Hi * Hi].view(B, g, Hi, Hi)
@@ -553,15 +568,18 @@ class ResNetEngine:
 
     # ----------------------------------------------------------------- forward
     def forward(self, x: torch.Tensor, keep: Optional[List[BlockOutputs]] = None, slot: int = 0,
-                logits_out: Optional[torch.Tensor] = None, want_stats: bool = True, forced=None):
+                logits_out: Optional[torch.Tensor] = None, want_stats: bool = True, forced=None, gumbel_noise=None,
+                temperature: float = 1.0):
         """forced (tests): per block a pair (channel mask [B,G] | None, spatial mask [B,g,S,S] | None) installed
-        instead of the block's own gating decision - the teacher-forced network forward."""
+        instead of the block's own gating decision - the teacher-forced network forward.
+        gumbel_noise: per block a pair (channel sample [B,2G] | None, spatial sample [B,2g,S,S] | None): the gates take
+        the training branch (hard Gumbel-softmax at `temperature`) with these samples, BatchNorm in eval mode."""
         if x.device.type != "cuda":
             raise LaudError("ResNet.forward: expected a CUDA tensor - there is no CPU path")
         with torch.cuda.device(x.device):        # launches go to the current stream of the INPUT's device
-            return self._forward(x, keep, slot, logits_out, want_stats, forced)
+            return self._forward(x, keep, slot, logits_out, want_stats, forced, gumbel_noise, temperature)
 
-    def _forward(self, x, keep, slot, logits_out, want_stats, forced=None):
+    def _forward(self, x, keep, slot, logits_out, want_stats, forced=None, gumbel_noise=None, temperature=1.0):
         m = self.model
         if self.prepared_for != x.device:
             self.prepare()
@@ -594,7 +612,8 @@ class ResNetEngine:
             gap_out = self._gap_fusable(p)
             fc, fs = forced[p.index] if forced is not None else (None, None)
             res_buf = self.run_block(p, bufs[cur], bufs[nxt], bufs[idb], B, ws, ko, gap_in=gap_in, gap_out=gap_out,
-                                     forced_channel_mask=fc, forced_spatial_mask=fs)
+                                     forced_channel_mask=fc, forced_spatial_mask=fs,
+                                     noise=gumbel_noise[p.index] if gumbel_noise is not None else None, tau=temperature)
             gap_in = gap_out
             if nvtx:
                 torch.cuda.nvtx.range_pop()

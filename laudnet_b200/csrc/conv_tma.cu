@@ -716,7 +716,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
     __syncwarp();
   } else if (warp >= GATHER_WARP0) {
     // =========================================================== weight gather (cp.async)
-    if (M::bmode(pl) != BMODE_TMA) {
+    if (M::bmode(pl) == BMODE_ROWS || M::bmode(pl) == BMODE_KROWS) {
       const int pt = threadIdx.x - GATHER_WARP0 * 32;            // 0..191
       const int pw = pt >> 5;
       const int ac = pt & 7, ar0 = pt >> 3;                      // ROWS: 16-byte chunk, first row (rows ar0 + 24 i)

@@ -755,3 +755,83 @@ extern "C" int laud_compact_rows(const uint8_t* gate, int B, int g, int HW, int3
   compact_write_kernel<<<nblk, 256, 0, s>>>(gate, g, HW, n, block_ws, rows_out);
   return check_launch("compact_write_kernel");
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Training-mode gate with SUPPLIED Gumbel noise (reference utils.py:56-58, 123-125, 161-163):
+//   F.gumbel_softmax(logits.view(b, 2, ...), dim=1, tau, hard=True)[:, 0]
+// draws g ~ Gumbel(0,1) from torch's generator, forms y = softmax((logits + g) / tau) over the keep/drop pair and returns
+// the one-hot argmax (index 0 = keep wins ties).  A custom kernel cannot reproduce torch's Philox stream, so the noise is
+// an INPUT: given the same noise tensor the forward value of the gate is reproduced exactly:
+//   keep  <=>  (l_keep + g_keep) / tau  >=  (l_drop + g_drop) / tau        (fp32, the reference's operation order)
+// logits / noise: fp32 [B, 2, G, inner] (channel gates: inner = 1; spatial gates: inner = S*S).
+// One CTA per sample; with idx_out the active group ids are compacted in ascending order, then the inactive ones (the
+// layout the eval-mode maskers emit), cnt_out[b] = #active.  total_out += #active decisions (statistics counter).
+__global__ void __launch_bounds__(256) gate_from_logits_kernel(const float* __restrict__ logits, const float* __restrict__ noise,
+                                                               int G, int inner, float tau, uint8_t* __restrict__ mask_out,
+                                                               int* __restrict__ idx_out, int* __restrict__ cnt_out,
+                                                               int* __restrict__ total_out) {
+  __shared__ int s_warp[8];
+  __shared__ int s_base;
+  const int b = blockIdx.x, n = G * inner;
+  const float* lk = logits + (size_t)b * 2 * n;
+  const float* ld = lk + n;
+  const float* gk = noise ? noise + (size_t)b * 2 * n : nullptr;
+  const float* gd = gk ? gk + n : nullptr;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  int total = 0;
+  for (int i0 = 0; i0 < n; i0 += 256) {
+    const int i = i0 + threadIdx.x;
+    int keep = 0;
+    if (i < n) {
+      const float a = (lk[i] + (gk ? gk[i] : 0.f)) / tau, d = (ld[i] + (gd ? gd[i] : 0.f)) / tau;
+      keep = a >= d ? 1 : 0;
+      mask_out[(size_t)b * n + i] = (uint8_t)keep;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int before = s_base;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    if (idx_out && inner == 1 && keep) idx_out[(size_t)b * G + before + __popc(bal & ((1u << lane) - 1u))] = i;
+    int chunk = 0;
+    for (int w = 0; w < 8; ++w) chunk += s_warp[w];
+    total += chunk;
+    __syncthreads();
+    if (threadIdx.x == 0) s_base += chunk;
+    __syncthreads();
+  }
+  if (idx_out && inner == 1) {                       // inactive ids after the active ones, ascending
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += 256) {
+      const int i = i0 + threadIdx.x;
+      const int off = (i < n && mask_out[(size_t)b * n + i] == 0) ? 1 : 0;
+      const unsigned bal = __ballot_sync(0xffffffffu, off);
+      if (lane == 0) s_warp[warp] = __popc(bal);
+      __syncthreads();
+      int before = s_base;
+      for (int w = 0; w < warp; ++w) before += s_warp[w];
+      if (off) idx_out[(size_t)b * G + total + before + __popc(bal & ((1u << lane) - 1u))] = i;
+      int chunk = 0;
+      for (int w = 0; w < 8; ++w) chunk += s_warp[w];
+      __syncthreads();
+      if (threadIdx.x == 0) s_base += chunk;
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) {
+    if (cnt_out) cnt_out[b] = total;
+    if (total_out) atomicAdd(total_out, total);
+  }
+}
+
+extern "C" int laud_gate_from_logits(const float* logits, const float* noise, int B, int G, int inner, float tau,
+                                     uint8_t* mask_out, int32_t* idx_out, int32_t* cnt_out, int32_t* total_out, void* stream) {
+  LAUD_REQUIRE(logits && mask_out && B > 0 && G > 0 && inner > 0, "laud_gate_from_logits: bad arguments");
+  LAUD_REQUIRE(tau > 0.f, "laud_gate_from_logits: temperature must be positive (got %f)", (double)tau);
+  LAUD_REQUIRE(!idx_out || inner == 1, "laud_gate_from_logits: index lists exist for channel gates only (inner == 1)");
+  gate_from_logits_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(logits, noise, G, inner, tau, mask_out, idx_out, cnt_out, total_out);
+  return check_launch("gate_from_logits_kernel");
+}

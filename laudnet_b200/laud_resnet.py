@@ -269,11 +269,16 @@ class ResNet(nn.Module):
         self._engine.impl = impl
         return self
 
-    def forward(self, x, temperature=1.0, keep=None, forced=None):
-        if self.training:
-            raise LaudError("ResNet: training mode (Gumbel gates, reference utils.py:56-58) is not part of the "
-                            "CUDA inference path; call .eval()")
-        logits, stats = self._engine.forward(x, keep, forced=forced)
+    def forward(self, x, temperature=1.0, keep=None, forced=None, gumbel_noise=None):
+        """gumbel_noise: per block (channel sample [B,2G] | None, spatial sample [B,2g,S,S] | None).  With it the gates
+        run the reference's TRAINING branch - hard Gumbel-softmax at `temperature` (utils.py:56-58,123-125) - on the
+        supplied samples; BatchNorm uses its running statistics (eval), the configuration in which the mmdet backbones
+        train the gates (lad_mmdet_resnet.py, norm_eval).  Full training mode (batch-statistics BN, backward) is not
+        part of the CUDA path."""
+        if self.training and gumbel_noise is None:
+            raise LaudError("ResNet: training mode draws Gumbel noise from torch's generator (reference utils.py:56-58); pass "
+                            "the samples as gumbel_noise=[(channel, spatial), ...] or call .eval()")
+        logits, stats = self._engine.forward(x, keep, forced=forced, gumbel_noise=gumbel_noise, temperature=temperature)
         r3, r2, r1, rc, perc, flops = self._engine.split_stats(stats)
         return logits, r3, r2, r1, rc, perc, flops
 

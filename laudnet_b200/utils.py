@@ -68,10 +68,29 @@ def to_nchw_f32(y: torch.Tensor, channels: Optional[int] = None) -> torch.Tensor
     return out
 
 
-def _no_training(mod: nn.Module, name: str) -> None:
-    if mod.training:
-        raise LaudError(f"{name}: training mode (Gumbel-softmax gate, reference utils.py:56-58) is not part of "
-                        "the CUDA inference path; call .eval()")
+def _no_training(mod: nn.Module, name: str, noise=None) -> None:
+    if mod.training and noise is None:
+        raise LaudError(f"{name}: training mode draws Gumbel noise from torch's generator (reference utils.py:56-58), which "
+                        "a kernel cannot reproduce: pass the sample as `noise=` (same shape as the gate logits), or call "
+                        ".eval() for the argmax gate")
+
+
+def gumbel_noise_like(shape, generator=None, device=None) -> torch.Tensor:
+    """A Gumbel(0,1) sample drawn the way F.gumbel_softmax draws it (-log(Exp(1))): the `noise=` input of the
+    training-mode gates."""
+    return -torch.empty(shape, device=device).exponential_(generator=generator).log()
+
+
+def gate_from_logits(logits: torch.Tensor, noise: Optional[torch.Tensor], tau: float, G: int, inner: int,
+                     mask: torch.Tensor, idx: Optional[torch.Tensor] = None, cnt: Optional[torch.Tensor] = None,
+                     total: Optional[torch.Tensor] = None) -> None:
+    """laud_gate_from_logits: hard two-way decision from fp32 logits [B,2,G,inner] (+ Gumbel noise) at temperature tau."""
+    if noise is not None:
+        if noise.numel() != logits.numel():
+            raise LaudError(f"Gumbel noise has {noise.numel()} elements, the gate logits {logits.numel()}")
+        noise = noise.to(device=logits.device, dtype=torch.float32).contiguous()
+    check(lib().laud_gate_from_logits(ptr(logits), ptr(noise), logits.shape[0], G, inner, float(tau), ptr(mask), ptr(idx),
+                                      ptr(cnt), ptr(total), stream_ptr()), "laud_gate_from_logits")
 
 
 # ---------------------------------------------------------------------------
@@ -141,12 +160,18 @@ class Masker_spatial(nn.Module):
                                         ptr(logits), ptr(mask), ptr(total), stream_ptr()), "laud_masker_spatial")
         return mask, logits
 
-    def forward(self, x, temperature):
-        _no_training(self, "Masker_spatial")
+    def forward(self, x, temperature, noise=None):
+        """noise (training mode): Gumbel sample [B, 2g, S, S] -> the hard Gumbel-softmax gate of utils.py:56-58."""
+        _no_training(self, "Masker_spatial", noise)
         _lib.require_cuda(x, "Masker_spatial")
         b, c, h, w = x.shape
         total = torch.zeros(1, dtype=torch.int32, device=x.device)
-        mask_u8, _ = self.gate_nhwc(to_nhwc_f16(x), total)
+        if self.training:
+            mask_u8, logits = self.gate_nhwc(to_nhwc_f16(x), None, want_logits=True)
+            g, s_ = self.mask_channel_group, mask_u8.shape[-1]
+            gate_from_logits(logits, noise, temperature, g, s_ * s_, mask_u8, total=total)
+        else:
+            mask_u8, _ = self.gate_nhwc(to_nhwc_f16(x), total)
         s = mask_u8.shape[-1]
         flops = c * s * s + self.conv_flops_pp * s * s
         mask = mask_u8.float()
@@ -259,12 +284,17 @@ class Masker_channel_MLP(nn.Module):
                                                       ptr(total), stream_ptr()), "laud_masker_channel_from_partials")
         return out
 
-    def forward(self, x, temperature):
-        _no_training(self, "Masker_channel_MLP")
+    def forward(self, x, temperature, noise=None):
+        """noise (training mode): Gumbel sample [B, 2G] -> the hard Gumbel-softmax gate of utils.py:123-125."""
+        _no_training(self, "Masker_channel_MLP", noise)
         _lib.require_cuda(x, "Masker_channel_MLP")
         b, c, h, w = x.shape
         total = torch.zeros(1, dtype=torch.int32, device=x.device)
-        gate = self.gate_nhwc(to_nhwc_f16(x), total)
+        if self.training:
+            gate = self.gate_nhwc(to_nhwc_f16(x), None, want_logits=True)
+            gate_from_logits(gate.logits, noise, temperature, self.channel_dyn_group, 1, gate.mask, gate.idx, gate.cnt, total)
+        else:
+            gate = self.gate_nhwc(to_nhwc_f16(x), total)
         flops = c * h * w + self.conv_flops
         mask = gate.mask.float()
         sparsity = total[0].float() / float(gate.mask.numel())
@@ -345,12 +375,18 @@ class Masker_channel_conv_linear(nn.Module):
                                                     ptr(total), stream_ptr()), "laud_masker_channel_from_pooled")
         return out
 
-    def forward(self, x, temperature):
-        _no_training(self, "Masker_channel_conv_linear")
+    def forward(self, x, temperature, noise=None):
+        """noise (training mode, BatchNorm frozen - its running statistics are used, as the mmdet backbones run it):
+        Gumbel sample [B, 2G] -> the hard Gumbel-softmax gate of utils.py:161-163."""
+        _no_training(self, "Masker_channel_conv_linear", noise)
         _lib.require_cuda(x, "Masker_channel_conv_linear")
         b, c, h, w = x.shape
         total = torch.zeros(1, dtype=torch.int32, device=x.device)
-        gate = self.gate_nhwc(to_nhwc_f16(x), total)
+        if self.training:
+            gate = self.gate_nhwc(to_nhwc_f16(x), None, want_logits=True)
+            gate_from_logits(gate.logits, noise, temperature, self.channel_dyn_group, 1, gate.mask, gate.idx, gate.cnt, total)
+        else:
+            gate = self.gate_nhwc(to_nhwc_f16(x), total)
         cr = self.conv[0].weight.shape[0]
         flops = cr * h * w + self.masker_flops
         mask = gate.mask.float()

@@ -114,9 +114,29 @@ def two_way_decision(logits: Tensor) -> Tensor:
     return (logits[:, :half] >= logits[:, half:]).to(torch.float32)
 
 
-def masker_channel_mlp(x: Tensor, sd: Dict[str, Tensor], prefix: str, layers: int
-                       ) -> Tuple[Tensor, Tensor, int, Tensor]:
-    """models/utils.py:113-131.  Returns (mask[B,G], sparsity, flops, logits)."""
+def gumbel_two_way_decision(logits: Tensor, noise: Tensor, tau: float) -> Tensor:
+    """Training-mode gate (models/utils.py:56-58, 123-125, 161-163):
+        F.gumbel_softmax(logits.view(b, 2, ...), dim=1, tau=temperature, hard=True)[:, 0]
+    with the Gumbel(0,1) sample `noise` (same shape as `logits`) GIVEN instead of drawn - torch computes
+    y_soft = softmax((logits + g) / tau) over the pair and returns one_hot(argmax) (+ y_soft - y_soft.detach(), which is
+    the one-hot value in the forward pass up to one rounding).  Returns the 0/1 keep mask."""
+    b = logits.shape[0]
+    half = logits.shape[1] // 2
+    lg = torch.stack([logits[:, :half], logits[:, half:]], dim=1)
+    g = torch.stack([noise[:, :half], noise[:, half:]], dim=1)
+    y_soft = ((lg + g) / tau).softmax(dim=1)
+    index = y_soft.max(dim=1)[1]                     # ties -> index 0 = keep
+    return (index == 0).to(torch.float32)
+
+
+def _decide(logits: Tensor, noise: Optional[Tensor], tau: float) -> Tensor:
+    return two_way_decision(logits) if noise is None else gumbel_two_way_decision(logits, noise, tau)
+
+
+def masker_channel_mlp(x: Tensor, sd: Dict[str, Tensor], prefix: str, layers: int,
+                       noise: Optional[Tensor] = None, tau: float = 1.0) -> Tuple[Tensor, Tensor, int, Tensor]:
+    """models/utils.py:113-131.  Returns (mask[B,G], sparsity, flops, logits).  noise: training-mode Gumbel sample
+    [B, 2G] (None = the eval branch)."""
     b, c, h, w = x.shape
     pooled = x.mean(dim=(2, 3))                                   # :116 GAP
     if layers == 2:
@@ -129,12 +149,12 @@ def masker_channel_mlp(x: Tensor, sd: Dict[str, Tensor], prefix: str, layers: in
         w1, b1 = sd[prefix + "conv.weight"], sd[prefix + "conv.bias"]
         logits = F.linear(pooled, w1, b1)
         mlp_flops = c * w1.shape[0]
-    mask = two_way_decision(logits)
+    mask = _decide(logits, noise, tau)
     return mask, mask.mean(), c * h * w + mlp_flops, logits
 
 
-def masker_channel_conv_linear(x: Tensor, sd: Dict[str, Tensor], prefix: str
-                               ) -> Tuple[Tensor, Tensor, int, Tensor]:
+def masker_channel_conv_linear(x: Tensor, sd: Dict[str, Tensor], prefix: str,
+                               noise: Optional[Tensor] = None, tau: float = 1.0) -> Tuple[Tensor, Tensor, int, Tensor]:
     """models/utils.py:150-169: 1x1 conv -> BN -> ReLU -> GAP -> Linear."""
     wc = sd[prefix + "conv.0.weight"]
     z = F.conv2d(x, wc)
@@ -145,21 +165,21 @@ def masker_channel_conv_linear(x: Tensor, sd: Dict[str, Tensor], prefix: str
     pooled = z.mean(dim=(2, 3))
     wl, bl = sd[prefix + "linear.weight"], sd[prefix + "linear.bias"]
     logits = F.linear(pooled, wl, bl)
-    mask = two_way_decision(logits)
+    mask = _decide(logits, noise, tau)
     cin = x.shape[1]
     flops = cr * h * w + cin * cr + cr * wl.shape[0]              # :148,153,157
     return mask, mask.mean(), flops, logits
 
 
-def masker_spatial(x: Tensor, weight: Tensor, bias: Tensor, mask_size: int
-                   ) -> Tuple[Tensor, Tensor, int, Tensor]:
+def masker_spatial(x: Tensor, weight: Tensor, bias: Tensor, mask_size: int,
+                   noise: Optional[Tensor] = None, tau: float = 1.0) -> Tuple[Tensor, Tensor, int, Tensor]:
     """models/utils.py:47-65.  Returns (mask[B,g,S,S], sparsity, flops, logits)."""
     q = F.adaptive_avg_pool2d(x, mask_size) if mask_size < x.shape[2] else x   # :48
     flops = q.shape[1] * q.shape[2] * q.shape[3]
     logits = F.conv2d(q, weight, bias)                                          # :51
     per_pixel = weight.shape[0] * weight.shape[1] + weight.shape[1]             # :41
     flops += per_pixel * logits.shape[2] * logits.shape[3]
-    mask = two_way_decision(logits)
+    mask = _decide(logits, noise, tau)
     return mask, mask.mean(), flops, logits
 
 
@@ -236,8 +256,11 @@ class BlockTrace:
 def bottleneck_forward(x: Tensor, sd: Dict[str, Tensor], g: BlockGeom,
                        trace: Optional[BlockTrace] = None,
                        forced_channel_mask: Optional[Tensor] = None,
-                       forced_spatial_mask: Optional[Tensor] = None):
-    """laud_resnet.py:88-165, eval mode.
+                       forced_spatial_mask: Optional[Tensor] = None,
+                       noise: Optional[Tuple[Optional[Tensor], Optional[Tensor]]] = None, tau: float = 1.0):
+    """laud_resnet.py:88-165, eval-mode BatchNorm.  noise = (channel [B,2G] | None, spatial [B,2g,S,S] | None): the
+    maskers take their TRAINING branch (hard Gumbel-softmax at temperature tau) with these Gumbel samples - the
+    configuration of the mmdet backbones, which train the gates with frozen BN (lad_mmdet_resnet.py norm_eval).
 
     Returns (out, rho3, rho2, rho1, rho_c, sparse_flops, dense_flops) with the
     densities as 0-dim tensors like the reference.  `forced_*` feed a given
@@ -254,9 +277,11 @@ def bottleneck_forward(x: Tensor, sd: Dict[str, Tensor], g: BlockGeom,
     cflops = sflops = 0
     if use_c:                                                       # :94,:102
         if g.masker_kind == "MLP":
-            cm, rho_c, cflops, clog = masker_channel_mlp(x, sd, p + "masker_channel.", g.masker_layers)
+            cm, rho_c, cflops, clog = masker_channel_mlp(x, sd, p + "masker_channel.", g.masker_layers,
+                                                         noise[0] if noise else None, tau)
         else:
-            cm, rho_c, cflops, clog = masker_channel_conv_linear(x, sd, p + "masker_channel.")
+            cm, rho_c, cflops, clog = masker_channel_conv_linear(x, sd, p + "masker_channel.",
+                                                                 noise[0] if noise else None, tau)
         if forced_channel_mask is not None:
             cm = forced_channel_mask.to(torch.float32)
             rho_c = cm.mean()
@@ -264,7 +289,8 @@ def bottleneck_forward(x: Tensor, sd: Dict[str, Tensor], g: BlockGeom,
             trace.channel_mask, trace.channel_logits = cm, clog
     if use_s:                                                       # :98,:103
         small, rho3, sflops, slog = masker_spatial(
-            x, sd[p + "masker_spatial.conv.weight"], sd[p + "masker_spatial.conv.bias"], g.mask_size)
+            x, sd[p + "masker_spatial.conv.weight"], sd[p + "masker_spatial.conv.bias"], g.mask_size,
+            noise[1] if noise else None, tau)
         if forced_spatial_mask is not None:
             small = forced_spatial_mask.to(torch.float32)
             rho3 = small.mean()
@@ -329,15 +355,17 @@ def stem_forward(x: Tensor, sd: Dict[str, Tensor]) -> Tuple[Tensor, int]:
 
 
 def resnet_forward(sd: Dict[str, Tensor], cfg: ResNetCfg, x: Tensor,
-                   traces: Optional[List[BlockTrace]] = None):
+                   traces: Optional[List[BlockTrace]] = None, noise: Optional[List] = None, tau: float = 1.0):
     """laud_resnet.py:316-363.  Returns the reference's 7-tuple:
-    (logits, rho3[4], rho2[4], rho1[4], rho_c[4], flops_perc[n_blocks], flops)."""
+    (logits, rho3[4], rho2[4], rho1[4], rho_c[4], flops_perc[n_blocks], flops).
+    noise: per block (channel Gumbel sample | None, spatial Gumbel sample | None) -> training-branch gates at
+    temperature tau with eval-mode BatchNorm (see bottleneck_forward)."""
     feat, flops = stem_forward(x, sd)
     per_stage = {k: [[] for _ in range(4)] for k in ("r3", "r2", "r1", "rc")}
     perc: List[Tensor] = []
-    for g in resnet_geometry(cfg):
+    for bi, g in enumerate(resnet_geometry(cfg)):
         tr = BlockTrace() if traces is not None else None
-        feat, r3, r2, r1, rc, sparse, dense = bottleneck_forward(feat, sd, g, tr)
+        feat, r3, r2, r1, rc, sparse, dense = bottleneck_forward(feat, sd, g, tr, noise=noise[bi] if noise else None, tau=tau)
         s = int(g.prefix[5]) - 1
         for key, val in (("r3", r3), ("r2", r2), ("r1", r1), ("rc", rc)):
             per_stage[key][s].append(val.reshape(1))
@@ -457,7 +485,8 @@ def squeeze_excitation(x: Tensor, sd: Dict[str, Tensor], p: str) -> Tensor:
 
 
 def regnet_block_forward(x: Tensor, sd: Dict[str, Tensor], g: RegBlockGeom, trace: Optional[BlockTrace] = None,
-                         forced_channel_mask: Optional[Tensor] = None, forced_spatial_mask: Optional[Tensor] = None):
+                         forced_channel_mask: Optional[Tensor] = None, forced_spatial_mask: Optional[Tensor] = None,
+                         noise: Optional[Tuple[Optional[Tensor], Optional[Tensor]]] = None, tau: float = 1.0):
     """BottleneckTransform.forward + ResBottleneckBlock.forward (laud_regnet.py:157-217, 281-295), eval mode.
     Returns (out, rho3, rho2, rho1, rho_c, sparse_flops, dense_flops, se_flops, sparse_flops_of_the_transform,
     projection_flops) - the last two because the reference adds them to `flops` separately."""
@@ -470,9 +499,11 @@ def regnet_block_forward(x: Tensor, sd: Dict[str, Tensor], g: RegBlockGeom, trac
     cflops = sflops = 0
     if use_c:                                                       # :161,:169
         if g.masker_kind == "MLP":
-            cm, rho_c, cflops, clog = masker_channel_mlp(x, sd, p + "masker_channel.", g.masker_layers)
+            cm, rho_c, cflops, clog = masker_channel_mlp(x, sd, p + "masker_channel.", g.masker_layers,
+                                                         noise[0] if noise else None, tau)
         else:
-            cm, rho_c, cflops, clog = masker_channel_conv_linear(x, sd, p + "masker_channel.")
+            cm, rho_c, cflops, clog = masker_channel_conv_linear(x, sd, p + "masker_channel.",
+                                                                 noise[0] if noise else None, tau)
         if forced_channel_mask is not None:
             cm = forced_channel_mask.to(torch.float32)
             rho_c = cm.mean()
@@ -480,7 +511,8 @@ def regnet_block_forward(x: Tensor, sd: Dict[str, Tensor], g: RegBlockGeom, trac
             trace.channel_mask, trace.channel_logits = cm, clog
     if use_s:                                                       # :165,:170,:172-177
         small, rho3, sflops, slog = masker_spatial(
-            x, sd[p + "masker_spatial.conv.weight"], sd[p + "masker_spatial.conv.bias"], g.mask_size)
+            x, sd[p + "masker_spatial.conv.weight"], sd[p + "masker_spatial.conv.bias"], g.mask_size,
+            noise[1] if noise else None, tau)
         if forced_spatial_mask is not None:
             small = forced_spatial_mask.to(torch.float32)
             rho3 = small.mean()

@@ -492,6 +492,94 @@ def test_conv_rejects_bad_arguments(cuda_lib):
         _engine.run_conv(x, w, y, 1, 4, 4, 16, 3, 3, 8, 1, 1, 0)
 
 
+# --------------------------------------------------------------------------- training-mode gates with supplied Gumbel noise
+@pytest.mark.parametrize("tag", ["spatial", "layer", "mlp2", "mlp1", "convlin"])
+def test_gumbel_gate_operators_vs_reference_kat(cuda_lib, tag):
+    """Masker_*.forward in TRAIN mode with `noise=` (laud_gate_from_logits) against masks the reference's own classes
+    produced with F.gumbel_softmax(hard=True) for the same noise (tests/golden/kat_gumbel.npz); without noise training
+    mode raises."""
+    from tests.test_oracle_golden import gumbel_cases
+    t, z, sd = next(c for c in gumbel_cases() if c[0] == tag)
+    x, noise, tau = torch.from_numpy(z[f"{t}.x"]), torch.from_numpy(z[f"{t}.noise"]), float(z[f"{t}.tau"])
+    want = z[f"{t}.mask"]
+    if t in ("spatial", "layer"):
+        g, S = want.shape[1], want.shape[-1]
+        mod = L.Masker_spatial(x.shape[1], g, S)
+    elif t == "convlin":
+        mod = L.Masker_channel_conv_linear(x.shape[1], want.shape[1], reduction=4)
+    else:
+        mod = L.Masker_channel_MLP(x.shape[1], want.shape[1], layers=2 if t == "mlp2" else 1, reduction=16)
+    mod.load_state_dict(sd, strict=True)
+    mod = mod.to(DEV)
+    xh = x.half().float()                                  # the CUDA maskers read fp16 activations
+    mod.train()
+    if t == "convlin":
+        mod.conv[1].eval()
+    with pytest.raises(_lib.LaudError):
+        mod(xh.to(DEV), tau)
+    mask, rho, flops = mod(xh.to(DEV), tau, noise=noise.to(DEV))
+    # the oracle on the SAME fp16-rounded input decides which decisions are clear of rounding
+    if t in ("spatial", "layer"):
+        mo, _, fo, lg = O.masker_spatial(xh, sd["conv.weight"], sd["conv.bias"], want.shape[-1], noise, tau)
+    elif t == "convlin":
+        mo, _, fo, lg = O.masker_channel_conv_linear(xh, sd, "", noise, tau)
+    else:
+        mo, _, fo, lg = O.masker_channel_mlp(xh, sd, "", 2 if t == "mlp2" else 1, noise, tau)
+    G = lg.shape[1] // 2
+    margin = ((lg[:, :G] + noise[:, :G]) - (lg[:, G:] + noise[:, G:])).abs()
+    clear = margin > 1e-4 * float(lg.abs().max())
+    assert clear.float().mean() > 0.98
+    assert torch.equal(mask.cpu()[clear], mo[clear])
+    assert flops == fo
+    agree_ref = (mo.numpy().astype(np.uint8) == want)       # fp16 rounding of x may move a decision at the margin
+    assert agree_ref.mean() > 0.97
+    mod.eval()
+    ev = mod(xh.to(DEV), tau)[0]
+    assert not torch.equal(ev, mask), "the noise must matter"
+
+
+def test_network_gumbel_gates_frozen_bn_vs_oracle(cuda_lib):
+    """Network forward with the gates on their TRAINING branch (hard Gumbel-softmax on supplied samples, eval BatchNorm -
+    the mmdet backbones' norm_eval configuration) against the oracle fed the same samples: tiny_both exercises channel
+    (MLP + conv_linear) and spatial gates, groups > 1."""
+    cfg, sd, x, z = load_case("tiny_both")
+    model = _model(cfg, sd)
+    geoms = O.resnet_geometry(cfg)
+    gen = torch.Generator().manual_seed(77)
+    B = x.shape[0]
+    noise = []
+    for g in geoms:
+        nc = ns = None
+        if g.dyn_mode in ("channel", "both"):
+            nc = -torch.empty(B, 2 * g.groups_channel).exponential_(generator=gen).log()
+        if g.dyn_mode in ("spatial", "layer", "both"):
+            S = min(g.mask_size, g.output_size * g.stride)
+            ns = -torch.empty(B, 2 * g.groups_spatial, S, S).exponential_(generator=gen).log()
+        noise.append((nc, ns))
+    tau = 0.6
+    traces = []
+    with torch.no_grad():
+        ref = O.resnet_forward(sd, cfg, x, traces, noise=noise, tau=tau)
+        ev = O.resnet_forward(sd, cfg, x)
+        keep = []
+        out = model(x.to(DEV), tau, keep=keep, gumbel_noise=[(None if a is None else a.to(DEV), None if b is None else b.to(DEV))
+                                                              for a, b in noise])
+        torch.cuda.synchronize()
+    assert not torch.equal(ref[0], ev[0]), "the noise must change the network's decisions"
+    flips = total = 0
+    for ko, tr in zip(keep, traces):
+        for got, want in ((ko.channel_mask, tr.channel_mask), (ko.spatial_mask_small, tr.spatial_mask_small)):
+            if got is not None:
+                flips += int((got.cpu().float().reshape(-1) != want.reshape(-1)).sum())
+                total += want.numel()
+    print(f"gumbel network: {flips}/{total} decisions differ from the oracle's")
+    assert flips <= max(1, total // 500)
+    if flips == 0:
+        assert _rel_err(out[0], ref[0]) <= 5e-3
+        np.testing.assert_array_equal(torch.cat(out[4]).cpu().numpy(), torch.cat(ref[4]).numpy())
+        np.testing.assert_allclose(out[6].item(), ref[6].item(), rtol=1e-6)
+
+
 # --------------------------------------------------------------------------- channel skipping with a dense result (n_expand)
 @pytest.mark.parametrize("B,H,C,gran,rates", [
     (5, 14, 256, 2, (0.6, 0.0, 1.0, 0.95, 0.3)),        # stage-3 shape: typical, none, all, > 192 active (two n-tiles), few

@@ -222,3 +222,37 @@ def test_full_size_network_matches_reference(name):
         stats = np.array([o.mean().item(), o.abs().mean().item(), o.abs().max().item()])
         np.testing.assert_allclose(stats, z[tag + ".out_stats"], rtol=1e-4)
     assert n_gates > 0
+
+
+# --------------------------------------------------------------------------- training-mode gate with supplied Gumbel noise
+def gumbel_cases():
+    z = np.load(os.path.join(GOLDEN_DIR, "kat_gumbel.npz"))
+    for tag in ("spatial", "layer", "mlp2", "mlp1", "convlin"):
+        sd = {k[len(tag) + 4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith(tag + ".sd.")}
+        yield tag, z, sd
+
+
+@pytest.mark.parametrize("tag", ["spatial", "layer", "mlp2", "mlp1", "convlin"])
+def test_gumbel_gate_with_supplied_noise_matches_reference(tag):
+    """The reference maskers in TRAIN mode (F.gumbel_softmax, hard) with the generator seeded so that the noise they drew
+    is known (tests/golden/make_golden_gumbel.py): the oracle, given that noise, reproduces the hard masks bit for bit -
+    and they differ from the eval-mode masks (the noise matters)."""
+    for t, z, sd in gumbel_cases():
+        if t != tag:
+            continue
+        x, noise, tau = torch.from_numpy(z[f"{t}.x"]), torch.from_numpy(z[f"{t}.noise"]), float(z[f"{t}.tau"])
+        if t in ("spatial", "layer"):
+            S = z[f"{t}.mask"].shape[-1]
+            mask, rho, _, _ = O.masker_spatial(x, sd["conv.weight"], sd["conv.bias"], S, noise, tau)
+            ev = O.masker_spatial(x, sd["conv.weight"], sd["conv.bias"], S)[0]
+        elif t == "convlin":
+            mask, rho, _, _ = O.masker_channel_conv_linear(x, sd, "", noise, tau)
+            ev = O.masker_channel_conv_linear(x, sd, "")[0]
+        else:
+            layers = 2 if t == "mlp2" else 1
+            mask, rho, _, _ = O.masker_channel_mlp(x, sd, "", layers, noise, tau)
+            ev = O.masker_channel_mlp(x, sd, "", layers)[0]
+        np.testing.assert_array_equal(mask.numpy().astype(np.uint8), z[f"{t}.mask"])
+        np.testing.assert_array_equal(ev.numpy().astype(np.uint8), z[f"{t}.eval_mask"])
+        assert abs(float(rho) - float(z[f"{t}.sparsity"])) < 1e-6
+        assert (z[f"{t}.mask"] != z[f"{t}.eval_mask"]).any()
