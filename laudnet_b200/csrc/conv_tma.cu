@@ -139,6 +139,9 @@ struct Plan {              // host-computed launch geometry
   int nm;                  // 1: masked-dense channel gate (n_mask) looked up per accumulator ROW in the epilogue - the column
                            //    tables stay static, so a gated 1x1 layer can still be flat;  nm_fast: granularity 2, 16-byte rows
   int nm_fast;
+  int g4_cp;               // BMODE_G4: 1 = the active weight rows are staged by the six gather warps with 16-byte cp.async
+                           //   (192 threads, ~7 copies each per stage); 0 = by TMA tile::gather4 from the producer warp
+                           //   (four rows per instruction - measured issue-bound: ~100 cycles per copy, profiles/r02c_*)
   int tsplit;              // 1: (flat, one n-group, MT == 2) CTAs own contiguous ranges of m-TILES, processed two at a time:
                            //    the critical path is ceil(tiles / CTAs) tiles instead of 2 x ceil(tile pairs / CTAs)
   int dbg;                 // LAUD_DBG timing experiments (wrong results): 2 no activation loads, 4 no MMAs, 8 no epilogue work, 16 half-N MMAs
@@ -495,7 +498,24 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
 
   if (warp == TMA_WARP) {
     // =========================================================== TMA producer
-    if (M::bmode(pl) == BMODE_G4) {
+    if (M::bmode(pl) == BMODE_G4 && pl.g4_cp) {
+      // ---- channel skipping, weight rows by cp.async (gather warps): this warp streams the activation tiles only -
+      //      one per sub-item and 64-channel chunk, in order, as soon as one of the two slots is free
+      if (lane == 0) {
+        Walker wa;
+        walker_init(a, pl, wa);
+        Sub sa;
+        int a_next = 0;
+        while (walker_next<M>(a, pl, T, wa, sa))
+          for (int kq = 0; kq < sa.cpt; ++kq, ++a_next) {
+            const int slot = a_next & 1;
+            mbar_wait(&T.aempty[slot], (uint32_t)((a_next >> 1) & 1) ^ 1u);
+            mbar_arrive_expect_tx(&T.afull[slot], (uint32_t)pl.a_tx);
+            tma_load_4d(a_base + slot * pl.a_slot_bytes, &map_a, &T.afull[slot], kq * 64, -1, (sa.mt0) * pl.R - 1, sa.b);
+          }
+      }
+      __syncwarp();
+    } else if (M::bmode(pl) == BMODE_G4) {
       // ---- channel skipping: the WHOLE warp produces.  Lane 0 stages the activation tiles (halo mode, as below); every
       //      lane issues the tile::gather4 copies of its four-row groups of the sample's ACTIVE weight rows: group j of
       //      a stage lands at byte j * 512 of the B tile - rows 4j .. 4j+3 of a K-major SWIZZLE_128B tile (the swizzle
@@ -663,6 +683,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
               const int ty = tap / 3, tx_ = tap - ty * 3;
               mbar_wait(&T.full[stage], phase);
               KP_LAP(2);
+              if (M::bmode(pl) == BMODE_G4) fence_proxy_async();   // (cp.async rows: generic-proxy writes -> async proxy)
               tc_fence_after();
               const uint64_t bd = umma_desc(smem_base + stage * pl.stage_bytes, 16, 1024);
               if (!(pl.dbg & 4))
@@ -716,7 +737,50 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
     __syncwarp();
   } else if (warp >= GATHER_WARP0) {
     // =========================================================== weight gather (cp.async)
-    if (M::bmode(pl) == BMODE_ROWS || M::bmode(pl) == BMODE_KROWS) {
+    if (M::bmode(pl) == BMODE_G4) {
+      if (pl.g4_cp) {
+        // the sample's ACTIVE weight rows (K-major w: one row = one output channel) -> rows of a swizzled K-major B tile;
+        // thread = (16-byte chunk ac, rows ar0 + 24 i): the 8 threads of a row fetch its 128 contiguous bytes.
+        // Stage order = the halo MMA loop's: 64-channel chunk outer, tap inner.
+        const int pt = threadIdx.x - GATHER_WARP0 * 32;          // 0..191
+        const int ac = pt & 7, ar0 = pt >> 3;
+        int stage = 0;
+        uint32_t phase = 0;
+        while (walker_next<M>(a, pl, T, wk, s)) {
+          int browr[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = ar0 + 24 * i, jj = s.n0 + row;
+            browr[i] = (row < s.umma_n && jj < s.Nc)
+                           ? (__ldg(a.n_idx + (size_t)s.b * a.n_ld + jj / a.n_gran) * a.n_gran + jj % a.n_gran) * taps * a.C_in
+                           : -1;
+          }
+          for (int kq = 0; kq < s.cpt; ++kq) {
+            const int n16 = min(4, s.nk16 - kq * 4);
+            const int k = kq * 64 + ac * 8;
+            const bool kok = ac < 2 * n16 && k < a.C_in;
+            for (int tap = 0; tap < taps; ++tap) {
+              mbar_wait(&T.empty[stage], phase ^ 1);
+              const uint32_t Bs = smem_base + stage * pl.stage_bytes;
+              const __half* wk_ = a.w + tap * a.C_in + k;
+              if (ac < 2 * n16) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const int row = ar0 + 24 * i;
+                  if (row < s.umma_n) {
+                    const bool ok = kok && browr[i] >= 0;
+                    cp_async_16(Bs + sw128_off(row, ac), ok ? wk_ + browr[i] : a.w, ok ? 16u : 0u);
+                  }
+                }
+              }
+              cp_async_arrive(&T.full[stage]);
+              if (++stage == pl.stages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+      }
+    } else if (M::bmode(pl) == BMODE_ROWS || M::bmode(pl) == BMODE_KROWS) {
       const int pt = threadIdx.x - GATHER_WARP0 * 32;            // 0..191
       const int pw = pt >> 5;
       const int ac = pt & 7, ar0 = pt >> 3;                      // ROWS: 16-byte chunk, first row (rows ar0 + 24 i)
@@ -1584,7 +1648,12 @@ static int conv_forward_tma_x(const ConvArgs& a_in, cudaStream_t s, bool allow_r
     if (pl.omode == OUT_EXPAND) { set_error("conv_forward_tma: no shared memory left for the n_expand pipeline"); return LAUD_E_UNSUPPORTED; }
     return conv_forward_umma(a, s);
   }
-  pl.full_count = 1 + ((pl.bmode == BMODE_TMA || pl.bmode == BMODE_G4) ? 0 : GATHER_THREADS);
+  {
+    static const char* g4 = getenv("LAUD_G4");                  // "tma": stage the active weight rows by TMA gather4 (A/B switch)
+    pl.g4_cp = (pl.bmode == BMODE_G4 && !(g4 && !strcmp(g4, "tma"))) ? 1 : 0;
+  }
+  pl.full_count = pl.bmode == BMODE_G4 ? (pl.g4_cp ? GATHER_THREADS : 1)
+                                       : 1 + (pl.bmode == BMODE_TMA ? 0 : GATHER_THREADS);
   const int rows_box = pl.rows_per_tile < HWo ? pl.rows_per_tile : HWo;     // boxes never exceed the tensor extent
   int bn_box = pl.BN < a.C_out ? pl.BN : a.C_out;
   static const bool dbg_halfb = getenv("LAUD_DBG") && (atoi(getenv("LAUD_DBG")) & 1);   // TIMING EXPERIMENT ONLY (wrong results): half of every weight tile
