@@ -224,6 +224,14 @@ class ResNetEngine:
         # and the block output is written in place over the block input (skipped samples are untouched: relu(identity)
         # == identity bit-exactly, laud_resnet.py:133-144); "mask" = masked-dense (compute all, zero the gated rows).
         self.layer_exec = os.environ.get("LAUD_LAYER_EXEC", "skip")
+        # How a spatially gated block (dyn_mode='spatial', one mask group) executes:
+        #   "mask": masked-dense - conv1/conv2/conv3 everywhere, the gate applied in conv3's epilogue (what the reference does);
+        #   "skip": the scheme the reference only MODELS (DyNetSimulator multi_cores.py:67-337,470-511): conv1 runs on the
+        #           pixels of mask_conv1 (the 3x3-dilated footprint), conv2 / conv3 on the pixels of mask_conv2 / mask_conv3,
+        #           taken from device-side pixel lists; the block output is written IN PLACE over the block input, so a
+        #           gated-off pixel keeps relu(identity) == identity bit-exactly (laud_resnet.py:133-144).  Lists with fewer
+        #           than ~one MMA tile of pixels fall to the CUDA-core kernel (device-side dispatch, laud_conv_forward).
+        self.spatial_exec = os.environ.get("LAUD_SPATIAL_EXEC", "mask")
         # conv3 leaves the global-average-pool partial sums of the block output for the next block's channel masker
         self.fuse_gap = os.environ.get("LAUD_NO_GAP_FUSE") is None
         self._ws: Dict[tuple, dict] = {}
@@ -330,7 +338,10 @@ class ResNetEngine:
             m2=torch.empty(B * g_max * hw_max, dtype=torch.uint8, device=dev),
             m1=torch.empty(B * g_max * hw_max, dtype=torch.uint8, device=dev),
             counts=torch.zeros((nb, 4), **i32),
-            srows=torch.empty((B,), **i32), scnt=torch.zeros((1,), **i32), cws=torch.zeros((64,), **i32),
+            srows=torch.empty((B,), **i32), scnt=torch.zeros((1,), **i32),
+            cws=torch.zeros((max(64, B * hw_max // 2048 + 2),), **i32),
+            rows1=torch.empty((B * hw_max,), **i32), rows2=torch.empty((B * hw_max,), **i32),
+            rcnt=torch.zeros((2,), **i32),
             lidx=torch.empty((B * g_max,), **i32), lcnt=torch.empty((B,), **i32),
             stats=torch.empty(nb * 5 + 1, dtype=torch.float32, device=dev),
             logits=None,
@@ -476,6 +487,9 @@ class ResNetEngine:
                       "laud_compact_rows")
             sl = dict(sample_idx=ws["srows"], sample_cnt=ws["scnt"])
         a1, a2 = ws["a1"], ws["a2"]
+        if (p.mode == "spatial" and self.spatial_exec == "skip" and p.g_spatial == 1 and gate is None and "rows1" in ws
+                and self.impl == _lib.CONV_AUTO):
+            return self._run_block_spatial_skip(p, x, out, B, ws, m3, m2, m1, keep)
         sparse_gate = gate is not None and not dense_gate
         ck = dict(k_idx=gate.idx, k_cnt=gate.cnt, k_gran=p.gran) if sparse_gate else {}
         cn = dict(n_idx=gate.idx, n_cnt=gate.cnt, n_gran=p.gran, n_pad_align=16) if sparse_gate else {}
@@ -538,6 +552,38 @@ class ResNetEngine:
             keep.a2 = a2[:B * Ho * Ho * ld12].view(B, Ho, Ho, ld12).clone()
             keep.out = out[:B * Ho * Ho * p.outplanes].view(B, Ho, Ho, p.outplanes).clone()
         return out          # the buffer that holds the block output (the input buffer for an in-place layer skip)
+
+    def _run_block_spatial_skip(self, p: BlockPlan, x, out, B, ws, m3, m2, m1, keep):
+        """Spatial skipping executed (see spatial_exec): pixel lists of mask_conv1 / mask_conv2 (= mask_conv3 for one mask
+        group), conv1 -> conv2 -> conv3 over the listed pixels only, output in place."""
+        L = lib()
+        st = stream_ptr()
+        Hi, Ho = p.H_in, p.H_out
+        rows1, rows2, rc = ws["rows1"], ws["rows2"], ws["rcnt"]
+        check(L.laud_compact_rows(ptr(m1), B, 1, Hi * Hi, ptr(rows1), ptr(rc[0:1]), ptr(ws["cws"]), st), "laud_compact_rows")
+        check(L.laud_compact_rows(ptr(m2), B, 1, Ho * Ho, ptr(rows2), ptr(rc[1:2]), ptr(ws["cws"]), st), "laud_compact_rows")
+        a1, a2 = ws["a1"], ws["a2"]
+        tag = f"s{p.stage + 1}"
+        # conv1 on the dilated footprint: everything conv2 will read (ExpandMask(stride, 1) covers its 3x3 windows)
+        run_conv(x, p.w1, a1, B, Hi, Hi, p.inplanes, Hi, Hi, p.width, 1, 1, 0, ldx=p.inplanes, ldy=p.width,
+                 scale=p.s1, shift=p.t1, relu=_lib.RELU_ALL, impl=self.impl, tag=tag + ".conv1", row_idx=rows1, row_cnt=rc[0:1])
+        run_conv(a1, p.w2, a2, B, Hi, Hi, p.width, Ho, Ho, p.width, 3, p.stride, 1, ldx=p.width, ldy=p.width,
+                 scale=p.s2, shift=p.t2, relu=_lib.RELU_ALL, impl=self.impl, tag=tag + ".conv2", row_idx=rows2, row_cnt=rc[1:2])
+        if p.wd is not None:
+            # every pixel gets its downsampled identity straight into `out`; a gated-off pixel's output is relu(identity)
+            # (ReLU applied here, where the gate is 0), an active one is finished by conv3 in place
+            run_conv(x, p.wd, out, B, Hi, Hi, p.inplanes, Ho, Ho, p.outplanes, 1, p.stride, 0, ldx=p.inplanes,
+                     ldy=p.outplanes, scale=p.sd, shift=p.td, relu=_lib.RELU_WHERE_GATE0, out_mask=m3, mask_groups=1,
+                     impl=self.impl, tag=tag + ".down")
+            dst = out
+        else:
+            dst = x                                # in place: gated-off pixels keep relu(x) == x
+        run_conv(a2, p.w3, dst, B, Ho, Ho, p.width, Ho, Ho, p.outplanes, 1, 1, 0, ldx=p.width, ldy=p.outplanes,
+                 scale=p.s3, shift=p.t3, relu=_lib.RELU_ALL, residual=dst, ldr=p.outplanes, impl=self.impl,
+                 tag=tag + ".conv3", row_idx=rows2, row_cnt=rc[1:2])
+        if keep is not None:
+            keep.out = dst[:B * Ho * Ho * p.outplanes].view(B, Ho, Ho, p.outplanes).clone()
+        return dst
 
     def _gap_fusable(self, p: BlockPlan) -> bool:
         """True if block p's conv3 can leave the GAP partial sums of its output for the NEXT block's channel masker:

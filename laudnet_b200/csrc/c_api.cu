@@ -180,6 +180,8 @@ extern "C" int laud_conv_forward(const laud_conv_desc* d, int impl, void* stream
   a.bias_t = (const __half*)d->bias_t; a.bias_ld = d->bias_ld;
   a.n_mask = d->n_mask; a.n_mask_gran = d->n_mask_gran;
   a.n_expand = d->n_expand;
+  a.row_lo = 0;
+  a.row_hi = 0x7fffffff;
   a.gap_hw = 0;
 
   cudaStream_t s = (cudaStream_t)stream;
@@ -190,6 +192,19 @@ extern "C" int laud_conv_forward(const laud_conv_desc* d, int impl, void* stream
         set_error("laud_conv_forward: layout not supported by the tcgen05 kernel but w_t was given "
                   "(channel granularity must be 2, 4 or a multiple of 8; pitches multiples of 8; 16-byte aligned)");
         return LAUD_E_UNSUPPORTED;
+      }
+      if (a.row_idx && impl == LAUD_CONV_AUTO && conv_rows_simt_supported(a) && conv_umma_supported(a)) {
+        // Row lists (spatial skipping): density-dependent dispatch ON THE DEVICE.  Both kernels are enqueued; each reads
+        // *row_cnt and returns at once unless the count is in its regime - below LAUD_ROWS_SIMT_MAX active pixels (less
+        // than one 128-row MMA tile) the vectorised CUDA-core kernel, above it the tcgen05 kernel.
+        static const int simt_max = getenv("LAUD_ROWS_SIMT_MAX") ? atoi(getenv("LAUD_ROWS_SIMT_MAX")) : 96;
+        if (simt_max > 0) {
+          ConvArgs lo = a, hi = a;
+          lo.row_hi = simt_max;
+          hi.row_lo = simt_max;
+          if (int e = conv_forward_rows_simt(lo, s)) return e;
+          return conv_forward_umma(hi, s);
+        }
       }
       {
         static const bool force_v3 = getenv("LAUD_CONV_V3") != nullptr;     // A/B switch for profiling

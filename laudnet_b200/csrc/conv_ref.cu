@@ -82,6 +82,70 @@ __global__ void conv_naive_kernel(ConvArgs a) {
   a.y[pix * a.ldy + j] = __float2half(conv_epilogue(a, acc, b, r.oy, r.ox, j, o));
 }
 
+// --------------------------------------------------------------------------
+// Low-density fallback for row lists (spatial skipping with almost nothing active): below ~one tensor-core tile of
+// active pixels a 128-row MMA tile is mostly padding and the launch is latency-bound; this kernel walks the list with
+// one CTA per active pixel: the pixel's input patch (taps x C_in fp16) is staged in shared memory, every thread
+// owns output channels and streams their weight rows with 16-byte read-only loads, fp32 accumulate, the shared
+// epilogue.  It runs only if row_lo <= *row_cnt < row_hi (device-side dispatch, see ConvArgs).
+// --------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv_rows_simt_kernel(ConvArgs a) {
+  extern __shared__ __align__(16) unsigned char simt_smem[];
+  __half* patch = reinterpret_cast<__half*>(simt_smem);          // [taps][C_in]
+  const int cnt = __ldg(a.row_cnt);
+  if (cnt < a.row_lo || cnt >= a.row_hi) return;
+  const int HWo = a.H_out * a.W_out, taps = a.ksize * a.ksize, K = taps * a.C_in;
+  for (int m = blockIdx.x; m < cnt; m += gridDim.x) {
+    const int flat = __ldg(a.row_idx + m);
+    const int b = flat / HWo, p = flat - b * HWo, oy = p / a.W_out, ox = p - oy * a.W_out;
+    __syncthreads();                                             // previous pixel's patch no longer read
+    for (int i = threadIdx.x * 8; i < K; i += blockDim.x * 8) {
+      const int tap = i / a.C_in, k = i - tap * a.C_in;
+      const int iy = oy * a.stride + tap / a.ksize - a.pad, ix = ox * a.stride + tap % a.ksize - a.pad;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (iy >= 0 && ix >= 0 && iy < a.H_in && ix < a.W_in)
+        v = __ldg(reinterpret_cast<const uint4*>(a.x + (((size_t)b * a.H_in + iy) * a.W_in + ix) * a.ldx + k));
+      *reinterpret_cast<uint4*>(patch + i) = v;
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < a.C_out; o += blockDim.x) {
+      const __half* wrow = a.w + (size_t)o * K;
+      float acc = 0.f;
+      for (int i = 0; i < K; i += 8) {
+        const uint4 wv = __ldg(reinterpret_cast<const uint4*>(wrow + i));
+        const uint4 xv = *reinterpret_cast<const uint4*>(patch + i);
+        const __half2* wh = reinterpret_cast<const __half2*>(&wv);
+        const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 wf = __half22float2(wh[e]), xf = __half22float2(xh[e]);
+          acc = fmaf(xf.x, wf.x, acc);
+          acc = fmaf(xf.y, wf.y, acc);
+        }
+      }
+      a.y[((size_t)b * HWo + p) * a.ldy + o] = __float2half(conv_epilogue(a, acc, b, oy, ox, o, o));
+    }
+  }
+}
+
+bool conv_rows_simt_supported(const ConvArgs& a) {
+  return a.row_idx && !a.k_idx && !a.n_idx && !a.n_mask && !a.pre_bias && !a.bias_t && !a.sample_idx && !a.gap_partial &&
+         a.C_in % 8 == 0 && a.ldx % 8 == 0 && (size_t)a.ksize * a.ksize * a.C_in * 2 <= 96 * 1024;
+}
+
+int conv_forward_rows_simt(const ConvArgs& a, cudaStream_t s) {
+  const size_t smem = (size_t)a.ksize * a.ksize * a.C_in * sizeof(__half);
+  static size_t smem_set[MAX_DEVICES] = {0};
+  const int dev = current_device();
+  if (smem > 48 * 1024 && smem > smem_set[dev]) {
+    LAUD_CUDA(cudaFuncSetAttribute(conv_rows_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set[dev] = smem;
+  }
+  const int grid = a.row_hi < 1024 ? (a.row_hi > 0 ? a.row_hi : 1) : 1024;   // at most row_hi - 1 pixels are ever processed here
+  conv_rows_simt_kernel<<<grid, 256, smem, s>>>(a);
+  return check_launch("conv_rows_simt_kernel");
+}
+
 int conv_forward_naive(const ConvArgs& a, cudaStream_t s) {
   const int Nmax = round_up(a.C_out, a.n_pad_align);
   const long long HWo = (long long)a.H_out * a.W_out;

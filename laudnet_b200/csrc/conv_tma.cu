@@ -746,7 +746,9 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
         const int ac = pt & 7, ar0 = pt >> 3;
         int stage = 0;
         uint32_t phase = 0;
+        KP_DECL;
         while (walker_next<M>(a, pl, T, wk, s)) {
+          KP_LAP(0);
           int browr[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -759,8 +761,10 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
             const int n16 = min(4, s.nk16 - kq * 4);
             const int k = kq * 64 + ac * 8;
             const bool kok = ac < 2 * n16 && k < a.C_in;
+            KP_LAP(1);
             for (int tap = 0; tap < taps; ++tap) {
               mbar_wait(&T.empty[stage], phase ^ 1);
+              KP_LAP(2);
               const uint32_t Bs = smem_base + stage * pl.stage_bytes;
               const __half* wk_ = a.w + tap * a.C_in + k;
               if (ac < 2 * n16) {
@@ -775,9 +779,11 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
               }
               cp_async_arrive(&T.full[stage]);
               if (++stage == pl.stages) { stage = 0; phase ^= 1; }
+              KP_LAP(3);
             }
           }
         }
+        if (pt == 0) KP_FLUSH(2);
         asm volatile("cp.async.wait_all;" ::: "memory");
       }
     } else if (M::bmode(pl) == BMODE_ROWS || M::bmode(pl) == BMODE_KROWS) {

@@ -154,6 +154,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_umma_kernel(const __grid_
   const int HWo = a.H_out * a.W_out;
   const int taps = a.ksize * a.ksize;
   const int mode = pl.mode;
+  if (a.row_idx) {            // density-dependent dispatch, decided on the device: not this kernel's regime -> nothing to do
+    const int cnt = __ldg(a.row_cnt);
+    if (cnt < a.row_lo || cnt >= a.row_hi) return;      // (uniform over the grid; before any barrier / TMEM allocation)
+  }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < pl.stages; ++s) {

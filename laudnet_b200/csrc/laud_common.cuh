@@ -103,6 +103,9 @@ struct ConvArgs {
   const __half* bias_t; int bias_ld;
   const uint8_t* n_mask; int n_mask_gran;
   int n_expand;
+  int row_lo, row_hi;       // internal (row lists): this launch handles the list only if row_lo <= *row_cnt < row_hi - the
+                            // density-dependent dispatch between the tensor-core and the CUDA-core kernel is decided ON
+                            // THE DEVICE (the count never visits the host); 0 / INT_MAX = always
   int gap_hw;               // internal: pixels per sample of the layer (set by the launcher when gap_partial is used)
 };
 
@@ -121,6 +124,8 @@ int conv_forward_hmma(const ConvArgs& a, cudaStream_t s);
 int conv_forward_umma(const ConvArgs& a, cudaStream_t s);
 bool conv_umma_supported(const ConvArgs& a);
 int conv_forward_tma(const ConvArgs& a, cudaStream_t s);
+int conv_forward_rows_simt(const ConvArgs& a, cudaStream_t s);   // low-density row lists: vectorised CUDA-core kernel
+bool conv_rows_simt_supported(const ConvArgs& a);
 bool conv_tma_supported(const ConvArgs& a);
 
 // Shared epilogue: value for output (b, oy, ox), compact channel j / real channel o.

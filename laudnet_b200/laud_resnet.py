@@ -133,6 +133,7 @@ class _SoloEngine(ResNetEngine):
         self.impl = _lib.CONV_AUTO
         self.channel_exec = os.environ.get("LAUD_CHANNEL_EXEC", "dense")
         self.layer_exec = os.environ.get("LAUD_LAYER_EXEC", "skip")
+        self.spatial_exec = os.environ.get("LAUD_SPATIAL_EXEC", "mask")
         self._ws = {}
         dev = blk.conv1.weight.device
         p = BlockPlan(index=0, stage=0, inplanes=blk.conv1.weight.shape[1], width=blk.conv1.weight.shape[0],
@@ -172,7 +173,9 @@ class _SoloEngine(ResNetEngine):
                 m3=torch.empty(B * p.g_spatial * hw, dtype=torch.uint8, device=dev),
                 m2=torch.empty(B * p.g_spatial * hw, dtype=torch.uint8, device=dev),
                 m1=torch.empty(B * p.g_spatial * hw, dtype=torch.uint8, device=dev),
-                srows=torch.empty((B,), **i32), scnt=torch.zeros((1,), **i32), cws=torch.zeros((64,), **i32),
+                srows=torch.empty((B,), **i32), scnt=torch.zeros((1,), **i32),
+                cws=torch.zeros((max(64, B * hw // 2048 + 2),), **i32),
+                rows1=torch.empty((B * hw,), **i32), rows2=torch.empty((B * hw,), **i32), rcnt=torch.zeros((2,), **i32),
                 lidx=torch.empty((B * p.g_spatial,), **i32), lcnt=torch.empty((B,), **i32),
                 counts=torch.zeros((1, 4), **i32), mkz=None, mkpool=None)
             consts = self.stats_consts.clone()

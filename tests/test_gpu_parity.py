@@ -492,6 +492,53 @@ def test_conv_rejects_bad_arguments(cuda_lib):
         _engine.run_conv(x, w, y, 1, 4, 4, 16, 3, 3, 8, 1, 1, 0)
 
 
+# --------------------------------------------------------------------------- pixel lists (spatial skipping), both density regimes
+@pytest.mark.parametrize("B,H,Cin,Cout,k,stride,n_rows", [
+    (3, 14, 64, 256, 1, 1, 300),     # conv3-like: tensor-core regime, residual in place
+    (3, 14, 64, 256, 1, 1, 40),      # same layer, almost nothing active: CUDA-core regime (device-side dispatch)
+    (2, 14, 64, 64, 3, 1, 180),      # conv2-like 3x3
+    (2, 14, 64, 64, 3, 1, 7),
+    (2, 28, 32, 32, 3, 2, 150),      # stride-2 conv2 (first block of a stage)
+    (2, 28, 32, 32, 3, 2, 1),
+    (2, 8, 16, 32, 1, 1, 0),         # empty list: nothing may be written
+])
+def test_conv_row_lists_in_place_both_density_regimes(cuda_lib, B, H, Cin, Cout, k, stride, n_rows):
+    """laud_conv_desc.row_idx / row_cnt (spatial skipping): only the listed output pixels are computed, the others keep
+    their bytes (in-place residual: y doubles as the residual).  Below LAUD_ROWS_SIMT_MAX (96) listed pixels the vectorised
+    CUDA-core kernel runs, above it the tcgen05 kernel - chosen on the device from *row_cnt; both against the fp32 oracle."""
+    gen = torch.Generator().manual_seed(B * 977 + H * 31 + Cin + Cout + k + stride + n_rows)
+    pad = 1 if k == 3 else 0
+    Ho = (H + 2 * pad - k) // stride + 1
+    x = torch.randn(B, Cin, H, H, generator=gen).half().float()
+    w = (torch.randn(Cout, Cin, k, k, generator=gen) / (Cin * k * k) ** 0.5).half().float()
+    scale = torch.rand(Cout, generator=gen) + 0.5
+    shift = torch.randn(Cout, generator=gen) * 0.3
+    y0 = torch.relu(torch.randn(B, Cout, Ho, Ho, generator=gen)).half().float()
+    ref = torch.relu(F.conv2d(x, w, stride=stride, padding=pad) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1) + y0)
+    perm = torch.randperm(B * Ho * Ho, generator=gen)[:n_rows].sort().values.to(torch.int32)
+    listed = torch.zeros(B * Ho * Ho, dtype=torch.bool)
+    listed[perm.long()] = True
+    xd = x.permute(0, 2, 3, 1).contiguous().half().to(DEV)
+    wd = _engine.pack_conv_weight(w).to(DEV)
+    yd = y0.permute(0, 2, 3, 1).contiguous().half().to(DEV)
+    before = yd.clone()
+    rows = torch.full((B * Ho * Ho,), -1, dtype=torch.int32)
+    rows[:n_rows] = perm
+    rows_d, cnt_d = rows.to(DEV), torch.tensor([n_rows], dtype=torch.int32, device=DEV)
+    n0 = _lib.launch_count()
+    _engine.run_conv(xd, wd, yd, B, H, H, Cin, Ho, Ho, Cout, k, stride, pad, scale=scale.to(DEV), shift=shift.to(DEV),
+                     relu=_lib.RELU_ALL, residual=yd, ldr=Cout, row_idx=rows_d, row_cnt=cnt_d)
+    torch.cuda.synchronize()
+    assert _lib.launch_count() - n0 == 2, "both regimes' kernels are enqueued; the device picks"
+    got = yd.view(B * Ho * Ho, Cout).float().cpu()
+    want = ref.permute(0, 2, 3, 1).reshape(B * Ho * Ho, Cout)
+    assert torch.equal(yd.view(B * Ho * Ho, Cout)[~listed.to(DEV)], before.view(B * Ho * Ho, Cout)[~listed.to(DEV)]), \
+        "a pixel that is not listed was written"
+    if n_rows:
+        err = ((got[listed] - want[listed]).abs().max() / want.abs().max()).item()
+        assert err <= ACT_TOL, f"listed rows differ from the oracle: {err:.2e}"
+
+
 # --------------------------------------------------------------------------- training-mode gates with supplied Gumbel noise
 @pytest.mark.parametrize("tag", ["spatial", "layer", "mlp2", "mlp1", "convlin"])
 def test_gumbel_gate_operators_vs_reference_kat(cuda_lib, tag):
@@ -768,6 +815,28 @@ def test_network_free_running_vs_golden(cuda_lib, name, channel_exec):
                                       np.concatenate([z[f"rho3.{s}"] for s in range(4)]))
         np.testing.assert_allclose(perc.cpu().numpy(), z["flops_perc"], rtol=1e-6)
         np.testing.assert_allclose(flops.item(), float(z["flops"]), rtol=1e-6)
+
+
+def test_spatial_skip_network_matches_golden_and_masked_dense(cuda_lib):
+    """tiny_spatial with the spatial skipping executed: logits vs the reference golden, and the skipped pixels of every block
+    bit-identical to the masked-dense execution's (relu(identity) in place)."""
+    cfg, sd, x, z = load_case("tiny_spatial")
+    outs = {}
+    for mode in ("mask", "skip"):
+        model = _model(cfg, sd)
+        model._engine.spatial_exec = mode
+        keep = []
+        with torch.no_grad():
+            logits = model(x.to(DEV), 1.0, keep=keep)[0]
+            again = model.forward_logits(x.to(DEV)).clone()
+        assert torch.equal(logits, again), "the forward must be repeatable (in-place block outputs)"
+        outs[mode] = (logits.float().cpu(), [k.out.float().cpu() for k in keep], [k.mask_conv3.cpu() for k in keep])
+    err = _rel_err(outs["skip"][0], torch.from_numpy(z["logits"]))
+    assert err <= 5e-3, f"logits error {err:.2e}"
+    for o_mask, o_skip, m3 in zip(outs["mask"][1], outs["skip"][1], outs["mask"][2]):
+        off = (m3[:, 0] == 0)                                       # [B,H,W] gated-off pixels
+        if torch.equal(outs["mask"][0], outs["skip"][0]):
+            assert torch.equal(o_skip[off], o_mask[off])
 
 
 @pytest.mark.parametrize("layer_exec", ["skip", "mask"])
@@ -1056,10 +1125,12 @@ def test_headline_r101_channel_bs8_both_executions_vs_oracle(cuda_lib, channel_e
     _bs8_vs_oracle("full_r101_channel", setup=lambda m: setattr(m._engine, "channel_exec", channel_exec))
 
 
-def test_resnet50_spatial_bs8_full_size_vs_oracle(cuda_lib):
+@pytest.mark.parametrize("spatial_exec", ["mask", "skip"])
+def test_resnet50_spatial_bs8_full_size_vs_oracle(cuda_lib, spatial_exec):
     """BASELINE configs[0] (LAUD-ResNet50 spatial 4-4-2-1, batch 8, 224x224) against the CPU oracle: spatial gates,
-    dilated masks' densities, logits, flops."""
-    _bs8_vs_oracle("full_r50_spatial", graphed_chains=1)
+    dilated masks' densities, logits, flops - masked-dense and with the spatial skipping EXECUTED (pixel lists of
+    mask_conv1 / mask_conv2 / mask_conv3, in-place block outputs; the graphed serving path included)."""
+    _bs8_vs_oracle("full_r50_spatial", graphed_chains=1, setup=lambda m: setattr(m._engine, "spatial_exec", spatial_exec))
 
 
 @pytest.mark.parametrize("layer_exec", ["skip", "mask"])
