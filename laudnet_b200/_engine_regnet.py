@@ -6,6 +6,8 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import Dict, List, Optional
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -64,6 +66,8 @@ class RegNetEngine:
         self.plans: List[RegPlan] = []
         self.prepared_for: Optional[torch.device] = None
         self.impl = _lib.CONV_AUTO
+        # "skip": conv c runs on the pixel list of mask_conv3, block output in place (see run_block); "mask": masked-dense
+        self.spatial_exec = os.environ.get("LAUD_SPATIAL_EXEC", "mask")
         self._ws: Dict[tuple, dict] = {}
 
     # ------------------------------------------------------------------ prepare
@@ -167,7 +171,9 @@ class RegNetEngine:
             m3=torch.empty(B * g_max * hw_max, dtype=torch.uint8, device=dev),
             m2=torch.empty(B * g_max * hw_max, dtype=torch.uint8, device=dev),
             m1=torch.empty(B * g_max * hw_max, dtype=torch.uint8, device=dev),
-            counts=torch.zeros((nb, 4), **i32), stats=torch.empty(nb * 5 + 1, **f32))
+            counts=torch.zeros((nb, 4), **i32), stats=torch.empty(nb * 5 + 1, **f32),
+            rows2=torch.empty((B * hw_max,), **i32), rcnt=torch.zeros((2,), **i32),
+            cws=torch.zeros((max(64, B * hw_max // 2048 + 2),), **i32))
         consts = self.stats_consts.clone()
         for i, p in enumerate(self.plans):
             S = min(p.mask_size, p.H_in)
@@ -243,6 +249,28 @@ class RegNetEngine:
         check(L.laud_se_gate(ptr(ws["pooled"]), B, p.w_b, ptr(p.se_w1), ptr(p.se_b1), p.se_width, ptr(p.se_w2),
                              ptr(p.se_b2), ptr(cmask), p.gran, ptr(ws["segate"]), st), "laud_se_gate")
         check(L.laud_scale_channels(ptr(a2), B, Ho * Ho, p.w_b, ptr(ws["segate"]), st), "laud_scale_channels")
+        spatial_skip = (getattr(self, "spatial_exec", "mask") == "skip" and p.mode == "spatial" and p.g_spatial == 1
+                        and "rows2" in ws and self.impl == _lib.CONV_AUTO)
+        if spatial_skip:
+            # Parity mode of SURVEY 7 H2: the Squeeze-Excitation pools the DENSE conv-b output, so a / b run everywhere;
+            # conv c - the one layer the reference's semantics allow to skip - runs on the pixel list of mask_conv3 and
+            # the block output is written in place (a gated-off pixel keeps relu(identity), laud_regnet.py:197-198,290-295)
+            rc = ws["rcnt"]
+            check(L.laud_compact_rows(ptr(m3), B, 1, Ho * Ho, ptr(ws["rows2"]), ptr(rc[1:2]), ptr(ws["cws"]), st),
+                  "laud_compact_rows")
+            if p.wp is not None:
+                run_conv(x, p.wp, out, B, Hi, Hi, p.w_in, Ho, Ho, p.w_out, 1, p.stride, 0, ldx=p.w_in, ldy=p.w_out,
+                         scale=p.sp, shift=p.tp, relu=_lib.RELU_WHERE_GATE0, out_mask=m3, mask_groups=1, impl=self.impl,
+                         tag=tag + ".proj")
+                dst = out
+            else:
+                dst = x
+            run_conv(a2, p.wc, dst, B, Ho, Ho, p.w_b, Ho, Ho, p.w_out, 1, 1, 0, ldx=p.w_b, ldy=p.w_out, scale=p.sc,
+                     shift=p.tc, relu=_lib.RELU_ALL, residual=dst, ldr=p.w_out, impl=self.impl, tag=tag + ".c",
+                     row_idx=ws["rows2"], row_cnt=rc[1:2])
+            if keep is not None:
+                keep.out = dst[:B * Ho * Ho * p.w_out].view(B, Ho, Ho, p.w_out).clone()
+            return dst
         # identity / projection     :284-290
         if p.wp is not None:
             run_conv(x, p.wp, idbuf, B, Hi, Hi, p.w_in, Ho, Ho, p.w_out, 1, p.stride, 0, ldx=p.w_in, ldy=p.w_out,
@@ -296,8 +324,9 @@ class RegNetEngine:
                 ko = BlockOutputs()
                 keep.append(ko)
             fc, fs = forced[p.index] if forced is not None else (None, None)
-            self.run_block(p, bufs[cur], bufs[nxt], bufs[idb], B, ws, ko, fc, fs)
-            cur = nxt
+            res_buf = self.run_block(p, bufs[cur], bufs[nxt], bufs[idb], B, ws, ko, fc, fs)
+            if res_buf is not bufs[cur]:          # (an in-place spatial skip returns the input buffer)
+                cur = nxt
         last = self.plans[-1]
         ncls = m.fc.weight.shape[0]
         logits = torch.empty((B, ncls), dtype=torch.float32, device=x.device)

@@ -1147,8 +1147,11 @@ def test_resnet50_conv_linear_channel_bs8_full_size_vs_oracle(cuda_lib):
     assert not any(m._engine._gap_fusable(p) for p in m._engine.plans[:-1])
 
 
-def test_regnet_y_800mf_spatial_bs8_full_size_vs_oracle(cuda_lib):
-    _bs8_vs_oracle("full_regnety800_spatial")
+@pytest.mark.parametrize("spatial_exec", ["mask", "skip"])
+def test_regnet_y_800mf_spatial_bs8_full_size_vs_oracle(cuda_lib, spatial_exec):
+    """BASELINE configs[4] architecture at batch 8 vs the CPU oracle; "skip": conv c on the pixel list of mask_conv3,
+    block output in place (the SE pools the dense conv-b output, so a / b run everywhere: SURVEY 7 H2 parity mode)."""
+    _bs8_vs_oracle("full_regnety800_spatial", graphed_chains=1, setup=lambda m: setattr(m._engine, "spatial_exec", spatial_exec))
 
 
 # =========================================================================== LAUD-RegNet-Y (laud_regnet.py)
