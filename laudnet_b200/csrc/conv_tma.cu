@@ -53,6 +53,7 @@ namespace {
 constexpr int BM = 128;
 constexpr int A_TILE_BYTES = BM * 128;           // 128 rows x 64 fp16
 constexpr int EPI_WARPS = 8, TMA_WARP = 8, MMA_WARP = 9, GATHER_WARP0 = 10, GATHER_WARPS = 6;
+constexpr int MMA_WARP2 = 15;                     // second MMA issuer (Plan::dual): another scheduler than MMA_WARP's
 constexpr int NUM_THREADS = (GATHER_WARP0 + GATHER_WARPS) * 32;   // 512
 constexpr int EPI_THREADS = EPI_WARPS * 32, HALF_THREADS = EPI_THREADS / 2;
 constexpr int GATHER_THREADS = GATHER_WARPS * 32;
@@ -139,6 +140,11 @@ struct Plan {              // host-computed launch geometry
   int nm;                  // 1: masked-dense channel gate (n_mask) looked up per accumulator ROW in the epilogue - the column
                            //    tables stay static, so a gated 1x1 layer can still be flat;  nm_fast: granularity 2, 16-byte rows
   int nm_fast;
+  int dual;                // 1: TWO MMA-issuing warps (MT == 2, direct / expanding epilogue): warp 9 issues the MMAs of m-tile 0,
+                           //    warp 15 those of m-tile 1.  An issued tcgen05.mma costs ~24 issue slots (seven R2UR.BROADCAST
+                           //    moves of its operands into uniform registers) on a scheduler shared with two epilogue warps:
+                           //    ~110 cycles per MMA from one warp whatever N (measured, profiles/r02*_kprof*), i.e. every
+                           //    layer with N < 256 - and channel skipping - was issue-bound, not tensor-bound
   int g4_cp;               // BMODE_G4: 1 = the active weight rows are staged by the six gather warps with 16-byte cp.async
                            //   (192 threads, ~7 copies each per stage); 0 = by TMA tile::gather4 from the producer warp
                            //   (four rows per instruction - measured issue-bound: ~100 cycles per copy, profiles/r02c_*)
@@ -440,17 +446,17 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
   if (threadIdx.x == 0) {
     for (int s = 0; s < pl.stages; ++s) {
       mbar_init(&T.full[s], pl.full_count);
-      mbar_init(&T.empty[s], 1);
+      mbar_init(&T.empty[s], pl.dual ? 2 : 1);
     }
     for (int i = 0; i < 4; ++i) {
-      mbar_init(&T.tfull[i], 1);
+      mbar_init(&T.tfull[i], pl.dual ? 2 : 1);
       mbar_init(&T.tempty[i], EPI_WARPS);        // one arrival per epilogue warp (256 arrivals on one word serialise)
     }
     for (int h = 0; h < 2; ++h)
       for (int i = 0; i < MAX_RING; ++i) mbar_init(&T.rfull[h][i], 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&T.afull[i], 1);
-      mbar_init(&T.aempty[i], 1);
+      mbar_init(&T.aempty[i], pl.dual ? 2 : 1);
     }
     for (int h = 0; h < 2; ++h)
       for (int i = 0; i < MAX_RING; ++i) {
@@ -657,19 +663,33 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
       KP_FLUSH(0);
     }
     __syncwarp();
-  } else if (warp == MMA_WARP) {
+  } else if (warp == MMA_WARP || (pl.dual && warp == MMA_WARP2)) {
     // =========================================================== MMA issuer
     // The whole warp runs this loop with identical values and an elected lane issues (see umma_f16_elect).
     {
+      const int m_first = (pl.dual && warp == MMA_WARP2) ? 1 : 0, m_step = pl.dual ? 2 : 1;   // this warp's m-tiles
       int stage = 0, buf = 0, hg = 0;
       uint32_t phase = 0, bphase = 0;
       KP_DECL;
+      // Everything the MMA operands are built from is the same in all 32 lanes, but values that came through memory
+      // (the TMEM base address, the shared-memory window, decoded work items) live in per-thread registers as far as the
+      // compiler knows, and every tcgen05.mma then needs seven R2UR.BROADCAST moves into uniform registers.  A full-warp
+      // shuffle from lane 0 tells the compiler the value is warp-uniform: descriptors are then computed on the uniform
+      // datapath and an MMA costs a handful of issue slots - this warp shares its scheduler with two epilogue warps.
+      const uint32_t tmem_base_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t a_base_u = __shfl_sync(0xffffffffu, a_base, 0), smem_base_u = __shfl_sync(0xffffffffu, smem_base, 0);
       while (walker_next<M>(a, pl, T, wk, s)) {
+        s.mt_cnt = __shfl_sync(0xffffffffu, s.mt_cnt, 0);
+        s.cpt = __shfl_sync(0xffffffffu, s.cpt, 0);
+        s.nk16 = __shfl_sync(0xffffffffu, s.nk16, 0);
+        s.umma_n = __shfl_sync(0xffffffffu, s.umma_n, 0);
+        s.nchunks = __shfl_sync(0xffffffffu, s.nchunks, 0);
+        s.has_bias = __shfl_sync(0xffffffffu, s.has_bias, 0);
         KP_LAP(0);                                               // decode
         mbar_wait(&T.tempty[buf], bphase ^ 1);                   // epilogue has drained this buffer
         KP_LAP(1);                                               // wait for a free accumulator
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * (pl.MT * pl.acc_cols);
+        const uint32_t d_tmem = tmem_base_u + buf * (pl.MT * pl.acc_cols);
         const uint32_t idesc = umma_idesc_f16((pl.dbg & 16) ? s.umma_n / 2 : s.umma_n, M::bmode(pl) == BMODE_KROWS);   // (dbg 16: half-N MMAs, timing only)
         if (M::halo(pl)) {
           for (int kq = 0; kq < s.cpt; ++kq, ++hg) {
@@ -678,19 +698,21 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
             mbar_wait(&T.afull[aslot], (uint32_t)((hg >> 1) & 1));
             KP_LAP(2);
             tc_fence_after();
-            const uint32_t Aslot = a_base + aslot * pl.a_slot_bytes;
+            const uint32_t Aslot = a_base_u + aslot * pl.a_slot_bytes;
             for (int tap = 0; tap < taps; ++tap) {
               const int ty = tap / 3, tx_ = tap - ty * 3;
               mbar_wait(&T.full[stage], phase);
               KP_LAP(2);
               if (M::bmode(pl) == BMODE_G4) fence_proxy_async();   // (cp.async rows: generic-proxy writes -> async proxy)
               tc_fence_after();
-              const uint64_t bd = umma_desc(smem_base + stage * pl.stage_bytes, 16, 1024);
+              const uint64_t bd = umma_desc(smem_base_u + stage * pl.stage_bytes, 16, 1024);
               if (!(pl.dbg & 4))
-              for (int m = 0; m < s.mt_cnt; ++m) {
+              for (int m = m_first; m < s.mt_cnt; m += m_step) {
                 // tile m, tap (ty,tx): 128 consecutive rows of the padded image starting at row (m R + ty) Wp + tx
                 const uint32_t aaddr = Aslot + (uint32_t)(((m * pl.R + ty) * pl.Wp + tx_) * 128);
                 const uint64_t ad = umma_desc(aaddr, 16, 1024) | (pl.halo_bo ? ((uint64_t)((aaddr >> 7) & 7u) << 49) : 0ull);
+                if (n16 == 4) umma_f16_elect_x4(d_tmem + m * pl.acc_cols, ad, bd, idesc, (kq | tap) ? 1u : 0u, 2u);
+                else
                 for (int k = 0; k < n16; ++k)
                   umma_f16_elect(d_tmem + m * pl.acc_cols, ad + 2 * k, bd + 2 * k, idesc, (kq | tap | k) ? 1u : 0u);
               }
@@ -712,13 +734,15 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
             if (M::bmode(pl) != BMODE_TMA) fence_proxy_async();  // cp.async (generic proxy) writes -> async proxy
             tc_fence_after();
             KP_LAP(4);                                           // fences
-            const uint32_t As = smem_base + stage * pl.stage_bytes;
+            const uint32_t As = smem_base_u + stage * pl.stage_bytes;
             const uint32_t Bs = As + pl.b_off;
             const uint64_t bd = M::bmode(pl) == BMODE_KROWS ? umma_desc(Bs, 8192, 1024) : umma_desc(Bs, 16, 1024);
             const uint64_t bstep = M::bmode(pl) == BMODE_KROWS ? 128 : 2;
             if (!(pl.dbg & 4))
-            for (int m = 0; m < s.mt_cnt; ++m) {
+            for (int m = m_first; m < s.mt_cnt; m += m_step) {
               const uint64_t ad = umma_desc(As + m * A_TILE_BYTES, 16, 1024);
+              if (n16 == 4) umma_f16_elect_x4(d_tmem + m * pl.acc_cols, ad, bd, idesc, ch ? 1u : 0u, (uint32_t)bstep);
+              else
               for (int k = 0; k < n16; ++k)
                 umma_f16_elect(d_tmem + m * pl.acc_cols, ad + 2 * k, bd + bstep * k, idesc, (ch | k) ? 1u : 0u);
             }
@@ -732,7 +756,7 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
         else if (lane == 0) mbar_arrive(&T.tfull[buf]);          // no active input channel: accumulator unused
         if (++buf == pl.nbuf) { buf = 0; bphase ^= 1; }
       }
-      if (lane == 0) KP_FLUSH(1);
+      if (lane == 0 && warp == MMA_WARP) KP_FLUSH(1);
     }
     __syncwarp();
   } else if (warp >= GATHER_WARP0) {
@@ -742,17 +766,18 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
         // the sample's ACTIVE weight rows (K-major w: one row = one output channel) -> rows of a swizzled K-major B tile;
         // thread = (16-byte chunk ac, rows ar0 + 24 i): the 8 threads of a row fetch its 128 contiguous bytes.
         // Stage order = the halo MMA loop's: 64-channel chunk outer, tap inner.
-        const int pt = threadIdx.x - GATHER_WARP0 * 32;          // 0..191
+        const int pt = threadIdx.x - GATHER_WARP0 * 32;          // 0..191 (0..159 with a second MMA warp)
         const int ac = pt & 7, ar0 = pt >> 3;
+        const int rstep = pl.dual ? 20 : 24;                     // rows ar0 + rstep * i
         int stage = 0;
         uint32_t phase = 0;
         KP_DECL;
         while (walker_next<M>(a, pl, T, wk, s)) {
           KP_LAP(0);
-          int browr[8];
+          int browr[10];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int row = ar0 + 24 * i, jj = s.n0 + row;
+          for (int i = 0; i < 10; ++i) {
+            const int row = ar0 + rstep * i, jj = s.n0 + row;
             browr[i] = (row < s.umma_n && jj < s.Nc)
                            ? (__ldg(a.n_idx + (size_t)s.b * a.n_ld + jj / a.n_gran) * a.n_gran + jj % a.n_gran) * taps * a.C_in
                            : -1;
@@ -769,8 +794,8 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
               const __half* wk_ = a.w + tap * a.C_in + k;
               if (ac < 2 * n16) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const int row = ar0 + 24 * i;
+                for (int i = 0; i < 10; ++i) {
+                  const int row = ar0 + rstep * i;
                   if (row < s.umma_n) {
                     const bool ok = kok && browr[i] >= 0;
                     cp_async_16(Bs + sw128_off(row, ac), ok ? wk_ + browr[i] : a.w, ok ? 16u : 0u);
@@ -1658,7 +1683,12 @@ static int conv_forward_tma_x(const ConvArgs& a_in, cudaStream_t s, bool allow_r
     static const char* g4 = getenv("LAUD_G4");                  // "tma": stage the active weight rows by TMA gather4 (A/B switch)
     pl.g4_cp = (pl.bmode == BMODE_G4 && !(g4 && !strcmp(g4, "tma"))) ? 1 : 0;
   }
-  pl.full_count = pl.bmode == BMODE_G4 ? (pl.g4_cp ? GATHER_THREADS : 1)
+  {
+    static const bool no_dual = getenv("LAUD_NO_DUAL_MMA") != nullptr;            // A/B switch
+    pl.dual = (!no_dual && pl.MT == 2 && (pl.omode == OUT_DIRECT || pl.omode == OUT_EXPAND) &&
+               (pl.bmode == BMODE_TMA || pl.bmode == BMODE_G4)) ? 1 : 0;
+  }
+  pl.full_count = pl.bmode == BMODE_G4 ? (pl.g4_cp ? (pl.dual ? GATHER_THREADS - 32 : GATHER_THREADS) : 1)
                                        : 1 + (pl.bmode == BMODE_TMA ? 0 : GATHER_THREADS);
   const int rows_box = pl.rows_per_tile < HWo ? pl.rows_per_tile : HWo;     // boxes never exceed the tensor extent
   int bn_box = pl.BN < a.C_out ? pl.BN : a.C_out;

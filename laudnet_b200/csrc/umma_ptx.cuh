@@ -115,6 +115,28 @@ __device__ __forceinline__ void umma_f16_elect(uint32_t tmem_d, uint64_t adesc, 
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Four consecutive K=16 steps of one 64-channel chunk in ONE asm block (A advances 32 bytes per step inside the swizzle
+// atom, B by `bstep` descriptor units): the tensor-core instruction takes its operands from UNIFORM registers, and ptxas
+// moves every operand of every tcgen05.mma there with its own R2UR.BROADCAST (seven per MMA, ~24 issue slots - the MMA warp
+// shares its scheduler with two epilogue warps, measured ~110 cycles per MMA whatever N).  Inside one block the accumulator
+// address, the instruction descriptor and the descriptor high words are moved once for the four MMAs, one ELECT serves all.
+__device__ __forceinline__ void umma_f16_elect_x4(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                  uint32_t accumulate_first, uint32_t bstep) {
+  asm volatile(
+      "{\n\t.reg .pred p, pe, pt;\n\t.reg .b64 a1, a2, a3, b1, b2, b3, st;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 pt, 0, 0;\n\t"
+      "cvt.u64.u32 st, %5;\n\t"
+      "add.u64 a1, %1, 2;\n\tadd.u64 a2, %1, 4;\n\tadd.u64 a3, %1, 6;\n\t"
+      "add.u64 b1, %2, st;\n\tadd.u64 b2, b1, st;\n\tadd.u64 b3, b2, st;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, pt;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate_first), "r"(bstep)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_elect(unsigned long long* b) {
   asm volatile(
       "{\n\t.reg .pred pe;\n\t"
