@@ -137,6 +137,12 @@ int laud_expand_mask(const uint8_t* mask, int B, int g, int H, int W, int stride
 int laud_resize_mask_nearest(const uint8_t* mask, int B, int g, int S, int H_out,
                              uint8_t* out, void* stream);
 
+/* The three spatial masks of a block in one launch (laud_resnet.py:105-110 = laud_resize_mask_nearest +
+ * laud_expand_mask(1,0) + laud_expand_mask(stride,1)): small u8 [B,g,S,S] -> m3, m2 u8 [B,g,H_out,H_out],
+ * m1 u8 [B,g,H_out*stride,H_out*stride]; total2 / total1 += ones of m2 / m1 (x g, as the reference's means count). */
+int laud_spatial_masks(const uint8_t* small, int B, int g, int S, int H_out, int stride, uint8_t* m3, uint8_t* m2,
+                       uint8_t* m1, int32_t* total2, int32_t* total1, void* stream);
+
 /* Ordered compaction of a gate: rows_out[0..n) = ascending flat indices i with
  * gate[i] != 0 (any group), n -> count_out[0].  gate u8 [N] (g==1) or [B,g,HW]
  * (a row is active if any of its g groups is).  Deterministic (single pass,

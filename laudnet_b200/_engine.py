@@ -468,10 +468,8 @@ class ResNetEngine:
                 if p.wd is not None:     # the downsample branch gates its ReLU per pixel
                     check(L.laud_resize_mask_nearest(ptr(small), B, g, S, Ho, ptr(m3), st), "laud_resize_mask_nearest")
             else:
-                check(L.laud_resize_mask_nearest(ptr(small), B, g, S, Ho, ptr(m3), st), "laud_resize_mask_nearest")
-                check(L.laud_expand_mask(ptr(m3), B, g, Ho, Ho, 1, 0, ptr(m2), ptr(counts[2:3]), st), "laud_expand_mask")
-                check(L.laud_expand_mask(ptr(m2), B, g, Ho, Ho, p.stride, 1, ptr(m1), ptr(counts[3:4]), st),
-                      "laud_expand_mask")
+                check(L.laud_spatial_masks(ptr(small), B, g, S, Ho, p.stride, ptr(m3), ptr(m2), ptr(m1), ptr(counts[2:3]),
+                                           ptr(counts[3:4]), st), "laud_spatial_masks")
             if keep is not None:
                 keep.spatial_mask_small, keep.spatial_logits = small.clone(), slog
                 keep.mask_conv3, keep.mask_conv2, keep.mask_conv1 = m3.clone(), m2.clone(), m1.clone()

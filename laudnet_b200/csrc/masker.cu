@@ -491,6 +491,60 @@ __global__ void expand_mask_kernel(const uint8_t* __restrict__ m, int B, int g, 
   if ((threadIdx.x & 31) == 0 && bal && total_out) atomicAdd(total_out, __popc(bal) * g);
 }
 
+// The three spatial masks of a block in ONE launch (laud_resnet.py:105-110): m3 = nearest-resize(small) to the output
+// size, m2 = ExpandMask(1, 0)(m3) (the OR over mask groups), m1 = ExpandMask(stride, 1)(m2) at the input size, with the
+// counts the statistics need.  Everything is a function of the tiny gate map `small`, so each thread derives its cells
+// from it directly.  Thread i < B*Hi*Hi owns input-resolution cell i (m1) and, if i < B*Ho*Ho, output cell i (m3, m2).
+__device__ __forceinline__ int m2_at(const uint8_t* __restrict__ small, int b, int g, int S, int Ho, int y, int x) {
+  const int sy = (y * S) / Ho, sx = (x * S) / Ho;
+  for (int q = 0; q < g; ++q)
+    if (small[(((size_t)b * g + q) * S + sy) * S + sx]) return 1;
+  return 0;
+}
+__global__ void spatial_masks_kernel(const uint8_t* __restrict__ small, int B, int g, int S, int Ho, int stride,
+                                     uint8_t* __restrict__ m3, uint8_t* __restrict__ m2, uint8_t* __restrict__ m1,
+                                     int* __restrict__ total2, int* __restrict__ total1) {
+  const int Hi = Ho * stride;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n_out = (long long)B * Ho * Ho, n_in = (long long)B * Hi * Hi;
+  int f2 = 0, f1 = 0;
+  if (i < n_out) {
+    const int x = (int)(i % Ho), y = (int)((i / Ho) % Ho), b = (int)(i / ((long long)Ho * Ho));
+    const int sy = (y * S) / Ho, sx = (x * S) / Ho;
+    for (int q = 0; q < g; ++q) {
+      const uint8_t v = small[(((size_t)b * g + q) * S + sy) * S + sx];
+      m3[(((size_t)b * g + q) * Ho + y) * Ho + x] = v;
+      f2 |= v != 0;
+    }
+    for (int q = 0; q < g; ++q) m2[(((size_t)b * g + q) * Ho + y) * Ho + x] = (uint8_t)f2;
+  }
+  if (i < n_in) {
+    const int X = (int)(i % Hi), Y = (int)((i / Hi) % Hi), b = (int)(i / ((long long)Hi * Hi));
+    for (int dy = -1; dy <= 1 && !f1; ++dy)
+      for (int dx = -1; dx <= 1 && !f1; ++dx) {
+        const int uy = Y + dy, ux = X + dx;
+        if (uy < 0 || ux < 0 || uy >= Hi || ux >= Hi || uy % stride || ux % stride) continue;
+        f1 = m2_at(small, b, g, S, Ho, uy / stride, ux / stride);
+      }
+    for (int q = 0; q < g; ++q) m1[(((size_t)b * g + q) * Hi + Y) * Hi + X] = (uint8_t)f1;
+  }
+  const unsigned b2 = __ballot_sync(0xffffffffu, f2), b1 = __ballot_sync(0xffffffffu, f1);
+  if ((threadIdx.x & 31) == 0) {
+    if (b2 && total2) atomicAdd(total2, __popc(b2) * g);
+    if (b1 && total1) atomicAdd(total1, __popc(b1) * g);
+  }
+}
+
+extern "C" int laud_spatial_masks(const uint8_t* small, int B, int g, int S, int H_out, int stride, uint8_t* m3, uint8_t* m2,
+                                  uint8_t* m1, int32_t* total2, int32_t* total1, void* stream) {
+  LAUD_REQUIRE(small && m3 && m2 && m1 && B > 0 && g > 0 && S > 0 && H_out > 0 && stride >= 1,
+               "laud_spatial_masks: bad arguments");
+  const long long n = (long long)B * H_out * stride * H_out * stride;
+  spatial_masks_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(small, B, g, S, H_out, stride, m3, m2, m1,
+                                                                                 total2, total1);
+  return check_launch("spatial_masks_kernel");
+}
+
 // Ordered compaction of active rows.  Pass A: per-CTA counts (2048 items each);
 // pass B: one CTA scans the counts; pass C: ordered scatter.
 constexpr int kCompactItems = 2048;
