@@ -769,38 +769,41 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
         const int pt = threadIdx.x - GATHER_WARP0 * 32;          // 0..191 (0..159 with a second MMA warp)
         const int ac = pt & 7, ar0 = pt >> 3;
         const int rstep = pl.dual ? 20 : 24;                     // rows ar0 + rstep * i
+        // per thread, fixed for the whole kernel: where its rows' 16-byte chunk lands in a (swizzled) B tile
+        uint32_t soff[10];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) soff[i] = sw128_off(ar0 + rstep * i, ac);
         int stage = 0;
         uint32_t phase = 0;
         KP_DECL;
         while (walker_next<M>(a, pl, T, wk, s)) {
           KP_LAP(0);
-          int browr[10];
+          // per sub-item: the weight row each of this thread's tile rows comes from (null: zero fill - pad rows)
+          const __half* wrow[10];
 #pragma unroll
           for (int i = 0; i < 10; ++i) {
             const int row = ar0 + rstep * i, jj = s.n0 + row;
-            browr[i] = (row < s.umma_n && jj < s.Nc)
-                           ? (__ldg(a.n_idx + (size_t)s.b * a.n_ld + jj / a.n_gran) * a.n_gran + jj % a.n_gran) * taps * a.C_in
-                           : -1;
+            wrow[i] = (row < s.umma_n && jj < s.Nc)
+                          ? a.w + (size_t)(__ldg(a.n_idx + (size_t)s.b * a.n_ld + jj / a.n_gran) * a.n_gran + jj % a.n_gran) * taps * a.C_in + ac * 8
+                          : nullptr;
           }
+          const int nrow = (s.umma_n - ar0 + rstep - 1) / rstep;   // this thread's rows < umma_n (may be <= 0)
           for (int kq = 0; kq < s.cpt; ++kq) {
             const int n16 = min(4, s.nk16 - kq * 4);
-            const int k = kq * 64 + ac * 8;
-            const bool kok = ac < 2 * n16 && k < a.C_in;
+            const bool kok = ac < 2 * n16 && kq * 64 + ac * 8 < a.C_in;
             KP_LAP(1);
             for (int tap = 0; tap < taps; ++tap) {
               mbar_wait(&T.empty[stage], phase ^ 1);
               KP_LAP(2);
               const uint32_t Bs = smem_base + stage * pl.stage_bytes;
-              const __half* wk_ = a.w + tap * a.C_in + k;
+              const int koff = tap * a.C_in + kq * 64;
               if (ac < 2 * n16) {
 #pragma unroll
-                for (int i = 0; i < 10; ++i) {
-                  const int row = ar0 + rstep * i;
-                  if (row < s.umma_n) {
-                    const bool ok = kok && browr[i] >= 0;
-                    cp_async_16(Bs + sw128_off(row, ac), ok ? wk_ + browr[i] : a.w, ok ? 16u : 0u);
+                for (int i = 0; i < 10; ++i)
+                  if (i < nrow) {
+                    const bool ok = kok && wrow[i] != nullptr;
+                    cp_async_16(Bs + soff[i], ok ? wrow[i] + koff : a.w, ok ? 16u : 0u);
                   }
-                }
               }
               cp_async_arrive(&T.full[stage]);
               if (++stage == pl.stages) { stage = 0; phase ^= 1; }
@@ -1311,19 +1314,41 @@ conv_tma_kernel(const __grid_constant__ ConvArgs a, const __grid_constant__ Plan
           // flush this n-tile's share of the dense rows: the words whose compact position lies in [n0, n0 + n_valid) and,
           // with the sample's first n-tile, the BN constants of every gated pair
           named_bar_sync(5, EPI_THREADS);
+          KP_LAP(6);                                             // (profiling: barrier after staging)
           {
+            // Each lane owns the same four words (channel pairs) of every row: where they come from - a compact staging
+            // word, the BN constant, or another n-tile's flush - is looked up ONCE; the row loop is then four independent
+            // shared-memory loads and four coalesced stores (the straightforward per-word loop was a serial
+            // LDS -> LDS -> STG chain: 12.7k cycles per tile, measured with the lap timers).
             const int nw = a.C_out >> 1, klo = s.n0 >> 1, khi = (s.n0 + s.n_valid) >> 1;
             const bool consts = s.n0 == 0;
-            for (int r = warp; r < rows; r += EPI_WARPS) {
-              const uint32_t src = smem_u32(stg) + (uint32_t)r * (uint32_t)pl.stg_pitch;
-              uint32_t* dst = reinterpret_cast<uint32_t*>(a.y + ((size_t)s.b * HWo + m0 + r) * a.ldy);
-              for (int w = lane; w < nw; w += 32) {
-                const int k = T.wsrc[w];
-                if (k >= klo && k < khi) dst[w] = lds_u1(src + (uint32_t)(k - klo) * 4u);
-                else if (k < 0 && consts) dst[w] = T.cw[w];
+            for (int w0 = lane; w0 < nw; w0 += 128) {
+              int off[4];                                          // >= 0: byte offset in the staging row; -1: constant; -2: skip
+              uint32_t cc[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int w = w0 + 32 * j;
+                off[j] = -2;
+                cc[j] = 0u;
+                if (w < nw) {
+                  const int k = T.wsrc[w];
+                  if (k >= klo && k < khi) off[j] = (k - klo) * 4;
+                  else if (k < 0 && consts) { off[j] = -1; cc[j] = T.cw[w]; }
+                }
+              }
+              for (int r = warp; r < rows; r += EPI_WARPS) {
+                const uint32_t src = smem_u32(stg) + (uint32_t)r * (uint32_t)pl.stg_pitch;
+                uint32_t* dst = reinterpret_cast<uint32_t*>(a.y + ((size_t)s.b * HWo + m0 + r) * a.ldy) + w0;
+                uint32_t v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = off[j] >= 0 ? lds_u1(src + (uint32_t)off[j]) : cc[j];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  if (off[j] >= -1) dst[32 * j] = v[j];
               }
             }
           }
+          KP_LAP(7);                                             // (profiling: flush loop)
           named_bar_sync(5, EPI_THREADS);                        // staging may be overwritten by the next tile
           KP_LAP(5);
         } else {

@@ -777,7 +777,7 @@ def test_network_free_running_vs_golden(cuda_lib, name, channel_exec):
         pytest.skip("no channel gate in this configuration")
     model = _model(cfg, sd)
     model._engine.channel_exec = channel_exec
-    model._engine.nskip_min_width = 0            # (tiny widths: exercise the gather4 path)
+    model._engine.nskip_min_width = model._engine.nskip_min_pixels = 0            # (tiny nets: exercise the gather path)
     keep = []
     with torch.no_grad():
         logits, r3, r2, r1, rc, perc, flops = model(x.to(DEV), 1.0, keep=keep)
