@@ -405,9 +405,17 @@ def run_graft(args, conf):
                 # MACs the kernels really execute: all of them when a gate is executed masked-dense, the gated share when it
                 # is executed as a skip (layer skip over sample lists, gathered channel execution)
                 skipping = ((conf["kw"] == "LAYER" and eng.layer_exec == "skip") or
-                            (conf["kw"] == "HEADLINE" and eng.channel_exec != "dense") or
+                            (conf["kw"] == "HEADLINE" and eng.channel_exec == "sparse") or
                             (conf["kw"] == "SPATIAL" and getattr(eng, "spatial_exec", "mask") != "mask"))
-                roof["executes"] = "gated work skipped" if skipping else "masked-dense (every MAC executed, gates applied in the epilogue)"
+                # "nskip": only the 3x3 layers of the blocks engine.uses_nskip() names skip - and only their gated OUTPUT
+                # channels (N), not the input channels: executed MACs = dense x rho_c there, dense elsewhere
+                nskip_tags = {f"s{p.stage + 1}.conv2": sum(rho_c[q.index] for q in eng.plans if q.stage == p.stage and eng.uses_nskip(q)) /
+                              max(1, sum(1 for q in eng.plans if q.stage == p.stage and eng.uses_nskip(q)))
+                              for p in eng.plans if hasattr(eng, "uses_nskip") and eng.uses_nskip(p)}
+                roof["executes"] = ("gated work skipped" if skipping else
+                                    ("masked-dense, except the gated output channels of " + ", ".join(sorted(nskip_tags)) + " (TMA-free "
+                                     "weight-row gather + expanding epilogue)" if nskip_tags else
+                                     "masked-dense (every MAC executed, gates applied in the epilogue)"))
                 for t, (n_, ms) in sorted(by_tag.items()):
                     w = work.by_class.get(t)
                     if w is None:
@@ -417,7 +425,7 @@ def run_graft(args, conf):
                     gbs = w["bytes"] * B / sec / 1e9
                     classes[t] = {"launches": n_, "ms": round(ms, 4), "achieved_gbs": round(gbs, 1),
                                   "hbm_frac": round(gbs / peaks["hbm_gbs"], 4),
-                                  "executed_tflops": round(2 * (w["macs"] if skipping else w["macs_dense"]) * B / sec / 1e12, 1),
+                                  "executed_tflops": round(2 * (w["macs"] if skipping else w["macs_dense"] * nskip_tags.get(t, 1.0)) * B / sec / 1e12, 1),
                                   "credited_tflops": round(2 * w["macs"] * B / sec / 1e12, 1)}
                 roof["by_layer_class"] = classes
             else:

@@ -219,7 +219,7 @@ class ResNetEngine:
         #             rows arrive by TMA gather4, the MMAs run over N = active columns, the epilogue expands them to dense
         #             rows with the BN constants of the gated channels (laud_conv_desc.n_expand) - the consumer still reads
         #             ordinary dense activations with shared weights.
-        self.channel_exec = os.environ.get("LAUD_CHANNEL_EXEC", "dense")     # measured (profiles/)
+        self.channel_exec = os.environ.get("LAUD_CHANNEL_EXEC", "nskip")     # measured (profiles/r02*): 34.6k vs 34.0k img/s
         # How a layer-gated block executes: "skip" = the convolutions run only on the device-side list of ACTIVE samples
         # and the block output is written in place over the block input (skipped samples are untouched: relu(identity)
         # == identity bit-exactly, laud_resnet.py:133-144); "mask" = masked-dense (compute all, zero the gated rows).
@@ -497,8 +497,7 @@ class ResNetEngine:
         run_conv(x, p.w1, a1, B, Hi, Hi, p.inplanes, Hi, Hi, p.width, 1, 1, 0, ldx=p.inplanes, ldy=ld12,
                  scale=p.s1, shift=p.t1, relu=_lib.RELU_ALL, impl=self.impl, tag=f"s{p.stage + 1}.conv1", **cn, **nm, **sl)
         # conv2 3x3/stride (+ mask) + bn2 + relu     laud_resnet.py:123-126
-        if (dense_gate and self.channel_exec == "nskip" and p.stride == 1 and Ho + 2 <= 128 and p.gran % 2 == 0
-                and p.width >= 128 and self.impl in (_lib.CONV_AUTO, _lib.CONV_UMMA) and not sl):
+        if dense_gate and not sl and self.uses_nskip(p):
             # channel skipping with a dense result: active weight rows by TMA gather4, N = active columns, expanded rows
             run_conv(a1, p.w2, a2, B, Hi, Hi, p.width, Ho, Ho, p.width, 3, 1, 1, ldx=p.width, ldy=p.width,
                      scale=p.s2, shift=p.t2, relu=_lib.RELU_ALL, impl=self.impl, tag=f"s{p.stage + 1}.conv2",
@@ -550,6 +549,16 @@ class ResNetEngine:
             keep.a2 = a2[:B * Ho * Ho * ld12].view(B, Ho, Ho, ld12).clone()
             keep.out = out[:B * Ho * Ho * p.outplanes].view(B, Ho, Ho, p.outplanes).clone()
         return out          # the buffer that holds the block output (the input buffer for an in-place layer skip)
+
+    def uses_nskip(self, p: BlockPlan) -> bool:
+        """True if block p's 3x3 convolution computes only the sample's ACTIVE output channels (laud_conv_desc.n_expand).
+        Where it pays, measured on B200 (profiles/r02*): width >= 256 with at least two m-tiles per sample (14x14 maps:
+        1.36 ms vs 1.55 ms masked-dense over the 22 stage-3 layers of ResNet-101); narrower layers are not MMA-bound and
+        at 7x7 the per-sample weight-row gather (4.7 MB of weights per sample) costs more than the skipped MMAs save."""
+        return (self.channel_exec == "nskip" and p.use_c and p.stride == 1 and p.H_out + 2 <= 128 and p.gran % 2 == 0
+                and p.width >= getattr(self, "nskip_min_width", 256)
+                and p.H_out * p.H_out >= getattr(self, "nskip_min_pixels", 128)
+                and self.impl in (_lib.CONV_AUTO, _lib.CONV_UMMA))
 
     def _run_block_spatial_skip(self, p: BlockPlan, x, out, B, ws, m3, m2, m1, keep):
         """Spatial skipping executed (see spatial_exec): pixel lists of mask_conv1 / mask_conv2 (= mask_conv3 for one mask

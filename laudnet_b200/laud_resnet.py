@@ -131,7 +131,7 @@ class _SoloEngine(ResNetEngine):
     def __init__(self, blk: Bottleneck):
         self.model = None
         self.impl = _lib.CONV_AUTO
-        self.channel_exec = os.environ.get("LAUD_CHANNEL_EXEC", "dense")
+        self.channel_exec = os.environ.get("LAUD_CHANNEL_EXEC", "nskip")
         self.layer_exec = os.environ.get("LAUD_LAYER_EXEC", "skip")
         self.spatial_exec = os.environ.get("LAUD_SPATIAL_EXEC", "mask")
         self._ws = {}

@@ -940,7 +940,7 @@ def test_headline_r101_channel_full_size_fused_gap_equals_standalone_masker(cuda
     model = model.to(DEV).eval()
     x = synth.synth_images(6, 224, 11).to(DEV)
     eng = model._engine
-    assert eng.fuse_gap and eng.channel_exec == "dense"
+    assert eng.fuse_gap and eng.channel_exec in ("dense", "nskip")
     runs = []
     with torch.no_grad():
         for fuse in (True, False):
