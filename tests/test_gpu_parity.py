@@ -1117,7 +1117,7 @@ def test_headline_r101_channel_bs8_graphed_two_chains_vs_oracle(cuda_lib):
     """BASELINE configs[1] (LAUD-ResNet101 channel-2222, calibrated weights) at batch 8: eager forward with every
     gate checked, then the CUDA-graphed two-chain forward that bench.py times - both against the CPU oracle."""
     m = _bs8_vs_oracle("full_r101_channel", graphed_chains=2)
-    assert m._engine.channel_exec in ("dense", "sparse", "auto")
+    assert m._engine.channel_exec in ("dense", "sparse", "nskip")
 
 
 @pytest.mark.parametrize("channel_exec", ["sparse", "dense", "nskip"])
