@@ -513,7 +513,18 @@ def run_graft(args, conf):
             "dynet_simulator": dynet, "cpu_baseline": cpu,
         }) + "\n").encode())
     if world > 1:
-        dist.destroy_process_group()
+        # The communicator's all-gather lives inside a captured CUDA graph: tearing NCCL down while that graph exists
+        # blocks forever (measured: the 2-GPU run printed its line and then sat in destroy_process_group).  Release the
+        # graphs first, meet at a barrier, and leave without the collective teardown.
+        del graphed
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     if parity is not None and not parity["ok"]:
         sys.stderr.write("[bench] PARITY FAILURE: %s\n" % json.dumps(parity))
         sys.exit(3)
