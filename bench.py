@@ -431,6 +431,32 @@ def run_graft(args, conf):
             else:
                 roof.update({"achieved": None, "frac": None,
                              "by_layer_ms": {t: round(ms, 4) for t, (n_, ms) in sorted(by_tag.items())}})
+            if work is not None:
+                # per block: measured densities + the summed conv-kernel time of the block's launches (a block's launches
+                # are consecutive and start with its conv1) - the walk DyNetSimulator's per-block prediction is set against
+                blocks, cur = [], None
+                for t, ms in zip(tags, med):
+                    if t.endswith(".conv1") or cur is None:
+                        cur = {"block": len(blocks), "stage": int(t[1]), "conv_ms": 0.0}
+                        blocks.append(cur)
+                    cur["conv_ms"] += ms
+                for bi, brow in enumerate(blocks):
+                    if bi < len(rho_c):
+                        brow.update({"rho_c": rho_c[bi], "rho3": r3[bi], "rho2": r2[bi], "rho1": r1[bi], "conv_ms": round(brow["conv_ms"], 5)})
+                dpb = os.path.join(ROOT, "profiles", "dynet_per_block_b200.json")
+                if os.path.exists(dpb):        # predicted by the reference's simulator for THESE densities (build container)
+                    pj = json.load(open(dpb)).get(str(args.config))
+                    if pj and len(pj["blocks"]) == len(blocks) and all(
+                            abs(a_["rho_c"] - b_["rho_c"]) < 1e-6 and abs(a_["rho3"] - b_["rho3"]) < 1e-6
+                            for a_, b_ in zip(pj["blocks"], blocks)):
+                        for a_, b_ in zip(pj["blocks"], blocks):
+                            b_["dynet_predicted_ms"] = round(a_["predicted_ms"] * B / pj["batch"], 5)
+                        roof["per_block_note"] = ("dynet_predicted_ms: DyNetSimulator (reference code, FP32 CUDA-core model, B200 "
+                                                  "parameter set) walked over these blocks with these measured densities - "
+                                                  "scripts/make_dynet_per_block.py, profiles/dynet_per_block_b200.json")
+                    else:
+                        roof["per_block_note"] = "profiles/dynet_per_block_b200.json is for other densities (stale): regenerate it"
+                roof["per_block"] = blocks
             # DRAM traffic of the same launches: from the committed ncu capture of THIS build (hash-checked), else null
             traffic, traffic_src = None, "no ncu capture of this build (profiles/conv_traffic.json absent or of another build)"
             tpath = os.path.join(ROOT, "profiles", "conv_traffic.json")

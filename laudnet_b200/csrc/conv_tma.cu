@@ -1710,7 +1710,8 @@ static int conv_forward_tma_x(const ConvArgs& a_in, cudaStream_t s, bool allow_r
   }
   {
     static const bool no_dual = getenv("LAUD_NO_DUAL_MMA") != nullptr;            // A/B switch
-    pl.dual = (!no_dual && pl.MT == 2 && (pl.omode == OUT_DIRECT || pl.omode == OUT_EXPAND) &&
+    // (slab layers too, unless warp 15 is a pooling warp of the fused GAP)
+    pl.dual = (!no_dual && pl.MT == 2 && (pl.omode == OUT_DIRECT || pl.omode == OUT_EXPAND || (pl.omode == OUT_SLAB && !pl.gap)) &&
                (pl.bmode == BMODE_TMA || pl.bmode == BMODE_G4)) ? 1 : 0;
   }
   pl.full_count = pl.bmode == BMODE_G4 ? (pl.g4_cp ? (pl.dual ? GATHER_THREADS - 32 : GATHER_THREADS) : 1)
