@@ -9,7 +9,8 @@ from ._lib import LaudError, LIB_PATH  # noqa: F401
 from .laud_resnet import Bottleneck, ResNet, uni_resnet50, uni_resnet101  # noqa: F401
 from .laud_regnet import (LAD_RegNet, lad_regnet_y_400mf, lad_regnet_y_800mf, lad_regnet_y_1_6gf,  # noqa: F401
                           lad_regnet_y_3_2gf, lad_regnet_y_8gf, lad_regnet_y_16gf)
+from .mmdet_adapter import LAD_MMDet_ResNet  # noqa: F401
 from .utils import (ExpandMask, Masker_channel_conv_linear, Masker_channel_MLP, Masker_spatial,  # noqa: F401
                     apply_channel_mask, apply_spatial_mask)
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"

@@ -622,7 +622,7 @@ class ResNetEngine:
     # ----------------------------------------------------------------- forward
     def forward(self, x: torch.Tensor, keep: Optional[List[BlockOutputs]] = None, slot: int = 0,
                 logits_out: Optional[torch.Tensor] = None, want_stats: bool = True, forced=None, gumbel_noise=None,
-                temperature: float = 1.0):
+                temperature: float = 1.0, stage_outputs: Optional[list] = None):
         """forced (tests): per block a pair (channel mask [B,G] | None, spatial mask [B,g,S,S] | None) installed
         instead of the block's own gating decision - the teacher-forced network forward.
         gumbel_noise: per block a pair (channel sample [B,2G] | None, spatial sample [B,2g,S,S] | None): the gates take
@@ -630,9 +630,12 @@ class ResNetEngine:
         if x.device.type != "cuda":
             raise LaudError("ResNet.forward: expected a CUDA tensor - there is no CPU path")
         with torch.cuda.device(x.device):        # launches go to the current stream of the INPUT's device
-            return self._forward(x, keep, slot, logits_out, want_stats, forced, gumbel_noise, temperature)
+            return self._forward(x, keep, slot, logits_out, want_stats, forced, gumbel_noise, temperature, stage_outputs)
 
-    def _forward(self, x, keep, slot, logits_out, want_stats, forced=None, gumbel_noise=None, temperature=1.0):
+    def _forward(self, x, keep, slot, logits_out, want_stats, forced=None, gumbel_noise=None, temperature=1.0,
+                 stage_outputs=None):
+        """stage_outputs: a list -> BACKBONE mode (the mmdet adapter): the output of the last block of every stage is
+        appended as fp32 NCHW, no classifier head is run and the returned flops exclude it (lad_mmdet_resnet.py:680-751)."""
         m = self.model
         if self.prepared_for != x.device:
             self.prepare()
@@ -672,6 +675,13 @@ class ResNetEngine:
                 torch.cuda.nvtx.range_pop()
             if res_buf is not bufs[cur]:
                 cur = nxt
+            if stage_outputs is not None and (p.index + 1 == len(self.plans) or self.plans[p.index + 1].stage != p.stage):
+                from .utils import to_nchw_f32
+                stage_outputs.append(to_nchw_f32(bufs[cur][:B * p.H_out * p.H_out * p.outplanes].view(B, p.H_out, p.H_out, p.outplanes)))
+        if stage_outputs is not None:
+            stats = torch.empty_like(ws["stats"])
+            self._launch_stats(ws["counts"], ws["consts"], H, W, stats, head=False)
+            return None, stats
         last = self.plans[-1]
         feat = last.outplanes
         ncls = m.fc.weight.shape[0]
@@ -689,13 +699,13 @@ class ResNetEngine:
         self._launch_stats(ws["counts"], ws["consts"], H, W, stats)
         return logits, stats
 
-    def _launch_stats(self, counts, consts, H, W, stats) -> None:
+    def _launch_stats(self, counts, consts, H, W, stats, head: bool = True) -> None:
         m = self.model
         C0 = m.conv1.weight.shape[0]
         feat, ncls = self.plans[-1].outplanes, m.fc.weight.shape[0]
         stem_flops = 3 * C0 * (H // 2) * (W // 2) * 49 + C0 * (H // 4) * (W // 4) * 9
-        check(lib().laud_forward_stats(ptr(counts), ptr(consts), len(self.plans), stem_flops, feat, feat * ncls,
-                                       ptr(stats), stream_ptr()), "laud_forward_stats")
+        check(lib().laud_forward_stats(ptr(counts), ptr(consts), len(self.plans), stem_flops, feat if head else 0,
+                                       feat * ncls if head else 0, ptr(stats), stream_ptr()), "laud_forward_stats")
 
     def forward_split(self, x: torch.Tensor, splits: int):
         """The forward as `splits` independent chains over contiguous slices of the batch, each on its own stream

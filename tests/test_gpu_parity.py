@@ -1154,6 +1154,51 @@ def test_regnet_y_800mf_spatial_bs8_full_size_vs_oracle(cuda_lib, spatial_exec):
     _bs8_vs_oracle("full_regnety800_spatial", graphed_chains=1, setup=lambda m: setattr(m._engine, "spatial_exec", spatial_exec))
 
 
+# --------------------------------------------------------------------------- detection-backbone adapter
+@pytest.mark.parametrize("mode,side", [("channel", 128), ("layer", 96)])
+def test_mmdet_backbone_adapter_vs_oracle(cuda_lib, mode, side):
+    """LAD_MMDet_ResNet.forward (lad_mmdet_resnet.py:680-751) on the CUDA engine: the four stage feature maps, the
+    additional dict (densities, flops_perc, flops without the classifier head, dense_flops) and model_configs, for a
+    detection-style input size, against the oracle's block trace with its gating decisions installed; then a second
+    input size through the same module (the masks follow the actual feature size, :274)."""
+    kw = dict(depth=50, out_indices=(0, 1, 2, 3), norm_eval=True, sparsity_target=0.5, temperature_0=1.0, temperature_t=0.01,
+              channel_dyn_granularity=[2, 2, 2, 2], dyn_mode=[mode] * 4, channel_masker=["MLP"] * 4,
+              channel_masker_layers=[2] * 4, reduction_ratio=[16] * 4, mask_spatial_granularity=[1, 1, 1, 1])
+    model = L.LAD_MMDet_ResNet(**kw)
+    cfg = O.ResNetCfg(layers=(3, 4, 6, 3), input_size=side, num_classes=1, dyn_mode=(mode,) * 4,
+                      channel_dyn_granularity=(2, 2, 2, 2), mask_spatial_granularity=(side // 4, side // 8, side // 16, side // 32)
+                      if mode == "layer" else (1, 1, 1, 1))
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    shapes.update({"fc.weight": (1, 2048), "fc.bias": (1,)})
+    x = synth.synth_images(3, side, 41)
+    sd = synth.calibrate_resnet(synth.synth_state_dict(shapes, 41), O.resnet_geometry(cfg), x, 41, channel_rate=0.6, layer_rate=0.5)
+    model.load_state_dict({k: v for k, v in sd.items() if not k.startswith("fc.")}, strict=True)
+    model = model.to(DEV).eval()
+    traces = []
+    with torch.no_grad():
+        ref = O.resnet_forward(sd, cfg, x, traces)
+        outs, additional, model_configs = model(x.to(DEV), 0, 100, forced=_forced_masks(traces))
+        torch.cuda.synchronize()
+    assert model_configs == {"dyn_mode": [mode] * 4, "sparsity_target": 0.5}
+    last = [2, 6, 12, 15]                                          # last block of each ResNet-50 stage
+    assert len(outs) == 4
+    for o, bi, c, h in zip(outs, last, (256, 512, 1024, 2048), (side // 4, side // 8, side // 16, side // 32)):
+        assert tuple(o.shape) == (3, c, h, h) and o.dtype == torch.float32
+        assert _rel_err(o, traces[bi].out) <= 2e-3
+    np.testing.assert_array_equal(torch.cat(additional["channel_sparsity"]).cpu().numpy(), torch.cat(list(ref[4])).numpy())
+    np.testing.assert_array_equal(torch.cat(additional["spatial_sparsity_conv3"]).cpu().numpy(), torch.cat(list(ref[1])).numpy())
+    np.testing.assert_allclose(additional["flops_perc_list"].cpu().numpy(), ref[5].numpy(), rtol=1e-6)
+    head = 2048 + 2048 * 1                                         # the oracle's classifier terms (laud_resnet.py:349-356)
+    np.testing.assert_allclose(additional["flops"].item(), ref[6].item() - head, rtol=1e-6)
+    assert additional["dense_flops"].item() > additional["flops"].item()
+    # free-running (the backbone's own gates) on another input side through the same module
+    x2 = synth.synth_images(2, side + 32, 42)
+    with torch.no_grad():
+        outs2, add2, _ = model(x2.to(DEV))
+    assert tuple(outs2[0].shape) == (2, 256, (side + 32) // 4, (side + 32) // 4) and torch.isfinite(outs2[3]).all()
+    assert 0.0 < float(add2["flops_perc_list"].mean()) <= 1.0
+
+
 # =========================================================================== LAUD-RegNet-Y (laud_regnet.py)
 from tests.golden_cases import REGNET_CASES, load_regnet_case, regnet_model     # noqa: E402
 

@@ -347,3 +347,30 @@ def test_validate_matches_reference_loop_gloo_world2():
         assert p.exitcode == 0
     assert [r[:3] for r in res] == [(0, True, True), (1, True, True)]
     assert np.allclose(res[0][3], res[1][3])
+
+
+def test_mmdet_adapter_interface_and_state_dict_keys():
+    """laudnet_b200.LAD_MMDet_ResNet: the reference backbone's constructor keywords, its parameter names
+    (the reference classifier's keys minus `fc.*`: build_norm_layer(postfix) names the norms bn1..3), and the refusals."""
+    import json
+    import laudnet_b200 as L
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_state_dict.json")))
+    kw = dict(depth=101, num_stages=4, out_indices=(0, 1, 2, 3), frozen_stages=1, norm_cfg=dict(type="BN", requires_grad=True),
+              norm_eval=True, style="pytorch", sparsity_target=0.5, temperature_0=1.0, temperature_t=0.01,
+              spatial_mask_channel_group=[1, 1, 1, 1], mask_spatial_granularity=[1, 1, 1, 1], channel_dyn_granularity=[2, 2, 2, 2],
+              dyn_mode=["channel"] * 4, channel_masker=["MLP"] * 4, channel_masker_layers=[2] * 4, reduction_ratio=[16] * 4)
+    m = L.LAD_MMDet_ResNet(**kw)          # the backbone dict of the reference's faster_rcnn ... channel_2222 config (:14-20)
+    keys = set(m.state_dict().keys())
+    fx = ref["r101_channel2222"]                     # keys of the REFERENCE classifier with the same LAUD kwargs
+    names = fx["shapes"].keys() if "shapes" in fx else fx["keys"]
+    assert keys == {k for k in names if not k.startswith("fc.")}
+    assert not any(k.startswith(("fc.", "_net.")) for k in keys) and "layer3.22.masker_channel.conv.2.bias" in keys
+    assert m.norm1 is m.bn1
+    m.train()
+    assert not m.bn1.training and m.layer1[0].masker_channel.training          # norm_eval: BN frozen, gates train
+    with pytest.raises(_lib.LaudError):
+        L.LAD_MMDet_ResNet(depth=50, dyn_mode=["spatial"] * 4)                 # the reference backbone has no such masker
+    with pytest.raises(_lib.LaudError):
+        L.LAD_MMDet_ResNet(depth=50, dyn_mode=["layer"] * 4, deep_stem=True)
+    with pytest.raises(_lib.LaudError):
+        m(torch.zeros(1, 3, 800, 1344))                                         # rectangular inputs: not this round
