@@ -1184,7 +1184,7 @@ def test_mmdet_backbone_adapter_vs_oracle(cuda_lib, mode, side):
     assert len(outs) == 4
     for o, bi, c, h in zip(outs, last, (256, 512, 1024, 2048), (side // 4, side // 8, side // 16, side // 32)):
         assert tuple(o.shape) == (3, c, h, h) and o.dtype == torch.float32
-        assert _rel_err(o, traces[bi].out) <= 2e-3
+        assert _rel_err(o, traces[bi].out) <= LOGIT_TOL            # free-running fp16 chain (up to 16 blocks), oracle gates
     np.testing.assert_array_equal(torch.cat(additional["channel_sparsity"]).cpu().numpy(), torch.cat(list(ref[4])).numpy())
     np.testing.assert_array_equal(torch.cat(additional["spatial_sparsity_conv3"]).cpu().numpy(), torch.cat(list(ref[1])).numpy())
     np.testing.assert_allclose(additional["flops_perc_list"].cpu().numpy(), ref[5].numpy(), rtol=1e-6)
