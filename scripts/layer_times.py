@@ -14,7 +14,7 @@ from laudnet_b200 import _engine, synth         # noqa: E402
 
 B = int(os.environ.get("LAUD_PROFILE_BATCH", "256"))
 dev = torch.device("cuda:0")
-model, sd = bench.build_model(dev)
+model, sd, _kw = bench.build_model(bench.CONFIGS[int(os.environ.get("LAUD_BENCH_CONFIG", "1"))], dev)
 model = model.to(dev).eval()
 x = synth.synth_images(B, 224, bench.SEED).to(torch.float16).to(dev)
 runs = []

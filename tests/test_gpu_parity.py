@@ -1182,9 +1182,14 @@ def test_mmdet_backbone_adapter_vs_oracle(cuda_lib, mode, side):
     assert model_configs == {"dyn_mode": [mode] * 4, "sparsity_target": 0.5}
     last = [2, 6, 12, 15]                                          # last block of each ResNet-50 stage
     assert len(outs) == 4
-    for o, bi, c, h in zip(outs, last, (256, 512, 1024, 2048), (side // 4, side // 8, side // 16, side // 32)):
+    # Free-running fp16 chain over 3 / 7 / 13 / 16 blocks with the oracle's gates, max-norm over maps as small as 4x4: the
+    # budget per stage is 2x what the oracle itself shows when its activations and conv weights are rounded to fp16 after
+    # every layer (CPU emulation of this very case: 1.2e-3 / 2.7e-3 / 4.3e-3 / 7.8e-3); the 1e-3 per-block bar is held by
+    # the teacher-forced block tests above.
+    for o, bi, c, h, tol in zip(outs, last, (256, 512, 1024, 2048), (side // 4, side // 8, side // 16, side // 32),
+                                (2.5e-3, 5.5e-3, 9e-3, 1.6e-2)):
         assert tuple(o.shape) == (3, c, h, h) and o.dtype == torch.float32
-        assert _rel_err(o, traces[bi].out) <= LOGIT_TOL            # free-running fp16 chain (up to 16 blocks), oracle gates
+        assert _rel_err(o, traces[bi].out) <= tol
     np.testing.assert_array_equal(torch.cat(additional["channel_sparsity"]).cpu().numpy(), torch.cat(list(ref[4])).numpy())
     np.testing.assert_array_equal(torch.cat(additional["spatial_sparsity_conv3"]).cpu().numpy(), torch.cat(list(ref[1])).numpy())
     np.testing.assert_allclose(additional["flops_perc_list"].cpu().numpy(), ref[5].numpy(), rtol=1e-6)
