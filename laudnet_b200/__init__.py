@@ -10,6 +10,7 @@ from .laud_resnet import Bottleneck, ResNet, uni_resnet50, uni_resnet101  # noqa
 from .laud_regnet import (LAD_RegNet, lad_regnet_y_400mf, lad_regnet_y_800mf, lad_regnet_y_1_6gf,  # noqa: F401
                           lad_regnet_y_3_2gf, lad_regnet_y_8gf, lad_regnet_y_16gf)
 from .mmdet_adapter import LAD_MMDet_ResNet  # noqa: F401
+from .adavit import AdaViT, ada_deit_tiny_patch16_224, ada_deit_small_patch16_224, ada_deit_base_patch16_224  # noqa: F401
 from .utils import (ExpandMask, Masker_channel_conv_linear, Masker_channel_MLP, Masker_spatial,  # noqa: F401
                     apply_channel_mask, apply_spatial_mask)
 

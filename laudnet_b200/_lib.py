@@ -50,7 +50,27 @@ class ConvDesc(C.Structure):
     ]
 
 
-# name -> argtypes; every symbol include/laud_b200.h declares must be listed here
+class TokGemmDesc(C.Structure):
+    """Mirror of `struct laud_tok_gemm_desc` (include/laud_adavit.h)."""
+    _fields_ = [
+        ("a", _vp), ("lda", C.c_int32),
+        ("w", _vp),
+        ("bias", _vp),
+        ("rows_max", C.c_int32), ("K", C.c_int32), ("N", C.c_int32),
+        ("row_cnt", _vp),
+        ("act", C.c_int32),
+        ("out", _vp), ("ldo", C.c_int32),
+        ("resid", _vp), ("ldres", C.c_int32),
+        ("row_idx", _vp),
+        ("col_gate", _vp), ("gate_ld", C.c_int32),
+        ("row_sample", _vp),
+        ("bn", C.c_int32),
+    ]
+
+
+ACT_NONE, ACT_GELU = 0, 1
+
+# name -> argtypes; every symbol include/*.h declares must be listed here
 SIGNATURES = {
     "laud_abi_version": ([], C.c_int),
     "laud_last_error": ([], C.c_char_p),
@@ -84,6 +104,16 @@ SIGNATURES = {
     "laud_nchw_to_nhwc_f16": ([_vp, _i, _i, _i, _i, _i, _vp, _i, _vp], _i),
     "laud_nhwc_f16_to_nchw_f32": ([_vp, _i, _i, _i, _i, _i, _fp, _vp], _i),
     "laud_forward_stats": ([_i32p, _vp, _i, _i64, _i64, _i64, _fp, _vp], _i),
+    # include/laud_adavit.h
+    "laud_tok_gemm": ([C.POINTER(TokGemmDesc), _vp], _i),
+    "laud_tok_gemm_launch_count": ([], C.c_ulonglong),
+    "laud_vit_patchify": ([_vp, _i, _i, _i, _vp, _vp], _i),
+    "laud_vit_init_tokens": ([_fp, _i, _i, _i, _fp, _fp, _vp], _i),
+    "laud_adavit_policy": ([_fp, _i, _i, _i, _i, C.c_float, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp,
+                            _u8p, _i32p, _u8p, _u8p, _fp, _fp, _fp, _vp], _i),
+    "laud_adavit_lists": ([_i32p, _u8p, _i, _i32p, _i32p, _vp], _i),
+    "laud_adavit_ln_gather": ([_fp, _i, _i, _i, C.c_float, _fp, _fp, _u8p, _i32p, _vp, _i32p, _i32p, _vp], _i),
+    "laud_adavit_attention": ([_vp, _i, _i32p, _u8p, _i, _i, _i, _vp, _vp], _i),
 }
 
 _lib: Optional[C.CDLL] = None

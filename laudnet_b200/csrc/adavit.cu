@@ -1,0 +1,690 @@
+// AdaViT token / head / layer-skip block for sm_100a (include/laud_adavit.h; self-oracle oracle/adavit_oracle.py).
+//
+//   tok_gemm_kernel        persistent, warp-specialised tcgen05 GEMM over COMPACT token rows with a device-side row count:
+//                          warp 0 = TMA producer (A rows and W rows as 128B-swizzled K-major tiles), warp 1 = MMA issuer
+//                          (warp-uniform, tcgen05.mma M=128 N=bn K=16, fp32 accumulators double-buffered in TMEM),
+//                          warps 2-5 = epilogue (tcgen05.ld -> bias / GELU -> fp16 rows, or fp32 add into the residual
+//                          stream at the rows' destinations).  Dropped tokens are simply not in the row list; dropped heads
+//                          drop whole n-tiles of the QKV projection (col_gate).
+//   adavit_attention_kernel one CTA per (sample, head): kept tokens only, softmax(QK^T)V on warp-level tensor cores
+//                          (mma.sync m16n8k16, the whole score row lives in registers: L <= 208).
+//   policy / lists / ln_gather / patchify / init: the HBM-bound glue (one pass over the fp32 token stream each).
+#include <cuda.h>
+#include <string.h>
+#include "laud_adavit.h"
+#include "laud_common.cuh"
+#include "umma_ptx.cuh"
+
+namespace laud {
+namespace {
+
+std::atomic<unsigned long long> g_tok_gemm_launches{0};
+
+// =====================================================================================================================
+// token GEMM
+// =====================================================================================================================
+constexpr int TG_BM = 128, TG_BK = 64, TG_STAGES = 4;
+constexpr int TG_THREADS = 192;                       // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int TG_A_BYTES = TG_BM * 128;
+constexpr int TG_ACC_STRIDE = 256;                    // TMEM columns between the two accumulator buffers
+
+struct TgArgs {
+  const float* bias;
+  int rows_max, K, N, bn;
+  const int* row_cnt;
+  int act;
+  __half* out; int ldo;
+  float* resid; int ldres;
+  const int* row_idx;
+  const uint8_t* col_gate; int gate_ld;
+  const int* row_sample;
+};
+
+struct alignas(8) TgBars {
+  unsigned long long full[TG_STAGES], empty[TG_STAGES], tfull[2], tempty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ bool tg_tile_active(const TgArgs& a, int m, int nt, int cnt) {
+  if (!a.col_gate) return true;
+  const int r0 = m * TG_BM, r1 = min(r0 + TG_BM, cnt) - 1;
+  const int s0 = __ldg(a.row_sample + r0), s1 = __ldg(a.row_sample + r1);
+  for (int s = s0; s <= s1; ++s)
+    if (__ldg(a.col_gate + (size_t)s * a.gate_ld + nt)) return true;
+  return false;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+__global__ void __launch_bounds__(TG_THREADS, 1)
+tok_gemm_kernel(const TgArgs a, const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ TgBars bars;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int stage_bytes = TG_A_BYTES + a.bn * 128;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TG_STAGES; ++i) { mbar_init(&bars.full[i], 1); mbar_init(&bars.empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars.tfull[i], 1); mbar_init(&bars.tempty[i], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars.tmem_base)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars.tmem_base;
+
+  const int cnt = a.row_cnt ? min(__ldg(a.row_cnt), a.rows_max) : a.rows_max;
+  const int m_tiles = (cnt + TG_BM - 1) / TG_BM, n_tiles = (a.N + a.bn - 1) / a.bn;
+  const int items = m_tiles * n_tiles, kchunks = a.K / TG_BK;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        const int m = it / n_tiles, nt = it - m * n_tiles;
+        if (!tg_tile_active(a, m, nt, cnt)) continue;
+        for (int kc = 0; kc < kchunks; ++kc) {
+          mbar_wait(&bars.empty[stage], phase ^ 1u);
+          const uint32_t As = smem_base + stage * stage_bytes;
+          mbar_arrive_expect_tx(&bars.full[stage], (uint32_t)stage_bytes);
+          tma_load_2d(As, &map_a, &bars.full[stage], kc * TG_BK, m * TG_BM);
+          tma_load_2d(As + TG_A_BYTES, &map_b, &bars.full[stage], kc * TG_BK, nt * a.bn);
+          if (++stage == TG_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (warp-uniform, elected lane issues)
+    const uint32_t idesc = umma_idesc_f16(a.bn, 0);
+    int stage = 0, buf = 0;
+    uint32_t phase = 0, bphase = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      const int m = it / n_tiles, nt = it - m * n_tiles;
+      if (!tg_tile_active(a, m, nt, cnt)) continue;
+      mbar_wait(&bars.tempty[buf], bphase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + buf * TG_ACC_STRIDE;
+      for (int kc = 0; kc < kchunks; ++kc) {
+        mbar_wait(&bars.full[stage], phase);
+        tc_fence_after();
+        const uint32_t As = smem_base + stage * stage_bytes;
+        const uint64_t ad = umma_desc(As, 16, 1024), bd = umma_desc(As + TG_A_BYTES, 16, 1024);
+        umma_f16_elect_x4(d_tmem, ad, bd, idesc, kc ? 1u : 0u, 2u);
+        umma_commit_elect(&bars.empty[stage]);
+        if (++stage == TG_STAGES) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit_elect(&bars.tfull[buf]);
+      if (++buf == 2) { buf = 0; bphase ^= 1u; }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------ epilogue: one accumulator row (TMEM lane) per thread
+    const int q = warp & 3;
+    int buf = 0;
+    uint32_t bphase = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      const int m = it / n_tiles, nt = it - m * n_tiles;
+      if (!tg_tile_active(a, m, nt, cnt)) continue;
+      const int row = m * TG_BM + q * 32 + lane;
+      const bool valid = row < cnt;
+      const int n0 = nt * a.bn;
+      float* rdst = nullptr;
+      __half* hdst = nullptr;
+      if (valid) {
+        if (a.resid) rdst = a.resid + (size_t)__ldg(a.row_idx + row) * a.ldres + n0;
+        else hdst = a.out + (size_t)row * a.ldo + n0;
+      }
+      mbar_wait(&bars.tfull[buf], bphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + buf * TG_ACC_STRIDE + ((uint32_t)(q * 32) << 16);
+      for (int c0 = 0; c0 < a.bn; c0 += 32) {
+        const int ncol = min(32, a.N - (n0 + c0));           // warp-uniform
+        if (ncol <= 0) break;
+        float v[32];
+        tmem_ld32(taddr + c0, v);
+        if (valid) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (g * 8 >= ncol) break;
+          float r[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r[j] = v[g * 8 + j];
+          if (a.bias) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + c0 + g * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + c0 + g * 8 + 4));
+            r[0] += b0.x; r[1] += b0.y; r[2] += b0.z; r[3] += b0.w;
+            r[4] += b1.x; r[5] += b1.y; r[6] += b1.z; r[7] += b1.w;
+          }
+          if (a.act == LAUD_ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = gelu_erf(r[j]);
+          }
+          if (rdst) {
+            float4* p = reinterpret_cast<float4*>(rdst + c0 + g * 8);
+            float4 x0 = p[0], x1 = p[1];
+            x0.x += r[0]; x0.y += r[1]; x0.z += r[2]; x0.w += r[3];
+            x1.x += r[4]; x1.y += r[5]; x1.z += r[6]; x1.w += r[7];
+            p[0] = x0; p[1] = x1;
+          } else {
+            __half2 h0 = __floats2half2_rn(r[0], r[1]), h1 = __floats2half2_rn(r[2], r[3]);
+            __half2 h2 = __floats2half2_rn(r[4], r[5]), h3 = __floats2half2_rn(r[6], r[7]);
+            uint4 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(hdst + c0 + g * 8) = pk;
+          }
+        }
+        }
+        __syncwarp();                                          // tcgen05.ld is warp-collective: reconverge before the next one
+      }
+      tc_fence_before();
+      mbar_arrive(&bars.tempty[buf]);
+      if (++buf == 2) { buf = 0; bphase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tg_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+// fp16 [rows, ld] row-major, box {64 columns, box_rows}, 128-byte swizzle, out-of-bounds rows read as zero
+bool tg_map(CUtensorMap* m, const void* base, long long cols, long long rows, long long ld, int box_rows) {
+  EncodeTiledFn fn = tg_encode_fn();
+  if (!fn) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows}, gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows}, es[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+struct DevInfo { int sms; bool gemm_attr, attn_attr; };
+DevInfo g_dev[MAX_DEVICES];
+
+// =====================================================================================================================
+// LayerNorm helpers: one warp per token, element j = lane + 32 i
+// =====================================================================================================================
+constexpr int LN_MAX_NV = 32;      // D <= 1024
+
+__device__ __forceinline__ void warp_ln_stats(const float* __restrict__ xr, int nv, int D, float eps, float* xv, float& mean,
+                                              float& rstd) {
+  const int lane = threadIdx.x & 31;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_NV; ++i)
+    if (i < nv) { xv[i] = xr[lane + 32 * i]; s += xv[i]; }
+  mean = warp_sum(s) / (float)D;
+  float v = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_NV; ++i)
+    if (i < nv) { const float d = xv[i] - mean; v += d * d; }
+  rstd = rsqrtf(warp_sum(v) / (float)D + eps);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// policy: grid = B, 256 threads
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adavit_policy_kernel(const float* __restrict__ x, int L, int D, int H, float eps, const float* n1_w, const float* n1_b,
+                     const float* ts_w, const float* ts_b, const float* np_w, const float* np_b, const float* ls_w,
+                     const float* ls_b, const float* hs_w, const float* hs_b, uint8_t* tok_mask, int* tok_cnt,
+                     uint8_t* head_sel, uint8_t* layer_sel, float* tok_logits, float* head_logits, float* layer_logits) {
+  __shared__ int s_cnt;
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int nv = D / 32;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  float xv[LN_MAX_NV];
+  int kept = 0;
+  if (ts_w) {
+    for (int l = 1 + warp; l < L; l += nwarps) {
+      float mean, rstd;
+      warp_ln_stats(x + ((size_t)b * L + l) * D, nv, D, eps, xv, mean, rstd);
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < LN_MAX_NV; ++i)
+        if (i < nv) {
+          const int j = lane + 32 * i;
+          acc += ((xv[i] - mean) * rstd * __ldg(n1_w + j) + __ldg(n1_b + j)) * __ldg(ts_w + j);
+        }
+      const float lg = warp_sum(acc) + __ldg(ts_b);
+      const bool keep = lg >= 0.f;
+      if (lane == 0) {
+        tok_mask[(size_t)b * L + l] = keep ? 1 : 0;
+        if (tok_logits) tok_logits[(size_t)b * L + l] = lg;
+      }
+      kept += keep ? 1 : 0;
+    }
+  } else {
+    for (int l = 1 + threadIdx.x; l < L; l += blockDim.x) {
+      tok_mask[(size_t)b * L + l] = 1;
+      if (tok_logits) tok_logits[(size_t)b * L + l] = 0.f;
+    }
+  }
+  if (lane == 0 && kept) atomicAdd(&s_cnt, kept);
+  // the class token: always kept; it is the policy token of the layer / head decisions
+  if (warp == 0) {
+    if (lane == 0) {
+      tok_mask[(size_t)b * L] = 1;
+      if (tok_logits) tok_logits[(size_t)b * L] = 0.f;
+    }
+    if (ls_w || hs_w) {
+      float mean, rstd;
+      warp_ln_stats(x + (size_t)b * L * D, nv, D, eps, xv, mean, rstd);
+#pragma unroll
+      for (int i = 0; i < LN_MAX_NV; ++i)
+        if (i < nv) {
+          const int j = lane + 32 * i;
+          xv[i] = (xv[i] - mean) * rstd * __ldg(np_w + j) + __ldg(np_b + j);
+        }
+      const int n_out = (ls_w ? 2 : 0) + (hs_w ? H : 0);
+      for (int o = 0; o < n_out; ++o) {
+        const bool is_layer = ls_w && o < 2;
+        const int r = is_layer ? o : o - (ls_w ? 2 : 0);
+        const float* wrow = (is_layer ? ls_w : hs_w) + (size_t)r * D;
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < LN_MAX_NV; ++i)
+          if (i < nv) acc += xv[i] * __ldg(wrow + lane + 32 * i);
+        const float lg = warp_sum(acc) + __ldg((is_layer ? ls_b : hs_b) + r);
+        if (lane == 0) {
+          if (is_layer) {
+            layer_sel[b * 2 + r] = lg >= 0.f ? 1 : 0;
+            if (layer_logits) layer_logits[b * 2 + r] = lg;
+          } else {
+            head_sel[(size_t)b * H + r] = lg >= 0.f ? 1 : 0;
+            if (head_logits) head_logits[(size_t)b * H + r] = lg;
+          }
+        }
+      }
+    }
+    if (!ls_w && lane < 2) {
+      layer_sel[b * 2 + lane] = 1;
+      if (layer_logits) layer_logits[b * 2 + lane] = 0.f;
+    }
+    if (!hs_w)
+      for (int h = lane; h < H; h += 32) {
+        head_sel[(size_t)b * H + h] = 1;
+        if (head_logits) head_logits[(size_t)b * H + h] = 0.f;
+      }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) tok_cnt[b] = ts_w ? s_cnt + 1 : L;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// lists: one CTA, ordered exclusive scans of the per-sample row counts of the two sub-layers
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+adavit_lists_kernel(const int* __restrict__ tok_cnt, const uint8_t* __restrict__ layer_sel, int B, int* off_attn, int* off_mlp) {
+  __shared__ int s_a[1024], s_m[1024];
+  __shared__ int carry_a, carry_m;
+  if (threadIdx.x == 0) { carry_a = 0; carry_m = 0; }
+  __syncthreads();
+  for (int base = 0; base < B; base += 1024) {
+    const int b = base + threadIdx.x;
+    const int ca = b < B && layer_sel[b * 2] ? tok_cnt[b] : 0, cm = b < B && layer_sel[b * 2 + 1] ? tok_cnt[b] : 0;
+    s_a[threadIdx.x] = ca;
+    s_m[threadIdx.x] = cm;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {                       // Hillis-Steele inclusive scan (integers: order-free)
+      const int va = threadIdx.x >= o ? s_a[threadIdx.x - o] : 0, vm = threadIdx.x >= o ? s_m[threadIdx.x - o] : 0;
+      __syncthreads();
+      s_a[threadIdx.x] += va;
+      s_m[threadIdx.x] += vm;
+      __syncthreads();
+    }
+    if (b < B) {
+      off_attn[b] = carry_a + s_a[threadIdx.x] - ca;
+      off_mlp[b] = carry_m + s_m[threadIdx.x] - cm;
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) { carry_a += s_a[1023]; carry_m += s_m[1023]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { off_attn[B] = carry_a; off_mlp[B] = carry_m; }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// LayerNorm + gather of the kept tokens: grid = B, 256 threads
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adavit_ln_gather_kernel(const float* __restrict__ x, int L, int D, float eps, const float* __restrict__ w,
+                        const float* __restrict__ bias, const uint8_t* __restrict__ tok_mask, const int* __restrict__ off,
+                        __half* __restrict__ y, int* row_idx, int* row_sample) {
+  __shared__ short s_rank[1024];
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int o0 = off[b], n = off[b + 1] - o0;
+  if (n <= 0) return;
+  if (warp == 0) {                                             // ordered ranks of the kept tokens
+    int run = 0;
+    for (int l0 = 0; l0 < L; l0 += 32) {
+      const int l = l0 + lane;
+      const bool k = l < L && (!tok_mask || tok_mask[(size_t)b * L + l]);
+      const unsigned m = __ballot_sync(0xffffffffu, k);
+      if (l < L) s_rank[l] = k ? (short)(run + __popc(m & ((1u << lane) - 1u))) : (short)-1;
+      run += __popc(m);
+    }
+  }
+  __syncthreads();
+  const int nv = D / 32;
+  float xv[LN_MAX_NV];
+  for (int l = warp; l < L; l += nwarps) {
+    const int rk = s_rank[l];
+    if (rk < 0) continue;
+    float mean, rstd;
+    warp_ln_stats(x + ((size_t)b * L + l) * D, nv, D, eps, xv, mean, rstd);
+    __half* yr = y + (size_t)(o0 + rk) * D;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_NV; ++i)
+      if (i < nv) {
+        const int j = lane + 32 * i;
+        yr[j] = __float2half_rn((xv[i] - mean) * rstd * __ldg(w + j) + __ldg(bias + j));
+      }
+    if (lane == 0) {
+      if (row_idx) row_idx[o0 + rk] = b * L + l;
+      if (row_sample) row_sample[o0 + rk] = b;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// attention over the kept tokens: grid = B*H, 128 threads; Q, K, V of the (sample, head) in shared memory
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int AT_MAX_T = 208, AT_PITCH = 72;          // rows of 64 halves padded to 72 (144 B: conflict-free ldmatrix)
+constexpr int AT_NT = AT_MAX_T / 8;                   // 26 score n8-tiles
+constexpr int AT_SMEM = 3 * AT_MAX_T * AT_PITCH * 2;  // 89 856 B
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(128)
+adavit_attention_kernel(const __half* __restrict__ qkv, int ldq, const int* __restrict__ off, const uint8_t* __restrict__ head_sel,
+                        int H, __half* __restrict__ o) {
+  extern __shared__ __align__(16) unsigned char at_smem[];
+  const int b = blockIdx.x / H, h = blockIdx.x - b * H;
+  const int r0 = off[b], n = off[b + 1] - r0;
+  if (n <= 0) return;                                           // the sample skips its attention sub-layer
+  const int D = H * 64;
+  if (!head_sel[(size_t)b * H + h]) {                           // dropped head: zeros into the projection's input
+    for (int i = threadIdx.x; i < n * 8; i += blockDim.x)
+      *reinterpret_cast<uint4*>(o + (size_t)(r0 + (i >> 3)) * D + h * 64 + (i & 7) * 8) = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  __half* sQ = reinterpret_cast<__half*>(at_smem);
+  __half* sK = sQ + AT_MAX_T * AT_PITCH;
+  __half* sV = sK + AT_MAX_T * AT_PITCH;
+  const int n16 = (n + 15) & ~15;
+  for (int i = threadIdx.x; i < n16 * 24; i += blockDim.x) {
+    const int r = i / 24, part = i - r * 24, which = part >> 3, ch = part & 7;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (r < n) v = __ldg(reinterpret_cast<const uint4*>(qkv + (size_t)(r0 + r) * ldq + h * 192 + which * 64 + ch * 8));
+    *reinterpret_cast<uint4*>((which == 0 ? sQ : which == 1 ? sK : sV) + r * AT_PITCH + ch * 8) = v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int nk16 = n16 >> 4, nt8 = nk16 * 2;
+  const float sc = 0.125f * 1.44269504088896341f;               // 1/sqrt(64) x log2(e)
+  const uint32_t q_u = smem_u32(sQ), k_u = smem_u32(sK), v_u = smem_u32(sV);
+  for (int qt = warp; qt < nk16; qt += 4) {
+    const int q0 = qt * 16;
+    uint32_t qa[4][4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+      ldmatrix_x4(q_u + (uint32_t)(((q0 + (lane & 7) + ((lane >> 3) & 1) * 8) * AT_PITCH + kk * 16 + (lane >> 4) * 8) * 2), qa[kk][0],
+                  qa[kk][1], qa[kk][2], qa[kk][3]);
+    float s[AT_NT][4];
+#pragma unroll
+    for (int j = 0; j < AT_NT; ++j) {
+      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+      if (j < nt8) {
+#pragma unroll
+        for (int kp = 0; kp < 2; ++kp) {                        // two k16 steps per ldmatrix.x4
+          uint32_t b0, b1, b2, b3;
+          ldmatrix_x4(k_u + (uint32_t)(((j * 8 + (lane & 7)) * AT_PITCH + kp * 32 + (lane >> 3) * 8) * 2), b0, b1, b2, b3);
+          mma16816(s[j], qa[2 * kp][0], qa[2 * kp][1], qa[2 * kp][2], qa[2 * kp][3], b0, b1);
+          mma16816(s[j], qa[2 * kp + 1][0], qa[2 * kp + 1][1], qa[2 * kp + 1][2], qa[2 * kp + 1][3], b2, b3);
+        }
+      }
+    }
+    // softmax over the kept keys (columns >= n are padding)
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < AT_NT; ++j)
+      if (j < nt8) {
+        const int c = j * 8 + 2 * t;
+        if (c >= n) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
+        if (c + 1 >= n) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+        mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+      }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < AT_NT; ++j)
+      if (j < nt8) {
+        s[j][0] = exp2f((s[j][0] - mx0) * sc); s[j][1] = exp2f((s[j][1] - mx0) * sc);
+        s[j][2] = exp2f((s[j][2] - mx1) * sc); s[j][3] = exp2f((s[j][3] - mx1) * sc);
+        sum0 += s[j][0] + s[j][1];
+        sum1 += s[j][2] + s[j][3];
+      }
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+    // O = P V
+    float acc[8][4];
+#pragma unroll
+    for (int d8 = 0; d8 < 8; ++d8) acc[d8][0] = acc[d8][1] = acc[d8][2] = acc[d8][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < AT_NT / 2; ++kk)
+      if (kk < nk16) {
+        const uint32_t a0 = pack_h2(s[2 * kk][0], s[2 * kk][1]), a1 = pack_h2(s[2 * kk][2], s[2 * kk][3]);
+        const uint32_t a2 = pack_h2(s[2 * kk + 1][0], s[2 * kk + 1][1]), a3 = pack_h2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+        for (int dp = 0; dp < 4; ++dp) {                        // two d8 tiles per ldmatrix.x4.trans
+          uint32_t b0, b1, b2, b3;
+          ldmatrix_x4_trans(v_u + (uint32_t)(((kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * AT_PITCH + dp * 16 + (lane >> 4) * 8) * 2),
+                            b0, b1, b2, b3);
+          mma16816(acc[2 * dp], a0, a1, a2, a3, b0, b1);
+          mma16816(acc[2 * dp + 1], a0, a1, a2, a3, b2, b3);
+        }
+      }
+    const float i0 = 1.f / sum0, i1 = 1.f / sum1;
+    const int ra = q0 + g, rb = q0 + g + 8;
+#pragma unroll
+    for (int d8 = 0; d8 < 8; ++d8) {
+      if (ra < n)
+        *reinterpret_cast<uint32_t*>(o + (size_t)(r0 + ra) * D + h * 64 + d8 * 8 + 2 * t) = pack_h2(acc[d8][0] * i0, acc[d8][1] * i0);
+      if (rb < n)
+        *reinterpret_cast<uint32_t*>(o + (size_t)(r0 + rb) * D + h * 64 + d8 * 8 + 2 * t) = pack_h2(acc[d8][2] * i1, acc[d8][3] * i1);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// patch embedding glue
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void vit_patchify_kernel(const __half* __restrict__ x, int B, int S, int P, __half* __restrict__ out) {
+  const int gw = S / P, ppr = P / 8;                            // 16-byte pieces per patch row
+  const size_t total = (size_t)B * 3 * S * (S / 8);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int xc = (int)(i % (S / 8));                          // 16-byte piece within the image row
+    size_t r = i / (S / 8);
+    const int yy = (int)(r % S); r /= S;
+    const int c = (int)(r % 3);
+    const int b = (int)(r / 3);
+    const int px = xc / ppr, ix8 = xc - px * ppr, py = yy / P, iy = yy - py * P;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(x) + i);
+    *reinterpret_cast<uint4*>(out + ((size_t)(b * gw * gw + py * gw + px)) * (3 * P * P) + c * P * P + iy * P + ix8 * 8) = v;
+  }
+}
+__global__ void vit_init_tokens_kernel(float* __restrict__ x, int B, int L, int D, const float* __restrict__ pos,
+                                       const float* __restrict__ cls) {
+  const size_t total = (size_t)B * L * D;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int d = (int)(i % D);
+    const int l = (int)((i / D) % L);
+    x[i] = __ldg(pos + (size_t)l * D + d) + (l == 0 ? __ldg(cls + d) : 0.f);
+  }
+}
+
+}  // namespace
+}  // namespace laud
+
+using namespace laud;
+
+extern "C" unsigned long long laud_tok_gemm_launch_count(void) { return g_tok_gemm_launches.load(); }
+
+extern "C" int laud_tok_gemm(const laud_tok_gemm_desc* d, void* stream) {
+  LAUD_REQUIRE(d != nullptr, "laud_tok_gemm: null descriptor");
+  LAUD_REQUIRE(d->a && d->w && d->rows_max > 0 && d->K > 0 && d->N > 0, "laud_tok_gemm: null operand or empty shape");
+  LAUD_REQUIRE(d->K % 64 == 0 && d->N % 8 == 0 && d->lda % 8 == 0 && d->lda >= d->K, "laud_tok_gemm: K %% 64, N %% 8, lda %% 8 required (K=%d N=%d lda=%d)", d->K, d->N, d->lda);
+  LAUD_REQUIRE((d->out != nullptr) != (d->resid != nullptr), "laud_tok_gemm: exactly one of out / resid");
+  LAUD_REQUIRE(!d->out || (d->ldo % 8 == 0 && d->ldo >= d->N), "laud_tok_gemm: ldo %% 8 == 0 and ldo >= N required");
+  LAUD_REQUIRE(!d->resid || (d->row_idx && d->ldres % 4 == 0 && d->ldres >= d->N), "laud_tok_gemm: resid needs row_idx, ldres %% 4 == 0, ldres >= N");
+  LAUD_REQUIRE(d->act == LAUD_ACT_NONE || d->act == LAUD_ACT_GELU, "laud_tok_gemm: unknown activation %d", d->act);
+  LAUD_REQUIRE(((uintptr_t)d->a & 15) == 0 && ((uintptr_t)d->w & 15) == 0 && ((uintptr_t)d->out & 15) == 0 && ((uintptr_t)d->resid & 15) == 0 &&
+               ((uintptr_t)d->bias & 15) == 0, "laud_tok_gemm: operands must be 16-byte aligned");
+  int bn = d->bn;
+  if (bn == 0) bn = d->N % 256 == 0 ? 256 : d->N % 192 == 0 ? 192 : d->N % 128 == 0 ? 128 : d->N >= 256 ? 256 : 64 * ((d->N + 63) / 64);
+  LAUD_REQUIRE(bn == 64 || bn == 128 || bn == 192 || bn == 256, "laud_tok_gemm: bn must be 64 / 128 / 192 / 256 (got %d)", bn);
+  LAUD_REQUIRE(!d->col_gate || (d->row_sample && d->gate_ld >= (d->N + bn - 1) / bn), "laud_tok_gemm: col_gate needs row_sample and gate_ld >= n-tiles");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int dev = current_device();
+  DevInfo& di = g_dev[dev];
+  if (!di.sms) {
+    cudaDeviceProp prop;
+    LAUD_CUDA(cudaGetDeviceProperties(&prop, dev));
+    di.sms = prop.multiProcessorCount;
+  }
+  const size_t smem = (size_t)TG_STAGES * (TG_A_BYTES + bn * 128) + 1024;
+  if (!di.gemm_attr) {
+    LAUD_CUDA(cudaFuncSetAttribute(tok_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_STAGES * (TG_A_BYTES + 256 * 128) + 1024));
+    di.gemm_attr = true;
+  }
+  CUtensorMap ma, mb;
+  if (!tg_map(&ma, d->a, d->K, d->rows_max, d->lda, TG_BM) || !tg_map(&mb, d->w, d->K, d->N, d->K, bn)) {
+    set_error("laud_tok_gemm: cuTensorMapEncodeTiled failed");
+    return LAUD_E_CUDA;
+  }
+  TgArgs a;
+  a.bias = d->bias; a.rows_max = d->rows_max; a.K = d->K; a.N = d->N; a.bn = bn; a.row_cnt = d->row_cnt; a.act = d->act;
+  a.out = (__half*)d->out; a.ldo = d->ldo; a.resid = d->resid; a.ldres = d->ldres; a.row_idx = d->row_idx;
+  a.col_gate = d->col_gate; a.gate_ld = d->gate_ld; a.row_sample = d->row_sample;
+  const int items = ((d->rows_max + TG_BM - 1) / TG_BM) * ((d->N + bn - 1) / bn);
+  const int grid = items < di.sms ? items : di.sms;
+  tok_gemm_kernel<<<grid, TG_THREADS, smem, s>>>(a, ma, mb);
+  g_tok_gemm_launches.fetch_add(1, std::memory_order_relaxed);
+  return check_launch("tok_gemm_kernel");
+}
+
+extern "C" int laud_vit_patchify(const void* x_nchw, int B, int S, int P, void* patches, void* stream) {
+  LAUD_REQUIRE(x_nchw && patches && B > 0 && S > 0 && P > 0 && S % P == 0 && P % 8 == 0, "laud_vit_patchify: bad shape (S=%d P=%d)", S, P);
+  const size_t total = (size_t)B * 3 * S * (S / 8);
+  const int grid = (int)((total + 255) / 256 < 65535 * 4 ? (total + 255) / 256 : 65535 * 4);
+  vit_patchify_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)x_nchw, B, S, P, (__half*)patches);
+  return check_launch("vit_patchify_kernel");
+}
+
+extern "C" int laud_vit_init_tokens(float* x, int B, int L, int D, const float* pos, const float* cls, void* stream) {
+  LAUD_REQUIRE(x && pos && cls && B > 0 && L > 0 && D > 0, "laud_vit_init_tokens: bad arguments");
+  const size_t total = (size_t)B * L * D;
+  const int grid = (int)((total + 255) / 256 < 65535 * 4 ? (total + 255) / 256 : 65535 * 4);
+  vit_init_tokens_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, B, L, D, pos, cls);
+  return check_launch("vit_init_tokens_kernel");
+}
+
+extern "C" int laud_adavit_policy(const float* x, int B, int L, int D, int H, float eps, const float* n1_w, const float* n1_b,
+                                  const float* ts_w, const float* ts_b, const float* np_w, const float* np_b, const float* ls_w,
+                                  const float* ls_b, const float* hs_w, const float* hs_b, uint8_t* tok_mask, int32_t* tok_cnt,
+                                  uint8_t* head_sel, uint8_t* layer_sel, float* tok_logits, float* head_logits,
+                                  float* layer_logits, void* stream) {
+  LAUD_REQUIRE(x && tok_mask && tok_cnt && head_sel && layer_sel, "laud_adavit_policy: null output");
+  LAUD_REQUIRE(B > 0 && L > 0 && L <= 1024 && D % 32 == 0 && D <= 1024 && H > 0, "laud_adavit_policy: bad shape (L=%d D=%d H=%d)", L, D, H);
+  LAUD_REQUIRE(!ts_w || (n1_w && n1_b && ts_b), "laud_adavit_policy: the token score needs norm1 and its bias");
+  LAUD_REQUIRE(!(ls_w || hs_w) || (np_w && np_b), "laud_adavit_policy: layer / head policies need the policy LayerNorm");
+  LAUD_REQUIRE((!ls_w || ls_b) && (!hs_w || hs_b), "laud_adavit_policy: missing policy bias");
+  adavit_policy_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(x, L, D, H, eps, n1_w, n1_b, ts_w, ts_b, np_w, np_b, ls_w, ls_b, hs_w,
+                                                            hs_b, tok_mask, tok_cnt, head_sel, layer_sel, tok_logits, head_logits,
+                                                            layer_logits);
+  return check_launch("adavit_policy_kernel");
+}
+
+extern "C" int laud_adavit_lists(const int32_t* tok_cnt, const uint8_t* layer_sel, int B, int32_t* off_attn, int32_t* off_mlp,
+                                 void* stream) {
+  LAUD_REQUIRE(tok_cnt && layer_sel && off_attn && off_mlp && B > 0, "laud_adavit_lists: bad arguments");
+  adavit_lists_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(tok_cnt, layer_sel, B, off_attn, off_mlp);
+  return check_launch("adavit_lists_kernel");
+}
+
+extern "C" int laud_adavit_ln_gather(const float* x, int B, int L, int D, float eps, const float* w, const float* bias,
+                                     const uint8_t* tok_mask, const int32_t* off, void* y, int32_t* row_idx, int32_t* row_sample,
+                                     void* stream) {
+  LAUD_REQUIRE(x && w && bias && off && y, "laud_adavit_ln_gather: null argument");
+  LAUD_REQUIRE(B > 0 && L > 0 && L <= 1024 && D % 32 == 0 && D <= 1024, "laud_adavit_ln_gather: bad shape (L=%d D=%d)", L, D);
+  adavit_ln_gather_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(x, L, D, eps, w, bias, tok_mask, off, (__half*)y, row_idx, row_sample);
+  return check_launch("adavit_ln_gather_kernel");
+}
+
+extern "C" int laud_adavit_attention(const void* qkv, int ldq, const int32_t* off, const uint8_t* head_sel, int B, int H, int L,
+                                     void* o, void* stream) {
+  LAUD_REQUIRE(qkv && off && head_sel && o && B > 0 && H > 0, "laud_adavit_attention: bad arguments");
+  if (L > AT_MAX_T) {
+    set_error("laud_adavit_attention: at most %d tokens per sample (got L=%d)", AT_MAX_T, L);
+    return LAUD_E_UNSUPPORTED;
+  }
+  LAUD_REQUIRE(ldq % 8 == 0 && ldq >= H * 192, "laud_adavit_attention: ldq %% 8 == 0 and ldq >= 192 H required");
+  const int dev = current_device();
+  DevInfo& di = g_dev[dev];
+  if (!di.attn_attr) {
+    LAUD_CUDA(cudaFuncSetAttribute(adavit_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+    di.attn_attr = true;
+  }
+  adavit_attention_kernel<<<B * H, 128, AT_SMEM, (cudaStream_t)stream>>>((const __half*)qkv, ldq, off, head_sel, H, (__half*)o);
+  return check_launch("adavit_attention_kernel");
+}

@@ -391,3 +391,85 @@ def synth_calibrated_state_dict(model, seed: int, calib_images: torch.Tensor, ch
                                 spatial_rate=spatial_rate)
     return calibrate_resnet(sd, geometry_of(model), calib_images, seed, channel_rate=channel_rate,
                             spatial_rate=spatial_rate, layer_rate=layer_rate)
+
+
+# --------------------------------------------------------------------------
+# AdaViT (BASELINE configs[3]): seeded DeiT weights + policy heads calibrated to target keep rates
+# --------------------------------------------------------------------------
+ADAVIT_RATES = dict(token_rate=0.65, head_rate=0.7, layer_rate=0.85)   # AdaViT reports ~2x fewer FLOPs on DeiT-S
+
+
+def synth_adavit_tensor(name: str, shape: Tuple[int, ...], seed: int) -> torch.Tensor:
+    r = _rng(seed, "adavit." + name)
+    leaf = name.rsplit(".", 1)[-1]
+    if name in ("cls_token", "pos_embed"):
+        a = 0.5 * r.standard_normal(shape)
+    elif leaf == "weight" and len(shape) == 1:                 # LayerNorm gamma
+        a = 1.0 + 0.1 * r.standard_normal(shape)
+    elif leaf == "bias" and ("norm" in name):                  # LayerNorm beta
+        a = 0.1 * r.standard_normal(shape)
+    elif leaf == "weight":                                     # Linear / patch conv
+        fan_in = int(np.prod(shape[1:]))
+        gain = 0.5 if (".proj." in name and "patch_embed" not in name) or ".fc2." in name else 1.0   # tame residual growth
+        a = gain * r.standard_normal(shape) / np.sqrt(fan_in)
+    else:                                                      # Linear bias
+        a = 0.1 * r.standard_normal(shape)
+    return torch.from_numpy(np.asarray(a, dtype=np.float32).reshape(shape))
+
+
+def synth_adavit_state_dict(shapes: Mapping[str, Tuple[int, ...]], seed: int) -> Dict[str, torch.Tensor]:
+    """Backbone Linear / conv weights are rounded to fp16-representable values (the oracle is fed the weights the
+    tensor cores see); LayerNorm and policy parameters stay fp32."""
+    sd = {}
+    for name, shape in shapes.items():
+        t = synth_adavit_tensor(name, tuple(shape), seed)
+        if t.dim() >= 2 and "_select" not in name and name not in ("cls_token", "pos_embed"):
+            t = t.half().float()
+        sd[name] = t
+    return sd
+
+
+def calibrate_adavit(sd: Dict[str, torch.Tensor], model_kwargs: dict, images: torch.Tensor, token_rate: float = 0.65,
+                     head_rate: float = 0.7, layer_rate: float = 0.85) -> Dict[str, torch.Tensor]:
+    """Shift the biases of the policy heads, block by block on a calibration batch, so that the eval decisions fire at
+    the target rates (stands in for training the policies).  Plain torch on `images.device`; weight synthesis only."""
+    import torch.nn.functional as F
+    dev = images.device
+    s = {k: v.to(dev) for k, v in sd.items()}
+    D, H, P = model_kwargs["embed_dim"], model_kwargs["num_heads"], model_kwargs["patch_size"]
+    depth, keep_layers = model_kwargs["depth"], model_kwargs.get("keep_layers", 1)
+    d = D // H
+    ln = lambda t, p: F.layer_norm(t, (D,), s[p + "weight"], s[p + "bias"], 1e-6)
+    with torch.no_grad():
+        t = F.conv2d(images.float(), s["patch_embed.proj.weight"], s["patch_embed.proj.bias"], stride=P).flatten(2).transpose(1, 2)
+        x = torch.cat([s["cls_token"].expand(t.shape[0], -1, -1), t], 1) + s["pos_embed"]
+        B, L, _ = x.shape
+        for i in range(depth):
+            p = f"blocks.{i}."
+            tok = torch.ones(B, L, dtype=torch.bool, device=dev)
+            head = torch.ones(B, H, dtype=torch.bool, device=dev)
+            layer = torch.ones(B, 2, dtype=torch.bool, device=dev)
+            if i >= keep_layers and (p + "norm_policy.weight") in s:
+                pt = ln(x[:, 0], p + "norm_policy.")
+                if p + "layer_select.weight" in s:
+                    lg = F.linear(pt, s[p + "layer_select.weight"])
+                    s[p + "layer_select.bias"] = -calibrate_two_way_bias(lg, layer_rate, per_group=True).to(dev)
+                    layer = (lg + s[p + "layer_select.bias"]) >= 0
+                if p + "head_select.weight" in s:
+                    lg = F.linear(pt, s[p + "head_select.weight"])
+                    s[p + "head_select.bias"] = -calibrate_two_way_bias(lg, head_rate, per_group=True).to(dev)
+                    head = (lg + s[p + "head_select.bias"]) >= 0
+                if p + "token_select.weight" in s:
+                    lg = F.linear(ln(x[:, 1:], p + "norm1."), s[p + "token_select.weight"]).squeeze(-1)
+                    s[p + "token_select.bias"] = -calibrate_two_way_bias(lg.reshape(-1, 1), token_rate, per_group=True).to(dev)
+                    tok = torch.cat([tok[:, :1], (lg + s[p + "token_select.bias"]) >= 0], 1)
+            qkv = F.linear(ln(x, p + "norm1."), s[p + "attn.qkv.weight"], s[p + "attn.qkv.bias"]).view(B, L, 3, H, d).permute(2, 0, 3, 1, 4)
+            a = (qkv[0] @ qkv[1].transpose(-1, -2)) * d ** -0.5
+            a = a.masked_fill(~tok[:, None, None, :], float("-inf")).softmax(-1) @ qkv[2]
+            a = (a * head[:, :, None, None]).transpose(1, 2).reshape(B, L, D)
+            a = F.linear(a, s[p + "attn.proj.weight"], s[p + "attn.proj.bias"])
+            x = x + a * tok[:, :, None] * layer[:, 0, None, None]
+            m = F.linear(F.gelu(F.linear(ln(x, p + "norm2."), s[p + "mlp.fc1.weight"], s[p + "mlp.fc1.bias"])),
+                         s[p + "mlp.fc2.weight"], s[p + "mlp.fc2.bias"])
+            x = x + m * tok[:, :, None] * layer[:, 1, None, None]
+    return {k: v.float().cpu() for k, v in s.items()}

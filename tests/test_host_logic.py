@@ -86,14 +86,17 @@ def test_product_package_does_not_import_oracle():
 
 # ------------------------------------------------------------------ C ABI
 def _declared_symbols():
-    hdr = open(os.path.join(ROOT, "include", "laud_b200.h")).read()
-    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    return sorted(set(re.findall(r"\b(laud_[a-z0-9_]+)\s*\(", hdr)))
+    import glob
+    names = set()
+    for path in sorted(glob.glob(os.path.join(ROOT, "include", "*.h"))):      # laud_b200.h, laud_adavit.h
+        hdr = re.sub(r"/\*.*?\*/", "", open(path).read(), flags=re.S)
+        names.update(re.findall(r"\b(laud_[a-z0-9_]+)\s*\(", hdr))
+    return sorted(names)
 
 
 def test_header_and_binding_agree():
     declared = _declared_symbols()
-    assert declared, "no symbols parsed from include/laud_b200.h"
+    assert declared, "no symbols parsed from include/*.h"
     assert sorted(_lib.SIGNATURES) == declared
 
 
