@@ -2,7 +2,7 @@
 """Benchmark of the LAUD hot path (BASELINE.json metric): images/sec of LAUD-ResNet101 channel-2222 target-0.5 at
 batch 256 per GPU (configs[1]) - or, with --config, one of the other BASELINE configurations.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl graft|reference] [--config 0|1|2|4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl graft|reference] [--config 0|1|2|3|4]
 
 One JSON line on stdout (rank 0).  A "step" is one forward pass of the hot path over one synthetic batch:
   * value : whole-job images/s, inputs already resident in HBM, CUDA-graphed forward (two parallel chains at batch
@@ -41,8 +41,13 @@ UNIT = "images/s"
 SEED = 1
 CALIB_IMAGES = 32
 
-# BASELINE.json configs (index = position in `configs`); configs[3] (AdaViT) has no reference code in the tree.
+# BASELINE.json configs (index = position in `configs`); configs[3] (AdaViT) has no reference code in the tree: it runs
+# against the declared self-oracle oracle/adavit_oracle.py (run_adavit below).
 CONFIGS = {
+    3: dict(metric="images/sec AdaViT-DeiT-S token+head+layer skipping bs512", arch="adavit_deit_s", batch=512,
+            rates=dict(token_rate=0.65, head_rate=0.7, layer_rate=0.85),
+            workload="AdaViT on DeiT-S (D=384, 6 heads, 12 blocks) token + head + layer skipping, batch 512 x 3x224x224 per GPU "
+                     "(configs[3]; self-oracle: no AdaViT code in the reference tree)"),
     0: dict(metric="images/sec LAUD-ResNet50 spatial t0.5 bs8", arch="resnet50", kw="SPATIAL", batch=8,
             rates=dict(spatial_rate=0.4),
             workload="LAUD-ResNet50 spatial-skip 4-4-2-1 target-0.5, batch 8 x 3x224x224 (configs[0])"),
@@ -556,6 +561,249 @@ def run_graft(args, conf):
         sys.exit(3)
 
 
+# ----------------------------------------------------------------------------- configs[3]: AdaViT (self-oracle)
+def build_adavit(conf, device):
+    from laudnet_b200 import synth
+    from laudnet_b200.adavit import ada_deit_small_patch16_224
+    model = ada_deit_small_patch16_224()
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    kw = dict(img_size=224, patch_size=16, embed_dim=384, depth=12, num_heads=6, mlp_ratio=4.0, num_classes=1000, keep_layers=1,
+              ada_token=True, ada_head=True, ada_layer=True)
+    calib = synth.synth_images(CALIB_IMAGES if device.type == "cuda" else 8, 224, SEED + 100).to(device)
+    sd = synth.calibrate_adavit(synth.synth_adavit_state_dict(shapes, SEED), kw, calib, **conf["rates"])
+    model.load_state_dict(sd, strict=True)
+    return model, sd, kw
+
+
+def run_adavit_reference(args, conf):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from laudnet_b200 import synth
+    from oracle import adavit_oracle as A
+    model, sd, kw = build_adavit(conf, torch.device("cpu"))
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = A.AdaViTCfg(**kw)
+    n = min(args.cpu_sample, conf["batch"])
+    x = synth.synth_images(n, 224, SEED)
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            A.forward(sd, cfg, x)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            A.forward(sd, cfg, x)
+        dt = time.perf_counter() - t0
+    v = n * args.steps / dt
+    sample = f"{n} of the {conf['batch']} images per step (fp32 masked-dense self-oracle, torch {torch.__version__} CPU, {cores} threads)"
+    print(json.dumps({
+        "impl": "reference", "metric": conf["metric"], "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": conf["workload"] + ", CPU self-oracle (masked-dense torch)", "batch_per_step": n},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_adavit(args, conf):
+    from laudnet_b200 import _lib, synth
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    out_fd = os.dup(1)
+    os.dup2(2, 1)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    _lib.lib()
+    B = args.batch or conf["batch"]
+    model, sd, kw = build_adavit(conf, dev)
+    model = model.to(dev).eval()
+    x_host = synth.synth_images(B, 224, SEED, start=rank * B).to(torch.float16).pin_memory()
+    x_dev = x_host.to(dev)
+    ncls = model.num_classes
+    gathered = torch.empty((world * B, ncls), dtype=torch.float32, device=dev) if world > 1 else None
+    peaks = _peaks()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    with torch.no_grad():
+        # eager forward: decisions (measured keep rates), launch census, per-kernel-class times (events between launches)
+        n0, g0 = _lib.launch_count(), int(_lib.lib().laud_tok_gemm_launch_count())
+        model.forward_logits(x_dev)
+        torch.cuda.synchronize()
+        launches_per_step = _lib.launch_count() - n0
+        gemm_launches = int(_lib.lib().laud_tok_gemm_launch_count()) - g0
+        tok, head, layer = (t.bool().transpose(0, 1).cpu() for t in model.decisions(B))
+        model.profile = []
+        model.forward_logits(x_dev)
+        torch.cuda.synchronize()
+        marks, model.profile = model.profile, None
+        by_class = {}
+        for (tag, e), (_, e_next) in zip(marks[:-1], marks[1:]):
+            by_class[tag] = by_class.get(tag, 0.0) + e.elapsed_time(e_next)
+
+        graphed = model.capture(B)
+
+        def step_resident():
+            lg = graphed.replay()
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, lg)
+            return lg
+
+        clk = ClockSampler(local)
+        clk.__enter__()
+        ms_total = timed(step_resident, args.steps, args.warmup)
+        ms_step = ms_total / args.steps
+        value = world * B * args.steps / (ms_total * 1e-3)
+        graphed_logits = graphed.logits.clone()
+
+        logits_host = torch.empty((B, ncls), dtype=torch.float32).pin_memory()
+
+        def step_e2e():
+            lg = graphed.replay(x_host)                   # H2D of the batch from pinned memory into the graph's input
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, lg)
+            logits_host.copy_(lg, non_blocking=True)      # D2H of this rank's logits
+
+        ms_e2e = timed(step_e2e, args.steps, args.warmup)
+        clk.__exit__()
+        clocks = clk.summary()
+        e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+
+    # ---- algorithmic work at the measured decisions (oracle-free arithmetic: the formula of simulate_adavit.py:83-182)
+    D, H, L, Hd, dh = model.embed_dim, model.num_heads, model.seq_len, model.hidden, 64
+    nt, nh = tok.sum(-1).double(), head.sum(-1).double()                       # [B, depth]
+    la, lm = layer[..., 0].double(), layer[..., 1].double()
+    macs_qkv = (la * nt * D * 3 * dh * nh).sum().item()
+    macs_attn = (la * 2 * nt * nt * dh * nh).sum().item()
+    macs_proj = (la * nt * dh * nh * D).sum().item()
+    macs_mlp = (lm * 2 * nt * D * Hd).sum().item()
+    macs_fixed = B * (model.num_patches * D * 3 * model.patch_size ** 2 + D * ncls)
+    flops_step = 2.0 * (macs_qkv + macs_attn + macs_proj + macs_mlp + macs_fixed)
+    dense_flops_step = 2.0 * B * (model.num_patches * D * 3 * model.patch_size ** 2 + D * ncls +
+                                  model.depth * (L * D * 3 * D + 2 * L * L * D + L * D * D + 2 * L * D * Hd))
+    # executed GEMM FLOPs: QKV computes every head of a kept m-tile unless the whole tile drops it; proj reads all D inputs
+    rows_a, rows_m = (la * nt).sum().item(), (lm * nt).sum().item()
+    gemm_flops_exec = 2.0 * (rows_a * D * 3 * D + rows_a * D * D + rows_m * 2 * D * Hd) + 2.0 * macs_fixed
+    gemm_ms = sum(v for k, v in by_class.items() if k.startswith("gemm")) + by_class.get("embed", 0.0) + by_class.get("head", 0.0)
+    eager_ms = sum(by_class.values())
+    roof = {
+        "kernel": "laud::tok_gemm_kernel (tcgen05 token GEMM over compact rows: patch projection, QKV, proj, fc1+GELU, fc2, classifier; "
+                  "all %d launches of one step)" % gemm_launches,
+        "bound": "tensor", "peak": peaks["tflops"], "unit": "TFLOP/s", "peak_source": peaks["source"],
+        "launches_per_step": gemm_launches, "kernel_ms_per_step": gemm_ms, "avg_launch_us": 1e3 * gemm_ms / max(1, gemm_launches),
+        "eager_ms_per_step": eager_ms, "share_of_step": gemm_ms / eager_ms,
+        "achieved": gemm_flops_exec / (gemm_ms * 1e-3) / 1e12, "frac": gemm_flops_exec / (gemm_ms * 1e-3) / 1e12 / peaks["tflops"],
+        "timing": "CUDA events between consecutive launches of one eager forward (single stream; includes the patchify / init / "
+                  "LayerNorm launches of the embed and head groups); `value` times the CUDA-graph replay",
+        "algorithmic_flops_per_step": flops_step, "executed_gemm_flops_per_step": gemm_flops_exec,
+        "credited_whole_step": {"achieved": flops_step / (ms_step * 1e-3) / 1e12, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                                "frac": flops_step / (ms_step * 1e-3) / 1e12 / peaks["tflops"],
+                                "note": "sparsity-adjusted algorithmic FLOPs of the whole network / graphed step time"},
+        "ms_by_kernel_class": {k: round(v, 4) for k, v in sorted(by_class.items())}, "traffic": None,
+    }
+    net = {"flops_per_image": flops_step / B, "dense_flops_per_image": dense_flops_step / B, "flops_ratio": flops_step / dense_flops_step,
+           "token_keep_rate_dynamic_blocks": tok[:, model.keep_layers:, 1:].float().mean().item(),
+           "head_keep_rate_dynamic_blocks": head[:, model.keep_layers:].float().mean().item(),
+           "attn_sublayer_rate": layer[:, model.keep_layers:, 0].float().mean().item(),
+           "mlp_sublayer_rate": layer[:, model.keep_layers:, 1].float().mean().item()}
+
+    cpu = parity = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import adavit_oracle as A
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        cfg = A.AdaViTCfg(**kw)
+        n = min(args.cpu_sample, B)
+        sd_cpu = {k: v.cpu() for k, v in sd.items()}
+        xs = synth.synth_images(n, 224, SEED)
+        with torch.no_grad():
+            A.forward(sd_cpu, cfg, xs)
+            times = []
+            for _ in range(2):
+                traces = []
+                t0 = time.perf_counter()
+                want, wt, wh, wl = A.forward(sd_cpu, cfg, xs, traces)
+                times.append(time.perf_counter() - t0)
+        cpu = {"value": n / statistics.median(times), "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n} of the {B} images, 2 timed forwards after a warm-up (fp32 masked-dense self-oracle, {cores} threads)"}
+        # parity of the timed path: decisions per sample in execution order up to the first differing block (a difference
+        # is explained only inside the fp16 operand margin), graphed logits of the samples whose decisions all agree, and
+        # the logits of ALL samples with the oracle's decisions installed
+        TOL = 5e-3
+        agree = torch.ones(n, dtype=torch.bool)
+        flips = unexplained = compared = 0
+        for i, t in enumerate(traces):
+            pol = t.policy
+            for ours, want_d, lg in ((tok[:n, i, 1:], pol.token[:, 1:], pol.token_logits), (head[:n, i], pol.head, pol.head_logits),
+                                     (layer[:n, i], pol.layer, pol.layer_logits)):
+                if lg is None:
+                    continue
+                diff = (ours != want_d).reshape(n, -1)
+                lgr = lg.reshape(n, -1)
+                compared += int(agree.sum()) * lgr.shape[1]
+                for b in torch.nonzero(agree & diff.any(1)).flatten().tolist():
+                    inside = lgr[b][diff[b]].abs() <= TOL * lgr.abs().max()
+                    flips += int(inside.sum())
+                    unexplained += int((~inside).sum())
+            same = (tok[:n, i] == pol.token).all(1) & (head[:n, i] == pol.head).all(1) & (layer[:n, i] == pol.layer).all(1)
+            agree &= same
+        rel = lambda a, b: ((a.double() - b.double()).abs().max() / b.double().abs().max()).item()
+        err = rel(graphed_logits[:n].cpu()[agree], want[agree]) if agree.any() else float("nan")
+        with torch.no_grad():
+            forced = [(t.policy.token.to(dev), t.policy.head.to(dev), t.policy.layer.to(dev)) for t in traces]
+            lf = model(x_dev[:n], forced=forced)[0]
+        err_forced = rel(lf.cpu(), want)
+        parity = {"kind": "self-oracle (oracle/adavit_oracle.py; the reference tree holds no AdaViT code: parity unpinned)",
+                  "images": n, "decisions_compared": compared, "first_flips_within_margin": flips, "unexplained_flips": unexplained,
+                  "margin_tol_rel": TOL, "samples_all_decisions_equal": int(agree.sum()), "max_rel_err": err,
+                  "max_rel_err_teacher_forced_all_samples": err_forced, "logits_tolerance": TOL,
+                  "ok": bool(unexplained == 0 and err_forced <= TOL and (err != err or err <= TOL))}
+
+    if rank == 0:
+        sys.stdout.flush()
+        os.write(out_fd, (json.dumps({
+            "metric": conf["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": conf["workload"], "baseline_config_index": args.config, "batch_per_gpu": B, "global_batch": world * B,
+                       "parallelism": f"batch-sharded x{world}, replicated weights, one NCCL all-gather of logits per step" if world > 1
+                       else "single GPU", "l2": "inputs + token stream per step exceed the 126 MB L2; no explicit flush",
+                       "weights": "seeded synthetic DeiT-S, policy biases calibrated (%s)" % ", ".join(f"{k}={v}" for k, v in conf["rates"].items()),
+                       "cuda_graph": True, "execution": "token / head / layer skipping executed (compact row lists, device-side row counts)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 2, "d2h_bytes_per_step": B * ncls * 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step, "clocks": clocks,
+            "parity": parity, "roofline": roof, "net": net, "cpu_baseline": cpu,
+        }) + "\n").encode())
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        sys.stderr.write("[bench] PARITY FAILURE: %s\n" % json.dumps(parity))
+        sys.exit(3)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -571,7 +819,9 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "graft" else args.warmup
     conf = CONFIGS[args.config]
-    if args.impl == "reference":
+    if args.config == 3:
+        (run_adavit_reference if args.impl == "reference" else run_adavit)(args, conf)
+    elif args.impl == "reference":
         run_reference(args, conf)
     else:
         run_graft(args, conf)

@@ -112,6 +112,7 @@ class AdaViT(nn.Module):
         self._ws: Dict[int, dict] = {}
         self._graphs: Dict[int, "GraphedAdaViT"] = {}
         self.head_tile_skip = True          # drop whole per-head n-tiles of the QKV projection (A/B switch)
+        self.profile: Optional[list] = None  # measurement aid: a list makes _run record (tag, CUDA event) before every launch
 
     # ------------------------------------------------------------------ parameters -> device layouts (once)
     def _invalidate(self):
@@ -208,7 +209,16 @@ class AdaViT(nn.Module):
         ws, st = self.workspace(B), stream_ptr()
         L, D, H, Hd = self.seq_len, self.embed_dim, self.num_heads, self.hidden
         rows, x = B * L, ws["x"]
+        prof = self.profile
+
+        def mark(tag):
+            if prof is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                prof.append((tag, e))
+
         if x_tokens is None:
+            mark("embed")
             check(lib.laud_vit_patchify(ptr(x_img), B, self.img_size, self.patch_size, ptr(ws["patches"]), st), "laud_vit_patchify")
             check(lib.laud_vit_init_tokens(ptr(x), B, L, D, ptr(P["pos"]), ptr(P["cls"]), st), "laud_vit_init_tokens")
             self._gemm(ws["patches"], P["patch_w"], P["patch_b"], B * self.num_patches, 3 * self.patch_size ** 2, D, st,
@@ -220,6 +230,7 @@ class AdaViT(nn.Module):
             q = P["blocks"][i]
             tok, cnt, head, layer = ws["tok"][i], ws["cnt"][i], ws["head"][i], ws["layer"][i]
             off_a, off_m = ws["off_a"][i], ws["off_m"][i]
+            mark("policy")
             check(lib.laud_adavit_policy(ptr(x), B, L, D, H, LN_EPS, ptr(q["n1_w"]), ptr(q["n1_b"]), ptr(q["ts_w"]), ptr(q["ts_b"]),
                                          ptr(q["np_w"]), ptr(q["np_b"]), ptr(q["ls_w"]), ptr(q["ls_b"]), ptr(q["hs_w"]),
                                          ptr(q["hs_b"]), ptr(tok), ptr(cnt), ptr(head), ptr(layer), ptr(ws["tok_lg"][i]),
@@ -232,29 +243,38 @@ class AdaViT(nn.Module):
                 cnt.copy_(ft.sum(1).to(torch.int32))
             check(lib.laud_adavit_lists(ptr(cnt), ptr(layer), B, ptr(off_a), ptr(off_m), st), "laud_adavit_lists")
             # ---- attention sub-layer on the kept tokens of the samples that run it
+            mark("ln_gather")
             check(lib.laud_adavit_ln_gather(ptr(x), B, L, D, LN_EPS, ptr(q["n1_w"]), ptr(q["n1_b"]), ptr(tok), ptr(off_a),
                                             ptr(ws["y"]), ptr(ws["rows_a"]), ptr(ws["samp_a"]), st), "laud_adavit_ln_gather")
             gate = head if self.head_tile_skip else None
+            mark("gemm_qkv")
             self._gemm(ws["y"], q["qkv_w"], q["qkv_b"], rows, D, 3 * D, st, row_cnt=off_a[B:], out=ws["qkv"], bn=192,
                        col_gate=gate, gate_ld=H, row_sample=ws["samp_a"] if gate is not None else None)
+            mark("attention")
             check(lib.laud_adavit_attention(ptr(ws["qkv"]), 3 * D, ptr(off_a), ptr(head), B, H, L, ptr(ws["o"]), st),
                   "laud_adavit_attention")
+            mark("gemm_proj")
             self._gemm(ws["o"], q["proj_w"], q["proj_b"], rows, D, D, st, row_cnt=off_a[B:], resid=x, ldres=D, row_idx=ws["rows_a"])
             # ---- MLP sub-layer
+            mark("ln_gather")
             check(lib.laud_adavit_ln_gather(ptr(x), B, L, D, LN_EPS, ptr(q["n2_w"]), ptr(q["n2_b"]), ptr(tok), ptr(off_m),
                                             ptr(ws["y"]), ptr(ws["rows_m"]), None, st), "laud_adavit_ln_gather")
+            mark("gemm_fc1")
             self._gemm(ws["y"], q["fc1_w"], q["fc1_b"], rows, D, Hd, st, row_cnt=off_m[B:], act=_lib.ACT_GELU, out=ws["hdn"])
+            mark("gemm_fc2")
             self._gemm(ws["hdn"], q["fc2_w"], q["fc2_b"], rows, Hd, D, st, row_cnt=off_m[B:], resid=x, ldres=D, row_idx=ws["rows_m"])
             if keep is not None:
                 keep.append(BlockKeep(tok.bool().clone(), head.bool().clone(), layer.bool().clone(), ws["tok_lg"][i].clone(),
                                       ws["head_lg"][i].clone(), ws["layer_lg"][i].clone(), x.clone()))
         if only_block is None:
             # classifier: LayerNorm of the class tokens only, then the fc as a token GEMM into zeroed fp32 logits
+            mark("head")
             check(lib.laud_adavit_ln_gather(ptr(x), B, L, D, LN_EPS, ptr(P["norm_w"]), ptr(P["norm_b"]), ptr(ws["cls_mask"]),
                                             ptr(ws["cls_off"]), ptr(ws["ycls"]), None, None, st), "laud_adavit_ln_gather")
             ws["logits"].zero_()
             self._gemm(ws["ycls"], P["head_w"], P["head_b"], B, D, self.num_classes, st, resid=ws["logits"],
                        ldres=self.num_classes, row_idx=ws["cls_rows"])
+        mark("end")
         return ws
 
     def _check_input(self, x: torch.Tensor) -> torch.Tensor:
