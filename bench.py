@@ -663,6 +663,7 @@ def run_adavit(args, conf):
             by_class[tag] = by_class.get(tag, 0.0) + e.elapsed_time(e_next)
 
         graphed = model.capture(B)
+        graphed.x.copy_(x_dev)                            # the graph's static input buffer: the batch stays resident in HBM
 
         def step_resident():
             lg = graphed.replay()
@@ -679,14 +680,39 @@ def run_adavit(args, conf):
 
         logits_host = torch.empty((B, ncls), dtype=torch.float32).pin_memory()
 
+        # end to end from pinned host memory: the H2D copy of step i+1 runs on a copy stream behind step i's compute
+        copy_stream = torch.cuda.Stream()
+        stage = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        state = {"i": 0}
+
+        def issue_copy(i):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[i % 2])
+                stage[i % 2].copy_(x_host, non_blocking=True)
+                ready[i % 2].record(copy_stream)
+
         def step_e2e():
-            lg = graphed.replay(x_host)                   # H2D of the batch from pinned memory into the graph's input
+            i = state["i"]
+            if i == 0:
+                issue_copy(0)
+            issue_copy(i + 1)
+            cur = torch.cuda.current_stream()
+            cur.wait_event(ready[i % 2])
+            graphed.x.copy_(stage[i % 2], non_blocking=True)
+            consumed[i % 2].record(cur)
+            lg = graphed.replay()
             if world > 1:
                 dist.all_gather_into_tensor(gathered, lg)
             logits_host.copy_(lg, non_blocking=True)      # D2H of this rank's logits
+            state["i"] = i + 1
 
+        for ev in consumed:
+            ev.record()
         ms_e2e = timed(step_e2e, args.steps, args.warmup)
-        clk.__exit__()
+        copy_stream.synchronize()
+        clk.__exit__(None, None, None)
         clocks = clk.summary()
         e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
 

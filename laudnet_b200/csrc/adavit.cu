@@ -20,11 +20,22 @@ namespace {
 
 std::atomic<unsigned long long> g_tok_gemm_launches{0};
 
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // =====================================================================================================================
 // token GEMM
 // =====================================================================================================================
 constexpr int TG_BM = 128, TG_BK = 64, TG_STAGES = 4;
-constexpr int TG_THREADS = 192;                       // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int TG_EPI_WARPS = 8;                       // two warps per TMEM lane quarter, each takes half of the tile's columns
+constexpr int TG_THREADS = (2 + TG_EPI_WARPS) * 32;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int TG_A_BYTES = TG_BM * 128;
 constexpr int TG_ACC_STRIDE = 256;                    // TMEM columns between the two accumulator buffers
 
@@ -54,7 +65,22 @@ __device__ __forceinline__ bool tg_tile_active(const TgArgs& a, int m, int nt, i
   return false;
 }
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// GELU = 0.5 x (1 + erf(x / sqrt 2)) with erf(z) = 1 - 2^(-z g(z)), z = min(|x| / sqrt 2, 4.2), g a degree-5 polynomial
+// (weighted least-squares fit of -log2(erfc(z)) / z on [0, 4.2]; |erf error| <= 3.3e-7 in fp32 arithmetic, i.e. below the
+// fp16 rounding of the result by three orders of magnitude): 13 instructions with ONE MUFU (ex2) per element - erff() costs
+// about twice that and the fc1 epilogue is CUDA-core bound (32 768 elements per 128 x 256 tile against 3 072 MMA cycles).
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fminf(fabsf(x) * 0.70710678118654752f, 4.2f);
+  float g = -0.00014210730552722268f;
+  g = fmaf(g, z, 0.0036644166832296744f);
+  g = fmaf(g, z, -0.030896032968564496f);
+  g = fmaf(g, z, 0.1496990034547756f);
+  g = fmaf(g, z, 0.9181656741673894f);
+  g = fmaf(g, z, 1.6279250470245474f);
+  const float erf_abs = 1.0f - fast_ex2(-(g * z));
+  const float hx = 0.5f * x;
+  return fmaf(fabsf(hx), erf_abs, hx);
+}
 
 __global__ void __launch_bounds__(TG_THREADS, 1)
 tok_gemm_kernel(const TgArgs a, const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b) {
@@ -66,7 +92,7 @@ tok_gemm_kernel(const TgArgs a, const __grid_constant__ CUtensorMap map_a, const
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < TG_STAGES; ++i) { mbar_init(&bars.full[i], 1); mbar_init(&bars.empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars.tfull[i], 1); mbar_init(&bars.tempty[i], 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars.tfull[i], 1); mbar_init(&bars.tempty[i], TG_EPI_WARPS * 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
@@ -130,7 +156,8 @@ tok_gemm_kernel(const TgArgs a, const __grid_constant__ CUtensorMap map_a, const
     __syncwarp();
   } else {
     // ------------------------------------------------------------ epilogue: one accumulator row (TMEM lane) per thread
-    const int q = warp & 3;
+    const int q = warp & 3, half = (warp - 2) >> 2;           // TMEM lane quarter of this warp; which half of the columns
+    const int cbeg = half * (a.bn >> 1), cend = cbeg + (a.bn >> 1);
     int buf = 0;
     uint32_t bphase = 0;
     for (int it = blockIdx.x; it < items; it += gridDim.x) {
@@ -148,7 +175,7 @@ tok_gemm_kernel(const TgArgs a, const __grid_constant__ CUtensorMap map_a, const
       mbar_wait(&bars.tfull[buf], bphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + buf * TG_ACC_STRIDE + ((uint32_t)(q * 32) << 16);
-      for (int c0 = 0; c0 < a.bn; c0 += 32) {
+      for (int c0 = cbeg; c0 < cend; c0 += 32) {
         const int ncol = min(32, a.N - (n0 + c0));           // warp-uniform
         if (ncol <= 0) break;
         float v[32];
@@ -236,17 +263,41 @@ DevInfo g_dev[MAX_DEVICES];
 // =====================================================================================================================
 constexpr int LN_MAX_NV = 32;      // D <= 1024
 
+
+// Element of register slot i: lane + 32 i (scalar loads), or - V4, D % 128 == 0 - lane*4 + 128 (i/4) + i%4 (16-byte loads).
+template <bool V4>
+__device__ __forceinline__ int ln_idx(int i) {
+  const int lane = threadIdx.x & 31;
+  return V4 ? lane * 4 + 128 * (i >> 2) + (i & 3) : lane + 32 * i;
+}
+template <bool V4, int NVT>
+__device__ __forceinline__ void ln_load(const float* __restrict__ p, int nv, float* v) {
+  const int lane = threadIdx.x & 31;
+  if (V4) {
+#pragma unroll
+    for (int i4 = 0; i4 < NVT / 4; ++i4)
+      if (4 * i4 < nv) {
+        const float4 t = *reinterpret_cast<const float4*>(p + lane * 4 + 128 * i4);
+        v[4 * i4] = t.x; v[4 * i4 + 1] = t.y; v[4 * i4 + 2] = t.z; v[4 * i4 + 3] = t.w;
+      }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NVT; ++i)
+      if (i < nv) v[i] = p[lane + 32 * i];
+  }
+}
+template <bool V4, int NVT>
 __device__ __forceinline__ void warp_ln_stats(const float* __restrict__ xr, int nv, int D, float eps, float* xv, float& mean,
                                               float& rstd) {
-  const int lane = threadIdx.x & 31;
+  ln_load<V4, NVT>(xr, nv, xv);
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_NV; ++i)
-    if (i < nv) { xv[i] = xr[lane + 32 * i]; s += xv[i]; }
+  for (int i = 0; i < NVT; ++i)
+    if (i < nv) s += xv[i];
   mean = warp_sum(s) / (float)D;
   float v = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_NV; ++i)
+  for (int i = 0; i < NVT; ++i)
     if (i < nv) { const float d = xv[i] - mean; v += d * d; }
   rstd = rsqrtf(warp_sum(v) / (float)D + eps);
 }
@@ -254,6 +305,7 @@ __device__ __forceinline__ void warp_ln_stats(const float* __restrict__ xr, int 
 // ---------------------------------------------------------------------------------------------------------------------
 // policy: grid = B, 256 threads
 // ---------------------------------------------------------------------------------------------------------------------
+template <bool V4, int NVT>
 __global__ void __launch_bounds__(256)
 adavit_policy_kernel(const float* __restrict__ x, int L, int D, int H, float eps, const float* n1_w, const float* n1_b,
                      const float* ts_w, const float* ts_b, const float* np_w, const float* np_b, const float* ls_w,
@@ -264,20 +316,30 @@ adavit_policy_kernel(const float* __restrict__ x, int L, int D, int H, float eps
   const int nv = D / 32;
   if (threadIdx.x == 0) s_cnt = 0;
   __syncthreads();
-  float xv[LN_MAX_NV];
+  float xv[NVT];
   int kept = 0;
   if (ts_w) {
+    // per-lane constants of the token score: tok_logit = rstd * sum((x - mean) * gw) + c0, gw = gamma * w_t, c0 = beta . w_t + b_t
+    float gw[NVT];
+    float c0 = 0.f;
+    {
+      float tw[NVT], tb[NVT];
+      ln_load<V4, NVT>(n1_w, nv, gw);
+      ln_load<V4, NVT>(ts_w, nv, tw);
+      ln_load<V4, NVT>(n1_b, nv, tb);
+#pragma unroll
+      for (int i = 0; i < NVT; ++i)
+        if (i < nv) { gw[i] *= tw[i]; c0 += tb[i] * tw[i]; }
+      c0 = warp_sum(c0) + __ldg(ts_b);
+    }
     for (int l = 1 + warp; l < L; l += nwarps) {
       float mean, rstd;
-      warp_ln_stats(x + ((size_t)b * L + l) * D, nv, D, eps, xv, mean, rstd);
+      warp_ln_stats<V4, NVT>(x + ((size_t)b * L + l) * D, nv, D, eps, xv, mean, rstd);
       float acc = 0.f;
 #pragma unroll
-      for (int i = 0; i < LN_MAX_NV; ++i)
-        if (i < nv) {
-          const int j = lane + 32 * i;
-          acc += ((xv[i] - mean) * rstd * __ldg(n1_w + j) + __ldg(n1_b + j)) * __ldg(ts_w + j);
-        }
-      const float lg = warp_sum(acc) + __ldg(ts_b);
+      for (int i = 0; i < NVT; ++i)
+        if (i < nv) acc += (xv[i] - mean) * gw[i];
+      const float lg = warp_sum(acc) * rstd + c0;
       const bool keep = lg >= 0.f;
       if (lane == 0) {
         tok_mask[(size_t)b * L + l] = keep ? 1 : 0;
@@ -300,11 +362,11 @@ adavit_policy_kernel(const float* __restrict__ x, int L, int D, int H, float eps
     }
     if (ls_w || hs_w) {
       float mean, rstd;
-      warp_ln_stats(x + (size_t)b * L * D, nv, D, eps, xv, mean, rstd);
+      warp_ln_stats<V4, NVT>(x + (size_t)b * L * D, nv, D, eps, xv, mean, rstd);
 #pragma unroll
-      for (int i = 0; i < LN_MAX_NV; ++i)
+      for (int i = 0; i < NVT; ++i)
         if (i < nv) {
-          const int j = lane + 32 * i;
+          const int j = ln_idx<V4>(i);
           xv[i] = (xv[i] - mean) * rstd * __ldg(np_w + j) + __ldg(np_b + j);
         }
       const int n_out = (ls_w ? 2 : 0) + (hs_w ? H : 0);
@@ -314,8 +376,8 @@ adavit_policy_kernel(const float* __restrict__ x, int L, int D, int H, float eps
         const float* wrow = (is_layer ? ls_w : hs_w) + (size_t)r * D;
         float acc = 0.f;
 #pragma unroll
-        for (int i = 0; i < LN_MAX_NV; ++i)
-          if (i < nv) acc += xv[i] * __ldg(wrow + lane + 32 * i);
+        for (int i = 0; i < NVT; ++i)
+          if (i < nv) acc += xv[i] * __ldg(wrow + ln_idx<V4>(i));
         const float lg = warp_sum(acc) + __ldg((is_layer ? ls_b : hs_b) + r);
         if (lane == 0) {
           if (is_layer) {
@@ -378,6 +440,7 @@ adavit_lists_kernel(const int* __restrict__ tok_cnt, const uint8_t* __restrict__
 // ---------------------------------------------------------------------------------------------------------------------
 // LayerNorm + gather of the kept tokens: grid = B, 256 threads
 // ---------------------------------------------------------------------------------------------------------------------
+template <bool V4, int NVT>
 __global__ void __launch_bounds__(256)
 adavit_ln_gather_kernel(const float* __restrict__ x, int L, int D, float eps, const float* __restrict__ w,
                         const float* __restrict__ bias, const uint8_t* __restrict__ tok_mask, const int* __restrict__ off,
@@ -398,19 +461,32 @@ adavit_ln_gather_kernel(const float* __restrict__ x, int L, int D, float eps, co
   }
   __syncthreads();
   const int nv = D / 32;
-  float xv[LN_MAX_NV];
+  float xv[NVT], gv[NVT], bv[NVT];
+  ln_load<V4, NVT>(w, nv, gv);
+  ln_load<V4, NVT>(bias, nv, bv);
   for (int l = warp; l < L; l += nwarps) {
     const int rk = s_rank[l];
     if (rk < 0) continue;
     float mean, rstd;
-    warp_ln_stats(x + ((size_t)b * L + l) * D, nv, D, eps, xv, mean, rstd);
+    warp_ln_stats<V4, NVT>(x + ((size_t)b * L + l) * D, nv, D, eps, xv, mean, rstd);
     __half* yr = y + (size_t)(o0 + rk) * D;
+    if (V4) {
 #pragma unroll
-    for (int i = 0; i < LN_MAX_NV; ++i)
-      if (i < nv) {
-        const int j = lane + 32 * i;
-        yr[j] = __float2half_rn((xv[i] - mean) * rstd * __ldg(w + j) + __ldg(bias + j));
-      }
+      for (int i4 = 0; i4 < NVT / 4; ++i4)
+        if (4 * i4 < nv) {
+          float r[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) r[c] = (xv[4 * i4 + c] - mean) * rstd * gv[4 * i4 + c] + bv[4 * i4 + c];
+          uint2 pk;
+          pk.x = pack_h2(r[0], r[1]);
+          pk.y = pack_h2(r[2], r[3]);
+          *reinterpret_cast<uint2*>(yr + lane * 4 + 128 * i4) = pk;
+        }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NVT; ++i)
+        if (i < nv) yr[lane + 32 * i] = __float2half_rn((xv[i] - mean) * rstd * gv[i] + bv[i]);
+    }
     if (lane == 0) {
       if (row_idx) row_idx[o0 + rk] = b * L + l;
       if (row_sample) row_sample[o0 + rk] = b;
@@ -437,10 +513,6 @@ __device__ __forceinline__ void mma16816(float* c, uint32_t a0, uint32_t a1, uin
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
-  const __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<const uint32_t*>(&h);
 }
 
 __global__ void __launch_bounds__(128)
@@ -509,8 +581,8 @@ adavit_attention_kernel(const __half* __restrict__ qkv, int ldq, const int* __re
 #pragma unroll
     for (int j = 0; j < AT_NT; ++j)
       if (j < nt8) {
-        s[j][0] = exp2f((s[j][0] - mx0) * sc); s[j][1] = exp2f((s[j][1] - mx0) * sc);
-        s[j][2] = exp2f((s[j][2] - mx1) * sc); s[j][3] = exp2f((s[j][3] - mx1) * sc);
+        s[j][0] = fast_ex2((s[j][0] - mx0) * sc); s[j][1] = fast_ex2((s[j][1] - mx0) * sc);
+        s[j][2] = fast_ex2((s[j][2] - mx1) * sc); s[j][3] = fast_ex2((s[j][3] - mx1) * sc);
         sum0 += s[j][0] + s[j][1];
         sum1 += s[j][2] + s[j][3];
       }
@@ -577,6 +649,17 @@ __global__ void vit_init_tokens_kernel(float* __restrict__ x, int B, int L, int 
 }  // namespace laud
 
 using namespace laud;
+
+// register slots per lane (D / 32) as a compile-time bound: DeiT-Ti/S/B and the test sizes get exact instantiations
+#define LAUD_LN_DISPATCH(LAUNCH)                         \
+  do {                                                   \
+    if (v4 && D == 128) LAUNCH(true, 4);                 \
+    else if (v4 && D == 384) LAUNCH(true, 12);           \
+    else if (v4 && D == 768) LAUNCH(true, 24);           \
+    else if (v4) LAUNCH(true, 32);                       \
+    else if (D <= 192) LAUNCH(false, 6);                 \
+    else LAUNCH(false, 32);                              \
+  } while (0)
 
 extern "C" unsigned long long laud_tok_gemm_launch_count(void) { return g_tok_gemm_launches.load(); }
 
@@ -649,9 +732,14 @@ extern "C" int laud_adavit_policy(const float* x, int B, int L, int D, int H, fl
   LAUD_REQUIRE(!ts_w || (n1_w && n1_b && ts_b), "laud_adavit_policy: the token score needs norm1 and its bias");
   LAUD_REQUIRE(!(ls_w || hs_w) || (np_w && np_b), "laud_adavit_policy: layer / head policies need the policy LayerNorm");
   LAUD_REQUIRE((!ls_w || ls_b) && (!hs_w || hs_b), "laud_adavit_policy: missing policy bias");
-  adavit_policy_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(x, L, D, H, eps, n1_w, n1_b, ts_w, ts_b, np_w, np_b, ls_w, ls_b, hs_w,
-                                                            hs_b, tok_mask, tok_cnt, head_sel, layer_sel, tok_logits, head_logits,
-                                                            layer_logits);
+  const bool v4 = D % 128 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)n1_w & 15) == 0 && ((uintptr_t)n1_b & 15) == 0 &&
+                  ((uintptr_t)ts_w & 15) == 0;
+#define LAUD_POLICY_LAUNCH(V4, NVT)                                                                                               \
+  adavit_policy_kernel<V4, NVT><<<B, 256, 0, (cudaStream_t)stream>>>(x, L, D, H, eps, n1_w, n1_b, ts_w, ts_b, np_w, np_b, ls_w, ls_b, \
+                                                                     hs_w, hs_b, tok_mask, tok_cnt, head_sel, layer_sel, tok_logits, \
+                                                                     head_logits, layer_logits)
+  LAUD_LN_DISPATCH(LAUD_POLICY_LAUNCH);
+#undef LAUD_POLICY_LAUNCH
   return check_launch("adavit_policy_kernel");
 }
 
@@ -667,7 +755,13 @@ extern "C" int laud_adavit_ln_gather(const float* x, int B, int L, int D, float 
                                      void* stream) {
   LAUD_REQUIRE(x && w && bias && off && y, "laud_adavit_ln_gather: null argument");
   LAUD_REQUIRE(B > 0 && L > 0 && L <= 1024 && D % 32 == 0 && D <= 1024, "laud_adavit_ln_gather: bad shape (L=%d D=%d)", L, D);
-  adavit_ln_gather_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(x, L, D, eps, w, bias, tok_mask, off, (__half*)y, row_idx, row_sample);
+  const bool v4 = D % 128 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0 && ((uintptr_t)bias & 15) == 0 &&
+                  ((uintptr_t)y & 7) == 0;
+#define LAUD_LNG_LAUNCH(V4, NVT)                                                                                            \
+  adavit_ln_gather_kernel<V4, NVT><<<B, 256, 0, (cudaStream_t)stream>>>(x, L, D, eps, w, bias, tok_mask, off, (__half*)y, row_idx, \
+                                                                        row_sample)
+  LAUD_LN_DISPATCH(LAUD_LNG_LAUNCH);
+#undef LAUD_LNG_LAUNCH
   return check_launch("adavit_ln_gather_kernel");
 }
 
