@@ -10,6 +10,7 @@
 //                          (mma.sync m16n8k16, the whole score row lives in registers: L <= 208).
 //   policy / lists / ln_gather / patchify / init: the HBM-bound glue (one pass over the fp32 token stream each).
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 #include "laud_adavit.h"
 #include "laud_common.cuh"
@@ -34,6 +35,8 @@ __device__ __forceinline__ float fast_ex2(float x) {
 // token GEMM
 // =====================================================================================================================
 constexpr int TG_BM = 128, TG_BK = 64, TG_STAGES = 4;
+constexpr int TG_MAX_STAGES = 6;                      // weight-resident mode: 16 KB activation stages
+constexpr int TG_SMEM_MAX = 230400;                   // dynamic shared memory the kernel may ask for (+ static barriers < 227 KB)
 constexpr int TG_EPI_WARPS = 8;                       // two warps per TMEM lane quarter, each takes half of the tile's columns
 constexpr int TG_THREADS = (2 + TG_EPI_WARPS) * 32;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int TG_A_BYTES = TG_BM * 128;
@@ -49,10 +52,14 @@ struct TgArgs {
   const int* row_idx;
   const uint8_t* col_gate; int gate_ld;
   const int* row_sample;
+  int bres;       // weight-resident mode: the CTA owns ONE n-tile, keeps its whole [bn, K] weight tile in shared memory and
+                  // streams only activation tiles (L2 -> SM operand feed, ~20-35 B/clk/SM measured, is what bounds this GEMM:
+                  // 96 KB instead of 288 KB per 128 x 192 x 384 tile)
+  int stages;
 };
 
 struct alignas(8) TgBars {
-  unsigned long long full[TG_STAGES], empty[TG_STAGES], tfull[2], tempty[2];
+  unsigned long long full[TG_MAX_STAGES], empty[TG_MAX_STAGES], tfull[2], tempty[2], bfull;
   uint32_t tmem_base;
 };
 
@@ -88,10 +95,13 @@ tok_gemm_kernel(const TgArgs a, const __grid_constant__ CUtensorMap map_a, const
   __shared__ TgBars bars;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int stage_bytes = TG_A_BYTES + a.bn * 128;
+  const int b_bytes = a.bn * 128;                                    // one 64-channel chunk of the weight tile
+  const int stage_bytes = a.bres ? TG_A_BYTES : TG_A_BYTES + b_bytes;
+  const uint32_t bres_base = smem_base + a.stages * stage_bytes;      // resident weight tile: K/64 chunks of b_bytes
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < TG_STAGES; ++i) { mbar_init(&bars.full[i], 1); mbar_init(&bars.empty[i], 1); }
+    for (int i = 0; i < TG_MAX_STAGES; ++i) { mbar_init(&bars.full[i], 1); mbar_init(&bars.empty[i], 1); }
+    mbar_init(&bars.bfull, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&bars.tfull[i], 1); mbar_init(&bars.tempty[i], TG_EPI_WARPS * 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&map_a);
@@ -109,23 +119,35 @@ tok_gemm_kernel(const TgArgs a, const __grid_constant__ CUtensorMap map_a, const
 
   const int cnt = a.row_cnt ? min(__ldg(a.row_cnt), a.rows_max) : a.rows_max;
   const int m_tiles = (cnt + TG_BM - 1) / TG_BM, n_tiles = (a.N + a.bn - 1) / a.bn;
-  const int items = m_tiles * n_tiles, kchunks = a.K / TG_BK;
+  const int kchunks = a.K / TG_BK;
+  // work of this CTA: items it0, it0 + step, ... < items; item -> (m-tile, n-tile)
+  //   streaming mode: item = m * n_tiles + nt over the whole grid;  weight-resident mode: the CTA's n-tile is fixed
+  //   (blockIdx.x % n_tiles) and it walks the m-tiles g, g + G, ... of its group of G = gridDim.x / n_tiles CTAs
+  const int my_nt = a.bres ? (int)(blockIdx.x % n_tiles) : 0;
+  const int it0 = a.bres ? (int)(blockIdx.x / n_tiles) : (int)blockIdx.x;
+  const int step = a.bres ? (int)(gridDim.x / n_tiles) : (int)gridDim.x;
+  const int items = a.bres ? m_tiles : m_tiles * n_tiles;
+#define TG_DECODE(it, m, nt) const int m = a.bres ? (it) : (it) / n_tiles, nt = a.bres ? my_nt : (it) - m * n_tiles
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
+      if (a.bres && it0 < items) {
+        mbar_arrive_expect_tx(&bars.bfull, (uint32_t)(kchunks * b_bytes));
+        for (int kc = 0; kc < kchunks; ++kc) tma_load_2d(bres_base + kc * b_bytes, &map_b, &bars.bfull, kc * TG_BK, my_nt * a.bn);
+      }
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = blockIdx.x; it < items; it += gridDim.x) {
-        const int m = it / n_tiles, nt = it - m * n_tiles;
+      for (int it = it0; it < items; it += step) {
+        TG_DECODE(it, m, nt);
         if (!tg_tile_active(a, m, nt, cnt)) continue;
         for (int kc = 0; kc < kchunks; ++kc) {
           mbar_wait(&bars.empty[stage], phase ^ 1u);
           const uint32_t As = smem_base + stage * stage_bytes;
           mbar_arrive_expect_tx(&bars.full[stage], (uint32_t)stage_bytes);
           tma_load_2d(As, &map_a, &bars.full[stage], kc * TG_BK, m * TG_BM);
-          tma_load_2d(As + TG_A_BYTES, &map_b, &bars.full[stage], kc * TG_BK, nt * a.bn);
-          if (++stage == TG_STAGES) { stage = 0; phase ^= 1u; }
+          if (!a.bres) tma_load_2d(As + TG_A_BYTES, &map_b, &bars.full[stage], kc * TG_BK, nt * a.bn);
+          if (++stage == a.stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -135,9 +157,11 @@ tok_gemm_kernel(const TgArgs a, const __grid_constant__ CUtensorMap map_a, const
     const uint32_t idesc = umma_idesc_f16(a.bn, 0);
     int stage = 0, buf = 0;
     uint32_t phase = 0, bphase = 0;
-    for (int it = blockIdx.x; it < items; it += gridDim.x) {
-      const int m = it / n_tiles, nt = it - m * n_tiles;
+    bool b_ready = !a.bres;
+    for (int it = it0; it < items; it += step) {
+      TG_DECODE(it, m, nt);
       if (!tg_tile_active(a, m, nt, cnt)) continue;
+      if (!b_ready) { mbar_wait(&bars.bfull, 0); b_ready = true; }
       mbar_wait(&bars.tempty[buf], bphase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + buf * TG_ACC_STRIDE;
@@ -145,10 +169,11 @@ tok_gemm_kernel(const TgArgs a, const __grid_constant__ CUtensorMap map_a, const
         mbar_wait(&bars.full[stage], phase);
         tc_fence_after();
         const uint32_t As = smem_base + stage * stage_bytes;
-        const uint64_t ad = umma_desc(As, 16, 1024), bd = umma_desc(As + TG_A_BYTES, 16, 1024);
+        const uint64_t ad = umma_desc(As, 16, 1024);
+        const uint64_t bd = umma_desc(a.bres ? bres_base + kc * b_bytes : As + TG_A_BYTES, 16, 1024);
         umma_f16_elect_x4(d_tmem, ad, bd, idesc, kc ? 1u : 0u, 2u);
         umma_commit_elect(&bars.empty[stage]);
-        if (++stage == TG_STAGES) { stage = 0; phase ^= 1u; }
+        if (++stage == a.stages) { stage = 0; phase ^= 1u; }
       }
       umma_commit_elect(&bars.tfull[buf]);
       if (++buf == 2) { buf = 0; bphase ^= 1u; }
@@ -158,10 +183,11 @@ tok_gemm_kernel(const TgArgs a, const __grid_constant__ CUtensorMap map_a, const
     // ------------------------------------------------------------ epilogue: one accumulator row (TMEM lane) per thread
     const int q = warp & 3, half = (warp - 2) >> 2;           // TMEM lane quarter of this warp; which half of the columns
     const int cbeg = half * (a.bn >> 1), cend = cbeg + (a.bn >> 1);
+    const bool st32 = a.out && (a.ldo & 15) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 31) == 0;   // 32-byte row pieces
     int buf = 0;
     uint32_t bphase = 0;
-    for (int it = blockIdx.x; it < items; it += gridDim.x) {
-      const int m = it / n_tiles, nt = it - m * n_tiles;
+    for (int it = it0; it < items; it += step) {
+      TG_DECODE(it, m, nt);
       if (!tg_tile_active(a, m, nt, cnt)) continue;
       const int row = m * TG_BM + q * 32 + lane;
       const bool valid = row < cnt;
@@ -182,36 +208,47 @@ tok_gemm_kernel(const TgArgs a, const __grid_constant__ CUtensorMap map_a, const
         tmem_ld32(taddr + c0, v);
         if (valid) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (g * 8 >= ncol) break;
-          float r[8];
+          for (int g2 = 0; g2 < 2; ++g2) {                       // 16 columns = 32 bytes of fp16 per step
+            const int n16 = ncol - g2 * 16;                      // warp-uniform
+            if (n16 <= 0) break;
+            float r[16];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) r[j] = v[g * 8 + j];
-          if (a.bias) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + c0 + g * 8));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + c0 + g * 8 + 4));
-            r[0] += b0.x; r[1] += b0.y; r[2] += b0.z; r[3] += b0.w;
-            r[4] += b1.x; r[5] += b1.y; r[6] += b1.z; r[7] += b1.w;
-          }
-          if (a.act == LAUD_ACT_GELU) {
+            for (int j = 0; j < 16; ++j) r[j] = v[g2 * 16 + j];
+            const int cc = c0 + g2 * 16;
+            if (a.bias) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) r[j] = gelu_erf(r[j]);
+              for (int j4 = 0; j4 < 4; ++j4)
+                if (j4 * 4 < n16) {
+                  const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + cc + j4 * 4));
+                  r[j4 * 4] += bb.x; r[j4 * 4 + 1] += bb.y; r[j4 * 4 + 2] += bb.z; r[j4 * 4 + 3] += bb.w;
+                }
+            }
+            if (a.act == LAUD_ACT_GELU) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) r[j] = gelu_erf(r[j]);
+            }
+            if (rdst) {
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4)
+                if (j4 * 4 < n16)
+                  // x += r as a 16-byte reduction at L2 (REDG.ADD.F32x4): every element is owned by exactly one thread of one
+                  // launch, so the sum is the same single fp32 addition a load-add-store would do - without the load's
+                  // round trip (a read-modify-write chain per row piece made proj / fc2 latency-bound: 24 x ~800 cycles)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(rdst + cc + j4 * 4), "f"(r[j4 * 4]),
+                               "f"(r[j4 * 4 + 1]), "f"(r[j4 * 4 + 2]), "f"(r[j4 * 4 + 3])
+                               : "memory");
+            } else {
+              uint4 p0, p1;
+              p0.x = pack_h2(r[0], r[1]); p0.y = pack_h2(r[2], r[3]); p0.z = pack_h2(r[4], r[5]); p0.w = pack_h2(r[6], r[7]);
+              p1.x = pack_h2(r[8], r[9]); p1.y = pack_h2(r[10], r[11]); p1.z = pack_h2(r[12], r[13]); p1.w = pack_h2(r[14], r[15]);
+              if (n16 >= 16 && st32) {
+                stg256(hdst + cc, p0, p1);
+              } else {
+                *reinterpret_cast<uint4*>(hdst + cc) = p0;
+                if (n16 > 8) *reinterpret_cast<uint4*>(hdst + cc + 8) = p1;
+              }
+            }
           }
-          if (rdst) {
-            float4* p = reinterpret_cast<float4*>(rdst + c0 + g * 8);
-            float4 x0 = p[0], x1 = p[1];
-            x0.x += r[0]; x0.y += r[1]; x0.z += r[2]; x0.w += r[3];
-            x1.x += r[4]; x1.y += r[5]; x1.z += r[6]; x1.w += r[7];
-            p[0] = x0; p[1] = x1;
-          } else {
-            __half2 h0 = __floats2half2_rn(r[0], r[1]), h1 = __floats2half2_rn(r[2], r[3]);
-            __half2 h2 = __floats2half2_rn(r[4], r[5]), h3 = __floats2half2_rn(r[6], r[7]);
-            uint4 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-            *reinterpret_cast<uint4*>(hdst + c0 + g * 8) = pk;
-          }
-        }
         }
         __syncwarp();                                          // tcgen05.ld is warp-collective: reconverge before the next one
       }
@@ -221,6 +258,9 @@ tok_gemm_kernel(const TgArgs a, const __grid_constant__ CUtensorMap map_a, const
     }
   }
 
+#undef TG_DECODE
+  if (a.bres && warp == 0 && lane == 0 && it0 < items) mbar_wait(&bars.bfull, 0);   // the weight tile's copies have landed (a
+                                                                                  // CTA whose tiles were all gated never used it)
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -674,7 +714,11 @@ extern "C" int laud_tok_gemm(const laud_tok_gemm_desc* d, void* stream) {
   LAUD_REQUIRE(((uintptr_t)d->a & 15) == 0 && ((uintptr_t)d->w & 15) == 0 && ((uintptr_t)d->out & 15) == 0 && ((uintptr_t)d->resid & 15) == 0 &&
                ((uintptr_t)d->bias & 15) == 0, "laud_tok_gemm: operands must be 16-byte aligned");
   int bn = d->bn;
-  if (bn == 0) bn = d->N % 256 == 0 ? 256 : d->N % 192 == 0 ? 192 : d->N % 128 == 0 ? 128 : d->N >= 256 ? 256 : 64 * ((d->N + 63) / 64);
+  if (bn == 0) {
+    // 192-wide tiles whose whole [192, K] weight tile can stay resident next to >= 3 activation stages (K <= 384) come first
+    if (d->N % 192 == 0 && (long long)(d->K / 64) * 192 * 128 + 3 * TG_A_BYTES + 1024 <= TG_SMEM_MAX) bn = 192;
+    else bn = d->N % 256 == 0 ? 256 : d->N % 192 == 0 ? 192 : d->N % 128 == 0 ? 128 : d->N >= 256 ? 256 : 64 * ((d->N + 63) / 64);
+  }
   LAUD_REQUIRE(bn == 64 || bn == 128 || bn == 192 || bn == 256, "laud_tok_gemm: bn must be 64 / 128 / 192 / 256 (got %d)", bn);
   LAUD_REQUIRE(!d->col_gate || (d->row_sample && d->gate_ld >= (d->N + bn - 1) / bn), "laud_tok_gemm: col_gate needs row_sample and gate_ld >= n-tiles");
   cudaStream_t s = (cudaStream_t)stream;
@@ -685,9 +729,22 @@ extern "C" int laud_tok_gemm(const laud_tok_gemm_desc* d, void* stream) {
     LAUD_CUDA(cudaGetDeviceProperties(&prop, dev));
     di.sms = prop.multiProcessorCount;
   }
-  const size_t smem = (size_t)TG_STAGES * (TG_A_BYTES + bn * 128) + 1024;
+  const int n_tiles = (d->N + bn - 1) / bn, m_tiles_max = (d->rows_max + TG_BM - 1) / TG_BM;
+  // weight-resident mode when the [bn, K] tile + >= 3 activation stages fit and every n-tile gets at least one CTA
+  int bres = 0, stages = TG_STAGES;
+  {
+    const long long wbytes = (long long)(d->K / 64) * bn * 128;
+    const long long room = (long long)TG_SMEM_MAX - 1024 - wbytes;
+    if (!getenv("LAUD_TOKGEMM_STREAM") && room >= 3 * TG_A_BYTES && n_tiles <= di.sms && m_tiles_max >= 2 * (di.sms / n_tiles)) {
+      bres = 1;
+      stages = (int)(room / TG_A_BYTES);
+      if (stages > TG_MAX_STAGES) stages = TG_MAX_STAGES;
+    }
+  }
+  const size_t smem = bres ? (size_t)stages * TG_A_BYTES + (size_t)(d->K / 64) * bn * 128 + 1024
+                           : (size_t)TG_STAGES * (TG_A_BYTES + bn * 128) + 1024;
   if (!di.gemm_attr) {
-    LAUD_CUDA(cudaFuncSetAttribute(tok_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_STAGES * (TG_A_BYTES + 256 * 128) + 1024));
+    LAUD_CUDA(cudaFuncSetAttribute(tok_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_MAX));
     di.gemm_attr = true;
   }
   CUtensorMap ma, mb;
@@ -699,8 +756,9 @@ extern "C" int laud_tok_gemm(const laud_tok_gemm_desc* d, void* stream) {
   a.bias = d->bias; a.rows_max = d->rows_max; a.K = d->K; a.N = d->N; a.bn = bn; a.row_cnt = d->row_cnt; a.act = d->act;
   a.out = (__half*)d->out; a.ldo = d->ldo; a.resid = d->resid; a.ldres = d->ldres; a.row_idx = d->row_idx;
   a.col_gate = d->col_gate; a.gate_ld = d->gate_ld; a.row_sample = d->row_sample;
-  const int items = ((d->rows_max + TG_BM - 1) / TG_BM) * ((d->N + bn - 1) / bn);
-  const int grid = items < di.sms ? items : di.sms;
+  a.bres = bres; a.stages = stages;
+  const int items = m_tiles_max * n_tiles;
+  const int grid = bres ? (di.sms / n_tiles) * n_tiles : (items < di.sms ? items : di.sms);
   tok_gemm_kernel<<<grid, TG_THREADS, smem, s>>>(a, ma, mb);
   g_tok_gemm_launches.fetch_add(1, std::memory_order_relaxed);
   return check_launch("tok_gemm_kernel");

@@ -34,7 +34,9 @@ def _gemm(a, w, bias, rows_max, K, N, **kw):
 
 # --------------------------------------------------------------------------- token GEMM
 @pytest.mark.parametrize("rows,K,N,bn", [(300, 128, 192, 0), (1000, 384, 1152, 192), (517, 1536, 384, 0), (130, 384, 1000, 0),
-                                         (64, 64, 64, 0), (2600, 384, 1536, 256), (333, 768, 384, 128)])
+                                         (64, 64, 64, 0), (2600, 384, 1536, 256), (333, 768, 384, 128),
+                                         # weight-resident mode (K <= 384, enough m-tiles per CTA): QKV / proj / fc1 shapes
+                                         (12000, 384, 1152, 192), (21000, 384, 384, 0), (9000, 384, 1536, 0), (7000, 128, 192, 0)])
 def test_tok_gemm_store_vs_torch(cuda_lib, rows, K, N, bn):
     g = torch.Generator().manual_seed(rows + K + N)
     a = (torch.randn(rows, K, generator=g) * 0.5).half().to(DEV)
@@ -71,10 +73,11 @@ def test_tok_gemm_residual_scatter_and_no_row_count(cuda_lib):
     assert torch.equal(x[untouched], x0[untouched])
 
 
-def test_tok_gemm_head_tile_skip(cuda_lib):
+@pytest.mark.parametrize("big", [False, True])      # big: enough rows for the weight-resident mode
+def test_tok_gemm_head_tile_skip(cuda_lib, big):
     """col_gate: an n-tile is computed iff one of the samples of the m-tile's rows keeps that head."""
     g = torch.Generator().manual_seed(9)
-    B, H, K = 12, 6, 384
+    B, H, K = (12, 6, 384) if not big else (96, 6, 384)
     N = H * 192
     cnts = torch.randint(20, 150, (B,), generator=g)
     rows = int(cnts.sum())
