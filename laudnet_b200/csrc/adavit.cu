@@ -36,7 +36,8 @@ __device__ __forceinline__ float fast_ex2(float x) {
 // =====================================================================================================================
 constexpr int TG_BM = 128, TG_BK = 64, TG_STAGES = 4;
 constexpr int TG_MAX_STAGES = 6;                      // weight-resident mode: 16 KB activation stages
-constexpr int TG_SMEM_MAX = 230400;                   // dynamic shared memory the kernel may ask for (+ static barriers < 227 KB)
+constexpr int TG_BIAS_MAX = 2048, TG_ACT_MAX = 1024;   // static tables: bias of all N columns, activity flag of the CTA's items
+constexpr int TG_SMEM_MAX = 232448 - TG_BIAS_MAX * 4 - TG_ACT_MAX - 512;   // dynamic shared memory the kernel may ask for
 constexpr int TG_EPI_WARPS = 8;                       // two warps per TMEM lane quarter, each takes half of the tile's columns
 constexpr int TG_THREADS = (2 + TG_EPI_WARPS) * 32;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int TG_A_BYTES = TG_BM * 128;
@@ -93,6 +94,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1)
 tok_gemm_kernel(const TgArgs a, const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ TgBars bars;
+  __shared__ __align__(16) float s_bias[TG_BIAS_MAX];
+  __shared__ uint8_t s_act[TG_ACT_MAX];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int b_bytes = a.bn * 128;                                    // one 64-channel chunk of the weight tile
@@ -112,13 +115,29 @@ tok_gemm_kernel(const TgArgs a, const __grid_constant__ CUtensorMap map_a, const
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  const int cnt = a.row_cnt ? min(__ldg(a.row_cnt), a.rows_max) : a.rows_max;
+  const int m_tiles = (cnt + TG_BM - 1) / TG_BM, n_tiles = (a.N + a.bn - 1) / a.bn;
+  // tables every role reads: the bias of all N columns (the epilogue stalled on its global loads: 30 % of all stall
+  // samples), and - with col_gate - the activity flag of every item of this CTA, evaluated by all threads in parallel
+  // (two dependent global loads per item otherwise sit in front of every role's item loop)
+  const bool bias_tab = a.bias && a.N <= TG_BIAS_MAX;
+  if (bias_tab)
+    for (int i = threadIdx.x; i < a.N; i += TG_THREADS) s_bias[i] = __ldg(a.bias + i);
+  {
+    const int nt_ = a.bres ? (int)(blockIdx.x % n_tiles) : 0, i0_ = a.bres ? (int)(blockIdx.x / n_tiles) : (int)blockIdx.x;
+    const int st_ = a.bres ? (int)(gridDim.x / n_tiles) : (int)gridDim.x, items_ = a.bres ? m_tiles : m_tiles * n_tiles;
+    const int n_local = i0_ < items_ ? (items_ - i0_ + st_ - 1) / st_ : 0;
+    if (a.col_gate && n_local <= TG_ACT_MAX)
+      for (int j = threadIdx.x; j < n_local; j += TG_THREADS) {
+        const int it = i0_ + j * st_;
+        const int m = a.bres ? it : it / n_tiles, nt = a.bres ? nt_ : it - m * n_tiles;
+        s_act[j] = tg_tile_active(a, m, nt, cnt) ? 1 : 0;
+      }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars.tmem_base;
-
-  const int cnt = a.row_cnt ? min(__ldg(a.row_cnt), a.rows_max) : a.rows_max;
-  const int m_tiles = (cnt + TG_BM - 1) / TG_BM, n_tiles = (a.N + a.bn - 1) / a.bn;
   const int kchunks = a.K / TG_BK;
   // work of this CTA: items it0, it0 + step, ... < items; item -> (m-tile, n-tile)
   //   streaming mode: item = m * n_tiles + nt over the whole grid;  weight-resident mode: the CTA's n-tile is fixed
@@ -128,6 +147,8 @@ tok_gemm_kernel(const TgArgs a, const __grid_constant__ CUtensorMap map_a, const
   const int step = a.bres ? (int)(gridDim.x / n_tiles) : (int)gridDim.x;
   const int items = a.bres ? m_tiles : m_tiles * n_tiles;
 #define TG_DECODE(it, m, nt) const int m = a.bres ? (it) : (it) / n_tiles, nt = a.bres ? my_nt : (it) - m * n_tiles
+  const bool act_tab = a.col_gate && (it0 < items ? (items - it0 + step - 1) / step : 0) <= TG_ACT_MAX;
+#define TG_ACTIVE(it, m, nt) (!a.col_gate || (act_tab ? s_act[((it) - it0) / step] != 0 : tg_tile_active(a, m, nt, cnt)))
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -140,7 +161,7 @@ tok_gemm_kernel(const TgArgs a, const __grid_constant__ CUtensorMap map_a, const
       uint32_t phase = 0;
       for (int it = it0; it < items; it += step) {
         TG_DECODE(it, m, nt);
-        if (!tg_tile_active(a, m, nt, cnt)) continue;
+        if (!TG_ACTIVE(it, m, nt)) continue;
         for (int kc = 0; kc < kchunks; ++kc) {
           mbar_wait(&bars.empty[stage], phase ^ 1u);
           const uint32_t As = smem_base + stage * stage_bytes;
@@ -160,7 +181,7 @@ tok_gemm_kernel(const TgArgs a, const __grid_constant__ CUtensorMap map_a, const
     bool b_ready = !a.bres;
     for (int it = it0; it < items; it += step) {
       TG_DECODE(it, m, nt);
-      if (!tg_tile_active(a, m, nt, cnt)) continue;
+      if (!TG_ACTIVE(it, m, nt)) continue;
       if (!b_ready) { mbar_wait(&bars.bfull, 0); b_ready = true; }
       mbar_wait(&bars.tempty[buf], bphase ^ 1u);
       tc_fence_after();
@@ -188,7 +209,7 @@ tok_gemm_kernel(const TgArgs a, const __grid_constant__ CUtensorMap map_a, const
     uint32_t bphase = 0;
     for (int it = it0; it < items; it += step) {
       TG_DECODE(it, m, nt);
-      if (!tg_tile_active(a, m, nt, cnt)) continue;
+      if (!TG_ACTIVE(it, m, nt)) continue;
       const int row = m * TG_BM + q * 32 + lane;
       const bool valid = row < cnt;
       const int n0 = nt * a.bn;
@@ -219,7 +240,8 @@ tok_gemm_kernel(const TgArgs a, const __grid_constant__ CUtensorMap map_a, const
 #pragma unroll
               for (int j4 = 0; j4 < 4; ++j4)
                 if (j4 * 4 < n16) {
-                  const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + cc + j4 * 4));
+                  const float4 bb = bias_tab ? *reinterpret_cast<const float4*>(s_bias + n0 + cc + j4 * 4)
+                                             : __ldg(reinterpret_cast<const float4*>(a.bias + n0 + cc + j4 * 4));
                   r[j4 * 4] += bb.x; r[j4 * 4 + 1] += bb.y; r[j4 * 4 + 2] += bb.z; r[j4 * 4 + 3] += bb.w;
                 }
             }
@@ -259,6 +281,7 @@ tok_gemm_kernel(const TgArgs a, const __grid_constant__ CUtensorMap map_a, const
   }
 
 #undef TG_DECODE
+#undef TG_ACTIVE
   if (a.bres && warp == 0 && lane == 0 && it0 < items) mbar_wait(&bars.bfull, 0);   // the weight tile's copies have landed (a
                                                                                   // CTA whose tiles were all gated never used it)
   tc_fence_before();
