@@ -21,6 +21,18 @@ namespace {
 
 std::atomic<unsigned long long> g_tok_gemm_launches{0};
 
+#ifdef LAUD_KPROF   // lap timers (diagnostic build: python -m laudnet_b200.build --prof; scripts/tgprof.py)
+__device__ long long g_tgprof[160 * 4 * 8];
+#define TP_DECL long long tp_t = clock64(), tp_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define TP_LAP(i) do { const long long tp_n = clock64(); tp_acc[i] += tp_n - tp_t; tp_t = tp_n; } while (0)
+#define TP_FLUSH(role) do { if (blockIdx.x < 160) for (int tp_i = 0; tp_i < 8; ++tp_i) \
+    g_tgprof[(blockIdx.x * 4 + (role)) * 8 + tp_i] = tp_acc[tp_i]; } while (0)
+#else
+#define TP_DECL
+#define TP_LAP(i)
+#define TP_FLUSH(role)
+#endif
+
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
@@ -35,11 +47,14 @@ __device__ __forceinline__ float fast_ex2(float x) {
 // token GEMM
 // =====================================================================================================================
 constexpr int TG_BM = 128, TG_BK = 64, TG_STAGES = 4;
+constexpr int TG_EPI_WARPS = 8;                       // two warps per TMEM lane quarter, each takes half of the tile's columns
 constexpr int TG_MAX_STAGES = 6;                      // weight-resident mode: 16 KB activation stages
 constexpr int TG_BIAS_MAX = 2048, TG_ACT_MAX = 1024;   // static tables: bias of all N columns, activity flag of the CTA's items
+constexpr int TG_SCR_BYTES = TG_EPI_WARPS * 2048;      // transposing write-out: 32 rows x 64 B per epilogue warp
 constexpr int TG_SMEM_MAX = 232448 - TG_BIAS_MAX * 4 - TG_ACT_MAX - 512;   // dynamic shared memory the kernel may ask for
-constexpr int TG_EPI_WARPS = 8;                       // two warps per TMEM lane quarter, each takes half of the tile's columns
-constexpr int TG_THREADS = (2 + TG_EPI_WARPS) * 32;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+                                                                            // (pipeline stages, resident weights, residual-mode scratch)
+constexpr int TG_THREADS = (3 + TG_EPI_WARPS) * 32;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue, warp 10 second TMA producer
+constexpr int TG_PROD2_WARP = 2 + TG_EPI_WARPS;
 constexpr int TG_A_BYTES = TG_BM * 128;
 constexpr int TG_ACC_STRIDE = 256;                    // TMEM columns between the two accumulator buffers
 
@@ -57,6 +72,9 @@ struct TgArgs {
                   // streams only activation tiles (L2 -> SM operand feed, ~20-35 B/clk/SM measured, is what bounds this GEMM:
                   // 96 KB instead of 288 KB per 128 x 192 x 384 tile)
   int stages;
+  int dbg;        // LAUD_KPROF builds only (timing experiments, WRONG results): 1 no global writes, 2 no write-out at all, 4 no tcgen05.ld
+  int kcs;        // 64-channel chunks per pipeline stage (one TMA instruction per operand and stage: a producer iteration
+                  // costs ~590 cycles whatever it moves up to 32 KB - scripts/l2_feed.cu - so stages carry 32 KB or more)
 };
 
 struct alignas(8) TgBars {
@@ -99,8 +117,10 @@ tok_gemm_kernel(const TgArgs a, const __grid_constant__ CUtensorMap map_a, const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int b_bytes = a.bn * 128;                                    // one 64-channel chunk of the weight tile
-  const int stage_bytes = a.bres ? TG_A_BYTES : TG_A_BYTES + b_bytes;
+  const int stage_bytes = a.kcs * (a.bres ? TG_A_BYTES : TG_A_BYTES + b_bytes);
+  const int a_stage_bytes = a.kcs * TG_A_BYTES;                       // [kcs][128 rows][64 ch], then (streaming) [kcs][bn rows][64 ch]
   const uint32_t bres_base = smem_base + a.stages * stage_bytes;      // resident weight tile: K/64 chunks of b_bytes
+  const uint32_t scr_base = bres_base + (a.bres ? (a.K / TG_BK) * b_bytes : 0);   // residual mode: transposing scratch
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < TG_MAX_STAGES; ++i) { mbar_init(&bars.full[i], 1); mbar_init(&bars.empty[i], 1); }
@@ -150,27 +170,37 @@ tok_gemm_kernel(const TgArgs a, const __grid_constant__ CUtensorMap map_a, const
   const bool act_tab = a.col_gate && (it0 < items ? (items - it0 + step - 1) / step : 0) <= TG_ACT_MAX;
 #define TG_ACTIVE(it, m, nt) (!a.col_gate || (act_tab ? s_act[((it) - it0) / step] != 0 : tg_tile_active(a, m, nt, cnt)))
 
-  if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
+  if (warp == 0 || warp == TG_PROD2_WARP) {
+    // ------------------------------------------------------------ TMA producers: two threads in two warps take
+    // alternate pipeline stages (a thread's wait -> expect_tx -> copy iteration does not overlap with its own next one)
     if (lane == 0) {
-      if (a.bres && it0 < items) {
+      const int me = warp == 0 ? 0 : 1;
+      if (me == 0 && a.bres && it0 < items) {
         mbar_arrive_expect_tx(&bars.bfull, (uint32_t)(kchunks * b_bytes));
-        for (int kc = 0; kc < kchunks; ++kc) tma_load_2d(bres_base + kc * b_bytes, &map_b, &bars.bfull, kc * TG_BK, my_nt * a.bn);
+        for (int kc = 0; kc < kchunks; kc += a.kcs)
+          tma_load_3d(bres_base + kc * b_bytes, &map_b, &bars.bfull, 0, my_nt * a.bn, kc);
       }
-      int stage = 0;
+      int stage = 0, j = 0;
       uint32_t phase = 0;
+      TP_DECL;
       for (int it = it0; it < items; it += step) {
         TG_DECODE(it, m, nt);
         if (!TG_ACTIVE(it, m, nt)) continue;
-        for (int kc = 0; kc < kchunks; ++kc) {
-          mbar_wait(&bars.empty[stage], phase ^ 1u);
-          const uint32_t As = smem_base + stage * stage_bytes;
-          mbar_arrive_expect_tx(&bars.full[stage], (uint32_t)stage_bytes);
-          tma_load_2d(As, &map_a, &bars.full[stage], kc * TG_BK, m * TG_BM);
-          if (!a.bres) tma_load_2d(As + TG_A_BYTES, &map_b, &bars.full[stage], kc * TG_BK, nt * a.bn);
+        for (int kc = 0; kc < kchunks; kc += a.kcs, ++j) {
+          if ((j & 1) == me) {
+            TP_LAP(0);
+            mbar_wait(&bars.empty[stage], phase ^ 1u);
+            TP_LAP(1);                                     // wait for a free stage
+            const uint32_t As = smem_base + stage * stage_bytes;
+            mbar_arrive_expect_tx(&bars.full[stage], (uint32_t)stage_bytes);
+            tma_load_3d(As, &map_a, &bars.full[stage], 0, m * TG_BM, kc);
+            if (!a.bres) tma_load_3d(As + a_stage_bytes, &map_b, &bars.full[stage], 0, nt * a.bn, kc);
+            TP_LAP(2);                                     // issue
+          }
           if (++stage == a.stages) { stage = 0; phase ^= 1u; }
         }
       }
+      TP_FLUSH(me ? 3 : 0);
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -179,105 +209,173 @@ tok_gemm_kernel(const TgArgs a, const __grid_constant__ CUtensorMap map_a, const
     int stage = 0, buf = 0;
     uint32_t phase = 0, bphase = 0;
     bool b_ready = !a.bres;
+    TP_DECL;
     for (int it = it0; it < items; it += step) {
       TG_DECODE(it, m, nt);
       if (!TG_ACTIVE(it, m, nt)) continue;
+      TP_LAP(0);
       if (!b_ready) { mbar_wait(&bars.bfull, 0); b_ready = true; }
+      TP_LAP(4);                                           // resident weight tile
       mbar_wait(&bars.tempty[buf], bphase ^ 1u);
+      TP_LAP(1);                                           // wait for a free accumulator
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + buf * TG_ACC_STRIDE;
-      for (int kc = 0; kc < kchunks; ++kc) {
+      for (int kc = 0; kc < kchunks; kc += a.kcs) {
         mbar_wait(&bars.full[stage], phase);
+        TP_LAP(2);                                         // wait for operands
         tc_fence_after();
         const uint32_t As = smem_base + stage * stage_bytes;
-        const uint64_t ad = umma_desc(As, 16, 1024);
-        const uint64_t bd = umma_desc(a.bres ? bres_base + kc * b_bytes : As + TG_A_BYTES, 16, 1024);
-        umma_f16_elect_x4(d_tmem, ad, bd, idesc, kc ? 1u : 0u, 2u);
+        for (int c = 0; c < a.kcs; ++c) {
+          const uint64_t ad = umma_desc(As + c * TG_A_BYTES, 16, 1024);
+          const uint64_t bd = umma_desc(a.bres ? bres_base + (kc + c) * b_bytes : As + a_stage_bytes + c * b_bytes, 16, 1024);
+          umma_f16_elect_x4(d_tmem, ad, bd, idesc, (kc | c) ? 1u : 0u, 2u);
+        }
         umma_commit_elect(&bars.empty[stage]);
         if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+        TP_LAP(3);                                         // issue + commit
       }
       umma_commit_elect(&bars.tfull[buf]);
       if (++buf == 2) { buf = 0; bphase ^= 1u; }
     }
+    if (lane == 0) TP_FLUSH(1);
     __syncwarp();
   } else {
     // ------------------------------------------------------------ epilogue: one accumulator row (TMEM lane) per thread
     const int q = warp & 3, half = (warp - 2) >> 2;           // TMEM lane quarter of this warp; which half of the columns
     const int cbeg = half * (a.bn >> 1), cend = cbeg + (a.bn >> 1);
+    // Transposing write-out of the RESIDUAL mode.  A thread owns one accumulator ROW, so reducing its own row pieces puts
+    // the 32 lanes of every red.global on 32 different rows (lap timers: 11k cycles per tile against 2.3k of MMAs).  Each
+    // warp passes its 32 rows x 16 fp32 columns through 2 KB of shared memory (16-byte chunks XOR-swizzled by
+    // (row >> 1) & 3: conflict-free both ways) and issues the reductions with four lanes per row: 8 rows x 64
+    // contiguous bytes per instruction (7.7k cycles per tile).
     const bool st32 = a.out && (a.ldo & 15) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 31) == 0;   // 32-byte row pieces
+    const uint32_t scr = scr_base + (uint32_t)(warp - 2) * 2048u;
+    const uint32_t wr_base = scr + (uint32_t)lane * 64u;
+    const int wr_sw = (lane >> 1) & 3;
+    const int rd_ch = lane & 3;
     int buf = 0;
     uint32_t bphase = 0;
+    TP_DECL;
     for (int it = it0; it < items; it += step) {
       TG_DECODE(it, m, nt);
       if (!TG_ACTIVE(it, m, nt)) continue;
-      const int row = m * TG_BM + q * 32 + lane;
-      const bool valid = row < cnt;
+      TP_LAP(0);
+      const int row0 = m * TG_BM + q * 32;                     // first row of this warp's lane quarter
       const int n0 = nt * a.bn;
-      float* rdst = nullptr;
-      __half* hdst = nullptr;
-      if (valid) {
-        if (a.resid) rdst = a.resid + (size_t)__ldg(a.row_idx + row) * a.ldres + n0;
-        else hdst = a.out + (size_t)row * a.ldo + n0;
-      }
+      const int my_dst = (a.resid && row0 + lane < cnt) ? __ldg(a.row_idx + row0 + lane) : 0;   // destination row of MY row
       mbar_wait(&bars.tfull[buf], bphase);
+      TP_LAP(1);                                           // wait for the accumulator
       tc_fence_after();
       const uint32_t taddr = tmem_base + buf * TG_ACC_STRIDE + ((uint32_t)(q * 32) << 16);
       for (int c0 = cbeg; c0 < cend; c0 += 32) {
         const int ncol = min(32, a.N - (n0 + c0));           // warp-uniform
         if (ncol <= 0) break;
+        // the chunk's 32 bias values first: eight independent 16-byte broadcast loads in flight while tcgen05.ld waits
+        // (guarded loads interleaved with their adds serialise eight load latencies per chunk - measured: the epilogue,
+        // not the MMAs, set the pace of every GEMM)
+        const bool fast_bias = bias_tab && ncol == 32;
+        float4 bb[8];
+        if (fast_bias) {
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) bb[j4] = *reinterpret_cast<const float4*>(s_bias + n0 + c0 + j4 * 4);
+        }
         float v[32];
+#ifdef LAUD_KPROF
+        if (a.dbg & 4) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = (float)(lane + j);
+        } else
+#endif
         tmem_ld32(taddr + c0, v);
-        if (valid) {
+#ifdef LAUD_KPROF
+        if (a.dbg & 2) {
+          float sacc = 0.f;
 #pragma unroll
-          for (int g2 = 0; g2 < 2; ++g2) {                       // 16 columns = 32 bytes of fp16 per step
-            const int n16 = ncol - g2 * 16;                      // warp-uniform
-            if (n16 <= 0) break;
-            float r[16];
+          for (int j = 0; j < 32; ++j) sacc += v[j];
+          if (sacc == 123456.789f) a.out[0] = __float2half(sacc);
+          continue;
+        }
+#endif
+        if (fast_bias) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) r[j] = v[g2 * 16 + j];
-            const int cc = c0 + g2 * 16;
-            if (a.bias) {
+          for (int j4 = 0; j4 < 8; ++j4) {
+            v[j4 * 4] += bb[j4].x; v[j4 * 4 + 1] += bb[j4].y; v[j4 * 4 + 2] += bb[j4].z; v[j4 * 4 + 3] += bb[j4].w;
+          }
+        } else if (a.bias) {
 #pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4)
-                if (j4 * 4 < n16) {
-                  const float4 bb = bias_tab ? *reinterpret_cast<const float4*>(s_bias + n0 + cc + j4 * 4)
-                                             : __ldg(reinterpret_cast<const float4*>(a.bias + n0 + cc + j4 * 4));
-                  r[j4 * 4] += bb.x; r[j4 * 4 + 1] += bb.y; r[j4 * 4 + 2] += bb.z; r[j4 * 4 + 3] += bb.w;
-                }
+          for (int j4 = 0; j4 < 8; ++j4)
+            if (j4 * 4 < ncol) {
+              const float4 b1 = bias_tab ? *reinterpret_cast<const float4*>(s_bias + n0 + c0 + j4 * 4)
+                                         : __ldg(reinterpret_cast<const float4*>(a.bias + n0 + c0 + j4 * 4));
+              v[j4 * 4] += b1.x; v[j4 * 4 + 1] += b1.y; v[j4 * 4 + 2] += b1.z; v[j4 * 4 + 3] += b1.w;
             }
-            if (a.act == LAUD_ACT_GELU) {
+        }
+        if (a.act == LAUD_ACT_GELU) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) r[j] = gelu_erf(r[j]);
-            }
-            if (rdst) {
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        }
+        if (a.out) {
+          // fp16 rows: written by their owner thread, 32 bytes per store.  (Passing these through the transposing
+          // scratch was measured and is NOT faster: the SS-mode MMAs read ~107 B/clk of the SM's 128 B/clk of shared
+          // memory, so shared-memory traffic in the epilogue is what costs, not the 32 cache lines per store.)
+          if (row0 + lane < cnt) {
+            __half* hdst = a.out + (size_t)(row0 + lane) * a.ldo + n0 + c0;
 #pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4)
-                if (j4 * 4 < n16)
-                  // x += r as a 16-byte reduction at L2 (REDG.ADD.F32x4): every element is owned by exactly one thread of one
-                  // launch, so the sum is the same single fp32 addition a load-add-store would do - without the load's
-                  // round trip (a read-modify-write chain per row piece made proj / fc2 latency-bound: 24 x ~800 cycles)
-                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(rdst + cc + j4 * 4), "f"(r[j4 * 4]),
-                               "f"(r[j4 * 4 + 1]), "f"(r[j4 * 4 + 2]), "f"(r[j4 * 4 + 3])
-                               : "memory");
-            } else {
+            for (int g2 = 0; g2 < 2; ++g2) {
+              const int n16 = ncol - g2 * 16;                  // warp-uniform
+              if (n16 <= 0) break;
               uint4 p0, p1;
-              p0.x = pack_h2(r[0], r[1]); p0.y = pack_h2(r[2], r[3]); p0.z = pack_h2(r[4], r[5]); p0.w = pack_h2(r[6], r[7]);
-              p1.x = pack_h2(r[8], r[9]); p1.y = pack_h2(r[10], r[11]); p1.z = pack_h2(r[12], r[13]); p1.w = pack_h2(r[14], r[15]);
+              p0.x = pack_h2(v[16 * g2], v[16 * g2 + 1]); p0.y = pack_h2(v[16 * g2 + 2], v[16 * g2 + 3]);
+              p0.z = pack_h2(v[16 * g2 + 4], v[16 * g2 + 5]); p0.w = pack_h2(v[16 * g2 + 6], v[16 * g2 + 7]);
+              p1.x = pack_h2(v[16 * g2 + 8], v[16 * g2 + 9]); p1.y = pack_h2(v[16 * g2 + 10], v[16 * g2 + 11]);
+              p1.z = pack_h2(v[16 * g2 + 12], v[16 * g2 + 13]); p1.w = pack_h2(v[16 * g2 + 14], v[16 * g2 + 15]);
+#ifdef LAUD_KPROF
+              if ((a.dbg & 1) && p0.x != 0x12345678u) continue;
+#endif
               if (n16 >= 16 && st32) {
-                stg256(hdst + cc, p0, p1);
+                stg256(hdst + g2 * 16, p0, p1);
               } else {
-                *reinterpret_cast<uint4*>(hdst + cc) = p0;
-                if (n16 > 8) *reinterpret_cast<uint4*>(hdst + cc + 8) = p1;
+                *reinterpret_cast<uint4*>(hdst + g2 * 16) = p0;
+                if (n16 > 8) *reinterpret_cast<uint4*>(hdst + g2 * 16 + 8) = p1;
               }
             }
           }
+          __syncwarp();                                        // tcgen05.ld is warp-collective: reconverge before the next one
+        } else {
+          // fp32 residual add: two passes of 16 columns = 64 bytes per row.  x += r as a 16-byte reduction at L2
+          // (REDG.ADD.F32x4): every element is owned by exactly one thread of one launch, so the sum is the same single
+          // fp32 addition a load-add-store would do - without the load's round trip.
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            if (sub * 16 >= ncol) break;                       // warp-uniform
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 pk;
+              pk.x = __float_as_uint(v[sub * 16 + 4 * j]); pk.y = __float_as_uint(v[sub * 16 + 4 * j + 1]);
+              pk.z = __float_as_uint(v[sub * 16 + 4 * j + 2]); pk.w = __float_as_uint(v[sub * 16 + 4 * j + 3]);
+              sts128(wr_base + (uint32_t)((j ^ wr_sw) << 4), pk);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int rr = (lane >> 2) + 8 * k;
+              const int dst = __shfl_sync(0xffffffffu, my_dst, rr);
+              const uint4 pk = lds128(scr + (uint32_t)rr * 64u + (uint32_t)((rd_ch ^ ((rr >> 1) & 3)) << 4));
+              if (row0 + rr < cnt && sub * 16 + rd_ch * 4 < ncol)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.resid + (size_t)dst * a.ldres + n0 + c0 + sub * 16 + rd_ch * 4),
+                             "f"(__uint_as_float(pk.x)), "f"(__uint_as_float(pk.y)), "f"(__uint_as_float(pk.z)), "f"(__uint_as_float(pk.w))
+                             : "memory");
+            }
+            __syncwarp();
+          }
         }
-        __syncwarp();                                          // tcgen05.ld is warp-collective: reconverge before the next one
       }
+      TP_LAP(2);                                           // tcgen05.ld + arithmetic + stores
       tc_fence_before();
       mbar_arrive(&bars.tempty[buf]);
       if (++buf == 2) { buf = 0; bphase ^= 1u; }
     }
+    if (warp == 2 && lane == 0) TP_FLUSH(2);
   }
 
 #undef TG_DECODE
@@ -308,13 +406,14 @@ EncodeTiledFn tg_encode_fn() {
   }
   return fn;
 }
-// fp16 [rows, ld] row-major, box {64 columns, box_rows}, 128-byte swizzle, out-of-bounds rows read as zero
-bool tg_map(CUtensorMap* m, const void* base, long long cols, long long rows, long long ld, int box_rows) {
+// fp16 [rows, ld] row-major viewed as {64 channels, rows, K/64 chunks}: box {64, box_rows, kcs} lands in shared memory as
+// kcs consecutive K-major SWIZZLE_128B tiles [chunk][row][64]; out-of-bounds rows read as zero
+bool tg_map(CUtensorMap* m, const void* base, long long cols, long long rows, long long ld, int box_rows, int kcs) {
   EncodeTiledFn fn = tg_encode_fn();
   if (!fn) return false;
-  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows}, gstr[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64, (cuuint32_t)box_rows}, es[2] = {1, 1};
-  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  cuuint64_t gdim[3] = {64, (cuuint64_t)rows, (cuuint64_t)(cols / 64)}, gstr[2] = {(cuuint64_t)ld * 2, 128};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, (cuuint32_t)kcs}, es[3] = {1, 1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -726,6 +825,15 @@ using namespace laud;
 
 extern "C" unsigned long long laud_tok_gemm_launch_count(void) { return g_tok_gemm_launches.load(); }
 
+#ifdef LAUD_KPROF
+extern "C" int laud_debug_tgprof(long long* host_out /* [160][4][8] */, int reset) {
+  void* p = nullptr;
+  if (cudaGetSymbolAddress(&p, g_tgprof) != cudaSuccess) return -1;
+  if (reset) return cudaMemset(p, 0, sizeof(long long) * 160 * 4 * 8) == cudaSuccess ? 0 : -1;
+  return cudaMemcpy(host_out, p, sizeof(long long) * 160 * 4 * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
+}
+#endif
+
 extern "C" int laud_tok_gemm(const laud_tok_gemm_desc* d, void* stream) {
   LAUD_REQUIRE(d != nullptr, "laud_tok_gemm: null descriptor");
   LAUD_REQUIRE(d->a && d->w && d->rows_max > 0 && d->K > 0 && d->N > 0, "laud_tok_gemm: null operand or empty shape");
@@ -754,24 +862,32 @@ extern "C" int laud_tok_gemm(const laud_tok_gemm_desc* d, void* stream) {
   }
   const int n_tiles = (d->N + bn - 1) / bn, m_tiles_max = (d->rows_max + TG_BM - 1) / TG_BM;
   // weight-resident mode when the [bn, K] tile + >= 3 activation stages fit and every n-tile gets at least one CTA
-  int bres = 0, stages = TG_STAGES;
+  int bres = 0, stages = TG_STAGES, kcs = 1;
+  const int kchunks = d->K / 64;
   {
-    const long long wbytes = (long long)(d->K / 64) * bn * 128;
-    const long long room = (long long)TG_SMEM_MAX - 1024 - wbytes;
+    const long long wbytes = (long long)kchunks * bn * 128;
+    const long long scr_bytes = d->resid ? TG_SCR_BYTES : 0;
+    const long long room = (long long)TG_SMEM_MAX - 1024 - wbytes - scr_bytes;
     if (!getenv("LAUD_TOKGEMM_STREAM") && room >= 3 * TG_A_BYTES && n_tiles <= di.sms && m_tiles_max >= 2 * (di.sms / n_tiles)) {
       bres = 1;
-      stages = (int)(room / TG_A_BYTES);
-      if (stages > TG_MAX_STAGES) stages = TG_MAX_STAGES;
+      kcs = (kchunks % 2 == 0 && room >= 3 * 2 * TG_A_BYTES && !getenv("LAUD_TOKGEMM_KCS1")) ? 2 : 1;   // >= 3 stages in flight
+      stages = (int)(room / (kcs * TG_A_BYTES));
+    } else {
+      // streaming: two chunks per stage when at least two such stages fit
+      const long long st2 = 2LL * (TG_A_BYTES + bn * 128);
+      kcs = (kchunks % 2 == 0 && 2 * st2 + 1024 + scr_bytes <= TG_SMEM_MAX && !getenv("LAUD_TOKGEMM_KCS1")) ? 2 : 1;
+      stages = (int)((TG_SMEM_MAX - 1024 - scr_bytes) / (kcs * (TG_A_BYTES + bn * 128)));
     }
+    if (stages > TG_MAX_STAGES) stages = TG_MAX_STAGES;
   }
-  const size_t smem = bres ? (size_t)stages * TG_A_BYTES + (size_t)(d->K / 64) * bn * 128 + 1024
-                           : (size_t)TG_STAGES * (TG_A_BYTES + bn * 128) + 1024;
+  const size_t smem = (size_t)stages * kcs * (bres ? TG_A_BYTES : TG_A_BYTES + bn * 128) + (bres ? (size_t)kchunks * bn * 128 : 0) +
+                      (d->resid ? TG_SCR_BYTES : 0) + 1024;
   if (!di.gemm_attr) {
     LAUD_CUDA(cudaFuncSetAttribute(tok_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_MAX));
     di.gemm_attr = true;
   }
   CUtensorMap ma, mb;
-  if (!tg_map(&ma, d->a, d->K, d->rows_max, d->lda, TG_BM) || !tg_map(&mb, d->w, d->K, d->N, d->K, bn)) {
+  if (!tg_map(&ma, d->a, d->K, d->rows_max, d->lda, TG_BM, kcs) || !tg_map(&mb, d->w, d->K, d->N, d->K, bn, kcs)) {
     set_error("laud_tok_gemm: cuTensorMapEncodeTiled failed");
     return LAUD_E_CUDA;
   }
@@ -779,7 +895,8 @@ extern "C" int laud_tok_gemm(const laud_tok_gemm_desc* d, void* stream) {
   a.bias = d->bias; a.rows_max = d->rows_max; a.K = d->K; a.N = d->N; a.bn = bn; a.row_cnt = d->row_cnt; a.act = d->act;
   a.out = (__half*)d->out; a.ldo = d->ldo; a.resid = d->resid; a.ldres = d->ldres; a.row_idx = d->row_idx;
   a.col_gate = d->col_gate; a.gate_ld = d->gate_ld; a.row_sample = d->row_sample;
-  a.bres = bres; a.stages = stages;
+  a.bres = bres; a.stages = stages; a.kcs = kcs;
+  a.dbg = getenv("LAUD_TG_DBG") ? atoi(getenv("LAUD_TG_DBG")) : 0;
   const int items = m_tiles_max * n_tiles;
   const int grid = bres ? (di.sms / n_tiles) * n_tiles : (items < di.sms ? items : di.sms);
   tok_gemm_kernel<<<grid, TG_THREADS, smem, s>>>(a, ma, mb);
