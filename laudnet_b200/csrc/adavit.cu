@@ -661,7 +661,7 @@ adavit_ln_gather_kernel(const float* __restrict__ x, int L, int D, float eps, co
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int AT_MAX_T = 208, AT_PITCH = 72;          // rows of 64 halves padded to 72 (144 B: conflict-free ldmatrix)
 constexpr int AT_NT = AT_MAX_T / 8;                   // 26 score n8-tiles
-constexpr int AT_SMEM = 3 * AT_MAX_T * AT_PITCH * 2;  // 89 856 B
+constexpr int AT_SMEM = (2 * AT_MAX_T + 4 * 16) * AT_PITCH * 2;   // K, V of the (sample, head) + one 16-row Q tile per warp: 69 120 B (3 CTAs / SM)
 
 __device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
@@ -677,7 +677,7 @@ __device__ __forceinline__ void mma16816(float* c, uint32_t a0, uint32_t a1, uin
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 3)
 adavit_attention_kernel(const __half* __restrict__ qkv, int ldq, const int* __restrict__ off, const uint8_t* __restrict__ head_sel,
                         int H, __half* __restrict__ o) {
   extern __shared__ __align__(16) unsigned char at_smem[];
@@ -690,16 +690,18 @@ adavit_attention_kernel(const __half* __restrict__ qkv, int ldq, const int* __re
       *reinterpret_cast<uint4*>(o + (size_t)(r0 + (i >> 3)) * D + h * 64 + (i & 7) * 8) = make_uint4(0, 0, 0, 0);
     return;
   }
-  __half* sQ = reinterpret_cast<__half*>(at_smem);
-  __half* sK = sQ + AT_MAX_T * AT_PITCH;
+  __half* sK = reinterpret_cast<__half*>(at_smem);
   __half* sV = sK + AT_MAX_T * AT_PITCH;
+  __half* sQ = sV + AT_MAX_T * AT_PITCH + (threadIdx.x >> 5) * 16 * AT_PITCH;      // this warp's query tile
   const int n16 = (n + 15) & ~15;
-  for (int i = threadIdx.x; i < n16 * 24; i += blockDim.x) {
-    const int r = i / 24, part = i - r * 24, which = part >> 3, ch = part & 7;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (r < n) v = __ldg(reinterpret_cast<const uint4*>(qkv + (size_t)(r0 + r) * ldq + h * 192 + which * 64 + ch * 8));
-    *reinterpret_cast<uint4*>((which == 0 ? sQ : which == 1 ? sK : sV) + r * AT_PITCH + ch * 8) = v;
+  // K and V rows of the kept tokens: asynchronous 16-byte copies, all in flight at once (rows n .. n16 zero-filled)
+  for (int i = threadIdx.x; i < n16 * 16; i += blockDim.x) {
+    const int r = i >> 4, which = (i >> 3) & 1, ch = i & 7;
+    const int rr = r < n ? r : 0;
+    cp_async_16(smem_u32((which ? sV : sK) + r * AT_PITCH + ch * 8), qkv + (size_t)(r0 + rr) * ldq + h * 192 + 64 + which * 64 + ch * 8,
+                r < n ? 16u : 0u);
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int nk16 = n16 >> 4, nt8 = nk16 * 2;
@@ -707,10 +709,20 @@ adavit_attention_kernel(const __half* __restrict__ qkv, int ldq, const int* __re
   const uint32_t q_u = smem_u32(sQ), k_u = smem_u32(sK), v_u = smem_u32(sV);
   for (int qt = warp; qt < nk16; qt += 4) {
     const int q0 = qt * 16;
+    // the warp's 16 query rows -> its own staging tile (rows >= n zero-filled)
+    __syncwarp();
+#pragma unroll
+    for (int i = lane; i < 16 * 8; i += 32) {
+      const int r = i >> 3, ch = i & 7;
+      const int rr = q0 + r < n ? q0 + r : 0;
+      cp_async_16(q_u + (uint32_t)((r * AT_PITCH + ch * 8) * 2), qkv + (size_t)(r0 + rr) * ldq + h * 192 + ch * 8, q0 + r < n ? 16u : 0u);
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
     uint32_t qa[4][4];
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk)
-      ldmatrix_x4(q_u + (uint32_t)(((q0 + (lane & 7) + ((lane >> 3) & 1) * 8) * AT_PITCH + kk * 16 + (lane >> 4) * 8) * 2), qa[kk][0],
+      ldmatrix_x4(q_u + (uint32_t)((((lane & 7) + ((lane >> 3) & 1) * 8) * AT_PITCH + kk * 16 + (lane >> 4) * 8) * 2), qa[kk][0],
                   qa[kk][1], qa[kk][2], qa[kk][3]);
     float s[AT_NT][4];
 #pragma unroll
