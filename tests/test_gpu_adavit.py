@@ -236,6 +236,22 @@ def test_blocks_teacher_forced_vs_oracle(cuda_lib, cfg, batch):
     assert torch.equal(y0, y1)
 
 
+@pytest.mark.parametrize("dim,heads", [(192, 3), (768, 12)])
+def test_other_deit_widths_teacher_forced(cuda_lib, dim, heads):
+    """DeiT-Ti (D = 192: scalar LayerNorm loads, three 64-channel chunks) and DeiT-B (D = 768: the QKV / proj / fc1 weight tiles
+    no longer fit in shared memory -> streaming mode with head-tile skipping) through the same kernels, two blocks deep."""
+    cfg = A.AdaViTCfg(embed_dim=dim, num_heads=heads, depth=3, num_classes=40)
+    m, sd, x = _build(cfg, 61, 3, token_rate=0.5, head_rate=0.5, layer_rate=0.7)
+    traces = []
+    with torch.no_grad():
+        want = A.forward(sd, cfg, x, traces)[0]
+    for i, t in enumerate(traces):
+        y = m.run_block(i, t.x_in.to(DEV), forced=_forced(t.policy))
+        assert _rel(y, t.x_out) <= ACT_TOL, (i, _rel(y, t.x_out))
+    lf, *_ = m(x.to(DEV), forced=[_forced(t.policy) for t in traces])
+    assert _rel(lf, want) <= NET_TOL
+
+
 def _compare_free_running(keeps, traces, B):
     """Decisions in execution order per sample up to its first differing block; a difference is accepted only inside the
     margin.  Returns (agree mask [B], flips)."""
