@@ -1,9 +1,10 @@
 // AdaViT token / head / layer-skip block for sm_100a (include/laud_adavit.h; self-oracle oracle/adavit_oracle.py).
 //
-//   tok_gemm_kernel        persistent, warp-specialised tcgen05 GEMM over COMPACT token rows with a device-side row count:
+//   tok_gemm_kernel        persistent, warp-specialised tcgen05 GEMM over COMPACT token rows with a device-side row count (a
+//                          second TMA producer, warp 14, takes the odd pipeline stages):
 //                          warp 0 = TMA producer (A rows and W rows as 128B-swizzled K-major tiles), warp 1 = MMA issuer
 //                          (warp-uniform, tcgen05.mma M=128 N=bn K=16, fp32 accumulators double-buffered in TMEM),
-//                          warps 2-5 = epilogue (tcgen05.ld -> bias / GELU -> fp16 rows, or fp32 add into the residual
+//                          warps 2-13 = epilogue (tcgen05.ld -> bias / GELU -> fp16 rows, or fp32 add into the residual
 //                          stream at the rows' destinations).  Dropped tokens are simply not in the row list; dropped heads
 //                          drop whole n-tiles of the QKV projection (col_gate).
 //   adavit_attention_kernel one CTA per (sample, head): kept tokens only, softmax(QK^T)V on warp-level tensor cores
@@ -47,13 +48,13 @@ __device__ __forceinline__ float fast_ex2(float x) {
 // token GEMM
 // =====================================================================================================================
 constexpr int TG_BM = 128, TG_BK = 64, TG_STAGES = 4;
-constexpr int TG_EPI_WARPS = 8;                       // two warps per TMEM lane quarter, each takes half of the tile's columns
+constexpr int TG_EPI_WARPS = 12;                      // three warps per TMEM lane quarter, each takes a third of the tile's columns
 constexpr int TG_MAX_STAGES = 6;                      // weight-resident mode: 16 KB activation stages
 constexpr int TG_BIAS_MAX = 2048, TG_ACT_MAX = 1024;   // static tables: bias of all N columns, activity flag of the CTA's items
 constexpr int TG_SCR_BYTES = TG_EPI_WARPS * 2048;      // transposing write-out: 32 rows x 64 B per epilogue warp
 constexpr int TG_SMEM_MAX = 232448 - TG_BIAS_MAX * 4 - TG_ACT_MAX - 512;   // dynamic shared memory the kernel may ask for
                                                                             // (pipeline stages, resident weights, residual-mode scratch)
-constexpr int TG_THREADS = (3 + TG_EPI_WARPS) * 32;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue, warp 10 second TMA producer
+constexpr int TG_THREADS = (3 + TG_EPI_WARPS) * 32;   // warp 0 TMA, warp 1 MMA, warps 2..13 epilogue, warp 14 second TMA producer
 constexpr int TG_PROD2_WARP = 2 + TG_EPI_WARPS;
 constexpr int TG_A_BYTES = TG_BM * 128;
 constexpr int TG_ACC_STRIDE = 256;                    // TMEM columns between the two accumulator buffers
@@ -91,18 +92,17 @@ __device__ __forceinline__ bool tg_tile_active(const TgArgs& a, int m, int nt, i
   return false;
 }
 
-// GELU = 0.5 x (1 + erf(x / sqrt 2)) with erf(z) = 1 - 2^(-z g(z)), z = min(|x| / sqrt 2, 4.2), g a degree-5 polynomial
-// (weighted least-squares fit of -log2(erfc(z)) / z on [0, 4.2]; |erf error| <= 3.3e-7 in fp32 arithmetic, i.e. below the
-// fp16 rounding of the result by three orders of magnitude): 13 instructions with ONE MUFU (ex2) per element - erff() costs
-// about twice that and the fc1 epilogue is CUDA-core bound (32 768 elements per 128 x 256 tile against 3 072 MMA cycles).
+// GELU = 0.5 x (1 + erf(x / sqrt 2)) with erf(z) = 1 - 2^(-z g(z)), z = min(|x| / sqrt 2, 4.2), g a cubic (weighted
+// least-squares fit of -log2(erfc(z)) / z on [0, 4.2]; |erf error| <= 1.5e-5, relative GELU error <= 1.4e-5 in fp32
+// arithmetic - 35 times below the fp16 rounding of the result): 11 instructions with ONE MUFU (ex2) per element.  erff()
+// costs about twice that, and the fc1 epilogue is CUDA-core bound (24 576 elements per 128 x 192 tile against 2 304 MMA
+// cycles leave 12 instructions per element).
 __device__ __forceinline__ float gelu_erf(float x) {
   const float z = fminf(fabsf(x) * 0.70710678118654752f, 4.2f);
-  float g = -0.00014210730552722268f;
-  g = fmaf(g, z, 0.0036644166832296744f);
-  g = fmaf(g, z, -0.030896032968564496f);
-  g = fmaf(g, z, 0.1496990034547756f);
-  g = fmaf(g, z, 0.9181656741673894f);
-  g = fmaf(g, z, 1.6279250470245474f);
+  float g = -0.01912664651955773f;
+  g = fmaf(g, z, 0.1366242101912244f);
+  g = fmaf(g, z, 0.9236007311276428f);
+  g = fmaf(g, z, 1.6272712644631255f);
   const float erf_abs = 1.0f - fast_ex2(-(g * z));
   const float hx = 0.5f * x;
   return fmaf(fabsf(hx), erf_abs, hx);
@@ -241,8 +241,9 @@ tok_gemm_kernel(const TgArgs a, const __grid_constant__ CUtensorMap map_a, const
     __syncwarp();
   } else {
     // ------------------------------------------------------------ epilogue: one accumulator row (TMEM lane) per thread
-    const int q = warp & 3, half = (warp - 2) >> 2;           // TMEM lane quarter of this warp; which half of the columns
-    const int cbeg = half * (a.bn >> 1), cend = cbeg + (a.bn >> 1);
+    const int q = warp & 3, part = (warp - 2) >> 2;           // TMEM lane quarter of this warp; which third of the columns
+    const int per = ((a.bn / 32 + 2) / 3) * 32;               // 32-column chunks per warp: 64 | 64 | 64 of 192, 96 | 96 | 64 of 256
+    const int cbeg = part * per, cend = min(a.bn, cbeg + per);
     // Transposing write-out of the RESIDUAL mode.  A thread owns one accumulator ROW, so reducing its own row pieces puts
     // the 32 lanes of every red.global on 32 different rows (lap timers: 11k cycles per tile against 2.3k of MMAs).  Each
     // warp passes its 32 rows x 16 fp32 columns through 2 KB of shared memory (16-byte chunks XOR-swizzled by
