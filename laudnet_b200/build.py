@@ -35,12 +35,19 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
+# sources the mask-conditioned convolution kernels are built from (the kernels profiles/conv_traffic.json describes)
+CONV_SOURCES = ("conv_tma.cu", "conv_umma.cu", "conv_ref.cu", "c_api.cu", "umma_ptx.cuh", "laud_common.cuh", "laud_b200.h")
+
+
 def source_hash() -> str:
-    """sha256 over the CUDA sources and the C header (16 hex digits): ties a committed ncu capture
-    (profiles/conv_traffic.json) to the build it was taken from."""
+    """sha256 over the sources of the convolution kernels and their C header (16 hex digits): ties a committed ncu capture
+    (profiles/conv_traffic.json) to the build of those kernels it was taken from."""
     import hashlib
     h = hashlib.sha256()
-    for path in sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + sorted(glob.glob(os.path.join(ROOT, "include", "*.h"))):
+    paths = sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + sorted(glob.glob(os.path.join(ROOT, "include", "*.h")))
+    for path in paths:
+        if os.path.basename(path) not in CONV_SOURCES:
+            continue
         h.update(os.path.basename(path).encode())
         h.update(open(path, "rb").read())
     return h.hexdigest()[:16]

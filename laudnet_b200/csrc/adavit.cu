@@ -837,11 +837,17 @@ __global__ void vit_patchify_kernel(const __half* __restrict__ x, int B, int S, 
 }
 __global__ void vit_init_tokens_kernel(float* __restrict__ x, int B, int L, int D, const float* __restrict__ pos,
                                        const float* __restrict__ cls) {
-  const size_t total = (size_t)B * L * D;
+  const int d4n = D >> 2;                                       // 16-byte pieces per token (D % 4 == 0)
+  const size_t total = (size_t)B * L * d4n;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int d = (int)(i % D);
-    const int l = (int)((i / D) % L);
-    x[i] = __ldg(pos + (size_t)l * D + d) + (l == 0 ? __ldg(cls + d) : 0.f);
+    const int d4 = (int)(i % d4n);
+    const int l = (int)((i / d4n) % L);
+    float4 v = __ldg(reinterpret_cast<const float4*>(pos + (size_t)l * D) + d4);
+    if (l == 0) {
+      const float4 c = __ldg(reinterpret_cast<const float4*>(cls) + d4);
+      v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;
+    }
+    reinterpret_cast<float4*>(x)[i] = v;
   }
 }
 
@@ -951,8 +957,9 @@ extern "C" int laud_vit_patchify(const void* x_nchw, int B, int S, int P, void* 
 }
 
 extern "C" int laud_vit_init_tokens(float* x, int B, int L, int D, const float* pos, const float* cls, void* stream) {
-  LAUD_REQUIRE(x && pos && cls && B > 0 && L > 0 && D > 0, "laud_vit_init_tokens: bad arguments");
-  const size_t total = (size_t)B * L * D;
+  LAUD_REQUIRE(x && pos && cls && B > 0 && L > 0 && D > 0 && D % 4 == 0, "laud_vit_init_tokens: bad arguments (D %% 4 == 0)");
+  LAUD_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)pos & 15) == 0 && ((uintptr_t)cls & 15) == 0, "laud_vit_init_tokens: 16-byte alignment");
+  const size_t total = (size_t)B * L * (D / 4);
   const int grid = (int)((total + 255) / 256 < 65535 * 4 ? (total + 255) / 256 : 65535 * 4);
   vit_init_tokens_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, B, L, D, pos, cls);
   return check_launch("vit_init_tokens_kernel");
