@@ -137,6 +137,12 @@ int laud_expand_mask(const uint8_t* mask, int B, int g, int H, int W, int stride
 int laud_resize_mask_nearest(const uint8_t* mask, int B, int g, int S, int H_out,
                              uint8_t* out, void* stream);
 
+/* The S == 1 case of that resize on a NON-square feature map (the detection backbone resizes the gate to the actual
+ * feature size, mmdet/models/backbones/lad_mmdet_resnet.py:274): out[b, j, 0:hw] = gate[b, j] for every (sample, group);
+ * total_out += ones written (nullable). */
+int laud_broadcast_gate(const uint8_t* gate /* [B, g] */, int B, int g, int hw, uint8_t* out /* [B, g, hw] */,
+                        int32_t* total_out, void* stream);
+
 /* The three spatial masks of a block in one launch (laud_resnet.py:105-110 = laud_resize_mask_nearest +
  * laud_expand_mask(1,0) + laud_expand_mask(stride,1)): small u8 [B,g,S,S] -> m3, m2 u8 [B,g,H_out,H_out],
  * m1 u8 [B,g,H_out*stride,H_out*stride]; total2 / total1 += ones of m2 / m1 (x g, as the reference's means count). */

@@ -158,6 +158,12 @@ class BlockPlan:
     w3t: Optional[torch.Tensor] = None
     cw: Optional[torch.Tensor] = None       # H1 constants: [9*width + outplanes, width] weights pre-scaled by relu(shift)
     module: nn.Module = None
+    W_in: int = 0                           # feature-map widths (== heights for the classification networks; the detection
+    W_out: int = 0                          # backbone adapter runs non-square inputs in channel / layer mode)
+
+    def __post_init__(self):
+        self.W_in = self.W_in or self.H_in
+        self.W_out = self.W_out or self.H_out
 
     @property
     def masker_kind(self) -> Optional[str]:
@@ -255,6 +261,11 @@ class ResNetEngine:
                               H_in=blk.output_size * blk.stride, H_out=blk.output_size, mode=blk.dyn_mode,
                               gran=blk.channel_dyn_granularity, G=blk.channel_dyn_group,
                               g_spatial=blk.spatial_mask_channel_group, mask_size=blk.mask_size, module=blk)
+                p.W_out = getattr(blk, "output_w", None) or blk.output_size
+                p.W_in = p.W_out * blk.stride
+                if p.W_out != p.H_out and blk.dyn_mode in ("spatial", "both"):
+                    raise LaudError("non-square feature maps are supported in channel / layer mode only (the spatial mask "
+                                    "geometry kernels take square masks)")
                 if blk.conv2.groups != 1:
                     raise LaudError("grouped conv2 (group_width>1) is not supported by the CUDA path")
                 p.w1, p.w2, p.w3 = (pack_conv_weight(c.weight) for c in (blk.conv1, blk.conv2, blk.conv3))
@@ -288,18 +299,18 @@ class ResNetEngine:
             if p.use_c:
                 mk = blk.masker_channel
                 if hasattr(mk, "conv_flops"):
-                    m_chan = p.inplanes * p.H_in * p.H_in + mk.conv_flops
+                    m_chan = p.inplanes * p.H_in * p.W_in + mk.conv_flops
                 else:
                     cr = mk.conv[0].weight.shape[0]
-                    m_chan = cr * p.H_in * p.H_in + mk.masker_flops
+                    m_chan = cr * p.H_in * p.W_in + mk.masker_flops
             S = min(p.mask_size, p.H_in)
             if p.use_s:
                 m_spat = p.inplanes * S * S + blk.masker_spatial.conv_flops_pp * S * S
             rows.append([m_chan, m_spat,
-                         blk.conv1_flops_per_pixel * p.H_in * p.H_in,
-                         blk.conv2_flops_per_pixel * p.H_out * p.H_out,
-                         blk.conv3_flops_per_pixel * p.H_out * p.H_out,
-                         (blk.downsample_flops * p.H_out * p.H_out) if blk.downsample is not None else 0,
+                         blk.conv1_flops_per_pixel * p.H_in * p.W_in,
+                         blk.conv2_flops_per_pixel * p.H_out * p.W_out,
+                         blk.conv3_flops_per_pixel * p.H_out * p.W_out,
+                         (blk.downsample_flops * p.H_out * p.W_out) if blk.downsample is not None else 0,
                          0, 0, 0, 0,      # denominators depend on the batch: filled per forward
                          (1 if p.use_c else 0) | (2 if p.use_s else 0), 0])
         return torch.tensor(rows, dtype=torch.int64)     # host; a device copy per batch size lives in the workspace
@@ -314,15 +325,15 @@ class ResNetEngine:
         f16 = dict(dtype=torch.float16, device=dev)
         i32 = dict(dtype=torch.int32, device=dev)
         C0 = m.conv1.weight.shape[0]
-        act = max([B * (H // 4) * (W // 4) * C0] + [B * p.H_out * p.H_out * p.outplanes for p in self.plans])
-        a1 = max(B * p.H_in * p.H_in * (p.width + 16) for p in self.plans)
-        a2 = max(B * p.H_out * p.H_out * (p.width + 16) for p in self.plans)
+        act = max([B * (H // 4) * (W // 4) * C0] + [B * p.H_out * p.W_out * p.outplanes for p in self.plans])
+        a1 = max(B * p.H_in * p.W_in * (p.width + 16) for p in self.plans)
+        a2 = max(B * p.H_out * p.W_out * (p.width + 16) for p in self.plans)
         nb = len(self.plans)
         Gmax = max([p.G for p in self.plans if p.use_c] or [1])
         Cmax = max([p.inplanes for p in self.plans] + [m.fc.weight.shape[1]])
         wmax = max(p.width for p in self.plans)
         comax = max(p.outplanes for p in self.plans)
-        hw_max = max(p.H_in * p.H_in for p in self.plans)
+        hw_max = max(p.H_in * p.W_in for p in self.plans)
         g_max = max(p.g_spatial for p in self.plans)
         ws = dict(
             act=[torch.empty(act, **f16), torch.empty(act, **f16), torch.empty(act, **f16)],
@@ -345,13 +356,13 @@ class ResNetEngine:
             lidx=torch.empty((B * g_max,), **i32), lcnt=torch.empty((B,), **i32),
             stats=torch.empty(nb * 5 + 1, dtype=torch.float32, device=dev),
             logits=None,
-            gap=torch.empty(max(B * gap_tiles(p.H_out * p.H_out) * p.outplanes for p in self.plans), dtype=torch.float32,
+            gap=torch.empty(max(B * gap_tiles(p.H_out * p.W_out) * p.outplanes for p in self.plans), dtype=torch.float32,
                             device=dev),
         )
         cl = [p for p in self.plans if p.masker_kind == "conv_linear"]
         if cl:      # Masker_channel_conv_linear: reduced-width feature map and its pool
             cr = lambda p: (p.module.masker_channel.conv[0].weight.shape[0] + 7) // 8 * 8
-            ws["mkz"] = torch.empty(max(B * p.H_in * p.H_in * cr(p) for p in cl), **f16)
+            ws["mkz"] = torch.empty(max(B * p.H_in * p.W_in * cr(p) for p in cl), **f16)
             ws["mkpool"] = torch.empty(max(B * cr(p) for p in cl), dtype=torch.float32, device=dev)
         else:
             ws["mkz"] = ws["mkpool"] = None
@@ -360,8 +371,8 @@ class ResNetEngine:
             S = min(p.mask_size, p.H_in)
             consts[i, 6] = B * p.G
             consts[i, 7] = B * p.g_spatial * S * S
-            consts[i, 8] = B * p.g_spatial * p.H_out * p.H_out
-            consts[i, 9] = B * p.g_spatial * p.H_in * p.H_in
+            consts[i, 8] = B * p.g_spatial * p.H_out * p.W_out
+            consts[i, 9] = B * p.g_spatial * p.H_in * p.W_in
         ws["consts"] = consts.to(dev)
         self._ws[key] = ws
         return ws
@@ -380,7 +391,7 @@ class ResNetEngine:
         blk = p.module
         L = lib()
         st = stream_ptr()
-        Hi, Ho = p.H_in, p.H_out
+        Hi, Ho, Wi, Wo = p.H_in, p.H_out, p.W_in, p.W_out
         counts = ws["counts"][p.index]
         gate = None
         m3 = None
@@ -402,14 +413,14 @@ class ResNetEngine:
             if forced_channel_mask is not None:
                 self._force_channel_gate(gate, forced_channel_mask, counts[0:1])
             elif gap_in:
-                blk.masker_channel.gate_from_partials(ws["gap"], B, Hi * Hi, p.inplanes, gap_tiles(Hi * Hi), ctot, gate)
+                blk.masker_channel.gate_from_partials(ws["gap"], B, Hi * Wi, p.inplanes, gap_tiles(Hi * Wi), ctot, gate)
             elif p.masker_kind == "conv_linear":
                 # conv 1x1 + BN + ReLU at full resolution, then pool (utils.py:150-169): pre-packed weights, workspaces
-                blk.masker_channel.gate_nhwc(x[:B * Hi * Hi * p.inplanes].view(B, Hi, Hi, p.inplanes), ctot,
+                blk.masker_channel.gate_nhwc(x[:B * Hi * Wi * p.inplanes].view(B, Hi, Wi, p.inplanes), ctot,
                                              out=gate, partial_ws=ws["partial"], impl=self.impl, z_ws=ws["mkz"],
                                              pooled_ws=ws["mkpool"])
             else:
-                blk.masker_channel.gate_nhwc(x[:B * Hi * Hi * p.inplanes].view(B, Hi, Hi, p.inplanes), ctot,
+                blk.masker_channel.gate_nhwc(x[:B * Hi * Wi * p.inplanes].view(B, Hi, Wi, p.inplanes), ctot,
                                              out=gate, partial_ws=ws["partial"])
             if nz_c is not None and forced_channel_mask is None:
                 from .utils import gate_from_logits
@@ -445,28 +456,39 @@ class ResNetEngine:
                 if S == 1 and "lidx" in ws:
                     # one gate per sample (layer skip): global pool -> 2g-row linear -> keep>=drop is exactly the
                     # one-layer channel masker; its fused one-CTA-per-sample kernel pools at HBM speed
-                    check(L.laud_masker_channel_mlp(ptr(x), B, Hi * Hi, p.inplanes, 1, ptr(wt),
+                    check(L.laud_masker_channel_mlp(ptr(x), B, Hi * Wi, p.inplanes, 1, ptr(wt),
                                                     ptr(wbias), 0, None, None, g,
                                                     ptr(ws["partial"]), None, ptr(slog), ptr(small), ptr(ws["lidx"]),
                                                     ptr(ws["lcnt"]), ptr(stot), st), "laud_masker_channel_mlp")
                 else:
-                    check(L.laud_masker_spatial(ptr(x), B, Hi, Hi, p.inplanes, ptr(wt),
+                    check(L.laud_masker_spatial(ptr(x), B, Hi, Wi, p.inplanes, ptr(wt),
                                                 ptr(wbias), g, S, ptr(slog), ptr(small),
                                                 ptr(stot), st), "laud_masker_spatial")
                 if nz_s is not None:
                     from .utils import gate_from_logits
                     gate_from_logits(slog, nz_s, tau, g, S * S, small, total=counts[1:2])
-            m3 = ws["m3"][:B * g * Ho * Ho].view(B, g, Ho, Ho)
-            m2 = ws["m2"][:B * g * Ho * Ho].view(B, g, Ho, Ho)
-            m1 = ws["m1"][:B * g * Hi * Hi].view(B, g, Hi, Hi)
+            m3 = ws["m3"][:B * g * Ho * Wo].view(B, g, Ho, Wo)
+            m2 = ws["m2"][:B * g * Ho * Wo].view(B, g, Ho, Wo)
+            m1 = ws["m1"][:B * g * Hi * Wi].view(B, g, Hi, Wi)
             fast_layer = (p.mode == "layer" and self.layer_exec == "skip" and g == 1 and S == 1 and "srows" in ws
                           and keep is None)
             if fast_layer:
                 # one launch: active-sample work list + the counts of the broadcast / dilated masks
-                check(L.laud_layer_gate_lists(ptr(small), B, Ho * Ho, Hi * Hi, ptr(counts), ptr(ws["srows"]),
+                check(L.laud_layer_gate_lists(ptr(small), B, Ho * Wo, Hi * Wi, ptr(counts), ptr(ws["srows"]),
                                               ptr(ws["scnt"]), st), "laud_layer_gate_lists")
                 if p.wd is not None:     # the downsample branch gates its ReLU per pixel
-                    check(L.laud_resize_mask_nearest(ptr(small), B, g, S, Ho, ptr(m3), st), "laud_resize_mask_nearest")
+                    if Ho == Wo:
+                        check(L.laud_resize_mask_nearest(ptr(small), B, g, S, Ho, ptr(m3), st), "laud_resize_mask_nearest")
+                    else:
+                        check(L.laud_broadcast_gate(ptr(small), B, g, Ho * Wo, ptr(m3), None, st), "laud_broadcast_gate")
+            elif Ho != Wo:
+                # non-square map (detection adapter, layer mode: S == 1): the gate broadcast to the three mask sizes; a
+                # per-sample gate dilates to itself (ExpandMask of a constant map)
+                if S != 1:
+                    raise LaudError("non-square feature maps need a per-sample gate (mask_size 1)")
+                check(L.laud_broadcast_gate(ptr(small), B, g, Ho * Wo, ptr(m3), None, st), "laud_broadcast_gate")
+                check(L.laud_broadcast_gate(ptr(small), B, g, Ho * Wo, ptr(m2), ptr(counts[2:3]), st), "laud_broadcast_gate")
+                check(L.laud_broadcast_gate(ptr(small), B, g, Hi * Wi, ptr(m1), ptr(counts[3:4]), st), "laud_broadcast_gate")
             else:
                 check(L.laud_spatial_masks(ptr(small), B, g, S, Ho, p.stride, ptr(m3), ptr(m2), ptr(m1), ptr(counts[2:3]),
                                            ptr(counts[3:4]), st), "laud_spatial_masks")
@@ -494,16 +516,16 @@ class ResNetEngine:
         nm = dict(n_mask=gate.mask, n_mask_gran=p.gran) if dense_gate else {}
         ld12 = wp if sparse_gate else p.width
         # conv1 1x1 (+ mask) + bn1 + relu      laud_resnet.py:115-118
-        run_conv(x, p.w1, a1, B, Hi, Hi, p.inplanes, Hi, Hi, p.width, 1, 1, 0, ldx=p.inplanes, ldy=ld12,
+        run_conv(x, p.w1, a1, B, Hi, Wi, p.inplanes, Hi, Wi, p.width, 1, 1, 0, ldx=p.inplanes, ldy=ld12,
                  scale=p.s1, shift=p.t1, relu=_lib.RELU_ALL, impl=self.impl, tag=f"s{p.stage + 1}.conv1", **cn, **nm, **sl)
         # conv2 3x3/stride (+ mask) + bn2 + relu     laud_resnet.py:123-126
         if dense_gate and not sl and self.uses_nskip(p):
             # channel skipping with a dense result: active weight rows by TMA gather4, N = active columns, expanded rows
-            run_conv(a1, p.w2, a2, B, Hi, Hi, p.width, Ho, Ho, p.width, 3, 1, 1, ldx=p.width, ldy=p.width,
+            run_conv(a1, p.w2, a2, B, Hi, Wi, p.width, Ho, Wo, p.width, 3, 1, 1, ldx=p.width, ldy=p.width,
                      scale=p.s2, shift=p.t2, relu=_lib.RELU_ALL, impl=self.impl, tag=f"s{p.stage + 1}.conv2",
                      n_idx=gate.idx, n_cnt=gate.cnt, n_gran=p.gran, n_pad_align=16, n_expand=1)
         else:
-          run_conv(a1, p.w2, a2, B, Hi, Hi, p.width, Ho, Ho, p.width, 3, p.stride, 1, ldx=ld12, ldy=ld12,
+          run_conv(a1, p.w2, a2, B, Hi, Wi, p.width, Ho, Wo, p.width, 3, p.stride, 1, ldx=ld12, ldy=ld12,
                  scale=p.s2, shift=p.t2, relu=_lib.RELU_ALL, impl=self.impl, tag=f"s{p.stage + 1}.conv2",
                  pre_bias=ws["pb2"] if (sparse_gate and not use_wt) else None,
                  pre_bias_classes=16 if (sparse_gate and not use_wt) else 0,
@@ -514,40 +536,40 @@ class ResNetEngine:
             if p.wd is not None:
                 # every sample gets its downsampled identity straight into `out`; a skipped sample's output is
                 # relu(identity) (ReLU applied here, where the gate is 0), an active one is finished by conv3 in place
-                run_conv(x, p.wd, out, B, Hi, Hi, p.inplanes, Ho, Ho, p.outplanes, 1, p.stride, 0, ldx=p.inplanes,
+                run_conv(x, p.wd, out, B, Hi, Wi, p.inplanes, Ho, Wo, p.outplanes, 1, p.stride, 0, ldx=p.inplanes,
                          ldy=p.outplanes, scale=p.sd, shift=p.td, relu=_lib.RELU_WHERE_GATE0, out_mask=m3, mask_groups=1,
                          impl=self.impl, tag=f"s{p.stage + 1}.down")
                 dst = out
             else:
                 dst = x                            # in place: skipped samples keep relu(x) == x
-            run_conv(a2, p.w3, dst, B, Ho, Ho, p.width, Ho, Ho, p.outplanes, 1, 1, 0, ldx=ld12, ldy=p.outplanes,
+            run_conv(a2, p.w3, dst, B, Ho, Wo, p.width, Ho, Wo, p.outplanes, 1, 1, 0, ldx=ld12, ldy=p.outplanes,
                      scale=p.s3, shift=p.t3, relu=_lib.RELU_ALL, residual=dst, ldr=p.outplanes, impl=self.impl,
                      tag=f"s{p.stage + 1}.conv3", **sl)
             out = dst
         else:
             if p.wd is not None:
-                run_conv(x, p.wd, idbuf, B, Hi, Hi, p.inplanes, Ho, Ho, p.outplanes, 1, p.stride, 0, ldx=p.inplanes,
+                run_conv(x, p.wd, idbuf, B, Hi, Wi, p.inplanes, Ho, Wo, p.outplanes, 1, p.stride, 0, ldx=p.inplanes,
                          ldy=p.outplanes, scale=p.sd, shift=p.td, relu=_lib.RELU_NONE, impl=self.impl,
                          tag=f"s{p.stage + 1}.down")
                 res = idbuf
             else:
                 res = x
             # conv3 1x1 + bn3 (+ spatial mask) + identity + relu     laud_resnet.py:131-144
-            run_conv(a2, p.w3, out, B, Ho, Ho, p.width, Ho, Ho, p.outplanes, 1, 1, 0, ldx=ld12, ldy=p.outplanes,
+            run_conv(a2, p.w3, out, B, Ho, Wo, p.width, Ho, Wo, p.outplanes, 1, 1, 0, ldx=ld12, ldy=p.outplanes,
                      scale=p.s3, shift=p.t3, relu=_lib.RELU_ALL, residual=res, ldr=p.outplanes, impl=self.impl,
                      tag=f"s{p.stage + 1}.conv3", pre_bias=ws["pb3"] if (sparse_gate and not use_wt) else None,
                      pre_bias_classes=1 if (sparse_gate and not use_wt) else 0,
                      bias_t=T.view(-1)[9 * p.width:] if use_wt else None, bias_ld=Tn if use_wt else 0,
                      pre_bias_ld=p.outplanes if sparse_gate else 0, out_mask=m3, mask_groups=p.g_spatial if m3 is not None else 1,
                      w_t=p.w3t if (sparse_gate and use_wt) else None,
-                     gap_partial=ws["gap"] if gap_out else None, gap_tiles=gap_tiles(Ho * Ho) if gap_out else 0, **ck)
+                     gap_partial=ws["gap"] if gap_out else None, gap_tiles=gap_tiles(Ho * Wo) if gap_out else 0, **ck)
         if keep is not None:
             if gate is not None:
                 keep.channel_mask, keep.channel_idx, keep.channel_cnt = gate.mask.clone(), gate.idx.clone(), gate.cnt.clone()
                 keep.channel_logits = gate.logits
-            keep.a1 = a1[:B * Hi * Hi * ld12].view(B, Hi, Hi, ld12).clone()
-            keep.a2 = a2[:B * Ho * Ho * ld12].view(B, Ho, Ho, ld12).clone()
-            keep.out = out[:B * Ho * Ho * p.outplanes].view(B, Ho, Ho, p.outplanes).clone()
+            keep.a1 = a1[:B * Hi * Wi * ld12].view(B, Hi, Wi, ld12).clone()
+            keep.a2 = a2[:B * Ho * Wo * ld12].view(B, Ho, Wo, ld12).clone()
+            keep.out = out[:B * Ho * Wo * p.outplanes].view(B, Ho, Wo, p.outplanes).clone()
         return out          # the buffer that holds the block output (the input buffer for an in-place layer skip)
 
     def uses_nskip(self, p: BlockPlan) -> bool:
@@ -555,9 +577,9 @@ class ResNetEngine:
         Where it pays, measured on B200 (profiles/r02*): width >= 256 with at least two m-tiles per sample (14x14 maps:
         1.36 ms vs 1.55 ms masked-dense over the 22 stage-3 layers of ResNet-101); narrower layers are not MMA-bound and
         at 7x7 the per-sample weight-row gather (4.7 MB of weights per sample) costs more than the skipped MMAs save."""
-        return (self.channel_exec == "nskip" and p.use_c and p.stride == 1 and p.H_out + 2 <= 128 and p.gran % 2 == 0
+        return (self.channel_exec == "nskip" and p.use_c and p.stride == 1 and p.W_out + 2 <= 128 and p.gran % 2 == 0
                 and p.width >= getattr(self, "nskip_min_width", 256)
-                and p.H_out * p.H_out >= getattr(self, "nskip_min_pixels", 128)
+                and p.H_out * p.W_out >= getattr(self, "nskip_min_pixels", 128)
                 and self.impl in (_lib.CONV_AUTO, _lib.CONV_UMMA))
 
     def _run_block_spatial_skip(self, p: BlockPlan, x, out, B, ws, m3, m2, m1, keep):
@@ -565,31 +587,31 @@ class ResNetEngine:
         group), conv1 -> conv2 -> conv3 over the listed pixels only, output in place."""
         L = lib()
         st = stream_ptr()
-        Hi, Ho = p.H_in, p.H_out
+        Hi, Ho, Wi, Wo = p.H_in, p.H_out, p.W_in, p.W_out
         rows1, rows2, rc = ws["rows1"], ws["rows2"], ws["rcnt"]
-        check(L.laud_compact_rows(ptr(m1), B, 1, Hi * Hi, ptr(rows1), ptr(rc[0:1]), ptr(ws["cws"]), st), "laud_compact_rows")
-        check(L.laud_compact_rows(ptr(m2), B, 1, Ho * Ho, ptr(rows2), ptr(rc[1:2]), ptr(ws["cws"]), st), "laud_compact_rows")
+        check(L.laud_compact_rows(ptr(m1), B, 1, Hi * Wi, ptr(rows1), ptr(rc[0:1]), ptr(ws["cws"]), st), "laud_compact_rows")
+        check(L.laud_compact_rows(ptr(m2), B, 1, Ho * Wo, ptr(rows2), ptr(rc[1:2]), ptr(ws["cws"]), st), "laud_compact_rows")
         a1, a2 = ws["a1"], ws["a2"]
         tag = f"s{p.stage + 1}"
         # conv1 on the dilated footprint: everything conv2 will read (ExpandMask(stride, 1) covers its 3x3 windows)
-        run_conv(x, p.w1, a1, B, Hi, Hi, p.inplanes, Hi, Hi, p.width, 1, 1, 0, ldx=p.inplanes, ldy=p.width,
+        run_conv(x, p.w1, a1, B, Hi, Wi, p.inplanes, Hi, Wi, p.width, 1, 1, 0, ldx=p.inplanes, ldy=p.width,
                  scale=p.s1, shift=p.t1, relu=_lib.RELU_ALL, impl=self.impl, tag=tag + ".conv1", row_idx=rows1, row_cnt=rc[0:1])
-        run_conv(a1, p.w2, a2, B, Hi, Hi, p.width, Ho, Ho, p.width, 3, p.stride, 1, ldx=p.width, ldy=p.width,
+        run_conv(a1, p.w2, a2, B, Hi, Wi, p.width, Ho, Wo, p.width, 3, p.stride, 1, ldx=p.width, ldy=p.width,
                  scale=p.s2, shift=p.t2, relu=_lib.RELU_ALL, impl=self.impl, tag=tag + ".conv2", row_idx=rows2, row_cnt=rc[1:2])
         if p.wd is not None:
             # every pixel gets its downsampled identity straight into `out`; a gated-off pixel's output is relu(identity)
             # (ReLU applied here, where the gate is 0), an active one is finished by conv3 in place
-            run_conv(x, p.wd, out, B, Hi, Hi, p.inplanes, Ho, Ho, p.outplanes, 1, p.stride, 0, ldx=p.inplanes,
+            run_conv(x, p.wd, out, B, Hi, Wi, p.inplanes, Ho, Wo, p.outplanes, 1, p.stride, 0, ldx=p.inplanes,
                      ldy=p.outplanes, scale=p.sd, shift=p.td, relu=_lib.RELU_WHERE_GATE0, out_mask=m3, mask_groups=1,
                      impl=self.impl, tag=tag + ".down")
             dst = out
         else:
             dst = x                                # in place: gated-off pixels keep relu(x) == x
-        run_conv(a2, p.w3, dst, B, Ho, Ho, p.width, Ho, Ho, p.outplanes, 1, 1, 0, ldx=p.width, ldy=p.outplanes,
+        run_conv(a2, p.w3, dst, B, Ho, Wo, p.width, Ho, Wo, p.outplanes, 1, 1, 0, ldx=p.width, ldy=p.outplanes,
                  scale=p.s3, shift=p.t3, relu=_lib.RELU_ALL, residual=dst, ldr=p.outplanes, impl=self.impl,
                  tag=tag + ".conv3", row_idx=rows2, row_cnt=rc[1:2])
         if keep is not None:
-            keep.out = dst[:B * Ho * Ho * p.outplanes].view(B, Ho, Ho, p.outplanes).clone()
+            keep.out = dst[:B * Ho * Wo * p.outplanes].view(B, Ho, Wo, p.outplanes).clone()
         return dst
 
     def _gap_fusable(self, p: BlockPlan) -> bool:
@@ -606,7 +628,7 @@ class ResNetEngine:
             return False                 # A/B switches that take conv3 off the flat slab path of the TMA-staged kernel
         if p.use_s or (p.use_c and self.channel_exec not in ("dense", "nskip")) or self.impl not in (_lib.CONV_AUTO, _lib.CONV_UMMA):
             return False
-        return p.outplanes % 64 == 0 and p.H_out * p.H_out >= 43
+        return p.outplanes % 64 == 0 and p.H_out * p.W_out >= 43
 
     @staticmethod
     def _force_channel_gate(gate, mask: torch.Tensor, total: torch.Tensor) -> None:
@@ -642,8 +664,9 @@ class ResNetEngine:
         if x.dtype not in (torch.float16, torch.float32):
             raise LaudError(f"ResNet.forward: unsupported input dtype {x.dtype}")
         B, cin, H, W = x.shape
-        if cin != 3 or H != m.input_size or W != m.input_size:
-            raise LaudError(f"ResNet.forward: expected [B,3,{m.input_size},{m.input_size}], got {tuple(x.shape)}")
+        w_in = getattr(m, "input_w", None) or m.input_size       # (set by the detection adapter for non-square inputs)
+        if cin != 3 or H != m.input_size or W != w_in:
+            raise LaudError(f"ResNet.forward: expected [B,3,{m.input_size},{w_in}], got {tuple(x.shape)}")
         xh = x.contiguous() if x.dtype == torch.float16 else x.contiguous().to(torch.float16)
         ws = self._workspace(B, H, W, x.device, slot)
         L = lib()
@@ -677,7 +700,7 @@ class ResNetEngine:
                 cur = nxt
             if stage_outputs is not None and (p.index + 1 == len(self.plans) or self.plans[p.index + 1].stage != p.stage):
                 from .utils import to_nchw_f32
-                stage_outputs.append(to_nchw_f32(bufs[cur][:B * p.H_out * p.H_out * p.outplanes].view(B, p.H_out, p.H_out, p.outplanes)))
+                stage_outputs.append(to_nchw_f32(bufs[cur][:B * p.H_out * p.W_out * p.outplanes].view(B, p.H_out, p.W_out, p.outplanes)))
         if stage_outputs is not None:
             stats = torch.empty_like(ws["stats"])
             self._launch_stats(ws["counts"], ws["consts"], H, W, stats, head=False)
@@ -687,11 +710,11 @@ class ResNetEngine:
         ncls = m.fc.weight.shape[0]
         logits = logits_out if logits_out is not None else torch.empty((B, ncls), dtype=torch.float32, device=x.device)
         if gap_in:      # the last conv3 left the pool of its output
-            check(L.laud_head_forward_from_partials(ptr(ws["gap"]), B, last.H_out * last.H_out, feat,
-                                                    gap_tiles(last.H_out * last.H_out), ptr(self.fc_w), ptr(self.fc_b), ncls,
+            check(L.laud_head_forward_from_partials(ptr(ws["gap"]), B, last.H_out * last.W_out, feat,
+                                                    gap_tiles(last.H_out * last.W_out), ptr(self.fc_w), ptr(self.fc_b), ncls,
                                                     ptr(ws["partial"]), ptr(logits), st), "laud_head_forward_from_partials")
         else:
-            check(L.laud_head_forward(ptr(bufs[cur]), B, last.H_out * last.H_out, feat, ptr(self.fc_w), ptr(self.fc_b),
+            check(L.laud_head_forward(ptr(bufs[cur]), B, last.H_out * last.W_out, feat, ptr(self.fc_w), ptr(self.fc_b),
                                       ncls, ptr(ws["partial"]), ptr(logits), st), "laud_head_forward")
         if not want_stats:
             return logits, None
@@ -751,8 +774,8 @@ class ResNetEngine:
             S = min(p.mask_size, p.H_in)
             consts[i, 6] = B * p.G
             consts[i, 7] = B * p.g_spatial * S * S
-            consts[i, 8] = B * p.g_spatial * p.H_out * p.H_out
-            consts[i, 9] = B * p.g_spatial * p.H_in * p.H_in
+            consts[i, 8] = B * p.g_spatial * p.H_out * p.W_out
+            consts[i, 9] = B * p.g_spatial * p.H_in * p.W_in
         key = ("split_consts", B, dev)
         if key not in self._ws:
             self._ws[key] = consts.to(dev)

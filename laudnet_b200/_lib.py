@@ -87,6 +87,7 @@ SIGNATURES = {
     "laud_masker_spatial": ([_vp, _i, _i, _i, _i, _fp, _fp, _i, _i, _fp, _u8p, _i32p, _vp], _i),
     "laud_expand_mask": ([_u8p, _i, _i, _i, _i, _i, _i, _u8p, _i32p, _vp], _i),
     "laud_resize_mask_nearest": ([_u8p, _i, _i, _i, _i, _u8p, _vp], _i),
+    "laud_broadcast_gate": ([_u8p, _i, _i, _i, _u8p, _i32p, _vp], _i),
     "laud_spatial_masks": ([_u8p, _i, _i, _i, _i, _i, _u8p, _u8p, _u8p, _i32p, _i32p, _vp], _i),
     "laud_layer_gate_lists": ([_u8p, _i, _i, _i, _i32p, _i32p, _i32p, _vp], _i),
     "laud_compact_rows": ([_u8p, _i, _i, _i, _i32p, _i32p, _i32p, _vp], _i),

@@ -36,11 +36,11 @@ def sources():
 
 
 # sources the mask-conditioned convolution kernels are built from (the kernels profiles/conv_traffic.json describes)
-CONV_SOURCES = ("conv_tma.cu", "conv_umma.cu", "conv_ref.cu", "c_api.cu", "umma_ptx.cuh", "laud_common.cuh", "laud_b200.h")
+CONV_SOURCES = ("conv_tma.cu", "conv_umma.cu", "conv_ref.cu", "c_api.cu", "umma_ptx.cuh", "laud_common.cuh")
 
 
 def source_hash() -> str:
-    """sha256 over the sources of the convolution kernels and their C header (16 hex digits): ties a committed ncu capture
+    """sha256 over the sources of the convolution kernels (16 hex digits): ties a committed ncu capture
     (profiles/conv_traffic.json) to the build of those kernels it was taken from."""
     import hashlib
     h = hashlib.sha256()

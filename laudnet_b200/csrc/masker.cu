@@ -744,6 +744,34 @@ extern "C" int laud_resize_mask_nearest(const uint8_t* mask, int B, int g, int S
   return check_launch("resize_mask_kernel");
 }
 
+// A per-(sample, group) gate broadcast over hw positions (the S == 1 case of the nearest resize on a NON-square map:
+// lad_mmdet_resnet.py:274 resizes the mask to the actual feature size); total_out += ones written (nullable).
+namespace laud {
+namespace {
+__global__ void broadcast_gate_kernel(const uint8_t* __restrict__ gate, long long n, int hw, uint8_t* __restrict__ out,
+                                      int* __restrict__ total) {
+  int ones = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const uint8_t v = gate[i / hw] ? 1 : 0;
+    out[i] = v;
+    ones += v;
+  }
+  if (total) {
+    ones = (int)warp_sum((float)ones);                          // (exact: at most 32 x a few thousand per warp)
+    if ((threadIdx.x & 31) == 0 && ones) atomicAdd(total, ones);
+  }
+}
+}  // namespace
+}  // namespace laud
+
+extern "C" int laud_broadcast_gate(const uint8_t* gate, int B, int g, int hw, uint8_t* out, int32_t* total_out, void* stream) {
+  LAUD_REQUIRE(gate && out && B > 0 && g > 0 && hw > 0, "laud_broadcast_gate: bad arguments");
+  const long long n = (long long)B * g * hw;
+  const int grid = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+  broadcast_gate_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gate, n, hw, out, total_out);
+  return check_launch("broadcast_gate_kernel");
+}
+
 extern "C" int laud_expand_mask(const uint8_t* mask, int B, int g, int H, int W, int stride, int padding,
                                 uint8_t* out, int32_t* total_out, void* stream) {
   LAUD_REQUIRE(mask && out && B > 0 && g > 0 && H > 0 && W > 0, "laud_expand_mask: bad arguments");

@@ -99,25 +99,27 @@ class LAD_MMDet_ResNet(nn.Module):
                 m.eval()
         return self
 
-    def _set_input_side(self, side: int) -> None:
+    def _set_input_size(self, h: int, w: int) -> None:
+        """Feature-map geometry of an (h, w) input: stage s runs at (h, w) / (4 << s); the gates follow the actual feature
+        size (lad_mmdet_resnet.py:274).  Non-square inputs (detection batches are padded to a multiple of 32 per side)."""
         net = self._net
-        if net.input_size == side:
+        if net.input_size == h and (getattr(net, "input_w", None) or net.input_size) == w:
             return
-        net.input_size = side
+        net.input_size, net.input_w = h, w
         for s, layer in enumerate((self.layer1, self.layer2, self.layer3, self.layer4)):
             for blk in layer:
-                blk.output_size = side // (4 << s)
+                blk.output_size, blk.output_w = h // (4 << s), w // (4 << s)
                 blk.mask_size = 1 if blk.dyn_mode == "layer" else max(1, blk.output_size // blk.mask_spatial_granularity)
                 blk._solo_engine = None
         net._invalidate()
 
     def forward(self, x, iter_now=0, len_loader=100, gumbel_noise=None, keep=None, forced=None):
-        if x.dim() != 4 or x.shape[2] != x.shape[3] or x.shape[2] % 32:
-            raise LaudError(f"LAD_MMDet_ResNet: expected a square input whose side is a multiple of 32, got {tuple(x.shape)}")
+        if x.dim() != 4 or x.shape[2] % 32 or x.shape[3] % 32:
+            raise LaudError(f"LAD_MMDet_ResNet: expected [B, 3, H, W] with H and W multiples of 32, got {tuple(x.shape)}")
         gates_train = any(m.training for m in self.modules() if "Masker" in type(m).__name__)
         if gates_train and gumbel_noise is None:
             raise LaudError("LAD_MMDet_ResNet: gates in training mode draw Gumbel noise (utils.py:56-58); pass gumbel_noise= or .eval()")
-        self._set_input_side(int(x.shape[2]))
+        self._set_input_size(int(x.shape[2]), int(x.shape[3]))
         net = self._net
         eng = net._engine
         temperature = self.temperature_0 if self.temperature_0 is not None else 1.0
@@ -125,9 +127,9 @@ class LAD_MMDet_ResNet(nn.Module):
         _, stats = eng.forward(x, keep, forced=forced, gumbel_noise=gumbel_noise, temperature=temperature, stage_outputs=outs)
         r3, r2, r1, rc, perc, flops = eng.split_stats(stats)
         # dense FLOPs of stem + trunk (:688-693 and the per-block dense_flops of :243-300): static for a given input size
-        side = int(x.shape[2])
+        hh, ww = int(x.shape[2]), int(x.shape[3])
         c0 = self.conv1.weight.shape[0]
-        dense = 3 * c0 * (side // 2) ** 2 * 49 + c0 * (side // 4) ** 2 * 9
+        dense = 3 * c0 * (hh // 2) * (ww // 2) * 49 + c0 * (hh // 4) * (ww // 4) * 9
         consts = eng.stats_consts
         dense += int(consts[:, 0:6].sum())
         additional = {"spatial_sparsity_conv3": r3, "spatial_sparsity_conv2": r2, "spatial_sparsity_conv1": r1,

@@ -220,12 +220,14 @@ def apply_spatial_mask(x: Tensor, mask: Tensor) -> Tensor:
     return x * mask
 
 
-def nearest_resize(mask: Tensor, size: int) -> Tensor:
+def nearest_resize(mask: Tensor, size) -> Tensor:
     """F.interpolate(mode='nearest') as used at laud_resnet.py:106:
-    src index = floor(dst * in / out)."""
-    s_in = mask.shape[-1]
-    idx = torch.div(torch.arange(size) * s_in, size, rounding_mode="floor")
-    return mask[:, :, idx][:, :, :, idx]
+    src index = floor(dst * in / out).  `size` is an int (square maps) or (h, w): the detection backbone resizes to the
+    actual feature size (mmdet/models/backbones/lad_mmdet_resnet.py:274)."""
+    h, w = (size, size) if isinstance(size, int) else size
+    iy = torch.div(torch.arange(h) * mask.shape[-2], h, rounding_mode="floor")
+    ix = torch.div(torch.arange(w) * mask.shape[-1], w, rounding_mode="floor")
+    return mask[:, :, iy][:, :, :, ix]
 
 
 def _bn(z: Tensor, sd: Dict[str, Tensor], p: str) -> Tensor:
@@ -294,7 +296,8 @@ def bottleneck_forward(x: Tensor, sd: Dict[str, Tensor], g: BlockGeom,
         if forced_spatial_mask is not None:
             small = forced_spatial_mask.to(torch.float32)
             rho3 = small.mean()
-        sm3 = nearest_resize(small, g.output_size)                  # :106
+        sm3 = nearest_resize(small, (x.shape[2] // g.stride, x.shape[3] // g.stride))   # :106 (= g.output_size for square
+        #                                                                                  inputs; lad_mmdet_resnet.py:274)
         sm2 = expand_mask(sm3, 1, 0)                                # :107
         rho2 = sm2.float().mean()
         sm1 = expand_mask(sm2, g.stride, 1)                         # :109

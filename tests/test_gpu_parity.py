@@ -1202,6 +1202,19 @@ def test_mmdet_backbone_adapter_vs_oracle(cuda_lib, mode, side):
         outs2, add2, _ = model(x2.to(DEV))
     assert tuple(outs2[0].shape) == (2, 256, (side + 32) // 4, (side + 32) // 4) and torch.isfinite(outs2[3]).all()
     assert 0.0 < float(add2["flops_perc_list"].mean()) <= 1.0
+    # a NON-SQUARE detection-style input (padded to multiples of 32 per side) against the oracle, same gates installed
+    hh, ww = side, side + 64
+    x3 = synth.synth_images(2, ww, 43)[:, :, :hh, :].contiguous()
+    tr3 = []
+    with torch.no_grad():
+        ref3 = O.resnet_forward(sd, cfg, x3, tr3)
+        outs3, add3, _ = model(x3.to(DEV), forced=_forced_masks(tr3))
+        torch.cuda.synchronize()
+    for o, bi, c, sh, tol in zip(outs3, last, (256, 512, 1024, 2048), (4, 8, 16, 32), (2.5e-3, 5.5e-3, 9e-3, 1.6e-2)):
+        assert tuple(o.shape) == (2, c, hh // sh, ww // sh)
+        assert _rel_err(o, tr3[bi].out) <= tol
+    np.testing.assert_allclose(add3["flops_perc_list"].cpu().numpy(), ref3[5].numpy(), rtol=1e-6)
+    np.testing.assert_allclose(add3["flops"].item(), ref3[6].item() - head, rtol=1e-6)
 
 
 # =========================================================================== LAUD-RegNet-Y (laud_regnet.py)
