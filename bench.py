@@ -754,6 +754,16 @@ def run_adavit(args, conf):
            "attn_sublayer_rate": layer[:, model.keep_layers:, 0].float().mean().item(),
            "mlp_sublayer_rate": layer[:, model.keep_layers:, 1].float().mean().item()}
 
+    dynet = None
+    dpath = os.path.join(ROOT, "profiles", "dynet_adavit_b200.json")
+    if os.path.exists(dpath):       # the reference's analytic latency model on the same geometry and keep rates (build container)
+        dj = json.load(open(dpath))
+        dynet = {"predicted_images_per_s_per_gpu": dj["token_head_layer_skipping"]["images_per_s"],
+                 "predicted_static_dense_images_per_s_per_gpu": dj["static_dense"]["images_per_s"],
+                 "measured_images_per_s_per_gpu": value / world, "keep_rates_of_the_prediction": dj["keep_rates"],
+                 "hardware_parameters": dj["hardware_parameters"], "caveat": dj["caveat"], "source": "profiles/dynet_adavit_b200.json "
+                 "(scripts/make_dynet_adavit.py: DyNetSimulator/adavit/simulate_adavit.py imported unchanged from the reference)"}
+
     cpu = parity = None
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import adavit_oracle as A
@@ -819,7 +829,7 @@ def run_adavit(args, conf):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 2, "d2h_bytes_per_step": B * ncls * 4,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step, "clocks": clocks,
-            "parity": parity, "roofline": roof, "net": net, "cpu_baseline": cpu,
+            "parity": parity, "roofline": roof, "net": net, "dynet_simulator": dynet, "cpu_baseline": cpu,
         }) + "\n").encode())
     if world > 1:
         dist.barrier()
