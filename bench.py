@@ -816,6 +816,20 @@ def run_adavit(args, conf):
                   "max_rel_err_teacher_forced_all_samples": err_forced, "logits_tolerance": TOL,
                   "ok": bool(unexplained == 0 and err_forced <= TOL and (err != err or err <= TOL))}
 
+    gpu_base = None
+    if rank == 0 and world == 1 and not args.no_gpu_baseline:
+        try:
+            from laudnet_b200.torch_baseline import TorchMaskedDenseAdaViT
+            tb = TorchMaskedDenseAdaViT(model, dev)
+            rate, ms_b, lg = tb.measure(x_dev, steps=10, warmup=3)
+            gpu_base = {"value": rate, "unit": UNIT, "ms_per_step": ms_b, "kind": "stock PyTorch masked-dense AdaViT (every token / head / "
+                        "sub-layer computed, decisions multiplied in): fp16 weights + activations, F.scaled_dot_product_attention with "
+                        "the key mask, CUDA graph, batch %d" % B, "torch": torch.__version__, "finite": bool(torch.isfinite(lg).all()),
+                        "note": "a speed baseline, not a parity instrument (fp16 LayerNorm / policies change decisions)"}
+            del tb
+        except Exception as e:
+            gpu_base = {"unavailable": f"{type(e).__name__}: {e}"}
+
     if rank == 0:
         sys.stdout.flush()
         os.write(out_fd, (json.dumps({
@@ -829,7 +843,7 @@ def run_adavit(args, conf):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 2, "d2h_bytes_per_step": B * ncls * 4,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step, "clocks": clocks,
-            "parity": parity, "roofline": roof, "net": net, "dynet_simulator": dynet, "cpu_baseline": cpu,
+            "parity": parity, "roofline": roof, "net": net, "gpu_baseline": gpu_base, "dynet_simulator": dynet, "cpu_baseline": cpu,
         }) + "\n").encode())
     if world > 1:
         dist.barrier()

@@ -121,3 +121,72 @@ class TorchMaskedDenseResNet:
             return xs.shape[0] / ms * 1e3, ms, logits.float()
         finally:
             torch.backends.cudnn.benchmark = prev
+
+
+class TorchMaskedDenseAdaViT:
+    """Stock-PyTorch GPU baseline of BASELINE configs[3]: the AdaViT block executed MASKED-DENSE (everything computed, the
+    0/1 decisions multiplied in - how a PyTorch implementation of AdaViT runs) with fp16 weights and activations,
+    `F.scaled_dot_product_attention` with the key mask, captured in a CUDA graph.  A measurement aid (bench.py's
+    `gpu_baseline` of --config 3); not an oracle (fp16 LayerNorm / policies change decisions)."""
+
+    def __init__(self, model, device, dtype=torch.float16):
+        self.dev, self.dt = device, dtype
+        self.sd = {k: v.detach().to(device=device, dtype=dtype).contiguous() for k, v in model.state_dict().items()}
+        self.D, self.H, self.depth, self.P = model.embed_dim, model.num_heads, model.depth, model.patch_size
+        self.policy = [blk.has_policy for blk in model.blocks]
+        self.flags = (model.ada_token, model.ada_head, model.ada_layer)
+
+    def forward(self, img):
+        s, D, H = self.sd, self.D, self.H
+        d = D // H
+        ln = lambda t, p: F.layer_norm(t, (D,), s[p + "weight"], s[p + "bias"], 1e-6)
+        t = F.conv2d(img, s["patch_embed.proj.weight"], s["patch_embed.proj.bias"], stride=self.P).flatten(2).transpose(1, 2)
+        x = torch.cat([s["cls_token"].expand(t.shape[0], -1, -1), t], 1) + s["pos_embed"]
+        B, L, _ = x.shape
+        for i in range(self.depth):
+            p = f"blocks.{i}."
+            tok = head = layer = None
+            y = ln(x, p + "norm1.")
+            if self.policy[i]:
+                pt = ln(x[:, 0], p + "norm_policy.")
+                if self.flags[2]:
+                    layer = (F.linear(pt, s[p + "layer_select.weight"], s[p + "layer_select.bias"]) >= 0).to(x.dtype)
+                if self.flags[1]:
+                    head = (F.linear(pt, s[p + "head_select.weight"], s[p + "head_select.bias"]) >= 0).to(x.dtype)
+                if self.flags[0]:
+                    tl = F.linear(y[:, 1:], s[p + "token_select.weight"], s[p + "token_select.bias"]).squeeze(-1)
+                    tok = torch.cat([torch.ones(B, 1, dtype=torch.bool, device=x.device), tl >= 0], 1)
+            qkv = F.linear(y, s[p + "attn.qkv.weight"], s[p + "attn.qkv.bias"]).view(B, L, 3, H, d).permute(2, 0, 3, 1, 4)
+            mask = tok[:, None, None, :] if tok is not None else None
+            o = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2], attn_mask=mask)
+            if head is not None:
+                o = o * head[:, :, None, None]
+            o = F.linear(o.transpose(1, 2).reshape(B, L, D), s[p + "attn.proj.weight"], s[p + "attn.proj.bias"])
+            g = tok.to(x.dtype)[:, :, None] if tok is not None else 1.0
+            x = x + o * g * (layer[:, 0, None, None] if layer is not None else 1.0)
+            m = F.linear(F.gelu(F.linear(ln(x, p + "norm2."), s[p + "mlp.fc1.weight"], s[p + "mlp.fc1.bias"])),
+                         s[p + "mlp.fc2.weight"], s[p + "mlp.fc2.bias"])
+            x = x + m * g * (layer[:, 1, None, None] if layer is not None else 1.0)
+        return F.linear(ln(x[:, 0], "norm."), s["head.weight"], s["head.bias"])
+
+    def measure(self, x_nchw_f16: torch.Tensor, steps: int = 10, warmup: int = 3):
+        """-> (img/s, ms per step, logits) of the CUDA-graphed forward."""
+        with torch.no_grad():
+            xs = x_nchw_f16.to(self.dt).clone()
+            for _ in range(2):
+                self.forward(xs)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self.forward(xs)
+            for _ in range(warmup):
+                g.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+        return xs.shape[0] / (ms * 1e-3), ms, out.float()
