@@ -912,14 +912,16 @@ extern "C" int laud_tok_gemm(const laud_tok_gemm_desc* d, void* stream) {
     const long long wbytes = (long long)kchunks * bn * 128;
     const long long scr_bytes = d->resid ? TG_SCR_BYTES : 0;
     const long long room = (long long)TG_SMEM_MAX - 1024 - wbytes - scr_bytes;
-    if (!getenv("LAUD_TOKGEMM_STREAM") && room >= 3 * TG_A_BYTES && n_tiles <= di.sms && m_tiles_max >= 2 * (di.sms / n_tiles)) {
+    // A/B switches (diagnosis only): LAUD_TOKGEMM_STREAM = never keep the weight tile resident, LAUD_TOKGEMM_KCS1 = one chunk per stage
+    static const bool force_stream = getenv("LAUD_TOKGEMM_STREAM") != nullptr, kcs1 = getenv("LAUD_TOKGEMM_KCS1") != nullptr;
+    if (!force_stream && room >= 3 * TG_A_BYTES && n_tiles <= di.sms && m_tiles_max >= 2 * (di.sms / n_tiles)) {
       bres = 1;
-      kcs = (kchunks % 2 == 0 && room >= 3 * 2 * TG_A_BYTES && !getenv("LAUD_TOKGEMM_KCS1")) ? 2 : 1;   // >= 3 stages in flight
+      kcs = (kchunks % 2 == 0 && room >= 3 * 2 * TG_A_BYTES && !kcs1) ? 2 : 1;   // >= 3 stages in flight
       stages = (int)(room / (kcs * TG_A_BYTES));
     } else {
       // streaming: two chunks per stage when at least two such stages fit
       const long long st2 = 2LL * (TG_A_BYTES + bn * 128);
-      kcs = (kchunks % 2 == 0 && 2 * st2 + 1024 + scr_bytes <= TG_SMEM_MAX && !getenv("LAUD_TOKGEMM_KCS1")) ? 2 : 1;
+      kcs = (kchunks % 2 == 0 && 2 * st2 + 1024 + scr_bytes <= TG_SMEM_MAX && !kcs1) ? 2 : 1;
       stages = (int)((TG_SMEM_MAX - 1024 - scr_bytes) / (kcs * (TG_A_BYTES + bn * 128)));
     }
     if (stages > TG_MAX_STAGES) stages = TG_MAX_STAGES;
@@ -940,7 +942,8 @@ extern "C" int laud_tok_gemm(const laud_tok_gemm_desc* d, void* stream) {
   a.out = (__half*)d->out; a.ldo = d->ldo; a.resid = d->resid; a.ldres = d->ldres; a.row_idx = d->row_idx;
   a.col_gate = d->col_gate; a.gate_ld = d->gate_ld; a.row_sample = d->row_sample;
   a.bres = bres; a.stages = stages; a.kcs = kcs;
-  a.dbg = getenv("LAUD_TG_DBG") ? atoi(getenv("LAUD_TG_DBG")) : 0;
+  static const int tg_dbg = getenv("LAUD_TG_DBG") ? atoi(getenv("LAUD_TG_DBG")) : 0;
+  a.dbg = tg_dbg;
   const int items = m_tiles_max * n_tiles;
   const int grid = bres ? (di.sms / n_tiles) * n_tiles : (items < di.sms ? items : di.sms);
   tok_gemm_kernel<<<grid, TG_THREADS, smem, s>>>(a, ma, mb);
