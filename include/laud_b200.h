@@ -311,9 +311,10 @@ int laud_nhwc_f16_to_nchw_f32(const void* src, int lds, int B, int C, int H, int
  *   laud_regnet_stem_forward     SimpleStemIN conv3x3/2 + BN + ReLU (:59-71): x fp16 NCHW [B,3,H,W] -> y fp16 NHWC
  *                                [B,H/2,W/2,C0]; w fp16 [C0,3,3,3]
  *   laud_grouped_conv3x3_forward the transform's conv b (:118-120,188): grouped 3x3 (pad 1, stride 1|2) + BN + ReLU,
- *                                w fp16 [C][9][group_width] (out channel, tap, in channel of its group); optional channel
- *                                gate ch_mask u8 [B, C/mask_gran] applied to the input (= conv a's gated output, :183)
- *                                and to the output (:189)
+ *                                w fp16 [C][9][group_width] (out channel, tap, in channel of its group); group widths 8 / 16 / 24
+ *                                on dedicated kernels with an optional channel gate ch_mask u8 [B, C/mask_gran] applied to the
+ *                                input (= conv a's gated output, :183) and to the output (:189); any wider multiple of 8
+ *                                (RegNetY-8GF / 16GF / 32GF) runs group by group on the tcgen05 convolution kernel (no gate)
  *   laud_se_gate                 SqueezeExcitation gate (:128-132,194) from the pooled features fp32 [B,C]:
  *                                gate = sigmoid(W2 relu(W1 p + b1) + b2)  (p and gate multiplied by ch_mask if given);
  *                                w1 fp32 [S][C], w2 fp32 passed TRANSPOSED as [S][C]

@@ -95,9 +95,9 @@ class RegNetEngine:
                     for cdim in (p.w_in, p.w_b, p.w_out):
                         if cdim % 8:
                             raise LaudError(f"channel counts must be multiples of 8 for the fp16 kernels (got {cdim})")
-                    if p.gw not in (8, 16, 24):
-                        raise LaudError(f"grouped 3x3 convolution: group width {p.gw} is not supported by the CUDA path "
-                                        "(8, 16 and 24 are: RegNetY-400MF / 800MF / 1.6GF / 3.2GF)")
+                    if p.gw % 8 or (p.gw not in (8, 16, 24) and f.dyn_mode in ("channel", "both")):
+                        raise LaudError(f"grouped 3x3 convolution: group width {p.gw} with dyn_mode '{f.dyn_mode}' is not supported by "
+                                        "the CUDA path (multiples of 8; the channel gate of conv b is built for widths 8 / 16 / 24)")
                     p.wa = pack_conv_weight(f.a[0].weight)
                     p.sa, p.ta = fold_bn(f.a[1])
                     wb = f.b[0].weight.detach()                      # [w_b, gw, 3, 3] -> [w_b][tap][gw]

@@ -1755,7 +1755,9 @@ static int conv_forward_tma_x(const ConvArgs& a_in, cudaStream_t s, bool allow_r
     ok = ok && make_map(&map_b, a.w, 2, dims, str, box);
   }
   if (pl.omode == OUT_SLAB) {
-    const long long dims[3] = {a.ldy, HWo, a.B};
+    // compact outputs (n_idx) may be overwritten up to their pitch (scratch, see laud_conv_desc); a dense output is clipped
+    // at C_out, so a convolution can write a channel SLICE of a wider tensor (grouped convolutions run group by group)
+    const long long dims[3] = {a.n_idx ? a.ldy : a.C_out, HWo, a.B};
     const long long str[2] = {a.ldy, (long long)HWo * a.ldy};
     const int box[3] = {64, rows_box, 1};
     ok = ok && make_map(&map_y, a.y, 3, dims, str, box);

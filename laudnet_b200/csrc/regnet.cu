@@ -2,6 +2,7 @@
 // stem, the grouped 3x3 convolution of the bottleneck transform (group width 8/16: far too narrow for a tensor-core
 // tile, so it is a CUDA-core kernel that keeps one group's weights in shared memory), and Squeeze-Excitation.
 // The 1x1 convolutions (a, c, proj), the maskers and the head run on the kernels shared with LAUD-ResNet.
+#include <string.h>
 #include "laud_common.cuh"
 
 namespace laud {
@@ -313,9 +314,35 @@ extern "C" int laud_grouped_conv3x3_forward(const void* x, int B, int H_in, int 
   LAUD_REQUIRE(x && w && scale && shift && y, "laud_grouped_conv3x3_forward: null pointer");
   LAUD_REQUIRE(B > 0 && (stride == 1 || stride == 2) && H_in % stride == 0 && W_in % stride == 0,
                "laud_grouped_conv3x3_forward: stride must be 1 or 2 and divide H,W");
-  LAUD_REQUIRE((group_width == 8 || group_width == 16 || group_width == 24) && C % group_width == 0,
-               "laud_grouped_conv3x3_forward: group width must be 8, 16 or 24 and divide C (got %d, C=%d)", group_width, C);
+  LAUD_REQUIRE(group_width >= 8 && group_width % 8 == 0 && C % group_width == 0,
+               "laud_grouped_conv3x3_forward: group width must be a multiple of 8 and divide C (got %d, C=%d)", group_width, C);
   LAUD_REQUIRE(!ch_mask || (mask_gran >= 1 && C % mask_gran == 0), "laud_grouped_conv3x3_forward: bad mask granularity");
+  if (group_width != 8 && group_width != 16 && group_width != 24) {
+    // Wide groups (RegNetY-8GF / 16GF / 32GF: 56, 112, 232 channels per group) fill tensor-core tiles: every group is an
+    // ordinary 3x3 convolution over a channel slice of the NHWC tensors (pitch C) with its own [gw, 9, gw] rows of w,
+    // run on the mask-conditioned convolution kernel.
+    if (ch_mask) {
+      set_error("laud_grouped_conv3x3_forward: the channel gate is built for group widths 8 / 16 / 24 only");
+      return LAUD_E_UNSUPPORTED;
+    }
+    const int groups_w = C / group_width;
+    for (int g = 0; g < groups_w; ++g) {
+      laud_conv_desc d;
+      memset(&d, 0, sizeof(d));
+      d.x = (const __half*)x + (size_t)g * group_width;  d.ldx = C;
+      d.w = (const __half*)w + (size_t)g * group_width * 9 * group_width;
+      d.y = (__half*)y + (size_t)g * group_width;        d.ldy = C;
+      d.B = B; d.H_in = H_in; d.W_in = W_in; d.C_in = group_width;
+      d.H_out = H_in / stride; d.W_out = W_in / stride; d.C_out = group_width;
+      d.ksize = 3; d.stride = stride; d.pad = 1;
+      d.scale = scale + (size_t)g * group_width; d.shift = shift + (size_t)g * group_width;
+      d.relu_mode = LAUD_RELU_ALL;
+      d.mask_groups = 1;
+      const int rc = laud_conv_forward(&d, LAUD_CONV_AUTO, stream);
+      if (rc != LAUD_OK) return rc;
+    }
+    return LAUD_OK;
+  }
   const long long total = (long long)B * (H_in / stride) * (W_in / stride) * (group_width / 8);
   const int groups = C / group_width;
   long long tiles = (total + 127) / 128;

@@ -1248,7 +1248,10 @@ def test_regnet_stem_vs_oracle(cuda_lib, B, size, C0):
 
 
 @pytest.mark.parametrize("B,H,C,gw,stride,gran", [(2, 8, 32, 8, 1, 0), (3, 14, 64, 16, 2, 0), (2, 6, 48, 16, 1, 4),
-                                                  (1, 10, 40, 8, 2, 8), (2, 8, 48, 24, 1, 0), (1, 12, 72, 24, 2, 8)])
+                                                  (1, 10, 40, 8, 2, 8), (2, 8, 48, 24, 1, 0), (1, 12, 72, 24, 2, 8),
+                                                  # wide groups (RegNetY-8GF / 16GF / 32GF): group by group on the tcgen05 conv kernel
+                                                  (2, 14, 112, 56, 1, 0), (2, 14, 224, 56, 2, 0), (1, 8, 224, 112, 1, 0),
+                                                  (1, 14, 464, 232, 2, 0)])
 def test_grouped_conv3x3_vs_torch(cuda_lib, B, H, C, gw, stride, gran):
     """conv b of the RegNet transform (laud_regnet.py:118-120,188-189): grouped 3x3 + BN + ReLU, optional channel gate
     applied to its input and output, against F.conv2d(groups=...) on fp16-representable data."""
@@ -1326,6 +1329,53 @@ def test_regnet_blocks_teacher_forced(cuda_lib, name):
             err = _rel_err(out.float().permute(0, 3, 1, 2), out_o[0])
             assert err <= ACT_TOL, f"{name} {g.prefix}: block output error {err:.2e}"
             feat = out_o[0]
+
+
+@pytest.mark.parametrize("gw,depth", [(56, 5), (112, 5)])      # four stages (the reference network has exactly four)
+def test_regnet_wide_groups_vs_oracle(cuda_lib, gw, depth):
+    """Group widths of RegNetY-8GF (56) / 16GF (112): conv b runs group by group on the tcgen05 convolution kernel.  A small
+    trunk of that group width (BlockParams.from_init_params), spatial mode, against the oracle: every block teacher-forced
+    within ACT_TOL, then the whole network with the oracle's masks installed."""
+    from laudnet_b200.laud_regnet import BlockParams, LAD_RegNet
+    bp = BlockParams.from_init_params(depth=depth, w_0=gw, w_a=1.5 * gw, w_m=2.0, group_width=gw, se_ratio=0.25)
+    n = len(bp.widths)
+    assert n == 4
+    cfg = O.RegNetCfg(widths=tuple(bp.widths), depths=tuple(bp.depths), group_widths=tuple(bp.group_widths), strides=(2,) * n,
+                      se_ratio=0.25, stem_width=16, input_size=64, num_classes=24, dyn_mode=("spatial",) * n,
+                      channel_dyn_granularity=(1,) * n, spatial_mask_channel_group=(1,) * n,
+                      mask_spatial_granularity=(2, 2, 1, 1)[:n], channel_masker=("MLP",) * n, channel_masker_layers=(2,) * n,
+                      reduction_ratio=(16,) * n)
+    assert all(g == gw for g in bp.group_widths)
+    model = LAD_RegNet(bp, **cfg.kwargs())
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    x = synth.synth_images(3, 64, 77)
+    geoms = O.regnet_geometry(cfg)
+    sd = synth.calibrate_regnet(synth.synth_state_dict(shapes, 77), geoms, x, 77, spatial_rate=0.5)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(DEV).eval()
+    eng = model._engine
+    eng.prepare()
+    B = x.shape[0]
+    ws = eng._workspace(B, 64, 64, torch.device(DEV))
+    traces = []
+    with torch.no_grad():
+        ref = O.regnet_forward(sd, cfg, x, traces)
+        feat, _ = O.regnet_stem_forward(x, sd)
+        for g, p in zip(geoms, eng.plans):
+            xin = feat.half().float()
+            tr = O.BlockTrace()
+            out_o = O.regnet_block_forward(xin, sd, g, tr)
+            xd = L.utils.to_nhwc_f16(xin.to(DEV))
+            out = torch.empty((B, p.H_out, p.H_out, p.w_out), dtype=torch.float16, device=DEV)
+            idb = torch.empty_like(out)
+            ws["counts"].zero_()
+            eng.run_block(p, xd.view(-1), out.view(-1), idb.view(-1), B, ws, None, None, tr.spatial_mask_small.to(DEV))
+            torch.cuda.synchronize()
+            err = _rel_err(out.float().permute(0, 3, 1, 2), out_o[0])
+            assert err <= ACT_TOL, f"group width {gw} {g.prefix}: block output error {err:.2e}"
+            feat = out_o[0]
+        logits = model(x.to(DEV), 1.0, forced=_forced_masks(traces))[0]
+    assert _rel_err(logits, ref[0]) <= LOGIT_TOL
 
 
 @pytest.mark.parametrize("name", list(REGNET_CASES))
