@@ -40,6 +40,8 @@ enum { LAUD_ACT_NONE = 0, LAUD_ACT_GELU = 1 /* exact: 0.5 x (1 + erf(x / sqrt 2)
  * (columns [t*bn, (t+1)*bn)) of an m-tile is computed only if col_gate[s * gate_ld + t] != 0 for at least one sample s
  * among the samples of the tile's rows (row_sample[i] = sample of compact row i, ascending); skipped tiles are not written.
  * bn: n-tile width, one of 64 / 128 / 192 / 256 (0 = chosen by the library).
+ * For K <= 384 the CTA keeps the whole [bn, K] weight tile of ONE n-tile resident in shared memory and streams activation
+ * tiles only; longer reductions stream both operands.
  * ------------------------------------------------------------------------- */
 typedef struct laud_tok_gemm_desc {
   const void* a; int32_t lda;
@@ -54,6 +56,9 @@ typedef struct laud_tok_gemm_desc {
   const uint8_t* col_gate; int32_t gate_ld;
   const int32_t* row_sample;
   int32_t bn;
+  int32_t cta_pair;   /* 1: run in clusters of two CTAs (tcgen05.mma.cta_group::2: M = 256 across the pair, each CTA stages its own
+                         128 rows and HALF of every weight tile; commits multicast to both CTAs) where the shape allows (no col_gate,
+                         bn % 32 == 0).  Same results; measured slower on configs[3], hence opt-in.  0: single CTAs. */
 } laud_tok_gemm_desc;
 
 int laud_tok_gemm(const laud_tok_gemm_desc* desc /* host */, void* stream);

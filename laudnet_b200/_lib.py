@@ -65,6 +65,7 @@ class TokGemmDesc(C.Structure):
         ("col_gate", _vp), ("gate_ld", C.c_int32),
         ("row_sample", _vp),
         ("bn", C.c_int32),
+        ("cta_pair", C.c_int32),
     ]
 
 

@@ -190,14 +190,14 @@ class AdaViT(nn.Module):
     # ------------------------------------------------------------------ launches
     @staticmethod
     def _gemm(a, w, bias, rows_max, K, N, st, row_cnt=None, act=_lib.ACT_NONE, out=None, resid=None, ldres=0, row_idx=None,
-              col_gate=None, gate_ld=0, row_sample=None, bn=0):
+              col_gate=None, gate_ld=0, row_sample=None, bn=0, cta_pair=0):
         d = _lib.TokGemmDesc()
         d.a, d.lda, d.w, d.bias = ptr(a), K, ptr(w), ptr(bias)
         d.rows_max, d.K, d.N = rows_max, K, N
         d.row_cnt, d.act = ptr(row_cnt), act
         d.out, d.ldo = ptr(out), (N if out is not None else 0)
         d.resid, d.ldres, d.row_idx = ptr(resid), ldres, ptr(row_idx)
-        d.col_gate, d.gate_ld, d.row_sample, d.bn = ptr(col_gate), gate_ld, ptr(row_sample), bn
+        d.col_gate, d.gate_ld, d.row_sample, d.bn, d.cta_pair = ptr(col_gate), gate_ld, ptr(row_sample), bn, cta_pair
         check(_lib.lib().laud_tok_gemm(C.byref(d), st), "laud_tok_gemm")
 
     def _run(self, x_img: torch.Tensor, keep: Optional[List[BlockKeep]] = None, forced: Optional[Sequence] = None,

@@ -73,6 +73,9 @@ struct TgArgs {
                   // streams only activation tiles (L2 -> SM operand feed, ~20-35 B/clk/SM measured, is what bounds this GEMM:
                   // 96 KB instead of 288 KB per 128 x 192 x 384 tile)
   int stages;
+  int pair;       // CTA-PAIR mode (streaming GEMMs): clusters of two CTAs run tcgen05.mma.cta_group::2 - M = 256 across the pair,
+                  // each CTA stages its own 128 activation rows and HALF of every weight tile (bn/2 rows), so the weight bytes per
+                  // SM and per MMA halve; the leader (cluster rank 0) issues, commits are multicast to both CTAs' barriers
   int dbg;        // LAUD_KPROF builds only (timing experiments, WRONG results): 1 no global writes, 2 no write-out at all, 4 no tcgen05.ld
   int kcs;        // 64-channel chunks per pipeline stage (one TMA instruction per operand and stage: a producer iteration
                   // costs ~590 cycles whatever it moves up to 32 KB - scripts/l2_feed.cu - so stages carry 32 KB or more)
@@ -92,6 +95,61 @@ __device__ __forceinline__ bool tg_tile_active(const TgArgs& a, int m, int nt, i
   return false;
 }
 
+// ---- CTA-pair (cta_group::2) forms
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local` (a shared::cta address) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t bar_cluster_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_cluster_addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_addr(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+// TMA tile load whose completion is signalled on a barrier that may live in the PEER CTA (the leader's)
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const void* map, uint32_t bar_cluster_addr, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.cta_group::2 [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// four K=16 steps, M = 256 across the CTA pair (warp-uniform, one elected lane issues)
+__device__ __forceinline__ void umma_f16_pair_x4(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate_first) {
+  asm volatile(
+      "{\n\t.reg .pred p, pe, pt;\n\t.reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 pt, 0, 0;\n\t"
+      "add.u64 a1, %1, 2;\n\tadd.u64 a2, %1, 4;\n\tadd.u64 a3, %1, 6;\n\t"
+      "add.u64 b1, %2, 2;\n\tadd.u64 b2, %2, 4;\n\tadd.u64 b3, %2, 6;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], a1, b1, %3, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], a2, b2, %3, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], a3, b3, %3, pt;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate_first)
+      : "memory");
+}
+// arrive on the barrier at this shared-memory offset in BOTH CTAs once every MMA issued so far has completed
+__device__ __forceinline__ void umma_commit_pair_elect(unsigned long long* b) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t.reg .b16 m;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "mov.b16 m, 3;\n\t"
+      "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}"
+      ::"r"(smem_u32(b))
+      : "memory");
+}
+
 // GELU = 0.5 x (1 + erf(x / sqrt 2)) with erf(z) = 1 - 2^(-z g(z)), z = min(|x| / sqrt 2, 4.2), g a cubic (weighted
 // least-squares fit of -log2(erfc(z)) / z on [0, 4.2]; |erf error| <= 1.5e-5, relative GELU error <= 1.4e-5 in fp32
 // arithmetic - 35 times below the fp16 rounding of the result): 11 instructions with ONE MUFU (ex2) per element.  erff()
@@ -108,6 +166,9 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(fabsf(hx), erf_abs, hx);
 }
 
+// PAIR: the CTA-pair instantiation (tcgen05 ... cta_group::2; must be launched in clusters of two CTAs - a kernel that contains
+// these instructions cannot be launched without a cluster, so the single-CTA form is its own instantiation)
+template <bool PAIR>
 __global__ void __launch_bounds__(TG_THREADS, 1)
 tok_gemm_kernel(const TgArgs a, const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b) {
   extern __shared__ unsigned char smem_raw[];
@@ -116,24 +177,33 @@ tok_gemm_kernel(const TgArgs a, const __grid_constant__ CUtensorMap map_a, const
   __shared__ uint8_t s_act[TG_ACT_MAX];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int b_bytes = a.bn * 128;                                    // one 64-channel chunk of the weight tile
+  const uint32_t rank = PAIR ? cluster_rank() : 0u;                 // CTA-pair mode: 0 = leader (issues the MMAs)
+  const int b_bytes = (PAIR ? a.bn / 2 : a.bn) * 128;               // one 64-channel chunk of the weight tile (pair: this CTA's half)
   const int stage_bytes = a.kcs * (a.bres ? TG_A_BYTES : TG_A_BYTES + b_bytes);
   const int a_stage_bytes = a.kcs * TG_A_BYTES;                       // [kcs][128 rows][64 ch], then (streaming) [kcs][bn rows][64 ch]
   const uint32_t bres_base = smem_base + a.stages * stage_bytes;      // resident weight tile: K/64 chunks of b_bytes
   const uint32_t scr_base = bres_base + (a.bres ? (a.K / TG_BK) * b_bytes : 0);   // residual mode: transposing scratch
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < TG_MAX_STAGES; ++i) { mbar_init(&bars.full[i], 1); mbar_init(&bars.empty[i], 1); }
-    mbar_init(&bars.bfull, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars.tfull[i], 1); mbar_init(&bars.tempty[i], TG_EPI_WARPS * 32); }
+    // pair mode: the leader's full[] takes one expect_tx arrival per CTA, its tempty[] one arrival per epilogue warp of
+    // BOTH CTAs; empty[] / tfull[] of both CTAs are signalled by the leader's multicast commits
+    for (int i = 0; i < TG_MAX_STAGES; ++i) { mbar_init(&bars.full[i], PAIR ? 2 : 1); mbar_init(&bars.empty[i], 1); }
+    mbar_init(&bars.bfull, PAIR ? 2 : 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars.tfull[i], 1); mbar_init(&bars.tempty[i], TG_EPI_WARPS * (PAIR ? 2 : 1)); }   // (one arrival per epilogue warp)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars.tmem_base)), "r"(512u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars.tmem_base)), "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars.tmem_base)), "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   const int cnt = a.row_cnt ? min(__ldg(a.row_cnt), a.rows_max) : a.rows_max;
   const int m_tiles = (cnt + TG_BM - 1) / TG_BM, n_tiles = (a.N + a.bn - 1) / a.bn;
@@ -144,6 +214,7 @@ tok_gemm_kernel(const TgArgs a, const __grid_constant__ CUtensorMap map_a, const
   if (bias_tab)
     for (int i = threadIdx.x; i < a.N; i += TG_THREADS) s_bias[i] = __ldg(a.bias + i);
   {
+    // (pair mode never carries col_gate: this table is built in single-CTA mode only)
     const int nt_ = a.bres ? (int)(blockIdx.x % n_tiles) : 0, i0_ = a.bres ? (int)(blockIdx.x / n_tiles) : (int)blockIdx.x;
     const int st_ = a.bres ? (int)(gridDim.x / n_tiles) : (int)gridDim.x, items_ = a.bres ? m_tiles : m_tiles * n_tiles;
     const int n_local = i0_ < items_ ? (items_ - i0_ + st_ - 1) / st_ : 0;
@@ -156,17 +227,25 @@ tok_gemm_kernel(const TgArgs a, const __grid_constant__ CUtensorMap map_a, const
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();                                      // the peer's barriers exist before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = bars.tmem_base;
   const int kchunks = a.K / TG_BK;
   // work of this CTA: items it0, it0 + step, ... < items; item -> (m-tile, n-tile)
   //   streaming mode: item = m * n_tiles + nt over the whole grid;  weight-resident mode: the CTA's n-tile is fixed
   //   (blockIdx.x % n_tiles) and it walks the m-tiles g, g + G, ... of its group of G = gridDim.x / n_tiles CTAs
-  const int my_nt = a.bres ? (int)(blockIdx.x % n_tiles) : 0;
-  const int it0 = a.bres ? (int)(blockIdx.x / n_tiles) : (int)blockIdx.x;
-  const int step = a.bres ? (int)(gridDim.x / n_tiles) : (int)gridDim.x;
-  const int items = a.bres ? m_tiles : m_tiles * n_tiles;
-#define TG_DECODE(it, m, nt) const int m = a.bres ? (it) : (it) / n_tiles, nt = a.bres ? my_nt : (it) - m * n_tiles
+  //   pair mode: item = m-PAIR * n_tiles + nt over the clusters; CTA `rank` of the pair owns m-tile 2 * pair + rank
+  //   pair + weight-resident: the same with clusters as units - the pair's n-tile is fixed, each CTA keeps HALF of its weight
+  //   tile resident and the pair walks m-PAIRS
+  const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, units = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int m_units = PAIR ? (m_tiles + 1) >> 1 : m_tiles;             // m-tiles (single) or m-pairs
+  const int my_nt = a.bres ? unit % n_tiles : 0;
+  const int it0 = a.bres ? unit / n_tiles : unit;
+  const int step = a.bres ? units / n_tiles : units;
+  const int items = a.bres ? m_units : m_units * n_tiles;
+#define TG_DECODE(it, m, nt)                                                                       \
+  const int mu_ = a.bres ? (it) : (it) / n_tiles, m = PAIR ? 2 * mu_ + (int)rank : mu_,            \
+            nt = a.bres ? my_nt : (it) - mu_ * n_tiles
   const bool act_tab = a.col_gate && (it0 < items ? (items - it0 + step - 1) / step : 0) <= TG_ACT_MAX;
 #define TG_ACTIVE(it, m, nt) (!a.col_gate || (act_tab ? s_act[((it) - it0) / step] != 0 : tg_tile_active(a, m, nt, cnt)))
 
@@ -176,9 +255,16 @@ tok_gemm_kernel(const TgArgs a, const __grid_constant__ CUtensorMap map_a, const
     if (lane == 0) {
       const int me = warp == 0 ? 0 : 1;
       if (me == 0 && a.bres && it0 < items) {
-        mbar_arrive_expect_tx(&bars.bfull, (uint32_t)(kchunks * b_bytes));
-        for (int kc = 0; kc < kchunks; kc += a.kcs)
-          tma_load_3d(bres_base + kc * b_bytes, &map_b, &bars.bfull, 0, my_nt * a.bn, kc);
+        if (PAIR) {                                        // this CTA's half of the n-tile's weight rows; the leader waits for both
+          const uint32_t lbar = mapa_u32(smem_u32(&bars.bfull), 0u);
+          mbar_arrive_expect_tx_cluster(lbar, (uint32_t)(kchunks * b_bytes));
+          for (int kc = 0; kc < kchunks; kc += a.kcs)
+            tma_load_3d_pair(bres_base + kc * b_bytes, &map_b, lbar, 0, my_nt * a.bn + (int)rank * (a.bn >> 1), kc);
+        } else {
+          mbar_arrive_expect_tx(&bars.bfull, (uint32_t)(kchunks * b_bytes));
+          for (int kc = 0; kc < kchunks; kc += a.kcs)
+            tma_load_3d(bres_base + kc * b_bytes, &map_b, &bars.bfull, 0, my_nt * a.bn, kc);
+        }
       }
       int stage = 0, j = 0;
       uint32_t phase = 0;
@@ -192,9 +278,17 @@ tok_gemm_kernel(const TgArgs a, const __grid_constant__ CUtensorMap map_a, const
             mbar_wait(&bars.empty[stage], phase ^ 1u);
             TP_LAP(1);                                     // wait for a free stage
             const uint32_t As = smem_base + stage * stage_bytes;
+            if (PAIR) {
+              // this CTA's activation rows and its half of the weight rows; completion counted on the LEADER's barrier
+              const uint32_t lbar = mapa_u32(smem_u32(&bars.full[stage]), 0u);
+              mbar_arrive_expect_tx_cluster(lbar, (uint32_t)stage_bytes);
+              tma_load_3d_pair(As, &map_a, lbar, 0, m * TG_BM, kc);
+              if (!a.bres) tma_load_3d_pair(As + a_stage_bytes, &map_b, lbar, 0, nt * a.bn + (int)rank * (a.bn >> 1), kc);
+            } else {
             mbar_arrive_expect_tx(&bars.full[stage], (uint32_t)stage_bytes);
             tma_load_3d(As, &map_a, &bars.full[stage], 0, m * TG_BM, kc);
             if (!a.bres) tma_load_3d(As + a_stage_bytes, &map_b, &bars.full[stage], 0, nt * a.bn, kc);
+            }
             TP_LAP(2);                                     // issue
           }
           if (++stage == a.stages) { stage = 0; phase ^= 1u; }
@@ -205,11 +299,12 @@ tok_gemm_kernel(const TgArgs a, const __grid_constant__ CUtensorMap map_a, const
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (warp-uniform, elected lane issues)
-    const uint32_t idesc = umma_idesc_f16(a.bn, 0);
+    const uint32_t idesc = PAIR ? ((1u << 4) | ((uint32_t)(a.bn >> 3) << 17) | ((uint32_t)(256 >> 4) << 24)) : umma_idesc_f16(a.bn, 0);
     int stage = 0, buf = 0;
     uint32_t phase = 0, bphase = 0;
     bool b_ready = !a.bres;
     TP_DECL;
+    if (!(PAIR && rank != 0))                                 // pair mode: only the leader issues
     for (int it = it0; it < items; it += step) {
       TG_DECODE(it, m, nt);
       if (!TG_ACTIVE(it, m, nt)) continue;
@@ -228,13 +323,16 @@ tok_gemm_kernel(const TgArgs a, const __grid_constant__ CUtensorMap map_a, const
         for (int c = 0; c < a.kcs; ++c) {
           const uint64_t ad = umma_desc(As + c * TG_A_BYTES, 16, 1024);
           const uint64_t bd = umma_desc(a.bres ? bres_base + (kc + c) * b_bytes : As + a_stage_bytes + c * b_bytes, 16, 1024);
-          umma_f16_elect_x4(d_tmem, ad, bd, idesc, (kc | c) ? 1u : 0u, 2u);
+          if (PAIR) umma_f16_pair_x4(d_tmem, ad, bd, idesc, (kc | c) ? 1u : 0u);
+          else umma_f16_elect_x4(d_tmem, ad, bd, idesc, (kc | c) ? 1u : 0u, 2u);
         }
-        umma_commit_elect(&bars.empty[stage]);
+        if (PAIR) umma_commit_pair_elect(&bars.empty[stage]);
+        else umma_commit_elect(&bars.empty[stage]);
         if (++stage == a.stages) { stage = 0; phase ^= 1u; }
         TP_LAP(3);                                         // issue + commit
       }
-      umma_commit_elect(&bars.tfull[buf]);
+      if (PAIR) umma_commit_pair_elect(&bars.tfull[buf]);
+      else umma_commit_elect(&bars.tfull[buf]);
       if (++buf == 2) { buf = 0; bphase ^= 1u; }
     }
     if (lane == 0) TP_FLUSH(1);
@@ -373,7 +471,11 @@ tok_gemm_kernel(const TgArgs a, const __grid_constant__ CUtensorMap map_a, const
       }
       TP_LAP(2);                                           // tcgen05.ld + arithmetic + stores
       tc_fence_before();
-      mbar_arrive(&bars.tempty[buf]);
+      __syncwarp();
+      if (lane == 0) {                                     // one arrival per warp (pair mode: on the leader's barrier)
+        if (PAIR) mbar_arrive_cluster_addr(mapa_u32(smem_u32(&bars.tempty[buf]), 0u));
+        else mbar_arrive(&bars.tempty[buf]);
+      }
       if (++buf == 2) { buf = 0; bphase ^= 1u; }
     }
     if (warp == 2 && lane == 0) TP_FLUSH(2);
@@ -381,13 +483,15 @@ tok_gemm_kernel(const TgArgs a, const __grid_constant__ CUtensorMap map_a, const
 
 #undef TG_DECODE
 #undef TG_ACTIVE
-  if (a.bres && warp == 0 && lane == 0 && it0 < items) mbar_wait(&bars.bfull, 0);   // the weight tile's copies have landed (a
+  if (a.bres && warp == 0 && lane == 0 && it0 < items && (!PAIR || rank == 0)) mbar_wait(&bars.bfull, 0);   // the weight tile's copies have landed (a
                                                                                   // CTA whose tiles were all gated never used it)
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();                            // no CTA of the pair leaves while the other may still read / signal it
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -906,34 +1010,56 @@ extern "C" int laud_tok_gemm(const laud_tok_gemm_desc* d, void* stream) {
   }
   const int n_tiles = (d->N + bn - 1) / bn, m_tiles_max = (d->rows_max + TG_BM - 1) / TG_BM;
   // weight-resident mode when the [bn, K] tile + >= 3 activation stages fit and every n-tile gets at least one CTA
-  int bres = 0, stages = TG_STAGES, kcs = 1;
+  int bres = 0, stages = TG_STAGES, kcs = 1, pair = 0;
   const int kchunks = d->K / 64;
   {
     const long long wbytes = (long long)kchunks * bn * 128;
     const long long scr_bytes = d->resid ? TG_SCR_BYTES : 0;
     const long long room = (long long)TG_SMEM_MAX - 1024 - wbytes - scr_bytes;
-    // A/B switches (diagnosis only): LAUD_TOKGEMM_STREAM = never keep the weight tile resident, LAUD_TOKGEMM_KCS1 = one chunk per stage
-    static const bool force_stream = getenv("LAUD_TOKGEMM_STREAM") != nullptr, kcs1 = getenv("LAUD_TOKGEMM_KCS1") != nullptr;
-    if (!force_stream && room >= 3 * TG_A_BYTES && n_tiles <= di.sms && m_tiles_max >= 2 * (di.sms / n_tiles)) {
+    // A/B switches (diagnosis only): LAUD_TOKGEMM_STREAM = never keep the weight tile resident, LAUD_TOKGEMM_KCS1 = one chunk per
+    // stage, LAUD_TOKGEMM_NOPAIR = no CTA pairs
+    static const bool force_stream = getenv("LAUD_TOKGEMM_STREAM") != nullptr, kcs1 = getenv("LAUD_TOKGEMM_KCS1") != nullptr,
+                      no_pair = getenv("LAUD_TOKGEMM_NOPAIR") != nullptr;
+    // CTA pairs are opt-in (desc->cta_pair, or LAUD_TOKGEMM_PAIR = "bres" | "stream" | "all" for a whole run): measured on
+    // configs[3] they are correct but SLOWER in every class (fc1 1.11 -> 1.28 ms, proj 0.56 -> 0.62, fc2 1.17 -> 1.23 per step) -
+    // these GEMMs are bound by their epilogues and by HBM-sourced activation tiles, not by weight bytes
+    static const char* pair_env = getenv("LAUD_TOKGEMM_PAIR");
+    const bool pair_bres = d->cta_pair || (pair_env && (!strcmp(pair_env, "all") || !strcmp(pair_env, "bres")));
+    const bool pair_stream = d->cta_pair || (pair_env && (!strcmp(pair_env, "all") || !strcmp(pair_env, "stream")));
+    const bool pair_ok = !no_pair && !d->col_gate && bn % 32 == 0 && (di.sms & 1) == 0;
+    // weight-resident in CTA pairs: each CTA keeps HALF of the n-tile's weight rows (half the shared memory, half the weight
+    // bytes per MMA) - whenever a single CTA could keep the whole tile, or only the half fits
+    const long long room_pair = (long long)TG_SMEM_MAX - 1024 - wbytes / 2 - scr_bytes;
+    const int clusters_per_nt = (di.sms / 2) / n_tiles;
+    if (!force_stream && pair_ok && pair_bres && room_pair >= 3 * TG_A_BYTES && clusters_per_nt >= 1 &&
+        (m_tiles_max + 1) / 2 >= 2 * clusters_per_nt) {
+      bres = 1;
+      pair = 1;
+      kcs = (kchunks % 2 == 0 && room_pair >= 3 * 2 * TG_A_BYTES && !kcs1) ? 2 : 1;
+      stages = (int)(room_pair / (kcs * TG_A_BYTES));
+    } else if (!force_stream && room >= 3 * TG_A_BYTES && n_tiles <= di.sms && m_tiles_max >= 2 * (di.sms / n_tiles)) {
       bres = 1;
       kcs = (kchunks % 2 == 0 && room >= 3 * 2 * TG_A_BYTES && !kcs1) ? 2 : 1;   // >= 3 stages in flight
       stages = (int)(room / (kcs * TG_A_BYTES));
     } else {
-      // streaming: two chunks per stage when at least two such stages fit
-      const long long st2 = 2LL * (TG_A_BYTES + bn * 128);
-      kcs = (kchunks % 2 == 0 && 2 * st2 + 1024 + scr_bytes <= TG_SMEM_MAX && !kcs1) ? 2 : 1;
-      stages = (int)((TG_SMEM_MAX - 1024 - scr_bytes) / (kcs * (TG_A_BYTES + bn * 128)));
+      // streaming (the weight tile does not fit: K = 768 / 1536).  CTA pairs halve the weight bytes per SM when there is enough
+      // work for every pair; two chunks per stage when at least two such stages fit
+      pair = (pair_ok && pair_stream && m_tiles_max >= 16) ? 1 : 0;
+      const long long chunk = TG_A_BYTES + (pair ? bn / 2 : bn) * 128;
+      kcs = (kchunks % 2 == 0 && 2 * 2 * chunk + 1024 + scr_bytes <= TG_SMEM_MAX && !kcs1) ? 2 : 1;
+      stages = (int)((TG_SMEM_MAX - 1024 - scr_bytes) / (kcs * chunk));
     }
     if (stages > TG_MAX_STAGES) stages = TG_MAX_STAGES;
   }
-  const size_t smem = (size_t)stages * kcs * (bres ? TG_A_BYTES : TG_A_BYTES + bn * 128) + (bres ? (size_t)kchunks * bn * 128 : 0) +
-                      (d->resid ? TG_SCR_BYTES : 0) + 1024;
+  const size_t smem = (size_t)stages * kcs * (bres ? TG_A_BYTES : TG_A_BYTES + (pair ? bn / 2 : bn) * 128) +
+                      (bres ? (size_t)kchunks * (pair ? bn / 2 : bn) * 128 : 0) + (d->resid ? TG_SCR_BYTES : 0) + 1024;
   if (!di.gemm_attr) {
-    LAUD_CUDA(cudaFuncSetAttribute(tok_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_MAX));
+    LAUD_CUDA(cudaFuncSetAttribute(tok_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_MAX));
+    LAUD_CUDA(cudaFuncSetAttribute(tok_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_MAX));
     di.gemm_attr = true;
   }
   CUtensorMap ma, mb;
-  if (!tg_map(&ma, d->a, d->K, d->rows_max, d->lda, TG_BM, kcs) || !tg_map(&mb, d->w, d->K, d->N, d->K, bn, kcs)) {
+  if (!tg_map(&ma, d->a, d->K, d->rows_max, d->lda, TG_BM, kcs) || !tg_map(&mb, d->w, d->K, d->N, d->K, pair ? bn / 2 : bn, kcs)) {
     set_error("laud_tok_gemm: cuTensorMapEncodeTiled failed");
     return LAUD_E_CUDA;
   }
@@ -941,12 +1067,32 @@ extern "C" int laud_tok_gemm(const laud_tok_gemm_desc* d, void* stream) {
   a.bias = d->bias; a.rows_max = d->rows_max; a.K = d->K; a.N = d->N; a.bn = bn; a.row_cnt = d->row_cnt; a.act = d->act;
   a.out = (__half*)d->out; a.ldo = d->ldo; a.resid = d->resid; a.ldres = d->ldres; a.row_idx = d->row_idx;
   a.col_gate = d->col_gate; a.gate_ld = d->gate_ld; a.row_sample = d->row_sample;
-  a.bres = bres; a.stages = stages; a.kcs = kcs;
+  a.bres = bres; a.stages = stages; a.kcs = kcs; a.pair = pair;
   static const int tg_dbg = getenv("LAUD_TG_DBG") ? atoi(getenv("LAUD_TG_DBG")) : 0;
   a.dbg = tg_dbg;
   const int items = m_tiles_max * n_tiles;
-  const int grid = bres ? (di.sms / n_tiles) * n_tiles : (items < di.sms ? items : di.sms);
-  tok_gemm_kernel<<<grid, TG_THREADS, smem, s>>>(a, ma, mb);
+  int grid = bres ? (di.sms / n_tiles) * n_tiles : (items < di.sms ? items : di.sms);
+  if (pair && bres) {
+    grid = 2 * ((di.sms / 2) / n_tiles) * n_tiles;
+  } else if (pair) {
+    const int pairs = ((m_tiles_max + 1) / 2) * n_tiles;
+    grid = 2 * (pairs < di.sms / 2 ? pairs : di.sms / 2);
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(TG_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = pair ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pair ? 1 : 0;
+  if (pair) cudaLaunchKernelEx(&cfg, tok_gemm_kernel<true>, a, ma, mb);
+  else cudaLaunchKernelEx(&cfg, tok_gemm_kernel<false>, a, ma, mb);
   g_tok_gemm_launches.fetch_add(1, std::memory_order_relaxed);
   return check_launch("tok_gemm_kernel");
 }

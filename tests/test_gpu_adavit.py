@@ -36,8 +36,11 @@ def _gemm(a, w, bias, rows_max, K, N, **kw):
 @pytest.mark.parametrize("rows,K,N,bn", [(300, 128, 192, 0), (1000, 384, 1152, 192), (517, 1536, 384, 0), (130, 384, 1000, 0),
                                          (64, 64, 64, 0), (2600, 384, 1536, 256), (333, 768, 384, 128),
                                          # weight-resident mode (K <= 384, enough m-tiles per CTA): QKV / proj / fc1 shapes
-                                         (12000, 384, 1152, 192), (21000, 384, 384, 0), (9000, 384, 1536, 0), (7000, 128, 192, 0)])
-def test_tok_gemm_store_vs_torch(cuda_lib, rows, K, N, bn):
+                                         (12000, 384, 1152, 192), (21000, 384, 384, 0), (9000, 384, 1536, 0), (7000, 128, 192, 0),
+                                         # CTA-pair mode (streaming, >= 16 m-tiles): fc2 / patch-projection shapes, odd tile counts
+                                         (6000, 1536, 384, 0), (4225, 768, 384, 0), (2600, 1536, 1000, 0), (5000, 768, 64, 0)])
+@pytest.mark.parametrize("pair", [0, 1])      # 1: CTA pairs (tcgen05 cta_group::2) where the shape allows - same results
+def test_tok_gemm_store_vs_torch(cuda_lib, rows, K, N, bn, pair):
     g = torch.Generator().manual_seed(rows + K + N)
     a = (torch.randn(rows, K, generator=g) * 0.5).half().to(DEV)
     w = (torch.randn(N, K, generator=g) / K ** 0.5).half().to(DEV)
@@ -45,7 +48,7 @@ def test_tok_gemm_store_vs_torch(cuda_lib, rows, K, N, bn):
     cnt = torch.tensor([rows - 37 if rows > 100 else rows], dtype=torch.int32, device=DEV)
     for act in (_lib.ACT_NONE, _lib.ACT_GELU):
         out = torch.full((rows, N), 7.0, dtype=torch.float16, device=DEV)
-        _gemm(a, w, bias, rows, K, N, row_cnt=cnt, act=act, out=out, bn=bn)
+        _gemm(a, w, bias, rows, K, N, row_cnt=cnt, act=act, out=out, bn=bn, cta_pair=pair)
         ref = a.float() @ w.float().T + bias
         if act:
             ref = F.gelu(ref)
@@ -55,16 +58,17 @@ def test_tok_gemm_store_vs_torch(cuda_lib, rows, K, N, bn):
     assert cuda_lib.laud_tok_gemm_launch_count() > 0
 
 
-def test_tok_gemm_residual_scatter_and_no_row_count(cuda_lib):
+@pytest.mark.parametrize("rows,K,N,R", [(700, 384, 384, 1500), (5300, 1536, 384, 9000), (3000, 768, 384, 3000)])
+@pytest.mark.parametrize("pair", [0, 1])
+def test_tok_gemm_residual_scatter_and_no_row_count(cuda_lib, rows, K, N, R, pair):
     g = torch.Generator().manual_seed(5)
-    rows, K, N, R = 700, 384, 384, 1500
     a = (torch.randn(rows, K, generator=g) * 0.5).half().to(DEV)
     w = (torch.randn(N, K, generator=g) / K ** 0.5).half().to(DEV)
     bias = torch.randn(N, generator=g).to(DEV)
     dest = torch.randperm(R, generator=g)[:rows].to(torch.int32).to(DEV)
     x0 = torch.randn(R, N, generator=g).to(DEV)
     x = x0.clone()
-    _gemm(a, w, bias, rows, K, N, resid=x, ldres=N, row_idx=dest)
+    _gemm(a, w, bias, rows, K, N, resid=x, ldres=N, row_idx=dest, cta_pair=pair)
     ref = x0.clone()
     ref[dest.long()] += a.float() @ w.float().T + bias
     assert _rel(x, ref.cpu()) <= 2e-4
