@@ -258,6 +258,10 @@ typedef struct laud_conv_desc {
 } laud_conv_desc;
 
 int laud_conv_forward(const laud_conv_desc* desc /* host */, int impl, void* stream);
+/* Launch policy of the TMA-staged convolution kernel: 1 = programmatic dependent launch (the prologue of a kernel - barrier
+ * initialisation, TMEM allocation, descriptor prefetch - overlaps the tail of its predecessor in the stream).  Pays for
+ * single-chain forwards of small batches (configs[0], batch 8: +4 %), costs with two parallel graph chains; default 0. */
+void laud_conv_set_pdl(int enable);
 
 /* H1 constants of channel-skipping with mask-before-BN (laud_resnet.py:115-118,
  * 123-126): a masked channel k of conv1's (conv2's) output is the constant

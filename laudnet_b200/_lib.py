@@ -93,6 +93,7 @@ SIGNATURES = {
     "laud_layer_gate_lists": ([_u8p, _i, _i, _i, _i32p, _i32p, _i32p, _vp], _i),
     "laud_compact_rows": ([_u8p, _i, _i, _i, _i32p, _i32p, _i32p, _vp], _i),
     "laud_conv_forward": ([C.POINTER(ConvDesc), _i, _vp], _i),
+    "laud_conv_set_pdl": ([_i], None),
     "laud_gate_from_logits": ([_fp, _fp, _i, _i, _i, C.c_float, _u8p, _i32p, _i32p, _i32p, _vp], _i),
     "laud_gate_inactive": ([_u8p, _i, _i, _i, _vp, _vp], _i),
     "laud_channel_consts_fold": ([_vp, _i, _i, _i, _i32p, _i32p, _i, _i, _i, _fp, _fp, _vp], _i),

@@ -48,6 +48,7 @@
 #include "umma_ptx.cuh"
 
 namespace laud {
+std::atomic<int> g_conv_pdl{0};
 namespace {
 
 constexpr int BM = 128;
@@ -1790,7 +1791,11 @@ static int conv_forward_tma_x(const ConvArgs& a_in, cudaStream_t s, bool allow_r
       else if (pl.omode == OUT_DIRECT) spec = pl.halo ? 3 : 2;
     }
     if (pl.bmode == BMODE_G4) spec = 6;
-    static const bool pdl = getenv("LAUD_PDL") != nullptr;   // opt-in: measured -2.5 % with the two graph chains (early CTAs of one chain sit on SMs the other chain could use), +0.8 % with one
+    // programmatic dependent launch: measured -2.5 % with the two graph chains of a large batch (early CTAs of one chain sit on
+    // SMs the other chain could use), +0.8 % with one chain at batch 256, +4 % at batch 8 (configs[0]: 1.283 -> 1.234 ms) - the
+    // engines switch it on for single-chain forwards of small batches (laud_conv_set_pdl); LAUD_PDL forces it on
+    static const bool pdl_env = getenv("LAUD_PDL") != nullptr;
+    const bool pdl = pdl_env || g_conv_pdl.load(std::memory_order_relaxed) != 0;
     switch (spec) {
       case 1: launch_conv_tma<1>(grid, smem, s, pdl, a, pl, map_a, map_b, map_y, map_r); break;
       case 2: launch_conv_tma<2>(grid, smem, s, pdl, a, pl, map_a, map_b, map_y, map_r); break;
@@ -1816,3 +1821,5 @@ extern "C" int laud_debug_kprof(long long* host_out /* [160][5][8] */, int reset
 #endif
 
 }  // namespace laud
+
+extern "C" void laud_conv_set_pdl(int enable) { laud::g_conv_pdl.store(enable ? 1 : 0, std::memory_order_relaxed); }
