@@ -324,3 +324,50 @@ def test_skipping_is_executed_not_masked(cuda_lib):
     with torch.no_grad():
         want = A.forward(sd, cfg, x, forced=pol)[0]
     assert _rel(ws["logits"], want) <= NET_TOL
+
+
+def test_empty_and_ragged_edge_cases(cuda_lib):
+    """Edge cases of the compact lists: a block in which EVERY sample skips both sub-layers (zero rows: nothing is
+    scheduled, the stream is untouched), a block in which only one sample runs, batch 1, and the all-kept path."""
+    cfg = TINY
+    m, sd, x = _build(cfg, 71, 5)
+    B, L, H = 5, cfg.seq_len, cfg.num_heads
+    traces = []
+    with torch.no_grad():
+        A.forward(sd, cfg, x, traces)
+    x_in = traces[2].x_in
+    ones_t, ones_h = torch.ones(B, L, dtype=torch.bool), torch.ones(B, H, dtype=torch.bool)
+    # (1) nobody runs anything
+    pol = A.BlockPolicy(ones_t, ones_h, torch.zeros(B, 2, dtype=torch.bool))
+    y = m.run_block(2, x_in.to(DEV), forced=_forced(pol))
+    assert torch.equal(y.cpu(), x_in)
+    ws = m.workspace(B)
+    assert int(ws["off_a"][2][B]) == 0 and int(ws["off_m"][2][B]) == 0
+    # (2) only sample 3 runs, attention only, with a ragged token set and one head
+    tok = torch.zeros(B, L, dtype=torch.bool); tok[:, 0] = True; tok[3, 1::3] = True
+    head = torch.zeros(B, H, dtype=torch.bool); head[3, 1] = True
+    layer = torch.zeros(B, 2, dtype=torch.bool); layer[3, 0] = True
+    pol = A.BlockPolicy(tok, head, layer)
+    y = m.run_block(2, x_in.to(DEV), forced=_forced(pol))
+    with torch.no_grad():
+        want = A.block_forward(x_in, sd, cfg, 2, pol)
+    assert _rel(y, want) <= ACT_TOL
+    keep = torch.zeros(B, L, dtype=torch.bool); keep[3] = tok[3]
+    assert torch.equal(y.cpu()[~keep], x_in[~keep])
+    # (3) batch 1, free-running, against the oracle
+    with torch.no_grad():
+        w1 = A.forward(sd, cfg, x[:1])[0]
+    l1 = m(x[:1].to(DEV))[0]
+    assert torch.isfinite(l1).all() and tuple(l1.shape) == tuple(w1.shape)    # (a single free-running sample may take another
+    #                                                                           trajectory at a tie: parity is checked above)
+    # (4) every gate open (policies off): the dense DeiT path
+    cfg_d = A.AdaViTCfg(img_size=64, embed_dim=128, depth=3, num_heads=2, num_classes=16, ada_token=False, ada_head=False, ada_layer=False)
+    md = AdaViT(**cfg_d.kwargs())
+    sdd = synth.synth_adavit_state_dict(A.state_dict_shapes(cfg_d), 72)
+    md.load_state_dict(sdd, strict=True)
+    md = md.to(DEV).eval()
+    with torch.no_grad():
+        wd = A.forward(sdd, cfg_d, x)[0]
+    ld, tk, hd, ly = md(x.to(DEV))
+    assert tk.all() and hd.all() and ly.all()
+    assert _rel(ld, wd) <= NET_TOL
