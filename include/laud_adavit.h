@@ -65,6 +65,18 @@ int laud_tok_gemm(const laud_tok_gemm_desc* desc /* host */, void* stream);
 /* launches of the tcgen05 token GEMM in this process */
 unsigned long long laud_tok_gemm_launch_count(void);
 
+/* ---------------------------------------------------------------------------
+ * The MLP sub-layer in ONE kernel (simulate_adavit.py:130-147: fc1 "dylinear", GELU, fc2) with the hidden activations
+ * kept on chip:   resid[row_idx[i], 0:D] += GELU(y[i] W1^T + b1) W2^T + b2     for the compact rows i < *row_cnt.
+ * Per 128-row tile the normalised rows stay in shared memory; the hidden dimension is walked in chunks of 128 - GEMM1 into
+ * TMEM, + b1, GELU, fp16 into a swizzled shared-memory tile that is the A operand of GEMM2 (accumulated in TMEM over all
+ * chunks) - and the result is reduced into the residual stream.  The [rows, Hd] hidden tensor (166 MB per DeiT-S layer at
+ * batch 512) that laud_tok_gemm(fc1) + laud_tok_gemm(fc2) write and re-read never exists.
+ *   y fp16 [rows_max, D]; w1 fp16 [Hd, D], b1 fp32 [Hd]; w2 fp16 [D, Hd], b2 fp32 [D]; D = 128 | 256 | 384, Hd % 128 == 0.
+ * ------------------------------------------------------------------------- */
+int laud_adavit_mlp_fused(const void* y, int rows_max, int D, int Hd, const int32_t* row_cnt, const void* w1, const float* b1,
+                          const void* w2, const float* b2, float* resid, int ldres, const int32_t* row_idx, void* stream);
+
 /* Patch embedding, first half (the unfold of simulate_adavit.py:61): x fp16 NCHW [B, 3, S, S] -> patches fp16
  * [B * (S/P)^2, 3*P*P], column = c*P*P + iy*P + ix (the flattened conv weight's order); P % 8 == 0.  The projection
  * itself is laud_tok_gemm with resid = the token stream and row_idx[i] = b*L + 1 + p. */

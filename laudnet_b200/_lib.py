@@ -110,6 +110,7 @@ SIGNATURES = {
     # include/laud_adavit.h
     "laud_tok_gemm": ([C.POINTER(TokGemmDesc), _vp], _i),
     "laud_tok_gemm_launch_count": ([], C.c_ulonglong),
+    "laud_adavit_mlp_fused": ([_vp, _i, _i, _i, _i32p, _vp, _fp, _vp, _fp, _fp, _i, _i32p, _vp], _i),
     "laud_vit_patchify": ([_vp, _i, _i, _i, _vp, _vp], _i),
     "laud_vit_init_tokens": ([_fp, _i, _i, _i, _fp, _fp, _vp], _i),
     "laud_adavit_policy": ([_fp, _i, _i, _i, _i, C.c_float, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp,

@@ -18,6 +18,7 @@ There is no CPU path and no training path (`LaudError`).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence
 
@@ -112,6 +113,8 @@ class AdaViT(nn.Module):
         self._ws: Dict[int, dict] = {}
         self._graphs: Dict[int, "GraphedAdaViT"] = {}
         self.head_tile_skip = True          # drop whole per-head n-tiles of the QKV projection (A/B switch)
+        # fc1 -> GELU -> fc2 in one kernel, hidden activations on chip (laud_adavit_mlp_fused); False: two token GEMMs
+        self.fused_mlp = embed_dim in (128, 256, 384) and self.hidden % 128 == 0 and os.environ.get("LAUD_ADAVIT_MLP") != "split"
         self.profile: Optional[list] = None  # measurement aid: a list makes _run record (tag, CUDA event) before every launch
 
     # ------------------------------------------------------------------ parameters -> device layouts (once)
@@ -259,10 +262,16 @@ class AdaViT(nn.Module):
             mark("ln_gather")
             check(lib.laud_adavit_ln_gather(ptr(x), B, L, D, LN_EPS, ptr(q["n2_w"]), ptr(q["n2_b"]), ptr(tok), ptr(off_m),
                                             ptr(ws["y"]), ptr(ws["rows_m"]), None, st), "laud_adavit_ln_gather")
-            mark("gemm_fc1")
-            self._gemm(ws["y"], q["fc1_w"], q["fc1_b"], rows, D, Hd, st, row_cnt=off_m[B:], act=_lib.ACT_GELU, out=ws["hdn"])
-            mark("gemm_fc2")
-            self._gemm(ws["hdn"], q["fc2_w"], q["fc2_b"], rows, Hd, D, st, row_cnt=off_m[B:], resid=x, ldres=D, row_idx=ws["rows_m"])
+            if self.fused_mlp:
+                mark("gemm_mlp_fused")
+                check(lib.laud_adavit_mlp_fused(ptr(ws["y"]), rows, D, Hd, ptr(off_m[B:]), ptr(q["fc1_w"]), ptr(q["fc1_b"]),
+                                                ptr(q["fc2_w"]), ptr(q["fc2_b"]), ptr(x), D, ptr(ws["rows_m"]), st),
+                      "laud_adavit_mlp_fused")
+            else:
+                mark("gemm_fc1")
+                self._gemm(ws["y"], q["fc1_w"], q["fc1_b"], rows, D, Hd, st, row_cnt=off_m[B:], act=_lib.ACT_GELU, out=ws["hdn"])
+                mark("gemm_fc2")
+                self._gemm(ws["hdn"], q["fc2_w"], q["fc2_b"], rows, Hd, D, st, row_cnt=off_m[B:], resid=x, ldres=D, row_idx=ws["rows_m"])
             if keep is not None:
                 keep.append(BlockKeep(tok.bool().clone(), head.bool().clone(), layer.bool().clone(), ws["tok_lg"][i].clone(),
                                       ws["head_lg"][i].clone(), ws["layer_lg"][i].clone(), x.clone()))

@@ -522,7 +522,242 @@ bool tg_map(CUtensorMap* m, const void* base, long long cols, long long rows, lo
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-struct DevInfo { int sms; bool gemm_attr, attn_attr; };
+
+// =====================================================================================================================
+// fused MLP: x[row] += fc2(GELU(fc1(y) + b1)) + b2 with the hidden activations kept ON CHIP
+// =====================================================================================================================
+// One m-tile (128 compact rows) per CTA pass.  The normalised rows y [128, D] stay in shared memory for the whole pass; the
+// hidden dimension is walked in chunks of 128: GEMM1 (acc1 [128 x 128] in TMEM) -> epilogue: + b1, GELU, fp16 -> a K-major
+// 128B-swizzled shared-memory tile H_j that is the A operand of GEMM2 (acc2 [128 x D] in TMEM, accumulated over all chunks)
+// -> final epilogue: + b2, reduced into the residual stream.  The 166 MB of hidden activations per layer that the two-GEMM
+// form writes to and re-reads from HBM never exist; both weight matrices stream through a ring of 16 KB units
+// ([128 rows x 64 k]) in the order the MMAs consume them.
+//   warp 0 / warp 14: TMA producers (alternate units; warp 0 also the y tile)   warp 1: MMA issuer   warps 2-13: epilogue
+constexpr int FM_STAGES = 4, FM_UNIT = TG_A_BYTES;           // weight ring: 4 x 16 KB
+constexpr int FM_HC = 128;                                   // hidden columns per chunk
+struct FmArgs {
+  int rows_max, D, Hd;
+  const int* row_cnt;
+  const float* b1; const float* b2;
+  float* resid; int ldres;
+  const int* row_idx;
+};
+struct alignas(8) FmBars {
+  unsigned long long afull, aempty, wfull[FM_STAGES], wempty[FM_STAGES], acc1full, acc1empty, hfull[2], hempty[2], acc2full, acc2empty;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(TG_THREADS, 1)
+mlp_fused_kernel(const FmArgs a, const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w1,
+                 const __grid_constant__ CUtensorMap map_w2) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ FmBars bars;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int KD = a.D / 64, NB2 = a.D / 128, NJ = a.Hd / FM_HC;     // y chunks, output n-blocks of 128, hidden chunks
+  const uint32_t a_base = smem_base;                               // y tile: KD chunks of 16 KB
+  const uint32_t h_base = a_base + (uint32_t)KD * TG_A_BYTES;      // H double buffer: 2 x (2 chunks of 16 KB)
+  const uint32_t w_base = h_base + 2u * 2u * TG_A_BYTES;           // weight ring
+  if (threadIdx.x == 0) {
+    mbar_init(&bars.afull, 1); mbar_init(&bars.aempty, 1);
+    for (int i = 0; i < FM_STAGES; ++i) { mbar_init(&bars.wfull[i], 1); mbar_init(&bars.wempty[i], 1); }
+    mbar_init(&bars.acc1full, 1); mbar_init(&bars.acc1empty, TG_EPI_WARPS);
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars.hfull[i], TG_EPI_WARPS); mbar_init(&bars.hempty[i], 1); }
+    mbar_init(&bars.acc2full, 1); mbar_init(&bars.acc2empty, TG_EPI_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_w1); tma_prefetch_desc(&map_w2);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars.tmem_base)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  const int cnt = a.row_cnt ? min(__ldg(a.row_cnt), a.rows_max) : a.rows_max;
+  const int m_tiles = (cnt + TG_BM - 1) / TG_BM;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars.tmem_base;
+  const uint32_t acc1 = tmem_base, acc2 = tmem_base + 128u;
+
+  if (warp == 0 || warp == TG_PROD2_WARP) {
+    // ------------------------------------------------------------ producers
+    if (lane == 0) {
+      const int me = warp == 0 ? 0 : 1;
+      int stage = 0, u = 0, t = 0;
+      uint32_t phase = 0;
+      auto unit = [&](const CUtensorMap* map, int row0, int kchunk) {     // next 16 KB weight unit, in MMA order
+        if ((u & 1) == me) {
+          mbar_wait(&bars.wempty[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&bars.wfull[stage], (uint32_t)FM_UNIT);
+          tma_load_3d(w_base + stage * FM_UNIT, map, &bars.wfull[stage], 0, row0, kchunk);
+        }
+        ++u;
+        if (++stage == FM_STAGES) { stage = 0; phase ^= 1u; }
+      };
+      for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++t) {
+        if (me == 0) {                                                   // the pass's y tile (all KD chunks)
+          mbar_wait(&bars.aempty, (uint32_t)(t & 1) ^ 1u);
+          mbar_arrive_expect_tx(&bars.afull, (uint32_t)(KD * TG_A_BYTES));
+          for (int c = 0; c < KD; ++c) tma_load_3d(a_base + c * TG_A_BYTES, &map_a, &bars.afull, 0, mt * TG_BM, c);
+        }
+        for (int j = 0; j <= NJ; ++j) {
+          if (j < NJ)
+            for (int c = 0; c < KD; ++c) unit(&map_w1, j * FM_HC, c);                    // GEMM1_j: W1 rows of chunk j
+          if (j >= 1)
+            for (int c = 0; c < 2; ++c)
+              for (int nb = 0; nb < NB2; ++nb) unit(&map_w2, nb * 128, (j - 1) * 2 + c);  // GEMM2_{j-1}: W2[:, chunk j-1]
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (warp-uniform)
+    const uint32_t idesc = umma_idesc_f16(128, 0);
+    int stage = 0, t = 0, g1 = 0, g2 = 0;                    // g1 / g2: GEMM1 / GEMM2 chunks issued so far (barrier phases)
+    uint32_t phase = 0;
+    for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++t) {
+      mbar_wait(&bars.afull, (uint32_t)(t & 1));
+      tc_fence_after();
+      for (int j = 0; j <= NJ; ++j) {
+        if (j < NJ) {
+          mbar_wait(&bars.acc1empty, (uint32_t)(g1 & 1) ^ 1u);           // the previous chunk's accumulator has been read
+          tc_fence_after();
+          for (int c = 0; c < KD; ++c) {
+            mbar_wait(&bars.wfull[stage], phase);
+            tc_fence_after();
+            umma_f16_elect_x4(acc1, umma_desc(a_base + c * TG_A_BYTES, 16, 1024), umma_desc(w_base + stage * FM_UNIT, 16, 1024), idesc,
+                              c ? 1u : 0u, 2u);
+            umma_commit_elect(&bars.wempty[stage]);
+            if (++stage == FM_STAGES) { stage = 0; phase ^= 1u; }
+          }
+          umma_commit_elect(&bars.acc1full);
+          if (j == NJ - 1) umma_commit_elect(&bars.aempty);             // the y tile is free once the last GEMM1 has read it
+          ++g1;
+        }
+        if (j >= 1) {
+          const int b = (g2 & 1);
+          mbar_wait(&bars.hfull[b], (uint32_t)((g2 >> 1) & 1));
+          if (j == 1) mbar_wait(&bars.acc2empty, (uint32_t)(t & 1) ^ 1u);   // the previous pass's result has been drained
+          tc_fence_after();
+          for (int c = 0; c < 2; ++c)
+            for (int nb = 0; nb < NB2; ++nb) {
+              mbar_wait(&bars.wfull[stage], phase);
+              tc_fence_after();
+              umma_f16_elect_x4(acc2 + nb * 128, umma_desc(h_base + (b * 2 + c) * TG_A_BYTES, 16, 1024),
+                                umma_desc(w_base + stage * FM_UNIT, 16, 1024), idesc, (j > 1 || c) ? 1u : 0u, 2u);
+              umma_commit_elect(&bars.wempty[stage]);
+              if (++stage == FM_STAGES) { stage = 0; phase ^= 1u; }
+            }
+          umma_commit_elect(&bars.hempty[b]);
+          if (j == NJ) umma_commit_elect(&bars.acc2full);
+          ++g2;
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------ epilogue warps
+    const int q = warp & 3, part = (warp - 2) >> 2;           // TMEM lane quarter; which third of the column groups
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const int r = q * 32 + lane;                              // accumulator row of this thread
+    // residual write-out scratch (one 2 KB block per warp) lives in the H buffers once a pass's GEMM2s are done
+    const uint32_t scr = h_base + (uint32_t)(warp - 2) * 2048u;
+    const uint32_t wr_base = scr + (uint32_t)lane * 64u;
+    const int wr_sw = (lane >> 1) & 3, rd_ch = lane & 3;
+    int e1 = 0, t = 0;
+    for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++t) {
+      const int row0 = mt * TG_BM + q * 32;
+      for (int j = 0; j < NJ; ++j, ++e1) {
+        const int b = e1 & 1;
+        mbar_wait(&bars.acc1full, (uint32_t)(e1 & 1));
+        tc_fence_after();
+        // this warp's 32-column groups of the 128: part 0 takes groups 0 and 3, part 1 group 1, part 2 group 2
+        float v[2][32];
+        const int ng = part == 0 ? 2 : 1;
+        const int g0 = part == 0 ? 0 : part;
+        tmem_ld32(acc1 + lane_off + g0 * 32, v[0]);
+        if (ng == 2) tmem_ld32(acc1 + lane_off + 96, v[1]);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.acc1empty);          // GEMM1 of the next chunk may overwrite the accumulator
+        if (e1 >= 2) mbar_wait(&bars.hempty[b], (uint32_t)(((e1 >> 1) - 1) & 1));   // GEMM2 of chunk e1-2 has read this buffer
+        for (int gi = 0; gi < ng; ++gi) {
+          const int hc0 = gi == 0 ? g0 * 32 : 96;             // first hidden column (within the chunk) of this group
+          const float* bp = a.b1 + j * FM_HC + hc0;
+          float4 bb[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) bb[i] = __ldg(reinterpret_cast<const float4*>(bp) + i);
+          float* w = v[gi];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            w[4 * i] = gelu_erf(w[4 * i] + bb[i].x); w[4 * i + 1] = gelu_erf(w[4 * i + 1] + bb[i].y);
+            w[4 * i + 2] = gelu_erf(w[4 * i + 2] + bb[i].z); w[4 * i + 3] = gelu_erf(w[4 * i + 3] + bb[i].w);
+          }
+          const uint32_t tile = h_base + (uint32_t)(b * 2 + (hc0 >> 6)) * TG_A_BYTES;   // K-major swizzled [128 rows][64 hidden]
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 pk;
+            pk.x = pack_h2(w[8 * i], w[8 * i + 1]); pk.y = pack_h2(w[8 * i + 2], w[8 * i + 3]);
+            pk.z = pack_h2(w[8 * i + 4], w[8 * i + 5]); pk.w = pack_h2(w[8 * i + 6], w[8 * i + 7]);
+            sts128(tile + sw128_off(r, ((hc0 & 63) >> 3) + i), pk);
+          }
+        }
+        fence_proxy_async();                                  // generic-proxy writes -> visible to the tensor core's reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.hfull[b]);
+      }
+      // ---- final epilogue of the pass: acc2 [128 x D] + b2 -> x[row_idx[row]] (16-byte reductions, 8 rows x 64 B per instruction)
+      mbar_wait(&bars.acc2full, (uint32_t)(t & 1));
+      tc_fence_after();
+      const int my_dst = (row0 + lane < cnt) ? __ldg(a.row_idx + row0 + lane) : 0;
+      for (int g = part; g * 32 < a.D; g += 3) {
+        const int c0 = g * 32;
+        float4 bb[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) bb[i] = __ldg(reinterpret_cast<const float4*>(a.b2 + c0) + i);
+        float w[32];
+        tmem_ld32(acc2 + lane_off + c0, w);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { w[4 * i] += bb[i].x; w[4 * i + 1] += bb[i].y; w[4 * i + 2] += bb[i].z; w[4 * i + 3] += bb[i].w; }
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 pk;
+            pk.x = __float_as_uint(w[sub * 16 + 4 * i]); pk.y = __float_as_uint(w[sub * 16 + 4 * i + 1]);
+            pk.z = __float_as_uint(w[sub * 16 + 4 * i + 2]); pk.w = __float_as_uint(w[sub * 16 + 4 * i + 3]);
+            sts128(wr_base + (uint32_t)((i ^ wr_sw) << 4), pk);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int rr = (lane >> 2) + 8 * k;
+            const int dst = __shfl_sync(0xffffffffu, my_dst, rr);
+            const uint4 pk = lds128(scr + (uint32_t)rr * 64u + (uint32_t)((rd_ch ^ ((rr >> 1) & 3)) << 4));
+            if (row0 + rr < cnt)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.resid + (size_t)dst * a.ldres + c0 + sub * 16 + rd_ch * 4),
+                           "f"(__uint_as_float(pk.x)), "f"(__uint_as_float(pk.y)), "f"(__uint_as_float(pk.z)), "f"(__uint_as_float(pk.w))
+                           : "memory");
+          }
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.acc2empty);
+      // the scratch sits in the H buffers: the next pass's first epilogues write them only after every warp is done here
+      named_bar_sync(1, TG_EPI_WARPS * 32);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+struct DevInfo { int sms; bool gemm_attr, attn_attr, mlp_attr; };
 DevInfo g_dev[MAX_DEVICES];
 
 // =====================================================================================================================
@@ -1095,6 +1330,39 @@ extern "C" int laud_tok_gemm(const laud_tok_gemm_desc* d, void* stream) {
   else cudaLaunchKernelEx(&cfg, tok_gemm_kernel<false>, a, ma, mb);
   g_tok_gemm_launches.fetch_add(1, std::memory_order_relaxed);
   return check_launch("tok_gemm_kernel");
+}
+
+extern "C" int laud_adavit_mlp_fused(const void* y, int rows_max, int D, int Hd, const int32_t* row_cnt, const void* w1, const float* b1,
+                                     const void* w2, const float* b2, float* resid, int ldres, const int32_t* row_idx, void* stream) {
+  LAUD_REQUIRE(y && w1 && b1 && w2 && b2 && resid && row_idx && rows_max > 0, "laud_adavit_mlp_fused: null argument");
+  LAUD_REQUIRE(D % 128 == 0 && D >= 128 && D <= 384 && Hd % 128 == 0 && Hd >= 128 && ldres % 4 == 0 && ldres >= D,
+               "laud_adavit_mlp_fused: D must be 128 / 256 / 384, Hd a multiple of 128 (got D=%d Hd=%d)", D, Hd);
+  LAUD_REQUIRE(((uintptr_t)y & 15) == 0 && ((uintptr_t)w1 & 15) == 0 && ((uintptr_t)w2 & 15) == 0 && ((uintptr_t)b1 & 15) == 0 &&
+               ((uintptr_t)b2 & 15) == 0 && ((uintptr_t)resid & 15) == 0, "laud_adavit_mlp_fused: operands must be 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int dev = current_device();
+  DevInfo& di = g_dev[dev];
+  if (!di.sms) {
+    cudaDeviceProp prop;
+    LAUD_CUDA(cudaGetDeviceProperties(&prop, dev));
+    di.sms = prop.multiProcessorCount;
+  }
+  const size_t smem = (size_t)(D / 64) * TG_A_BYTES + 4 * TG_A_BYTES + FM_STAGES * FM_UNIT + 1024;
+  if (!di.mlp_attr) {
+    LAUD_CUDA(cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * TG_A_BYTES + 4 * TG_A_BYTES + FM_STAGES * FM_UNIT + 1024));
+    di.mlp_attr = true;
+  }
+  CUtensorMap ma, m1, m2;
+  if (!tg_map(&ma, y, D, rows_max, D, TG_BM, 1) || !tg_map(&m1, w1, D, Hd, D, 128, 1) || !tg_map(&m2, w2, Hd, D, Hd, 128, 1)) {
+    set_error("laud_adavit_mlp_fused: cuTensorMapEncodeTiled failed");
+    return LAUD_E_CUDA;
+  }
+  FmArgs a;
+  a.rows_max = rows_max; a.D = D; a.Hd = Hd; a.row_cnt = row_cnt; a.b1 = b1; a.b2 = b2; a.resid = resid; a.ldres = ldres; a.row_idx = row_idx;
+  const int m_tiles_max = (rows_max + TG_BM - 1) / TG_BM;
+  const int grid = m_tiles_max < di.sms ? m_tiles_max : di.sms;
+  mlp_fused_kernel<<<grid, TG_THREADS, smem, s>>>(a, ma, m1, m2);
+  return check_launch("mlp_fused_kernel");
 }
 
 extern "C" int laud_vit_patchify(const void* x_nchw, int B, int S, int P, void* patches, void* stream) {

@@ -107,6 +107,33 @@ def test_tok_gemm_head_tile_skip(cuda_lib, big):
     assert skipped > 0
 
 
+@pytest.mark.parametrize("rows,D,Hd", [(300, 128, 512), (1000, 384, 1536), (5000, 384, 1536), (129, 256, 1024)])
+def test_mlp_fused_vs_torch(cuda_lib, rows, D, Hd):
+    """fc1 -> GELU -> fc2 -> residual add in one kernel (hidden activations on chip) against fp32 torch on the same fp16
+    operands; rows past the device-side count and rows that are not destinations stay untouched."""
+    g = torch.Generator().manual_seed(rows + D)
+    y = (torch.randn(rows, D, generator=g) * 0.7).half().to(DEV)
+    w1 = (torch.randn(Hd, D, generator=g) / D ** 0.5).half().to(DEV)
+    w2 = (torch.randn(D, Hd, generator=g) / Hd ** 0.5).half().to(DEV)
+    b1, b2 = (torch.randn(Hd, generator=g) * 0.3).to(DEV), (torch.randn(D, generator=g) * 0.3).to(DEV)
+    R = rows + 77
+    dest = torch.randperm(R, generator=g)[:rows].to(torch.int32).to(DEV)
+    n = rows - 41 if rows > 200 else rows
+    cnt = torch.tensor([n], dtype=torch.int32, device=DEV)
+    x0 = torch.randn(R, D, generator=g).to(DEV)
+    x = x0.clone()
+    _lib.check(cuda_lib.laud_adavit_mlp_fused(y.data_ptr(), rows, D, Hd, cnt.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
+                                              b2.data_ptr(), x.data_ptr(), D, dest.data_ptr(), _lib.stream_ptr()), "laud_adavit_mlp_fused")
+    torch.cuda.synchronize()
+    hid = F.gelu(y.float() @ w1.float().T + b1).half().float()          # the hidden activations are fp16 on chip too
+    ref = x0.clone()
+    ref[dest[:n].long()] += (hid @ w2.float().T + b2)[:n]
+    assert _rel(x, ref.cpu()) <= 5e-4
+    untouched = torch.ones(R, dtype=torch.bool, device=DEV)
+    untouched[dest[:n].long()] = False
+    assert torch.equal(x[untouched], x0[untouched])
+
+
 def test_tok_gemm_rejects_bad_shapes(cuda_lib):
     a = torch.zeros(64, 100, dtype=torch.float16, device=DEV)
     with pytest.raises(_lib.LaudError):
