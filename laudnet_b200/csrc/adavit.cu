@@ -530,10 +530,17 @@ bool tg_map(CUtensorMap* m, const void* base, long long cols, long long rows, lo
 // hidden dimension is walked in chunks of 128: GEMM1 (acc1 [128 x 128] in TMEM) -> epilogue: + b1, GELU, fp16 -> a K-major
 // 128B-swizzled shared-memory tile H_j that is the A operand of GEMM2 (acc2 [128 x D] in TMEM, accumulated over all chunks)
 // -> final epilogue: + b2, reduced into the residual stream.  The 166 MB of hidden activations per layer that the two-GEMM
-// form writes to and re-reads from HBM never exist; both weight matrices stream through a ring of 16 KB units
-// ([128 rows x 64 k]) in the order the MMAs consume them.
+// form writes to and re-reads from HBM never exist; both weight matrices stream through a 64 KB ring of units
+// ([weight rows x 2 x 64 k], one TMA box each) in the order the MMAs consume them.
 //   warp 0 / warp 14: TMA producers (alternate units; warp 0 also the y tile)   warp 1: MMA issuer   warps 2-13: epilogue
-constexpr int FM_STAGES = 4, FM_UNIT = TG_A_BYTES;           // weight ring: 4 x 16 KB
+// PAIR: two CTAs (a cluster) run every MMA as tcgen05.mma.cta_group::2 - M = 256 (each CTA its own 128 rows, accumulators and
+// H tiles), each CTA stages only HALF of every weight unit (64 of its 128 rows).  A single CTA needs 192 KB of weights per
+// 3 072 MMA cycles - 64 B/clk/SM, above what L2 delivers to all SMs at once (~6 300 B/clk chip-wide = 42 B/clk/SM) and more
+// than a 64 KB ring covers at the L2 latency under that load (scripts/fm_bench.py: 100k cycles per pass against 37k of MMAs,
+// 75k with the loads switched off - ring round trips); the pair halves both.  The leader (cluster rank 0) issues; its
+// barriers count arrivals of BOTH CTAs (operands landed, accumulators drained, H tiles written), the "free" barriers of
+// both CTAs are signalled by its multicast commits.
+constexpr int FM_RING = 4 * TG_A_BYTES;                      // weight ring bytes per CTA
 constexpr int FM_HC = 128;                                   // hidden columns per chunk
 struct FmArgs {
   int rows_max, D, Hd;
@@ -541,43 +548,72 @@ struct FmArgs {
   const float* b1; const float* b2;
   float* resid; int ldres;
   const int* row_idx;
+  int dbg;                                                   // LAUD_KPROF builds only (LAUD_FM_DBG; timing experiments, WRONG results):
+                                                             // 1 no GELU arithmetic, 2 no weight loads, 4 no reductions, 8 no GELU epilogue body
 };
+constexpr int FM_MAX_STAGES = 4;
 struct alignas(8) FmBars {
-  unsigned long long afull, aempty, wfull[FM_STAGES], wempty[FM_STAGES], acc1full, acc1empty, hfull[2], hempty[2], acc2full, acc2empty;
+  unsigned long long afull, aempty, wfull[FM_MAX_STAGES], wempty[FM_MAX_STAGES], acc1full, acc1empty, hfull[2], hempty[2], acc2full, acc2empty;
   uint32_t tmem_base;
 };
 
+#ifdef LAUD_KPROF
+#define FM_DBG a.dbg      // timing experiments of the diagnostic build (WRONG results)
+#else
+#define FM_DBG 0
+#endif
+template <bool PAIR>
 __global__ void __launch_bounds__(TG_THREADS, 1)
 mlp_fused_kernel(const FmArgs a, const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w1,
                  const __grid_constant__ CUtensorMap map_w2) {
+  constexpr int WR = PAIR ? 64 : 128;                              // weight rows this CTA stages per unit
+  constexpr int HALF = WR * 128;                                   // bytes of one 64-k chunk of a unit
+  constexpr int UNIT = 2 * HALF, STAGES = FM_RING / UNIT;          // 16 KB x 4 (pair) / 32 KB x 2
+  constexpr int NE = TG_EPI_WARPS * (PAIR ? 2 : 1);                // epilogue warps that report to the issuer
   extern __shared__ unsigned char smem_raw[];
   __shared__ FmBars bars;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t rank = PAIR ? cluster_rank() : 0u;
   const int KD = a.D / 64, NB2 = a.D / 128, NJ = a.Hd / FM_HC;     // y chunks, output n-blocks of 128, hidden chunks
   const uint32_t a_base = smem_base;                               // y tile: KD chunks of 16 KB
   const uint32_t h_base = a_base + (uint32_t)KD * TG_A_BYTES;      // H double buffer: 2 x (2 chunks of 16 KB)
   const uint32_t w_base = h_base + 2u * 2u * TG_A_BYTES;           // weight ring
   if (threadIdx.x == 0) {
-    mbar_init(&bars.afull, 1); mbar_init(&bars.aempty, 1);
-    for (int i = 0; i < FM_STAGES; ++i) { mbar_init(&bars.wfull[i], 1); mbar_init(&bars.wempty[i], 1); }
-    mbar_init(&bars.acc1full, 1); mbar_init(&bars.acc1empty, TG_EPI_WARPS);
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars.hfull[i], TG_EPI_WARPS); mbar_init(&bars.hempty[i], 1); }
-    mbar_init(&bars.acc2full, 1); mbar_init(&bars.acc2empty, TG_EPI_WARPS);
+    mbar_init(&bars.afull, PAIR ? 2 : 1); mbar_init(&bars.aempty, 1);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&bars.wfull[i], PAIR ? 2 : 1); mbar_init(&bars.wempty[i], 1); }
+    mbar_init(&bars.acc1full, 1); mbar_init(&bars.acc1empty, NE);
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars.hfull[i], NE); mbar_init(&bars.hempty[i], 1); }
+    mbar_init(&bars.acc2full, 1); mbar_init(&bars.acc2empty, NE);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_w1); tma_prefetch_desc(&map_w2);
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars.tmem_base)), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars.tmem_base)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars.tmem_base)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   const int cnt = a.row_cnt ? min(__ldg(a.row_cnt), a.rows_max) : a.rows_max;
   const int m_tiles = (cnt + TG_BM - 1) / TG_BM;
+  // passes: m-tiles (single CTA) or m-PAIRS over the clusters - both CTAs of a pair run every pass of the pair (an odd last
+  // m-tile leaves the second CTA computing rows that are masked at the write-out)
+  const int u0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, ustep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int m_units = PAIR ? (m_tiles + 1) >> 1 : m_tiles;
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();                                    // the peer's barriers exist before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = bars.tmem_base;
   const uint32_t acc1 = tmem_base, acc2 = tmem_base + 128u;
+  // arrival of one epilogue warp on a barrier of the issuing CTA
+  auto arrive_issuer = [&](unsigned long long* b) {
+    if (PAIR) mbar_arrive_cluster_addr(mapa_u32(smem_u32(b), 0u));
+    else mbar_arrive(b);
+  };
 
   if (warp == 0 || warp == TG_PROD2_WARP) {
     // ------------------------------------------------------------ producers
@@ -585,53 +621,75 @@ mlp_fused_kernel(const FmArgs a, const __grid_constant__ CUtensorMap map_a, cons
       const int me = warp == 0 ? 0 : 1;
       int stage = 0, u = 0, t = 0;
       uint32_t phase = 0;
-      auto unit = [&](const CUtensorMap* map, int row0, int kchunk) {     // next 16 KB weight unit, in MMA order
+      auto unit = [&](const CUtensorMap* map, int row0, int kchunk) {     // next weight unit, in MMA order
         if ((u & 1) == me) {
           mbar_wait(&bars.wempty[stage], phase ^ 1u);
-          mbar_arrive_expect_tx(&bars.wfull[stage], (uint32_t)FM_UNIT);
-          tma_load_3d(w_base + stage * FM_UNIT, map, &bars.wfull[stage], 0, row0, kchunk);
+          if (FM_DBG & 2) { arrive_issuer(&bars.wfull[stage]); }
+          else if (PAIR) {
+            const uint32_t lbar = mapa_u32(smem_u32(&bars.wfull[stage]), 0u);
+            mbar_arrive_expect_tx_cluster(lbar, (uint32_t)UNIT);
+            tma_load_3d_pair(w_base + stage * UNIT, map, lbar, 0, row0 + (int)rank * WR, kchunk);
+          } else {
+            mbar_arrive_expect_tx(&bars.wfull[stage], (uint32_t)UNIT);
+            tma_load_3d(w_base + stage * UNIT, map, &bars.wfull[stage], 0, row0, kchunk);
+          }
         }
         ++u;
-        if (++stage == FM_STAGES) { stage = 0; phase ^= 1u; }
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       };
-      for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++t) {
+      for (int mu = u0; mu < m_units; mu += ustep, ++t) {
+        const int mt = PAIR ? 2 * mu + (int)rank : mu;
         if (me == 0) {                                                   // the pass's y tile (all KD chunks)
           mbar_wait(&bars.aempty, (uint32_t)(t & 1) ^ 1u);
-          mbar_arrive_expect_tx(&bars.afull, (uint32_t)(KD * TG_A_BYTES));
-          for (int c = 0; c < KD; ++c) tma_load_3d(a_base + c * TG_A_BYTES, &map_a, &bars.afull, 0, mt * TG_BM, c);
+          if (PAIR) {
+            const uint32_t lbar = mapa_u32(smem_u32(&bars.afull), 0u);
+            mbar_arrive_expect_tx_cluster(lbar, (uint32_t)(KD * TG_A_BYTES));
+            for (int c = 0; c < KD; ++c) tma_load_3d_pair(a_base + c * TG_A_BYTES, &map_a, lbar, 0, mt * TG_BM, c);
+          } else {
+            mbar_arrive_expect_tx(&bars.afull, (uint32_t)(KD * TG_A_BYTES));
+            for (int c = 0; c < KD; ++c) tma_load_3d(a_base + c * TG_A_BYTES, &map_a, &bars.afull, 0, mt * TG_BM, c);
+          }
         }
         for (int j = 0; j <= NJ; ++j) {
           if (j < NJ)
-            for (int c = 0; c < KD; ++c) unit(&map_w1, j * FM_HC, c);                    // GEMM1_j: W1 rows of chunk j
+            for (int c = 0; c < KD; c += 2) unit(&map_w1, j * FM_HC, c);                 // GEMM1_j: W1 rows of chunk j, two k-chunks per unit
           if (j >= 1)
-            for (int c = 0; c < 2; ++c)
-              for (int nb = 0; nb < NB2; ++nb) unit(&map_w2, nb * 128, (j - 1) * 2 + c);  // GEMM2_{j-1}: W2[:, chunk j-1]
+            for (int nb = 0; nb < NB2; ++nb) unit(&map_w2, nb * 128, (j - 1) * 2);       // GEMM2_{j-1}: W2[n-block, chunk j-1]
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (warp-uniform)
-    const uint32_t idesc = umma_idesc_f16(128, 0);
+    // ------------------------------------------------------------ MMA issuer (warp-uniform; pair mode: the leader's only)
+    const uint32_t idesc = PAIR ? ((1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24)) : umma_idesc_f16(128, 0);
+    auto mma = [&](uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t acc) {
+      if (PAIR) umma_f16_pair_x4(d, umma_desc(a_addr, 16, 1024), umma_desc(b_addr, 16, 1024), idesc, acc);
+      else umma_f16_elect_x4(d, umma_desc(a_addr, 16, 1024), umma_desc(b_addr, 16, 1024), idesc, acc, 2u);
+    };
+    auto commit = [&](unsigned long long* b) {
+      if (PAIR) umma_commit_pair_elect(b);
+      else umma_commit_elect(b);
+    };
     int stage = 0, t = 0, g1 = 0, g2 = 0;                    // g1 / g2: GEMM1 / GEMM2 chunks issued so far (barrier phases)
     uint32_t phase = 0;
-    for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++t) {
+    if (!(PAIR && rank != 0))
+    for (int mu = u0; mu < m_units; mu += ustep, ++t) {
       mbar_wait(&bars.afull, (uint32_t)(t & 1));
       tc_fence_after();
       for (int j = 0; j <= NJ; ++j) {
         if (j < NJ) {
           mbar_wait(&bars.acc1empty, (uint32_t)(g1 & 1) ^ 1u);           // the previous chunk's accumulator has been read
           tc_fence_after();
-          for (int c = 0; c < KD; ++c) {
+          for (int c = 0; c < KD; c += 2) {
             mbar_wait(&bars.wfull[stage], phase);
             tc_fence_after();
-            umma_f16_elect_x4(acc1, umma_desc(a_base + c * TG_A_BYTES, 16, 1024), umma_desc(w_base + stage * FM_UNIT, 16, 1024), idesc,
-                              c ? 1u : 0u, 2u);
-            umma_commit_elect(&bars.wempty[stage]);
-            if (++stage == FM_STAGES) { stage = 0; phase ^= 1u; }
+            mma(acc1, a_base + c * TG_A_BYTES, w_base + stage * UNIT, c ? 1u : 0u);
+            mma(acc1, a_base + (c + 1) * TG_A_BYTES, w_base + stage * UNIT + HALF, 1u);
+            commit(&bars.wempty[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
-          umma_commit_elect(&bars.acc1full);
-          if (j == NJ - 1) umma_commit_elect(&bars.aempty);             // the y tile is free once the last GEMM1 has read it
+          commit(&bars.acc1full);
+          if (j == NJ - 1) commit(&bars.aempty);                         // the y tile is free once the last GEMM1 has read it
           ++g1;
         }
         if (j >= 1) {
@@ -639,17 +697,16 @@ mlp_fused_kernel(const FmArgs a, const __grid_constant__ CUtensorMap map_a, cons
           mbar_wait(&bars.hfull[b], (uint32_t)((g2 >> 1) & 1));
           if (j == 1) mbar_wait(&bars.acc2empty, (uint32_t)(t & 1) ^ 1u);   // the previous pass's result has been drained
           tc_fence_after();
-          for (int c = 0; c < 2; ++c)
-            for (int nb = 0; nb < NB2; ++nb) {
-              mbar_wait(&bars.wfull[stage], phase);
-              tc_fence_after();
-              umma_f16_elect_x4(acc2 + nb * 128, umma_desc(h_base + (b * 2 + c) * TG_A_BYTES, 16, 1024),
-                                umma_desc(w_base + stage * FM_UNIT, 16, 1024), idesc, (j > 1 || c) ? 1u : 0u, 2u);
-              umma_commit_elect(&bars.wempty[stage]);
-              if (++stage == FM_STAGES) { stage = 0; phase ^= 1u; }
-            }
-          umma_commit_elect(&bars.hempty[b]);
-          if (j == NJ) umma_commit_elect(&bars.acc2full);
+          for (int nb = 0; nb < NB2; ++nb) {
+            mbar_wait(&bars.wfull[stage], phase);
+            tc_fence_after();
+            mma(acc2 + nb * 128, h_base + (b * 2) * TG_A_BYTES, w_base + stage * UNIT, j > 1 ? 1u : 0u);
+            mma(acc2 + nb * 128, h_base + (b * 2 + 1) * TG_A_BYTES, w_base + stage * UNIT + HALF, 1u);
+            commit(&bars.wempty[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+          commit(&bars.hempty[b]);
+          if (j == NJ) commit(&bars.acc2full);
           ++g2;
         }
       }
@@ -665,7 +722,8 @@ mlp_fused_kernel(const FmArgs a, const __grid_constant__ CUtensorMap map_a, cons
     const uint32_t wr_base = scr + (uint32_t)lane * 64u;
     const int wr_sw = (lane >> 1) & 3, rd_ch = lane & 3;
     int e1 = 0, t = 0;
-    for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++t) {
+    for (int mu = u0; mu < m_units; mu += ustep, ++t) {
+      const int mt = PAIR ? 2 * mu + (int)rank : mu;
       const int row0 = mt * TG_BM + q * 32;
       for (int j = 0; j < NJ; ++j, ++e1) {
         const int b = e1 & 1;
@@ -679,8 +737,9 @@ mlp_fused_kernel(const FmArgs a, const __grid_constant__ CUtensorMap map_a, cons
         if (ng == 2) tmem_ld32(acc1 + lane_off + 96, v[1]);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars.acc1empty);          // GEMM1 of the next chunk may overwrite the accumulator
+        if (lane == 0) arrive_issuer(&bars.acc1empty);        // GEMM1 of the next chunk may overwrite the accumulator
         if (e1 >= 2) mbar_wait(&bars.hempty[b], (uint32_t)(((e1 >> 1) - 1) & 1));   // GEMM2 of chunk e1-2 has read this buffer
+        if (!(FM_DBG & 8))
         for (int gi = 0; gi < ng; ++gi) {
           const int hc0 = gi == 0 ? g0 * 32 : 96;             // first hidden column (within the chunk) of this group
           const float* bp = a.b1 + j * FM_HC + hc0;
@@ -688,6 +747,10 @@ mlp_fused_kernel(const FmArgs a, const __grid_constant__ CUtensorMap map_a, cons
 #pragma unroll
           for (int i = 0; i < 8; ++i) bb[i] = __ldg(reinterpret_cast<const float4*>(bp) + i);
           float* w = v[gi];
+          if (FM_DBG & 1) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { w[4 * i] += bb[i].x; w[4 * i + 1] += bb[i].y; w[4 * i + 2] += bb[i].z; w[4 * i + 3] += bb[i].w; }
+          } else
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             w[4 * i] = gelu_erf(w[4 * i] + bb[i].x); w[4 * i + 1] = gelu_erf(w[4 * i + 1] + bb[i].y);
@@ -704,12 +767,14 @@ mlp_fused_kernel(const FmArgs a, const __grid_constant__ CUtensorMap map_a, cons
         }
         fence_proxy_async();                                  // generic-proxy writes -> visible to the tensor core's reads
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars.hfull[b]);
+        if (lane == 0) arrive_issuer(&bars.hfull[b]);
       }
       // ---- final epilogue of the pass: acc2 [128 x D] + b2 -> x[row_idx[row]] (16-byte reductions, 8 rows x 64 B per instruction)
       mbar_wait(&bars.acc2full, (uint32_t)(t & 1));
       tc_fence_after();
       const int my_dst = (row0 + lane < cnt) ? __ldg(a.row_idx + row0 + lane) : 0;
+      // (x[dst] += ... as 16-byte load - add - store instead of reductions was measured: 60.0 against 53.2 us per pass - the
+      // residual rows come from HBM either way, and the reductions do not wait for them)
       for (int g = part; g * 32 < a.D; g += 3) {
         const int c0 = g * 32;
         float4 bb[8];
@@ -734,7 +799,7 @@ mlp_fused_kernel(const FmArgs a, const __grid_constant__ CUtensorMap map_a, cons
             const int rr = (lane >> 2) + 8 * k;
             const int dst = __shfl_sync(0xffffffffu, my_dst, rr);
             const uint4 pk = lds128(scr + (uint32_t)rr * 64u + (uint32_t)((rd_ch ^ ((rr >> 1) & 3)) << 4));
-            if (row0 + rr < cnt)
+            if (row0 + rr < cnt && !(FM_DBG & 4))
               asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.resid + (size_t)dst * a.ldres + c0 + sub * 16 + rd_ch * 4),
                            "f"(__uint_as_float(pk.x)), "f"(__uint_as_float(pk.y)), "f"(__uint_as_float(pk.z)), "f"(__uint_as_float(pk.w))
                            : "memory");
@@ -744,20 +809,22 @@ mlp_fused_kernel(const FmArgs a, const __grid_constant__ CUtensorMap map_a, cons
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars.acc2empty);
+      if (lane == 0) arrive_issuer(&bars.acc2empty);
       // the scratch sits in the H buffers: the next pass's first epilogues write them only after every warp is done here
       named_bar_sync(1, TG_EPI_WARPS * 32);
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();            // no CTA leaves while the other can still signal its barriers or read its tiles
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
-struct DevInfo { int sms; bool gemm_attr, attn_attr, mlp_attr; };
+struct DevInfo { int sms; bool gemm_attr, attn_attr, mlp_attr; int mlp_pairs; };
 DevInfo g_dev[MAX_DEVICES];
 
 // =====================================================================================================================
@@ -1347,21 +1414,51 @@ extern "C" int laud_adavit_mlp_fused(const void* y, int rows_max, int D, int Hd,
     LAUD_CUDA(cudaGetDeviceProperties(&prop, dev));
     di.sms = prop.multiProcessorCount;
   }
-  const size_t smem = (size_t)(D / 64) * TG_A_BYTES + 4 * TG_A_BYTES + FM_STAGES * FM_UNIT + 1024;
+  const size_t smem = (size_t)(D / 64) * TG_A_BYTES + 4 * TG_A_BYTES + FM_RING + 1024;
+  const size_t smem_max = 6 * TG_A_BYTES + 4 * TG_A_BYTES + FM_RING + 1024;
   if (!di.mlp_attr) {
-    LAUD_CUDA(cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * TG_A_BYTES + 4 * TG_A_BYTES + FM_STAGES * FM_UNIT + 1024));
+    LAUD_CUDA(cudaFuncSetAttribute(mlp_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    LAUD_CUDA(cudaFuncSetAttribute(mlp_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    // CTA pairs that can be resident at once (a GPC with an odd number of SMs leaves one unpaired)
+    cudaLaunchConfig_t q;
+    memset(&q, 0, sizeof(q));
+    q.gridDim = dim3((unsigned)(di.sms & ~1)); q.blockDim = dim3(TG_THREADS); q.dynamicSmemBytes = smem_max;
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension;
+    qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+    q.attrs = qa; q.numAttrs = 1;
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, mlp_fused_kernel<true>, &q) != cudaSuccess || nc <= 0) { cudaGetLastError(); nc = 0; }
+    di.mlp_pairs = nc < di.sms / 2 ? nc : di.sms / 2;
     di.mlp_attr = true;
   }
+  const int m_tiles_max = (rows_max + TG_BM - 1) / TG_BM;
+  // CTA pairs (see the kernel) whenever there is work for every pair; LAUD_FM_PAIR=0 keeps single CTAs
+  static const int fm_pair = getenv("LAUD_FM_PAIR") ? atoi(getenv("LAUD_FM_PAIR")) : 1;
+  const bool pair = fm_pair && di.mlp_pairs > 0 && m_tiles_max >= 2 * di.mlp_pairs;
   CUtensorMap ma, m1, m2;
-  if (!tg_map(&ma, y, D, rows_max, D, TG_BM, 1) || !tg_map(&m1, w1, D, Hd, D, 128, 1) || !tg_map(&m2, w2, Hd, D, Hd, 128, 1)) {
+  if (!tg_map(&ma, y, D, rows_max, D, TG_BM, 1) || !tg_map(&m1, w1, D, Hd, D, pair ? 64 : 128, 2) ||
+      !tg_map(&m2, w2, Hd, D, Hd, pair ? 64 : 128, 2)) {
     set_error("laud_adavit_mlp_fused: cuTensorMapEncodeTiled failed");
     return LAUD_E_CUDA;
   }
   FmArgs a;
   a.rows_max = rows_max; a.D = D; a.Hd = Hd; a.row_cnt = row_cnt; a.b1 = b1; a.b2 = b2; a.resid = resid; a.ldres = ldres; a.row_idx = row_idx;
-  const int m_tiles_max = (rows_max + TG_BM - 1) / TG_BM;
-  const int grid = m_tiles_max < di.sms ? m_tiles_max : di.sms;
-  mlp_fused_kernel<<<grid, TG_THREADS, smem, s>>>(a, ma, m1, m2);
+  static const int fm_dbg = getenv("LAUD_FM_DBG") ? atoi(getenv("LAUD_FM_DBG")) : 0;
+  a.dbg = fm_dbg;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(pair ? 2 * di.mlp_pairs : (m_tiles_max < di.sms ? m_tiles_max : di.sms)));
+  cfg.blockDim = dim3(TG_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pair ? 1 : 0;
+  if (pair) cudaLaunchKernelEx(&cfg, mlp_fused_kernel<true>, a, ma, m1, m2);
+  else cudaLaunchKernelEx(&cfg, mlp_fused_kernel<false>, a, ma, m1, m2);
   return check_launch("mlp_fused_kernel");
 }
 

@@ -107,7 +107,9 @@ def test_tok_gemm_head_tile_skip(cuda_lib, big):
     assert skipped > 0
 
 
-@pytest.mark.parametrize("rows,D,Hd", [(300, 128, 512), (1000, 384, 1536), (5000, 384, 1536), (129, 256, 1024)])
+# the last three are large enough for the CTA-pair form (>= 2 m-tiles per pair of SMs), one with an odd number of m-tiles
+@pytest.mark.parametrize("rows,D,Hd", [(300, 128, 512), (1000, 384, 1536), (5000, 384, 1536), (129, 256, 1024),
+                                       (19369, 384, 1536), (40000, 128, 512), (25000, 256, 1024)])
 def test_mlp_fused_vs_torch(cuda_lib, rows, D, Hd):
     """fc1 -> GELU -> fc2 -> residual add in one kernel (hidden activations on chip) against fp32 torch on the same fp16
     operands; rows past the device-side count and rows that are not destinations stay untouched."""
