@@ -548,6 +548,7 @@ struct FmArgs {
   const float* b1; const float* b2;
   float* resid; int ldres;
   const int* row_idx;
+  int stagger;                                               // cycles per hidden chunk and quarter pass of start delay (0 = off)
   int dbg;                                                   // LAUD_KPROF builds only (LAUD_FM_DBG; timing experiments, WRONG results):
                                                              // 1 no GELU arithmetic, 2 no weight loads, 4 no reductions, 8 no GELU epilogue body
 };
@@ -603,6 +604,17 @@ mlp_fused_kernel(const FmArgs a, const __grid_constant__ CUtensorMap map_a, cons
   // m-tile leaves the second CTA computing rows that are masked at the write-out)
   const int u0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, ustep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int m_units = PAIR ? (m_tiles + 1) >> 1 : m_tiles;
+  // Stagger: every pass ends in a burst of residual traffic that is HBM-bound when all CTAs reach it together (8.7 of 49 us
+  // per pass) and starts with a burst of y-tile loads.  When the passes do not divide evenly, the CTAs (pairs) with one pass
+  // fewer than the busiest have a whole pass of slack: they start 1/4, 2/4 or 3/4 of a pass late, so that their bursts fall
+  // into the others' MMA phases.  (Nobody is delayed when all have the same number of passes.)
+  if (a.stagger) {
+    const int mine = u0 < m_units ? (m_units - u0 + ustep - 1) / ustep : 0, most = (m_units + ustep - 1) / ustep;
+    if (mine > 0 && mine < most && (u0 & 3)) {
+      const long long wait = (long long)(u0 & 3) * NJ * a.stagger, t0 = clock64();
+      while (clock64() - t0 < wait) __nanosleep(256);
+    }
+  }
   tc_fence_before();
   __syncthreads();
   if (PAIR) cluster_sync_all();                                    // the peer's barriers exist before anything arrives on them
@@ -1446,6 +1458,8 @@ extern "C" int laud_adavit_mlp_fused(const void* y, int rows_max, int D, int Hd,
   a.rows_max = rows_max; a.D = D; a.Hd = Hd; a.row_cnt = row_cnt; a.b1 = b1; a.b2 = b2; a.resid = resid; a.ldres = ldres; a.row_idx = row_idx;
   static const int fm_dbg = getenv("LAUD_FM_DBG") ? atoi(getenv("LAUD_FM_DBG")) : 0;
   a.dbg = fm_dbg;
+  static const int fm_stagger = getenv("LAUD_FM_STAGGER") ? atoi(getenv("LAUD_FM_STAGGER")) : 1024;
+  a.stagger = fm_stagger;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)(pair ? 2 * di.mlp_pairs : (m_tiles_max < di.sms ? m_tiles_max : di.sms)));

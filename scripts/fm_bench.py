@@ -4,10 +4,10 @@ import ctypes, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from laudnet_b200 import _lib
 
-def run(D=384, Hd=1536, passes=3, iters=20):
+def run(D=384, Hd=1536, passes=3, iters=20, tiles=None):
     L = _lib.lib()
     dev = torch.device("cuda:0")
-    rows = 148 * 128 * passes
+    rows = 128 * tiles if tiles else 148 * 128 * passes
     g = torch.Generator(device="cpu").manual_seed(1)
     y = (torch.randn(rows, D, generator=g) * 0.5).half().to(dev)
     w1 = (torch.randn(Hd, D, generator=g) * 0.05).half().to(dev)
@@ -28,7 +28,7 @@ def run(D=384, Hd=1536, passes=3, iters=20):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     fl = 4.0 * rows * D * Hd
-    print(f"dbg={os.environ.get('LAUD_FM_DBG','0')} D={D} Hd={Hd} passes={passes}: {ms*1e3:.1f} us, {ms*1e3/passes:.1f} us/pass, {fl/ms/1e9:.0f} TFLOP/s")
+    print(f"dbg={os.environ.get('LAUD_FM_DBG','0')} D={D} Hd={Hd} passes={passes} rows={rows}: {ms*1e3:.1f} us, {ms*1e3/passes:.1f} us/pass, {fl/ms/1e9:.0f} TFLOP/s")
 
 if __name__ == "__main__":
-    run(passes=int(sys.argv[1]) if len(sys.argv) > 1 else 3)
+    run(passes=int(sys.argv[1]) if len(sys.argv) > 1 else 3, tiles=int(sys.argv[2]) if len(sys.argv) > 2 else None)
