@@ -110,11 +110,13 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
   return r;
 }
+// (remote arrivals in the default form - release at CTA scope, as the local ones: spelled .release.cluster every arrival costs a
+// MEMBAR.ALL.CTA + ERRBAR pair, 18 % of the fused MLP kernel's stall samples in profiles/r04f)
 __device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t bar_cluster_addr, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_cluster_addr), "r"(bytes) : "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_cluster_addr), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster_addr(uint32_t bar_cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 // TMA tile load whose completion is signalled on a barrier that may live in the PEER CTA (the leader's)
 __device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const void* map, uint32_t bar_cluster_addr, int c0, int c1, int c2) {
