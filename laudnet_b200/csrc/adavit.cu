@@ -1154,22 +1154,27 @@ adavit_attention_kernel(const __half* __restrict__ qkv, int ldq, const int* __re
     cp_async_16(smem_u32((which ? sV : sK) + r * AT_PITCH + ch * 8), qkv + (size_t)(r0 + rr) * ldq + h * 192 + 64 + which * 64 + ch * 8,
                 r < n ? 16u : 0u);
   }
-  asm volatile("cp.async.wait_all;" ::: "memory");
-  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int nk16 = n16 >> 4, nt8 = nk16 * 2;
   const float sc = 0.125f * 1.44269504088896341f;               // 1/sqrt(64) x log2(e)
   const uint32_t q_u = smem_u32(sQ), k_u = smem_u32(sK), v_u = smem_u32(sV);
-  for (int qt = warp; qt < nk16; qt += 4) {
+  // the warp's 16 query rows of tile qt -> its own staging tile (rows >= n zero-filled).  The copy of the NEXT tile is issued as
+  // soon as this tile's fragments sit in registers, so its latency runs under the tile's MMAs instead of in front of them (a
+  // warp has 2 - 4 tiles; waiting for each copy right after issuing it was a third of its time)
+  auto issue_q = [&](int qt) {
     const int q0 = qt * 16;
-    // the warp's 16 query rows -> its own staging tile (rows >= n zero-filled)
-    __syncwarp();
 #pragma unroll
     for (int i = lane; i < 16 * 8; i += 32) {
       const int r = i >> 3, ch = i & 7;
       const int rr = q0 + r < n ? q0 + r : 0;
       cp_async_16(q_u + (uint32_t)((r * AT_PITCH + ch * 8) * 2), qkv + (size_t)(r0 + rr) * ldq + h * 192 + ch * 8, q0 + r < n ? 16u : 0u);
     }
+  };
+  if (warp < nk16) issue_q(warp);
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+  for (int qt = warp; qt < nk16; qt += 4) {
+    const int q0 = qt * 16;
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
     uint32_t qa[4][4];
@@ -1177,6 +1182,8 @@ adavit_attention_kernel(const __half* __restrict__ qkv, int ldq, const int* __re
     for (int kk = 0; kk < 4; ++kk)
       ldmatrix_x4(q_u + (uint32_t)((((lane & 7) + ((lane >> 3) & 1) * 8) * AT_PITCH + kk * 16 + (lane >> 4) * 8) * 2), qa[kk][0],
                   qa[kk][1], qa[kk][2], qa[kk][3]);
+    __syncwarp();
+    if (qt + 4 < nk16) issue_q(qt + 4);
     float s[AT_NT][4];
 #pragma unroll
     for (int j = 0; j < AT_NT; ++j) {
