@@ -935,20 +935,46 @@ adavit_policy_kernel(const float* __restrict__ x, int L, int D, int H, float eps
         if (i < nv) { gw[i] *= tw[i]; c0 += tb[i] * tw[i]; }
       c0 = warp_sum(c0) + __ldg(ts_b);
     }
-    for (int l = 1 + warp; l < L; l += nwarps) {
-      float mean, rstd;
-      warp_ln_stats<V4, NVT>(x + ((size_t)b * L + l) * D, nv, D, eps, xv, mean, rstd);
-      float acc = 0.f;
+    // two tokens per iteration: both rows' loads are in flight together and the two reduction chains interleave (a warp that
+    // loads one row, waits, then computes spent a third of its samples on the first use of the load; the arithmetic of each
+    // token is unchanged)
+    for (int l = 1 + warp; l < L; l += 2 * nwarps) {
+      const int l2 = l + nwarps;
+      const bool two = l2 < L;
+      float xw[NVT];
+      ln_load<V4, NVT>(x + ((size_t)b * L + l) * D, nv, xv);
+      ln_load<V4, NVT>(x + ((size_t)b * L + (two ? l2 : l)) * D, nv, xw);
+      float s1 = 0.f, s2 = 0.f;
 #pragma unroll
       for (int i = 0; i < NVT; ++i)
-        if (i < nv) acc += (xv[i] - mean) * gw[i];
-      const float lg = warp_sum(acc) * rstd + c0;
-      const bool keep = lg >= 0.f;
-      if (lane == 0) {
-        tok_mask[(size_t)b * L + l] = keep ? 1 : 0;
-        if (tok_logits) tok_logits[(size_t)b * L + l] = lg;
+        if (i < nv) { s1 += xv[i]; s2 += xw[i]; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+      const float mean1 = s1 / (float)D, mean2 = s2 / (float)D;
+      float v1 = 0.f, v2 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < NVT; ++i)
+        if (i < nv) {
+          const float d1 = xv[i] - mean1, d2 = xw[i] - mean2;
+          v1 += d1 * d1; v2 += d2 * d2;
+          a1 += d1 * gw[i]; a2 += d2 * gw[i];
+        }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        v1 += __shfl_xor_sync(0xffffffffu, v1, o); v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o);
       }
-      kept += keep ? 1 : 0;
+      const float lg1 = a1 * rsqrtf(v1 / (float)D + eps) + c0, lg2 = a2 * rsqrtf(v2 / (float)D + eps) + c0;
+      const bool keep1 = lg1 >= 0.f, keep2 = two && lg2 >= 0.f;
+      if (lane == 0) {
+        tok_mask[(size_t)b * L + l] = keep1 ? 1 : 0;
+        if (tok_logits) tok_logits[(size_t)b * L + l] = lg1;
+        if (two) {
+          tok_mask[(size_t)b * L + l2] = keep2 ? 1 : 0;
+          if (tok_logits) tok_logits[(size_t)b * L + l2] = lg2;
+        }
+      }
+      kept += (keep1 ? 1 : 0) + (keep2 ? 1 : 0);
     }
   } else {
     for (int l = 1 + threadIdx.x; l < L; l += blockDim.x) {
