@@ -12,6 +12,7 @@
  *   laud_adavit_policy   decisions of the block from the fp32 residual stream x [B, L, D]
  *   laud_adavit_lists    per-sample row offsets of the two COMPACT token lists (attention / MLP sub-layer)
  *   laud_adavit_ln_gather LayerNorm of the kept tokens only, written as consecutive fp16 rows (+ their destinations)
+ *   laud_adavit_row_lists / laud_adavit_ln_rows  the same in two steps: row lists of both sub-layers, LayerNorm over a row list
  *   laud_tok_gemm        tcgen05 GEMM over the compact rows (device-side row count): QKV, proj, fc1 (+GELU), fc2;
  *                        proj / fc2 add their result straight into the residual stream at the rows' destinations
  *   laud_adavit_attention softmax(QK^T)V over the kept tokens of each (sample, kept head)
@@ -112,6 +113,17 @@ int laud_adavit_lists(const int32_t* tok_cnt, const uint8_t* layer_sel, int B, i
 int laud_adavit_ln_gather(const float* x, int B, int L, int D, float eps, const float* w, const float* bias,
                           const uint8_t* tok_mask, const int32_t* off, void* y, int32_t* row_idx, int32_t* row_sample,
                           void* stream);
+
+/* The same job in two steps with an evenly loaded LayerNorm (what AdaViT.forward uses; results bit-identical to
+ * laud_adavit_ln_gather).  laud_adavit_row_lists: for every sample, the destination rows b*L + l of its kept tokens
+ * (tok_mask, ascending l; NULL = all L) at rows_attn[off_attn[b] + rank] (+ samp_attn[...] = b, nullable) when the sample
+ * runs its attention sub-layer, and at rows_mlp[off_mlp[b] + rank] when it runs its MLP; either (off, rows) pair may be
+ * NULL.  laud_adavit_ln_rows: y[r, 0:D] = LayerNorm(x[row_idx[r], 0:D]) as fp16 for r < min(*row_cnt, rows_max)
+ * (row_cnt NULL = rows_max); x fp32 rows of D.  (L_select tokens :108, layernorm :171,177 of simulate_adavit.py) */
+int laud_adavit_row_lists(const uint8_t* tok_mask, int B, int L, const int32_t* off_attn, const int32_t* off_mlp,
+                          int32_t* rows_attn, int32_t* samp_attn, int32_t* rows_mlp, void* stream);
+int laud_adavit_ln_rows(const float* x, int D, float eps, const float* w, const float* bias, const int32_t* row_idx,
+                        const int32_t* row_cnt, int rows_max, void* y, void* stream);
 
 /* Attention over the kept tokens (simulate_adavit.py:110-121: matmul + softmax + matmul on L_select tokens x kept heads).
  *   qkv fp16 [rows, ldq] compact rows of the attention list, HEAD-MAJOR columns: head h holds q | k | v (64 each) at

@@ -117,6 +117,8 @@ SIGNATURES = {
                             _u8p, _i32p, _u8p, _u8p, _fp, _fp, _fp, _vp], _i),
     "laud_adavit_lists": ([_i32p, _u8p, _i, _i32p, _i32p, _vp], _i),
     "laud_adavit_ln_gather": ([_fp, _i, _i, _i, C.c_float, _fp, _fp, _u8p, _i32p, _vp, _i32p, _i32p, _vp], _i),
+    "laud_adavit_row_lists": ([_u8p, _i, _i, _i32p, _i32p, _i32p, _i32p, _i32p, _vp], _i),
+    "laud_adavit_ln_rows": ([_fp, _i, C.c_float, _fp, _fp, _i32p, _i32p, _i, _vp, _vp], _i),
     "laud_adavit_attention": ([_vp, _i, _i32p, _u8p, _i, _i, _i, _vp, _vp], _i),
 }
 

@@ -246,9 +246,11 @@ class AdaViT(nn.Module):
                 cnt.copy_(ft.sum(1).to(torch.int32))
             check(lib.laud_adavit_lists(ptr(cnt), ptr(layer), B, ptr(off_a), ptr(off_m), st), "laud_adavit_lists")
             # ---- attention sub-layer on the kept tokens of the samples that run it
+            check(lib.laud_adavit_row_lists(ptr(tok), B, L, ptr(off_a), ptr(off_m), ptr(ws["rows_a"]), ptr(ws["samp_a"]),
+                                            ptr(ws["rows_m"]), st), "laud_adavit_row_lists")
             mark("ln_gather")
-            check(lib.laud_adavit_ln_gather(ptr(x), B, L, D, LN_EPS, ptr(q["n1_w"]), ptr(q["n1_b"]), ptr(tok), ptr(off_a),
-                                            ptr(ws["y"]), ptr(ws["rows_a"]), ptr(ws["samp_a"]), st), "laud_adavit_ln_gather")
+            check(lib.laud_adavit_ln_rows(ptr(x), D, LN_EPS, ptr(q["n1_w"]), ptr(q["n1_b"]), ptr(ws["rows_a"]), ptr(off_a[B:]), rows,
+                                          ptr(ws["y"]), st), "laud_adavit_ln_rows")
             gate = head if self.head_tile_skip else None
             mark("gemm_qkv")
             self._gemm(ws["y"], q["qkv_w"], q["qkv_b"], rows, D, 3 * D, st, row_cnt=off_a[B:], out=ws["qkv"], bn=192,
@@ -260,8 +262,8 @@ class AdaViT(nn.Module):
             self._gemm(ws["o"], q["proj_w"], q["proj_b"], rows, D, D, st, row_cnt=off_a[B:], resid=x, ldres=D, row_idx=ws["rows_a"])
             # ---- MLP sub-layer
             mark("ln_gather")
-            check(lib.laud_adavit_ln_gather(ptr(x), B, L, D, LN_EPS, ptr(q["n2_w"]), ptr(q["n2_b"]), ptr(tok), ptr(off_m),
-                                            ptr(ws["y"]), ptr(ws["rows_m"]), None, st), "laud_adavit_ln_gather")
+            check(lib.laud_adavit_ln_rows(ptr(x), D, LN_EPS, ptr(q["n2_w"]), ptr(q["n2_b"]), ptr(ws["rows_m"]), ptr(off_m[B:]), rows,
+                                          ptr(ws["y"]), st), "laud_adavit_ln_rows")
             if self.fused_mlp:
                 mark("gemm_mlp_fused")
                 check(lib.laud_adavit_mlp_fused(ptr(ws["y"]), rows, D, Hd, ptr(off_m[B:]), ptr(q["fc1_w"]), ptr(q["fc1_b"]),

@@ -916,7 +916,9 @@ adavit_policy_kernel(const float* __restrict__ x, int L, int D, int H, float eps
                      uint8_t* head_sel, uint8_t* layer_sel, float* tok_logits, float* head_logits, float* layer_logits) {
   __shared__ int s_cnt;
   const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  const int nv = D / 32;
+  // (the 16-byte instantiations for D = 128 / 384 / 768 are exact: the slot count is a compile-time constant and the per-slot
+  // guards fold away - they were a third of the instructions of these kernels)
+  const int nv = (V4 && NVT != 32) ? NVT : D / 32;
   if (threadIdx.x == 0) s_cnt = 0;
   __syncthreads();
   float xv[NVT];
@@ -1089,7 +1091,9 @@ adavit_ln_gather_kernel(const float* __restrict__ x, int L, int D, float eps, co
     }
   }
   __syncthreads();
-  const int nv = D / 32;
+  // (the 16-byte instantiations for D = 128 / 384 / 768 are exact: the slot count is a compile-time constant and the per-slot
+  // guards fold away - they were a third of the instructions of these kernels)
+  const int nv = (V4 && NVT != 32) ? NVT : D / 32;
   float xv[NVT], gv[NVT], bv[NVT];
   ln_load<V4, NVT>(w, nv, gv);
   ln_load<V4, NVT>(bias, nv, bv);
@@ -1132,6 +1136,116 @@ adavit_ln_gather_kernel(const float* __restrict__ x, int L, int D, float eps, co
       if (row_sample) row_sample[o0 + rk] = b;
     }
     l = ln;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// row lists of both sub-layers (one warp per sample) + LayerNorm over a row list (flat: warps stride over the compact rows)
+// ---------------------------------------------------------------------------------------------------------------------
+// adavit_ln_gather_kernel is one CTA per sample: ~430 live CTAs of ~128 tokens on 148 SMs, each with its own rank scan and
+// ramp.  Splitting the job gives the LayerNorm a grid of its own choosing and evenly spread rows (0.86 -> 0.68 ms per step,
+// + 0.05 ms for the row lists).
+__global__ void __launch_bounds__(256)
+adavit_row_lists_kernel(const uint8_t* __restrict__ tok_mask, int B, int L, const int* __restrict__ off_a, const int* __restrict__ off_m,
+                        int* __restrict__ rows_a, int* __restrict__ samp_a, int* __restrict__ rows_m) {
+  const int lane = threadIdx.x & 31, b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const int oa = off_a ? off_a[b] : 0, na = off_a ? off_a[b + 1] - oa : 0;
+  const int om = off_m ? off_m[b] : 0, nm = off_m ? off_m[b + 1] - om : 0;
+  if (na <= 0 && nm <= 0) return;                              // the sample runs neither sub-layer
+  int run = 0;
+  for (int l0 = 0; l0 < L; l0 += 256) {                        // eight independent loads, then eight ballots
+    uint8_t k[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int l = l0 + u * 32 + lane;
+      k[u] = l < L ? (tok_mask ? tok_mask[(size_t)b * L + l] : (uint8_t)1) : (uint8_t)0;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int l = l0 + u * 32 + lane;
+      const unsigned m = __ballot_sync(0xffffffffu, k[u] != 0);
+      if (k[u]) {
+        const int rk = run + __popc(m & ((1u << lane) - 1u));
+        if (na > 0) {
+          rows_a[oa + rk] = b * L + l;
+          if (samp_a) samp_a[oa + rk] = b;
+        }
+        if (nm > 0) rows_m[om + rk] = b * L + l;
+      }
+      run += __popc(m);
+    }
+  }
+}
+
+template <bool V4, int NVT>
+__global__ void __launch_bounds__(256)
+adavit_ln_rows_kernel(const float* __restrict__ x, int D, float eps, const float* __restrict__ w, const float* __restrict__ bias,
+                      const int* __restrict__ row_idx, const int* __restrict__ row_cnt, int rows_max, __half* __restrict__ y) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nv = (V4 && NVT != 32) ? NVT : D / 32;
+  const int rows = row_cnt ? min(__ldg(row_cnt), rows_max) : rows_max;
+  const int nw = gridDim.x * (blockDim.x >> 5);
+  int r = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (r >= rows) return;
+  float gv[NVT], bv[NVT];
+  ln_load<V4, NVT>(w, nv, gv);
+  ln_load<V4, NVT>(bias, nv, bv);
+  // two rows per iteration (both rows' loads in flight, interleaved reductions); the NEXT pair's source rows are looked up
+  // one iteration ahead so that the index load is not in front of the row loads.  Per row the arithmetic is that of
+  // adavit_ln_gather_kernel (bit-identical results).  (Also requesting the next pair's ROWS one iteration ahead - weight and
+  // bias in shared memory to make room - was measured and is slower: 0.81 vs 0.68 ms per step; with the fp16 rows it writes,
+  // the kernel already moves 4.9 TB/s.)
+  int s1 = __ldg(row_idx + r), s2 = r + nw < rows ? __ldg(row_idx + r + nw) : s1;
+  for (; r < rows; r += 2 * nw) {
+    const int r2 = r + nw;
+    const bool two = r2 < rows;
+    float xv[NVT], xw[NVT];
+    ln_load<V4, NVT>(x + (size_t)s1 * D, nv, xv);
+    ln_load<V4, NVT>(x + (size_t)s2 * D, nv, xw);
+    const int rn = r + 2 * nw;
+    if (rn < rows) { s1 = __ldg(row_idx + rn); s2 = rn + nw < rows ? __ldg(row_idx + rn + nw) : s1; }
+    float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NVT; ++i)
+      if (i < nv) { a1 += xv[i]; a2 += xw[i]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o); }
+    const float mean1 = a1 / (float)D, mean2 = a2 / (float)D;
+    float v1 = 0.f, v2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NVT; ++i)
+      if (i < nv) {
+        const float d1 = xv[i] - mean1, d2 = xw[i] - mean2;
+        v1 += d1 * d1; v2 += d2 * d2;
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { v1 += __shfl_xor_sync(0xffffffffu, v1, o); v2 += __shfl_xor_sync(0xffffffffu, v2, o); }
+    const float rstd1 = rsqrtf(v1 / (float)D + eps), rstd2 = rsqrtf(v2 / (float)D + eps);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      if (half && !two) break;
+      const float* xs = half ? xw : xv;
+      const float mean = half ? mean2 : mean1, rstd = half ? rstd2 : rstd1;
+      __half* yr = y + (size_t)(half ? r2 : r) * D;
+      if (V4) {
+#pragma unroll
+        for (int i4 = 0; i4 < NVT / 4; ++i4)
+          if (4 * i4 < nv) {
+            float q[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) q[c] = (xs[4 * i4 + c] - mean) * rstd * gv[4 * i4 + c] + bv[4 * i4 + c];
+            uint2 pk;
+            pk.x = pack_h2(q[0], q[1]);
+            pk.y = pack_h2(q[2], q[3]);
+            *reinterpret_cast<uint2*>(yr + lane * 4 + 128 * i4) = pk;
+          }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NVT; ++i)
+          if (i < nv) yr[lane + 32 * i] = __float2half_rn((xs[i] - mean) * rstd * gv[i] + bv[i]);
+      }
+    }
   }
 }
 
@@ -1576,6 +1690,37 @@ extern "C" int laud_adavit_ln_gather(const float* x, int B, int L, int D, float 
   LAUD_LN_DISPATCH(LAUD_LNG_LAUNCH);
 #undef LAUD_LNG_LAUNCH
   return check_launch("adavit_ln_gather_kernel");
+}
+
+extern "C" int laud_adavit_row_lists(const uint8_t* tok_mask, int B, int L, const int32_t* off_attn, const int32_t* off_mlp,
+                                     int32_t* rows_attn, int32_t* samp_attn, int32_t* rows_mlp, void* stream) {
+  LAUD_REQUIRE(B > 0 && L > 0 && (off_attn || off_mlp), "laud_adavit_row_lists: bad arguments");
+  LAUD_REQUIRE((!off_attn || rows_attn) && (!off_mlp || rows_mlp), "laud_adavit_row_lists: an offset list without its row list");
+  adavit_row_lists_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(tok_mask, B, L, off_attn, off_mlp, rows_attn, samp_attn, rows_mlp);
+  return check_launch("adavit_row_lists_kernel");
+}
+
+extern "C" int laud_adavit_ln_rows(const float* x, int D, float eps, const float* w, const float* bias, const int32_t* row_idx,
+                                   const int32_t* row_cnt, int rows_max, void* y, void* stream) {
+  LAUD_REQUIRE(x && w && bias && row_idx && y && rows_max > 0, "laud_adavit_ln_rows: null argument");
+  LAUD_REQUIRE(D % 32 == 0 && D > 0 && D <= 1024, "laud_adavit_ln_rows: bad shape (D=%d)", D);
+  const bool v4 = D % 128 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0 && ((uintptr_t)bias & 15) == 0 &&
+                  ((uintptr_t)y & 7) == 0;
+  const int dev = current_device();
+  DevInfo& di = g_dev[dev];
+  if (!di.sms) {
+    cudaDeviceProp prop;
+    LAUD_CUDA(cudaGetDeviceProperties(&prop, dev));
+    di.sms = prop.multiProcessorCount;
+  }
+  // three CTAs of eight warps per SM (register-bound), fewer when there are not two rows for every warp
+  int grid = (rows_max + 15) / 16;
+  if (grid > di.sms * 3) grid = di.sms * 3;
+#define LAUD_LNR_LAUNCH(V4, NVT) \
+  adavit_ln_rows_kernel<V4, NVT><<<grid, 256, 0, (cudaStream_t)stream>>>(x, D, eps, w, bias, row_idx, row_cnt, rows_max, (__half*)y)
+  LAUD_LN_DISPATCH(LAUD_LNR_LAUNCH);
+#undef LAUD_LNR_LAUNCH
+  return check_launch("adavit_ln_rows_kernel");
 }
 
 extern "C" int laud_adavit_attention(const void* qkv, int ldq, const int32_t* off, const uint8_t* head_sel, int B, int H, int L,

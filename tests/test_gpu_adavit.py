@@ -209,6 +209,20 @@ def test_policy_lists_and_gather_vs_oracle(cuda_lib, cfg, batch):
         ln = F.layer_norm(t.x_in, (D,), sd[f"blocks.{i}.norm1.weight"], sd[f"blocks.{i}.norm1.bias"], A.LN_EPS).reshape(B * L, D)
         assert _rel(y[:n], ln[want_rows.long()]) <= 1e-3
         assert (y[n:] == 9.0).all()
+        # the two-step form AdaViT.forward uses: row lists of both sub-layers, then LayerNorm over a row list - identical output
+        rows_a = torch.full((B * L,), -1, dtype=torch.int32, device=DEV)
+        rows_m, samp_a = rows_a.clone(), rows_a.clone()
+        _lib.check(lib.laud_adavit_row_lists(ws["tok"][i].data_ptr(), B, L, ws["off_a"][i].data_ptr(), ws["off_m"][i].data_ptr(),
+                                             rows_a.data_ptr(), samp_a.data_ptr(), rows_m.data_ptr(), st))
+        y2 = torch.full((B * L, D), 9.0, dtype=torch.float16, device=DEV)
+        _lib.check(lib.laud_adavit_ln_rows(xin.data_ptr(), D, A.LN_EPS, q["n1_w"].data_ptr(), q["n1_b"].data_ptr(), rows_a.data_ptr(),
+                                           ws["off_a"][i][B:].data_ptr(), B * L, y2.data_ptr(), st))
+        torch.cuda.synchronize()
+        assert torch.equal(rows_a, rows) and torch.equal(samp_a, samp)
+        assert torch.equal(y2, y)
+        want_m = torch.tensor([b * L + l for b in range(B) if layer[b, 1] for l in range(L) if tok[b, l]], dtype=torch.int32)
+        assert int(ws["off_m"][i][B]) == want_m.numel()
+        assert torch.equal(rows_m[:want_m.numel()].cpu(), want_m) and (rows_m[want_m.numel():] == -1).all()
 
 
 @pytest.mark.parametrize("H,L", [(2, 17), (6, 197), (3, 208)])
