@@ -1352,11 +1352,12 @@ adavit_attention_kernel(const __half* __restrict__ qkv, int ldq, const int* __re
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
     float sum0 = 0.f, sum1 = 0.f;
+    mx0 *= -sc; mx1 *= -sc;                                     // 2^((s - max) * sc) as one FMA per element
 #pragma unroll
     for (int j = 0; j < AT_NT; ++j)
       if (j < nt8) {
-        s[j][0] = fast_ex2((s[j][0] - mx0) * sc); s[j][1] = fast_ex2((s[j][1] - mx0) * sc);
-        s[j][2] = fast_ex2((s[j][2] - mx1) * sc); s[j][3] = fast_ex2((s[j][3] - mx1) * sc);
+        s[j][0] = fast_ex2(fmaf(s[j][0], sc, mx0)); s[j][1] = fast_ex2(fmaf(s[j][1], sc, mx0));
+        s[j][2] = fast_ex2(fmaf(s[j][2], sc, mx1)); s[j][3] = fast_ex2(fmaf(s[j][3], sc, mx1));
         sum0 += s[j][0] + s[j][1];
         sum1 += s[j][2] + s[j][3];
       }
