@@ -1,5 +1,11 @@
-"""Microbenchmark of the fused MLP kernel (laud_adavit_mlp_fused) at whole passes: rows = 148 x 128 x passes.
-LAUD_FM_DBG=1 drops the GELU arithmetic, =2 the weight loads (diagnostic builds of the same kernel)."""
+"""Microbenchmark of the fused MLP kernel (laud_adavit_mlp_fused): rows = 148 x 128 x passes, or 128 x tiles.
+
+    python scripts/fm_bench.py [passes [tiles]]
+
+Switches read by the library: LAUD_FM_PAIR=0 (single CTAs instead of CTA pairs), LAUD_FM_STAGGER=<cycles per chunk> (0 = off).
+Timing experiments (WRONG results) need the diagnostic build - `python -m laudnet_b200.build --prof`, then
+LAUD_LIB=laudnet_b200/lib/liblaud_b200_prof.so LAUD_FM_DBG=<bits>: 1 no GELU arithmetic, 2 no weight loads, 4 no residual
+reductions, 8 no GELU epilogue body (profiles/README.md has the table these produced)."""
 import ctypes, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from laudnet_b200 import _lib
