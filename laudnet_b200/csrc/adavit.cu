@@ -1295,7 +1295,7 @@ adavit_attention_kernel(const __half* __restrict__ qkv, int ldq, const int* __re
                 r < n ? 16u : 0u);
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int nk16 = n16 >> 4, nt8 = nk16 * 2;
+  const int nk16 = n16 >> 4;
   const float sc = 0.125f * 1.44269504088896341f;               // 1/sqrt(64) x log2(e)
   const uint32_t q_u = smem_u32(sQ), k_u = smem_u32(sK), v_u = smem_u32(sV);
   // the warp's 16 query rows of tile qt -> its own staging tile (rows >= n zero-filled).  The copy of the NEXT tile is issued as
@@ -1324,42 +1324,56 @@ adavit_attention_kernel(const __half* __restrict__ qkv, int ldq, const int* __re
                   qa[kk][1], qa[kk][2], qa[kk][3]);
     __syncwarp();
     if (qt + 4 < nk16) issue_q(qt + 4);
+    // scores: sixteen keys (two n8 tiles) per guarded step - two independent accumulator chains between the branches (one
+    // tile per branch left every HMMA waiting for the previous one on the same accumulator: `wait` was the top stall reason)
     float s[AT_NT][4];
 #pragma unroll
-    for (int j = 0; j < AT_NT; ++j) {
-      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-      if (j < nt8) {
+    for (int kk = 0; kk < AT_NT / 2; ++kk) {
+      float* sa = s[2 * kk];
+      float* sb = s[2 * kk + 1];
+      sa[0] = sa[1] = sa[2] = sa[3] = 0.f;
+      sb[0] = sb[1] = sb[2] = sb[3] = 0.f;
+      if (kk < nk16) {
 #pragma unroll
         for (int kp = 0; kp < 2; ++kp) {                        // two k16 steps per ldmatrix.x4
-          uint32_t b0, b1, b2, b3;
-          ldmatrix_x4(k_u + (uint32_t)(((j * 8 + (lane & 7)) * AT_PITCH + kp * 32 + (lane >> 3) * 8) * 2), b0, b1, b2, b3);
-          mma16816(s[j], qa[2 * kp][0], qa[2 * kp][1], qa[2 * kp][2], qa[2 * kp][3], b0, b1);
-          mma16816(s[j], qa[2 * kp + 1][0], qa[2 * kp + 1][1], qa[2 * kp + 1][2], qa[2 * kp + 1][3], b2, b3);
+          uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
+          ldmatrix_x4(k_u + (uint32_t)(((kk * 16 + (lane & 7)) * AT_PITCH + kp * 32 + (lane >> 3) * 8) * 2), a0, a1, a2, a3);
+          ldmatrix_x4(k_u + (uint32_t)(((kk * 16 + 8 + (lane & 7)) * AT_PITCH + kp * 32 + (lane >> 3) * 8) * 2), b0, b1, b2, b3);
+          mma16816(sa, qa[2 * kp][0], qa[2 * kp][1], qa[2 * kp][2], qa[2 * kp][3], a0, a1);
+          mma16816(sb, qa[2 * kp][0], qa[2 * kp][1], qa[2 * kp][2], qa[2 * kp][3], b0, b1);
+          mma16816(sa, qa[2 * kp + 1][0], qa[2 * kp + 1][1], qa[2 * kp + 1][2], qa[2 * kp + 1][3], a2, a3);
+          mma16816(sb, qa[2 * kp + 1][0], qa[2 * kp + 1][1], qa[2 * kp + 1][2], qa[2 * kp + 1][3], b2, b3);
         }
       }
     }
     // softmax over the kept keys (columns >= n are padding)
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < AT_NT; ++j)
-      if (j < nt8) {
-        const int c = j * 8 + 2 * t;
-        if (c >= n) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
-        if (c + 1 >= n) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
-        mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
-        mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+    for (int kk = 0; kk < AT_NT / 2; ++kk)
+      if (kk < nk16) {
+#pragma unroll
+        for (int j = 2 * kk; j < 2 * kk + 2; ++j) {
+          const int c = j * 8 + 2 * t;
+          if (c >= n) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
+          if (c + 1 >= n) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+          mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+          mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+        }
       }
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
     float sum0 = 0.f, sum1 = 0.f;
     mx0 *= -sc; mx1 *= -sc;                                     // 2^((s - max) * sc) as one FMA per element
 #pragma unroll
-    for (int j = 0; j < AT_NT; ++j)
-      if (j < nt8) {
-        s[j][0] = fast_ex2(fmaf(s[j][0], sc, mx0)); s[j][1] = fast_ex2(fmaf(s[j][1], sc, mx0));
-        s[j][2] = fast_ex2(fmaf(s[j][2], sc, mx1)); s[j][3] = fast_ex2(fmaf(s[j][3], sc, mx1));
-        sum0 += s[j][0] + s[j][1];
-        sum1 += s[j][2] + s[j][3];
+    for (int kk = 0; kk < AT_NT / 2; ++kk)
+      if (kk < nk16) {
+#pragma unroll
+        for (int j = 2 * kk; j < 2 * kk + 2; ++j) {
+          s[j][0] = fast_ex2(fmaf(s[j][0], sc, mx0)); s[j][1] = fast_ex2(fmaf(s[j][1], sc, mx0));
+          s[j][2] = fast_ex2(fmaf(s[j][2], sc, mx1)); s[j][3] = fast_ex2(fmaf(s[j][3], sc, mx1));
+          sum0 += s[j][0] + s[j][1];
+          sum1 += s[j][2] + s[j][3];
+        }
       }
     sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
     sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
