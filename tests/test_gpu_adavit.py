@@ -225,6 +225,22 @@ def test_policy_lists_and_gather_vs_oracle(cuda_lib, cfg, batch):
         assert torch.equal(rows_m[:want_m.numel()].cpu(), want_m) and (rows_m[want_m.numel():] == -1).all()
 
 
+@pytest.mark.parametrize("B", [1, 33, 1024, 2500])
+def test_lists_offsets_any_batch(cuda_lib, B):
+    """ordered exclusive scans of the per-sample row counts, also past one block of 1024 samples"""
+    g = torch.Generator().manual_seed(B)
+    cnt = torch.randint(1, 198, (B,), generator=g).to(torch.int32)
+    layer = (torch.rand(B, 2, generator=g) < 0.7).to(torch.uint8)
+    off_a = torch.full((B + 1,), -1, dtype=torch.int32, device=DEV)
+    off_m = off_a.clone()
+    cnt_d, layer_d = cnt.to(DEV), layer.to(DEV)
+    _lib.check(cuda_lib.laud_adavit_lists(cnt_d.data_ptr(), layer_d.data_ptr(), B, off_a.data_ptr(), off_m.data_ptr(), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    for col, off in ((0, off_a), (1, off_m)):
+        want = torch.cat([torch.zeros(1, dtype=torch.long), torch.cumsum(cnt.long() * layer[:, col].long(), 0)])
+        assert torch.equal(off.cpu().long(), want)
+
+
 @pytest.mark.parametrize("H,L", [(2, 17), (6, 197), (3, 208)])
 def test_attention_over_kept_tokens_vs_torch(cuda_lib, H, L):
     g = torch.Generator().manual_seed(H * 100 + L)
