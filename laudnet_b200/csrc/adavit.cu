@@ -1111,8 +1111,8 @@ adavit_ln_gather_kernel(const float* __restrict__ x, int L, int D, float eps, co
   ln_load<V4, NVT>(w, nv, gv);
   ln_load<V4, NVT>(bias, nv, bv);
   // this warp's kept tokens l = warp, warp + nwarps, ...; the next kept token's row is requested before the current one is
-  // normalised: one warp per token otherwise exposes a full HBM round trip per token (1.05 -> 0.88 ms per step; the same
-  // change made the policy kernel slower, 0.58 -> 0.77 ms, and was not kept there)
+  // normalised: one warp per token otherwise exposes a full HBM round trip per token (1.05 -> 0.88 ms per step; in the
+  // policy kernel a register copy of the next row was slower, two rows per iteration is what helped there)
   float xn[NVT];
   int l = warp;
   while (l < L && s_rank[l] < 0) l += nwarps;
