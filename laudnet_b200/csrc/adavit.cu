@@ -1208,7 +1208,8 @@ adavit_ln_rows_kernel(const float* __restrict__ x, int D, float eps, const float
   // one iteration ahead so that the index load is not in front of the row loads.  Per row the arithmetic is that of
   // adavit_ln_gather_kernel (bit-identical results).  (Also requesting the next pair's ROWS one iteration ahead - weight and
   // bias in shared memory to make room - was measured and is slower: 0.81 vs 0.68 ms per step; with the fp16 rows it writes,
-  // the kernel already moves 4.9 TB/s.)
+  // the kernel already moves 4.9 TB/s.  Weight / bias in shared memory for a fourth
+  // CTA per SM at 64 registers: 0.70 vs 0.68 ms - no gain either.)
   int s1 = __ldg(row_idx + r), s2 = r + nw < rows ? __ldg(row_idx + r + nw) : s1;
   for (; r < rows; r += 2 * nw) {
     const int r2 = r + nw;
